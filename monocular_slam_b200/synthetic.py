@@ -1,0 +1,91 @@
+"""Deterministic synthetic inputs for tests and bench.py (numpy only; no OpenCV needed on the GPU box).
+
+The reference ships no frames and no descriptor fixtures, and there is no
+network, so every workload in BASELINE.json is synthesised here from fixed seeds:
+
+* ``frame``      -- corner-dense grayscale frame: smoothed noise + random flat rectangles
+                    (numpy restatement of the SURVEY.md Appendix B generator).
+* ``sequence``   -- consecutive frames of a monocular sequence: one large texture viewed through a
+                    window that translates a few pixels per frame, so frame i matches frame i-1.
+* ``descriptors``/``planted_queries`` -- uniform random 256-bit descriptors, and queries that are
+                    near-duplicates of train rows (config 4 of BASELINE.json).
+"""
+import numpy as np
+
+
+def _gauss_blur(img, sigma):
+    r = int(3 * sigma + 0.5)
+    x = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (x / sigma) ** 2)
+    k /= k.sum()
+    f = img.astype(np.float32)
+    p = np.pad(f, ((0, 0), (r, r)), mode="reflect")
+    acc = np.zeros_like(f)
+    for i, kv in enumerate(k):
+        acc += np.float32(kv) * p[:, i:i + f.shape[1]]
+    p = np.pad(acc, ((r, r), (0, 0)), mode="reflect")
+    out = np.zeros_like(f)
+    for i, kv in enumerate(k):
+        out += np.float32(kv) * p[i:i + f.shape[0], :]
+    return out
+
+
+def frame(seed, w, h, nrect=300, sigma=1.5):
+    """One corner-dense frame (h x w uint8)."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    f = _gauss_blur(img, sigma)
+    lo, hi = float(f.min()), float(f.max())
+    img = np.clip(np.rint((f - lo) * (255.0 / max(hi - lo, 1e-6))), 0, 255).astype(np.uint8)
+    for _ in range(nrect):
+        x = int(rng.integers(0, max(w - 40, 1)))
+        y = int(rng.integers(0, max(h - 40, 1)))
+        rw, rh = (int(v) for v in rng.integers(5, 40, 2))
+        img[y:y + rh, x:x + rw] = int(rng.integers(0, 256))
+    return img
+
+
+def textured_frame(seed, w, h):
+    """A less adversarial frame: low-frequency shading + mid-frequency texture + a few hundred rectangles."""
+    rng = np.random.default_rng(seed)
+    coarse = _gauss_blur(rng.integers(0, 256, (h, w), dtype=np.uint8), 6.0)
+    fine = _gauss_blur(rng.integers(0, 256, (h, w), dtype=np.uint8), 1.0)
+    f = 0.6 * (coarse - coarse.mean()) * 6.0 + 0.4 * (fine - fine.mean()) * 1.5 + 128.0
+    img = np.clip(np.rint(f), 0, 255).astype(np.uint8)
+    for _ in range(200):
+        x = int(rng.integers(0, max(w - 60, 1)))
+        y = int(rng.integers(0, max(h - 60, 1)))
+        rw, rh = (int(v) for v in rng.integers(8, 60, 2))
+        img[y:y + rh, x:x + rw] = int(rng.integers(0, 256))
+    return img
+
+
+def sequence(nframes, w, h, seed=0, step=(3, 5), generator=frame):
+    """``nframes`` consecutive h x w views of one texture, translating ``step`` = (dy, dx) pixels per frame."""
+    dy, dx = step
+    big = generator(seed, w + abs(dx) * nframes, h + abs(dy) * nframes)
+    out = np.empty((nframes, h, w), np.uint8)
+    for i in range(nframes):
+        out[i] = big[i * abs(dy):i * abs(dy) + h, i * abs(dx):i * abs(dx) + w]
+    return out
+
+
+def descriptors(seed, n):
+    """n uniform-random 256-bit descriptors (n x 32 uint8)."""
+    return np.random.default_rng(seed).integers(0, 256, (n, 32), dtype=np.uint8)
+
+
+def planted_queries(seed, train, nq, frac=0.5, max_flips=20):
+    """Queries of which ``frac`` are copies of random train rows with <= max_flips bits flipped (so the ratio test passes)."""
+    rng = np.random.default_rng(seed)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    nplant = int(nq * frac)
+    rows = rng.choice(nq, nplant, replace=False)
+    src = rng.integers(0, len(train), nplant)
+    q[rows] = train[src]
+    for r in rows:
+        nflip = int(rng.integers(0, max_flips + 1))
+        bits = rng.choice(256, nflip, replace=False)
+        for b in bits:
+            q[r, b >> 3] ^= np.uint8(1 << (b & 7))
+    return q

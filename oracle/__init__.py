@@ -1,0 +1,251 @@
+"""ctypes wrapper around oracle/liborb_oracle.so (CPU restatement of the reference's ORB + BF-Hamming path).
+
+TEST INFRASTRUCTURE ONLY -- see the header of oracle/orb_oracle.c.  The product package
+(monocular_slam_b200) never imports this module; tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs do, as the checker or reported baseline.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborb_oracle.so")
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")]
+)
+assert KEYPOINT_DTYPE.itemsize == 28
+
+HARRIS_SCORE, FAST_SCORE = 0, 1
+
+
+class Params(C.Structure):
+    """cv::ORB constructor arguments; defaults are the reference's (src/FeatureExtractor.h:23-24)."""
+
+    _fields_ = [
+        ("nfeatures", C.c_int32),
+        ("scale_factor", C.c_float),
+        ("nlevels", C.c_int32),
+        ("edge_threshold", C.c_int32),
+        ("first_level", C.c_int32),
+        ("wta_k", C.c_int32),
+        ("score_type", C.c_int32),
+        ("patch_size", C.c_int32),
+        ("fast_threshold", C.c_int32),
+    ]
+
+    def __init__(self, nfeatures=500, scale_factor=1.2, nlevels=8, edge_threshold=31, first_level=0, wta_k=2,
+                 score_type=HARRIS_SCORE, patch_size=31, fast_threshold=20):
+        super().__init__(nfeatures, scale_factor, nlevels, edge_threshold, first_level, wta_k, score_type, patch_size,
+                         fast_threshold)
+
+
+def build(force=False):
+    """Compile liborb_oracle.so with the committed Makefile (gcc only)."""
+    src = os.path.join(_HERE, "orb_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        u8p, i32p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_float)
+        PP = C.POINTER(Params)
+        L.orc_level_scale.restype = C.c_float
+        L.orc_level_scale.argtypes = [PP, C.c_int]
+        L.orc_level_size.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_level_quotas.argtypes = [PP, C.POINTER(C.c_int)]
+        L.orc_resize_linear_exact.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+        L.orc_fast_score_map.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_fast_nms.argtypes = [u8p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int]
+        L.orc_harris.restype = C.c_float
+        L.orc_harris.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_ic_angle.restype = C.c_float
+        L.orc_ic_angle.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
+        L.orc_gauss_kernel7.argtypes = [f32p]
+        L.orc_blur7.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_describe.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_float, u8p]
+        L.orc_pyramid_level.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, u8p]
+        L.orc_detect.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int]
+        L.orc_compute.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, u8p]
+        L.orc_level_fast.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, i32p, i32p, i32p, C.c_int]
+        L.orc_knn2.argtypes = [u8p, C.c_int64, u8p, C.c_int64, i32p, i32p]
+        L.orc_ratio_test.restype = C.c_int64
+        L.orc_ratio_test.argtypes = [i32p, i32p, C.c_int64, C.c_float, i32p, i32p, i32p]
+        _lib = L
+    return _lib
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _i32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _gray(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 2
+    return img
+
+
+# ---------------------------------------------------------------- geometry
+def level_scales(params):
+    return np.array([lib().orc_level_scale(C.byref(params), l) for l in range(params.nlevels)], dtype=np.float32)
+
+
+def level_sizes(params, w, h):
+    out = []
+    for l in range(params.nlevels):
+        lw, lh = C.c_int(), C.c_int()
+        lib().orc_level_size(C.byref(params), w, h, l, C.byref(lw), C.byref(lh))
+        out.append((lw.value, lh.value))
+    return out
+
+
+def level_quotas(params):
+    q = (C.c_int * params.nlevels)()
+    lib().orc_level_quotas(C.byref(params), q)
+    return list(q)
+
+
+# ---------------------------------------------------------------- stages
+def resize_linear_exact(src, dw, dh):
+    src = _gray(src)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_exact(_u8(src), src.shape[1], src.shape[0], src.shape[1], _u8(dst), dw, dh, dw)
+    return dst
+
+
+def pyramid_level(params, img, level):
+    img = _gray(img)
+    h, w = img.shape
+    lw, lh = level_sizes(params, w, h)[level]
+    out = np.empty((lh, lw), np.uint8)
+    rc = lib().orc_pyramid_level(C.byref(params), _u8(img), w, h, w, level, _u8(out))
+    assert rc == 0
+    return out
+
+
+def fast_score_map(img, threshold=20):
+    img = _gray(img)
+    h, w = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orc_fast_score_map(_u8(img), w, h, w, threshold, _u8(out))
+    return out
+
+
+def fast_nms(score, border=31):
+    score = _gray(score)
+    h, w = score.shape
+    cap = (w // 2 + 1) * (h // 2 + 1)
+    xs, ys, sc = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().orc_fast_nms(_u8(score), w, h, border, _i32(xs), _i32(ys), _i32(sc), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def harris(img, x, y):
+    img = _gray(img)
+    return np.float32(lib().orc_harris(_u8(img), img.shape[1], int(x), int(y)))
+
+
+def fast_atan2(y, x):
+    return np.float32(lib().orc_fast_atan2(float(np.float32(y)), float(np.float32(x))))
+
+
+def ic_angle(img, x, y):
+    img = _gray(img)
+    return np.float32(lib().orc_ic_angle(_u8(img), img.shape[1], int(x), int(y)))
+
+
+def gauss_kernel7():
+    k = np.empty(7, np.float32)
+    lib().orc_gauss_kernel7(k.ctypes.data_as(C.POINTER(C.c_float)))
+    return k
+
+
+def blur7(img):
+    img = _gray(img)
+    out = np.empty_like(img)
+    lib().orc_blur7(_u8(img), img.shape[1], img.shape[0], img.shape[1], _u8(out))
+    return out
+
+
+# ---------------------------------------------------------------- whole path
+def detect(img, params, cap=None):
+    """ORB detect as the reference calls it (src/FeatureExtractor.cpp:17); canonical order (octave, y, x)."""
+    img = _gray(img)
+    h, w = img.shape
+    cap = cap or max(4 * params.nfeatures + 4096, 8192)
+    kps = np.zeros(cap, KEYPOINT_DTYPE)
+    n = lib().orc_detect(C.byref(params), _u8(img), w, h, w, kps.ctypes.data, cap)
+    if n < 0:
+        raise ValueError("oracle: unsupported ORB parameters (%d)" % n)
+    if n > cap:
+        return detect(img, params, cap=n)
+    return kps[:n].copy()
+
+
+def compute(img, kps, params):
+    """ORB compute (src/FeatureExtractor.cpp:19): returns (filtered/regrouped keypoints, N x 32 descriptors)."""
+    img = _gray(img)
+    h, w = img.shape
+    kps = np.array(kps, dtype=KEYPOINT_DTYPE, copy=True)
+    desc = np.zeros((len(kps), 32), np.uint8)
+    m = lib().orc_compute(C.byref(params), _u8(img), w, h, w, kps.ctypes.data, len(kps), _u8(desc))
+    if m < 0:
+        raise ValueError("oracle: bad keypoints / parameters (%d)" % m)
+    return kps[:m].copy(), desc[:m].copy()
+
+
+def detect_and_compute(img, params):
+    return compute(img, detect(img, params), params)
+
+
+def level_fast(img, params, level):
+    img = _gray(img)
+    h, w = img.shape
+    lw, lh = level_sizes(params, w, h)[level]
+    cap = (lw // 2 + 1) * (lh // 2 + 1)
+    xs, ys, sc = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().orc_level_fast(C.byref(params), _u8(img), w, h, w, level, _i32(xs), _i32(ys), _i32(sc), cap)
+    assert n >= 0
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def knn2(q, t):
+    """BFMatcher(NORM_HAMMING,false).knnMatch(q,t,2) (src/CameraPoseEstimator.cpp:202-204): (idx, dist) each nq x 2, -1 = absent."""
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.empty((len(q), 2), np.int32)
+    dist = np.empty((len(q), 2), np.int32)
+    lib().orc_knn2(_u8(q), len(q), _u8(t), len(t), _i32(idx), _i32(dist))
+    return idx, dist
+
+
+def ratio_test(idx, dist, ratio):
+    """Lowe ratio exactly as src/CameraPoseEstimator.cpp:208-212: returns (query_idx, train_idx, distance) arrays."""
+    idx = np.ascontiguousarray(idx, np.int32)
+    dist = np.ascontiguousarray(dist, np.int32)
+    nq = len(idx)
+    gq, gt, gd = (np.empty(nq, np.int32) for _ in range(3))
+    n = lib().orc_ratio_test(_i32(idx), _i32(dist), nq, float(ratio), _i32(gq), _i32(gt), _i32(gd))
+    return gq[:n].copy(), gt[:n].copy(), gd[:n].copy()
+
+
+def match_features(d1, d2, ratio=0.8):
+    """matchFeatures(descriptors1, descriptors2, matches, ratio) of src/CameraPoseEstimator.cpp:200-213."""
+    idx, dist = knn2(d1, d2)
+    return ratio_test(idx, dist, ratio)

@@ -1,0 +1,154 @@
+/*
+ * orbx.h -- C ABI of liborbx.so: a B200 (sm_100a) ORB front-end for the Monocular_SLAM pipeline.
+ *
+ * It replaces, and only replaces, the reference's per-frame feature extraction and descriptor matching:
+ *
+ *   reference call site                                                    replaced by
+ *   ---------------------------------------------------------------------  ---------------------------------
+ *   detector.detect(frameBuffer, keypoints)    src/FeatureExtractor.cpp:17  orbx_detect
+ *   extractor.compute(frameBuffer, kps, desc)  src/FeatureExtractor.cpp:19  orbx_compute
+ *   (the two back to back, FeatureExtractor::process :13-31)                orbx_detect_and_compute / orbx_extract_batch
+ *   BFMatcher(NORM_HAMMING,false).knnMatch(d1,d2,raw,2)
+ *                                      src/CameraPoseEstimator.cpp:202-204  hamx_knn2
+ *   matchFeatures(d1,d2,matches,ratio) src/CameraPoseEstimator.cpp:200-213  hamx_match_ratio
+ *   the distance itself   ThirdParty/DBoW2/DBoW2/FORB.cpp:81-101            (256-bit XOR + popcount inside hamx_*)
+ *
+ * The ORB objects in the reference are default-constructed cv::ORB (src/FeatureExtractor.h:23-24); their
+ * constructor arguments are the fields of orbx_params with the same defaults.  Results follow OpenCV's ORB /
+ * BFMatcher bit for bit (see DESIGN.md "Parity"); keypoints are returned in canonical order (octave, y, x) and
+ * descriptor row i always belongs to keypoint i, which is the index contract the reference relies on
+ * (src/CameraPoseEstimator.cpp:434-436,558-559).
+ *
+ * Conventions: plain C, no exceptions or STL across the boundary; every function returns 0 on success or a
+ * negative orbx_status; orbx_last_error() gives the message for the calling thread.  Pointers are HOST pointers
+ * unless the function name ends in _dev.  A handle is bound to one device and one stream and is not thread-safe
+ * (the reference runs its nodes on a single thread, src/main.cpp:49-51).  There is no CPU fallback: without a
+ * CUDA device every call fails with ORBX_E_CUDA.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ORBX_API __attribute__((visibility("default")))
+#else
+#define ORBX_API
+#endif
+
+typedef enum {
+    ORBX_OK = 0,
+    ORBX_E_INVALID = -1,   /* bad argument (null pointer, size out of range, unsupported parameter) */
+    ORBX_E_CUDA = -2,      /* CUDA runtime error, or no usable device */
+    ORBX_E_CAPACITY = -3,  /* more keypoints than the caller's buffer (or the handle's internal lists) can hold */
+    ORBX_E_ALLOC = -4,     /* out of host or device memory */
+    ORBX_E_ALIGN = -5      /* a device pointer is not 16-byte aligned */
+} orbx_status;
+
+/* == cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle (degrees), response, octave, class_id (-1) */
+typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } orbx_keypoint;
+/* == cv::DMatch (16 bytes) */
+typedef struct { int32_t query_idx, train_idx, img_idx; float distance; } orbx_dmatch;
+/* per-query best two neighbours; absent entries have idx = -1, dist = -1 */
+typedef struct { int32_t dist0, idx0, dist1, idx1; } hamx_top2;
+
+#define ORBX_HARRIS_SCORE 0
+#define ORBX_FAST_SCORE 1
+
+/* cv::ORB constructor arguments.  Only nfeatures, nlevels, scale_factor, score_type and fast_threshold may differ
+ * from the defaults; edge_threshold 31, first_level 0, wta_k 2, patch_size 31 are required. */
+typedef struct {
+    int32_t nfeatures;       /* 500  */
+    float scale_factor;      /* 1.2f */
+    int32_t nlevels;         /* 8    */
+    int32_t edge_threshold;  /* 31   */
+    int32_t first_level;     /* 0    */
+    int32_t wta_k;           /* 2    */
+    int32_t score_type;      /* ORBX_HARRIS_SCORE */
+    int32_t patch_size;      /* 31   */
+    int32_t fast_threshold;  /* 20   */
+} orbx_params;
+
+typedef struct orbx_context* orbx_handle;
+typedef struct hamx_context* hamx_handle;
+
+ORBX_API const char* orbx_last_error(void);
+ORBX_API const char* orbx_version(void);
+ORBX_API int orbx_device_count(void);
+ORBX_API void orbx_default_params(orbx_params* p);
+
+/* ------------------------------------------------------------------ extraction (FeatureExtractor) */
+
+/* Persistent state for frames up to max_w x max_h, up to max_batch frames in flight per call.
+ * Mirrors ProcessingNode::init()/destroy() (src/ProcessingNode.h:19-21). */
+ORBX_API int orbx_create(orbx_handle* out, const orbx_params* params, int device, int max_w, int max_h, int max_batch);
+ORBX_API int orbx_destroy(orbx_handle h);
+/* Run on a caller-provided cudaStream_t (e.g. the framework's current stream); NULL restores the handle's own. */
+ORBX_API int orbx_set_stream(orbx_handle h, void* cuda_stream);
+ORBX_API int orbx_synchronize(orbx_handle h);
+/* Largest number of keypoints one frame can return with the handle's parameters (ties included). */
+ORBX_API int orbx_max_keypoints(orbx_handle h);
+/* Level geometry and quotas as the handle computes them (arrays of nlevels entries; any pointer may be NULL). */
+ORBX_API int orbx_level_info(orbx_handle h, int w, int h_, int32_t* widths, int32_t* heights, float* scales, int32_t* quotas);
+
+/* OrbFeatureDetector::detect(image, keypoints): gray is h x w, 8-bit, row stride in bytes. */
+ORBX_API int orbx_detect(orbx_handle h, const uint8_t* gray, int w, int h_, size_t stride, orbx_keypoint* out, int cap, int* n);
+/* OrbDescriptorExtractor::compute(image, keypoints, descriptors): keypoints are filtered (border) and stably
+ * regrouped by octave in place, *n is updated, desc receives *n rows of 32 bytes.  Angles are taken from the
+ * keypoints, as OpenCV does. */
+ORBX_API int orbx_compute(orbx_handle h, const uint8_t* gray, int w, int h_, size_t stride, orbx_keypoint* kps, int* n, uint8_t* desc);
+/* detect followed by compute with one pyramid; results identical to the two separate calls. */
+ORBX_API int orbx_detect_and_compute(orbx_handle h, const uint8_t* gray, int w, int h_, size_t stride,
+                            orbx_keypoint* out, uint8_t* desc, int cap, int* n);
+/* nframes (<= max_batch) frames of one size in one submission.  Frame f writes out[f*cap ..], desc[f*cap*32 ..],
+ * counts[f].  This is the throughput entry point used for sequences (frames are independent, src/main.cpp:36-51). */
+ORBX_API int orbx_extract_batch(orbx_handle h, const uint8_t* const* frames, int nframes, int w, int h_, size_t stride,
+                       orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts);
+/* Same with everything resident on the handle's device: frames at d_frames + f*frame_pitch_bytes. Asynchronous on
+ * the handle's stream; d_counts[f] is the keypoint count of frame f.  Overflow is reported by orbx_check_dev. */
+ORBX_API int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, size_t frame_pitch_bytes, int nframes, int w, int h_,
+                           size_t stride, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts);
+/* Synchronises and returns ORBX_E_CAPACITY if any _dev call since the last check overflowed a list. */
+ORBX_API int orbx_check_dev(orbx_handle h);
+
+/* Stage-level taps for parity tests and profiling (device work + copy back). */
+ORBX_API int orbx_debug_pyramid_level(orbx_handle h, const uint8_t* gray, int w, int h_, size_t stride, int level, uint8_t* out);
+ORBX_API int orbx_debug_fast_level(orbx_handle h, const uint8_t* gray, int w, int h_, size_t stride, int level,
+                          int32_t* xs, int32_t* ys, int32_t* scores, int cap, int* n);
+
+/* ------------------------------------------------------------------ matching (CameraPoseEstimator::matchFeatures) */
+
+ORBX_API int hamx_create(hamx_handle* out, int device);
+ORBX_API int hamx_destroy(hamx_handle h);
+ORBX_API int hamx_set_stream(hamx_handle h, void* cuda_stream);
+ORBX_API int hamx_synchronize(hamx_handle h);
+
+/* BFMatcher(NORM_HAMMING,false).knnMatch(q, t, out, 2): q is nq x 32 bytes, t is nt x 32 bytes.
+ * out holds nq*2 entries; out_counts[i] = min(nt, 2) entries of row i are valid, sorted by (distance, trainIdx). */
+ORBX_API int hamx_knn2(hamx_handle h, const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, orbx_dmatch* out, int32_t* out_counts);
+/* matchFeatures(): knnMatch k=2 + Lowe ratio `d0 < d1 * ratio` in float, accepted matches in ascending query order.
+ * Queries with fewer than two neighbours are dropped (the reference would index out of range there). */
+ORBX_API int hamx_match_ratio(hamx_handle h, const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, float ratio,
+                     orbx_dmatch* good /* cap nq */, int64_t* ngood);
+
+/* Device-resident pieces (asynchronous on the handle's stream; pointers must be 16-byte aligned). */
+ORBX_API int hamx_knn2_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
+                  hamx_top2* d_out);
+/* Merge nparts per-shard results laid out [part][nq] (e.g. the output of an all-gather) into d_out[nq]. */
+ORBX_API int hamx_merge_top2_dev(hamx_handle h, const hamx_top2* d_parts, int nparts, int64_t nq, hamx_top2* d_out);
+/* Ratio test + ordered compaction: d_good gets the accepted matches, *d_ngood their number. */
+ORBX_API int hamx_ratio_dev(hamx_handle h, const hamx_top2* d_top2, int64_t nq, float ratio, orbx_dmatch* d_good, int64_t* d_ngood);
+
+/* Register-only popcount microbenchmark: the measured integer-pipe peak used as the matcher's roofline denominator.
+ * gpopc_per_s = 32-bit POPC results per second / 1e9, over the whole device. */
+ORBX_API int hamx_popc_peak(int device, double* gpopc_per_s, double* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

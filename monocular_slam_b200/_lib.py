@@ -1,0 +1,110 @@
+"""ctypes binding of liborbx.so (include/orbx.h).  No CPU fallback: a missing library or device raises."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborbx.so")
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")]
+)
+DMATCH_DTYPE = np.dtype([("query_idx", "<i4"), ("train_idx", "<i4"), ("img_idx", "<i4"), ("distance", "<f4")])
+TOP2_DTYPE = np.dtype([("dist0", "<i4"), ("idx0", "<i4"), ("dist1", "<i4"), ("idx1", "<i4")])
+assert KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DTYPE.itemsize == 16
+
+HARRIS_SCORE, FAST_SCORE = 0, 1
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_ALLOC, E_ALIGN = 0, -1, -2, -3, -4, -5
+
+# every symbol include/orbx.h declares (tests/test_abi.py checks the header against this list and the built library)
+SYMBOLS = [
+    "orbx_last_error", "orbx_version", "orbx_device_count", "orbx_default_params", "orbx_create", "orbx_destroy",
+    "orbx_set_stream", "orbx_synchronize", "orbx_max_keypoints", "orbx_level_info", "orbx_detect", "orbx_compute",
+    "orbx_detect_and_compute", "orbx_extract_batch", "orbx_extract_batch_dev", "orbx_check_dev",
+    "orbx_debug_pyramid_level", "orbx_debug_fast_level", "hamx_create", "hamx_destroy", "hamx_set_stream",
+    "hamx_synchronize", "hamx_knn2", "hamx_match_ratio", "hamx_knn2_dev", "hamx_merge_top2_dev", "hamx_ratio_dev",
+    "hamx_popc_peak",
+]
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("liborbx status %d: %s" % (status, message))
+        self.status = status
+
+
+class Params(C.Structure):
+    """cv::ORB constructor arguments (reference defaults: src/FeatureExtractor.h:23-24)."""
+
+    _fields_ = [
+        ("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32), ("edge_threshold", C.c_int32),
+        ("first_level", C.c_int32), ("wta_k", C.c_int32), ("score_type", C.c_int32), ("patch_size", C.c_int32),
+        ("fast_threshold", C.c_int32),
+    ]
+
+
+def build(force=False, verbose=False):
+    """Compile liborbx.so in-tree with nvcc for sm_100a (monocular_slam_b200/csrc/build.sh)."""
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc")) if f.endswith((".cu", ".cuh", ".inc", ".sh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "orbx.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    out = subprocess.run(["sh", os.path.join(_HERE, "csrc", "build.sh")], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode:
+        raise RuntimeError("building liborbx.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load liborbx.so; raises if it has not been built (there is deliberately no fallback implementation)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrbxError(E_CUDA, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(monocular_slam_b200 has no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32p, i64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    ip, fp, dp = C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_version.restype = C.c_char_p
+    L.orbx_default_params.argtypes = [C.POINTER(Params)]
+    L.orbx_default_params.restype = None
+    L.orbx_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_set_stream.argtypes = [vp, vp]
+    L.orbx_synchronize.argtypes = [vp]
+    L.orbx_max_keypoints.argtypes = [vp]
+    L.orbx_level_info.argtypes = [vp, C.c_int, C.c_int, i32p, i32p, fp, i32p]
+    L.orbx_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, ip]
+    L.orbx_compute.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, ip, vp]
+    L.orbx_detect_and_compute.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, vp, C.c_int, ip]
+    L.orbx_extract_batch.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_size_t, vp, vp, C.c_int, i32p]
+    L.orbx_extract_batch_dev.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, vp, C.c_int, vp]
+    L.orbx_check_dev.argtypes = [vp]
+    L.orbx_debug_pyramid_level.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_int, vp]
+    L.orbx_debug_fast_level.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_int, i32p, i32p, i32p, C.c_int, ip]
+    L.hamx_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.hamx_destroy.argtypes = [vp]
+    L.hamx_set_stream.argtypes = [vp, vp]
+    L.hamx_synchronize.argtypes = [vp]
+    L.hamx_knn2.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, i32p]
+    L.hamx_match_ratio.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_float, vp, i64p]
+    L.hamx_knn2_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64, vp]
+    L.hamx_merge_top2_dev.argtypes = [vp, vp, C.c_int, C.c_int64, vp]
+    L.hamx_ratio_dev.argtypes = [vp, vp, C.c_int64, C.c_float, vp, vp]
+    L.hamx_popc_peak.argtypes = [C.c_int, dp, dp]
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != 0:
+        raise OrbxError(status, lib().orbx_last_error().decode("utf-8", "replace"))

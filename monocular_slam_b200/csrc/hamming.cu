@@ -1,0 +1,554 @@
+// hamming.cu -- K6: brute-force 256-bit Hamming kNN(k=2) + Lowe ratio test for sm_100a.
+//
+// Replaces BFMatcher(NORM_HAMMING,false).knnMatch(d1,d2,raw,2) and the ratio loop of
+// matchFeatures (reference src/CameraPoseEstimator.cpp:200-213).  The distance is the one spelled out in
+// ThirdParty/DBoW2/DBoW2/FORB.cpp:81-101: XOR of the two 256-bit strings, population count, summed.
+//
+// Layout.  Descriptors are rows of 32 bytes (2 x uint4).  A CTA of 128 threads owns 256 query rows, two per thread,
+// held in registers for the whole kernel.  The train rows of the CTA's split are streamed through a 4-stage ring of
+// 4 KB shared-memory tiles filled by the TMA engine (cp.async.bulk + mbarrier complete_tx); every lane reads the
+// same train row (a shared-memory broadcast), XORs it against its two queries and issues 16 POPCs, which is the
+// pipe this kernel is bound by (8 POPC per comparison; DESIGN.md "K6").
+//
+// Tie rule.  OpenCV inserts candidates in ascending train order with a strict `<`, i.e. the result is the two
+// lexicographically smallest (distance, trainIdx) pairs.  Packing key = distance << 23 | trainIdx makes that a
+// plain unsigned min: best1 = min(best1, max(best0, key)); best0 = min(best0, key).  Train sets larger than 2^23
+// rows are processed in chunks by the host and merged with the same rule on 64-bit keys.
+#include "common.cuh"
+
+namespace orbx {
+namespace {
+
+constexpr int HT_THREADS = 128;
+constexpr int HT_QPT = 2;
+constexpr int HT_QB = HT_THREADS * HT_QPT;   // queries per CTA
+constexpr int HT_TT = 128;                   // train rows per stage
+constexpr int HT_STAGES = 4;
+constexpr int HT_IDX_BITS = 23;
+constexpr uint32_t HT_IDX_MASK = (1u << HT_IDX_BITS) - 1;
+constexpr uint32_t HT_NONE = 0xFFFFFFFFu;    // distance field 511: larger than any real key
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void top2_insert(uint32_t& b0, uint32_t& b1, uint32_t key)
+{
+    uint32_t hi = max(b0, key);
+    b0 = min(b0, key);
+    b1 = min(b1, hi);
+}
+
+__device__ __forceinline__ uint32_t ham256(const uint32_t (&q)[8], const uint4& a, const uint4& b)
+{
+    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) + __popc(q[4] ^ b.x) +
+           __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+}
+
+__device__ __forceinline__ hamx_top2 decode_top2(uint32_t k0, uint32_t k1, int64_t offset)
+{
+    hamx_top2 r;
+    r.dist0 = k0 == HT_NONE ? -1 : (int32_t)(k0 >> HT_IDX_BITS);
+    r.idx0 = k0 == HT_NONE ? -1 : (int32_t)((int64_t)(k0 & HT_IDX_MASK) + offset);
+    r.dist1 = k1 == HT_NONE ? -1 : (int32_t)(k1 >> HT_IDX_BITS);
+    r.idx1 = k1 == HT_NONE ? -1 : (int32_t)((int64_t)(k1 & HT_IDX_MASK) + offset);
+    return r;
+}
+
+// grid = (query blocks, train splits).  partial is [nsplit][nq] (only touched when nsplit > 1); the last CTA of a
+// query block to finish merges the splits, so one launch yields final results.
+__global__ void __launch_bounds__(HT_THREADS)
+k_hamming_knn2(const uint4* __restrict__ q, int64_t nq, const uint4* __restrict__ t, int nt, int tiles_per_split,
+               uint2* partial, unsigned int* arrivals, hamx_top2* __restrict__ out, int64_t idx_offset)
+{
+    __shared__ __align__(128) uint4 s_tile[HT_STAGES][HT_TT * 2];
+    __shared__ __align__(8) uint64_t s_full[HT_STAGES];
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x;
+    const int nsplit = gridDim.y;
+    const int ntiles_all = (nt + HT_TT - 1) / HT_TT;
+    const int tile_begin = blockIdx.y * tiles_per_split;
+    const int tile_end = min(tile_begin + tiles_per_split, ntiles_all);
+    const int ntiles = tile_end - tile_begin;
+
+    if (tid == 0) {
+        for (int s = 0; s < HT_STAGES; s++) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int i) {   // thread 0 only: fetch tile (tile_begin + i) into stage i % STAGES
+        int tile = tile_begin + i;
+        int rows = min(HT_TT, nt - tile * HT_TT);
+        uint32_t bytes = (uint32_t)rows * 32u;
+        int st = i % HT_STAGES;
+        mbar_expect_tx(&s_full[st], bytes);
+        tma_bulk_g2s(&s_tile[st][0], t + (size_t)tile * HT_TT * 2, bytes, &s_full[st]);
+    };
+    if (tid == 0)
+        for (int i = 0; i < HT_STAGES && i < ntiles; i++) issue(i);
+
+    // this thread's queries: coalesced over the CTA (thread tid takes rows tid, tid + 128 of the block)
+    uint32_t qr[HT_QPT][8];
+    int64_t qi[HT_QPT];
+    uint32_t b0[HT_QPT], b1[HT_QPT];
+#pragma unroll
+    for (int k = 0; k < HT_QPT; k++) {
+        qi[k] = (int64_t)blockIdx.x * HT_QB + k * HT_THREADS + tid;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (qi[k] < nq) { lo = q[2 * qi[k]]; hi = q[2 * qi[k] + 1]; }
+        qr[k][0] = lo.x; qr[k][1] = lo.y; qr[k][2] = lo.z; qr[k][3] = lo.w;
+        qr[k][4] = hi.x; qr[k][5] = hi.y; qr[k][6] = hi.z; qr[k][7] = hi.w;
+        b0[k] = HT_NONE; b1[k] = HT_NONE;
+    }
+
+    for (int i = 0; i < ntiles; i++) {
+        const int st = i % HT_STAGES;
+        mbar_wait(&s_full[st], (uint32_t)(i / HT_STAGES) & 1u);
+        const uint4* ts = &s_tile[st][0];
+        const int tile = tile_begin + i;
+        const uint32_t base = (uint32_t)tile * HT_TT;
+        const int rows = min(HT_TT, nt - tile * HT_TT);
+        if (rows == HT_TT) {
+#pragma unroll 4
+            for (int j = 0; j < HT_TT; j++) {
+                uint4 a = ts[2 * j], b = ts[2 * j + 1];
+#pragma unroll
+                for (int k = 0; k < HT_QPT; k++) {
+                    uint32_t d = ham256(qr[k], a, b);
+                    top2_insert(b0[k], b1[k], (d << HT_IDX_BITS) + (base + j));
+                }
+            }
+        } else {
+            for (int j = 0; j < rows; j++) {
+                uint4 a = ts[2 * j], b = ts[2 * j + 1];
+#pragma unroll
+                for (int k = 0; k < HT_QPT; k++) {
+                    uint32_t d = ham256(qr[k], a, b);
+                    top2_insert(b0[k], b1[k], (d << HT_IDX_BITS) + (base + j));
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with stage st before the TMA engine overwrites it
+        if (tid == 0 && i + HT_STAGES < ntiles) issue(i + HT_STAGES);
+    }
+
+    if (nsplit == 1) {
+#pragma unroll
+        for (int k = 0; k < HT_QPT; k++)
+            if (qi[k] < nq) out[qi[k]] = decode_top2(b0[k], b1[k], idx_offset);
+        return;
+    }
+
+#pragma unroll
+    for (int k = 0; k < HT_QPT; k++)
+        if (qi[k] < nq) __stcg(&partial[(size_t)blockIdx.y * nq + qi[k]], make_uint2(b0[k], b1[k]));
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int prev = atomicAdd(&arrivals[blockIdx.x], 1u);
+        s_last = (prev == (unsigned int)(nsplit - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < HT_QPT; k++) {
+        if (qi[k] >= nq) continue;
+        uint32_t m0 = HT_NONE, m1 = HT_NONE;
+        for (int s = 0; s < nsplit; s++) {
+            uint2 p = __ldcg(&partial[(size_t)s * nq + qi[k]]);
+            top2_insert(m0, m1, p.x);
+            top2_insert(m0, m1, p.y);
+        }
+        out[qi[k]] = decode_top2(m0, m1, idx_offset);
+    }
+    if (tid == 0) arrivals[blockIdx.x] = 0;   // ready for the next launch
+}
+
+__device__ __forceinline__ unsigned long long top2_key64(int32_t d, int32_t i)
+{
+    return i < 0 ? ~0ull : ((unsigned long long)(uint32_t)d << 32) | (uint32_t)i;
+}
+
+__device__ __forceinline__ void top2_insert64(unsigned long long& b0, unsigned long long& b1, unsigned long long key)
+{
+    unsigned long long hi = b0 > key ? b0 : key;
+    b0 = b0 < key ? b0 : key;
+    b1 = b1 < hi ? b1 : hi;
+}
+
+// parts is [nparts][nq]; lexicographic (distance, index) merge, identical to a single-device run over the union.
+__global__ void k_merge_top2(const hamx_top2* __restrict__ parts, int nparts, int64_t nq, hamx_top2* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    unsigned long long m0 = ~0ull, m1 = ~0ull;
+    for (int p = 0; p < nparts; p++) {
+        hamx_top2 v = parts[(size_t)p * nq + i];
+        top2_insert64(m0, m1, top2_key64(v.dist0, v.idx0));
+        top2_insert64(m0, m1, top2_key64(v.dist1, v.idx1));
+    }
+    hamx_top2 r;
+    r.dist0 = m0 == ~0ull ? -1 : (int32_t)(m0 >> 32);
+    r.idx0 = m0 == ~0ull ? -1 : (int32_t)(m0 & 0xFFFFFFFFu);
+    r.dist1 = m1 == ~0ull ? -1 : (int32_t)(m1 >> 32);
+    r.idx1 = m1 == ~0ull ? -1 : (int32_t)(m1 & 0xFFFFFFFFu);
+    out[i] = r;
+}
+
+__global__ void k_top2_to_dmatch(const hamx_top2* __restrict__ top2, int64_t nq, orbx_dmatch* __restrict__ out,
+                                 int32_t* __restrict__ counts)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    hamx_top2 v = top2[i];
+    orbx_dmatch a = { (int32_t)i, v.idx0, 0, (float)v.dist0 };
+    orbx_dmatch b = { (int32_t)i, v.idx1, 0, (float)v.dist1 };
+    out[2 * i] = a;
+    out[2 * i + 1] = b;
+    counts[i] = (v.idx0 >= 0) + (v.idx1 >= 0);
+}
+
+// Lowe ratio (src/CameraPoseEstimator.cpp:208-212: float multiply, strict <) + order-preserving compaction.
+// One CTA walks the queries in chunks of 1024 so the accepted list stays in ascending query order.
+__global__ void __launch_bounds__(1024) k_ratio_compact(const hamx_top2* __restrict__ top2, int64_t nq, float ratio,
+                                                        orbx_dmatch* __restrict__ good, long long* __restrict__ ngood)
+{
+    __shared__ int s_warp[32];
+    __shared__ long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int64_t c = 0; c < nq; c += 1024) {
+        int64_t i = c + tid;
+        bool ok = false;
+        hamx_top2 v = { 0, 0, 0, 0 };
+        if (i < nq) {
+            v = top2[i];
+            ok = v.idx0 >= 0 && v.idx1 >= 0 && (float)v.dist0 < __fmul_rn((float)v.dist1, ratio);
+        }
+        unsigned int bal = __ballot_sync(0xFFFFFFFFu, ok);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; w++) {   // 32 broadcast reads; negligible next to the matching kernel
+            int n = s_warp[w];
+            before += w < wid ? n : 0;
+            total += n;
+        }
+        long long base = s_base;
+        if (ok) {
+            long long pos = base + before + __popc(bal & ((1u << lane) - 1u));
+            orbx_dmatch m = { (int32_t)i, v.idx0, 0, (float)v.dist0 };
+            good[pos] = m;
+        }
+        __syncthreads();
+        if (tid == 0) s_base = base + total;
+        __syncthreads();
+    }
+    if (tid == 0) *ngood = s_base;
+}
+
+// Register-only POPC throughput probe: 8 independent POPC + 8 XOR per iteration and thread, like the matcher's inner
+// loop without its memory traffic.
+__global__ void __launch_bounds__(1024) k_popc_peak(uint32_t* sink, int iters, uint32_t seed)
+{
+    uint32_t x0 = seed ^ threadIdx.x, x1 = x0 * 2654435761u, x2 = x1 ^ 0x9E3779B9u, x3 = x2 * 40503u;
+    uint32_t x4 = ~x0, x5 = ~x1, x6 = ~x2, x7 = ~x3;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        uint32_t m = (uint32_t)i * 0x01010101u;
+        a0 += __popc(x0 ^ m) + __popc(x1 ^ m);
+        a1 += __popc(x2 ^ m) + __popc(x3 ^ m);
+        a2 += __popc(x4 ^ m) + __popc(x5 ^ m);
+        a3 += __popc(x6 ^ m) + __popc(x7 ^ m);
+    }
+    uint32_t a = a0 + a1 + a2 + a3;
+    if (a == 0xFFFFFFFFu) sink[0] = a;   // never true; keeps the loop alive
+}
+
+}  // namespace
+}  // namespace orbx
+
+// ------------------------------------------------------------------------------------------------ host side
+using namespace orbx;
+
+struct hamx_context {
+    int device;
+    cudaStream_t own_stream, stream;
+    // workspaces (grown on demand)
+    uint8_t* d_q; size_t q_bytes;
+    uint8_t* d_t; size_t t_bytes;
+    uint2* d_partial; size_t partial_bytes;
+    unsigned int* d_arrivals; size_t arrivals_n;
+    hamx_top2* d_top2; size_t top2_bytes;
+    hamx_top2* d_parts; size_t parts_bytes;
+    orbx_dmatch* d_dm; size_t dm_bytes;
+    int32_t* d_counts; size_t counts_bytes;
+    long long* d_ngood;
+    int sm_count;
+};
+
+template <typename T>
+static int grow(T** p, size_t* have, size_t want, bool zero = false, cudaStream_t s = 0)
+{
+    if (*have >= want && *p) return ORBX_OK;
+    if (*p) { cudaError_t e = cudaFree(*p); (void)e; *p = nullptr; *have = 0; }
+    size_t bytes = align_up(want + want / 4, 256);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ORBX_E_ALLOC; }
+    if (zero) { e = cudaMemsetAsync(*p, 0, bytes, s); if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return ORBX_E_CUDA; } }
+    *have = bytes;
+    return ORBX_OK;
+}
+
+extern "C" int hamx_create(hamx_handle* out, int device)
+{
+    ORBX_REQUIRE(out != nullptr, "hamx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { set_error("hamx_create: no CUDA device (%s); liborbx has no CPU fallback", cudaGetErrorString(e)); return ORBX_E_CUDA; }
+    ORBX_REQUIRE(device >= 0 && device < ndev, "hamx_create: device %d out of range [0,%d)", device, ndev);
+    ORBX_CUDA(cudaSetDevice(device));
+    hamx_context* h = new hamx_context();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    ORBX_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    ORBX_CUDA(cudaMalloc((void**)&h->d_ngood, sizeof(long long)));
+    *out = h;
+    return ORBX_OK;
+}
+
+extern "C" int hamx_destroy(hamx_handle h)
+{
+    if (!h) return ORBX_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_partial); cudaFree(h->d_arrivals); cudaFree(h->d_top2);
+    cudaFree(h->d_parts); cudaFree(h->d_dm); cudaFree(h->d_counts); cudaFree(h->d_ngood);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return ORBX_OK;
+}
+
+extern "C" int hamx_set_stream(hamx_handle h, void* cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_set_stream: NULL handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ORBX_OK;
+}
+
+extern "C" int hamx_synchronize(hamx_handle h)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_synchronize: NULL handle");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+static int fill_absent(hamx_handle h, hamx_top2* d_out, int64_t nq)
+{
+    // nt == 0: every query has no neighbours (all fields -1 == 0xFF bytes)
+    ORBX_CUDA(cudaMemsetAsync(d_out, 0xFF, (size_t)nq * sizeof(hamx_top2), h->stream));
+    return ORBX_OK;
+}
+
+static int launch_chunk(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int nt, int64_t offset, hamx_top2* d_out)
+{
+    const int64_t nqb = (nq + HT_QB - 1) / HT_QB;
+    const int ntiles = (nt + HT_TT - 1) / HT_TT;
+    const int64_t target = (int64_t)h->sm_count * 8;
+    int64_t nsplit = nqb >= target ? 1 : (target + nqb - 1) / nqb;
+    if (nsplit > ntiles) nsplit = ntiles;
+    if (nsplit > 65535) nsplit = 65535;
+    int tps = (int)((ntiles + nsplit - 1) / nsplit);
+    nsplit = (ntiles + tps - 1) / tps;
+    if (nsplit > 1) {
+        int rc = grow(&h->d_partial, &h->partial_bytes, (size_t)nsplit * nq * sizeof(uint2));
+        if (rc) return rc;
+        rc = grow(&h->d_arrivals, &h->arrivals_n, (size_t)nqb * sizeof(unsigned int), true, h->stream);
+        if (rc) return rc;
+    }
+    dim3 grid((unsigned int)nqb, (unsigned int)nsplit);
+    k_hamming_knn2<<<grid, HT_THREADS, 0, h->stream>>>((const uint4*)d_q, nq, (const uint4*)d_t, nt, tps, h->d_partial,
+                                                        h->d_arrivals, d_out, offset);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int hamx_knn2_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
+                             hamx_top2* d_out)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_knn2_dev: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nt >= 0, "hamx_knn2_dev: negative size");
+    ORBX_REQUIRE(nq < (1ll << 31) && nt + train_offset < (1ll << 31) && train_offset >= 0,
+                 "hamx_knn2_dev: indices must fit int32 (cv::DMatch), got nq=%lld nt=%lld offset=%lld", (long long)nq,
+                 (long long)nt, (long long)train_offset);
+    if (nq == 0) return ORBX_OK;
+    ORBX_REQUIRE(d_q && d_out && (nt == 0 || d_t), "hamx_knn2_dev: NULL pointer");
+    if ((((uintptr_t)d_q) | ((uintptr_t)d_t) | ((uintptr_t)d_out)) & 15) { set_error("hamx_knn2_dev: device pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    if (nt == 0) return fill_absent(h, d_out, nq);
+    const int64_t chunk = 1ll << HT_IDX_BITS;
+    if (nt <= chunk) return launch_chunk(h, d_q, nq, d_t, (int)nt, train_offset, d_out);
+    // > 2^23 train rows: per-chunk results merged with the 64-bit rule
+    int nchunks = (int)((nt + chunk - 1) / chunk);
+    int rc = grow(&h->d_parts, &h->parts_bytes, (size_t)nchunks * nq * sizeof(hamx_top2));
+    if (rc) return rc;
+    for (int c = 0; c < nchunks; c++) {
+        int64_t lo = (int64_t)c * chunk, n = nt - lo < chunk ? nt - lo : chunk;
+        rc = launch_chunk(h, d_q, nq, d_t + lo * 32, (int)n, train_offset + lo, h->d_parts + (size_t)c * nq);
+        if (rc) return rc;
+    }
+    return hamx_merge_top2_dev(h, h->d_parts, nchunks, nq, d_out);
+}
+
+extern "C" int hamx_merge_top2_dev(hamx_handle h, const hamx_top2* d_parts, int nparts, int64_t nq, hamx_top2* d_out)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_merge_top2_dev: NULL handle");
+    ORBX_REQUIRE(nparts >= 1 && nq >= 0, "hamx_merge_top2_dev: bad sizes");
+    if (nq == 0) return ORBX_OK;
+    ORBX_REQUIRE(d_parts && d_out, "hamx_merge_top2_dev: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    k_merge_top2<<<(unsigned int)((nq + 255) / 256), 256, 0, h->stream>>>(d_parts, nparts, nq, d_out);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int hamx_ratio_dev(hamx_handle h, const hamx_top2* d_top2, int64_t nq, float ratio, orbx_dmatch* d_good, int64_t* d_ngood)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_ratio_dev: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && d_ngood, "hamx_ratio_dev: bad arguments");
+    ORBX_REQUIRE(nq == 0 || (d_top2 && d_good), "hamx_ratio_dev: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    k_ratio_compact<<<1, 1024, 0, h->stream>>>(d_top2, nq, ratio, d_good, (long long*)d_ngood);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+static int upload_sets(hamx_handle h, const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt)
+{
+    int rc = grow(&h->d_q, &h->q_bytes, (size_t)nq * 32 + 32);
+    if (rc) return rc;
+    rc = grow(&h->d_t, &h->t_bytes, (size_t)nt * 32 + 32);
+    if (rc) return rc;
+    rc = grow(&h->d_top2, &h->top2_bytes, (size_t)nq * sizeof(hamx_top2) + 16);
+    if (rc) return rc;
+    if (nq) ORBX_CUDA(cudaMemcpyAsync(h->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, h->stream));
+    if (nt) ORBX_CUDA(cudaMemcpyAsync(h->d_t, t, (size_t)nt * 32, cudaMemcpyHostToDevice, h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int hamx_knn2(hamx_handle h, const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, orbx_dmatch* out, int32_t* out_counts)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_knn2: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nt >= 0, "hamx_knn2: negative size");
+    if (nq == 0) return ORBX_OK;
+    ORBX_REQUIRE(q && out && out_counts && (nt == 0 || t), "hamx_knn2: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int rc = upload_sets(h, q, nq, t, nt);
+    if (rc) return rc;
+    rc = hamx_knn2_dev(h, h->d_q, nq, h->d_t, nt, 0, h->d_top2);
+    if (rc) return rc;
+    rc = grow(&h->d_dm, &h->dm_bytes, (size_t)nq * 2 * sizeof(orbx_dmatch));
+    if (rc) return rc;
+    rc = grow(&h->d_counts, &h->counts_bytes, (size_t)nq * sizeof(int32_t));
+    if (rc) return rc;
+    k_top2_to_dmatch<<<(unsigned int)((nq + 255) / 256), 256, 0, h->stream>>>(h->d_top2, nq, h->d_dm, h->d_counts);
+    ORBX_CUDA(cudaGetLastError());
+    ORBX_CUDA(cudaMemcpyAsync(out, h->d_dm, (size_t)nq * 2 * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(out_counts, h->d_counts, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int hamx_match_ratio(hamx_handle h, const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, float ratio,
+                                orbx_dmatch* good, int64_t* ngood)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_match_ratio: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nt >= 0 && ngood, "hamx_match_ratio: bad arguments");
+    *ngood = 0;
+    if (nq == 0) return ORBX_OK;
+    ORBX_REQUIRE(q && good && (nt == 0 || t), "hamx_match_ratio: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int rc = upload_sets(h, q, nq, t, nt);
+    if (rc) return rc;
+    rc = hamx_knn2_dev(h, h->d_q, nq, h->d_t, nt, 0, h->d_top2);
+    if (rc) return rc;
+    rc = grow(&h->d_dm, &h->dm_bytes, (size_t)nq * 2 * sizeof(orbx_dmatch));
+    if (rc) return rc;
+    rc = hamx_ratio_dev(h, h->d_top2, nq, ratio, h->d_dm, (int64_t*)h->d_ngood);
+    if (rc) return rc;
+    long long n = 0;
+    ORBX_CUDA(cudaMemcpyAsync(&n, h->d_ngood, sizeof(n), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    if (n) ORBX_CUDA(cudaMemcpyAsync(good, h->d_dm, (size_t)n * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    *ngood = n;
+    return ORBX_OK;
+}
+
+extern "C" int hamx_popc_peak(int device, double* gpopc_per_s, double* elapsed_ms)
+{
+    ORBX_REQUIRE(gpopc_per_s != nullptr, "hamx_popc_peak: NULL output");
+    ORBX_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    ORBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    uint32_t* sink = nullptr;
+    ORBX_CUDA(cudaMalloc((void**)&sink, 256));
+    cudaEvent_t e0, e1;
+    ORBX_CUDA(cudaEventCreate(&e0));
+    ORBX_CUDA(cudaEventCreate(&e1));
+    const int iters = 1 << 16, blocks = sms * 2, threads = 1024;
+    k_popc_peak<<<blocks, threads>>>(sink, iters / 16, 1u);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        ORBX_CUDA(cudaEventRecord(e0));
+        k_popc_peak<<<blocks, threads>>>(sink, iters, 12345u + rep);
+        ORBX_CUDA(cudaEventRecord(e1));
+        ORBX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        ORBX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    ORBX_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    double popc = (double)blocks * threads * (double)iters * 8.0;
+    *gpopc_per_s = popc / (best * 1e-3) / 1e9;
+    if (elapsed_ms) *elapsed_ms = best;
+    return ORBX_OK;
+}

@@ -1,0 +1,580 @@
+// orbx_api.cu -- C ABI of liborbx.so: handle management, level geometry, and the extraction entry points
+// declared in include/orbx.h (the drop-in for reference src/FeatureExtractor.cpp:17,19).
+#include <math.h>
+#include <stdlib.h>
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace orbx {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+// defined in the kernel files
+void pyr_down_smem_extent(const int* ofs_x, int dw, const int* ofs_y, int dh, int sw, int sh, int* s_w, int* s_h);
+cudaError_t launch_pyr_down_level(uint8_t* slots, size_t slot_stride, const LevelGeom& src, const LevelGeom& dst, int s_w,
+                                  int s_h, int nframes, cudaStream_t s);
+void fast_tile_dims(int* tw, int* th);
+cudaError_t harris_select_prepare(int max_surv_cap);
+cudaError_t launch_harris_select(const FrameGeom& g, const uint8_t* slots, size_t slot_stride, const Cand* surv,
+                                 size_t surv_stride, Sel* sel, size_t sel_stride, FrameCounters* ctr, int nframes,
+                                 int max_surv_cap, float s4, cudaStream_t s);
+
+}  // namespace orbx
+
+using namespace orbx;
+
+struct orbx_context {
+    int device;
+    orbx_params p;
+    int max_w, max_h, max_batch;
+    cudaStream_t own_stream, stream;
+    // geometry: `gmax` sizes the allocations, `g` is the geometry of the frame size last used
+    FrameGeom gmax, g;
+    int geom_w, geom_h;
+    int pyr_sw[ORBX_MAX_LEVELS], pyr_sh[ORBX_MAX_LEVELS];
+    size_t slot_stride, cand_stride, surv_stride, sel_stride;
+    int max_surv_cap, dev_cap;
+    float harris_s4;
+    // device memory
+    uint8_t* d_slots;
+    Cand* d_cand;
+    Cand* d_surv;
+    Sel* d_sel;
+    FrameCounters* d_ctr;
+    orbx_keypoint* d_kps;
+    uint8_t* d_desc;
+    int32_t* d_counts;
+    uint8_t* d_tab;
+    size_t tab_bytes;
+    // pinned host memory
+    FrameCounters* h_ctr;
+    int32_t* h_counts;
+    std::vector<uint8_t>* h_tab;
+    bool dev_pending;   // a _dev submission has not been checked for overflow yet
+};
+
+static inline int rne_f(float v) { return (int)lrintf(v); }
+
+// Level sizes, quotas, list capacities and buffer offsets for a w x h frame.
+static int build_geometry(const orbx_params& p, int w, int h, FrameGeom* g)
+{
+    memset(g, 0, sizeof(*g));
+    g->nlevels = p.nlevels;
+    g->w = w;
+    g->h = h;
+    g->score_type = p.score_type;
+    g->fast_threshold = p.fast_threshold;
+    int tw, th;
+    fast_tile_dims(&tw, &th);
+
+    int quota[ORBX_MAX_LEVELS];
+    {
+        float factor = (float)(1.0 / (double)p.scale_factor);
+        float nd = (float)p.nfeatures * (1.f - factor) / (1.f - (float)pow((double)factor, (double)p.nlevels));
+        int sum = 0;
+        for (int l = 0; l < p.nlevels - 1; l++) {
+            quota[l] = rne_f(nd);
+            sum += quota[l];
+            nd *= factor;
+        }
+        quota[p.nlevels - 1] = std::max(p.nfeatures - sum, 0);
+    }
+
+    size_t img_off = 0, cand_off = 0, surv_off = 0, sel_off = 0;
+    int tile_start = 0;
+    for (int l = 0; l < p.nlevels; l++) {
+        LevelGeom& L = g->lv[l];
+        L.scale = (float)pow((double)p.scale_factor, (double)(l - p.first_level));
+        L.inv_scale = 1.f / L.scale;
+        L.w = rne_f((float)w / L.scale);
+        L.h = rne_f((float)h / L.scale);
+        if (L.w < 1 || L.h < 1) { set_error("pyramid level %d of a %dx%d frame is empty", l, w, h); return ORBX_E_INVALID; }
+        L.pitch = (int)align_up((size_t)L.w, 128);
+        L.quota = quota[l];
+        const int iw = std::max(L.w - 62, 0), ih = std::max(L.h - 62, 0);   // interior [31, w-31) x [31, h-31)
+        L.tiles_x = div_up(iw, tw);
+        L.tiles_y = div_up(ih, th);
+        if (iw == 0 || ih == 0) L.tiles_x = L.tiles_y = 0;
+        L.tile_start = tile_start;
+        tile_start += L.tiles_x * L.tiles_y;
+        L.cand_cap = (iw == 0 || ih == 0) ? 0 : (iw / 2 + 1) * (ih / 2 + 1);   // NMS: at most one maximum per 2x2
+        const int target = p.score_type == ORBX_HARRIS_SCORE ? 2 * L.quota : L.quota;
+        L.surv_cap = std::min(L.cand_cap, target + std::max(target, 4096));     // room for ties at the cut
+        L.img_off = img_off;
+        img_off += align_up((size_t)L.pitch * L.h, 256);
+        L.cand_off = cand_off; cand_off += (size_t)L.cand_cap;
+        L.surv_off = surv_off; surv_off += (size_t)L.surv_cap;
+        L.sel_off = sel_off;   sel_off += (size_t)L.surv_cap;
+    }
+    g->total_tiles = tile_start;
+    return ORBX_OK;
+}
+
+static void geometry_totals(const FrameGeom& g, size_t* img, size_t* cand, size_t* surv, int* max_surv)
+{
+    const LevelGeom& L = g.lv[g.nlevels - 1];
+    *img = L.img_off + align_up((size_t)L.pitch * L.h, 256);
+    *cand = L.cand_off + L.cand_cap;
+    *surv = L.surv_off + L.surv_cap;
+    int m = 0;
+    for (int l = 0; l < g.nlevels; l++) m = std::max(m, g.lv[l].surv_cap);
+    *max_surv = m;
+}
+
+// INTER_LINEAR_EXACT coefficient tables, computed in double exactly like OpenCV.
+static void linear_table(int n, int m, int* ofs, uint16_t* c1)
+{
+    const double s = 1.0 / ((double)m / (double)n);
+    for (int d = 0; d < m; d++) {
+        double f = s * (d + 0.5) - 0.5;
+        int i = (int)floor(f);
+        if (i < 0) { ofs[d] = 0; c1[d] = 0; }
+        else if (i >= n - 1) { ofs[d] = n - 1; c1[d] = 0; }
+        else { ofs[d] = i; c1[d] = (uint16_t)lrint((f - i) * 256.0); }
+    }
+}
+
+static size_t table_bytes(const FrameGeom& g)
+{
+    size_t b = 0;
+    for (int l = 1; l < g.nlevels; l++) b += align_up((size_t)(g.lv[l].w + g.lv[l].h) * 4, 16) + align_up((size_t)(g.lv[l].w + g.lv[l].h) * 2, 16);
+    return b + 256;
+}
+
+static int set_geometry(orbx_handle h, int w, int hh)
+{
+    if (h->geom_w == w && h->geom_h == hh) return ORBX_OK;
+    ORBX_REQUIRE(w >= 1 && hh >= 1 && w <= h->max_w && hh <= h->max_h, "frame %dx%d outside the handle's limits %dx%d", w, hh,
+                 h->max_w, h->max_h);
+    FrameGeom g;
+    int rc = build_geometry(h->p, w, hh, &g);
+    if (rc) return rc;
+    std::vector<uint8_t>& tab = *h->h_tab;
+    size_t off = 0;
+    for (int l = 1; l < g.nlevels; l++) {
+        LevelGeom& D = g.lv[l];
+        const LevelGeom& S = g.lv[l - 1];
+        int* ox = (int*)(tab.data() + off);
+        int* oy = ox + D.w;
+        size_t ioff = off;
+        off += align_up((size_t)(D.w + D.h) * 4, 16);
+        uint16_t* cx = (uint16_t*)(tab.data() + off);
+        uint16_t* cy = cx + D.w;
+        size_t coff = off;
+        off += align_up((size_t)(D.w + D.h) * 2, 16);
+        linear_table(S.w, D.w, ox, cx);
+        linear_table(S.h, D.h, oy, cy);
+        pyr_down_smem_extent(ox, D.w, oy, D.h, S.w, S.h, &h->pyr_sw[l], &h->pyr_sh[l]);
+        ORBX_REQUIRE((size_t)h->pyr_sh[l] * h->pyr_sw[l] + (size_t)h->pyr_sh[l] * 256 <= 200 * 1024,
+                     "scale factor %.3f needs more shared memory than one CTA has", (double)h->p.scale_factor);
+        D.ofs_x = (const int*)(h->d_tab + ioff);
+        D.ofs_y = D.ofs_x + D.w;
+        D.c1x = (const uint16_t*)(h->d_tab + coff);
+        D.c1y = D.c1x + D.w;
+    }
+    ORBX_REQUIRE(off <= h->tab_bytes, "internal: resize tables (%zu bytes) exceed their buffer (%zu)", off, h->tab_bytes);
+    // the previous tables may still be in use by work queued on the stream; the copy below is stream-ordered, but the
+    // pageable source is overwritten on the host, so drain first (geometry changes are rare: once per frame size)
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    if (off) ORBX_CUDA(cudaMemcpyAsync(h->d_tab, tab.data(), off, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    h->g = g;
+    h->geom_w = w;
+    h->geom_h = hh;
+    return ORBX_OK;
+}
+
+extern "C" const char* orbx_last_error(void) { return g_error; }
+extern "C" const char* orbx_version(void) { return "orbx 0.1 (sm_100a)"; }
+
+extern "C" int orbx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" void orbx_default_params(orbx_params* p)
+{
+    if (!p) return;
+    p->nfeatures = 500; p->scale_factor = 1.2f; p->nlevels = 8; p->edge_threshold = 31; p->first_level = 0; p->wta_k = 2;
+    p->score_type = ORBX_HARRIS_SCORE; p->patch_size = 31; p->fast_threshold = 20;
+}
+
+extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int device, int max_w, int max_h, int max_batch)
+{
+    ORBX_REQUIRE(out != nullptr, "orbx_create: out is NULL");
+    *out = nullptr;
+    orbx_params p;
+    orbx_default_params(&p);
+    if (params) p = *params;
+    ORBX_REQUIRE(p.nlevels >= 1 && p.nlevels <= ORBX_MAX_LEVELS, "nlevels %d outside [1,%d]", p.nlevels, ORBX_MAX_LEVELS);
+    ORBX_REQUIRE(p.scale_factor > 1.0f && p.scale_factor <= 2.0f, "scale_factor %.3f outside (1,2]", (double)p.scale_factor);
+    ORBX_REQUIRE(p.nfeatures >= 0 && p.nfeatures <= 20000, "nfeatures %d outside [0,20000]", p.nfeatures);
+    ORBX_REQUIRE(p.edge_threshold == 31 && p.first_level == 0 && p.wta_k == 2 && p.patch_size == 31,
+                 "only edge_threshold 31, first_level 0, wta_k 2, patch_size 31 (the reference's defaults) are supported");
+    ORBX_REQUIRE(p.score_type == ORBX_HARRIS_SCORE || p.score_type == ORBX_FAST_SCORE, "bad score_type %d", p.score_type);
+    ORBX_REQUIRE(p.fast_threshold >= 0 && p.fast_threshold <= 254, "fast_threshold %d outside [0,254]", p.fast_threshold);
+    ORBX_REQUIRE(max_w >= 1 && max_h >= 1 && max_w <= 16384 && max_h <= 16384, "max frame size %dx%d outside [1,16384]", max_w, max_h);
+    ORBX_REQUIRE(max_batch >= 1 && max_batch <= 1024, "max_batch %d outside [1,1024]", max_batch);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("orbx_create: no CUDA device (%s); liborbx has no CPU fallback", cudaGetErrorString(e));
+        return ORBX_E_CUDA;
+    }
+    ORBX_REQUIRE(device >= 0 && device < ndev, "orbx_create: device %d out of range [0,%d)", device, ndev);
+    ORBX_CUDA(cudaSetDevice(device));
+
+    orbx_context* h = new orbx_context();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->p = p;
+    h->max_w = max_w; h->max_h = max_h; h->max_batch = max_batch;
+    h->geom_w = h->geom_h = -1;
+    {
+        float scale = 1.f / ((1 << 2) * 7 * 255.f);    // OpenCV HarrisResponses, blockSize 7
+        h->harris_s4 = scale * scale * scale * scale;
+    }
+    int rc = build_geometry(p, max_w, max_h, &h->gmax);
+    if (rc) { delete h; return rc; }
+    size_t img, cand, surv;
+    geometry_totals(h->gmax, &img, &cand, &surv, &h->max_surv_cap);
+    if (harris_select_smem(h->max_surv_cap) > 220 * 1024) {
+        set_error("nfeatures %d needs %zu bytes of shared memory in the Harris selection (limit 220 KB)", p.nfeatures,
+                  harris_select_smem(h->max_surv_cap));
+        delete h;
+        return ORBX_E_INVALID;
+    }
+    h->slot_stride = align_up(img + 256, 256);
+    h->cand_stride = cand + 1;
+    h->surv_stride = surv + 1;
+    h->sel_stride = surv + 1;
+    h->dev_cap = (int)std::min<size_t>(surv, 1u << 20);
+    h->tab_bytes = table_bytes(h->gmax) + 4096;
+    h->h_tab = new std::vector<uint8_t>(h->tab_bytes);
+
+    ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    const size_t B = (size_t)max_batch;
+#define ORBX_ALLOC(ptr, bytes)                                                                            \
+    do {                                                                                                  \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                             \
+        if (e_ != cudaSuccess) {                                                                          \
+            set_error("orbx_create: cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); \
+            orbx_destroy(h);                                                                              \
+            return ORBX_E_ALLOC;                                                                          \
+        }                                                                                                 \
+    } while (0)
+    ORBX_ALLOC(h->d_slots, B * h->slot_stride);
+    ORBX_ALLOC(h->d_cand, B * h->cand_stride * sizeof(Cand));
+    ORBX_ALLOC(h->d_surv, B * h->surv_stride * sizeof(Cand));
+    ORBX_ALLOC(h->d_sel, B * h->sel_stride * sizeof(Sel));
+    ORBX_ALLOC(h->d_ctr, B * sizeof(FrameCounters));
+    ORBX_ALLOC(h->d_kps, B * (size_t)h->dev_cap * sizeof(orbx_keypoint) + 256);
+    ORBX_ALLOC(h->d_desc, B * (size_t)h->dev_cap * 32 + 256);
+    ORBX_ALLOC(h->d_counts, B * sizeof(int32_t) + 256);
+    ORBX_ALLOC(h->d_tab, h->tab_bytes);
+#undef ORBX_ALLOC
+    ORBX_CUDA(cudaMemset(h->d_slots, 0, B * h->slot_stride));   // padding bytes are read (never used) by vector loads
+    ORBX_CUDA(cudaMallocHost((void**)&h->h_ctr, B * sizeof(FrameCounters)));
+    ORBX_CUDA(cudaMallocHost((void**)&h->h_counts, B * sizeof(int32_t)));
+    ORBX_CUDA(harris_select_prepare(h->max_surv_cap));
+    *out = h;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_destroy(orbx_handle h)
+{
+    if (!h) return ORBX_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_slots); cudaFree(h->d_cand); cudaFree(h->d_surv); cudaFree(h->d_sel); cudaFree(h->d_ctr);
+    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_tab);
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h->h_tab;
+    delete h;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_set_stream(orbx_handle h, void* cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_set_stream: NULL handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_synchronize(orbx_handle h)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_synchronize: NULL handle");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_max_keypoints(orbx_handle h) { return h ? h->dev_cap : ORBX_E_INVALID; }
+
+extern "C" int orbx_level_info(orbx_handle h, int w, int hh, int32_t* widths, int32_t* heights, float* scales, int32_t* quotas)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_level_info: NULL handle");
+    FrameGeom g;
+    int rc = build_geometry(h->p, w, hh, &g);
+    if (rc) return rc;
+    for (int l = 0; l < g.nlevels; l++) {
+        if (widths) widths[l] = g.lv[l].w;
+        if (heights) heights[l] = g.lv[l].h;
+        if (scales) scales[l] = g.lv[l].scale;
+        if (quotas) quotas[l] = g.lv[l].quota;
+    }
+    return ORBX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- pipeline
+static int build_pyramids(orbx_handle h, int nframes)
+{
+    for (int l = 1; l < h->g.nlevels; l++)
+        ORBX_CUDA(launch_pyr_down_level(h->d_slots, h->slot_stride, h->g.lv[l - 1], h->g.lv[l], h->pyr_sw[l], h->pyr_sh[l], nframes,
+                                        h->stream));
+    return ORBX_OK;
+}
+
+static int upload_frames(orbx_handle h, const uint8_t* const* frames, int nframes, int w, int hh, size_t stride, cudaMemcpyKind kind)
+{
+    for (int f = 0; f < nframes; f++)
+        ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)f * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch, frames[f], stride,
+                                    (size_t)w, (size_t)hh, kind, h->stream));
+    return ORBX_OK;
+}
+
+// pyramids + FAST + selection + orientation (+ descriptors); results land in d_out / d_desc / d_counts
+static int run_extract(orbx_handle h, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
+{
+    ORBX_CUDA(cudaMemsetAsync(h->d_ctr, 0, (size_t)nframes * sizeof(FrameCounters), h->stream));
+    int rc = build_pyramids(h, nframes);
+    if (rc) return rc;
+    ORBX_CUDA(launch_fast(h->g, h->d_slots, h->slot_stride, h->d_cand, h->cand_stride, h->d_ctr, nframes, h->stream));
+    ORBX_CUDA(launch_select(h->g, h->d_cand, h->cand_stride, h->d_surv, h->surv_stride, h->d_ctr, nframes, h->stream));
+    ORBX_CUDA(launch_harris_select(h->g, h->d_slots, h->slot_stride, h->d_surv, h->surv_stride, h->d_sel, h->sel_stride, h->d_ctr,
+                                   nframes, h->max_surv_cap, h->harris_s4, h->stream));
+    ORBX_CUDA(launch_orient_describe(h->g, h->d_slots, h->slot_stride, h->d_sel, h->sel_stride, h->d_ctr, d_out,
+                                     (mode & ORBX_DO_DESC) ? d_desc : nullptr, cap, d_counts, nframes, mode, h->stream));
+    return ORBX_OK;
+}
+
+static int check_counters(orbx_handle h, int nframes, int cap)
+{
+    for (int f = 0; f < nframes; f++) {
+        const int ov = h->h_ctr[f].overflow;
+        if (ov & 1) { set_error("frame %d: FAST candidate list overflow (internal capacity)", f); return ORBX_E_CAPACITY; }
+        if (ov & 2) { set_error("frame %d: more than %d tied keypoints at a retention cut; raise nfeatures", f, h->max_surv_cap); return ORBX_E_CAPACITY; }
+        if (ov & 4) { set_error("frame %d: %d keypoints exceed the output capacity %d", f, h->h_ctr[f].total, cap); return ORBX_E_CAPACITY; }
+    }
+    return ORBX_OK;
+}
+
+static int common_checks(orbx_handle h, const void* img, int w, int hh, size_t stride, const char* fn)
+{
+    ORBX_REQUIRE(h != nullptr, "%s: NULL handle", fn);
+    ORBX_REQUIRE(img != nullptr, "%s: NULL image", fn);
+    ORBX_REQUIRE(w >= 1 && hh >= 1 && stride >= (size_t)w, "%s: bad image geometry %dx%d stride %zu", fn, w, hh, stride);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    return set_geometry(h, w, hh);
+}
+
+static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes, int w, int hh, size_t stride, orbx_keypoint* out,
+                        uint8_t* desc, int cap, int32_t* counts, int mode, const char* fn)
+{
+    ORBX_REQUIRE(h != nullptr, "%s: NULL handle", fn);
+    ORBX_REQUIRE(frames && out && counts && (desc || !(mode & ORBX_DO_DESC)), "%s: NULL pointer", fn);
+    ORBX_REQUIRE(nframes >= 1 && nframes <= h->max_batch, "%s: %d frames outside [1, max_batch=%d]", fn, nframes, h->max_batch);
+    ORBX_REQUIRE(cap >= 1, "%s: capacity must be positive", fn);
+    int rc = common_checks(h, frames[0], w, hh, stride, fn);
+    if (rc) return rc;
+    const int dcap = std::min(cap, h->dev_cap);
+    rc = upload_frames(h, frames, nframes, w, hh, stride, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    rc = run_extract(h, nframes, mode, h->d_kps, h->d_desc, dcap, h->d_counts);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < nframes; f++) counts[f] = h->h_ctr[f].total;
+    rc = check_counters(h, nframes, dcap);
+    if (rc) return rc;
+    // device rows are laid out [frame][dcap]; the caller's are [frame][cap]
+    int64_t total = 0;
+    for (int f = 0; f < nframes; f++) total += counts[f];
+    if (dcap == cap && total * 2 >= (int64_t)nframes * cap) {
+        ORBX_CUDA(cudaMemcpyAsync(out, h->d_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        if (mode & ORBX_DO_DESC)
+            ORBX_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        for (int f = 0; f < nframes; f++) {
+            if (!counts[f]) continue;
+            ORBX_CUDA(cudaMemcpyAsync(out + (size_t)f * cap, h->d_kps + (size_t)f * dcap, (size_t)counts[f] * sizeof(orbx_keypoint),
+                                      cudaMemcpyDeviceToHost, h->stream));
+            if (mode & ORBX_DO_DESC)
+                ORBX_CUDA(cudaMemcpyAsync(desc + (size_t)f * cap * 32, h->d_desc + (size_t)f * dcap * 32, (size_t)counts[f] * 32,
+                                          cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_detect(orbx_handle h, const uint8_t* gray, int w, int hh, size_t stride, orbx_keypoint* out, int cap, int* n)
+{
+    ORBX_REQUIRE(n != nullptr, "orbx_detect: n is NULL");
+    int32_t cnt = 0;
+    const uint8_t* frames[1] = { gray };
+    int rc = extract_host(h, frames, 1, w, hh, stride, out, nullptr, cap, &cnt, ORBX_DO_ANGLE, "orbx_detect");
+    *n = cnt;
+    return rc;
+}
+
+extern "C" int orbx_detect_and_compute(orbx_handle h, const uint8_t* gray, int w, int hh, size_t stride, orbx_keypoint* out,
+                                       uint8_t* desc, int cap, int* n)
+{
+    ORBX_REQUIRE(n != nullptr, "orbx_detect_and_compute: n is NULL");
+    int32_t cnt = 0;
+    const uint8_t* frames[1] = { gray };
+    int rc = extract_host(h, frames, 1, w, hh, stride, out, desc, cap, &cnt, ORBX_DO_ANGLE | ORBX_DO_DESC, "orbx_detect_and_compute");
+    *n = cnt;
+    return rc;
+}
+
+extern "C" int orbx_extract_batch(orbx_handle h, const uint8_t* const* frames, int nframes, int w, int hh, size_t stride,
+                                  orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts)
+{
+    return extract_host(h, frames, nframes, w, hh, stride, out, desc, cap, counts, ORBX_DO_ANGLE | ORBX_DO_DESC, "orbx_extract_batch");
+}
+
+extern "C" int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, size_t frame_pitch_bytes, int nframes, int w, int hh,
+                                      size_t stride, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_extract_batch_dev: NULL handle");
+    ORBX_REQUIRE(d_frames && d_out && d_desc && d_counts, "orbx_extract_batch_dev: NULL pointer");
+    ORBX_REQUIRE(nframes >= 1 && nframes <= h->max_batch, "orbx_extract_batch_dev: %d frames outside [1, max_batch=%d]", nframes, h->max_batch);
+    ORBX_REQUIRE(cap >= 1 && frame_pitch_bytes >= stride * (size_t)hh, "orbx_extract_batch_dev: bad capacity or frame pitch");
+    if (((uintptr_t)d_desc & 3) || ((uintptr_t)d_out & 3)) { set_error("orbx_extract_batch_dev: output pointers must be 4-byte aligned"); return ORBX_E_ALIGN; }
+    int rc = common_checks(h, d_frames, w, hh, stride, "orbx_extract_batch_dev");
+    if (rc) return rc;
+    for (int f = 0; f < nframes; f++)
+        ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)f * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch,
+                                    d_frames + (size_t)f * frame_pitch_bytes, stride, (size_t)w, (size_t)hh, cudaMemcpyDeviceToDevice, h->stream));
+    rc = run_extract(h, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_out, d_desc, cap, d_counts);
+    if (rc) return rc;
+    h->dev_pending = true;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_check_dev(orbx_handle h)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_check_dev: NULL handle");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    if (!h->dev_pending) { ORBX_CUDA(cudaStreamSynchronize(h->stream)); return ORBX_OK; }
+    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)h->max_batch * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    h->dev_pending = false;
+    for (int f = 0; f < h->max_batch; f++)
+        if (h->h_ctr[f].overflow) {
+            set_error("orbx_check_dev: frame slot %d overflowed (flags %d, %d keypoints)", f, h->h_ctr[f].overflow, h->h_ctr[f].total);
+            return ORBX_E_CAPACITY;
+        }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_compute(orbx_handle h, const uint8_t* gray, int w, int hh, size_t stride, orbx_keypoint* kps, int* n, uint8_t* desc)
+{
+    ORBX_REQUIRE(n != nullptr && *n >= 0, "orbx_compute: bad keypoint count");
+    ORBX_REQUIRE(*n == 0 || (kps && desc), "orbx_compute: NULL pointer");
+    int rc = common_checks(h, gray, w, hh, stride, "orbx_compute");
+    if (rc) return rc;
+    // OpenCV: KeyPointsFilter::runByImageBorder on full-resolution coordinates (rounded), then a stable regroup by octave
+    const int b = h->p.edge_threshold;
+    std::vector<orbx_keypoint> kept;
+    kept.reserve(*n);
+    if (!(hh <= 2 * b || w <= 2 * b)) {
+        for (int i = 0; i < *n; i++) {
+            ORBX_REQUIRE(kps[i].octave >= 0 && kps[i].octave < h->p.nlevels, "orbx_compute: keypoint %d has octave %d outside [0,%d)", i,
+                         kps[i].octave, h->p.nlevels);
+            const int xi = rne_f(kps[i].x), yi = rne_f(kps[i].y);
+            if (xi >= b && xi < w - b && yi >= b && yi < hh - b) kept.push_back(kps[i]);
+        }
+        std::stable_sort(kept.begin(), kept.end(), [](const orbx_keypoint& a, const orbx_keypoint& c) { return a.octave < c.octave; });
+    }
+    const int m = (int)kept.size();
+    ORBX_REQUIRE(m <= h->dev_cap, "orbx_compute: %d keypoints exceed the handle's capacity %d", m, h->dev_cap);
+    *n = m;
+    if (m == 0) return ORBX_OK;
+    memcpy(kps, kept.data(), (size_t)m * sizeof(orbx_keypoint));
+    const uint8_t* frames[1] = { gray };
+    rc = upload_frames(h, frames, 1, w, hh, stride, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    rc = build_pyramids(h, 1);   // the reference path rebuilds the pyramid in compute() as well
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(h->d_kps, kps, (size_t)m * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(launch_describe_given(h->g, h->d_slots, h->d_kps, m, h->d_desc, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)m * 32, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- debug taps
+extern "C" int orbx_debug_pyramid_level(orbx_handle h, const uint8_t* gray, int w, int hh, size_t stride, int level, uint8_t* out)
+{
+    int rc = common_checks(h, gray, w, hh, stride, "orbx_debug_pyramid_level");
+    if (rc) return rc;
+    ORBX_REQUIRE(out && level >= 0 && level < h->g.nlevels, "orbx_debug_pyramid_level: bad level %d", level);
+    const uint8_t* frames[1] = { gray };
+    rc = upload_frames(h, frames, 1, w, hh, stride, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    rc = build_pyramids(h, 1);
+    if (rc) return rc;
+    const LevelGeom& L = h->g.lv[level];
+    ORBX_CUDA(cudaMemcpy2DAsync(out, L.w, h->d_slots + L.img_off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_debug_fast_level(orbx_handle h, const uint8_t* gray, int w, int hh, size_t stride, int level, int32_t* xs,
+                                     int32_t* ys, int32_t* scores, int cap, int* n)
+{
+    int rc = common_checks(h, gray, w, hh, stride, "orbx_debug_fast_level");
+    if (rc) return rc;
+    ORBX_REQUIRE(xs && ys && scores && n && level >= 0 && level < h->g.nlevels, "orbx_debug_fast_level: bad arguments");
+    const uint8_t* frames[1] = { gray };
+    rc = upload_frames(h, frames, 1, w, hh, stride, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemsetAsync(h->d_ctr, 0, sizeof(FrameCounters), h->stream));
+    rc = build_pyramids(h, 1);
+    if (rc) return rc;
+    ORBX_CUDA(launch_fast(h->g, h->d_slots, h->slot_stride, h->d_cand, h->cand_stride, h->d_ctr, 1, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    const LevelGeom& L = h->g.lv[level];
+    const int cnt = h->h_ctr[0].ncand[level];
+    *n = cnt;
+    if (cnt > L.cand_cap) { set_error("orbx_debug_fast_level: candidate overflow (%d > %d)", cnt, L.cand_cap); return ORBX_E_CAPACITY; }
+    std::vector<Cand> v((size_t)cnt);
+    if (cnt) ORBX_CUDA(cudaMemcpy(v.data(), h->d_cand + L.cand_off, (size_t)cnt * sizeof(Cand), cudaMemcpyDeviceToHost));
+    std::sort(v.begin(), v.end(), [](const Cand& a, const Cand& c) { return a.xy < c.xy; });   // raster order (y, x)
+    for (int i = 0; i < cnt && i < cap; i++) {
+        xs[i] = (int32_t)(v[i].xy & 0xFFFFu);
+        ys[i] = (int32_t)(v[i].xy >> 16);
+        scores[i] = (int32_t)v[i].score;
+    }
+    return ORBX_OK;
+}

@@ -1,0 +1,335 @@
+"""Python mirror of the reference's call surface for the ORB front-end, over the C ABI of liborbx.so.
+
+Names and argument meaning follow the reference (and the OpenCV 2.4 objects it uses):
+
+* ``OrbFeatureDetector.detect`` / ``OrbDescriptorExtractor.compute``  -- src/FeatureExtractor.cpp:17,19
+  (members declared at src/FeatureExtractor.h:23-24); both are the same ``ORB`` class, as in OpenCV.
+* ``BFMatcher(NORM_HAMMING, False).knnMatch(q, t, 2)``               -- src/CameraPoseEstimator.cpp:202-204
+* ``match_features(d1, d2, ratio)``                                   -- matchFeatures, src/CameraPoseEstimator.cpp:200-213
+* ``FeatureExtractor`` (init / process / destroy)                     -- ProcessingNode, src/ProcessingNode.h:16-32
+
+Keypoints are numpy structured arrays with cv::KeyPoint's fields (``KEYPOINT_DTYPE``), descriptors ``N x 32 uint8``,
+matches structured arrays with cv::DMatch's fields (``DMATCH_DTYPE``).  Everything runs on the GPU through the
+library; there is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DMATCH_DTYPE, FAST_SCORE, HARRIS_SCORE, KEYPOINT_DTYPE, TOP2_DTYPE, OrbxError, Params, check
+
+NORM_HAMMING = 6   # cv::NORM_HAMMING
+
+
+def _gray(image):
+    img = np.asarray(image)
+    if img.dtype != np.uint8 or img.ndim != 2:
+        raise ValueError("expected an h x w uint8 grayscale image, got %s %s" % (img.dtype, img.shape))
+    if img.strides[1] != 1 or img.strides[0] < img.shape[1]:
+        img = np.ascontiguousarray(img)
+    return img
+
+
+class ORB:
+    """cv::ORB with the reference's defaults; only ``nfeatures``, ``scoreType``, ``nlevels``, ``scaleFactor`` and
+    ``fastThreshold`` may be changed (see include/orbx.h)."""
+
+    def __init__(self, nfeatures=500, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                 scoreType=HARRIS_SCORE, patchSize=31, fastThreshold=20, device=0, max_size=(1920, 1080), max_batch=1):
+        self._h = C.c_void_p()
+        self.params = Params(nfeatures, scaleFactor, nlevels, edgeThreshold, firstLevel, WTA_K, scoreType, patchSize,
+                             fastThreshold)
+        self.device = device
+        self.max_batch = max_batch
+        check(_lib.lib().orbx_create(C.byref(self._h), C.byref(self.params), device, int(max_size[0]), int(max_size[1]),
+                                     max_batch))
+        self.max_keypoints = _lib.lib().orbx_max_keypoints(self._h)
+        self.default_cap = min(self.max_keypoints, nfeatures + max(nfeatures // 4, 512))
+
+    # -- lifetime (ProcessingNode::destroy)
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().orbx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(_lib.lib().orbx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(_lib.lib().orbx_synchronize(self._h))
+
+    def level_info(self, w, h):
+        n = self.params.nlevels
+        ws, hs, qs = (np.zeros(n, np.int32) for _ in range(3))
+        sc = np.zeros(n, np.float32)
+        i32p = C.POINTER(C.c_int32)
+        check(_lib.lib().orbx_level_info(self._h, w, h, ws.ctypes.data_as(i32p), hs.ctypes.data_as(i32p),
+                                         sc.ctypes.data_as(C.POINTER(C.c_float)), qs.ctypes.data_as(i32p)))
+        return ws, hs, sc, qs
+
+    def _retry(self, fn, cap):
+        """Call fn(cap); on ORBX_E_CAPACITY (ties can return more than nfeatures) retry once with the maximum."""
+        try:
+            return fn(cap)
+        except OrbxError as e:
+            if e.status != _lib.E_CAPACITY or cap >= self.max_keypoints:
+                raise
+            return fn(self.max_keypoints)
+
+    # -- OrbFeatureDetector::detect(image, keypoints)
+    def detect(self, image, cap=None):
+        img = _gray(image)
+
+        def run(cap):
+            kps = np.zeros(cap, KEYPOINT_DTYPE)
+            n = C.c_int(0)
+            check(_lib.lib().orbx_detect(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0],
+                                         kps.ctypes.data, cap, C.byref(n)))
+            return kps[:n.value].copy()
+
+        return self._retry(run, cap or self.default_cap)
+
+    # -- OrbDescriptorExtractor::compute(image, keypoints, descriptors)
+    def compute(self, image, keypoints):
+        img = _gray(image)
+        kps = np.array(keypoints, dtype=KEYPOINT_DTYPE, copy=True)
+        n = C.c_int(len(kps))
+        desc = np.zeros((max(len(kps), 1), 32), np.uint8)
+        check(_lib.lib().orbx_compute(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0],
+                                      kps.ctypes.data, C.byref(n), desc.ctypes.data))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def detectAndCompute(self, image, cap=None):
+        img = _gray(image)
+
+        def run(cap):
+            kps = np.zeros(cap, KEYPOINT_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            n = C.c_int(0)
+            check(_lib.lib().orbx_detect_and_compute(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0],
+                                                     kps.ctypes.data, desc.ctypes.data, cap, C.byref(n)))
+            return kps[:n.value].copy(), desc[:n.value].copy()
+
+        return self._retry(run, cap or self.default_cap)
+
+    # -- a batch of frames of one size (sequence extraction; frames are independent, src/main.cpp:36-51)
+    def extract_batch(self, frames, cap=None, out=None):
+        """frames: sequence of h x w uint8 arrays (or one n x h x w array).  Returns (kps[n, cap], desc[n, cap, 32], counts[n]).
+        ``out`` may carry preallocated (kps, desc, counts) buffers, e.g. pinned memory."""
+        frames = [_gray(f) for f in frames]
+        n = len(frames)
+        h, w = frames[0].shape
+        stride = frames[0].strides[0]
+        if any(f.shape != (h, w) or f.strides[0] != stride for f in frames):
+            raise ValueError("all frames of a batch must share one shape and stride")
+        ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+
+        def run(cap):
+            if out is not None and out[0].shape[1] == cap:
+                kps, desc, counts = out
+            else:
+                kps = np.zeros((n, cap), KEYPOINT_DTYPE)
+                desc = np.zeros((n, cap, 32), np.uint8)
+                counts = np.zeros(n, np.int32)
+            check(_lib.lib().orbx_extract_batch(self._h, ptrs, n, w, h, stride, kps.ctypes.data, desc.ctypes.data, cap,
+                                                counts.ctypes.data_as(C.POINTER(C.c_int32))))
+            return kps, desc, counts
+
+        return self._retry(run, cap or self.default_cap)
+
+    def extract_batch_dev(self, d_frames_ptr, frame_pitch, nframes, w, h, stride, d_kps_ptr, d_desc_ptr, cap, d_counts_ptr):
+        """Device-resident variant (raw device pointers, asynchronous on the handle's stream)."""
+        check(_lib.lib().orbx_extract_batch_dev(self._h, d_frames_ptr, frame_pitch, nframes, w, h, stride, d_kps_ptr,
+                                                d_desc_ptr, cap, d_counts_ptr))
+
+    def check_dev(self):
+        check(_lib.lib().orbx_check_dev(self._h))
+
+    # -- stage taps for parity tests
+    def debug_pyramid_level(self, image, level):
+        img = _gray(image)
+        ws, hs, _, _ = self.level_info(img.shape[1], img.shape[0])
+        out = np.zeros((hs[level], ws[level]), np.uint8)
+        check(_lib.lib().orbx_debug_pyramid_level(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], level,
+                                                  out.ctypes.data))
+        return out
+
+    def debug_fast_level(self, image, level):
+        img = _gray(image)
+        ws, hs, _, _ = self.level_info(img.shape[1], img.shape[0])
+        cap = (int(ws[level]) // 2 + 1) * (int(hs[level]) // 2 + 1)
+        xs, ys, sc = (np.zeros(cap, np.int32) for _ in range(3))
+        n = C.c_int(0)
+        i32p = C.POINTER(C.c_int32)
+        check(_lib.lib().orbx_debug_fast_level(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], level,
+                                               xs.ctypes.data_as(i32p), ys.ctypes.data_as(i32p), sc.ctypes.data_as(i32p), cap,
+                                               C.byref(n)))
+        return xs[:n.value].copy(), ys[:n.value].copy(), sc[:n.value].copy()
+
+
+# The reference declares one object of each type (src/FeatureExtractor.h:23-24); in OpenCV 2.4 both are typedefs of cv::ORB.
+OrbFeatureDetector = ORB
+OrbDescriptorExtractor = ORB
+
+
+def ORB_create(nfeatures=500, scoreType=HARRIS_SCORE, **kw):
+    return ORB(nfeatures=nfeatures, scoreType=scoreType, **kw)
+
+
+class BFMatcher:
+    """cv::BFMatcher(NORM_HAMMING, crossCheck=false) as constructed at src/CameraPoseEstimator.cpp:202."""
+
+    def __init__(self, normType=NORM_HAMMING, crossCheck=False, device=0):
+        if normType != NORM_HAMMING or crossCheck:
+            raise ValueError("only BFMatcher(NORM_HAMMING, False) -- the reference's configuration -- is provided")
+        self._h = C.c_void_p()
+        self.device = device
+        check(_lib.lib().hamx_create(C.byref(self._h), device))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().hamx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(_lib.lib().hamx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(_lib.lib().hamx_synchronize(self._h))
+
+    @staticmethod
+    def _desc(d):
+        d = np.ascontiguousarray(d, dtype=np.uint8)
+        if d.ndim != 2 or d.shape[1] != 32:
+            if d.size == 0:
+                return d.reshape(0, 32)
+            raise ValueError("descriptors must be N x 32 uint8 (CV_8U, 256-bit ORB), got %s" % (d.shape,))
+        return d
+
+    def knnMatch(self, queryDescriptors, trainDescriptors, k=2):
+        """Returns (matches[nq, 2] DMATCH_DTYPE, counts[nq]): row i holds counts[i] = min(nt, 2) valid entries sorted by
+        (distance, trainIdx), exactly like vector<vector<DMatch>> from knnMatch(q, t, out, 2)."""
+        if k != 2:
+            raise ValueError("the reference calls knnMatch with k = 2 only")
+        q, t = self._desc(queryDescriptors), self._desc(trainDescriptors)
+        out = np.zeros((len(q), 2), DMATCH_DTYPE)
+        counts = np.zeros(len(q), np.int32)
+        check(_lib.lib().hamx_knn2(self._h, q.ctypes.data, len(q), t.ctypes.data, len(t), out.ctypes.data,
+                                   counts.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out, counts
+
+    def match_ratio(self, d1, d2, ratio):
+        q, t = self._desc(d1), self._desc(d2)
+        good = np.zeros(max(len(q), 1), DMATCH_DTYPE)
+        n = C.c_int64(0)
+        check(_lib.lib().hamx_match_ratio(self._h, q.ctypes.data, len(q), t.ctypes.data, len(t), float(ratio), good.ctypes.data,
+                                          C.byref(n)))
+        return good[:n.value].copy()
+
+    # device-resident pieces (raw device pointers; asynchronous on the handle's stream)
+    def knn2_dev(self, d_q, nq, d_t, nt, train_offset, d_out):
+        check(_lib.lib().hamx_knn2_dev(self._h, d_q, nq, d_t, nt, train_offset, d_out))
+
+    def merge_top2_dev(self, d_parts, nparts, nq, d_out):
+        check(_lib.lib().hamx_merge_top2_dev(self._h, d_parts, nparts, nq, d_out))
+
+    def ratio_dev(self, d_top2, nq, ratio, d_good, d_ngood):
+        check(_lib.lib().hamx_ratio_dev(self._h, d_top2, nq, float(ratio), d_good, d_ngood))
+
+
+_default_matcher = {}
+
+
+def match_features(descriptors1, descriptors2, ratio=0.8, device=0):
+    """matchFeatures(descriptors1, descriptors2, matches, ratio = 0.8) of src/CameraPoseEstimator.cpp:200-213:
+    BFMatcher(NORM_HAMMING).knnMatch(k=2), keep raw[i][0] iff raw[i][0].distance < raw[i][1].distance * ratio."""
+    m = _default_matcher.get(device)
+    if m is None:
+        m = _default_matcher[device] = BFMatcher(NORM_HAMMING, False, device=device)
+    return m.match_ratio(descriptors1, descriptors2, ratio)
+
+
+def popc_peak(device=0):
+    """Measured POPC throughput of the device in Gpopc/s (the matcher's roofline denominator)."""
+    g, ms = C.c_double(0), C.c_double(0)
+    check(_lib.lib().hamx_popc_peak(device, C.byref(g), C.byref(ms)))
+    return g.value, ms.value
+
+
+# ------------------------------------------------------------------------------------------------ pipeline node
+class Features:
+    """struct Features of src/Frame.h:22-34."""
+
+    def __init__(self):
+        self.positions = np.zeros((0, 2), np.float64)       # vector<Point2d>
+        self.descriptors = np.zeros((0, 32), np.uint8)      # Mat N x 32 CV_8U
+        self.mapPointsIndices = np.zeros(0, np.int32)       # vector<int>
+        self.scales = np.zeros(0, np.float64)               # vector<double>
+
+
+class Frame:
+    """The part of src/Frame.h:36-72 the front-end touches."""
+
+    def __init__(self, frameBuffer):
+        self.frameBuffer = frameBuffer
+        self.features = Features()
+
+
+class DataManager:
+    """src/DataManager.h:23-36 (frames only)."""
+
+    def __init__(self, frames=()):
+        self.frames = [f if isinstance(f, Frame) else Frame(f) for f in frames]
+
+
+class FeatureExtractor:
+    """ProcessingNode "FeatureExtractor" (src/FeatureExtractor.{h,cpp}): process(data, frameIdx) fills
+    frame.features.{descriptors, positions, scales, mapPointsIndices} exactly as lines 13-31 do."""
+
+    name = "FeatureExtractor"
+
+    def __init__(self, nfeatures=500, device=0, max_size=(1920, 1080), **orb_kw):
+        self._args = dict(nfeatures=nfeatures, device=device, max_size=max_size, **orb_kw)
+        self.detector = None
+        self.extractor = None
+
+    def init(self):
+        self.detector = OrbFeatureDetector(**self._args)
+        self.extractor = self.detector   # one pyramid/handle serves both, results identical to two objects
+
+    def destroy(self):
+        if self.detector is not None:
+            self.detector.close()
+        self.detector = self.extractor = None
+
+    def validationCheck(self, data, frameIdx):
+        return True
+
+    def process(self, data, frameIdx):
+        if self.detector is None:
+            self.init()
+        frame = data.frames[frameIdx]
+        img = frame.frameBuffer
+        if img.ndim != 2:
+            # frames may be 3-channel in the reference (FrameLoader.cpp:62; cv::ORB converts internally); colour
+            # conversion belongs to frame ingest, a "next" row of the scope table, and is not done on the CPU here
+            raise ValueError("FeatureExtractor expects 8-bit grayscale frames")
+        keypoints = self.detector.detect(img)
+        keypoints, descriptor = self.extractor.compute(img, keypoints)
+        frame.features.descriptors = descriptor
+        frame.features.positions = np.stack([keypoints["x"], keypoints["y"]], axis=1).astype(np.float64)
+        frame.features.scales = keypoints["size"].astype(np.float64)
+        frame.features.mapPointsIndices = np.full(len(keypoints), -1, np.int32)

@@ -75,7 +75,7 @@ def lib():
         L.orc_ic_angle.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
         L.orc_gauss_kernel7.argtypes = [f32p]
         L.orc_blur7.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p]
-        L.orc_describe.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_float, u8p]
+        L.orc_describe.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, u8p]
         L.orc_pyramid_level.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, u8p]
         L.orc_detect.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int]
         L.orc_compute.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, u8p]

@@ -272,12 +272,13 @@ void orc_blur7(const uint8_t* img, int w, int h, int stride, uint8_t* out /* w*h
     free(rows);
 }
 
-/* rotated BRIEF, WTA_K = 2 (OpenCV orb.cpp computeOrbDescriptors) */
-void orc_describe(const uint8_t* blur, int stride, int xi, int yi, float angle_deg, uint8_t* desc32)
+/* rotated BRIEF, WTA_K = 2 (OpenCV orb.cpp computeOrbDescriptors).  OpenCV blurs the level image in place inside a
+ * larger buffer whose 32-pixel BORDER_REFLECT_101 frame stays un-blurred, so a sample that lands outside the level
+ * (only possible for caller-provided keypoints close to the border of a coarse level) reads the raw reflected pixel. */
+void orc_describe(const uint8_t* blur, const uint8_t* raw, int w, int h, int stride, int xi, int yi, float angle_deg, uint8_t* desc32)
 {
     float ang = angle_deg * (float)(3.141592653589793238462643383279502884 / 180.f);
     float a = (float)cos((double)ang), b = (float)sin((double)ang);
-    const uint8_t* center = blur + (size_t)yi * stride + xi;
     for (int i = 0; i < 32; i++) {
         int byte = 0;
         for (int k = 0; k < 8; k++) {
@@ -287,7 +288,9 @@ void orc_describe(const uint8_t* blur, int stride, int xi, int yi, float angle_d
                 float px = (float)pt[2 * e], py = (float)pt[2 * e + 1];
                 float xr = px * a - py * b;
                 float yr = px * b + py * a;
-                v[e] = center[rne_f(yr) * stride + rne_f(xr)];
+                int sx = xi + rne_f(xr), sy = yi + rne_f(yr);
+                if (sx >= 0 && sx < w && sy >= 0 && sy < h) v[e] = blur[(size_t)sy * stride + sx];
+                else v[e] = raw[(size_t)reflect101(sy, h) * stride + reflect101(sx, w)];
             }
             byte |= (v[0] < v[1]) << k;
         }
@@ -442,7 +445,7 @@ static int compute_on_pyramid(const orc_params* p, const orc_pyramid* pyr, int w
         }
         float scale = 1.f / pyr->scale[l];
         int xi = rne_f(kps[i].x * scale), yi = rne_f(kps[i].y * scale);
-        orc_describe(blur[l], pyr->w[l], xi, yi, kps[i].angle, desc + (size_t)i * 32);
+        orc_describe(blur[l], pyr->img[l], pyr->w[l], pyr->h[l], pyr->w[l], xi, yi, kps[i].angle, desc + (size_t)i * 32);
     }
     for (int l = 0; l < ORC_MAX_LEVELS; l++) free(blur[l]);
     return m;

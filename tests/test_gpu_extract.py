@@ -1,0 +1,195 @@
+"""GPU parity: orbx_* (K1-K5) through the C ABI against the oracle and the cv2 golden vectors.
+
+Bar (BASELINE.json north_star): keypoint coordinates, scores/responses, octaves bit-exact; angles bit-exact here
+(tolerance allowed: 1e-4 rad); descriptor bytes bit-exact (allowance: 0.1% of descriptors, reported)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import assert_descriptors_equal, assert_keypoints_equal, sha
+from monocular_slam_b200 import FAST_SCORE, HARRIS_SCORE, ORB, DataManager, FeatureExtractor, OrbxError
+from monocular_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _orb(nf, score, size, batch=1):
+    return ORB(nfeatures=nf, scoreType=score, max_size=size, max_batch=batch)
+
+
+@pytest.mark.parametrize("w,h", [(1241, 376), (640, 480), (333, 257), (1920, 1080)])
+def test_pyramid_levels(w, h):
+    img = syn.frame(w + h, w, h)
+    orb = _orb(500, HARRIS_SCORE, (w, h))
+    P = oracle.Params(nfeatures=500)
+    for l in range(8):
+        got = orb.debug_pyramid_level(img, l)
+        want = oracle.pyramid_level(P, img, l)
+        assert got.shape == want.shape and np.array_equal(got, want), "level %d: %d px differ" % (l, (got != want).sum())
+    orb.close()
+
+
+def test_pyramid_golden_hashes(golden_dir):
+    g = np.load(os.path.join(golden_dir, "kitti_pair.npz"))
+    f0 = np.ascontiguousarray(g["canvas"][:376, :1241])
+    orb = _orb(2000, HARRIS_SCORE, (1241, 376))
+    for l in range(8):
+        assert sha(orb.debug_pyramid_level(f0, l)) == str(g["pyr_sha_f0"][l]), "level %d" % l
+    orb.close()
+
+
+@pytest.mark.parametrize("w,h", [(1241, 376), (640, 480), (200, 150)])
+def test_fast_levels(w, h):
+    img = syn.frame(3 * w + h, w, h)
+    orb = _orb(500, HARRIS_SCORE, (w, h))
+    P = oracle.Params(nfeatures=500)
+    for l in range(8):
+        xs, ys, sc = orb.debug_fast_level(img, l)
+        ox, oy, osc = oracle.level_fast(img, P, l)
+        assert len(xs) == len(ox), "level %d: %d corners, expected %d" % (l, len(xs), len(ox))
+        assert np.array_equal(xs, ox) and np.array_equal(ys, oy) and np.array_equal(sc, osc), "level %d" % l
+    orb.close()
+
+
+@pytest.mark.parametrize("score", ["harris", "fast"])
+def test_kitti_pair_golden(golden_dir, score):
+    g = np.load(os.path.join(golden_dir, "kitti_pair.npz"))
+    big = g["canvas"]
+    frames = [np.ascontiguousarray(big[:376, :1241]), np.ascontiguousarray(big[3:, 7:])]
+    orb = _orb(2000, HARRIS_SCORE if score == "harris" else FAST_SCORE, (1241, 376))
+    for i, f in enumerate(frames):
+        # the reference's call order: detect, then compute (src/FeatureExtractor.cpp:17,19)
+        k = orb.detect(f)
+        assert_keypoints_equal(k, g[f"{score}_kp{i}"], "detect %s %d" % (score, i))
+        k2, d = orb.compute(f, k)
+        assert_keypoints_equal(k2, g[f"{score}_kp{i}"], "compute %s %d" % (score, i))
+        assert_descriptors_equal(d, g[f"{score}_desc{i}"], "compute %s %d" % (score, i))
+        k3, d3 = orb.detectAndCompute(f)
+        assert_keypoints_equal(k3, k2, "detectAndCompute")
+        assert_descriptors_equal(d3, d, "detectAndCompute")
+    orb.close()
+
+
+def test_hd_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hd_frames.npz"))
+    orb = _orb(2000, HARRIS_SCORE, (1920, 1080))
+    for seed in (1, 2):
+        img = syn.frame(seed, 1920, 1080)
+        k, d = orb.detectAndCompute(img)
+        if sha(img) == str(g[f"s{seed}_img_sha"]):
+            assert_keypoints_equal(k, g[f"s{seed}_kp"], "hd golden %d" % seed)
+            assert_descriptors_equal(d, g[f"s{seed}_desc"], "hd golden %d" % seed)
+        ok, od = oracle.detect_and_compute(img, oracle.Params(nfeatures=2000))
+        assert_keypoints_equal(k, ok, "hd oracle %d" % seed)
+        assert_descriptors_equal(d, od, "hd oracle %d" % seed)
+    orb.close()
+
+
+SMALL = ["tiny_97x71", "small_200x150", "odd_333x257", "thin_300x63", "flat_400x300", "checker_640x480", "textured_640x480"]
+
+
+@pytest.mark.parametrize("score", ["harris", "fast"])
+def test_small_frames_golden(golden_dir, score):
+    g = np.load(os.path.join(golden_dir, "small_frames.npz"))
+    orb = _orb(500, HARRIS_SCORE if score == "harris" else FAST_SCORE, (640, 480))
+    for name in SMALL:
+        k, d = orb.detectAndCompute(g[f"{name}_img"])
+        assert_keypoints_equal(k, g[f"{name}_{score}_kp"], name)
+        assert_descriptors_equal(d, g[f"{name}_{score}_desc"], name)
+    orb.close()
+
+
+def test_compute_border_keypoints_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "small_frames.npz"))
+    orb = _orb(700, HARRIS_SCORE, (800, 600))
+    k, d = orb.compute(g["border_img"], g["border_kp_in"])
+    assert_keypoints_equal(k, g["border_kp_out"], "border")
+    assert_descriptors_equal(d, g["border_desc"], "border")
+    orb.close()
+
+
+def test_4k_8000(golden_dir):
+    img = syn.frame(11, 3840, 2160)
+    orb = _orb(8000, HARRIS_SCORE, (3840, 2160))
+    k, d = orb.detectAndCompute(img)
+    ok, od = oracle.detect_and_compute(img, oracle.Params(nfeatures=8000))
+    assert_keypoints_equal(k, ok, "4k")
+    assert_descriptors_equal(d, od, "4k")
+    orb.close()
+
+
+def test_batch_equals_single():
+    seq = syn.sequence(6, 1241, 376, seed=5)
+    orb = _orb(2000, HARRIS_SCORE, (1241, 376), batch=6)
+    kps, desc, counts = orb.extract_batch(list(seq))
+    P = oracle.Params(nfeatures=2000)
+    for i in range(len(seq)):
+        ok, od = oracle.detect_and_compute(seq[i], P)
+        assert counts[i] == len(ok)
+        assert_keypoints_equal(kps[i, :counts[i]], ok, "batch frame %d" % i)
+        assert_descriptors_equal(desc[i, :counts[i]], od, "batch frame %d" % i)
+    # a strided view (row stride > width) must give the same result
+    wide = np.zeros((376, 1300), np.uint8)
+    wide[:, :1241] = seq[0]
+    k, d = orb.detectAndCompute(wide[:, :1241])
+    assert_keypoints_equal(k, kps[0, :counts[0]], "strided")
+    orb.close()
+
+
+def test_handle_reuse_across_sizes():
+    orb = _orb(500, HARRIS_SCORE, (800, 600))
+    P = oracle.Params(nfeatures=500)
+    for (w, h) in [(800, 600), (320, 240), (799, 451), (800, 600)]:
+        img = syn.frame(w, w, h)
+        k, d = orb.detectAndCompute(img)
+        ok, od = oracle.detect_and_compute(img, P)
+        assert_keypoints_equal(k, ok, "%dx%d" % (w, h))
+        assert_descriptors_equal(d, od, "%dx%d" % (w, h))
+    with pytest.raises(OrbxError):
+        orb.detect(syn.frame(1, 801, 600))
+    orb.close()
+
+
+def test_capacity_error_and_retry():
+    img = syn.frame(1, 640, 480)
+    orb = _orb(500, FAST_SCORE, (640, 480))
+    n = len(oracle.detect(img, oracle.Params(nfeatures=500, score_type=1)))
+    assert n > 500    # FAST_SCORE keeps ties
+    k = orb.detect(img, cap=n)
+    assert len(k) == n
+    k = orb.detect(img, cap=500)     # too small: the wrapper retries with the handle's maximum
+    assert len(k) == n
+    orb.close()
+
+
+def test_feature_extractor_node():
+    """FeatureExtractor::process fills Features exactly as src/FeatureExtractor.cpp:13-31 does."""
+    seq = syn.sequence(2, 640, 480, seed=9)
+    dm = DataManager(list(seq))
+    node = FeatureExtractor(nfeatures=500, max_size=(640, 480))
+    node.init()
+    for i in range(2):
+        assert node.validationCheck(dm, i)
+        node.process(dm, i)
+        ok, od = oracle.detect_and_compute(seq[i], oracle.Params(nfeatures=500))
+        f = dm.frames[i].features
+        assert np.array_equal(f.descriptors, od)
+        assert np.array_equal(f.positions, np.stack([ok["x"], ok["y"]], 1).astype(np.float64))
+        assert np.array_equal(f.scales, ok["size"].astype(np.float64))
+        assert (f.mapPointsIndices == -1).all() and len(f.mapPointsIndices) == len(ok)
+    node.destroy()
+
+
+def test_bad_arguments():
+    with pytest.raises(OrbxError):
+        ORB(nfeatures=500, edgeThreshold=19)
+    with pytest.raises(OrbxError):
+        ORB(nfeatures=-1)
+    orb = _orb(500, HARRIS_SCORE, (64, 64))
+    with pytest.raises(ValueError):
+        orb.detect(np.zeros((10, 10, 3), np.uint8))
+    k = orb.detect(np.zeros((64, 64), np.uint8))
+    assert len(k) == 0
+    orb.close()

@@ -1,0 +1,145 @@
+"""GPU parity: hamx_* (K6) through the C ABI against the oracle and the cv2 golden vectors -- bit-exact indices and
+distances, ties broken by lowest train index (reference src/CameraPoseEstimator.cpp:200-213)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import knn_arrays
+from monocular_slam_b200 import BFMatcher, DMATCH_DTYPE, TOP2_DTYPE, match_features
+from monocular_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+MATCH = ["planted", "dup_rows", "zeros", "nt1", "nt2", "low_entropy", "ragged_33x65"]
+
+
+@pytest.fixture(scope="module")
+def matcher():
+    m = BFMatcher()
+    yield m
+    m.close()
+
+
+def _check(matcher, q, t):
+    m, c = matcher.knnMatch(q, t, 2)
+    idx, dist = knn_arrays(m, c)
+    oi, od = oracle.knn2(q, t)
+    assert np.array_equal(idx, oi), "train indices differ"
+    assert np.array_equal(dist, od), "distances differ"
+    assert (m["query_idx"] == np.arange(len(q))[:, None]).all() and (m["img_idx"] == 0).all()
+    assert (c == min(len(t), 2)).all()
+    return oi, od
+
+
+@pytest.mark.parametrize("name", MATCH)
+def test_golden_cases(matcher, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "matcher_cases.npz"))
+    q, t = g[f"{name}_q"], g[f"{name}_t"]
+    m, c = matcher.knnMatch(q, t, 2)
+    idx, dist = knn_arrays(m, c)
+    assert np.array_equal(idx, g[f"{name}_idx"]) and np.array_equal(dist, g[f"{name}_dist"])
+    if len(t) >= 2:
+        for r in (0.75, 0.8, 0.85):
+            good = matcher.match_ratio(q, t, r)
+            got = np.stack([good["query_idx"], good["train_idx"], good["distance"].astype(np.int32)], 1).reshape(-1, 3)
+            assert np.array_equal(got, g[f"{name}_good_{int(r * 100)}"]), "ratio %.2f" % r
+
+
+@pytest.mark.parametrize("score", ["harris", "fast"])
+def test_golden_frame_pair(matcher, golden_dir, score):
+    g = np.load(os.path.join(golden_dir, "kitti_pair.npz"))
+    m, c = matcher.knnMatch(g[f"{score}_desc0"], g[f"{score}_desc1"], 2)
+    idx, dist = knn_arrays(m, c)
+    assert np.array_equal(idx, g[f"{score}_knn_idx"]) and np.array_equal(dist, g[f"{score}_knn_dist"])
+    good = match_features(g[f"{score}_desc0"], g[f"{score}_desc1"], 0.75)
+    got = np.stack([good["query_idx"], good["train_idx"], good["distance"].astype(np.int32)], 1)
+    assert np.array_equal(got, g[f"{score}_good_75"])
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (1, 2), (5, 3), (127, 128), (128, 129), (257, 1025), (2000, 2000), (2115, 2064),
+                                   (300, 70000), (40000, 513), (8000, 8000)])
+def test_random_sizes(matcher, nq, nt):
+    _check(matcher, syn.descriptors(nq * 7 + 1, nq), syn.descriptors(nt * 3 + 2, nt))
+
+
+def test_heavy_ties(matcher):
+    rng = np.random.default_rng(3)
+    base = (rng.integers(0, 2, (8, 32)) * 255).astype(np.uint8)
+    t = base[rng.integers(0, 8, 5000)]
+    q = base[rng.integers(0, 8, 700)]
+    _check(matcher, q, t)
+
+
+def test_empty(matcher):
+    m, c = matcher.knnMatch(np.zeros((0, 32), np.uint8), syn.descriptors(1, 10), 2)
+    assert m.shape == (0, 2)
+    m, c = matcher.knnMatch(syn.descriptors(1, 10), np.zeros((0, 32), np.uint8), 2)
+    assert (c == 0).all() and (m["train_idx"] == -1).all()
+    assert len(matcher.match_ratio(syn.descriptors(1, 10), np.zeros((0, 32), np.uint8), 0.8)) == 0
+    assert len(matcher.match_ratio(syn.descriptors(1, 10), syn.descriptors(2, 1), 0.8)) == 0
+
+
+def test_rejects_bad_shapes(matcher):
+    with pytest.raises(ValueError):
+        matcher.knnMatch(np.zeros((4, 16), np.uint8), np.zeros((4, 32), np.uint8), 2)
+    with pytest.raises(ValueError):
+        BFMatcher(normType=4)
+
+
+def test_sharded_merge_equals_single(matcher):
+    """Train set cut into shards, per-shard top-2 with global offsets, merged: identical to one pass."""
+    import torch
+    t = syn.descriptors(11, 20000)
+    t[5000:5010] = t[100:110]        # duplicates across shard boundaries exercise the tie rule in the merge
+    q = syn.planted_queries(12, t, 3000)
+    oi, od = oracle.knn2(q, t)
+    dq = torch.from_numpy(q).cuda()
+    nparts = 8
+    bounds = np.linspace(0, len(t), nparts + 1).astype(int)
+    parts = torch.empty((nparts, len(q), 4), dtype=torch.int32, device="cuda")
+    shards = [torch.from_numpy(t[bounds[i]:bounds[i + 1]]).cuda() for i in range(nparts)]
+    matcher.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        for i in range(nparts):
+            matcher.knn2_dev(dq.data_ptr(), len(q), shards[i].data_ptr(), len(shards[i]), int(bounds[i]), parts[i].data_ptr())
+        out = torch.empty((len(q), 4), dtype=torch.int32, device="cuda")
+        matcher.merge_top2_dev(parts.data_ptr(), nparts, len(q), out.data_ptr())
+        good = torch.empty((len(q), 4), dtype=torch.int32, device="cuda")
+        ngood = torch.zeros(1, dtype=torch.int64, device="cuda")
+        matcher.ratio_dev(out.data_ptr(), len(q), 0.75, good.data_ptr(), ngood.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        matcher.set_stream(None)
+    r = out.cpu().numpy()
+    assert np.array_equal(r[:, [1, 3]], oi) and np.array_equal(r[:, [0, 2]], od)
+    gq, gt, gd = oracle.ratio_test(oi, od, 0.75)
+    n = int(ngood.item())
+    gm = good.cpu().numpy()[:n].copy().view(DMATCH_DTYPE).reshape(-1)
+    assert n == len(gq) and np.array_equal(gm["query_idx"], gq) and np.array_equal(gm["train_idx"], gt)
+    assert np.array_equal(gm["distance"].astype(np.int32), gd)
+
+
+def test_large_sampled(matcher):
+    """200k x 2000 (BASELINE config 4 shape): all queries checked against the oracle on the full train set."""
+    t = syn.descriptors(4, 200000)
+    q = syn.planted_queries(5, t, 2000)
+    _check(matcher, q, t)
+
+
+def test_large_properties(matcher):
+    """A size the oracle cannot sweep in seconds: 60k x 300k.  Checked through properties: sampled rows against the
+    oracle, d0 <= d1, indices in range, and invariance of the result to reversing the query order."""
+    t = syn.descriptors(6, 300000)
+    q = syn.descriptors(7, 60000)
+    m, c = matcher.knnMatch(q, t, 2)
+    idx, dist = knn_arrays(m, c)
+    assert (dist[:, 0] <= dist[:, 1]).all() and (idx >= 0).all() and (idx < len(t)).all()
+    assert ((dist[:, 0] < dist[:, 1]) | (idx[:, 0] < idx[:, 1])).all()
+    sample = np.random.default_rng(0).choice(len(q), 200, replace=False)
+    oi, od = oracle.knn2(q[sample], t)
+    assert np.array_equal(idx[sample], oi) and np.array_equal(dist[sample], od)
+    m2, c2 = matcher.knnMatch(q[::-1], t, 2)
+    i2, d2 = knn_arrays(m2, c2)
+    assert np.array_equal(i2[::-1], idx) and np.array_equal(d2[::-1], dist)

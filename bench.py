@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py -- ORB extract+match frames/s @1080p / 2000 kp (BASELINE.json metric), plus Hamming Gcmp/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference [...]                          # the reference's CPU path on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic frames: ORB extraction (pyramid, FAST+NMS, retention,
+Harris, orientation, rBRIEF) of every frame and matchFeatures(frame i, frame i-1, ratio 0.75) for consecutive frames.
+`value` is timed with the frames resident in HBM; `e2e` goes through the host-buffer C ABI (pinned host frames in,
+keypoints / descriptors / matches back in host memory) with the copies inside the timed region.  Under torchrun every
+rank extracts and matches its own block of frames (frame sharding, no collective: weak scaling); the secondary Hamming
+measurement shards the train set over the ranks and merges per-query top-2 after one all-gather.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ORB extract+match frames/s @1080p 2k kp; Hamming Gcmp/s at 1/2/4/8 GPUs"
+W, H, NFEAT, RATIO = 1920, 1080, 2000, 0.75
+HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml, else nvidia-smi)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "note": "no samples (nvml unavailable)"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference path
+_W = {}
+
+
+def _cpu_worker_init(seed, nframes, w, h, nfeat, use_cv2):
+    """Runs in a worker process: build this worker's own frames (no big pickles) and its extractor."""
+    from monocular_slam_b200 import synthetic as syn
+    _W["frames"] = syn.sequence(nframes, w, h, seed=seed)
+    _W["use_cv2"] = use_cv2
+    if use_cv2:
+        import cv2
+        cv2.setNumThreads(1)
+        _W["cv2"] = cv2
+        _W["orb"] = cv2.ORB_create(nfeatures=nfeat)
+        _W["bf"] = cv2.BFMatcher(cv2.NORM_HAMMING, False)
+    else:
+        import oracle
+        _W["oracle"] = oracle
+        _W["params"] = oracle.Params(nfeatures=nfeat)
+    _W["prev"] = None
+    return True
+
+
+def _cpu_worker_step(_):
+    """One bounded sample: extract every frame of the worker's block and match it against its predecessor, exactly in
+    the reference's call order (detect, compute: src/FeatureExtractor.cpp:17,19; knnMatch k=2 + ratio:
+    src/CameraPoseEstimator.cpp:200-213)."""
+    t0 = time.perf_counter()
+    for img in _W["frames"]:
+        if _W["use_cv2"]:
+            kp = _W["orb"].detect(img, None)
+            kp, des = _W["orb"].compute(img, kp)
+            if _W["prev"] is not None and des is not None:
+                raw = _W["bf"].knnMatch(des, _W["prev"], 2)
+                _W["good"] = [r[0] for r in raw if len(r) == 2 and r[0].distance < r[1].distance * np.float32(RATIO)]
+            _W["prev"] = des
+        else:
+            kp, des = _W["oracle"].detect_and_compute(img, _W["params"])
+            if _W["prev"] is not None:
+                _W["oracle"].match_features(des, _W["prev"], RATIO)
+            _W["prev"] = des
+    return len(_W["frames"]), time.perf_counter() - t0
+
+
+class CpuReference:
+    """The reference's CPU extract+match path on all host cores: one process per core, each running OpenCV's ORB /
+    BFMatcher single-threaded (cv2 is the library the reference calls; if it cannot be imported the C oracle port is
+    timed instead and `kind` says "port")."""
+
+    def __init__(self, frames_per_worker=2, max_workers=128):
+        import multiprocessing as mp
+        try:
+            import cv2  # noqa: F401
+            self.use_cv2 = True
+        except Exception:
+            self.use_cv2 = False
+            import oracle
+            oracle.build()
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except Exception:
+            ncpu = os.cpu_count() or 1
+        self.workers = max(1, min(ncpu, max_workers))
+        self.frames_per_worker = frames_per_worker
+        ctx = mp.get_context("spawn")
+        self.pools = []
+        # one single-process pool per worker so that each keeps its own frames and every step reaches every worker
+        for i in range(self.workers):
+            self.pools.append(ctx.Pool(1, initializer=_cpu_worker_init, initargs=(1000 + i, frames_per_worker, W, H, NFEAT, self.use_cv2)))
+        for p in self.pools:
+            p.apply(_cpu_worker_step, (0,))   # first touch: imports, page-in, first matches
+
+    def step(self):
+        t0 = time.perf_counter()
+        res = [p.apply_async(_cpu_worker_step, (0,)) for p in self.pools]
+        n = sum(r.get()[0] for r in res)
+        return n, time.perf_counter() - t0
+
+    def close(self):
+        for p in self.pools:
+            p.terminate()
+
+    def describe(self):
+        return {"kind": "reference" if self.use_cv2 else "port", "cores": self.workers,
+                "sample": "%d frames of %dx%d per step (%d per worker process, %s single-threaded per process), detect+compute+knnMatch(k=2)+ratio %.2f against the previous frame"
+                          % (self.workers * self.frames_per_worker, W, H, self.frames_per_worker,
+                             "cv2 %s ORB/BFMatcher" % __import__("cv2").__version__ if self.use_cv2 else "oracle/orb_oracle.c", RATIO)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ref = CpuReference(frames_per_worker=2)
+    for _ in range(args.warmup):
+        ref.step()
+    frames, elapsed = 0, 0.0
+    for _ in range(args.steps):
+        n, dt = ref.step()
+        frames += n
+        elapsed += dt
+    ref.close()
+    value = frames / elapsed
+    d = ref.describe()
+    d["value"] = value
+    d["unit"] = "frames/s"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "synthetic 1920x1080 monocular sequence, 2000 kp/frame, consecutive-frame matching (BASELINE.json configs[1]), CPU",
+                       "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "ratio": RATIO, "frames_per_step": frames // args.steps},
+            "cpu_baseline": d,
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU path
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from monocular_slam_b200 import ORB, BFMatcher, DMATCH_DTYPE, KEYPOINT_DTYPE, popc_peak
+    from monocular_slam_b200 import synthetic as syn
+    from monocular_slam_b200.sharded import ShardedMatcher, shard_bounds
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.batch
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    # every rank owns its own block of the sequence (frame sharding): B consecutive frames, seeded by rank
+    seq = syn.sequence(B, W, H, seed=100 + rank)
+    h_frames = torch.from_numpy(seq).pin_memory()
+    d_frames = h_frames.to(dev, non_blocking=True)
+    orb = ORB(nfeatures=NFEAT, max_size=(W, H), max_batch=B, device=local_rank)
+    matcher = BFMatcher(device=local_rank)
+    orb.set_stream(stream.cuda_stream)
+    matcher.set_stream(stream.cuda_stream)
+    cap = orb.default_cap
+    d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_good = torch.empty((B, cap, 4), dtype=torch.int32, device=dev)
+    d_ngood = torch.zeros(B, dtype=torch.int64, device=dev)
+    d_prev = torch.zeros((cap, 32), dtype=torch.uint8, device=dev)
+    d_prevn = torch.zeros(1, dtype=torch.int32, device=dev)
+    state = {"have_prev": False}
+
+    def step_device():
+        orb.extract_batch_dev(d_frames.data_ptr(), W * H, B, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
+        matcher.match_consecutive_dev(d_desc.data_ptr(), d_cnt.data_ptr(), B, cap,
+                                      d_prev.data_ptr() if state["have_prev"] else 0, d_prevn.data_ptr() if state["have_prev"] else 0,
+                                      RATIO, d_good.data_ptr(), d_ngood.data_ptr())
+        d_prev.copy_(d_desc[B - 1], non_blocking=True)
+        d_prevn.copy_(d_cnt[B - 1:B], non_blocking=True)
+        state["have_prev"] = True
+
+    # host-buffer path: pinned buffers for everything that crosses PCIe
+    h_kps = torch.empty((B, cap, 7), dtype=torch.float32).pin_memory()
+    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
+    h_cnt = np.zeros(B, np.int32)
+    h_good = torch.empty((B, cap, 4), dtype=torch.int32).pin_memory()
+    h_ngood = np.zeros(B, np.int64)
+    kps_np = h_kps.numpy().view(KEYPOINT_DTYPE).reshape(B, cap)
+    desc_np = h_desc.numpy()
+    good_np = h_good.numpy().view(DMATCH_DTYPE).reshape(B, cap)
+    frames_np = [h_frames[i].numpy() for i in range(B)]
+
+    def step_host():
+        orb.extract_batch(frames_np, cap=cap, out=(kps_np, desc_np, h_cnt))
+        orb.match_consecutive(matcher, RATIO, cap, B, out=(good_np, h_ngood))
+
+    def timed(step, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.__enter__()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if sampler:
+            sampler.__exit__()
+        barrier()
+        return e0.elapsed_time(e1), wall * 1e3
+
+    # ---- headline: device-resident
+    sampler = ClockSampler(local_rank)
+    orb.set_profiling(True)
+    for _ in range(args.warmup):
+        step_device()
+    orb.read_profile()     # drop the warm-up batches
+    dev_ms, _ = timed(step_device, args.steps, 0, sampler)
+    stages, nb = orb.read_profile()
+    orb.set_profiling(False)
+    orb.check_dev()
+    dev_ms = max_over_ranks(dev_ms)
+    counts = d_cnt.cpu().numpy()
+    ngood_dev = d_ngood.cpu().numpy()
+    value = world * B * args.steps / (dev_ms * 1e-3)
+
+    # matching kernels alone (same stream, CUDA events)
+    def step_match():
+        matcher.match_consecutive_dev(d_desc.data_ptr(), d_cnt.data_ptr(), B, cap, d_prev.data_ptr(), d_prevn.data_ptr(), RATIO,
+                                      d_good.data_ptr(), d_ngood.data_ptr())
+    match_ms, _ = timed(step_match, args.steps, 2)
+    match_ms /= args.steps
+
+    # ---- end to end through host buffers
+    orb.reset_sequence()
+    _, e2e_wall_ms = timed(step_host, args.steps, max(args.warmup, 1))
+    e2e_ms = max_over_ranks(e2e_wall_ms)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    h2d = B * W * H
+    d2h = int(h_cnt.sum()) * (28 + 32) + B * cap * 16 + B * (8 + 4) + B * 2200   # keypoints+descriptors, match lists, counts, counters
+    # parity of the two paths inside the bench: same counts, same number of accepted matches
+    assert np.array_equal(h_cnt, counts), "host and device paths disagree on keypoint counts"
+    assert np.array_equal(h_ngood[1:], ngood_dev[1:]), "host and device paths disagree on match counts"
+
+    # ---- roofline of the dominant kernel (FAST): algorithmic bytes = every level pixel read once
+    ws, hs, _, _ = orb.level_info(W, H)
+    level_px = int((ws.astype(np.int64) * hs).sum())
+    peak, peak_src = hbm_peak()
+    fast_ms = stages["fast"]
+    achieved = level_px * B / (fast_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "fast_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "k_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "launch_ms": fast_ms,
+                "algorithmic_bytes_per_launch": level_px * B,
+                "note": "FAST reads each pyramid-level byte once (3.096 x W x H per frame); it is integer-issue bound, not HBM bound"}
+
+    # ---- secondary metric: train-sharded Hamming kNN2, Gcmp/s over all ranks
+    hamming = None
+    if not args.no_hamming:
+        nq, nt_shard = args.ham_nq, args.ham_nt
+        gq = torch.Generator(device=dev); gq.manual_seed(7)
+        q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=gq)
+        gt = torch.Generator(device=dev); gt.manual_seed(60 + rank)
+        t_shard = torch.randint(0, 256, (nt_shard, 32), dtype=torch.uint8, device=dev, generator=gt)
+        sm = ShardedMatcher(matcher)
+        out = {}
+
+        def step_ham():
+            out["r"] = sm.knn2(q, t_shard, rank * nt_shard)
+        ham_steps = max(2, min(args.steps, 3))
+        ham_ms, _ = timed(step_ham, ham_steps, 1)
+        ham_ms = max_over_ranks(ham_ms) / ham_steps
+        gpopc, _ = popc_peak(local_rank)
+        gcmp = world * nq * nt_shard / (ham_ms * 1e-3) / 1e9
+        hamming = {"value": gcmp, "unit": "Gcmp/s", "nq": nq, "nt_per_gpu": nt_shard, "ms_per_step": ham_ms,
+                   "workload": "%d queries x %d train rows per GPU (train-sharded, 1 all-gather of 16 B/query/rank + merge)" % (nq, nt_shard),
+                   "roofline": {"bound": "int_popc", "achieved": gcmp * 8, "peak": gpopc * world, "unit": "Gpopc/s",
+                                "frac": gcmp * 8 / (gpopc * world),
+                                "note": "8 POPC per 256-bit comparison; peak = register-only POPC microbenchmark (hamx_popc_peak) per GPU x n_gpus"}}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            ref = CpuReference(frames_per_worker=2)
+            ref.step()
+            n, dt = 0, 0.0
+            for _ in range(2):
+                a, b = ref.step()
+                n += a
+                dt += b
+            ref.close()
+            cpu = ref.describe()
+            cpu.update({"value": n / dt, "unit": "frames/s"})
+        except Exception as e:   # the baseline is reporting only; never fail the GPU measurement for it
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+    clocks = sampler.summary()
+    launches_per_step = (len(ws) - 1) + 4 + 3    # 7 pyramid levels, FAST, select, Harris+select, orient+describe, pair table, kNN2, ratio
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic",
+                "config": {"workload": "synthetic 1920x1080 monocular sequence, 2000 kp/frame, consecutive-frame matching, ratio 0.75 (BASELINE.json configs[1])",
+                           "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "nlevels": 8, "scale_factor": 1.2, "score_type": "HARRIS",
+                           "batch_frames_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+                           "l2": "inputs larger than L2: %d frames x %.1f MB = %.0f MB of frames (+%.0f MB of pyramid levels) per step vs 126 MB L2"
+                                 % (B, W * H / 1e6, B * W * H / 1e6, B * (level_px - W * H) / 1e6),
+                           "keypoints_per_frame": float(counts.mean()), "matches_per_frame": float(ngood_dev[1:].mean())},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / args.steps, "timing": "host wall clock around blocking C-ABI calls, max over ranks"},
+                "gpu_launches": launches_per_step * args.steps,
+                "roofline": roofline,
+                "stages_ms_per_step": dict(stages, match=match_ms),
+                "cpu_baseline": cpu,
+                "hamming": hamming}
+        print(json.dumps(line), flush=True)
+    matcher.close()
+    orb.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU and step")
+    ap.add_argument("--ham-nq", type=int, default=1 << 20)
+    ap.add_argument("--ham-nt", type=int, default=125000, help="train rows per GPU")
+    ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        print("bench.py: --gpus %d needs torchrun (one process per GPU); running 1 GPU" % args.gpus, file=sys.stderr)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,8 @@ typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } 
 typedef struct { int32_t query_idx, train_idx, img_idx; float distance; } orbx_dmatch;
 /* per-query best two neighbours; absent entries have idx = -1, dist = -1 */
 typedef struct { int32_t dist0, idx0, dist1, idx1; } hamx_top2;
+/* one (query set, train set) problem of a batched launch; q and t are DEVICE pointers, 16-byte aligned */
+typedef struct { const uint8_t* q; const uint8_t* t; int32_t nq, nt; } hamx_pair;
 
 #define ORBX_HARRIS_SCORE 0
 #define ORBX_FAST_SCORE 1
@@ -116,6 +118,18 @@ ORBX_API int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, size
 /* Synchronises and returns ORBX_E_CAPACITY if any _dev call since the last check overflowed a list. */
 ORBX_API int orbx_check_dev(orbx_handle h);
 
+/* Sequence mode on host buffers: match every frame of the batch last extracted with orbx_extract_batch against its
+ * predecessor (frame 0 against the last frame of the previous batch; orbx_reset_sequence forgets it) without moving
+ * the descriptors back to the device.  good is [nframes][cap] with the cap of that extract call, ngood [nframes]. */
+ORBX_API int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, orbx_dmatch* good, int64_t* ngood);
+ORBX_API int orbx_reset_sequence(orbx_handle h);
+
+/* Per-stage device times (CUDA events on the handle's stream around each stage of every batch while enabled).
+ * stage_ms receives ORBX_NSTAGES averages per batch: pyramid, FAST, FAST-score cut, Harris+selection, orient+describe. */
+#define ORBX_NSTAGES 5
+ORBX_API int orbx_set_profiling(orbx_handle h, int enabled);
+ORBX_API int orbx_read_profile(orbx_handle h, float* stage_ms, int* nbatches);
+
 /* Stage-level taps for parity tests and profiling (device work + copy back). */
 ORBX_API int orbx_debug_pyramid_level(orbx_handle h, const uint8_t* gray, int w, int h_, size_t stride, int level, uint8_t* out);
 ORBX_API int orbx_debug_fast_level(orbx_handle h, const uint8_t* gray, int w, int h_, size_t stride, int level,
@@ -143,6 +157,19 @@ ORBX_API int hamx_knn2_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const 
 ORBX_API int hamx_merge_top2_dev(hamx_handle h, const hamx_top2* d_parts, int nparts, int64_t nq, hamx_top2* d_out);
 /* Ratio test + ordered compaction: d_good gets the accepted matches, *d_ngood their number. */
 ORBX_API int hamx_ratio_dev(hamx_handle h, const hamx_top2* d_top2, int64_t nq, float ratio, orbx_dmatch* d_good, int64_t* d_ngood);
+
+/* npairs independent matchFeatures() problems in one launch (d_pairs is a device-resident table; max_nq / max_nt bound
+ * the pairs' sizes).  Pair p writes its accepted matches to d_good + p*good_stride and their number to d_ngood[p]. */
+ORBX_API int hamx_match_pairs_dev(hamx_handle h, const hamx_pair* d_pairs, int npairs, int max_nq, int max_nt, float ratio,
+                         orbx_dmatch* d_good, size_t good_stride, int64_t* d_ngood);
+
+/* Consecutive-frame matching of a batch that orbx_extract_batch_dev left on the device (descriptors [nframes][cap][32],
+ * counts [nframes]): frame f is the query set, frame f-1 the train set -- matchFeatures(desc_cur, desc_prev) of
+ * src/CameraPoseEstimator.cpp:409; frame 0 is matched against d_prev_desc / *d_prev_count (the last frame of the
+ * previous batch) or, when those are NULL, yields no matches.  d_good is [nframes][cap], d_ngood [nframes]. */
+ORBX_API int hamx_match_consecutive_dev(hamx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap,
+                               const uint8_t* d_prev_desc, const int32_t* d_prev_count, float ratio,
+                               orbx_dmatch* d_good, int64_t* d_ngood);
 
 /* Register-only popcount microbenchmark: the measured integer-pipe peak used as the matcher's roofline denominator.
  * gpopc_per_s = 32-bit POPC results per second / 1e9, over the whole device. */

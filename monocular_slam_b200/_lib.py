@@ -25,8 +25,11 @@ SYMBOLS = [
     "orbx_detect_and_compute", "orbx_extract_batch", "orbx_extract_batch_dev", "orbx_check_dev",
     "orbx_debug_pyramid_level", "orbx_debug_fast_level", "hamx_create", "hamx_destroy", "hamx_set_stream",
     "hamx_synchronize", "hamx_knn2", "hamx_match_ratio", "hamx_knn2_dev", "hamx_merge_top2_dev", "hamx_ratio_dev",
-    "hamx_popc_peak",
+    "hamx_popc_peak", "hamx_match_pairs_dev", "hamx_match_consecutive_dev", "orbx_match_consecutive", "orbx_reset_sequence",
+    "orbx_set_profiling", "orbx_read_profile",
 ]
+NSTAGES = 5
+STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
 
 
 class OrbxError(RuntimeError):
@@ -101,6 +104,12 @@ def lib():
     L.hamx_merge_top2_dev.argtypes = [vp, vp, C.c_int, C.c_int64, vp]
     L.hamx_ratio_dev.argtypes = [vp, vp, C.c_int64, C.c_float, vp, vp]
     L.hamx_popc_peak.argtypes = [C.c_int, dp, dp]
+    L.hamx_match_pairs_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_size_t, vp]
+    L.hamx_match_consecutive_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_float, vp, vp]
+    L.orbx_match_consecutive.argtypes = [vp, vp, C.c_float, vp, i64p]
+    L.orbx_reset_sequence.argtypes = [vp]
+    L.orbx_set_profiling.argtypes = [vp, C.c_int]
+    L.orbx_read_profile.argtypes = [vp, fp, ip]
     _lib = L
     return L
 

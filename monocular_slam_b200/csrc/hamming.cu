@@ -84,22 +84,35 @@ __device__ __forceinline__ hamx_top2 decode_top2(uint32_t k0, uint32_t k1, int64
     return r;
 }
 
-// grid = (query blocks, train splits).  partial is [nsplit][nq] (only touched when nsplit > 1); the last CTA of a
-// query block to finish merges the splits, so one launch yields final results.
+// grid = (query blocks, train splits, pairs).  partial is [pair][nsplit][nq_stride] (only touched when nsplit > 1); the
+// last CTA of a query block to finish merges the splits, so one launch yields final results.  With `pairs` == NULL the
+// launch handles the single problem `one`; otherwise pair blockIdx.z of a device-resident table (batched matching of
+// many small frame pairs in one launch).
 __global__ void __launch_bounds__(HT_THREADS)
-k_hamming_knn2(const uint4* __restrict__ q, int64_t nq, const uint4* __restrict__ t, int nt, int tiles_per_split,
-               uint2* partial, unsigned int* arrivals, hamx_top2* __restrict__ out, int64_t idx_offset)
+k_hamming_knn2(const hamx_pair one, const hamx_pair* __restrict__ pairs, int tiles_per_split, uint2* partial,
+               size_t nq_stride, unsigned int* arrivals, int qblocks_stride, hamx_top2* __restrict__ out_base,
+               size_t out_stride, int64_t idx_offset)
 {
     __shared__ __align__(128) uint4 s_tile[HT_STAGES][HT_TT * 2];
     __shared__ __align__(8) uint64_t s_full[HT_STAGES];
     __shared__ int s_last;
+
+    const hamx_pair pd = pairs ? pairs[blockIdx.z] : one;
+    const int64_t nq = pd.nq;
+    const int nt = pd.nt;
+    if ((int64_t)blockIdx.x * HT_QB >= nq) return;   // batched launches are sized for the largest pair
+    const uint4* __restrict__ q = reinterpret_cast<const uint4*>(pd.q);
+    const uint4* __restrict__ t = reinterpret_cast<const uint4*>(pd.t);
+    hamx_top2* __restrict__ out = out_base + (size_t)blockIdx.z * out_stride;
+    partial += (size_t)blockIdx.z * gridDim.y * nq_stride;
+    arrivals += (size_t)blockIdx.z * qblocks_stride;
 
     const int tid = threadIdx.x;
     const int nsplit = gridDim.y;
     const int ntiles_all = (nt + HT_TT - 1) / HT_TT;
     const int tile_begin = blockIdx.y * tiles_per_split;
     const int tile_end = min(tile_begin + tiles_per_split, ntiles_all);
-    const int ntiles = tile_end - tile_begin;
+    const int ntiles = max(tile_end - tile_begin, 0);
 
     if (tid == 0) {
         for (int s = 0; s < HT_STAGES; s++) mbar_init(&s_full[s], 1);
@@ -172,7 +185,7 @@ k_hamming_knn2(const uint4* __restrict__ q, int64_t nq, const uint4* __restrict_
 
 #pragma unroll
     for (int k = 0; k < HT_QPT; k++)
-        if (qi[k] < nq) __stcg(&partial[(size_t)blockIdx.y * nq + qi[k]], make_uint2(b0[k], b1[k]));
+        if (qi[k] < nq) __stcg(&partial[(size_t)blockIdx.y * nq_stride + qi[k]], make_uint2(b0[k], b1[k]));
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -187,7 +200,7 @@ k_hamming_knn2(const uint4* __restrict__ q, int64_t nq, const uint4* __restrict_
         if (qi[k] >= nq) continue;
         uint32_t m0 = HT_NONE, m1 = HT_NONE;
         for (int s = 0; s < nsplit; s++) {
-            uint2 p = __ldcg(&partial[(size_t)s * nq + qi[k]]);
+            uint2 p = __ldcg(&partial[(size_t)s * nq_stride + qi[k]]);
             top2_insert(m0, m1, p.x);
             top2_insert(m0, m1, p.y);
         }
@@ -242,9 +255,15 @@ __global__ void k_top2_to_dmatch(const hamx_top2* __restrict__ top2, int64_t nq,
 
 // Lowe ratio (src/CameraPoseEstimator.cpp:208-212: float multiply, strict <) + order-preserving compaction.
 // One CTA walks the queries in chunks of 1024 so the accepted list stays in ascending query order.
-__global__ void __launch_bounds__(1024) k_ratio_compact(const hamx_top2* __restrict__ top2, int64_t nq, float ratio,
-                                                        orbx_dmatch* __restrict__ good, long long* __restrict__ ngood)
+__global__ void __launch_bounds__(1024) k_ratio_compact(const hamx_top2* __restrict__ top2_base, size_t top2_stride, int64_t nq_one,
+                                                        const hamx_pair* __restrict__ pairs, float ratio,
+                                                        orbx_dmatch* __restrict__ good_base, size_t good_stride,
+                                                        long long* __restrict__ ngood_base)
 {
+    const hamx_top2* __restrict__ top2 = top2_base + (size_t)blockIdx.x * top2_stride;
+    orbx_dmatch* __restrict__ good = good_base + (size_t)blockIdx.x * good_stride;
+    long long* __restrict__ ngood = ngood_base + blockIdx.x;
+    const int64_t nq = pairs ? pairs[blockIdx.x].nq : nq_one;
     __shared__ int s_warp[32];
     __shared__ long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -278,6 +297,30 @@ __global__ void __launch_bounds__(1024) k_ratio_compact(const hamx_top2* __restr
         __syncthreads();
     }
     if (tid == 0) *ngood = s_base;
+}
+
+// Pair table for consecutive-frame matching of a batch: frame f (query) against frame f-1 (train); frame 0 against the
+// last frame of the previous batch if there is one.  Counts live on the device, so no host round trip is needed.
+__global__ void k_build_consecutive_pairs(const uint8_t* desc, const int32_t* counts, int nframes, int cap,
+                                          const uint8_t* prev_desc, const int32_t* prev_count, hamx_pair* pairs)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    hamx_pair p;
+    p.q = desc + (size_t)f * cap * 32;
+    p.nq = min(counts[f], cap);
+    if (f > 0) {
+        p.t = desc + (size_t)(f - 1) * cap * 32;
+        p.nt = min(counts[f - 1], cap);
+    } else if (prev_desc) {
+        p.t = prev_desc;
+        p.nt = min(*prev_count, cap);
+    } else {
+        p.t = desc;
+        p.nt = 0;
+        p.nq = 0;   // the very first frame of a sequence has nothing to match against
+    }
+    pairs[f] = p;
 }
 
 // Register-only POPC throughput probe: 8 independent POPC + 8 XOR per iteration and thread, like the matcher's inner
@@ -318,6 +361,7 @@ struct hamx_context {
     orbx_dmatch* d_dm; size_t dm_bytes;
     int32_t* d_counts; size_t counts_bytes;
     long long* d_ngood;
+    hamx_pair* d_pairs; size_t pairs_bytes;
     int sm_count;
 };
 
@@ -359,7 +403,7 @@ extern "C" int hamx_destroy(hamx_handle h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_partial); cudaFree(h->d_arrivals); cudaFree(h->d_top2);
-    cudaFree(h->d_parts); cudaFree(h->d_dm); cudaFree(h->d_counts); cudaFree(h->d_ngood);
+    cudaFree(h->d_parts); cudaFree(h->d_dm); cudaFree(h->d_counts); cudaFree(h->d_ngood); cudaFree(h->d_pairs);
     cudaStreamDestroy(h->own_stream);
     delete h;
     return ORBX_OK;
@@ -387,27 +431,91 @@ static int fill_absent(hamx_handle h, hamx_top2* d_out, int64_t nq)
     return ORBX_OK;
 }
 
+static void plan_split(int sm_count, int64_t nqb, int ntiles, int64_t npairs, int* nsplit_out, int* tps_out)
+{
+    const int64_t target = (int64_t)sm_count * 8;
+    int64_t nsplit = nqb * npairs >= target ? 1 : (target + nqb * npairs - 1) / (nqb * npairs);
+    if (nsplit > ntiles) nsplit = ntiles;
+    if (nsplit > 65535) nsplit = 65535;
+    if (nsplit < 1) nsplit = 1;
+    int tps = (int)((ntiles + nsplit - 1) / nsplit);
+    if (tps < 1) tps = 1;
+    nsplit = (ntiles + tps - 1) / tps;
+    if (nsplit < 1) nsplit = 1;
+    *nsplit_out = (int)nsplit;
+    *tps_out = tps;
+}
+
 static int launch_chunk(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int nt, int64_t offset, hamx_top2* d_out)
 {
     const int64_t nqb = (nq + HT_QB - 1) / HT_QB;
     const int ntiles = (nt + HT_TT - 1) / HT_TT;
-    const int64_t target = (int64_t)h->sm_count * 8;
-    int64_t nsplit = nqb >= target ? 1 : (target + nqb - 1) / nqb;
-    if (nsplit > ntiles) nsplit = ntiles;
-    if (nsplit > 65535) nsplit = 65535;
-    int tps = (int)((ntiles + nsplit - 1) / nsplit);
-    nsplit = (ntiles + tps - 1) / tps;
+    int nsplit, tps;
+    plan_split(h->sm_count, nqb, ntiles, 1, &nsplit, &tps);
     if (nsplit > 1) {
         int rc = grow(&h->d_partial, &h->partial_bytes, (size_t)nsplit * nq * sizeof(uint2));
         if (rc) return rc;
         rc = grow(&h->d_arrivals, &h->arrivals_n, (size_t)nqb * sizeof(unsigned int), true, h->stream);
         if (rc) return rc;
     }
-    dim3 grid((unsigned int)nqb, (unsigned int)nsplit);
-    k_hamming_knn2<<<grid, HT_THREADS, 0, h->stream>>>((const uint4*)d_q, nq, (const uint4*)d_t, nt, tps, h->d_partial,
-                                                        h->d_arrivals, d_out, offset);
+    hamx_pair one;
+    one.q = d_q; one.t = d_t; one.nq = (int32_t)nq; one.nt = nt;
+    dim3 grid((unsigned int)nqb, (unsigned int)nsplit, 1);
+    k_hamming_knn2<<<grid, HT_THREADS, 0, h->stream>>>(one, nullptr, tps, h->d_partial, (size_t)nq, h->d_arrivals, (int)nqb, d_out, 0,
+                                                        offset);
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
+}
+
+// Many small (query, train) pairs in one launch: consecutive-frame matching of a whole batch of frames.
+extern "C" int hamx_match_pairs_dev(hamx_handle h, const hamx_pair* d_pairs, int npairs, int max_nq, int max_nt, float ratio,
+                                    orbx_dmatch* d_good, size_t good_stride, int64_t* d_ngood)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_match_pairs_dev: NULL handle");
+    ORBX_REQUIRE(npairs >= 0 && max_nq >= 0 && max_nt >= 0 && max_nt <= (1 << HT_IDX_BITS), "hamx_match_pairs_dev: bad sizes");
+    if (npairs == 0) return ORBX_OK;
+    ORBX_REQUIRE(d_pairs && d_good && d_ngood && good_stride >= (size_t)max_nq, "hamx_match_pairs_dev: bad pointers or stride");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    if (max_nq == 0) { ORBX_CUDA(cudaMemsetAsync(d_ngood, 0, (size_t)npairs * sizeof(int64_t), h->stream)); return ORBX_OK; }
+    const int64_t nqb = (max_nq + HT_QB - 1) / HT_QB;
+    const int ntiles = max_nt > 0 ? (max_nt + HT_TT - 1) / HT_TT : 1;
+    int nsplit, tps;
+    plan_split(h->sm_count, nqb, ntiles, npairs, &nsplit, &tps);
+    int rc = grow(&h->d_top2, &h->top2_bytes, (size_t)npairs * max_nq * sizeof(hamx_top2) + 16);
+    if (rc) return rc;
+    if (nsplit > 1) {
+        rc = grow(&h->d_partial, &h->partial_bytes, (size_t)npairs * nsplit * max_nq * sizeof(uint2));
+        if (rc) return rc;
+        rc = grow(&h->d_arrivals, &h->arrivals_n, (size_t)npairs * nqb * sizeof(unsigned int), true, h->stream);
+        if (rc) return rc;
+    }
+    hamx_pair none;
+    memset(&none, 0, sizeof(none));
+    dim3 grid((unsigned int)nqb, (unsigned int)nsplit, (unsigned int)npairs);
+    k_hamming_knn2<<<grid, HT_THREADS, 0, h->stream>>>(none, d_pairs, tps, h->d_partial, (size_t)max_nq, h->d_arrivals, (int)nqb,
+                                                        h->d_top2, (size_t)max_nq, 0);
+    ORBX_CUDA(cudaGetLastError());
+    k_ratio_compact<<<npairs, 1024, 0, h->stream>>>(h->d_top2, (size_t)max_nq, 0, d_pairs, ratio, d_good, good_stride, (long long*)d_ngood);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int hamx_match_consecutive_dev(hamx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap,
+                                          const uint8_t* d_prev_desc, const int32_t* d_prev_count, float ratio,
+                                          orbx_dmatch* d_good, int64_t* d_ngood)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_match_consecutive_dev: NULL handle");
+    ORBX_REQUIRE(nframes >= 0 && cap >= 1, "hamx_match_consecutive_dev: bad sizes");
+    if (nframes == 0) return ORBX_OK;
+    ORBX_REQUIRE(d_desc && d_counts && d_good && d_ngood && (!d_prev_desc || d_prev_count), "hamx_match_consecutive_dev: NULL pointer");
+    if ((((uintptr_t)d_desc) | ((uintptr_t)d_prev_desc)) & 15) { set_error("hamx_match_consecutive_dev: descriptor pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int rc = grow(&h->d_pairs, &h->pairs_bytes, (size_t)nframes * sizeof(hamx_pair));
+    if (rc) return rc;
+    k_build_consecutive_pairs<<<(nframes + 127) / 128, 128, 0, h->stream>>>(d_desc, d_counts, nframes, cap, d_prev_desc, d_prev_count,
+                                                                            h->d_pairs);
+    ORBX_CUDA(cudaGetLastError());
+    return hamx_match_pairs_dev(h, h->d_pairs, nframes, cap, cap, ratio, d_good, (size_t)cap, d_ngood);
 }
 
 extern "C" int hamx_knn2_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
@@ -455,7 +563,7 @@ extern "C" int hamx_ratio_dev(hamx_handle h, const hamx_top2* d_top2, int64_t nq
     ORBX_REQUIRE(nq >= 0 && d_ngood, "hamx_ratio_dev: bad arguments");
     ORBX_REQUIRE(nq == 0 || (d_top2 && d_good), "hamx_ratio_dev: NULL pointer");
     ORBX_CUDA(cudaSetDevice(h->device));
-    k_ratio_compact<<<1, 1024, 0, h->stream>>>(d_top2, nq, ratio, d_good, (long long*)d_ngood);
+    k_ratio_compact<<<1, 1024, 0, h->stream>>>(d_top2, 0, nq, nullptr, ratio, d_good, 0, (long long*)d_ngood);
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }

@@ -61,6 +61,18 @@ struct orbx_context {
     int32_t* h_counts;
     std::vector<uint8_t>* h_tab;
     bool dev_pending;   // a _dev submission has not been checked for overflow yet
+    // sequence mode (orbx_match_consecutive)
+    int last_nframes, last_cap;
+    uint8_t* d_prev_desc;
+    int32_t* d_prev_count;
+    bool have_prev;
+    orbx_dmatch* d_good;
+    int64_t* d_ngood;
+    int64_t* h_ngood;
+    // stage profiling
+    bool profiling;
+    std::vector<cudaEvent_t>* events;
+    size_t events_used;
 };
 
 static inline int rne_f(float v) { return (int)lrintf(v); }
@@ -286,7 +298,13 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     ORBX_ALLOC(h->d_desc, B * (size_t)h->dev_cap * 32 + 256);
     ORBX_ALLOC(h->d_counts, B * sizeof(int32_t) + 256);
     ORBX_ALLOC(h->d_tab, h->tab_bytes);
+    ORBX_ALLOC(h->d_prev_desc, (size_t)h->dev_cap * 32 + 256);
+    ORBX_ALLOC(h->d_prev_count, 256);
+    ORBX_ALLOC(h->d_good, B * (size_t)h->dev_cap * sizeof(orbx_dmatch) + 256);
+    ORBX_ALLOC(h->d_ngood, B * sizeof(int64_t) + 256);
 #undef ORBX_ALLOC
+    ORBX_CUDA(cudaMallocHost((void**)&h->h_ngood, B * sizeof(int64_t)));
+    h->events = new std::vector<cudaEvent_t>();
     ORBX_CUDA(cudaMemset(h->d_slots, 0, B * h->slot_stride));   // padding bytes are read (never used) by vector loads
     ORBX_CUDA(cudaMallocHost((void**)&h->h_ctr, B * sizeof(FrameCounters)));
     ORBX_CUDA(cudaMallocHost((void**)&h->h_counts, B * sizeof(int32_t)));
@@ -302,6 +320,9 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_slots); cudaFree(h->d_cand); cudaFree(h->d_surv); cudaFree(h->d_sel); cudaFree(h->d_ctr);
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_tab);
+    cudaFree(h->d_prev_desc); cudaFree(h->d_prev_count); cudaFree(h->d_good); cudaFree(h->d_ngood);
+    if (h->h_ngood) cudaFreeHost(h->h_ngood);
+    if (h->events) { for (cudaEvent_t e : *h->events) cudaEventDestroy(e); delete h->events; }
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -360,17 +381,64 @@ static int upload_frames(orbx_handle h, const uint8_t* const* frames, int nframe
 }
 
 // pyramids + FAST + selection + orientation (+ descriptors); results land in d_out / d_desc / d_counts
+static int stage_mark(orbx_handle h)
+{
+    if (!h->profiling) return ORBX_OK;
+    if (h->events_used == h->events->size()) {
+        cudaEvent_t e;
+        ORBX_CUDA(cudaEventCreate(&e));
+        h->events->push_back(e);
+    }
+    ORBX_CUDA(cudaEventRecord((*h->events)[h->events_used++], h->stream));
+    return ORBX_OK;
+}
+
 static int run_extract(orbx_handle h, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
 {
     ORBX_CUDA(cudaMemsetAsync(h->d_ctr, 0, (size_t)nframes * sizeof(FrameCounters), h->stream));
-    int rc = build_pyramids(h, nframes);
+    int rc = stage_mark(h);
     if (rc) return rc;
+    rc = build_pyramids(h, nframes);
+    if (rc) return rc;
+    if ((rc = stage_mark(h))) return rc;
     ORBX_CUDA(launch_fast(h->g, h->d_slots, h->slot_stride, h->d_cand, h->cand_stride, h->d_ctr, nframes, h->stream));
+    if ((rc = stage_mark(h))) return rc;
     ORBX_CUDA(launch_select(h->g, h->d_cand, h->cand_stride, h->d_surv, h->surv_stride, h->d_ctr, nframes, h->stream));
+    if ((rc = stage_mark(h))) return rc;
     ORBX_CUDA(launch_harris_select(h->g, h->d_slots, h->slot_stride, h->d_surv, h->surv_stride, h->d_sel, h->sel_stride, h->d_ctr,
                                    nframes, h->max_surv_cap, h->harris_s4, h->stream));
+    if ((rc = stage_mark(h))) return rc;
     ORBX_CUDA(launch_orient_describe(h->g, h->d_slots, h->slot_stride, h->d_sel, h->sel_stride, h->d_ctr, d_out,
                                      (mode & ORBX_DO_DESC) ? d_desc : nullptr, cap, d_counts, nframes, mode, h->stream));
+    return stage_mark(h);
+}
+
+extern "C" int orbx_set_profiling(orbx_handle h, int enabled)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_set_profiling: NULL handle");
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    h->profiling = enabled != 0;
+    h->events_used = 0;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_read_profile(orbx_handle h, float* stage_ms, int* nbatches)
+{
+    ORBX_REQUIRE(h != nullptr && stage_ms != nullptr, "orbx_read_profile: NULL argument");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    const size_t per = ORBX_NSTAGES + 1;
+    const size_t n = h->events_used / per;
+    for (int s = 0; s < ORBX_NSTAGES; s++) stage_ms[s] = 0.f;
+    for (size_t b = 0; b < n; b++)
+        for (int s = 0; s < ORBX_NSTAGES; s++) {
+            float ms = 0.f;
+            ORBX_CUDA(cudaEventElapsedTime(&ms, (*h->events)[b * per + s], (*h->events)[b * per + s + 1]));
+            stage_ms[s] += ms;
+        }
+    if (n) for (int s = 0; s < ORBX_NSTAGES; s++) stage_ms[s] /= (float)n;
+    if (nbatches) *nbatches = (int)n;
+    h->events_used = 0;
     return ORBX_OK;
 }
 
@@ -408,6 +476,8 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
     if (rc) return rc;
     rc = run_extract(h, nframes, mode, h->d_kps, h->d_desc, dcap, h->d_counts);
     if (rc) return rc;
+    h->last_nframes = (mode & ORBX_DO_DESC) ? nframes : 0;
+    h->last_cap = dcap;
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     for (int f = 0; f < nframes; f++) counts[f] = h->h_ctr[f].total;
@@ -529,6 +599,40 @@ extern "C" int orbx_compute(orbx_handle h, const uint8_t* gray, int w, int hh, s
     ORBX_CUDA(launch_describe_given(h->g, h->d_slots, h->d_kps, m, h->d_desc, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)m * 32, cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- sequence mode
+extern "C" int hamx_set_stream(hamx_handle h, void* cuda_stream);
+
+extern "C" int orbx_reset_sequence(orbx_handle h)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_reset_sequence: NULL handle");
+    h->have_prev = false;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, orbx_dmatch* good, int64_t* ngood)
+{
+    ORBX_REQUIRE(h != nullptr && m != nullptr, "orbx_match_consecutive: NULL handle");
+    ORBX_REQUIRE(good && ngood, "orbx_match_consecutive: NULL pointer");
+    ORBX_REQUIRE(h->last_nframes >= 1, "orbx_match_consecutive: no batch with descriptors has been extracted on this handle");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int n = h->last_nframes, cap = h->last_cap;
+    int rc = hamx_set_stream(m, (void*)h->stream);   // same stream as the extraction: ordered after it, no extra sync
+    if (rc) return rc;
+    rc = hamx_match_consecutive_dev(m, h->d_desc, h->d_counts, n, cap, h->have_prev ? h->d_prev_desc : nullptr,
+                                    h->have_prev ? h->d_prev_count : nullptr, ratio, h->d_good, h->d_ngood);
+    hamx_set_stream(m, nullptr);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(h->h_ngood, h->d_ngood, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(good, h->d_good, (size_t)n * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
+    // keep the last frame's descriptors for the next batch
+    ORBX_CUDA(cudaMemcpyAsync(h->d_prev_desc, h->d_desc + (size_t)(n - 1) * cap * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_prev_count, h->d_counts + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_prev = true;
+    for (int f = 0; f < n; f++) ngood[f] = h->h_ngood[f];
     return ORBX_OK;
 }
 

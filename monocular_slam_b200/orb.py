@@ -152,6 +152,32 @@ class ORB:
     def check_dev(self):
         check(_lib.lib().orbx_check_dev(self._h))
 
+    # -- sequence mode: consecutive-frame matching of the batch last extracted, descriptors stay on the device
+    def match_consecutive(self, matcher, ratio, cap, nframes, out=None):
+        """matchFeatures(desc[f], desc[f-1], ratio) for every frame f of the last extract_batch (frame 0 against the last
+        frame of the previous batch).  Returns (good[nframes, cap] DMATCH_DTYPE, ngood[nframes])."""
+        if out is not None:
+            good, ngood = out
+        else:
+            good = np.zeros((nframes, cap), DMATCH_DTYPE)
+            ngood = np.zeros(nframes, np.int64)
+        check(_lib.lib().orbx_match_consecutive(self._h, matcher._h, float(ratio), good.ctypes.data,
+                                                ngood.ctypes.data_as(C.POINTER(C.c_int64))))
+        return good, ngood
+
+    def reset_sequence(self):
+        check(_lib.lib().orbx_reset_sequence(self._h))
+
+    def set_profiling(self, enabled):
+        check(_lib.lib().orbx_set_profiling(self._h, int(bool(enabled))))
+
+    def read_profile(self):
+        """Average device milliseconds per batch of each stage since profiling was enabled: dict name -> ms, and #batches."""
+        ms = (C.c_float * _lib.NSTAGES)()
+        n = C.c_int(0)
+        check(_lib.lib().orbx_read_profile(self._h, ms, C.byref(n)))
+        return dict(zip(_lib.STAGE_NAMES, [float(v) for v in ms])), n.value
+
     # -- stage taps for parity tests
     def debug_pyramid_level(self, image, level):
         img = _gray(image)
@@ -248,6 +274,13 @@ class BFMatcher:
 
     def ratio_dev(self, d_top2, nq, ratio, d_good, d_ngood):
         check(_lib.lib().hamx_ratio_dev(self._h, d_top2, nq, float(ratio), d_good, d_ngood))
+
+    def match_pairs_dev(self, d_pairs, npairs, max_nq, max_nt, ratio, d_good, good_stride, d_ngood):
+        check(_lib.lib().hamx_match_pairs_dev(self._h, d_pairs, npairs, max_nq, max_nt, float(ratio), d_good, good_stride, d_ngood))
+
+    def match_consecutive_dev(self, d_desc, d_counts, nframes, cap, d_prev_desc, d_prev_count, ratio, d_good, d_ngood):
+        check(_lib.lib().hamx_match_consecutive_dev(self._h, d_desc, d_counts, nframes, cap, d_prev_desc or None,
+                                                    d_prev_count or None, float(ratio), d_good, d_ngood))
 
 
 _default_matcher = {}

@@ -1,0 +1,86 @@
+"""Multi-GPU sharding of the ORB front-end: one process per GPU, torch.distributed for the plumbing.
+
+* Extraction shards by FRAME and needs no collective: frames are independent (the reference loads every frame before
+  processing, src/main.cpp:36-51, and FeatureExtractor::process touches only frames[frameIdx], FeatureExtractor.cpp:14).
+  ``frame_block`` gives rank r a contiguous block so consecutive-frame matching stays local; the block's first frame is
+  matched against the previous rank's last frame, which the rank simply extracts itself (one extra frame, no exchange).
+* Large map-vs-frame / loop-closure matching shards the TRAIN set: every rank computes the per-query top-2 over its
+  contiguous train range with global indices, ONE all-gather moves the 16-byte candidates (nq x 16 B per rank) and a
+  merge kernel reduces them.  Top-2 under the lexicographic (distance, index) order is associative and commutative, so the
+  merged result is bit-identical to a single-device pass.
+"""
+import numpy as np
+
+
+def shard_bounds(n, world):
+    """Contiguous, near-equal ranges: rank r owns [bounds[r], bounds[r+1])."""
+    base, extra = divmod(int(n), int(world))
+    sizes = [base + (1 if r < extra else 0) for r in range(world)]
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+def frame_block(nframes, rank, world):
+    """Frames [lo, hi) extracted by ``rank`` and the frame its first one is matched against (``lo - 1``, or None)."""
+    b = shard_bounds(nframes, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    return lo, hi, (lo - 1 if lo > 0 else None)
+
+
+class ShardedMatcher:
+    """Train-sharded brute-force Hamming kNN(k=2) (BASELINE.json configs 4 and 5).
+
+    ``local_top2(q, t_shard, offset) -> tensor[nq, 4] int32 (dist0, idx0, dist1, idx1)`` and
+    ``merge(parts[world, nq, 4]) -> tensor[nq, 4]`` default to the CUDA kernels of a ``BFMatcher``; the host-side logic
+    (ranges, offsets, the single all-gather) can be exercised on CPU by injecting stand-ins (tests do, over gloo).
+    """
+
+    def __init__(self, matcher=None, group=None, local_top2=None, merge=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.matcher = matcher
+        self._local = local_top2 or self._local_cuda
+        self._merge = merge or self._merge_cuda
+        if matcher is None and (local_top2 is None or merge is None):
+            raise ValueError("ShardedMatcher needs a BFMatcher (CUDA); there is no CPU implementation in this package")
+
+    # ---- CUDA implementations (hamx_knn2_dev / hamx_merge_top2_dev on the current torch stream)
+    def _use_current_stream(self):
+        import torch
+        s = torch.cuda.current_stream().cuda_stream
+        if s == 0:
+            raise RuntimeError("run ShardedMatcher under a non-default torch stream (stream handle 0 selects the library's own stream)")
+        self.matcher.set_stream(s)
+
+    def _local_cuda(self, q, t_shard, offset):
+        import torch
+        self._use_current_stream()
+        out = torch.empty((q.shape[0], 4), dtype=torch.int32, device=q.device)
+        self.matcher.knn2_dev(q.data_ptr(), q.shape[0], t_shard.data_ptr(), t_shard.shape[0], int(offset), out.data_ptr())
+        return out
+
+    def _merge_cuda(self, parts):
+        import torch
+        self._use_current_stream()
+        out = torch.empty((parts.shape[1], 4), dtype=torch.int32, device=parts.device)
+        self.matcher.merge_top2_dev(parts.data_ptr(), parts.shape[0], parts.shape[1], out.data_ptr())
+        return out
+
+    # ---- the sharded operation
+    def knn2(self, q, t_shard, train_offset):
+        """q: [nq, 32] uint8, replicated on every rank; t_shard: this rank's rows [train_offset, train_offset + len)."""
+        import torch
+        local = self._local(q, t_shard, train_offset)
+        if self.world == 1:
+            return local
+        flat = torch.empty((self.world * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(flat, local.contiguous(), group=self.group)   # rank-major concatenation
+        return self._merge(flat.view(self.world, local.shape[0], local.shape[1]))
+
+    def knn2_from_full(self, q, t_full):
+        """Convenience for tests: every rank holds the full train set and takes its own slice."""
+        b = shard_bounds(t_full.shape[0], self.world)
+        lo, hi = int(b[self.rank]), int(b[self.rank + 1])
+        return self.knn2(q, t_full[lo:hi].contiguous(), lo)

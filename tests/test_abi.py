@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/orbx.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from monocular_slam_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "orbx.h")).read()
+    return re.findall(r"ORBX_API\s+[\w\s\*]+?\b((?:orbx|hamx)_\w+)\s*\(", src)
+
+
+def test_library_builds_and_exports_header():
+    _lib.build()
+    L = _lib.lib()
+    declared = _header_symbols()
+    assert len(declared) >= 30
+    assert sorted(declared) == sorted(_lib.SYMBOLS), "include/orbx.h and _lib.SYMBOLS disagree"
+    for s in declared:
+        assert hasattr(L, s), "liborbx.so does not export %s" % s
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    names = {ln.split()[-1] for ln in exported.splitlines() if " T " in ln}
+    assert names == set(declared), "exported symbols differ from the header: %s" % (names ^ set(declared))
+
+
+def test_pod_layouts():
+    assert _lib.KEYPOINT_DTYPE.itemsize == 28 and _lib.DMATCH_DTYPE.itemsize == 16 and _lib.TOP2_DTYPE.itemsize == 16
+    assert C.sizeof(_lib.Params) == 36
+    p = _lib.Params()
+    _lib.lib().orbx_default_params(C.byref(p))
+    assert (p.nfeatures, round(p.scale_factor, 4), p.nlevels, p.edge_threshold, p.first_level, p.wta_k, p.score_type,
+            p.patch_size, p.fast_threshold) == (500, 1.2, 8, 31, 0, 2, 0, 31, 20)   # reference defaults, FeatureExtractor.h:23-24
+
+
+def test_sass_is_blackwell_native():
+    """The matcher must be built for sm_100a and stage its train tiles with the TMA bulk-copy engine."""
+    sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    assert "UBLKCP" in sass and "POPC" in sass and "SYNCS" in sass
+
+
+@pytest.mark.skipif(_lib.lib().orbx_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback():
+    from monocular_slam_b200 import ORB, BFMatcher, OrbxError
+    with pytest.raises(OrbxError) as e:
+        ORB(nfeatures=500)
+    assert e.value.status == _lib.E_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(OrbxError):
+        BFMatcher()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "monocular_slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".sh", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "orb_oracle" not in txt, f
+    for f in ("orbx.h", "orbx_shim.hpp"):
+        p = os.path.join(ROOT, "include", f)
+        if os.path.exists(p):
+            assert "oracle" not in open(p).read()

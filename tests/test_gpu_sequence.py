@@ -1,0 +1,122 @@
+"""GPU parity: sequence mode (batched extraction + consecutive-frame matching with descriptors left on the device)
+against the oracle run frame by frame -- the reference's FeatureExtractor::process followed by
+matchFeatures(desc_cur, desc_prev) (src/FeatureExtractor.cpp:13-31, src/CameraPoseEstimator.cpp:200-213,409)."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import assert_descriptors_equal, assert_keypoints_equal
+from monocular_slam_b200 import ORB, BFMatcher, DMATCH_DTYPE, KEYPOINT_DTYPE
+from monocular_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_sequence(seq, nf, ratio):
+    P = oracle.Params(nfeatures=nf)
+    ext = [oracle.detect_and_compute(f, P) for f in seq]
+    matches = [None] + [oracle.match_features(ext[i][1], ext[i - 1][1], ratio) for i in range(1, len(seq))]
+    return ext, matches
+
+
+def _check_matches(good_row, n, want):
+    q, t, d = want
+    assert n == len(q)
+    g = good_row[:n]
+    assert np.array_equal(g["query_idx"], q) and np.array_equal(g["train_idx"], t)
+    assert np.array_equal(g["distance"].astype(np.int32), d) and (g["img_idx"] == 0).all()
+
+
+def test_sequence_host_path():
+    seq = syn.sequence(7, 800, 600, seed=21)
+    ext, matches = _oracle_sequence(seq, 1000, 0.8)
+    orb = ORB(nfeatures=1000, max_size=(800, 600), max_batch=4)
+    m = BFMatcher()
+    cap = orb.default_cap
+    # two submissions (4 + 3 frames): frame 4 must be matched against frame 3 of the previous batch
+    done = 0
+    for chunk in (list(seq[:4]), list(seq[4:])):
+        kps, desc, counts = orb.extract_batch(chunk, cap=cap)
+        good, ngood = orb.match_consecutive(m, 0.8, cap, len(chunk))
+        for i in range(len(chunk)):
+            f = done + i
+            assert_keypoints_equal(kps[i, :counts[i]], ext[f][0], "frame %d" % f)
+            assert_descriptors_equal(desc[i, :counts[i]], ext[f][1], "frame %d" % f)
+            if f == 0:
+                assert ngood[i] == 0
+            else:
+                _check_matches(good[i], int(ngood[i]), matches[f])
+        done += len(chunk)
+    orb.reset_sequence()
+    kps, desc, counts = orb.extract_batch(list(seq[:2]), cap=cap)
+    good, ngood = orb.match_consecutive(m, 0.8, cap, 2)
+    assert ngood[0] == 0
+    _check_matches(good[1], int(ngood[1]), matches[1])
+    m.close()
+    orb.close()
+
+
+def test_sequence_device_path():
+    import torch
+    seq = syn.sequence(5, 1241, 376, seed=22)
+    ext, matches = _oracle_sequence(seq, 2000, 0.75)
+    B, (H, W) = len(seq), seq[0].shape
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        orb = ORB(nfeatures=2000, max_size=(W, H), max_batch=B)
+        m = BFMatcher()
+        orb.set_stream(stream.cuda_stream)
+        m.set_stream(stream.cuda_stream)
+        cap = orb.default_cap
+        d_frames = torch.from_numpy(seq).cuda()
+        d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device="cuda")
+        d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+        d_good = torch.empty((B, cap, 4), dtype=torch.int32, device="cuda")
+        d_ngood = torch.zeros(B, dtype=torch.int64, device="cuda")
+        for _ in range(2):   # twice: counters, arrival counters and workspaces must be reusable
+            orb.extract_batch_dev(d_frames.data_ptr(), W * H, B, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
+            m.match_consecutive_dev(d_desc.data_ptr(), d_cnt.data_ptr(), B, cap, 0, 0, 0.75, d_good.data_ptr(), d_ngood.data_ptr())
+        orb.check_dev()
+        stream.synchronize()
+    cnt = d_cnt.cpu().numpy()
+    kps = d_kps.cpu().numpy().view(KEYPOINT_DTYPE).reshape(B, cap)
+    desc = d_desc.cpu().numpy()
+    good = d_good.cpu().numpy().view(DMATCH_DTYPE).reshape(B, cap)
+    ngood = d_ngood.cpu().numpy()
+    for f in range(B):
+        assert_keypoints_equal(kps[f, :cnt[f]], ext[f][0], "frame %d" % f)
+        assert_descriptors_equal(desc[f, :cnt[f]], ext[f][1], "frame %d" % f)
+        if f:
+            _check_matches(good[f], int(ngood[f]), matches[f])
+    assert ngood[0] == 0
+    m.close()
+    orb.close()
+
+
+def test_batched_pairs_ragged():
+    """hamx_match_pairs_dev on pairs of very different sizes, including empty ones."""
+    import torch
+    sizes = [(300, 500), (1, 1), (0, 40), (40, 0), (257, 129), (1000, 3), (5, 2000)]
+    sets = [(syn.descriptors(2 * i + 1, nq), syn.descriptors(2 * i + 2, nt)) for i, (nq, nt) in enumerate(sizes)]
+    max_nq = max(s[0] for s in sizes)
+    max_nt = max(s[1] for s in sizes)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        m = BFMatcher()
+        m.set_stream(stream.cuda_stream)
+        dq = [torch.from_numpy(q).cuda() if len(q) else torch.zeros((1, 32), dtype=torch.uint8, device="cuda") for q, _ in sets]
+        dt = [torch.from_numpy(t).cuda() if len(t) else torch.zeros((1, 32), dtype=torch.uint8, device="cuda") for _, t in sets]
+        table = np.zeros(len(sets), np.dtype([("q", "<u8"), ("t", "<u8"), ("nq", "<i4"), ("nt", "<i4")]))
+        for i, (q, t) in enumerate(sets):
+            table[i] = (dq[i].data_ptr(), dt[i].data_ptr(), len(q), len(t))
+        d_pairs = torch.from_numpy(table.view(np.uint8)).cuda()
+        d_good = torch.empty((len(sets), max_nq, 4), dtype=torch.int32, device="cuda")
+        d_ngood = torch.zeros(len(sets), dtype=torch.int64, device="cuda")
+        m.match_pairs_dev(d_pairs.data_ptr(), len(sets), max_nq, max_nt, 0.8, d_good.data_ptr(), max_nq, d_ngood.data_ptr())
+        stream.synchronize()
+    good = d_good.cpu().numpy().view(DMATCH_DTYPE).reshape(len(sets), max_nq)
+    ngood = d_ngood.cpu().numpy()
+    for i, (q, t) in enumerate(sets):
+        _check_matches(good[i], int(ngood[i]), oracle.match_features(q, t, 0.8))
+    m.close()

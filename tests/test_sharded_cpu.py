@@ -1,0 +1,73 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU paths (ranges, global offsets, the single
+all-gather, merge order).  The per-shard top-2 and the merge are CUDA kernels in the product; here the oracle and a
+numpy lexicographic merge stand in for them so the plumbing can be checked without a GPU."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from monocular_slam_b200 import synthetic as syn
+from monocular_slam_b200.sharded import ShardedMatcher, frame_block, shard_bounds
+
+
+def test_shard_bounds():
+    assert shard_bounds(10, 3).tolist() == [0, 4, 7, 10]
+    assert shard_bounds(200000, 8).tolist() == [25000 * i for i in range(9)]
+    assert shard_bounds(2, 4).tolist() == [0, 1, 2, 2, 2]
+    covered = []
+    for r in range(4):
+        lo, hi, prev = frame_block(257, r, 4)
+        covered += list(range(lo, hi))
+        assert prev == (lo - 1 if lo else None)
+    assert covered == list(range(257))
+
+
+def _local_top2(q, t, offset):
+    idx, d = oracle.knn2(q.numpy(), t.numpy())
+    idx = np.where(idx >= 0, idx + offset, -1)
+    return torch.from_numpy(np.stack([d[:, 0], idx[:, 0], d[:, 1], idx[:, 1]], 1).astype(np.int32))
+
+
+def _merge(parts):
+    p = parts.numpy().astype(np.int64)                      # [world, nq, 4]
+    keys = np.concatenate([np.where(p[..., 1] >= 0, (p[..., 0] << 32) | p[..., 1], np.iinfo(np.int64).max),
+                           np.where(p[..., 3] >= 0, (p[..., 2] << 32) | p[..., 3], np.iinfo(np.int64).max)], 0)
+    keys.sort(axis=0)
+    out = np.full((p.shape[1], 4), -1, np.int32)
+    for j in range(2):
+        k = keys[j]
+        ok = k != np.iinfo(np.int64).max
+        out[ok, 2 * j] = (k[ok] >> 32).astype(np.int32)
+        out[ok, 2 * j + 1] = (k[ok] & 0xFFFFFFFF).astype(np.int32)
+    return torch.from_numpy(out)
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = syn.descriptors(31, 4001)
+    t[3000:3005] = t[10:15]                     # duplicates on both sides of the shard boundary: tie rule across shards
+    q = syn.planted_queries(32, t, 300)
+    sm = ShardedMatcher(matcher=None, local_top2=_local_top2, merge=_merge)
+    r = sm.knn2_from_full(torch.from_numpy(q), torch.from_numpy(t)).numpy()
+    oi, od = oracle.knn2(q, t)
+    ok = np.array_equal(r[:, [1, 3]], oi) and np.array_equal(r[:, [0, 2]], od)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_train_sharded_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    oracle.build()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -1,0 +1,277 @@
+// orbx_shim.hpp -- header-only C++ host side over the C ABI of liborbx.so (include/orbx.h).
+//
+// It re-creates exactly the objects the reference's hot path uses, with the same names, argument meaning and error
+// behaviour, so that the reference's two call sites compile unchanged against it:
+//
+//   src/FeatureExtractor.h:23-24      OrbFeatureDetector detector;  OrbDescriptorExtractor extractor;
+//   src/FeatureExtractor.cpp:17,19    detector.detect(frameBuffer, keypoints);  extractor.compute(frameBuffer, keypoints, descriptor);
+//   src/CameraPoseEstimator.cpp:200-213   static void matchFeatures(const Mat&, const Mat&, vector<DMatch>&, float ratio = 0.8)
+//                                          { BFMatcher matcher(NORM_HAMMING, false); matcher.knnMatch(d1, d2, raw, 2); ... }
+//
+// Without OpenCV headers (this image has none) the POD mirrors below stand in for cv::KeyPoint / cv::DMatch / cv::Mat;
+// define ORBX_SHIM_USE_OPENCV before including to bind to the real cv types instead (same memory layouts:
+// orbx_keypoint == cv::KeyPoint, orbx_dmatch == cv::DMatch).  Bad input throws (the reference never catches
+// cv::Exception either).  No algorithm runs on the CPU here: every call goes to the GPU through liborbx.so.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "orbx.h"
+
+#ifdef ORBX_SHIM_USE_OPENCV
+#include <opencv2/core/core.hpp>
+#include <opencv2/features2d/features2d.hpp>
+#endif
+
+namespace orbx_shim {
+
+#ifdef ORBX_SHIM_USE_OPENCV
+using cv::DMatch;
+using cv::KeyPoint;
+using cv::Mat;
+using cv::NORM_HAMMING;
+static inline const uint8_t* mat_ptr(const Mat& m) { return m.data; }
+static inline void mat_create_u8(Mat& m, int rows, int cols) { m.create(rows, cols, CV_8UC1); }
+static inline size_t mat_step(const Mat& m) { return m.step; }
+#else
+enum { NORM_HAMMING = 6 };
+struct Point2f { float x, y; };
+struct Point2d { double x, y; };
+struct KeyPoint {               // field order and size of cv::KeyPoint (28 bytes)
+    Point2f pt; float size, angle, response; int octave, class_id;
+};
+struct DMatch {                 // cv::DMatch (16 bytes)
+    int queryIdx, trainIdx, imgIdx; float distance;
+};
+struct Mat {                    // the part of cv::Mat the hot path touches: an 8-bit, single-channel matrix
+    int rows = 0, cols = 0;
+    size_t step = 0;
+    uint8_t* data = nullptr;
+    std::vector<uint8_t> storage;
+    Mat() {}
+    Mat(int r, int c, uint8_t* borrowed, size_t stp = 0) : rows(r), cols(c), step(stp ? stp : (size_t)c), data(borrowed) {}
+    void create(int r, int c) { rows = r; cols = c; step = (size_t)c; storage.assign((size_t)r * c, 0); data = storage.data(); }
+    bool empty() const { return rows == 0 || cols == 0; }
+    uint8_t* ptr(int r) { return data + (size_t)r * step; }
+    const uint8_t* ptr(int r) const { return data + (size_t)r * step; }
+};
+static inline const uint8_t* mat_ptr(const Mat& m) { return m.data; }
+static inline void mat_create_u8(Mat& m, int rows, int cols) { m.create(rows, cols); }
+static inline size_t mat_step(const Mat& m) { return m.step; }
+#endif
+
+static_assert(sizeof(KeyPoint) == sizeof(orbx_keypoint), "KeyPoint must have cv::KeyPoint's layout");
+static_assert(sizeof(DMatch) == sizeof(orbx_dmatch), "DMatch must have cv::DMatch's layout");
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string& what) : std::runtime_error(what), status(s) {}
+};
+static inline void check(int status, const char* where)
+{
+    if (status != ORBX_OK) throw Error(status, std::string(where) + ": " + orbx_last_error());
+}
+
+// cv::ORB with the reference's constructor defaults (src/FeatureExtractor.h:23-24 default-constructs it).
+class ORB {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+    explicit ORB(int nfeatures = 500, float scaleFactor = 1.2f, int nlevels = 8, int edgeThreshold = 31, int firstLevel = 0,
+                 int WTA_K = 2, int scoreType = HARRIS_SCORE, int patchSize = 31, int device = 0, int maxWidth = 1920, int maxHeight = 1080)
+        : h_(nullptr), device_(device), maxw_(maxWidth), maxh_(maxHeight)
+    {
+        orbx_default_params(&p_);
+        p_.nfeatures = nfeatures; p_.scale_factor = scaleFactor; p_.nlevels = nlevels; p_.edge_threshold = edgeThreshold;
+        p_.first_level = firstLevel; p_.wta_k = WTA_K; p_.score_type = scoreType; p_.patch_size = patchSize;
+    }
+    ~ORB() { if (h_) orbx_destroy(h_); }
+    ORB(const ORB&) = delete;
+    ORB& operator=(const ORB&) = delete;
+
+    // FeatureDetector::detect(image, keypoints): keypoints is cleared and filled (canonical order: octave, y, x)
+    void detect(const Mat& image, std::vector<KeyPoint>& keypoints)
+    {
+        ensure(image);
+        int cap = default_cap(), n = 0;
+        keypoints.resize((size_t)cap);
+        int rc = orbx_detect(h_, mat_ptr(image), image.cols, image.rows, mat_step(image), reinterpret_cast<orbx_keypoint*>(keypoints.data()), cap, &n);
+        if (rc == ORBX_E_CAPACITY) {   // ties at a retention cut can return more than nfeatures (OpenCV does the same)
+            cap = orbx_max_keypoints(h_);
+            keypoints.resize((size_t)cap);
+            rc = orbx_detect(h_, mat_ptr(image), image.cols, image.rows, mat_step(image), reinterpret_cast<orbx_keypoint*>(keypoints.data()), cap, &n);
+        }
+        check(rc, "ORB::detect");
+        keypoints.resize((size_t)n);
+    }
+
+    // DescriptorExtractor::compute(image, keypoints, descriptors): keypoints may be filtered / regrouped by octave;
+    // descriptors becomes N x 32 CV_8U with row i describing keypoints[i]
+    void compute(const Mat& image, std::vector<KeyPoint>& keypoints, Mat& descriptors)
+    {
+        ensure(image);
+        int n = (int)keypoints.size();
+        mat_create_u8(descriptors, n > 0 ? n : 1, 32);
+        check(orbx_compute(h_, mat_ptr(image), image.cols, image.rows, mat_step(image), reinterpret_cast<orbx_keypoint*>(keypoints.data()), &n,
+                           descriptors.data),
+              "ORB::compute");
+        keypoints.resize((size_t)n);
+        descriptors.rows = n;
+    }
+
+    // cv::ORB::operator()(image, mask, keypoints, descriptors): detect + compute with one pyramid
+    void operator()(const Mat& image, std::vector<KeyPoint>& keypoints, Mat& descriptors)
+    {
+        ensure(image);
+        int cap = default_cap(), n = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            keypoints.resize((size_t)cap);
+            mat_create_u8(descriptors, cap, 32);
+            int rc = orbx_detect_and_compute(h_, mat_ptr(image), image.cols, image.rows, mat_step(image),
+                                             reinterpret_cast<orbx_keypoint*>(keypoints.data()), descriptors.data, cap, &n);
+            if (rc == ORBX_E_CAPACITY && attempt == 0) { cap = orbx_max_keypoints(h_); continue; }
+            check(rc, "ORB::operator()");
+            break;
+        }
+        keypoints.resize((size_t)n);
+        descriptors.rows = n;
+    }
+
+    orbx_handle handle() { return h_; }
+
+private:
+    int default_cap() const { return p_.nfeatures + (p_.nfeatures / 4 > 512 ? p_.nfeatures / 4 : 512); }
+    void ensure(const Mat& image)
+    {
+        if (image.empty() || !mat_ptr(image)) throw Error(ORBX_E_INVALID, "ORB: empty image");
+        if (h_ && (image.cols > maxw_ || image.rows > maxh_)) { orbx_destroy(h_); h_ = nullptr; }
+        if (!h_) {
+            if (image.cols > maxw_) maxw_ = image.cols;
+            if (image.rows > maxh_) maxh_ = image.rows;
+            check(orbx_create(&h_, &p_, device_, maxw_, maxh_, 1), "ORB: orbx_create");   // lazily, like ProcessingNode::init()
+        }
+    }
+    orbx_handle h_;
+    orbx_params p_;
+    int device_, maxw_, maxh_;
+};
+
+typedef ORB OrbFeatureDetector;        // OpenCV 2.4 typedefs, the names used at src/FeatureExtractor.h:23-24
+typedef ORB OrbDescriptorExtractor;
+
+// cv::BFMatcher(NORM_HAMMING, crossCheck = false)
+class BFMatcher {
+public:
+    explicit BFMatcher(int normType = NORM_HAMMING, bool crossCheck = false, int device = 0) : h_(nullptr)
+    {
+        if (normType != NORM_HAMMING || crossCheck) throw Error(ORBX_E_INVALID, "BFMatcher: only (NORM_HAMMING, false) is provided");
+        check(hamx_create(&h_, device), "BFMatcher");
+    }
+    ~BFMatcher() { if (h_) hamx_destroy(h_); }
+    BFMatcher(const BFMatcher&) = delete;
+    BFMatcher& operator=(const BFMatcher&) = delete;
+
+    // knnMatch(queryDescriptors, trainDescriptors, matches, k = 2): matches.size() == query rows; each row sorted by
+    // (distance, trainIdx) and shorter than 2 only if the train set has fewer than 2 rows
+    void knnMatch(const Mat& query, const Mat& train, std::vector<std::vector<DMatch> >& matches, int k)
+    {
+        if (k != 2) throw Error(ORBX_E_INVALID, "BFMatcher::knnMatch: the reference calls it with k = 2 only");
+        if ((query.rows && query.cols != 32) || (train.rows && train.cols != 32) || (query.rows && mat_step(query) != 32) ||
+            (train.rows && mat_step(train) != 32))
+            throw Error(ORBX_E_INVALID, "BFMatcher::knnMatch: descriptors must be continuous N x 32 CV_8U");
+        std::vector<orbx_dmatch> flat((size_t)query.rows * 2);
+        std::vector<int32_t> counts((size_t)query.rows);
+        check(hamx_knn2(h_, mat_ptr(query), query.rows, mat_ptr(train), train.rows, flat.data(), counts.data()), "BFMatcher::knnMatch");
+        matches.assign((size_t)query.rows, std::vector<DMatch>());
+        for (int i = 0; i < query.rows; i++)
+            for (int j = 0; j < counts[(size_t)i]; j++) {
+                DMatch m;
+                std::memcpy(&m, &flat[(size_t)2 * i + j], sizeof(m));
+                matches[(size_t)i].push_back(m);
+            }
+    }
+
+    // the whole of matchFeatures() in one submission (knnMatch k=2 + ratio test on the device)
+    void matchRatio(const Mat& d1, const Mat& d2, std::vector<DMatch>& matches, float ratio)
+    {
+        std::vector<orbx_dmatch> good((size_t)(d1.rows > 0 ? d1.rows : 1));
+        int64_t n = 0;
+        check(hamx_match_ratio(h_, mat_ptr(d1), d1.rows, mat_ptr(d2), d2.rows, ratio, good.data(), &n), "BFMatcher::matchRatio");
+        matches.resize((size_t)n);
+        if (n) std::memcpy(matches.data(), good.data(), (size_t)n * sizeof(DMatch));
+    }
+
+    hamx_handle handle() { return h_; }
+
+private:
+    hamx_handle h_;
+};
+
+// The reference's routine, line for line in behaviour (src/CameraPoseEstimator.cpp:200-213).  It constructs a matcher
+// per call like the reference does; hold a BFMatcher and call matchRatio() to avoid that.
+static inline void matchFeatures(const Mat& descriptors1, const Mat& descriptors2, std::vector<DMatch>& matches, float ratio = 0.8f)
+{
+    BFMatcher matcher(NORM_HAMMING, false);
+    std::vector<std::vector<DMatch> > raw_matches;
+    matcher.knnMatch(descriptors1, descriptors2, raw_matches, 2);
+    matches.clear();
+    for (size_t i = 0; i < raw_matches.size(); i++) {
+        if (raw_matches[i].size() < 2) continue;   // the reference indexes [1] unguarded; such rows cannot pass a ratio test
+        if (raw_matches[i][0].distance < raw_matches[i][1].distance * ratio) matches.push_back(raw_matches[i][0]);
+    }
+}
+
+#ifndef ORBX_SHIM_USE_OPENCV
+// ---- the slice of the reference's data model and node API that the front-end touches
+struct Features {                           // src/Frame.h:22-34
+    std::vector<Point2d> positions;
+    Mat descriptors;
+    std::vector<int> mapPointsIndices;
+    std::vector<double> scales;
+};
+struct Frame { Mat frameBuffer; Features features; };          // src/Frame.h:36-72 (front-end fields)
+struct DataManager { std::vector<Frame> frames; };             // src/DataManager.h:23-36
+
+class ProcessingNode {                      // src/ProcessingNode.h:16-32
+public:
+    explicit ProcessingNode(const std::string& n) : name(n) {}
+    virtual void init() {}
+    virtual void finish() {}
+    virtual void destroy() {}
+    virtual ~ProcessingNode() {}
+    virtual void process(DataManager&, int) {}
+    virtual bool validationCheck(DataManager&, int) { return true; }
+    std::string name;
+};
+
+class FeatureExtractor : public ProcessingNode {   // src/FeatureExtractor.{h,cpp}
+public:
+    FeatureExtractor() : ProcessingNode("FeatureExtractor") {}
+    explicit FeatureExtractor(int nfeatures) : ProcessingNode("FeatureExtractor"), detector(nfeatures), extractor(nfeatures) {}
+    virtual void process(DataManager& data, int frameIdx)
+    {
+        Frame& frame = data.frames[(size_t)frameIdx];
+        std::vector<KeyPoint> keypoints;
+        detector.detect(frame.frameBuffer, keypoints);
+        Mat descriptor;
+        extractor.compute(frame.frameBuffer, keypoints, descriptor);
+        frame.features.descriptors = descriptor;
+        if (frame.features.descriptors.storage.size()) frame.features.descriptors.data = frame.features.descriptors.storage.data();
+        for (size_t i = 0; i < keypoints.size(); i++) {
+            Point2d p = { (double)keypoints[i].pt.x, (double)keypoints[i].pt.y };
+            frame.features.positions.push_back(p);
+            frame.features.scales.push_back((double)keypoints[i].size);
+        }
+        frame.features.mapPointsIndices.resize(keypoints.size(), -1);
+    }
+    virtual bool validationCheck(DataManager&, int) { return true; }
+
+private:
+    OrbFeatureDetector detector;
+    OrbDescriptorExtractor extractor;
+};
+#endif
+
+}  // namespace orbx_shim

@@ -78,7 +78,7 @@ __device__ __forceinline__ float orient_describe_body(const uint8_t* __restrict_
     __shared__ float s_row[OD_P * OD_B];
     __shared__ uint8_t s_val[OD_B * OD_BP];
     __shared__ int s_m[2][OD_THREADS / 32];
-    __shared__ float s_angle;
+    __shared__ float s_angle, s_cos, s_sin;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const bool interior = xi >= OD_R && yi >= OD_R && xi + OD_R < w && yi + OD_R < h;
@@ -118,6 +118,11 @@ __device__ __forceinline__ float orient_describe_body(const uint8_t* __restrict_
         angle = s_angle;
     }
     if (!(mode & ORBX_DO_DESC)) return angle;
+    if (tid == 0) {   // one double-precision cos/sin per keypoint: a = (float)cos((double)ang), as the CPU path does
+        const float ang = __fmul_rn(angle, (float)(3.141592653589793238462643383279502884 / 180.f));
+        s_cos = (float)cos((double)ang);
+        s_sin = (float)sin((double)ang);
+    }
 
     // ---- blur: row pass over 43 rows x 37 columns
     // cv::getGaussianKernel(7, 2, CV_32F)
@@ -154,8 +159,7 @@ __device__ __forceinline__ float orient_describe_body(const uint8_t* __restrict_
     __syncthreads();
 
     // ---- rBRIEF: thread t evaluates test t
-    const float ang = __fmul_rn(angle, (float)(3.141592653589793238462643383279502884 / 180.f));
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const float a = s_cos, b = s_sin;   // written before the two barriers of the blur passes
     const char4 pt = __ldg(reinterpret_cast<const char4*>(d_pattern) + tid);
     const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
     const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));

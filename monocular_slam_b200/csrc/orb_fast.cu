@@ -7,53 +7,92 @@
 //   corner  <=>  m > threshold (20);  score = m - 1;  keep iff score > all 8 neighbours' scores (non-corners score 0)
 //   and 31 <= x < w-31, 31 <= y < h-31.
 //
-// A CTA owns a 128x32 tile of the interior [31,w-31) x [31,h-31) of one level.  It stages the tile plus a 4-pixel
+// A CTA owns a 124x30 tile of the interior [31,w-31) x [31,h-31) of one level.  It stages the tile plus a 4-pixel
 // halo in shared memory with 16-byte loads (rows are 128-byte pitched), then
-//   1a. every thread tests ~17 pixels of the (tile + 1) score region: the 16 ring comparisons are folded into two
-//       16-bit masks and the 9-contiguous test is 4 shift-ANDs on the doubled mask; corners are appended to a
-//       shared-memory queue with one ballot-aggregated atomic per warp,
-//   1b. the queue is drained densely (no divergence): sliding-window minimum over the ring gives m exactly,
-//   2.  NMS on the score tile; survivors are staged in shared memory, the CTA reserves its range of the level's
-//       candidate list with ONE global atomic and writes (x, y, score); the per-level score histogram used by the
-//       retainBest cut (K3) is accumulated with one RED per survivor.
-// Bound: integer ALU / shared-memory issue, not HBM (each level byte is read 1.3x from L2, once from HBM).
+//   1. scores the (tile + 1) region branch-free, four horizontally adjacent pixels per thread and two pixels per
+//      instruction: ring-minus-centre differences live in packed s16x2 lanes (VIADD.16x2) and the sliding
+//      9-of-16 window minimum / maximum is a log-step network of VIMNMX.S16x2 (55 min/max per sign and pixel pair),
+//      which yields m = max(max_k min9(d), -min_k max9(d)) exactly -- no corner pre-test, no divergence.  A warp
+//      covers one score row (32 groups of 4 pixels), 21 aligned 32-bit shared-memory loads feed 4 pixels;
+//   2. NMS on the score tile (a whole word of four zero scores is skipped at once); survivors are staged in shared
+//      memory, the CTA reserves its range of the level's candidate list with ONE global atomic and writes
+//      (x, y, score); the per-level score histogram used by the retainBest cut (K3) gets one RED per survivor.
+// Bound: integer ALU issue (VIMNMX/PRMT), not HBM: each level byte is read once from HBM and ~1.4x from L2.
 #include "common.cuh"
 
 namespace orbx {
 namespace {
 
-constexpr int FT_TW = 128;
-constexpr int FT_TH = 32;
+constexpr int FT_TW = 124;
+constexpr int FT_TH = 30;
 constexpr int FT_THREADS = 256;
-constexpr int FT_SP = 160;               // smem image pitch: 11 (alignment) + 4 + 128 + 4 = 147 -> 10 vectors
-constexpr int FT_SH = FT_TH + 8;         // 40 rows
-constexpr int FT_CW = FT_TW + 2;         // score region 130 x 34
-constexpr int FT_CH = FT_TH + 2;
-constexpr int FT_CP = 132;               // score pitch
-constexpr int FT_NPOS = FT_CW * FT_CH;   // 4420
+constexpr int FT_SP = 160;               // smem pitch (image and score share column coordinates): <= 15 + 4 + 124 + 4
+constexpr int FT_SH = FT_TH + 8;         // 38 image rows
+constexpr int FT_CH = FT_TH + 2;         // 32 score rows = 8 warps x 4
 constexpr int FT_EMIT = (FT_TW / 2 + 1) * (FT_TH / 2 + 1);   // NMS allows at most one maximum per 2x2 block
 
-__device__ __forceinline__ bool arc9(uint32_t m)
+// 16x2 lanes from bytes (0,1) / (2,3) of g
+__device__ __forceinline__ uint32_t lanes_lo(uint32_t g) { return __byte_perm(g, 0u, 0x4140); }
+__device__ __forceinline__ uint32_t lanes_hi(uint32_t g) { return __byte_perm(g, 0u, 0x4342); }
+
+// bytes [4 + dx, 8 + dx) of the 12-byte window {w0, w1, w2} (w1 holds the four centre columns)
+template <int DX>
+__device__ __forceinline__ uint32_t window4(uint32_t w0, uint32_t w1, uint32_t w2)
 {
-    m |= m << 16;
-    uint32_t r = m & (m >> 1);
-    r &= r >> 2;
-    r &= r >> 4;          // bit i: ring pixels i..i+7 all set
-    r &= m >> 8;          // ... and i+8
-    return (r & 0xFFFFu) != 0;
+    if (DX == 0) return w1;
+    if (DX == -1) return __byte_perm(w0, w1, 0x6543);
+    if (DX == -2) return __byte_perm(w0, w1, 0x5432);
+    if (DX == -3) return __byte_perm(w0, w1, 0x4321);
+    if (DX == 1) return __byte_perm(w1, w2, 0x4321);
+    if (DX == 2) return __byte_perm(w1, w2, 0x5432);
+    return __byte_perm(w1, w2, 0x6543);   // DX == 3
 }
+
+// m + 256, m = max over the 16 arcs of 9 contiguous ring positions of max(min d, min -d), for two pixels at once.
+// d[] holds the BIASED differences I(ring) - I(centre) + 256 in s16x2 lanes: every lane stays in [1, 511], so the
+// per-lane additions that produce them are plain 32-bit adds (no carry between lanes, and ptxas may place them on the
+// FMA pipe as IMAD.IADD), while the min/max network is shift-invariant.
+__device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&d)[16])
+{
+    uint32_t lo2[8], hi2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {       // window {2j+1, 2j+2}
+        lo2[j] = __vmins2(d[2 * j + 1], d[(2 * j + 2) & 15]);
+        hi2[j] = __vmaxs2(d[2 * j + 1], d[(2 * j + 2) & 15]);
+    }
+    uint32_t lo4[8], hi4[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {       // window 2j+1 .. 2j+4
+        lo4[j] = __vmins2(lo2[j], lo2[(j + 1) & 7]);
+        hi4[j] = __vmaxs2(hi2[j], hi2[(j + 1) & 7]);
+    }
+    uint32_t best_lo = 0u, best_hi = 0x7FFF7FFFu;   // running max of arc minima / min of arc maxima
+#pragma unroll
+    for (int j = 0; j < 8; j++) {       // window 2j+1 .. 2j+8, extended by 2j (arc 2j) or 2j+9 (arc 2j+1)
+        const uint32_t lo8 = __vmins2(lo4[j], lo4[(j + 2) & 7]);
+        const uint32_t hi8 = __vmaxs2(hi4[j], hi4[(j + 2) & 7]);
+        best_lo = __vmaxs2(best_lo, __vmins2(lo8, d[2 * j]));
+        best_lo = __vmaxs2(best_lo, __vmins2(lo8, d[(2 * j + 9) & 15]));
+        best_hi = __vmins2(best_hi, __vmaxs2(hi8, d[2 * j]));
+        best_hi = __vmins2(best_hi, __vmaxs2(hi8, d[(2 * j + 9) & 15]));
+    }
+    // bright: best_lo - 256; dark: 256 - best_hi; both re-biased by +256 (lanes of 512 - best_hi are in [1, 511])
+    return __vmaxs2(best_lo, 0x02000200u - best_hi);
+}
+
+// biased strength M = m + 256 -> score m - 1 if m > thr else 0
+__device__ __forceinline__ uint32_t score_from_strength(uint32_t M, int thr) { return (int)M > thr + 256 ? M - 257u : 0u; }
 
 __global__ void __launch_bounds__(FT_THREADS)
 k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, size_t slot_stride, Cand* __restrict__ cand,
        size_t cand_stride, FrameCounters* __restrict__ ctr)
 {
     __shared__ __align__(16) uint8_t s_img[FT_SH * FT_SP];
-    __shared__ uint8_t s_score[FT_CH * FT_CP];
-    __shared__ uint16_t s_queue[FT_NPOS];
+    __shared__ __align__(16) uint8_t s_score[FT_CH * FT_SP];
     __shared__ Cand s_emit[FT_EMIT];
-    __shared__ int s_qn, s_en, s_base;
+    __shared__ int s_en, s_base;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int frame = blockIdx.y;
 
     int level = 0;
@@ -64,10 +103,10 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
     const int w = L.w, h = L.h, pitch = L.pitch;
     const uint8_t* img = slots + frame * slot_stride + L.img_off;
     const int ox = 31 + tx * FT_TW, oy = 31 + ty * FT_TH;   // first output pixel of the tile
-    const int gx0 = ox - 15, gy0 = oy - 4;                  // image coords of s_img[0][0]; gx0 is a multiple of 16
+    const int gx0 = (ox - 4) & ~15, gy0 = oy - 4;           // image coordinates of s_img[0][0]
     const int thr = g.fast_threshold;
 
-    if (tid == 0) { s_qn = 0; s_en = 0; }
+    if (tid == 0) s_en = 0;
     for (int i = tid; i < FT_SH * (FT_SP / 16); i += FT_THREADS) {
         int r = i / (FT_SP / 16), v = i - r * (FT_SP / 16);
         int gy = gy0 + r, gx = gx0 + v * 16;
@@ -75,91 +114,64 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
         if (gy < h && gx < pitch) val = *reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx);
         *reinterpret_cast<uint4*>(s_img + r * FT_SP + v * 16) = val;
     }
-    for (int i = tid; i < FT_CH * FT_CP / 4; i += FT_THREADS) reinterpret_cast<uint32_t*>(s_score)[i] = 0;
     __syncthreads();
 
-    // ---- 1a: corner test over the score region (tile + 1 pixel each side)
-    for (int p0 = 0; p0 < FT_NPOS; p0 += FT_THREADS) {
-        const int p = p0 + tid;
-        bool corner = false, dark = false;
-        if (p < FT_NPOS) {
-            const int cy = p / FT_CW, cx = p - cy * FT_CW;
-            const int x = ox - 1 + cx, y = oy - 1 + cy;
-            if (x <= w - 31 && y <= h - 31) {
-                const uint8_t* c = s_img + (cy + 3) * FT_SP + (cx + 14);
-                const int v = c[0], hi = v + thr, lo = v - thr;
-                // compass pixels k = 0, 4, 8, 12: any 9-arc contains at least two of them
-                const int q0 = c[3 * FT_SP], q4 = c[3], q8 = c[-3 * FT_SP], q12 = c[-3];
-                const int nb = (q0 > hi) + (q4 > hi) + (q8 > hi) + (q12 > hi);
-                const int nd = (q0 < lo) + (q4 < lo) + (q8 < lo) + (q12 < lo);
-                if (nb >= 2 || nd >= 2) {
-                    int r[16];
-                    r[0] = q0; r[4] = q4; r[8] = q8; r[12] = q12;
-                    r[1] = c[3 * FT_SP + 1];  r[2] = c[2 * FT_SP + 2];   r[3] = c[FT_SP + 3];
-                    r[5] = c[-FT_SP + 3];     r[6] = c[-2 * FT_SP + 2];  r[7] = c[-3 * FT_SP + 1];
-                    r[9] = c[-3 * FT_SP - 1]; r[10] = c[-2 * FT_SP - 2]; r[11] = c[-FT_SP - 3];
-                    r[13] = c[FT_SP - 3];     r[14] = c[2 * FT_SP - 2];  r[15] = c[3 * FT_SP - 1];
-                    uint32_t bm = 0, dm = 0;
+    // ---- 1: scores of rows oy-1 .. oy+30, columns ox-3 .. ox+124 (32 groups of 4, group start is a multiple of 4)
+    const int c = (ox - 3 - gx0) + 4 * lane;   // smem column of the group's first pixel (multiple of 4)
+#pragma unroll 1
+    for (int it = 0; it < FT_CH / 8; it++) {
+        const int sr = wid + 8 * it;            // score row; its centre pixels sit in image smem row sr + 3
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(s_img + (sr + 3) * FT_SP + c - 4);
+        auto W = [&](int dy, int i) { return base[dy * (FT_SP / 4) + i]; };
+        // biased ring differences d[k] = I(ring k) - I(centre) + 256 for pixel pairs A = (c, c+1) and B = (c+2, c+3)
+        const uint32_t ctr4 = W(0, 1);
+        const uint32_t cA = 0x01000100u - lanes_lo(ctr4), cB = 0x01000100u - lanes_hi(ctr4);   // 256 - centre per lane
+        uint32_t dA[16], dB[16];
+#define RING(K, DX, DY)                                                    \
+        {                                                                  \
+            const uint32_t g4 = window4<DX>(W(DY, 0), W(DY, 1), W(DY, 2)); \
+            dA[K] = lanes_lo(g4) + cA;                                     \
+            dB[K] = lanes_hi(g4) + cB;                                     \
+        }
+        RING(0, 0, 3)   RING(1, 1, 3)    RING(2, 2, 2)    RING(3, 3, 1)
+        RING(4, 3, 0)   RING(5, 3, -1)   RING(6, 2, -2)   RING(7, 1, -3)
+        RING(8, 0, -3)  RING(9, -1, -3)  RING(10, -2, -2) RING(11, -3, -1)
+        RING(12, -3, 0) RING(13, -3, 1)  RING(14, -2, 2)  RING(15, -1, 3)
+#undef RING
+        const uint32_t mA = arc_strength2(dA), mB = arc_strength2(dB);
+        const uint32_t s0 = score_from_strength(mA & 0xFFFFu, thr);
+        const uint32_t s1 = score_from_strength(mA >> 16, thr);
+        const uint32_t s2 = score_from_strength(mB & 0xFFFFu, thr);
+        const uint32_t s3 = score_from_strength(mB >> 16, thr);
+        *reinterpret_cast<uint32_t*>(s_score + sr * FT_SP + c) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+    }
+    __syncthreads();
+
+    // ---- 2: non-max suppression on the tile proper (score row yy + 1, smem column ox - gx0 + xx)
+    const int cx0 = ox - gx0;                         // multiple of 4 plus 3: tile columns start inside a word
+    const int word0 = (cx0 & ~3), nwords = ((cx0 + FT_TW - 1) >> 2) - (cx0 >> 2) + 1;
+    for (int i = tid; i < nwords * FT_TH; i += FT_THREADS) {
+        const int yy = i / nwords, wi = i - yy * nwords;
+        const int col = word0 + 4 * wi;
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(s_score + (yy + 1) * FT_SP + col);
+        if (word == 0) continue;
+        const int y = oy + yy;
+        if (y >= h - 31) continue;
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        bm |= (uint32_t)(r[k] > hi) << k;
-                        dm |= (uint32_t)(r[k] < lo) << k;
-                    }
-                    dark = arc9(dm);
-                    corner = dark || arc9(bm);
-                }
+        for (int bq = 0; bq < 4; bq++) {
+            const int s = (word >> (8 * bq)) & 0xFF;
+            const int cc = col + bq;
+            const int x = gx0 + cc;
+            if (s == 0 || cc < cx0 || cc >= cx0 + FT_TW || x >= w - 31) continue;
+            const uint8_t* sp = s_score + (yy + 1) * FT_SP + cc;
+            if (s > sp[-1] && s > sp[1] && s > sp[-FT_SP - 1] && s > sp[-FT_SP] && s > sp[-FT_SP + 1] && s > sp[FT_SP - 1] &&
+                s > sp[FT_SP] && s > sp[FT_SP + 1]) {
+                int pos = atomicAdd(&s_en, 1);
+                Cand cnd;
+                cnd.xy = ((uint32_t)y << 16) | (uint32_t)x;
+                cnd.score = (uint32_t)s;
+                s_emit[pos] = cnd;
             }
-        }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, corner);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_qn, __popc(bal));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (corner) s_queue[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(p | (dark ? 0x8000 : 0));
-        }
-    }
-    __syncthreads();
-
-    // ---- 1b: exact score of the queued corners
-    const int qn = s_qn;
-    for (int i = tid; i < qn; i += FT_THREADS) {
-        const int e = s_queue[i];
-        const int p = e & 0x7FFF;
-        const int cy = p / FT_CW, cx = p - cy * FT_CW;
-        const uint8_t* c = s_img + (cy + 3) * FT_SP + (cx + 14);
-        const int v = c[0];
-        int d[16];
-        d[0] = c[3 * FT_SP];       d[1] = c[3 * FT_SP + 1];   d[2] = c[2 * FT_SP + 2];   d[3] = c[FT_SP + 3];
-        d[4] = c[3];               d[5] = c[-FT_SP + 3];      d[6] = c[-2 * FT_SP + 2];  d[7] = c[-3 * FT_SP + 1];
-        d[8] = c[-3 * FT_SP];      d[9] = c[-3 * FT_SP - 1];  d[10] = c[-2 * FT_SP - 2]; d[11] = c[-FT_SP - 3];
-        d[12] = c[-3];             d[13] = c[FT_SP - 3];      d[14] = c[2 * FT_SP - 2];  d[15] = c[3 * FT_SP - 1];
-        const bool dk = (e & 0x8000) != 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = dk ? v - d[k] : d[k] - v;   // positive on the corner's arc
-        int t3[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) t3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
-        int m = -256;
-#pragma unroll
-        for (int k = 0; k < 16; k++) m = max(m, min(min(t3[k], t3[(k + 3) & 15]), t3[(k + 6) & 15]));
-        s_score[cy * FT_CP + cx] = (uint8_t)(m - 1);   // m in (thr, 255]
-    }
-    __syncthreads();
-
-    // ---- 2: non-max suppression on the tile proper
-    for (int p = tid; p < FT_TW * FT_TH; p += FT_THREADS) {
-        const int yy = p / FT_TW, xx = p - yy * FT_TW;
-        const int x = ox + xx, y = oy + yy;
-        const uint8_t* sp = s_score + (yy + 1) * FT_CP + (xx + 1);
-        const int s = sp[0];
-        if (s == 0 || x >= w - 31 || y >= h - 31) continue;
-        if (s > sp[-1] && s > sp[1] && s > sp[-FT_CP - 1] && s > sp[-FT_CP] && s > sp[-FT_CP + 1] && s > sp[FT_CP - 1] &&
-            s > sp[FT_CP] && s > sp[FT_CP + 1]) {
-            int pos = atomicAdd(&s_en, 1);
-            Cand cnd;
-            cnd.xy = ((uint32_t)y << 16) | (uint32_t)x;
-            cnd.score = (uint32_t)s;
-            s_emit[pos] = cnd;
         }
     }
     __syncthreads();

@@ -361,11 +361,12 @@ def run_ours(args, rank, world, local_rank):
         def step_ham():
             out["r"] = sm.knn2(q, t_shard, rank * nt_shard)
         ham_steps = max(2, min(args.steps, 3))
-        ham_ms, _ = timed(step_ham, ham_steps, 1)
+        ham_sampler = ClockSampler(local_rank)
+        ham_ms, _ = timed(step_ham, ham_steps, 1, ham_sampler)
         ham_ms = max_over_ranks(ham_ms) / ham_steps
         gpopc, _ = popc_peak(local_rank)
         gcmp = world * nq * nt_shard / (ham_ms * 1e-3) / 1e9
-        hamming = {"value": gcmp, "unit": "Gcmp/s", "nq": nq, "nt_per_gpu": nt_shard, "ms_per_step": ham_ms,
+        hamming = {"value": gcmp, "unit": "Gcmp/s", "nq": nq, "nt_per_gpu": nt_shard, "ms_per_step": ham_ms, "clocks": ham_sampler.summary(),
                    "workload": "%d queries x %d train rows per GPU (train-sharded, 1 all-gather of 16 B/query/rank + merge)" % (nq, nt_shard),
                    "roofline": {"bound": "int_popc", "achieved": gcmp * 8, "peak": gpopc * world, "unit": "Gpopc/s",
                                 "frac": gcmp * 8 / (gpopc * world),

@@ -38,6 +38,9 @@ struct orbx_context {
     orbx_params p;
     int max_w, max_h, max_batch;
     cudaStream_t own_stream, stream;
+    cudaStream_t copy_stream;                 // host-buffer path: uploads of chunk i+1 overlap the kernels of chunk i
+    std::vector<cudaEvent_t>* copy_events;
+    cudaEvent_t order_event;                  // makes the copy stream wait for work already queued on the compute stream
     // geometry: `gmax` sizes the allocations, `g` is the geometry of the frame size last used
     FrameGeom gmax, g;
     int geom_w, geom_h;
@@ -278,6 +281,9 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     h->h_tab = new std::vector<uint8_t>(h->tab_bytes);
 
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    ORBX_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    h->copy_events = new std::vector<cudaEvent_t>();
+    ORBX_CUDA(cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming));
     h->stream = h->own_stream;
     const size_t B = (size_t)max_batch;
 #define ORBX_ALLOC(ptr, bytes)                                                                            \
@@ -326,6 +332,9 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->order_event) cudaEventDestroy(h->order_event);
+    if (h->copy_events) { for (cudaEvent_t e : *h->copy_events) cudaEventDestroy(e); delete h->copy_events; }
     delete h->h_tab;
     delete h;
     return ORBX_OK;
@@ -364,19 +373,20 @@ extern "C" int orbx_level_info(orbx_handle h, int w, int hh, int32_t* widths, in
 }
 
 // ---------------------------------------------------------------------------------------------- pipeline
-static int build_pyramids(orbx_handle h, int nframes)
+static int build_pyramids(orbx_handle h, int f0, int nframes)
 {
     for (int l = 1; l < h->g.nlevels; l++)
-        ORBX_CUDA(launch_pyr_down_level(h->d_slots, h->slot_stride, h->g.lv[l - 1], h->g.lv[l], h->pyr_sw[l], h->pyr_sh[l], nframes,
-                                        h->stream));
+        ORBX_CUDA(launch_pyr_down_level(h->d_slots + (size_t)f0 * h->slot_stride, h->slot_stride, h->g.lv[l - 1], h->g.lv[l],
+                                        h->pyr_sw[l], h->pyr_sh[l], nframes, h->stream));
     return ORBX_OK;
 }
 
-static int upload_frames(orbx_handle h, const uint8_t* const* frames, int nframes, int w, int hh, size_t stride, cudaMemcpyKind kind)
+static int upload_frames(orbx_handle h, const uint8_t* const* frames, int f0, int nframes, int w, int hh, size_t stride,
+                         cudaMemcpyKind kind, cudaStream_t s)
 {
-    for (int f = 0; f < nframes; f++)
+    for (int f = f0; f < f0 + nframes; f++)
         ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)f * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch, frames[f], stride,
-                                    (size_t)w, (size_t)hh, kind, h->stream));
+                                    (size_t)w, (size_t)hh, kind, s));
     return ORBX_OK;
 }
 
@@ -393,23 +403,30 @@ static int stage_mark(orbx_handle h)
     return ORBX_OK;
 }
 
-static int run_extract(orbx_handle h, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
+// frames [f0, f0 + nframes) of the handle's slots; d_out / d_desc / d_counts are the arrays of the WHOLE batch
+static int run_extract(orbx_handle h, int f0, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
 {
-    ORBX_CUDA(cudaMemsetAsync(h->d_ctr, 0, (size_t)nframes * sizeof(FrameCounters), h->stream));
+    uint8_t* slots = h->d_slots + (size_t)f0 * h->slot_stride;
+    Cand* cand = h->d_cand + (size_t)f0 * h->cand_stride;
+    Cand* surv = h->d_surv + (size_t)f0 * h->surv_stride;
+    Sel* sel = h->d_sel + (size_t)f0 * h->sel_stride;
+    FrameCounters* ctr = h->d_ctr + f0;
+    ORBX_CUDA(cudaMemsetAsync(ctr, 0, (size_t)nframes * sizeof(FrameCounters), h->stream));
     int rc = stage_mark(h);
     if (rc) return rc;
-    rc = build_pyramids(h, nframes);
+    rc = build_pyramids(h, f0, nframes);
     if (rc) return rc;
     if ((rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_fast(h->g, h->d_slots, h->slot_stride, h->d_cand, h->cand_stride, h->d_ctr, nframes, h->stream));
+    ORBX_CUDA(launch_fast(h->g, slots, h->slot_stride, cand, h->cand_stride, ctr, nframes, h->stream));
     if ((rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_select(h->g, h->d_cand, h->cand_stride, h->d_surv, h->surv_stride, h->d_ctr, nframes, h->stream));
+    ORBX_CUDA(launch_select(h->g, cand, h->cand_stride, surv, h->surv_stride, ctr, nframes, h->stream));
     if ((rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_harris_select(h->g, h->d_slots, h->slot_stride, h->d_surv, h->surv_stride, h->d_sel, h->sel_stride, h->d_ctr,
-                                   nframes, h->max_surv_cap, h->harris_s4, h->stream));
+    ORBX_CUDA(launch_harris_select(h->g, slots, h->slot_stride, surv, h->surv_stride, sel, h->sel_stride, ctr, nframes,
+                                   h->max_surv_cap, h->harris_s4, h->stream));
     if ((rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_orient_describe(h->g, h->d_slots, h->slot_stride, h->d_sel, h->sel_stride, h->d_ctr, d_out,
-                                     (mode & ORBX_DO_DESC) ? d_desc : nullptr, cap, d_counts, nframes, mode, h->stream));
+    ORBX_CUDA(launch_orient_describe(h->g, slots, h->slot_stride, sel, h->sel_stride, ctr, d_out + (size_t)f0 * cap,
+                                     (mode & ORBX_DO_DESC) ? d_desc + (size_t)f0 * cap * 32 : nullptr, cap, d_counts + f0, nframes,
+                                     mode, h->stream));
     return stage_mark(h);
 }
 
@@ -472,10 +489,27 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
     int rc = common_checks(h, frames[0], w, hh, stride, fn);
     if (rc) return rc;
     const int dcap = std::min(cap, h->dev_cap);
-    rc = upload_frames(h, frames, nframes, w, hh, stride, cudaMemcpyHostToDevice);
-    if (rc) return rc;
-    rc = run_extract(h, nframes, mode, h->d_kps, h->d_desc, dcap, h->d_counts);
-    if (rc) return rc;
+    // chunks of 16 frames: the upload of chunk i+1 (copy stream) overlaps the kernels of chunk i (compute stream)
+    const int chunk = 16, nchunks = div_up(nframes, chunk);
+    while ((int)h->copy_events->size() < nchunks) {
+        cudaEvent_t e;
+        ORBX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->copy_events->push_back(e);
+    }
+    ORBX_CUDA(cudaEventRecord(h->order_event, h->stream));          // e.g. an earlier asynchronous _dev submission
+    ORBX_CUDA(cudaStreamWaitEvent(h->copy_stream, h->order_event, 0));
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * chunk, n = std::min(chunk, nframes - f0);
+        rc = upload_frames(h, frames, f0, n, w, hh, stride, cudaMemcpyHostToDevice, h->copy_stream);
+        if (rc) return rc;
+        ORBX_CUDA(cudaEventRecord((*h->copy_events)[c], h->copy_stream));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * chunk, n = std::min(chunk, nframes - f0);
+        ORBX_CUDA(cudaStreamWaitEvent(h->stream, (*h->copy_events)[c], 0));
+        rc = run_extract(h, f0, n, mode, h->d_kps, h->d_desc, dcap, h->d_counts);
+        if (rc) return rc;
+    }
     h->last_nframes = (mode & ORBX_DO_DESC) ? nframes : 0;
     h->last_cap = dcap;
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
@@ -544,7 +578,7 @@ extern "C" int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, si
     for (int f = 0; f < nframes; f++)
         ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)f * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch,
                                     d_frames + (size_t)f * frame_pitch_bytes, stride, (size_t)w, (size_t)hh, cudaMemcpyDeviceToDevice, h->stream));
-    rc = run_extract(h, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_out, d_desc, cap, d_counts);
+    rc = run_extract(h, 0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_out, d_desc, cap, d_counts);
     if (rc) return rc;
     h->dev_pending = true;
     return ORBX_OK;
@@ -591,9 +625,9 @@ extern "C" int orbx_compute(orbx_handle h, const uint8_t* gray, int w, int hh, s
     if (m == 0) return ORBX_OK;
     memcpy(kps, kept.data(), (size_t)m * sizeof(orbx_keypoint));
     const uint8_t* frames[1] = { gray };
-    rc = upload_frames(h, frames, 1, w, hh, stride, cudaMemcpyHostToDevice);
+    rc = upload_frames(h, frames, 0, 1, w, hh, stride, cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;
-    rc = build_pyramids(h, 1);   // the reference path rebuilds the pyramid in compute() as well
+    rc = build_pyramids(h, 0, 1);   // the reference path rebuilds the pyramid in compute() as well
     if (rc) return rc;
     ORBX_CUDA(cudaMemcpyAsync(h->d_kps, kps, (size_t)m * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, h->stream));
     ORBX_CUDA(launch_describe_given(h->g, h->d_slots, h->d_kps, m, h->d_desc, h->stream));
@@ -643,9 +677,9 @@ extern "C" int orbx_debug_pyramid_level(orbx_handle h, const uint8_t* gray, int 
     if (rc) return rc;
     ORBX_REQUIRE(out && level >= 0 && level < h->g.nlevels, "orbx_debug_pyramid_level: bad level %d", level);
     const uint8_t* frames[1] = { gray };
-    rc = upload_frames(h, frames, 1, w, hh, stride, cudaMemcpyHostToDevice);
+    rc = upload_frames(h, frames, 0, 1, w, hh, stride, cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;
-    rc = build_pyramids(h, 1);
+    rc = build_pyramids(h, 0, 1);
     if (rc) return rc;
     const LevelGeom& L = h->g.lv[level];
     ORBX_CUDA(cudaMemcpy2DAsync(out, L.w, h->d_slots + L.img_off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
@@ -660,10 +694,10 @@ extern "C" int orbx_debug_fast_level(orbx_handle h, const uint8_t* gray, int w, 
     if (rc) return rc;
     ORBX_REQUIRE(xs && ys && scores && n && level >= 0 && level < h->g.nlevels, "orbx_debug_fast_level: bad arguments");
     const uint8_t* frames[1] = { gray };
-    rc = upload_frames(h, frames, 1, w, hh, stride, cudaMemcpyHostToDevice);
+    rc = upload_frames(h, frames, 0, 1, w, hh, stride, cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;
     ORBX_CUDA(cudaMemsetAsync(h->d_ctr, 0, sizeof(FrameCounters), h->stream));
-    rc = build_pyramids(h, 1);
+    rc = build_pyramids(h, 0, 1);
     if (rc) return rc;
     ORBX_CUDA(launch_fast(h->g, h->d_slots, h->slot_stride, h->d_cand, h->cand_stride, h->d_ctr, 1, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));

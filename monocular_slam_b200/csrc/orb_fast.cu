@@ -8,13 +8,16 @@
 //   and 31 <= x < w-31, 31 <= y < h-31.
 //
 // A CTA owns a 124x30 tile of the interior [31,w-31) x [31,h-31) of one level.  It stages the tile plus a 4-pixel
-// halo in shared memory with 16-byte loads (rows are 128-byte pitched), then
+// halo in shared memory with 16-byte loads (rows are 128-byte pitched), widening every pixel to 16 bits on the way so
+// that two horizontally adjacent pixels already form one packed s16x2 register operand, then
 //   1. scores the (tile + 1) region branch-free, four horizontally adjacent pixels per thread and two pixels per
 //      instruction: ring-minus-centre differences live in packed s16x2 lanes (VIADD.16x2) and the sliding
 //      9-of-16 window minimum / maximum is a log-step network of VIMNMX.S16x2 (55 min/max per sign and pixel pair),
 //      which yields m = max(max_k min9(d), -min_k max9(d)) exactly -- no corner pre-test, no divergence.  A warp
-//      covers one score row (32 groups of 4 pixels), 21 aligned 32-bit shared-memory loads feed 4 pixels;
-//   2. NMS on the score tile (a whole word of four zero scores is skipped at once); survivors are staged in shared
+//      covers one score row (32 groups of 4 pixels); 21 aligned 64-bit shared-memory loads and 18 byte-permutes feed
+//      4 pixels (ring columns at even offsets are register operands as loaded);
+//   2. NMS on the score tile, again four pixels per thread in packed u16x2 lanes: the 8-neighbour maximum is three
+//      3-input VIMNMX per pixel pair and "strictly greater" is one subtraction + sign test; survivors are staged in shared
 //      memory, the CTA reserves its range of the level's candidate list with ONE global atomic and writes
 //      (x, y, score); the per-level score histogram used by the retainBest cut (K3) gets one RED per survivor.
 // Bound: integer ALU issue (VIMNMX/PRMT), not HBM: each level byte is read once from HBM and ~1.4x from L2.
@@ -34,19 +37,8 @@ constexpr int FT_EMIT = (FT_TW / 2 + 1) * (FT_TH / 2 + 1);   // NMS allows at mo
 // 16x2 lanes from bytes (0,1) / (2,3) of g
 __device__ __forceinline__ uint32_t lanes_lo(uint32_t g) { return __byte_perm(g, 0u, 0x4140); }
 __device__ __forceinline__ uint32_t lanes_hi(uint32_t g) { return __byte_perm(g, 0u, 0x4342); }
-
-// bytes [4 + dx, 8 + dx) of the 12-byte window {w0, w1, w2} (w1 holds the four centre columns)
-template <int DX>
-__device__ __forceinline__ uint32_t window4(uint32_t w0, uint32_t w1, uint32_t w2)
-{
-    if (DX == 0) return w1;
-    if (DX == -1) return __byte_perm(w0, w1, 0x6543);
-    if (DX == -2) return __byte_perm(w0, w1, 0x5432);
-    if (DX == -3) return __byte_perm(w0, w1, 0x4321);
-    if (DX == 1) return __byte_perm(w1, w2, 0x4321);
-    if (DX == 2) return __byte_perm(w1, w2, 0x5432);
-    return __byte_perm(w1, w2, 0x6543);   // DX == 3
-}
+// lanes (hi of a, lo of b): the pixel pair that straddles two aligned pairs
+__device__ __forceinline__ uint32_t straddle(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5432); }
 
 // m + 256, m = max over the 16 arcs of 9 contiguous ring positions of max(min d, min -d), for two pixels at once.
 // d[] holds the BIASED differences I(ring) - I(centre) + 256 in s16x2 lanes: every lane stays in [1, 511], so the
@@ -80,15 +72,12 @@ __device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&d)[16])
     return __vmaxs2(best_lo, 0x02000200u - best_hi);
 }
 
-// biased strength M = m + 256 -> score m - 1 if m > thr else 0
-__device__ __forceinline__ uint32_t score_from_strength(uint32_t M, int thr) { return (int)M > thr + 256 ? M - 257u : 0u; }
-
 __global__ void __launch_bounds__(FT_THREADS)
 k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, size_t slot_stride, Cand* __restrict__ cand,
        size_t cand_stride, FrameCounters* __restrict__ ctr)
 {
-    __shared__ __align__(16) uint8_t s_img[FT_SH * FT_SP];
-    __shared__ __align__(16) uint8_t s_score[FT_CH * FT_SP];
+    __shared__ __align__(16) uint16_t s_img[FT_SH * FT_SP];       // pixels widened to 16 bits
+    __shared__ __align__(16) uint16_t s_score[FT_CH * FT_SP];     // m - thr for corners (1 .. 255 - thr), 0 otherwise
     __shared__ Cand s_emit[FT_EMIT];
     __shared__ int s_en, s_base;
 
@@ -107,69 +96,108 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
     const int thr = g.fast_threshold;
 
     if (tid == 0) s_en = 0;
+    for (int i = tid; i < FT_CH * FT_SP / 8; i += FT_THREADS) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < FT_SH * (FT_SP / 16); i += FT_THREADS) {
         int r = i / (FT_SP / 16), v = i - r * (FT_SP / 16);
         int gy = gy0 + r, gx = gx0 + v * 16;
         uint4 val = make_uint4(0, 0, 0, 0);
         if (gy < h && gx < pitch) val = *reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx);
-        *reinterpret_cast<uint4*>(s_img + r * FT_SP + v * 16) = val;
+        uint4* dst = reinterpret_cast<uint4*>(s_img + r * FT_SP + v * 16);
+        dst[0] = make_uint4(lanes_lo(val.x), lanes_hi(val.x), lanes_lo(val.y), lanes_hi(val.y));
+        dst[1] = make_uint4(lanes_lo(val.z), lanes_hi(val.z), lanes_lo(val.w), lanes_hi(val.w));
     }
     __syncthreads();
 
     // ---- 1: scores of rows oy-1 .. oy+30, columns ox-3 .. ox+124 (32 groups of 4, group start is a multiple of 4)
     const int c = (ox - 3 - gx0) + 4 * lane;   // smem column of the group's first pixel (multiple of 4)
+    const uint32_t K = (uint32_t)(thr + 256) * 0x00010001u;
 #pragma unroll 1
     for (int it = 0; it < FT_CH / 8; it++) {
         const int sr = wid + 8 * it;            // score row; its centre pixels sit in image smem row sr + 3
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(s_img + (sr + 3) * FT_SP + c - 4);
-        auto W = [&](int dy, int i) { return base[dy * (FT_SP / 4) + i]; };
-        // biased ring differences d[k] = I(ring k) - I(centre) + 256 for pixel pairs A = (c, c+1) and B = (c+2, c+3)
-        const uint32_t ctr4 = W(0, 1);
-        const uint32_t cA = 0x01000100u - lanes_lo(ctr4), cB = 0x01000100u - lanes_hi(ctr4);   // 256 - centre per lane
-        uint32_t dA[16], dB[16];
-#define RING(K, DX, DY)                                                    \
-        {                                                                  \
-            const uint32_t g4 = window4<DX>(W(DY, 0), W(DY, 1), W(DY, 2)); \
-            dA[K] = lanes_lo(g4) + cA;                                     \
-            dB[K] = lanes_hi(g4) + cB;                                     \
+        // pixel pairs of row dy: q[i] = pixels (c - 4 + 2i, c - 3 + 2i), i = 0..5, as s16x2 registers
+        const uint2* base = reinterpret_cast<const uint2*>(s_img + (sr + 3) * FT_SP + c - 4);
+        auto P = [&](int dy, int i) { return base[dy * (FT_SP / 4) + i]; };
+        uint32_t dA[16], dB[16];   // biased ring differences for pixel pairs A = (c, c+1), B = (c+2, c+3)
+        {
+            const uint2 p0 = P(0, 0), p1 = P(0, 1), p2 = P(0, 2);          // row y: centre, ring 4 (dx +3), ring 12 (dx -3)
+            const uint32_t cA = 0x01000100u - p1.x, cB = 0x01000100u - p1.y;   // 256 - centre per lane
+            dA[4] = straddle(p1.y, p2.x) + cA;  dB[4] = straddle(p2.x, p2.y) + cB;
+            dA[12] = straddle(p0.x, p0.y) + cA; dB[12] = straddle(p0.y, p1.x) + cB;
+#define ROW3(DY, KM, K0, KP)   /* rows y +- 3: dx -1, 0, +1 */                                   \
+            {                                                                                     \
+                const uint2 a0 = P(DY, 0), a1 = P(DY, 1), a2 = P(DY, 2);                          \
+                const uint32_t m = straddle(a0.y, a1.x), z = straddle(a1.x, a1.y), n = straddle(a1.y, a2.x); \
+                dA[KM] = m + cA;    dB[KM] = z + cB;                                              \
+                dA[K0] = a1.x + cA; dB[K0] = a1.y + cB;                                           \
+                dA[KP] = z + cA;    dB[KP] = n + cB;                                              \
+            }
+#define ROW2(DY, KM, KP)       /* rows y +- 2: dx -2, +2 */                                       \
+            {                                                                                     \
+                const uint2 a0 = P(DY, 0), a1 = P(DY, 1), a2 = P(DY, 2);                          \
+                dA[KM] = a0.y + cA; dB[KM] = a1.x + cB;                                           \
+                dA[KP] = a1.y + cA; dB[KP] = a2.x + cB;                                           \
+            }
+#define ROW1(DY, KM, KP)       /* rows y +- 1: dx -3, +3 */                                       \
+            {                                                                                     \
+                const uint2 a0 = P(DY, 0), a1 = P(DY, 1), a2 = P(DY, 2);                          \
+                dA[KM] = straddle(a0.x, a0.y) + cA; dB[KM] = straddle(a0.y, a1.x) + cB;           \
+                dA[KP] = straddle(a1.y, a2.x) + cA; dB[KP] = straddle(a2.x, a2.y) + cB;           \
+            }
+            ROW3(3, 15, 0, 1)    // ring 15 (-1,+3), 0 (0,+3), 1 (+1,+3)
+            ROW2(2, 14, 2)       // ring 14 (-2,+2), 2 (+2,+2)
+            ROW1(1, 13, 3)       // ring 13 (-3,+1), 3 (+3,+1)
+            ROW1(-1, 11, 5)      // ring 11 (-3,-1), 5 (+3,-1)
+            ROW2(-2, 10, 6)      // ring 10 (-2,-2), 6 (+2,-2)
+            ROW3(-3, 9, 8, 7)    // ring 9 (-1,-3), 8 (0,-3), 7 (+1,-3)
+#undef ROW3
+#undef ROW2
+#undef ROW1
         }
-        RING(0, 0, 3)   RING(1, 1, 3)    RING(2, 2, 2)    RING(3, 3, 1)
-        RING(4, 3, 0)   RING(5, 3, -1)   RING(6, 2, -2)   RING(7, 1, -3)
-        RING(8, 0, -3)  RING(9, -1, -3)  RING(10, -2, -2) RING(11, -3, -1)
-        RING(12, -3, 0) RING(13, -3, 1)  RING(14, -2, 2)  RING(15, -1, 3)
-#undef RING
-        const uint32_t mA = arc_strength2(dA), mB = arc_strength2(dB);
-        const uint32_t s0 = score_from_strength(mA & 0xFFFFu, thr);
-        const uint32_t s1 = score_from_strength(mA >> 16, thr);
-        const uint32_t s2 = score_from_strength(mB & 0xFFFFu, thr);
-        const uint32_t s3 = score_from_strength(mB >> 16, thr);
-        *reinterpret_cast<uint32_t*>(s_score + sr * FT_SP + c) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+        // biased strength M = m + 256; store m - thr for corners, 0 otherwise (order-preserving, so NMS is unaffected)
+        const uint32_t sA = __vmaxs2(arc_strength2(dA), K) - K, sB = __vmaxs2(arc_strength2(dB), K) - K;
+        *reinterpret_cast<uint2*>(s_score + sr * FT_SP + c) = make_uint2(sA, sB);
     }
     __syncthreads();
 
-    // ---- 2: non-max suppression on the tile proper (score row yy + 1, smem column ox - gx0 + xx)
-    const int cx0 = ox - gx0;                         // multiple of 4 plus 3: tile columns start inside a word
-    const int word0 = (cx0 & ~3), nwords = ((cx0 + FT_TW - 1) >> 2) - (cx0 >> 2) + 1;
-    for (int i = tid; i < nwords * FT_TH; i += FT_THREADS) {
-        const int yy = i / nwords, wi = i - yy * nwords;
-        const int col = word0 + 4 * wi;
-        const uint32_t word = *reinterpret_cast<const uint32_t*>(s_score + (yy + 1) * FT_SP + col);
-        if (word == 0) continue;
-        const int y = oy + yy;
-        if (y >= h - 31) continue;
+    // ---- 2: non-max suppression on the tile proper: same thread -> group mapping as above, score rows 1 .. 30
+    const int cx0 = ox - gx0;                         // smem column of the tile's first pixel
+#pragma unroll 1
+    for (int it = 0; it < FT_CH / 8; it++) {
+        const int sr = wid + 8 * it;
+        const int y = oy - 1 + sr;
+        if (sr == 0 || sr == FT_CH - 1 || y >= h - 31) continue;
+        const uint16_t* rowp = s_score + sr * FT_SP + c;
+        const uint2 mid = *reinterpret_cast<const uint2*>(rowp);             // pairs A = (c, c+1), B = (c+2, c+3)
+        if ((mid.x | mid.y) == 0) continue;                                    // no corner among the four pixels
+        uint32_t nA, nB;                                                       // maximum over the 8 neighbours, per lane
+        {
+            const uint32_t l = *reinterpret_cast<const uint32_t*>(rowp - 2), r = *reinterpret_cast<const uint32_t*>(rowp + 4);
+            const uint32_t z = straddle(mid.x, mid.y);
+            nA = __vmaxu2(straddle(l, mid.x), z);
+            nB = __vmaxu2(z, straddle(mid.y, r));
+        }
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy += 2) {
+            const uint16_t* q = rowp + dy * FT_SP;
+            const uint2 m2 = *reinterpret_cast<const uint2*>(q);
+            const uint32_t l = *reinterpret_cast<const uint32_t*>(q - 2), r = *reinterpret_cast<const uint32_t*>(q + 4);
+            const uint32_t z = straddle(m2.x, m2.y);
+            nA = __vmaxu2(nA, __vmaxu2(__vmaxu2(straddle(l, m2.x), m2.x), z));
+            nB = __vmaxu2(nB, __vmaxu2(__vmaxu2(z, m2.y), straddle(m2.y, r)));
+        }
+        // strictly greater than every neighbour <=> score - nmax > 0 (lanes are in [0, 255], so plain 32-bit
+        // subtraction of (nmax) from (score + 256) cannot borrow across lanes)
+        const uint32_t fA = (mid.x | 0x01000100u) - nA, fB = (mid.y | 0x01000100u) - nB;
+        const uint32_t lanes[4] = { fA & 0xFFFFu, fA >> 16, fB & 0xFFFFu, fB >> 16 };
+        const uint32_t sc[4] = { mid.x & 0xFFFFu, mid.x >> 16, mid.y & 0xFFFFu, mid.y >> 16 };
 #pragma unroll
         for (int bq = 0; bq < 4; bq++) {
-            const int s = (word >> (8 * bq)) & 0xFF;
-            const int cc = col + bq;
-            const int x = gx0 + cc;
-            if (s == 0 || cc < cx0 || cc >= cx0 + FT_TW || x >= w - 31) continue;
-            const uint8_t* sp = s_score + (yy + 1) * FT_SP + cc;
-            if (s > sp[-1] && s > sp[1] && s > sp[-FT_SP - 1] && s > sp[-FT_SP] && s > sp[-FT_SP + 1] && s > sp[FT_SP - 1] &&
-                s > sp[FT_SP] && s > sp[FT_SP + 1]) {
+            const int cc = c + bq, x = gx0 + cc;
+            if (lanes[bq] > 256u && cc >= cx0 && cc < cx0 + FT_TW && x < w - 31) {
                 int pos = atomicAdd(&s_en, 1);
                 Cand cnd;
                 cnd.xy = ((uint32_t)y << 16) | (uint32_t)x;
-                cnd.score = (uint32_t)s;
+                cnd.score = sc[bq] + (uint32_t)thr - 1u;   // FAST score = m - 1
                 s_emit[pos] = cnd;
             }
         }

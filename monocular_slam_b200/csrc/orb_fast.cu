@@ -11,9 +11,10 @@
 // halo in shared memory with 16-byte loads (rows are 128-byte pitched), widening every pixel to 16 bits on the way so
 // that two horizontally adjacent pixels already form one packed s16x2 register operand, then
 //   1. scores the (tile + 1) region branch-free, four horizontally adjacent pixels per thread and two pixels per
-//      instruction: ring-minus-centre differences live in packed s16x2 lanes (VIADD.16x2) and the sliding
-//      9-of-16 window minimum / maximum is a log-step network of VIMNMX.S16x2 (55 min/max per sign and pixel pair),
-//      which yields m = max(max_k min9(d), -min_k max9(d)) exactly -- no corner pre-test, no divergence.  A warp
+//      instruction: the RAW ring pixels live in packed 16x2 lanes and the sliding 9-of-16 window minimum / maximum
+//      is a network of VIMNMX.S16x2 / VIMNMX3.S16x2 (36 per sign and pixel pair); min/max is shift-invariant, so the
+//      centre is subtracted once from the two results instead of from the 16 ring pixels, which yields
+//      m = max(max_k min9(ring) - c, c - min_k max9(ring)) exactly -- no corner pre-test, no divergence.  A warp
 //      covers one score row (32 groups of 4 pixels); 21 aligned 64-bit shared-memory loads and 18 byte-permutes feed
 //      4 pixels (ring columns at even offsets are register operands as loaded);
 //   2. NMS on the score tile, again four pixels per thread in packed u16x2 lanes: the 8-neighbour maximum is three
@@ -40,17 +41,20 @@ __device__ __forceinline__ uint32_t lanes_hi(uint32_t g) { return __byte_perm(g,
 // lanes (hi of a, lo of b): the pixel pair that straddles two aligned pairs
 __device__ __forceinline__ uint32_t straddle(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5432); }
 
-// m + 256, m = max over the 16 arcs of 9 contiguous ring positions of max(min d, min -d), for two pixels at once.
-// d[] holds the BIASED differences I(ring) - I(centre) + 256 in s16x2 lanes: every lane stays in [1, 511], so the
-// per-lane additions that produce them are plain 32-bit adds (no carry between lanes, and ptxas may place them on the
-// FMA pipe as IMAD.IADD), while the min/max network is shift-invariant.
-__device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&d)[16])
+// thr-clamped corner strength of two pixels at once.  r[] holds the RAW ring pixels (0..255) in 16x2 lanes, c the centre
+// pixels.  Sliding min/max is shift-invariant, so the centre is subtracted once at the end instead of from every ring
+// pixel:  m = max(max_arcs min_arc(ring) - c, c - min_arcs max_arc(ring)).
+// Arc k = ring positions k .. k+8.  With W_j = positions 2j+1 .. 2j+8 (min of two 4-windows), arcs 2j and 2j+1 are
+// W_j extended by position 2j resp. 2j+9, and max(min(W,a), min(W,b)) == min(W, max(a,b)), so both arcs cost one
+// 2-input and one 3-input instruction: 36 VIMNMX(3).S16x2 per sign and pixel pair (8 + 8 + 8 + 8 + 4).
+// Returns max(m - thr, 0) per lane; K = (thr + 256) in both lanes.
+__device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&r)[16], uint32_t c, uint32_t K)
 {
     uint32_t lo2[8], hi2[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {       // window {2j+1, 2j+2}
-        lo2[j] = __vmins2(d[2 * j + 1], d[(2 * j + 2) & 15]);
-        hi2[j] = __vmaxs2(d[2 * j + 1], d[(2 * j + 2) & 15]);
+        lo2[j] = __vmins2(r[2 * j + 1], r[(2 * j + 2) & 15]);
+        hi2[j] = __vmaxs2(r[2 * j + 1], r[(2 * j + 2) & 15]);
     }
     uint32_t lo4[8], hi4[8];
 #pragma unroll
@@ -58,18 +62,20 @@ __device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&d)[16])
         lo4[j] = __vmins2(lo2[j], lo2[(j + 1) & 7]);
         hi4[j] = __vmaxs2(hi2[j], hi2[(j + 1) & 7]);
     }
-    uint32_t best_lo = 0u, best_hi = 0x7FFF7FFFu;   // running max of arc minima / min of arc maxima
+    uint32_t alo[8], ahi[8];            // best of arcs 2j and 2j+1
 #pragma unroll
-    for (int j = 0; j < 8; j++) {       // window 2j+1 .. 2j+8, extended by 2j (arc 2j) or 2j+9 (arc 2j+1)
-        const uint32_t lo8 = __vmins2(lo4[j], lo4[(j + 2) & 7]);
-        const uint32_t hi8 = __vmaxs2(hi4[j], hi4[(j + 2) & 7]);
-        best_lo = __vmaxs2(best_lo, __vmins2(lo8, d[2 * j]));
-        best_lo = __vmaxs2(best_lo, __vmins2(lo8, d[(2 * j + 9) & 15]));
-        best_hi = __vmins2(best_hi, __vmaxs2(hi8, d[2 * j]));
-        best_hi = __vmins2(best_hi, __vmaxs2(hi8, d[(2 * j + 9) & 15]));
+    for (int j = 0; j < 8; j++) {
+        const uint32_t e0 = r[2 * j], e1 = r[(2 * j + 9) & 15];
+        alo[j] = __vimin3_s16x2(lo4[j], lo4[(j + 2) & 7], __vmaxs2(e0, e1));
+        ahi[j] = __vimax3_s16x2(hi4[j], hi4[(j + 2) & 7], __vmins2(e0, e1));
     }
-    // bright: best_lo - 256; dark: 256 - best_hi; both re-biased by +256 (lanes of 512 - best_hi are in [1, 511])
-    return __vmaxs2(best_lo, 0x02000200u - best_hi);
+    const uint32_t best_lo = __vimax3_s16x2(__vimax3_s16x2(alo[0], alo[1], alo[2]), __vimax3_s16x2(alo[3], alo[4], alo[5]),
+                                            __vmaxs2(alo[6], alo[7]));
+    const uint32_t best_hi = __vimin3_s16x2(__vimin3_s16x2(ahi[0], ahi[1], ahi[2]), __vimin3_s16x2(ahi[3], ahi[4], ahi[5]),
+                                            __vmins2(ahi[6], ahi[7]));
+    // bright: best_lo - c, dark: c - best_hi, both biased by +256 so every lane stays in [1, 511] (plain 32-bit adds)
+    const uint32_t bright = best_lo + 0x01000100u - c, dark = c + 0x01000100u - best_hi;
+    return __vimax3_s16x2(bright, dark, K) - K;
 }
 
 __global__ void __launch_bounds__(FT_THREADS)
@@ -117,31 +123,32 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
         // pixel pairs of row dy: q[i] = pixels (c - 4 + 2i, c - 3 + 2i), i = 0..5, as s16x2 registers
         const uint2* base = reinterpret_cast<const uint2*>(s_img + (sr + 3) * FT_SP + c - 4);
         auto P = [&](int dy, int i) { return base[dy * (FT_SP / 4) + i]; };
-        uint32_t dA[16], dB[16];   // biased ring differences for pixel pairs A = (c, c+1), B = (c+2, c+3)
+        uint32_t rA[16], rB[16];   // raw ring pixels for pixel pairs A = (c, c+1), B = (c+2, c+3)
+        uint32_t cA, cB;           // centre pixels
         {
             const uint2 p0 = P(0, 0), p1 = P(0, 1), p2 = P(0, 2);          // row y: centre, ring 4 (dx +3), ring 12 (dx -3)
-            const uint32_t cA = 0x01000100u - p1.x, cB = 0x01000100u - p1.y;   // 256 - centre per lane
-            dA[4] = straddle(p1.y, p2.x) + cA;  dB[4] = straddle(p2.x, p2.y) + cB;
-            dA[12] = straddle(p0.x, p0.y) + cA; dB[12] = straddle(p0.y, p1.x) + cB;
+            cA = p1.x; cB = p1.y;
+            rA[4] = straddle(p1.y, p2.x);  rB[4] = straddle(p2.x, p2.y);
+            rA[12] = straddle(p0.x, p0.y); rB[12] = straddle(p0.y, p1.x);
 #define ROW3(DY, KM, K0, KP)   /* rows y +- 3: dx -1, 0, +1 */                                   \
             {                                                                                     \
                 const uint2 a0 = P(DY, 0), a1 = P(DY, 1), a2 = P(DY, 2);                          \
                 const uint32_t m = straddle(a0.y, a1.x), z = straddle(a1.x, a1.y), n = straddle(a1.y, a2.x); \
-                dA[KM] = m + cA;    dB[KM] = z + cB;                                              \
-                dA[K0] = a1.x + cA; dB[K0] = a1.y + cB;                                           \
-                dA[KP] = z + cA;    dB[KP] = n + cB;                                              \
+                rA[KM] = m;    rB[KM] = z;                                                        \
+                rA[K0] = a1.x; rB[K0] = a1.y;                                                     \
+                rA[KP] = z;    rB[KP] = n;                                                        \
             }
 #define ROW2(DY, KM, KP)       /* rows y +- 2: dx -2, +2 */                                       \
             {                                                                                     \
                 const uint2 a0 = P(DY, 0), a1 = P(DY, 1), a2 = P(DY, 2);                          \
-                dA[KM] = a0.y + cA; dB[KM] = a1.x + cB;                                           \
-                dA[KP] = a1.y + cA; dB[KP] = a2.x + cB;                                           \
+                rA[KM] = a0.y; rB[KM] = a1.x;                                                     \
+                rA[KP] = a1.y; rB[KP] = a2.x;                                                     \
             }
 #define ROW1(DY, KM, KP)       /* rows y +- 1: dx -3, +3 */                                       \
             {                                                                                     \
                 const uint2 a0 = P(DY, 0), a1 = P(DY, 1), a2 = P(DY, 2);                          \
-                dA[KM] = straddle(a0.x, a0.y) + cA; dB[KM] = straddle(a0.y, a1.x) + cB;           \
-                dA[KP] = straddle(a1.y, a2.x) + cA; dB[KP] = straddle(a2.x, a2.y) + cB;           \
+                rA[KM] = straddle(a0.x, a0.y); rB[KM] = straddle(a0.y, a1.x);                     \
+                rA[KP] = straddle(a1.y, a2.x); rB[KP] = straddle(a2.x, a2.y);                     \
             }
             ROW3(3, 15, 0, 1)    // ring 15 (-1,+3), 0 (0,+3), 1 (+1,+3)
             ROW2(2, 14, 2)       // ring 14 (-2,+2), 2 (+2,+2)
@@ -153,8 +160,8 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
 #undef ROW2
 #undef ROW1
         }
-        // biased strength M = m + 256; store m - thr for corners, 0 otherwise (order-preserving, so NMS is unaffected)
-        const uint32_t sA = __vmaxs2(arc_strength2(dA), K) - K, sB = __vmaxs2(arc_strength2(dB), K) - K;
+        // store m - thr for corners, 0 otherwise (order-preserving, so NMS is unaffected)
+        const uint32_t sA = arc_strength2(rA, cA, K), sB = arc_strength2(rB, cB, K);
         *reinterpret_cast<uint2*>(s_score + sr * FT_SP + c) = make_uint2(sA, sB);
     }
     __syncthreads();

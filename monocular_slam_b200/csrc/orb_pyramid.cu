@@ -85,7 +85,35 @@ k_pyr_down(uint8_t* __restrict__ slots, size_t slot_stride, size_t src_off, int 
     }
 }
 
+// Level 0 of every frame slot from a batch of device-resident frames, in ONE launch (frames are frame_pitch bytes apart,
+// rows `stride` bytes apart).  16-byte vectors when the source allows it, bytes otherwise; the slot's padding columns
+// [w, pitch) are never written (they stay zero from orbx_create).
+__global__ void __launch_bounds__(256)
+k_ingest(const uint8_t* __restrict__ src, size_t frame_pitch, size_t stride, int w, int h, uint8_t* __restrict__ slots,
+         size_t slot_stride, size_t dst_off, int dpitch, int vec_ok)
+{
+    const uint8_t* s = src + blockIdx.z * frame_pitch;
+    uint8_t* d = slots + blockIdx.z * slot_stride + dst_off;
+    const int nv = vec_ok ? w >> 4 : 0;
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const uint8_t* sr = s + (size_t)y * stride;
+        uint8_t* dr = d + (size_t)y * dpitch;
+        for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x)
+            reinterpret_cast<uint4*>(dr)[v] = __ldcs(reinterpret_cast<const uint4*>(sr) + v);
+        for (int x = nv * 16 + blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) dr[x] = sr[x];
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_ingest(const uint8_t* d_frames, size_t frame_pitch, size_t stride, int w, int h, uint8_t* slots,
+                          size_t slot_stride, const LevelGeom& L0, int nframes, cudaStream_t s)
+{
+    const int vec_ok = (((uintptr_t)d_frames | frame_pitch | stride) & 15) == 0;
+    dim3 grid(div_up(div_up(w, 16), 256), h < 270 ? h : 270, nframes);
+    k_ingest<<<grid, 256, 0, s>>>(d_frames, frame_pitch, stride, w, h, slots, slot_stride, L0.img_off, L0.pitch, vec_ok);
+    return cudaGetLastError();
+}
 
 // Largest staged source rectangle over all tiles of a level (host tables), so shared memory can be sized exactly.
 void pyr_down_smem_extent(const int* ofs_x, int dw, const int* ofs_y, int dh, int sw, int sh, int* s_w, int* s_h)

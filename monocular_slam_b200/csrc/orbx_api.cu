@@ -24,6 +24,8 @@ void pyr_down_smem_extent(const int* ofs_x, int dw, const int* ofs_y, int dh, in
 cudaError_t launch_pyr_down_level(uint8_t* slots, size_t slot_stride, const LevelGeom& src, const LevelGeom& dst, int s_w,
                                   int s_h, int nframes, cudaStream_t s);
 void fast_tile_dims(int* tw, int* th);
+cudaError_t launch_ingest(const uint8_t* d_frames, size_t frame_pitch, size_t stride, int w, int h, uint8_t* slots,
+                          size_t slot_stride, const LevelGeom& L0, int nframes, cudaStream_t s);
 cudaError_t harris_select_prepare(int max_surv_cap);
 cudaError_t launch_harris_select(const FrameGeom& g, const uint8_t* slots, size_t slot_stride, const Cand* surv,
                                  size_t surv_stride, Sel* sel, size_t sel_stride, FrameCounters* ctr, int nframes,
@@ -575,9 +577,7 @@ extern "C" int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, si
     if (((uintptr_t)d_desc & 3) || ((uintptr_t)d_out & 3)) { set_error("orbx_extract_batch_dev: output pointers must be 4-byte aligned"); return ORBX_E_ALIGN; }
     int rc = common_checks(h, d_frames, w, hh, stride, "orbx_extract_batch_dev");
     if (rc) return rc;
-    for (int f = 0; f < nframes; f++)
-        ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)f * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch,
-                                    d_frames + (size_t)f * frame_pitch_bytes, stride, (size_t)w, (size_t)hh, cudaMemcpyDeviceToDevice, h->stream));
+    ORBX_CUDA(launch_ingest(d_frames, frame_pitch_bytes, stride, w, hh, h->d_slots, h->slot_stride, h->g.lv[0], nframes, h->stream));
     rc = run_extract(h, 0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_out, d_desc, cap, d_counts);
     if (rc) return rc;
     h->dev_pending = true;

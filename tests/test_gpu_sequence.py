@@ -56,14 +56,15 @@ def test_sequence_host_path():
     orb.close()
 
 
-def test_sequence_device_path():
+@pytest.mark.parametrize("w,h,nf", [(1241, 376, 2000), (640, 480, 700)])   # byte-wise and 16-byte-vector ingest
+def test_sequence_device_path(w, h, nf):
     import torch
-    seq = syn.sequence(5, 1241, 376, seed=22)
-    ext, matches = _oracle_sequence(seq, 2000, 0.75)
+    seq = syn.sequence(5, w, h, seed=22)
+    ext, matches = _oracle_sequence(seq, nf, 0.75)
     B, (H, W) = len(seq), seq[0].shape
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        orb = ORB(nfeatures=2000, max_size=(W, H), max_batch=B)
+        orb = ORB(nfeatures=nf, max_size=(W, H), max_batch=B)
         m = BFMatcher()
         orb.set_stream(stream.cuda_stream)
         m.set_stream(stream.cuda_stream)

@@ -26,7 +26,7 @@ SYMBOLS = [
     "orbx_debug_pyramid_level", "orbx_debug_fast_level", "hamx_create", "hamx_destroy", "hamx_set_stream",
     "hamx_synchronize", "hamx_knn2", "hamx_match_ratio", "hamx_knn2_dev", "hamx_merge_top2_dev", "hamx_ratio_dev",
     "hamx_popc_peak", "hamx_match_pairs_dev", "hamx_match_consecutive_dev", "orbx_match_consecutive", "orbx_reset_sequence",
-    "orbx_set_profiling", "orbx_read_profile",
+    "orbx_set_profiling", "orbx_read_profile", "orbx_submit_batch", "orbx_wait_batch", "orbx_batches_in_flight",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -108,6 +108,9 @@ def lib():
     L.hamx_match_consecutive_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_float, vp, vp]
     L.orbx_match_consecutive.argtypes = [vp, vp, C.c_float, vp, i64p]
     L.orbx_reset_sequence.argtypes = [vp]
+    L.orbx_submit_batch.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_float, vp, vp, C.c_int, vp, vp, vp]
+    L.orbx_wait_batch.argtypes = [vp]
+    L.orbx_batches_in_flight.argtypes = [vp]
     L.orbx_set_profiling.argtypes = [vp, C.c_int]
     L.orbx_read_profile.argtypes = [vp, fp, ip]
     _lib = L

@@ -102,7 +102,7 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
     const int thr = g.fast_threshold;
 
     if (tid == 0) s_en = 0;
-    for (int i = tid; i < FT_CH * FT_SP / 8; i += FT_THREADS) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
+    // s_score needs no clearing: every entry NMS consumes for a pixel of the tile proper is written by the scoring pass
     for (int i = tid; i < FT_SH * (FT_SP / 16); i += FT_THREADS) {
         int r = i / (FT_SP / 16), v = i - r * (FT_SP / 16);
         int gy = gy0 + r, gx = gx0 + v * 16;

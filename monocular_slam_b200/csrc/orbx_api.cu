@@ -35,6 +35,17 @@ cudaError_t launch_harris_select(const FrameGeom& g, const uint8_t* slots, size_
 
 using namespace orbx;
 
+// One of the two batches that may be in flight through orbx_submit_batch / orbx_wait_batch.  Lane l owns slots
+// [l * max_batch, (l + 1) * max_batch) of every per-frame array of the handle.
+struct orbx_lane {
+    bool busy;
+    int nframes, cap;
+    cudaEvent_t uploaded, computed, done;
+    int32_t* counts;      // caller's arrays, filled by orbx_wait_batch
+    int64_t* ngood;
+};
+constexpr int ORBX_LANES = 2;
+
 struct orbx_context {
     int device;
     orbx_params p;
@@ -74,6 +85,10 @@ struct orbx_context {
     orbx_dmatch* d_good;
     int64_t* d_ngood;
     int64_t* h_ngood;
+    // pipelined host path
+    orbx_lane lanes[ORBX_LANES];
+    int lane_head, lane_next;                 // oldest batch in flight, lane the next submission uses
+    cudaStream_t d2h_stream;
     // stage profiling
     bool profiling;
     std::vector<cudaEvent_t>* events;
@@ -284,10 +299,16 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
 
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    ORBX_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    for (int l = 0; l < ORBX_LANES; l++) {
+        ORBX_CUDA(cudaEventCreateWithFlags(&h->lanes[l].uploaded, cudaEventDisableTiming));
+        ORBX_CUDA(cudaEventCreateWithFlags(&h->lanes[l].computed, cudaEventDisableTiming));
+        ORBX_CUDA(cudaEventCreateWithFlags(&h->lanes[l].done, cudaEventDisableTiming));
+    }
     h->copy_events = new std::vector<cudaEvent_t>();
     ORBX_CUDA(cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming));
     h->stream = h->own_stream;
-    const size_t B = (size_t)max_batch;
+    const size_t B = (size_t)max_batch * ORBX_LANES;   // blocking calls use lane 0 only
 #define ORBX_ALLOC(ptr, bytes)                                                                            \
     do {                                                                                                  \
         cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                             \
@@ -335,6 +356,12 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+    for (int l = 0; l < ORBX_LANES; l++) {
+        if (h->lanes[l].uploaded) cudaEventDestroy(h->lanes[l].uploaded);
+        if (h->lanes[l].computed) cudaEventDestroy(h->lanes[l].computed);
+        if (h->lanes[l].done) cudaEventDestroy(h->lanes[l].done);
+    }
     if (h->order_event) cudaEventDestroy(h->order_event);
     if (h->copy_events) { for (cudaEvent_t e : *h->copy_events) cudaEventDestroy(e); delete h->copy_events; }
     delete h->h_tab;
@@ -383,12 +410,20 @@ static int build_pyramids(orbx_handle h, int f0, int nframes)
     return ORBX_OK;
 }
 
+// frames[f0 .. f0 + nframes) -> slots slot0 + f0 ..
 static int upload_frames(orbx_handle h, const uint8_t* const* frames, int f0, int nframes, int w, int hh, size_t stride,
-                         cudaMemcpyKind kind, cudaStream_t s)
+                         cudaMemcpyKind kind, cudaStream_t s, int slot0 = 0)
 {
     for (int f = f0; f < f0 + nframes; f++)
-        ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)f * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch, frames[f], stride,
-                                    (size_t)w, (size_t)hh, kind, s));
+        ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)(slot0 + f) * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch, frames[f],
+                                    stride, (size_t)w, (size_t)hh, kind, s));
+    return ORBX_OK;
+}
+
+static int require_idle(orbx_handle h, const char* fn)
+{
+    for (int l = 0; l < ORBX_LANES; l++)
+        ORBX_REQUIRE(!h->lanes[l].busy, "%s: a batch submitted with orbx_submit_batch is still in flight; call orbx_wait_batch first", fn);
     return ORBX_OK;
 }
 
@@ -461,13 +496,13 @@ extern "C" int orbx_read_profile(orbx_handle h, float* stage_ms, int* nbatches)
     return ORBX_OK;
 }
 
-static int check_counters(orbx_handle h, int nframes, int cap)
+static int check_counters(orbx_handle h, int nframes, int cap, int slot0 = 0)
 {
     for (int f = 0; f < nframes; f++) {
-        const int ov = h->h_ctr[f].overflow;
+        const int ov = h->h_ctr[slot0 + f].overflow;
         if (ov & 1) { set_error("frame %d: FAST candidate list overflow (internal capacity)", f); return ORBX_E_CAPACITY; }
         if (ov & 2) { set_error("frame %d: more than %d tied keypoints at a retention cut; raise nfeatures", f, h->max_surv_cap); return ORBX_E_CAPACITY; }
-        if (ov & 4) { set_error("frame %d: %d keypoints exceed the output capacity %d", f, h->h_ctr[f].total, cap); return ORBX_E_CAPACITY; }
+        if (ov & 4) { set_error("frame %d: %d keypoints exceed the output capacity %d", f, h->h_ctr[slot0 + f].total, cap); return ORBX_E_CAPACITY; }
     }
     return ORBX_OK;
 }
@@ -477,6 +512,8 @@ static int common_checks(orbx_handle h, const void* img, int w, int hh, size_t s
     ORBX_REQUIRE(h != nullptr, "%s: NULL handle", fn);
     ORBX_REQUIRE(img != nullptr, "%s: NULL image", fn);
     ORBX_REQUIRE(w >= 1 && hh >= 1 && stride >= (size_t)w, "%s: bad image geometry %dx%d stride %zu", fn, w, hh, stride);
+    int rc = require_idle(h, fn);
+    if (rc) return rc;
     ORBX_CUDA(cudaSetDevice(h->device));
     return set_geometry(h, w, hh);
 }
@@ -651,6 +688,7 @@ extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio,
     ORBX_REQUIRE(h != nullptr && m != nullptr, "orbx_match_consecutive: NULL handle");
     ORBX_REQUIRE(good && ngood, "orbx_match_consecutive: NULL pointer");
     ORBX_REQUIRE(h->last_nframes >= 1, "orbx_match_consecutive: no batch with descriptors has been extracted on this handle");
+    { int rc_ = require_idle(h, "orbx_match_consecutive"); if (rc_) return rc_; }
     ORBX_CUDA(cudaSetDevice(h->device));
     const int n = h->last_nframes, cap = h->last_cap;
     int rc = hamx_set_stream(m, (void*)h->stream);   // same stream as the extraction: ordered after it, no extra sync
@@ -668,6 +706,97 @@ extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio,
     h->have_prev = true;
     for (int f = 0; f < n; f++) ngood[f] = h->h_ngood[f];
     return ORBX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- pipelined host path
+// Two batches in flight: while batch k is being extracted and matched on the compute stream, the frames of batch k+1
+// cross PCIe on the copy stream and the results of batch k-1 return on the D2H stream.
+extern "C" int orbx_submit_batch(orbx_handle h, hamx_handle m, const uint8_t* const* frames, int nframes, int w, int hh, size_t stride,
+                                 float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts, orbx_dmatch* good,
+                                 int64_t* ngood)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_submit_batch: NULL handle");
+    ORBX_REQUIRE(frames && out && desc && counts && (m == nullptr || (good && ngood)), "orbx_submit_batch: NULL pointer");
+    ORBX_REQUIRE(nframes >= 1 && nframes <= h->max_batch, "orbx_submit_batch: %d frames outside [1, max_batch=%d]", nframes, h->max_batch);
+    ORBX_REQUIRE(cap >= 1 && cap <= h->dev_cap, "orbx_submit_batch: capacity %d outside [1, %d]", cap, h->dev_cap);
+    ORBX_REQUIRE(frames[0] && w >= 1 && hh >= 1 && stride >= (size_t)w, "orbx_submit_batch: bad image geometry %dx%d stride %zu", w, hh, stride);
+    const int li = h->lane_next;
+    orbx_lane& L = h->lanes[li];
+    ORBX_REQUIRE(!L.busy, "orbx_submit_batch: %d batches are already in flight; call orbx_wait_batch first", ORBX_LANES);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int rc = set_geometry(h, w, hh);      // drains the compute stream if the frame size changed
+    if (rc) return rc;
+    const int s0 = li * h->max_batch;
+    // the lane's slots are free: its previous batch was collected by orbx_wait_batch and the blocking entry points drain
+    // the compute stream before they return.  Only an unchecked asynchronous _dev submission can still be using lane 0;
+    // then (and only then: the wait would also serialise this upload behind the other lane's kernels) order behind it.
+    if (h->dev_pending) {
+        ORBX_CUDA(cudaEventRecord(h->order_event, h->stream));
+        ORBX_CUDA(cudaStreamWaitEvent(h->copy_stream, h->order_event, 0));
+    }
+    rc = upload_frames(h, frames, 0, nframes, w, hh, stride, cudaMemcpyHostToDevice, h->copy_stream, s0);
+    if (rc) return rc;
+    ORBX_CUDA(cudaEventRecord(L.uploaded, h->copy_stream));
+    ORBX_CUDA(cudaStreamWaitEvent(h->stream, L.uploaded, 0));
+    rc = run_extract(h, s0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, h->d_kps, h->d_desc, cap, h->d_counts);
+    if (rc) return rc;
+    uint8_t* d_desc = h->d_desc + (size_t)s0 * cap * 32;
+    orbx_dmatch* d_good = h->d_good + (size_t)s0 * cap;
+    if (m) {
+        rc = hamx_set_stream(m, (void*)h->stream);
+        if (rc) return rc;
+        rc = hamx_match_consecutive_dev(m, d_desc, h->d_counts + s0, nframes, cap, h->have_prev ? h->d_prev_desc : nullptr,
+                                        h->have_prev ? h->d_prev_count : nullptr, ratio, d_good, h->d_ngood + s0);
+        hamx_set_stream(m, nullptr);
+        if (rc) return rc;
+        ORBX_CUDA(cudaMemcpyAsync(h->d_prev_desc, d_desc + (size_t)(nframes - 1) * cap * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(h->d_prev_count, h->d_counts + s0 + (nframes - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+        h->have_prev = true;
+    }
+    ORBX_CUDA(cudaEventRecord(L.computed, h->stream));
+    ORBX_CUDA(cudaStreamWaitEvent(h->d2h_stream, L.computed, 0));
+    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr + s0, h->d_ctr + s0, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->d2h_stream));
+    ORBX_CUDA(cudaMemcpyAsync(out, h->d_kps + (size_t)s0 * cap, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->d2h_stream));
+    ORBX_CUDA(cudaMemcpyAsync(desc, d_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (m) {
+        ORBX_CUDA(cudaMemcpyAsync(good, d_good, (size_t)nframes * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->d2h_stream));
+        ORBX_CUDA(cudaMemcpyAsync(h->h_ngood + s0, h->d_ngood + s0, (size_t)nframes * sizeof(int64_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
+    ORBX_CUDA(cudaEventRecord(L.done, h->d2h_stream));
+    L.busy = true;
+    L.nframes = nframes;
+    L.cap = cap;
+    L.counts = counts;
+    L.ngood = m ? ngood : nullptr;
+    h->last_nframes = 0;            // orbx_match_consecutive pairs with orbx_extract_batch only
+    h->lane_next = (li + 1) % ORBX_LANES;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_wait_batch(orbx_handle h)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_wait_batch: NULL handle");
+    const int li = h->lane_head;
+    orbx_lane& L = h->lanes[li];
+    ORBX_REQUIRE(L.busy, "orbx_wait_batch: no batch in flight");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    ORBX_CUDA(cudaEventSynchronize(L.done));
+    L.busy = false;
+    h->lane_head = (li + 1) % ORBX_LANES;
+    const int s0 = li * h->max_batch;
+    for (int f = 0; f < L.nframes; f++) {
+        L.counts[f] = h->h_ctr[s0 + f].total;
+        if (L.ngood) L.ngood[f] = h->h_ngood[s0 + f];
+    }
+    return check_counters(h, L.nframes, L.cap, s0);
+}
+
+extern "C" int orbx_batches_in_flight(orbx_handle h)
+{
+    if (!h) return ORBX_E_INVALID;
+    int n = 0;
+    for (int l = 0; l < ORBX_LANES; l++) n += h->lanes[l].busy ? 1 : 0;
+    return n;
 }
 
 // ---------------------------------------------------------------------------------------------- debug taps

@@ -165,6 +165,38 @@ class ORB:
                                                 ngood.ctypes.data_as(C.POINTER(C.c_int64))))
         return good, ngood
 
+    # -- pipelined sequence mode: two batches in flight (upload / kernels / download overlap across batches)
+    def submit_batch(self, frames, matcher, ratio, out):
+        """Enqueue extraction (+ consecutive-frame matching when ``matcher`` is given) of a batch and return at once.
+        ``out`` = (kps[n, cap], desc[n, cap, 32], counts[n] int32, good[n, cap], ngood[n] int64): caller-owned buffers
+        (pinned for real overlap) that are complete after the matching ``wait_batch()``."""
+        frames = [_gray(f) for f in frames]
+        n = len(frames)
+        h, w = frames[0].shape
+        stride = frames[0].strides[0]
+        if any(f.shape != (h, w) or f.strides[0] != stride for f in frames):
+            raise ValueError("all frames of a batch must share one shape and stride")
+        kps, desc, counts, good, ngood = out
+        cap = kps.shape[1]
+        if kps.shape[0] < n or desc.shape[:2] != kps.shape[:2] or counts.dtype != np.int32 or ngood.dtype != np.int64:
+            raise ValueError("bad output buffers")
+        ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        self._inflight = getattr(self, "_inflight", [])
+        check(_lib.lib().orbx_submit_batch(self._h, matcher._h if matcher is not None else None, ptrs, n, w, h, stride,
+                                           float(ratio), kps.ctypes.data, desc.ctypes.data, cap, counts.ctypes.data,
+                                           good.ctypes.data, ngood.ctypes.data))
+        self._inflight.append((frames, out))     # keep the buffers alive until the batch is collected
+
+    def wait_batch(self):
+        """Block until the oldest submitted batch is complete; returns its ``out`` tuple."""
+        status = _lib.lib().orbx_wait_batch(self._h)
+        done = self._inflight.pop(0)[1] if getattr(self, "_inflight", None) else None
+        check(status)
+        return done
+
+    def batches_in_flight(self):
+        return _lib.lib().orbx_batches_in_flight(self._h)
+
     def reset_sequence(self):
         check(_lib.lib().orbx_reset_sequence(self._h))
 

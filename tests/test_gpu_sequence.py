@@ -121,3 +121,57 @@ def test_batched_pairs_ragged():
     for i, (q, t) in enumerate(sets):
         _check_matches(good[i], int(ngood[i]), oracle.match_features(q, t, 0.8))
     m.close()
+
+
+def test_pipelined_submit_wait():
+    """orbx_submit_batch / orbx_wait_batch: two batches in flight, results identical to the frame-by-frame oracle,
+    including the match of each batch's first frame against the previous batch's last frame."""
+    import torch
+    seq = syn.sequence(8, 800, 600, seed=23)
+    ext, matches = _oracle_sequence(seq, 1000, 0.8)
+    orb = ORB(nfeatures=1000, max_size=(800, 600), max_batch=3)
+    m = BFMatcher()
+    cap = orb.default_cap
+
+    def buffers(n):
+        return (torch.zeros((n, cap, 7), dtype=torch.float32).pin_memory().numpy().view(KEYPOINT_DTYPE).reshape(n, cap),
+                torch.zeros((n, cap, 32), dtype=torch.uint8).pin_memory().numpy(),
+                np.zeros(n, np.int32),
+                torch.zeros((n, cap, 4), dtype=torch.int32).pin_memory().numpy().view(DMATCH_DTYPE).reshape(n, cap),
+                np.zeros(n, np.int64))
+
+    chunks = [(0, 3), (3, 6), (6, 8)]
+    pinned = torch.from_numpy(seq).pin_memory().numpy()
+    outs = []
+
+    def collect(lo, hi):
+        kps, desc, counts, good, ngood = orb.wait_batch()
+        for i in range(hi - lo):
+            f = lo + i
+            assert_keypoints_equal(kps[i, :counts[i]], ext[f][0], "frame %d" % f)
+            assert_descriptors_equal(desc[i, :counts[i]], ext[f][1], "frame %d" % f)
+            if f == 0:
+                assert ngood[i] == 0
+            else:
+                _check_matches(good[i], int(ngood[i]), matches[f])
+
+    pending = []
+    for lo, hi in chunks:
+        if orb.batches_in_flight() == 2:
+            collect(*pending.pop(0))
+        orb.submit_batch(list(pinned[lo:hi]), m, 0.8, buffers(hi - lo))
+        pending.append((lo, hi))
+    assert orb.batches_in_flight() == 2
+    # the blocking entry points refuse to run while batches are in flight
+    with pytest.raises(Exception):
+        orb.extract_batch(list(seq[:1]), cap=cap)
+    while pending:
+        collect(*pending.pop(0))
+    assert orb.batches_in_flight() == 0
+    with pytest.raises(Exception):
+        orb.wait_batch()
+    # the handle is usable through the blocking path again
+    kps, desc, counts = orb.extract_batch(list(seq[:1]), cap=cap)
+    assert_keypoints_equal(kps[0, :counts[0]], ext[0][0], "blocking after pipelined")
+    m.close()
+    orb.close()

@@ -7,8 +7,9 @@
 // Layout.  Descriptors are rows of 32 bytes (2 x uint4).  A CTA of 128 threads owns 256 query rows, two per thread,
 // held in registers for the whole kernel.  The train rows of the CTA's split are streamed through a 4-stage ring of
 // 4 KB shared-memory tiles filled by the TMA engine (cp.async.bulk + mbarrier complete_tx); every lane reads the
-// same train row (a shared-memory broadcast), XORs it against its two queries and issues 16 POPCs, which is the
-// pipe this kernel is bound by (8 POPC per comparison; DESIGN.md "K6").
+// same train row (a shared-memory broadcast) and XORs it against its two queries.  A plain popcount needs 8 POPC per
+// comparison and is bound by the POPC pipe (16 lanes/clk/SM); ham256() first compresses the XOR words with carry-save
+// adders on the 4x wider LOP3 pipe, which leaves 5 POPC per comparison and balances the two pipes (DESIGN.md "K6").
 //
 // Tie rule.  OpenCV inserts candidates in ascending train order with a strict `<`, i.e. the result is the two
 // lexicographically smallest (distance, trainIdx) pairs.  Packing key = distance << 23 | trainIdx makes that a
@@ -68,10 +69,38 @@ __device__ __forceinline__ void top2_insert(uint32_t& b0, uint32_t& b1, uint32_t
     b1 = min(b1, hi);
 }
 
+// Carry-save adder on 32 bit positions at once: a + b + c == s + 2 * cy (two LOP3: 3-input XOR and majority).
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& s, uint32_t& cy)
+{
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(cy) : "r"(a), "r"(b), "r"(c));
+}
+
+#ifndef HT_CSA
+#define HT_CSA 1    // measured on B200 (1 M x 125 k): 0 -> 549, 1 -> 833, 2 -> 812 Gcmp/s
+#endif
+// 256-bit Hamming distance (ThirdParty/DBoW2/DBoW2/FORB.cpp:81-101: XOR, population count, sum).  The POPC pipe issues
+// 16 lanes/clk/SM against 64 for LOP3, so instead of 8 POPC the eight XOR words are first compressed with carry-save
+// adders (Harley-Seal): x0..x6 -> s3 + 2 (c1 + c2 + c3) -> s3 + 2 s5 + 4 c5, leaving 4 POPC (HT_CSA == 2) or 5 (== 1).
 __device__ __forceinline__ uint32_t ham256(const uint32_t (&q)[8], const uint4& a, const uint4& b)
 {
-    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) + __popc(q[4] ^ b.x) +
-           __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+#if HT_CSA == 0
+    return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
+#else
+    uint32_t s1, c1, s2, c2, s3, c3;
+    csa(x0, x1, x2, s1, c1);
+    csa(x3, x4, x5, s2, c2);
+    csa(s1, s2, x6, s3, c3);
+#if HT_CSA == 1
+    return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+#else
+    uint32_t s5, c5;
+    csa(c1, c2, c3, s5, c5);
+    return __popc(s3) + __popc(x7) + 2 * __popc(s5) + 4 * __popc(c5);
+#endif
+#endif
 }
 
 __device__ __forceinline__ hamx_top2 decode_top2(uint32_t k0, uint32_t k1, int64_t offset)

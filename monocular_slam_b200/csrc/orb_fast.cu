@@ -41,21 +41,43 @@ __device__ __forceinline__ uint32_t lanes_hi(uint32_t g) { return __byte_perm(g,
 // lanes (hi of a, lo of b): the pixel pair that straddles two aligned pairs
 __device__ __forceinline__ uint32_t straddle(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5432); }
 
+// The 16-bit lanes hold integers 0..255; read as fp16 they are subnormals whose order and sums are those of the
+// integers, so (min, max) of two lane registers can be had on the otherwise idle FMA pipe, exactly, as
+// t = relu(a - b), min = a - t, max = b + t (3 HFMA2 for both results; tools/fastnet_probe.cu checks it exhaustively).
+__device__ __forceinline__ uint32_t hfma2_relu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void minmax_fma(uint32_t a, uint32_t b, uint32_t& mn, uint32_t& mx)
+{
+    const uint32_t one = 0x3C003C00u, neg_one = 0xBC00BC00u;
+    const uint32_t t = hfma2_relu(b, neg_one, a);
+    mn = hfma2(t, neg_one, a);
+    mx = hfma2(t, one, b);
+}
+
 // thr-clamped corner strength of two pixels at once.  r[] holds the RAW ring pixels (0..255) in 16x2 lanes, c the centre
 // pixels.  Sliding min/max is shift-invariant, so the centre is subtracted once at the end instead of from every ring
 // pixel:  m = max(max_arcs min_arc(ring) - c, c - min_arcs max_arc(ring)).
 // Arc k = ring positions k .. k+8.  With W_j = positions 2j+1 .. 2j+8 (min of two 4-windows), arcs 2j and 2j+1 are
 // W_j extended by position 2j resp. 2j+9, and max(min(W,a), min(W,b)) == min(W, max(a,b)), so both arcs cost one
-// 2-input and one 3-input instruction: 36 VIMNMX(3).S16x2 per sign and pixel pair (8 + 8 + 8 + 8 + 4).
+// 2-input and one 3-input instruction: 36 min/max per sign and pixel pair (8 + 8 + 8 + 8 + 4).  The 16 (min, max)
+// pairs that share their inputs (first level, arc extensions) run on the FMA pipe (48 HFMA2), the other 40 + 4
+// instructions are VIMNMX(3).S16x2 on the ALU pipe, which is the pipe this kernel is bound by.
 // Returns max(m - thr, 0) per lane; K = (thr + 256) in both lanes.
 __device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&r)[16], uint32_t c, uint32_t K)
 {
     uint32_t lo2[8], hi2[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {       // window {2j+1, 2j+2}
-        lo2[j] = __vmins2(r[2 * j + 1], r[(2 * j + 2) & 15]);
-        hi2[j] = __vmaxs2(r[2 * j + 1], r[(2 * j + 2) & 15]);
-    }
+    for (int j = 0; j < 8; j++) minmax_fma(r[2 * j + 1], r[(2 * j + 2) & 15], lo2[j], hi2[j]);   // window {2j+1, 2j+2}
     uint32_t lo4[8], hi4[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {       // window 2j+1 .. 2j+4
@@ -65,9 +87,10 @@ __device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&r)[16], uint3
     uint32_t alo[8], ahi[8];            // best of arcs 2j and 2j+1
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const uint32_t e0 = r[2 * j], e1 = r[(2 * j + 9) & 15];
-        alo[j] = __vimin3_s16x2(lo4[j], lo4[(j + 2) & 7], __vmaxs2(e0, e1));
-        ahi[j] = __vimax3_s16x2(hi4[j], hi4[(j + 2) & 7], __vmins2(e0, e1));
+        uint32_t emn, emx;
+        minmax_fma(r[2 * j], r[(2 * j + 9) & 15], emn, emx);
+        alo[j] = __vimin3_s16x2(lo4[j], lo4[(j + 2) & 7], emx);
+        ahi[j] = __vimax3_s16x2(hi4[j], hi4[(j + 2) & 7], emn);
     }
     const uint32_t best_lo = __vimax3_s16x2(__vimax3_s16x2(alo[0], alo[1], alo[2]), __vimax3_s16x2(alo[3], alo[4], alo[5]),
                                             __vmaxs2(alo[6], alo[7]));

@@ -207,7 +207,7 @@ static int set_geometry(orbx_handle h, int w, int hh)
         linear_table(S.w, D.w, ox, cx);
         linear_table(S.h, D.h, oy, cy);
         pyr_down_smem_extent(ox, D.w, oy, D.h, S.w, S.h, &h->pyr_sw[l], &h->pyr_sh[l]);
-        ORBX_REQUIRE((size_t)h->pyr_sh[l] * h->pyr_sw[l] + (size_t)h->pyr_sh[l] * 256 <= 200 * 1024,
+        ORBX_REQUIRE((size_t)h->pyr_sw[l] * 32 * 2 + 16 <= 200 * 1024,
                      "scale factor %.3f needs more shared memory than one CTA has", (double)h->p.scale_factor);
         D.ofs_x = (const int*)(h->d_tab + ioff);
         D.ofs_y = D.ofs_x + D.w;

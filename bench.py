@@ -410,7 +410,9 @@ def run_ours(args, rank, world, local_rank):
                    "workload": "%d queries x %d train rows per GPU (train-sharded, 1 all-gather of 16 B/query/rank + merge)" % (nq, nt_shard),
                    "roofline": {"bound": "int_popc", "achieved": gcmp * 8, "peak": gpopc * world, "unit": "Gpopc/s",
                                 "frac": gcmp * 8 / (gpopc * world),
-                                "note": "8 POPC per 256-bit comparison; peak = register-only POPC microbenchmark (hamx_popc_peak) per GPU x n_gpus"}}
+                                "note": "ALGORITHMIC work of 8 POPC per 256-bit comparison (SURVEY.md 8d) against the register-only POPC "
+                                        "microbenchmark (hamx_popc_peak) per GPU x n_gpus; frac > 1 because the kernel issues only 5 POPC per "
+                                        "comparison after carry-save compression on the LOP3 pipe (csrc/hamming.cu ham256)"}}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores
     cpu = None

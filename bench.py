@@ -193,7 +193,7 @@ def run_reference(args, rank):
                        "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "ratio": RATIO, "frames_per_step": frames // args.steps},
             "cpu_baseline": d,
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU path
@@ -454,14 +454,33 @@ def run_ours(args, rank, world, local_rank):
                 "stages_ms_per_step": dict(stages, match=match_ms),
                 "cpu_baseline": cpu,
                 "hamming": hamming}
-        print(json.dumps(line), flush=True)
+        emit(line)
     matcher.close()
     orb.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there when NCCL_DEBUG is set)
+    write to file descriptor 1 directly, so point fd 1 at stderr for the whole run and keep the real stdout aside."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
+_REAL_STDOUT = sys.stdout
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -185,6 +185,27 @@ ORBX_API int hamx_match_consecutive_dev(hamx_handle h, const uint8_t* d_desc, co
                                const uint8_t* d_prev_desc, const int32_t* d_prev_count, float ratio,
                                orbx_dmatch* d_good, int64_t* d_ngood);
 
+/* Train-sharded matching over peer memory (BASELINE configs 4 and 5; one process per GPU of one NVLink box).  The
+ * reference has no counterpart (it is single-device); the result is bit-identical to hamx_knn2_dev over the union of
+ * the shards.  Setup, once: every rank calls hamx_p2p_export (allocates its gather buffer and returns a 64-byte
+ * cudaIpc handle), the ranks exchange the handles (e.g. torch.distributed.all_gather), every rank calls hamx_p2p_import
+ * with the world's handles in rank order, then a barrier.  hamx_p2p_import_ptrs is the same-process variant (raw
+ * device pointers of the other ranks' local_base, e.g. several handles in one test process).
+ * Per query batch (collective: same nq on every rank, same number of calls): hamx_knn2_p2p_dev computes the local
+ * top-2 over this rank's train rows [train_offset, train_offset + nt), the matching kernel itself stores them into
+ * every rank's gather buffer over NVLink and publishes a flag, and a merge kernel waits for all ranks' flags and
+ * reduces with the (distance, trainIdx) rule.  No NCCL call and no host synchronisation is involved.  The two halves are
+ * also exported separately (scatter, merge). */
+ORBX_API int hamx_p2p_export(hamx_handle h, int64_t nq_max, int world, int rank, uint8_t* ipc_handle /* 64 bytes, may be NULL */,
+                    void** local_base /* may be NULL */);
+ORBX_API int hamx_p2p_import(hamx_handle h, const uint8_t* ipc_handles /* world * 64 bytes, rank order */);
+ORBX_API int hamx_p2p_import_ptrs(hamx_handle h, void* const* peer_bases /* world entries; own entry ignored */);
+ORBX_API int hamx_p2p_close(hamx_handle h);
+ORBX_API int hamx_knn2_p2p_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
+                      hamx_top2* d_out);
+ORBX_API int hamx_knn2_p2p_scatter_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset);
+ORBX_API int hamx_p2p_merge_dev(hamx_handle h, int64_t nq, hamx_top2* d_out);
+
 /* Register-only popcount microbenchmark: the measured integer-pipe peak used as the matcher's roofline denominator.
  * gpopc_per_s = 32-bit POPC results per second / 1e9, over the whole device. */
 ORBX_API int hamx_popc_peak(int device, double* gpopc_per_s, double* elapsed_ms);

@@ -27,6 +27,8 @@ SYMBOLS = [
     "hamx_synchronize", "hamx_knn2", "hamx_match_ratio", "hamx_knn2_dev", "hamx_merge_top2_dev", "hamx_ratio_dev",
     "hamx_popc_peak", "hamx_match_pairs_dev", "hamx_match_consecutive_dev", "orbx_match_consecutive", "orbx_reset_sequence",
     "orbx_set_profiling", "orbx_read_profile", "orbx_submit_batch", "orbx_wait_batch", "orbx_batches_in_flight",
+    "hamx_p2p_export", "hamx_p2p_import", "hamx_p2p_import_ptrs", "hamx_p2p_close", "hamx_knn2_p2p_dev",
+    "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -111,6 +113,13 @@ def lib():
     L.orbx_submit_batch.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_float, vp, vp, C.c_int, vp, vp, vp]
     L.orbx_wait_batch.argtypes = [vp]
     L.orbx_batches_in_flight.argtypes = [vp]
+    L.hamx_p2p_export.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.hamx_p2p_import.argtypes = [vp, vp]
+    L.hamx_p2p_import_ptrs.argtypes = [vp, C.POINTER(vp)]
+    L.hamx_p2p_close.argtypes = [vp]
+    L.hamx_knn2_p2p_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64, vp]
+    L.hamx_knn2_p2p_scatter_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64]
+    L.hamx_p2p_merge_dev.argtypes = [vp, C.c_int64, vp]
     L.orbx_set_profiling.argtypes = [vp, C.c_int]
     L.orbx_read_profile.argtypes = [vp, fp, ip]
     _lib = L

@@ -15,6 +15,8 @@
 // lexicographically smallest (distance, trainIdx) pairs.  Packing key = distance << 23 | trainIdx makes that a
 // plain unsigned min: best1 = min(best1, max(best0, key)); best0 = min(best0, key).  Train sets larger than 2^23
 // rows are processed in chunks by the host and merged with the same rule on 64-bit keys.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace orbx {
@@ -113,14 +115,76 @@ __device__ __forceinline__ hamx_top2 decode_top2(uint32_t k0, uint32_t k1, int64
     return r;
 }
 
+__device__ __forceinline__ unsigned long long top2_key64(int32_t d, int32_t i)
+{
+    return i < 0 ? ~0ull : ((unsigned long long)(uint32_t)d << 32) | (uint32_t)i;
+}
+
+__device__ __forceinline__ void top2_insert64(unsigned long long& b0, unsigned long long& b1, unsigned long long key)
+{
+    unsigned long long hi = b0 > key ? b0 : key;
+    b0 = b0 < key ? b0 : key;
+    b1 = b1 < hi ? b1 : hi;
+}
+
+// ---- train-sharded matching over peer memory (one process per GPU, NVLink P2P) ----------------------------------------
+// Every rank owns a gather buffer [2 parities][world][nq_max] of hamx_top2 plus [2][world] epoch flags, mapped into all
+// peers (cudaIpc).  The matching kernel's epilogue stores each query's local top-2 straight into slot [rank] of EVERY
+// rank's gather buffer (16-byte stores over NVLink; no staging copy, no separate all-gather launch); the last CTA to
+// finish publishes the call's epoch in every rank's flag slot with a system-scope release.  k_merge_top2_p2p waits for
+// the world's flags with system-scope acquires and reduces the slots with the lexicographic rule.
+constexpr int HT_MAX_WORLD = 16;
+struct P2PView {
+    hamx_top2* gather[HT_MAX_WORLD];     // base of rank r's gather buffer as mapped into this process
+    unsigned int* flags[HT_MAX_WORLD];   // base of rank r's flag array
+    unsigned int* done;                  // local CTA completion counter
+    long long nq_max;
+    int world, rank;
+    unsigned int epoch;                  // 0: P2P disabled
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void p2p_store(const P2PView& pv, long long qi, const hamx_top2& v)
+{
+    const size_t slot = ((size_t)(pv.epoch & 1u) * pv.world + pv.rank) * (size_t)pv.nq_max + (size_t)qi;
+    const uint4 bits = make_uint4((uint32_t)v.dist0, (uint32_t)v.idx0, (uint32_t)v.dist1, (uint32_t)v.idx1);
+    for (int r = 0; r < pv.world; r++) *reinterpret_cast<uint4*>(pv.gather[r] + slot) = bits;
+}
+
+// called by every CTA that wrote results, after its last p2p_store; `writers` = number of such CTAs in the grid
+__device__ __forceinline__ void p2p_publish(const P2PView& pv, unsigned int writers)
+{
+    __threadfence_system();     // this thread's peer stores are visible system-wide before the flag can be
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(pv.done, 1u);
+        if (prev == writers - 1) {
+            *pv.done = 0;       // ready for the next launch (stream-ordered)
+            __threadfence_system();
+            for (int r = 0; r < pv.world; r++) st_release_sys(pv.flags[r] + (pv.epoch & 1u) * pv.world + pv.rank, pv.epoch);
+        }
+    }
+}
+
 // grid = (query blocks, train splits, pairs).  partial is [pair][nsplit][nq_stride] (only touched when nsplit > 1); the
 // last CTA of a query block to finish merges the splits, so one launch yields final results.  With `pairs` == NULL the
 // launch handles the single problem `one`; otherwise pair blockIdx.z of a device-resident table (batched matching of
 // many small frame pairs in one launch).
+template <bool P2P>
 __global__ void __launch_bounds__(HT_THREADS)
 k_hamming_knn2(const hamx_pair one, const hamx_pair* __restrict__ pairs, int tiles_per_split, uint2* partial,
                size_t nq_stride, unsigned int* arrivals, int qblocks_stride, hamx_top2* __restrict__ out_base,
-               size_t out_stride, int64_t idx_offset)
+               size_t out_stride, int64_t idx_offset, const __grid_constant__ P2PView pv)
 {
     __shared__ __align__(128) uint4 s_tile[HT_STAGES][HT_TT * 2];
     __shared__ __align__(8) uint64_t s_full[HT_STAGES];
@@ -208,7 +272,12 @@ k_hamming_knn2(const hamx_pair one, const hamx_pair* __restrict__ pairs, int til
     if (nsplit == 1) {
 #pragma unroll
         for (int k = 0; k < HT_QPT; k++)
-            if (qi[k] < nq) out[qi[k]] = decode_top2(b0[k], b1[k], idx_offset);
+            if (qi[k] < nq) {
+                const hamx_top2 v = decode_top2(b0[k], b1[k], idx_offset);
+                if (P2P) p2p_store(pv, qi[k], v);
+                else out[qi[k]] = v;
+            }
+        if (P2P) p2p_publish(pv, gridDim.x);
         return;
     }
 
@@ -233,21 +302,45 @@ k_hamming_knn2(const hamx_pair one, const hamx_pair* __restrict__ pairs, int til
             top2_insert(m0, m1, p.x);
             top2_insert(m0, m1, p.y);
         }
-        out[qi[k]] = decode_top2(m0, m1, idx_offset);
+        const hamx_top2 v = decode_top2(m0, m1, idx_offset);
+        if (P2P) p2p_store(pv, qi[k], v);
+        else out[qi[k]] = v;
     }
     if (tid == 0) arrivals[blockIdx.x] = 0;   // ready for the next launch
+    if (P2P) p2p_publish(pv, gridDim.x);      // one merging CTA per query block
 }
 
-__device__ __forceinline__ unsigned long long top2_key64(int32_t d, int32_t i)
+// Scatter of an already computed local result (train sets that needed several launches) with the same signalling.
+__global__ void __launch_bounds__(256) k_scatter_p2p(const hamx_top2* __restrict__ local, long long nq, const __grid_constant__ P2PView pv)
 {
-    return i < 0 ? ~0ull : ((unsigned long long)(uint32_t)d << 32) | (uint32_t)i;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (long long)gridDim.x * blockDim.x)
+        p2p_store(pv, i, local[i]);
+    p2p_publish(pv, gridDim.x);
 }
 
-__device__ __forceinline__ void top2_insert64(unsigned long long& b0, unsigned long long& b1, unsigned long long key)
+// Waits until every rank has published `epoch`, then merges the world's slots of this rank's gather buffer.
+__global__ void __launch_bounds__(256) k_merge_top2_p2p(long long nq, hamx_top2* __restrict__ out, const __grid_constant__ P2PView pv)
 {
-    unsigned long long hi = b0 > key ? b0 : key;
-    b0 = b0 < key ? b0 : key;
-    b1 = b1 < hi ? b1 : hi;
+    if (threadIdx.x < pv.world) {
+        const unsigned int* f = pv.flags[pv.rank] + (pv.epoch & 1u) * pv.world + threadIdx.x;
+        while ((int)(ld_acquire_sys(f) - pv.epoch) < 0) __nanosleep(200);
+    }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const hamx_top2* base = pv.gather[pv.rank] + (size_t)(pv.epoch & 1u) * pv.world * (size_t)pv.nq_max;
+    unsigned long long m0 = ~0ull, m1 = ~0ull;
+    for (int r = 0; r < pv.world; r++) {
+        const uint4 bits = __ldcg(reinterpret_cast<const uint4*>(base + (size_t)r * pv.nq_max + i));   // written by a peer: skip L1
+        top2_insert64(m0, m1, top2_key64((int32_t)bits.x, (int32_t)bits.y));
+        top2_insert64(m0, m1, top2_key64((int32_t)bits.z, (int32_t)bits.w));
+    }
+    hamx_top2 r;
+    r.dist0 = m0 == ~0ull ? -1 : (int32_t)(m0 >> 32);
+    r.idx0 = m0 == ~0ull ? -1 : (int32_t)(m0 & 0xFFFFFFFFu);
+    r.dist1 = m1 == ~0ull ? -1 : (int32_t)(m1 >> 32);
+    r.idx1 = m1 == ~0ull ? -1 : (int32_t)(m1 & 0xFFFFFFFFu);
+    out[i] = r;
 }
 
 // parts is [nparts][nq]; lexicographic (distance, index) merge, identical to a single-device run over the union.
@@ -392,7 +485,15 @@ struct hamx_context {
     long long* d_ngood;
     hamx_pair* d_pairs; size_t pairs_bytes;
     int sm_count;
+    // peer-memory path (hamx_p2p_*)
+    P2PView pv;                        // host copy; epoch advances per collective call
+    void* p2p_buf;                     // this rank's exported allocation: flags, then the gather buffer
+    size_t p2p_bytes;
+    void* p2p_opened[HT_MAX_WORLD];    // peer mappings opened through cudaIpc (closed by hamx_p2p_close)
+    hamx_top2* d_p2p_local; size_t p2p_local_bytes;
 };
+
+static const P2PView kNoP2P = {};
 
 template <typename T>
 static int grow(T** p, size_t* have, size_t want, bool zero = false, cudaStream_t s = 0)
@@ -433,6 +534,8 @@ extern "C" int hamx_destroy(hamx_handle h)
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_partial); cudaFree(h->d_arrivals); cudaFree(h->d_top2);
     cudaFree(h->d_parts); cudaFree(h->d_dm); cudaFree(h->d_counts); cudaFree(h->d_ngood); cudaFree(h->d_pairs);
+    hamx_p2p_close(h);
+    cudaFree(h->d_p2p_local);
     cudaStreamDestroy(h->own_stream);
     delete h;
     return ORBX_OK;
@@ -475,7 +578,8 @@ static void plan_split(int sm_count, int64_t nqb, int ntiles, int64_t npairs, in
     *tps_out = tps;
 }
 
-static int launch_chunk(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int nt, int64_t offset, hamx_top2* d_out)
+static int launch_chunk(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int nt, int64_t offset, hamx_top2* d_out,
+                        const P2PView* pv = nullptr)
 {
     const int64_t nqb = (nq + HT_QB - 1) / HT_QB;
     const int ntiles = (nt + HT_TT - 1) / HT_TT;
@@ -490,8 +594,12 @@ static int launch_chunk(hamx_handle h, const uint8_t* d_q, int64_t nq, const uin
     hamx_pair one;
     one.q = d_q; one.t = d_t; one.nq = (int32_t)nq; one.nt = nt;
     dim3 grid((unsigned int)nqb, (unsigned int)nsplit, 1);
-    k_hamming_knn2<<<grid, HT_THREADS, 0, h->stream>>>(one, nullptr, tps, h->d_partial, (size_t)nq, h->d_arrivals, (int)nqb, d_out, 0,
-                                                        offset);
+    if (pv)
+        k_hamming_knn2<true><<<grid, HT_THREADS, 0, h->stream>>>(one, nullptr, tps, h->d_partial, (size_t)nq, h->d_arrivals, (int)nqb,
+                                                                  d_out, 0, offset, *pv);
+    else
+        k_hamming_knn2<false><<<grid, HT_THREADS, 0, h->stream>>>(one, nullptr, tps, h->d_partial, (size_t)nq, h->d_arrivals, (int)nqb,
+                                                                   d_out, 0, offset, kNoP2P);
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }
@@ -521,8 +629,8 @@ extern "C" int hamx_match_pairs_dev(hamx_handle h, const hamx_pair* d_pairs, int
     hamx_pair none;
     memset(&none, 0, sizeof(none));
     dim3 grid((unsigned int)nqb, (unsigned int)nsplit, (unsigned int)npairs);
-    k_hamming_knn2<<<grid, HT_THREADS, 0, h->stream>>>(none, d_pairs, tps, h->d_partial, (size_t)max_nq, h->d_arrivals, (int)nqb,
-                                                        h->d_top2, (size_t)max_nq, 0);
+    k_hamming_knn2<false><<<grid, HT_THREADS, 0, h->stream>>>(none, d_pairs, tps, h->d_partial, (size_t)max_nq, h->d_arrivals, (int)nqb,
+                                                               h->d_top2, (size_t)max_nq, 0, kNoP2P);
     ORBX_CUDA(cudaGetLastError());
     k_ratio_compact<<<npairs, 1024, 0, h->stream>>>(h->d_top2, (size_t)max_nq, 0, d_pairs, ratio, d_good, good_stride, (long long*)d_ngood);
     ORBX_CUDA(cudaGetLastError());
@@ -657,6 +765,137 @@ extern "C" int hamx_match_ratio(hamx_handle h, const uint8_t* q, int64_t nq, con
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     *ngood = n;
     return ORBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ peer-memory path
+static size_t p2p_flag_bytes(int world) { return align_up((size_t)2 * world * sizeof(unsigned int), 256); }
+
+static void p2p_set_view(hamx_handle h, int r, void* base)
+{
+    h->pv.flags[r] = reinterpret_cast<unsigned int*>(base);
+    h->pv.gather[r] = reinterpret_cast<hamx_top2*>(reinterpret_cast<uint8_t*>(base) + p2p_flag_bytes(h->pv.world));
+}
+
+extern "C" int hamx_p2p_export(hamx_handle h, int64_t nq_max, int world, int rank, uint8_t* ipc_handle, void** local_base)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_p2p_export: NULL handle");
+    ORBX_REQUIRE(world >= 1 && world <= HT_MAX_WORLD && rank >= 0 && rank < world && nq_max >= 1 && nq_max < (1ll << 31),
+                 "hamx_p2p_export: bad world %d / rank %d / nq_max %lld", world, rank, (long long)nq_max);
+    ORBX_REQUIRE(h->p2p_buf == nullptr, "hamx_p2p_export: already exported; call hamx_p2p_close first");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    memset(&h->pv, 0, sizeof(h->pv));
+    h->pv.world = world; h->pv.rank = rank; h->pv.nq_max = nq_max;
+    h->p2p_bytes = p2p_flag_bytes(world) + (size_t)2 * world * (size_t)nq_max * sizeof(hamx_top2);
+    cudaError_t e = cudaMalloc(&h->p2p_buf, h->p2p_bytes);
+    if (e != cudaSuccess) { h->p2p_buf = nullptr; set_error("hamx_p2p_export: cudaMalloc(%zu) failed: %s", h->p2p_bytes, cudaGetErrorString(e)); return ORBX_E_ALLOC; }
+    ORBX_CUDA(cudaMemset(h->p2p_buf, 0, p2p_flag_bytes(world)));     // epoch 0 = nothing published
+    ORBX_CUDA(cudaMalloc((void**)&h->pv.done, 256));
+    ORBX_CUDA(cudaMemset(h->pv.done, 0, 256));
+    ORBX_CUDA(cudaDeviceSynchronize());
+    p2p_set_view(h, rank, h->p2p_buf);
+    if (ipc_handle) {
+        cudaIpcMemHandle_t ih;
+        ORBX_CUDA(cudaIpcGetMemHandle(&ih, h->p2p_buf));
+        static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(ipc_handle, &ih, sizeof(ih));
+    }
+    if (local_base) *local_base = h->p2p_buf;
+    return ORBX_OK;
+}
+
+extern "C" int hamx_p2p_import(hamx_handle h, const uint8_t* ipc_handles)
+{
+    ORBX_REQUIRE(h != nullptr && h->p2p_buf != nullptr && ipc_handles != nullptr, "hamx_p2p_import: export first");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    for (int r = 0; r < h->pv.world; r++) {
+        if (r == h->pv.rank) continue;
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, ipc_handles + (size_t)r * sizeof(ih), sizeof(ih));
+        void* base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { set_error("hamx_p2p_import: cannot map rank %d's buffer: %s", r, cudaGetErrorString(e)); return ORBX_E_CUDA; }
+        h->p2p_opened[r] = base;
+        p2p_set_view(h, r, base);
+    }
+    return ORBX_OK;
+}
+
+extern "C" int hamx_p2p_import_ptrs(hamx_handle h, void* const* peer_bases)
+{
+    ORBX_REQUIRE(h != nullptr && h->p2p_buf != nullptr && peer_bases != nullptr, "hamx_p2p_import_ptrs: export first");
+    for (int r = 0; r < h->pv.world; r++) {
+        if (r == h->pv.rank) continue;
+        ORBX_REQUIRE(peer_bases[r] != nullptr, "hamx_p2p_import_ptrs: NULL base for rank %d", r);
+        p2p_set_view(h, r, peer_bases[r]);
+    }
+    return ORBX_OK;
+}
+
+extern "C" int hamx_p2p_close(hamx_handle h)
+{
+    if (!h) return ORBX_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < HT_MAX_WORLD; r++)
+        if (h->p2p_opened[r]) { cudaIpcCloseMemHandle(h->p2p_opened[r]); h->p2p_opened[r] = nullptr; }
+    if (h->pv.done) cudaFree(h->pv.done);
+    if (h->p2p_buf) cudaFree(h->p2p_buf);
+    h->p2p_buf = nullptr;
+    memset(&h->pv, 0, sizeof(h->pv));
+    return ORBX_OK;
+}
+
+static int p2p_ready(hamx_handle h, int64_t nq, const char* fn)
+{
+    ORBX_REQUIRE(h != nullptr, "%s: NULL handle", fn);
+    ORBX_REQUIRE(h->p2p_buf != nullptr, "%s: call hamx_p2p_export / hamx_p2p_import first", fn);
+    for (int r = 0; r < h->pv.world; r++) ORBX_REQUIRE(h->pv.gather[r] != nullptr, "%s: rank %d's buffer has not been imported", fn, r);
+    ORBX_REQUIRE(nq >= 1 && nq <= h->pv.nq_max, "%s: nq %lld outside [1, nq_max=%lld]", fn, (long long)nq, (long long)h->pv.nq_max);
+    return ORBX_OK;
+}
+
+// Collective, phase 1: local top-2 over this rank's train shard, scattered into every rank's gather buffer by the
+// matching kernel itself.  All ranks must call it with the same nq, the same number of times.
+extern "C" int hamx_knn2_p2p_scatter_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset)
+{
+    int rc = p2p_ready(h, nq, "hamx_knn2_p2p_scatter_dev");
+    if (rc) return rc;
+    ORBX_REQUIRE(nt >= 0 && train_offset >= 0 && nt + train_offset < (1ll << 31), "hamx_knn2_p2p_scatter_dev: indices must fit int32");
+    ORBX_REQUIRE(d_q && (nt == 0 || d_t), "hamx_knn2_p2p_scatter_dev: NULL pointer");
+    if ((((uintptr_t)d_q) | ((uintptr_t)d_t)) & 15) { set_error("hamx_knn2_p2p_scatter_dev: device pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    h->pv.epoch += 1;
+    if (h->pv.epoch == 0) h->pv.epoch = 1;
+    if (nt > 0 && nt <= (1ll << HT_IDX_BITS)) return launch_chunk(h, d_q, nq, d_t, (int)nt, train_offset, nullptr, &h->pv);
+    // empty or multi-launch shard: compute locally, then scatter
+    rc = grow(&h->d_p2p_local, &h->p2p_local_bytes, (size_t)nq * sizeof(hamx_top2));
+    if (rc) return rc;
+    rc = hamx_knn2_dev(h, d_q, nq, d_t, nt, train_offset, h->d_p2p_local);
+    if (rc) return rc;
+    const int blocks = (int)std::min<int64_t>((nq + 255) / 256, (int64_t)h->sm_count * 8);
+    k_scatter_p2p<<<blocks, 256, 0, h->stream>>>(h->d_p2p_local, nq, h->pv);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// Collective, phase 2: wait for every rank's scatter of the current call, merge -> d_out[nq] (identical on all ranks).
+extern "C" int hamx_p2p_merge_dev(hamx_handle h, int64_t nq, hamx_top2* d_out)
+{
+    int rc = p2p_ready(h, nq, "hamx_p2p_merge_dev");
+    if (rc) return rc;
+    ORBX_REQUIRE(d_out != nullptr && h->pv.epoch != 0, "hamx_p2p_merge_dev: no scatter in flight or NULL output");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    k_merge_top2_p2p<<<(unsigned int)((nq + 255) / 256), 256, 0, h->stream>>>(nq, d_out, h->pv);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int hamx_knn2_p2p_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
+                                 hamx_top2* d_out)
+{
+    int rc = hamx_knn2_p2p_scatter_dev(h, d_q, nq, d_t, nt, train_offset);
+    if (rc) return rc;
+    return hamx_p2p_merge_dev(h, nq, d_out);
 }
 
 extern "C" int hamx_popc_peak(int device, double* gpopc_per_s, double* elapsed_ms)

@@ -301,6 +301,37 @@ class BFMatcher:
     def knn2_dev(self, d_q, nq, d_t, nt, train_offset, d_out):
         check(_lib.lib().hamx_knn2_dev(self._h, d_q, nq, d_t, nt, train_offset, d_out))
 
+    # -- train-sharded matching over peer memory (include/orbx.h "hamx_p2p_*")
+    def p2p_export(self, nq_max, world, rank):
+        """Allocate this rank's gather buffer; returns (64-byte cudaIpc handle as bytes, local device base address)."""
+        buf = (C.c_uint8 * 64)()
+        base = C.c_void_p()
+        check(_lib.lib().hamx_p2p_export(self._h, int(nq_max), int(world), int(rank), buf, C.byref(base)))
+        return bytes(buf), base.value
+
+    def p2p_import(self, handles):
+        """handles: the world's 64-byte cudaIpc handles in rank order (other processes' buffers)."""
+        blob = b"".join(handles)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(_lib.lib().hamx_p2p_import(self._h, arr))
+
+    def p2p_import_ptrs(self, bases):
+        """Same-process variant: device base addresses of the world's buffers in rank order."""
+        arr = (C.c_void_p * len(bases))(*[C.c_void_p(b) for b in bases])
+        check(_lib.lib().hamx_p2p_import_ptrs(self._h, arr))
+
+    def p2p_close(self):
+        check(_lib.lib().hamx_p2p_close(self._h))
+
+    def knn2_p2p_dev(self, d_q, nq, d_t, nt, train_offset, d_out):
+        check(_lib.lib().hamx_knn2_p2p_dev(self._h, d_q, nq, d_t, nt, train_offset, d_out))
+
+    def knn2_p2p_scatter_dev(self, d_q, nq, d_t, nt, train_offset):
+        check(_lib.lib().hamx_knn2_p2p_scatter_dev(self._h, d_q, nq, d_t, nt, train_offset))
+
+    def p2p_merge_dev(self, nq, d_out):
+        check(_lib.lib().hamx_p2p_merge_dev(self._h, nq, d_out))
+
     def merge_top2_dev(self, d_parts, nparts, nq, d_out):
         check(_lib.lib().hamx_merge_top2_dev(self._h, d_parts, nparts, nq, d_out))
 

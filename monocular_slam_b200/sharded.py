@@ -5,9 +5,12 @@
   ``frame_block`` gives rank r a contiguous block so consecutive-frame matching stays local; the block's first frame is
   matched against the previous rank's last frame, which the rank simply extracts itself (one extra frame, no exchange).
 * Large map-vs-frame / loop-closure matching shards the TRAIN set: every rank computes the per-query top-2 over its
-  contiguous train range with global indices, ONE all-gather moves the 16-byte candidates (nq x 16 B per rank) and a
-  merge kernel reduces them.  Top-2 under the lexicographic (distance, index) order is associative and commutative, so the
-  merged result is bit-identical to a single-device pass.
+  contiguous train range with global indices and the 16-byte candidates (nq x 16 B per rank) are exchanged and merged.
+  Top-2 under the lexicographic (distance, index) order is associative and commutative, so the merged result is
+  bit-identical to a single-device pass.  Two exchanges exist: ``p2p=True`` (product path on an NVLink box) -- the
+  matching kernel stores its results straight into every rank's gather buffer over peer memory and a merge kernel waits
+  on device-side flags, no NCCL call on the data path; ``p2p=False`` -- ONE NCCL all-gather followed by a merge kernel
+  (the baseline the fused path is compared with, and the path the CPU/gloo tests exercise with injected stand-ins).
 """
 import numpy as np
 
@@ -34,7 +37,7 @@ class ShardedMatcher:
     (ranges, offsets, the single all-gather) can be exercised on CPU by injecting stand-ins (tests do, over gloo).
     """
 
-    def __init__(self, matcher=None, group=None, local_top2=None, merge=None):
+    def __init__(self, matcher=None, group=None, local_top2=None, merge=None, p2p=False, nq_max=0):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -45,6 +48,30 @@ class ShardedMatcher:
         self._merge = merge or self._merge_cuda
         if matcher is None and (local_top2 is None or merge is None):
             raise ValueError("ShardedMatcher needs a BFMatcher (CUDA); there is no CPU implementation in this package")
+        self.p2p = bool(p2p)
+        self.nq_max = int(nq_max)
+        if self.p2p:
+            self._setup_p2p()
+
+    def _setup_p2p(self):
+        """Export this rank's gather buffer, exchange the cudaIpc handles (plumbing: one all_gather_object), map the peers."""
+        if self.matcher is None or self.nq_max < 1:
+            raise ValueError("p2p=True needs a BFMatcher and nq_max >= 1")
+        handle, _ = self.matcher.p2p_export(self.nq_max, self.world, self.rank)
+        handles = [handle]
+        if self.world > 1:
+            handles = [None] * self.world
+            self.dist.all_gather_object(handles, handle, group=self.group)
+        self.matcher.p2p_import(handles)
+        if self.world > 1:
+            self.dist.barrier(group=self.group)     # nobody scatters before every rank has mapped every buffer
+
+    def close(self):
+        if self.p2p and self.matcher is not None:
+            if self.world > 1:
+                self.dist.barrier(group=self.group)  # peers may still be writing into this rank's buffer
+            self.matcher.p2p_close()
+            self.p2p = False
 
     # ---- CUDA implementations (hamx_knn2_dev / hamx_merge_top2_dev on the current torch stream)
     def _use_current_stream(self):
@@ -72,6 +99,13 @@ class ShardedMatcher:
     def knn2(self, q, t_shard, train_offset):
         """q: [nq, 32] uint8, replicated on every rank; t_shard: this rank's rows [train_offset, train_offset + len)."""
         import torch
+        if self.p2p:
+            if q.shape[0] > self.nq_max:
+                raise ValueError("%d queries exceed nq_max=%d of the peer-memory buffers" % (q.shape[0], self.nq_max))
+            self._use_current_stream()
+            out = torch.empty((q.shape[0], 4), dtype=torch.int32, device=q.device)
+            self.matcher.knn2_p2p_dev(q.data_ptr(), q.shape[0], t_shard.data_ptr(), t_shard.shape[0], int(train_offset), out.data_ptr())
+            return out
         local = self._local(q, t_shard, train_offset)
         if self.world == 1:
             return local

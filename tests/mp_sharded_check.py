@@ -1,0 +1,79 @@
+"""Multi-process check of the train-sharded matcher on real GPUs (run under torchrun, one rank per GPU):
+peer-memory (fused scatter + flag-wait merge) and NCCL all-gather exchanges must both equal a single-device pass.
+Launched by tests/test_gpu_multi.py when the box has >= 2 GPUs; also usable by hand:
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mp_sharded_check.py
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from monocular_slam_b200 import BFMatcher
+from monocular_slam_b200.sharded import ShardedMatcher, shard_bounds
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    m = BFMatcher(device=local)
+    m.set_stream(stream.cuda_stream)
+    nq_max = 70000
+    p2p = ShardedMatcher(m, p2p=True, nq_max=nq_max)
+    nccl = ShardedMatcher(m, p2p=False)
+    timings = {}
+    for case, (nq, nt) in enumerate([(2000, 200000), (1, 17), (257, 1000), (65536, 100003), (2000, 200000)]):
+        g = torch.Generator(device=dev)
+        g.manual_seed(1000 + case)                          # same data on every rank
+        q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=g)
+        t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device=dev, generator=g)
+        t[nt // 3] = q[0]
+        t[:: max(nt // 50, 1)] = t[0]                        # duplicates across shard borders
+        b = shard_bounds(nt, world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        shard = t[lo:hi].contiguous()
+        ref = torch.empty((nq, 4), dtype=torch.int32, device=dev)
+        m.knn2_dev(q.data_ptr(), nq, t.data_ptr(), nt, 0, ref.data_ptr())
+        for rep in range(3):
+            a = p2p.knn2(q, shard, lo)
+            c = nccl.knn2(q, shard, lo)
+            stream.synchronize()
+            assert torch.equal(a, ref), "rank %d case %d rep %d: peer-memory result differs from the single-device pass" % (rank, case, rep)
+            assert torch.equal(c, ref), "rank %d case %d rep %d: all-gather result differs from the single-device pass" % (rank, case, rep)
+        # device time of the two exchanges for the map-vs-frame shape (BASELINE config 4), max over ranks
+        if (nq, nt) == (2000, 200000):
+            for name, sm in (("p2p", p2p), ("nccl", nccl)):
+                for _ in range(5):
+                    sm.knn2(q, shard, lo)
+                stream.synchronize()
+                dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(50):
+                    sm.knn2(q, shard, lo)
+                e1.record(stream)
+                e1.synchronize()
+                mine = e0.elapsed_time(e1) / 50
+                ms = torch.tensor([mine], dtype=torch.float64, device=dev)
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                timings[name] = float(ms.item())
+                print("rank %d %s %.3f us" % (rank, name, mine * 1e3), file=sys.stderr, flush=True)
+    p2p.close()
+    m.close()
+    dist.barrier()
+    if rank == 0:
+        print("MP_SHARDED_OK world=%d  2000x200000: peer-memory %.1f us, nccl all-gather %.1f us per call" % (
+            world, timings["p2p"] * 1e3, timings["nccl"] * 1e3), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -143,3 +143,43 @@ def test_large_properties(matcher):
     m2, c2 = matcher.knnMatch(q[::-1], t, 2)
     i2, d2 = knn_arrays(m2, c2)
     assert np.array_equal(i2[::-1], idx) and np.array_equal(d2[::-1], dist)
+
+
+@pytest.mark.parametrize("world,nq,nt", [(1, 300, 1000), (2, 2000, 5001), (3, 777, 130), (4, 257, 4096), (8, 2000, 200000)])
+def test_p2p_fused_scatter_merge_single_process(world, nq, nt):
+    """hamx_knn2_p2p_*: `world` ranks emulated by `world` handles of one process on one GPU (same-process pointer import).
+    All scatters are queued before any merge, so no kernel ever waits on a later launch.  Twice, to cover both buffer
+    parities and the reuse of the completion counter."""
+    import torch
+    from monocular_slam_b200.sharded import shard_bounds
+    q = syn.descriptors(31, nq)
+    t = syn.descriptors(32, nt)
+    t[nt // 2] = q[5]                    # an exact hit and duplicated rows across shard borders: ties by lowest index
+    t[::97] = t[0]
+    want_idx, want_dist = oracle.knn2(q, t)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ms = [BFMatcher() for _ in range(world)]
+        for m in ms:
+            m.set_stream(stream.cuda_stream)
+        bases = [m.p2p_export(nq + 13, world, r)[1] for r, m in enumerate(ms)]
+        for m in ms:
+            m.p2p_import_ptrs(bases)
+        dq = torch.from_numpy(q).cuda()
+        dt = torch.from_numpy(t).cuda()
+        b = shard_bounds(nt, world)
+        for rep in range(3):
+            outs = [torch.full((nq, 4), -7, dtype=torch.int32, device="cuda") for _ in range(world)]
+            for r, m in enumerate(ms):
+                lo, hi = int(b[r]), int(b[r + 1])
+                shard = dt[lo:hi].contiguous() if hi > lo else torch.zeros((1, 32), dtype=torch.uint8, device="cuda")
+                m.knn2_p2p_scatter_dev(dq.data_ptr(), nq, shard.data_ptr(), hi - lo, lo)
+            for r, m in enumerate(ms):
+                m.p2p_merge_dev(nq, outs[r].data_ptr())
+            stream.synchronize()
+            for r in range(world):
+                got = outs[r].cpu().numpy()
+                assert np.array_equal(got[:, 1], want_idx[:, 0]) and np.array_equal(got[:, 3], want_idx[:, 1]), "rank %d rep %d" % (r, rep)
+                assert np.array_equal(got[:, 0], want_dist[:, 0]) and np.array_equal(got[:, 2], want_dist[:, 1])
+        for m in ms:
+            m.close()

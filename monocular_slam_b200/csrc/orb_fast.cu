@@ -101,7 +101,7 @@ __device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&r)[16], uint3
     return __vimax3_s16x2(bright, dark, K) - K;
 }
 
-__global__ void __launch_bounds__(FT_THREADS)
+__global__ void __launch_bounds__(FT_THREADS, 5)
 k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, size_t slot_stride, Cand* __restrict__ cand,
        size_t cand_stride, FrameCounters* __restrict__ ctr)
 {
@@ -126,14 +126,17 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
 
     if (tid == 0) s_en = 0;
     // s_score needs no clearing: every entry NMS consumes for a pixel of the tile proper is written by the scoring pass
-    for (int i = tid; i < FT_SH * (FT_SP / 16); i += FT_THREADS) {
-        int r = i / (FT_SP / 16), v = i - r * (FT_SP / 16);
-        int gy = gy0 + r, gx = gx0 + v * 16;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (gy < h && gx < pitch) val = *reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx);
-        uint4* dst = reinterpret_cast<uint4*>(s_img + r * FT_SP + v * 16);
-        dst[0] = make_uint4(lanes_lo(val.x), lanes_hi(val.x), lanes_lo(val.y), lanes_hi(val.y));
-        dst[1] = make_uint4(lanes_lo(val.z), lanes_hi(val.z), lanes_lo(val.w), lanes_hi(val.w));
+    // 8-byte units: 38 rows x 20 units = 760 = 3 per thread (less 8), so every warp reaches the barrier with the same work
+#pragma unroll
+    for (int k = 0; k < (FT_SH * (FT_SP / 8) + FT_THREADS - 1) / FT_THREADS; k++) {
+        const int i = tid + k * FT_THREADS;
+        if (i < FT_SH * (FT_SP / 8)) {
+            const int r = i / (FT_SP / 8), v = i - r * (FT_SP / 8);
+            const int gy = gy0 + r, gx = gx0 + v * 8;
+            uint2 val = make_uint2(0, 0);
+            if (gy < h && gx < pitch) val = *reinterpret_cast<const uint2*>(img + (size_t)gy * pitch + gx);
+            *reinterpret_cast<uint4*>(s_img + r * FT_SP + v * 8) = make_uint4(lanes_lo(val.x), lanes_hi(val.x), lanes_lo(val.y), lanes_hi(val.y));
+        }
     }
     __syncthreads();
 

@@ -93,6 +93,11 @@ ORBX_API int orbx_destroy(orbx_handle h);
 /* Run on a caller-provided cudaStream_t (e.g. the framework's current stream); NULL restores the handle's own. */
 ORBX_API int orbx_set_stream(orbx_handle h, void* cuda_stream);
 ORBX_API int orbx_synchronize(orbx_handle h);
+/* Input pixel format of every image pointer passed afterwards: 1 = CV_8UC1 gray (default), 3 = CV_8UC3 BGR interleaved
+ * (stride in bytes, >= 3 * w).  cv::ORB converts non-gray input with cvtColor(BGR2GRAY) before anything else -- the
+ * reference loads frames with CV_LOAD_IMAGE_UNCHANGED (src/FrameLoader.cpp:62) and hands them to detect()/compute()
+ * as they are (src/FeatureExtractor.cpp:17,19) -- and so does this library, on the device, bit-exactly. */
+ORBX_API int orbx_set_input_channels(orbx_handle h, int channels);
 /* Largest number of keypoints one frame can return with the handle's parameters (ties included). */
 ORBX_API int orbx_max_keypoints(orbx_handle h);
 /* Level geometry and quotas as the handle computes them (arrays of nlevels entries; any pointer may be NULL). */

@@ -120,6 +120,40 @@ k_ingest(const uint8_t* __restrict__ src, size_t frame_pitch, size_t stride, int
     }
 }
 
+// Same for 3-channel frames (cv::Mat CV_8UC3, BGR interleaved): cvtColor(BGR2GRAY) as cv::ORB applies it to non-gray
+// input, OpenCV's 15-bit fixed point gray = (B*3735 + G*19235 + R*9798 + 2^14) >> 15.  4 pixels (12 bytes) per thread.
+__global__ void __launch_bounds__(256)
+k_ingest_bgr(const uint8_t* __restrict__ src, size_t frame_pitch, size_t stride, int w, int h, uint8_t* __restrict__ slots,
+             size_t slot_stride, size_t dst_off, int dpitch, int word_ok)
+{
+    const uint8_t* s = src + blockIdx.z * frame_pitch;
+    uint8_t* d = slots + blockIdx.z * slot_stride + dst_off;
+    const int ngroups = (w + 3) >> 2;
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const uint8_t* sr = s + (size_t)y * stride;
+        uint8_t* dr = d + (size_t)y * dpitch;
+        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+            const int x = 4 * g;
+            uint32_t px[12];
+            if (word_ok && x + 4 <= w) {
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(sr + 3 * x);
+                const uint32_t a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2);
+#pragma unroll
+                for (int i = 0; i < 4; i++) { px[i] = (a >> (8 * i)) & 255u; px[4 + i] = (b >> (8 * i)) & 255u; px[8 + i] = (c >> (8 * i)) & 255u; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; i++) px[i] = (x + i / 3 < w) ? sr[3 * x + i] : 0u;
+            }
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                packed |= ((px[3 * j] * 3735u + px[3 * j + 1] * 19235u + px[3 * j + 2] * 9798u + (1u << 14)) >> 15) << (8 * j);
+            if (x + 4 <= w) *reinterpret_cast<uint32_t*>(dr + x) = packed;      // rows are 128-byte pitched: aligned
+            else for (int j = 0; x + j < w; j++) dr[x + j] = (uint8_t)(packed >> (8 * j));   // keep the padding columns zero
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_ingest(const uint8_t* d_frames, size_t frame_pitch, size_t stride, int w, int h, uint8_t* slots,
@@ -128,6 +162,15 @@ cudaError_t launch_ingest(const uint8_t* d_frames, size_t frame_pitch, size_t st
     const int vec_ok = (((uintptr_t)d_frames | frame_pitch | stride) & 15) == 0;
     dim3 grid(div_up(div_up(w, 16), 256), h < 270 ? h : 270, nframes);
     k_ingest<<<grid, 256, 0, s>>>(d_frames, frame_pitch, stride, w, h, slots, slot_stride, L0.img_off, L0.pitch, vec_ok);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ingest_bgr(const uint8_t* d_frames, size_t frame_pitch, size_t stride, int w, int h, uint8_t* slots,
+                              size_t slot_stride, const LevelGeom& L0, int nframes, cudaStream_t s)
+{
+    const int word_ok = (((uintptr_t)d_frames | frame_pitch | stride) & 3) == 0;
+    dim3 grid(div_up(div_up(w, 4), 256), h < 270 ? h : 270, nframes);
+    k_ingest_bgr<<<grid, 256, 0, s>>>(d_frames, frame_pitch, stride, w, h, slots, slot_stride, L0.img_off, L0.pitch, word_ok);
     return cudaGetLastError();
 }
 

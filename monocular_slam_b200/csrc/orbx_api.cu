@@ -26,6 +26,8 @@ cudaError_t launch_pyr_down_level(uint8_t* slots, size_t slot_stride, const Leve
 void fast_tile_dims(int* tw, int* th);
 cudaError_t launch_ingest(const uint8_t* d_frames, size_t frame_pitch, size_t stride, int w, int h, uint8_t* slots,
                           size_t slot_stride, const LevelGeom& L0, int nframes, cudaStream_t s);
+cudaError_t launch_ingest_bgr(const uint8_t* d_frames, size_t frame_pitch, size_t stride, int w, int h, uint8_t* slots,
+                              size_t slot_stride, const LevelGeom& L0, int nframes, cudaStream_t s);
 cudaError_t harris_select_prepare(int max_surv_cap);
 cudaError_t launch_harris_select(const FrameGeom& g, const uint8_t* slots, size_t slot_stride, const Cand* surv,
                                  size_t surv_stride, Sel* sel, size_t sel_stride, FrameCounters* ctr, int nframes,
@@ -85,6 +87,9 @@ struct orbx_context {
     orbx_dmatch* d_good;
     int64_t* d_ngood;
     int64_t* h_ngood;
+    // 3-channel input (orbx_set_input_channels): packed BGR staging for the host paths, allocated on first use
+    int channels;
+    uint8_t* d_bgr;
     // pipelined host path
     orbx_lane lanes[ORBX_LANES];
     int lane_head, lane_next;                 // oldest batch in flight, lane the next submission uses
@@ -96,6 +101,7 @@ struct orbx_context {
 };
 
 static inline int rne_f(float v) { return (int)lrintf(v); }
+static int require_idle(orbx_handle h, const char* fn);
 
 // Level sizes, quotas, list capacities and buffer offsets for a w x h frame.
 static int build_geometry(const orbx_params& p, int w, int h, FrameGeom* g)
@@ -275,6 +281,7 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     h->p = p;
     h->max_w = max_w; h->max_h = max_h; h->max_batch = max_batch;
     h->geom_w = h->geom_h = -1;
+    h->channels = 1;
     {
         float scale = 1.f / ((1 << 2) * 7 * 255.f);    // OpenCV HarrisResponses, blockSize 7
         h->harris_s4 = scale * scale * scale * scale;
@@ -349,7 +356,7 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_slots); cudaFree(h->d_cand); cudaFree(h->d_surv); cudaFree(h->d_sel); cudaFree(h->d_ctr);
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_tab);
-    cudaFree(h->d_prev_desc); cudaFree(h->d_prev_count); cudaFree(h->d_good); cudaFree(h->d_ngood);
+    cudaFree(h->d_prev_desc); cudaFree(h->d_prev_count); cudaFree(h->d_good); cudaFree(h->d_ngood); cudaFree(h->d_bgr);
     if (h->h_ngood) cudaFreeHost(h->h_ngood);
     if (h->events) { for (cudaEvent_t e : *h->events) cudaEventDestroy(e); delete h->events; }
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -384,6 +391,16 @@ extern "C" int orbx_synchronize(orbx_handle h)
     return ORBX_OK;
 }
 
+extern "C" int orbx_set_input_channels(orbx_handle h, int channels)
+{
+    ORBX_REQUIRE(h != nullptr, "orbx_set_input_channels: NULL handle");
+    ORBX_REQUIRE(channels == 1 || channels == 3, "orbx_set_input_channels: %d channels (only CV_8UC1 and CV_8UC3 BGR are supported)", channels);
+    int rc = require_idle(h, "orbx_set_input_channels");
+    if (rc) return rc;
+    h->channels = channels;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_max_keypoints(orbx_handle h) { return h ? h->dev_cap : ORBX_E_INVALID; }
 
 extern "C" int orbx_level_info(orbx_handle h, int w, int hh, int32_t* widths, int32_t* heights, float* scales, int32_t* quotas)
@@ -410,13 +427,28 @@ static int build_pyramids(orbx_handle h, int f0, int nframes)
     return ORBX_OK;
 }
 
-// frames[f0 .. f0 + nframes) -> slots slot0 + f0 ..
+// frames[f0 .. f0 + nframes) -> slots slot0 + f0 ..  (3-channel frames go through the packed BGR staging buffer and
+// the conversion kernel, queued on the same stream as the copies)
 static int upload_frames(orbx_handle h, const uint8_t* const* frames, int f0, int nframes, int w, int hh, size_t stride,
                          cudaMemcpyKind kind, cudaStream_t s, int slot0 = 0)
 {
+    if (h->channels == 1) {
+        for (int f = f0; f < f0 + nframes; f++)
+            ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)(slot0 + f) * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch, frames[f],
+                                        stride, (size_t)w, (size_t)hh, kind, s));
+        return ORBX_OK;
+    }
+    ORBX_REQUIRE(stride >= (size_t)w * 3, "3-channel frame: stride %zu is smaller than 3 * width %d", stride, w);
+    const size_t frame_bytes = align_up((size_t)h->max_w * 3, 16) * (size_t)h->max_h;
+    if (!h->d_bgr) {
+        cudaError_t e = cudaMalloc((void**)&h->d_bgr, frame_bytes * (size_t)h->max_batch * ORBX_LANES);
+        if (e != cudaSuccess) { h->d_bgr = nullptr; set_error("cudaMalloc of the BGR staging buffer failed: %s", cudaGetErrorString(e)); return ORBX_E_ALLOC; }
+    }
+    const size_t row = align_up((size_t)w * 3, 16);
     for (int f = f0; f < f0 + nframes; f++)
-        ORBX_CUDA(cudaMemcpy2DAsync(h->d_slots + (size_t)(slot0 + f) * h->slot_stride + h->g.lv[0].img_off, h->g.lv[0].pitch, frames[f],
-                                    stride, (size_t)w, (size_t)hh, kind, s));
+        ORBX_CUDA(cudaMemcpy2DAsync(h->d_bgr + (size_t)(slot0 + f) * frame_bytes, row, frames[f], stride, (size_t)w * 3, (size_t)hh, kind, s));
+    ORBX_CUDA(launch_ingest_bgr(h->d_bgr + (size_t)(slot0 + f0) * frame_bytes, frame_bytes, row, w, hh,
+                                h->d_slots + (size_t)(slot0 + f0) * h->slot_stride, h->slot_stride, h->g.lv[0], nframes, s));
     return ORBX_OK;
 }
 
@@ -511,7 +543,8 @@ static int common_checks(orbx_handle h, const void* img, int w, int hh, size_t s
 {
     ORBX_REQUIRE(h != nullptr, "%s: NULL handle", fn);
     ORBX_REQUIRE(img != nullptr, "%s: NULL image", fn);
-    ORBX_REQUIRE(w >= 1 && hh >= 1 && stride >= (size_t)w, "%s: bad image geometry %dx%d stride %zu", fn, w, hh, stride);
+    ORBX_REQUIRE(w >= 1 && hh >= 1 && stride >= (size_t)w * h->channels, "%s: bad image geometry %dx%d (%d channel(s)) stride %zu", fn, w,
+                 hh, h->channels, stride);
     int rc = require_idle(h, fn);
     if (rc) return rc;
     ORBX_CUDA(cudaSetDevice(h->device));
@@ -614,7 +647,10 @@ extern "C" int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, si
     if (((uintptr_t)d_desc & 3) || ((uintptr_t)d_out & 3)) { set_error("orbx_extract_batch_dev: output pointers must be 4-byte aligned"); return ORBX_E_ALIGN; }
     int rc = common_checks(h, d_frames, w, hh, stride, "orbx_extract_batch_dev");
     if (rc) return rc;
-    ORBX_CUDA(launch_ingest(d_frames, frame_pitch_bytes, stride, w, hh, h->d_slots, h->slot_stride, h->g.lv[0], nframes, h->stream));
+    if (h->channels == 3)
+        ORBX_CUDA(launch_ingest_bgr(d_frames, frame_pitch_bytes, stride, w, hh, h->d_slots, h->slot_stride, h->g.lv[0], nframes, h->stream));
+    else
+        ORBX_CUDA(launch_ingest(d_frames, frame_pitch_bytes, stride, w, hh, h->d_slots, h->slot_stride, h->g.lv[0], nframes, h->stream));
     rc = run_extract(h, 0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_out, d_desc, cap, d_counts);
     if (rc) return rc;
     h->dev_pending = true;
@@ -719,7 +755,7 @@ extern "C" int orbx_submit_batch(orbx_handle h, hamx_handle m, const uint8_t* co
     ORBX_REQUIRE(frames && out && desc && counts && (m == nullptr || (good && ngood)), "orbx_submit_batch: NULL pointer");
     ORBX_REQUIRE(nframes >= 1 && nframes <= h->max_batch, "orbx_submit_batch: %d frames outside [1, max_batch=%d]", nframes, h->max_batch);
     ORBX_REQUIRE(cap >= 1 && cap <= h->dev_cap, "orbx_submit_batch: capacity %d outside [1, %d]", cap, h->dev_cap);
-    ORBX_REQUIRE(frames[0] && w >= 1 && hh >= 1 && stride >= (size_t)w, "orbx_submit_batch: bad image geometry %dx%d stride %zu", w, hh, stride);
+    ORBX_REQUIRE(frames[0] && w >= 1 && hh >= 1 && stride >= (size_t)w * h->channels, "orbx_submit_batch: bad image geometry %dx%d stride %zu", w, hh, stride);
     const int li = h->lane_next;
     orbx_lane& L = h->lanes[li];
     ORBX_REQUIRE(!L.busy, "orbx_submit_batch: %d batches are already in flight; call orbx_wait_batch first", ORBX_LANES);

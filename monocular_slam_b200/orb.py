@@ -23,10 +23,14 @@ NORM_HAMMING = 6   # cv::NORM_HAMMING
 
 
 def _gray(image):
+    """An h x w (CV_8UC1) or h x w x 3 (CV_8UC3, BGR) uint8 image with contiguous rows; 3-channel frames are converted to
+    gray on the device, as cv::ORB does on the CPU."""
     img = np.asarray(image)
-    if img.dtype != np.uint8 or img.ndim != 2:
-        raise ValueError("expected an h x w uint8 grayscale image, got %s %s" % (img.dtype, img.shape))
-    if img.strides[1] != 1 or img.strides[0] < img.shape[1]:
+    if img.dtype != np.uint8 or not (img.ndim == 2 or (img.ndim == 3 and img.shape[2] == 3)):
+        raise ValueError("expected an h x w (gray) or h x w x 3 (BGR) uint8 image, got %s %s" % (img.dtype, img.shape))
+    if img.ndim == 2 and (img.strides[1] != 1 or img.strides[0] < img.shape[1]):
+        img = np.ascontiguousarray(img)
+    if img.ndim == 3 and (img.strides[2] != 1 or img.strides[1] != 3 or img.strides[0] < 3 * img.shape[1]):
         img = np.ascontiguousarray(img)
     return img
 
@@ -46,6 +50,17 @@ class ORB:
                                      max_batch))
         self.max_keypoints = _lib.lib().orbx_max_keypoints(self._h)
         self.default_cap = min(self.max_keypoints, nfeatures + max(nfeatures // 4, 512))
+
+    def _set_channels(self, img):
+        ch = 3 if img.ndim == 3 else 1
+        if ch != getattr(self, "_channels", 1):
+            check(_lib.lib().orbx_set_input_channels(self._h, ch))
+            self._channels = ch
+
+    def set_input_channels(self, channels):
+        """For the raw-pointer (_dev) entry points: 1 = gray, 3 = BGR interleaved."""
+        check(_lib.lib().orbx_set_input_channels(self._h, int(channels)))
+        self._channels = int(channels)
 
     # -- lifetime (ProcessingNode::destroy)
     def close(self):
@@ -86,6 +101,7 @@ class ORB:
     # -- OrbFeatureDetector::detect(image, keypoints)
     def detect(self, image, cap=None):
         img = _gray(image)
+        self._set_channels(img)
 
         def run(cap):
             kps = np.zeros(cap, KEYPOINT_DTYPE)
@@ -99,6 +115,7 @@ class ORB:
     # -- OrbDescriptorExtractor::compute(image, keypoints, descriptors)
     def compute(self, image, keypoints):
         img = _gray(image)
+        self._set_channels(img)
         kps = np.array(keypoints, dtype=KEYPOINT_DTYPE, copy=True)
         n = C.c_int(len(kps))
         desc = np.zeros((max(len(kps), 1), 32), np.uint8)
@@ -108,6 +125,7 @@ class ORB:
 
     def detectAndCompute(self, image, cap=None):
         img = _gray(image)
+        self._set_channels(img)
 
         def run(cap):
             kps = np.zeros(cap, KEYPOINT_DTYPE)
@@ -124,10 +142,11 @@ class ORB:
         """frames: sequence of h x w uint8 arrays (or one n x h x w array).  Returns (kps[n, cap], desc[n, cap, 32], counts[n]).
         ``out`` may carry preallocated (kps, desc, counts) buffers, e.g. pinned memory."""
         frames = [_gray(f) for f in frames]
+        self._set_channels(frames[0])
         n = len(frames)
-        h, w = frames[0].shape
+        h, w = frames[0].shape[:2]
         stride = frames[0].strides[0]
-        if any(f.shape != (h, w) or f.strides[0] != stride for f in frames):
+        if any(f.shape != frames[0].shape or f.strides[0] != stride for f in frames):
             raise ValueError("all frames of a batch must share one shape and stride")
         ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
 
@@ -171,10 +190,11 @@ class ORB:
         ``out`` = (kps[n, cap], desc[n, cap, 32], counts[n] int32, good[n, cap], ngood[n] int64): caller-owned buffers
         (pinned for real overlap) that are complete after the matching ``wait_batch()``."""
         frames = [_gray(f) for f in frames]
+        self._set_channels(frames[0])
         n = len(frames)
-        h, w = frames[0].shape
+        h, w = frames[0].shape[:2]
         stride = frames[0].strides[0]
-        if any(f.shape != (h, w) or f.strides[0] != stride for f in frames):
+        if any(f.shape != frames[0].shape or f.strides[0] != stride for f in frames):
             raise ValueError("all frames of a batch must share one shape and stride")
         kps, desc, counts, good, ngood = out
         cap = kps.shape[1]
@@ -213,6 +233,7 @@ class ORB:
     # -- stage taps for parity tests
     def debug_pyramid_level(self, image, level):
         img = _gray(image)
+        self._set_channels(img)
         ws, hs, _, _ = self.level_info(img.shape[1], img.shape[0])
         out = np.zeros((hs[level], ws[level]), np.uint8)
         check(_lib.lib().orbx_debug_pyramid_level(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], level,
@@ -221,6 +242,7 @@ class ORB:
 
     def debug_fast_level(self, image, level):
         img = _gray(image)
+        self._set_channels(img)
         ws, hs, _, _ = self.level_info(img.shape[1], img.shape[0])
         cap = (int(ws[level]) // 2 + 1) * (int(hs[level]) // 2 + 1)
         xs, ys, sc = (np.zeros(cap, np.int32) for _ in range(3))

@@ -89,3 +89,8 @@ def planted_queries(seed, train, nq, frac=0.5, max_flips=20):
         for b in bits:
             q[r, b >> 3] ^= np.uint8(1 << (b & 7))
     return q
+
+
+def bgr_frame(seed, w, h):
+    """A 3-channel (BGR, 8UC3) frame: three differently seeded gray frames as channels, so the gray conversion matters."""
+    return np.ascontiguousarray(np.stack([frame(seed + 101 * c, w, h, nrect=120) for c in range(3)], axis=2))

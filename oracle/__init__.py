@@ -81,6 +81,8 @@ def lib():
         L.orc_compute.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, u8p]
         L.orc_level_fast.argtypes = [PP, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, i32p, i32p, i32p, C.c_int]
         L.orc_knn2.argtypes = [u8p, C.c_int64, u8p, C.c_int64, i32p, i32p]
+        L.orc_bgr2gray.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p]
+        L.orc_bgr2gray.restype = None
         L.orc_ratio_test.restype = C.c_int64
         L.orc_ratio_test.argtypes = [i32p, i32p, C.c_int64, C.c_float, i32p, i32p, i32p]
         _lib = L
@@ -95,8 +97,19 @@ def _i32(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
+def bgr2gray(img):
+    """cvtColor(BGR2GRAY) as cv::ORB applies it to 3-channel input (orc_bgr2gray)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 3 and img.shape[2] == 3
+    out = np.zeros(img.shape[:2], np.uint8)
+    lib().orc_bgr2gray(_u8(img), img.shape[1], img.shape[0], img.strides[0], _u8(out))
+    return out
+
+
 def _gray(img):
     img = np.ascontiguousarray(img, dtype=np.uint8)
+    if img.ndim == 3:
+        return bgr2gray(img)
     assert img.ndim == 2
     return img
 

@@ -78,6 +78,21 @@ void orc_level_quotas(const orc_params* p, int* q)
     q[p->nlevels - 1] = last > 0 ? last : 0;
 }
 
+/* ---- A0': gray conversion.  cv::ORB starts with `if (image.type() != CV_8UC1) cvtColor(image, gray, COLOR_BGR2GRAY)`
+ * (the reference loads frames with CV_LOAD_IMAGE_UNCHANGED, src/FrameLoader.cpp:62, so 3-channel frames reach
+ * detect()/compute() at src/FeatureExtractor.cpp:17,19).  OpenCV 4.x 8-bit path: 15-bit fixed point,
+ * gray = (B*3735 + G*19235 + R*9798 + 2^14) >> 15 (imgproc color_rgb.simd.hpp RGB2Gray<uchar>); checked against
+ * cv2.cvtColor in tests/golden/make_golden.py. */
+void orc_bgr2gray(const uint8_t* bgr, int w, int h, size_t stride, uint8_t* gray /* w*h */)
+{
+    for (int y = 0; y < h; y++) {
+        const uint8_t* s = bgr + (size_t)y * stride;
+        uint8_t* d = gray + (size_t)y * w;
+        for (int x = 0; x < w; x++)
+            d[x] = (uint8_t)((s[3 * x] * 3735 + s[3 * x + 1] * 19235 + s[3 * x + 2] * 9798 + (1 << 14)) >> 15);
+    }
+}
+
 /* ---- A1: INTER_LINEAR_EXACT resize, 8-bit, 1 channel (OpenCV imgproc resize.cpp, fixed-point path) ---- */
 static void linear_coeffs(int n, int m, int* ofs, int* c1)
 {

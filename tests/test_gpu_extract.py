@@ -189,7 +189,58 @@ def test_bad_arguments():
         ORB(nfeatures=-1)
     orb = _orb(500, HARRIS_SCORE, (64, 64))
     with pytest.raises(ValueError):
-        orb.detect(np.zeros((10, 10, 3), np.uint8))
+        orb.detect(np.zeros((10, 10, 4), np.uint8))          # only CV_8UC1 and CV_8UC3 exist on this path
+    with pytest.raises(ValueError):
+        orb.detect(np.zeros((10, 10), np.float32))
+    assert len(orb.detect(np.zeros((10, 10, 3), np.uint8))) == 0   # 3-channel frames are accepted (converted to gray)
     k = orb.detect(np.zeros((64, 64), np.uint8))
     assert len(k) == 0
+    orb.close()
+
+
+def test_bgr_input_golden(golden_dir):
+    """CV_8UC3 frames: gray conversion on the device (cvtColor BGR2GRAY arithmetic) + extraction == cv2 on the BGR frame;
+    single-frame, batched, pipelined and device-pointer entry points, odd width (unaligned rows) and aligned width."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "bgr_frame.npz"))
+    img = g["img"]
+    orb = ORB(nfeatures=500, max_size=(640, 480), max_batch=2)
+    k = orb.detect(img)
+    k, d = orb.compute(img, k)
+    assert_keypoints_equal(k, g["kp"], "bgr detect+compute")
+    assert_descriptors_equal(d, g["desc"], "bgr detect+compute")
+    gray = oracle.bgr2gray(img)
+    for level in (0, 3):
+        assert np.array_equal(orb.debug_pyramid_level(img, level), orb.debug_pyramid_level(gray, level))
+    kps, desc, counts = orb.extract_batch([img, img])
+    for i in range(2):
+        assert_keypoints_equal(kps[i, :counts[i]], g["kp"], "bgr batch %d" % i)
+        assert_descriptors_equal(desc[i, :counts[i]], g["desc"], "bgr batch %d" % i)
+    orb.close()
+    big = syn.bgr_frame(12, 640, 480)
+    orb = ORB(nfeatures=1000, max_size=(640, 480), max_batch=2)
+    kps, desc, counts = orb.extract_batch([big, big])
+    assert_keypoints_equal(kps[1, :counts[1]], g["big_kp"], "bgr 640x480 batch")
+    assert_descriptors_equal(desc[1, :counts[1]], g["big_desc"], "bgr 640x480 batch")
+    # device-resident BGR frames
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        orb.set_stream(stream.cuda_stream)
+        orb.set_input_channels(3)
+        cap = orb.default_cap
+        d_frames = torch.from_numpy(np.stack([big, big])).cuda()
+        d_kps = torch.empty((2, cap, 7), dtype=torch.float32, device="cuda")
+        d_desc = torch.empty((2, cap, 32), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+        orb.extract_batch_dev(d_frames.data_ptr(), 640 * 480 * 3, 2, 640, 480, 640 * 3, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
+        orb.check_dev()
+        stream.synchronize()
+    from monocular_slam_b200 import KEYPOINT_DTYPE
+    n = int(d_cnt[0])
+    assert_keypoints_equal(d_kps.cpu().numpy().view(KEYPOINT_DTYPE).reshape(2, cap)[0, :n], g["big_kp"], "bgr dev")
+    assert_descriptors_equal(d_desc.cpu().numpy()[0, :n], g["big_desc"], "bgr dev")
+    orb.set_stream(0)
+    # back to gray on the same handle
+    k1, d1 = orb.detectAndCompute(oracle.bgr2gray(big))
+    assert_keypoints_equal(k1, g["big_kp"], "gray after bgr")
     orb.close()

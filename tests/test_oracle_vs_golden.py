@@ -109,3 +109,19 @@ def test_quotas_and_sizes():
     assert oracle.level_sizes(P, 1920, 1080) == [(1920, 1080), (1600, 900), (1333, 750), (1111, 625), (926, 521), (772, 434),
                                                  (643, 362), (536, 301)]
     assert oracle.level_quotas(oracle.Params(nfeatures=500)) == [109, 90, 75, 63, 52, 44, 36, 31]
+
+
+def test_bgr_input(golden_dir):
+    """3-channel frames: the oracle's cvtColor(BGR2GRAY) restatement and the extraction behind it reproduce cv2."""
+    g = np.load(os.path.join(golden_dir, "bgr_frame.npz"))
+    assert np.array_equal(oracle.bgr2gray(g["lattice"]), g["lattice_gray"])
+    img = g["img"]
+    assert sha(oracle.bgr2gray(img)) == str(g["gray_sha"])
+    k, d = oracle.detect_and_compute(img, oracle.Params(nfeatures=500))
+    assert_keypoints_equal(k, g["kp"], "bgr 333x257")
+    assert_descriptors_equal(d, g["desc"], "bgr 333x257")
+    big = syn.bgr_frame(12, 640, 480)
+    assert sha(big) == str(g["big_sha"]) and sha(oracle.bgr2gray(big)) == str(g["big_gray_sha"])
+    k, d = oracle.detect_and_compute(big, oracle.Params(nfeatures=1000))
+    assert_keypoints_equal(k, g["big_kp"], "bgr 640x480")
+    assert_descriptors_equal(d, g["big_desc"], "bgr 640x480")

@@ -36,6 +36,7 @@ using cv::NORM_HAMMING;
 static inline const uint8_t* mat_ptr(const Mat& m) { return m.data; }
 static inline void mat_create_u8(Mat& m, int rows, int cols) { m.create(rows, cols, CV_8UC1); }
 static inline size_t mat_step(const Mat& m) { return m.step; }
+static inline int mat_channels(const Mat& m) { return m.channels(); }
 #else
 enum { NORM_HAMMING = 6 };
 struct Point2f { float x, y; };
@@ -46,13 +47,16 @@ struct KeyPoint {               // field order and size of cv::KeyPoint (28 byte
 struct DMatch {                 // cv::DMatch (16 bytes)
     int queryIdx, trainIdx, imgIdx; float distance;
 };
-struct Mat {                    // the part of cv::Mat the hot path touches: an 8-bit, single-channel matrix
+struct Mat {                    // the part of cv::Mat the hot path touches: an 8-bit matrix, 1 channel (gray, descriptors) or 3 (BGR)
     int rows = 0, cols = 0;
     size_t step = 0;
     uint8_t* data = nullptr;
+    int nchannels = 1;
     std::vector<uint8_t> storage;
     Mat() {}
-    Mat(int r, int c, uint8_t* borrowed, size_t stp = 0) : rows(r), cols(c), step(stp ? stp : (size_t)c), data(borrowed) {}
+    Mat(int r, int c, uint8_t* borrowed, size_t stp = 0, int ch = 1)
+        : rows(r), cols(c), step(stp ? stp : (size_t)c * ch), data(borrowed), nchannels(ch) {}
+    int channels() const { return nchannels; }
     void create(int r, int c) { rows = r; cols = c; step = (size_t)c; storage.assign((size_t)r * c, 0); data = storage.data(); }
     bool empty() const { return rows == 0 || cols == 0; }
     uint8_t* ptr(int r) { return data + (size_t)r * step; }
@@ -61,6 +65,7 @@ struct Mat {                    // the part of cv::Mat the hot path touches: an 
 static inline const uint8_t* mat_ptr(const Mat& m) { return m.data; }
 static inline void mat_create_u8(Mat& m, int rows, int cols) { m.create(rows, cols); }
 static inline size_t mat_step(const Mat& m) { return m.step; }
+static inline int mat_channels(const Mat& m) { return m.nchannels; }
 #endif
 
 static_assert(sizeof(KeyPoint) == sizeof(orbx_keypoint), "KeyPoint must have cv::KeyPoint's layout");
@@ -151,8 +156,13 @@ private:
             if (image.cols > maxw_) maxw_ = image.cols;
             if (image.rows > maxh_) maxh_ = image.rows;
             check(orbx_create(&h_, &p_, device_, maxw_, maxh_, 1), "ORB: orbx_create");   // lazily, like ProcessingNode::init()
+            channels_ = 1;
         }
+        // cv::ORB converts non-gray frames itself (the reference loads them CV_LOAD_IMAGE_UNCHANGED, src/FrameLoader.cpp:62)
+        const int ch = mat_channels(image);
+        if (ch != channels_) { check(orbx_set_input_channels(h_, ch), "ORB: orbx_set_input_channels"); channels_ = ch; }
     }
+    int channels_ = 1;
     orbx_handle h_;
     orbx_params p_;
     int device_, maxw_, maxh_;

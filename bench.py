@@ -395,7 +395,9 @@ def run_ours(args, rank, world, local_rank):
         q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=gq)
         gt = torch.Generator(device=dev); gt.manual_seed(60 + rank)
         t_shard = torch.randint(0, 256, (nt_shard, 32), dtype=torch.uint8, device=dev, generator=gt)
-        sm = ShardedMatcher(matcher)
+        # product exchange: peer memory (the matching kernel scatters its top-2 into every rank's gather buffer, flag-wait
+        # merge); with one rank there is nothing to exchange and the plain kernel runs
+        sm = ShardedMatcher(matcher, p2p=world > 1, nq_max=nq)
         out = {}
 
         def step_ham():
@@ -407,12 +409,29 @@ def run_ours(args, rank, world, local_rank):
         gpopc, _ = popc_peak(local_rank)
         gcmp = world * nq * nt_shard / (ham_ms * 1e-3) / 1e9
         hamming = {"value": gcmp, "unit": "Gcmp/s", "nq": nq, "nt_per_gpu": nt_shard, "ms_per_step": ham_ms, "clocks": ham_sampler.summary(),
-                   "workload": "%d queries x %d train rows per GPU (train-sharded, 1 all-gather of 16 B/query/rank + merge)" % (nq, nt_shard),
+                   "workload": "%d queries x %d train rows per GPU (train-sharded; %s)" % (
+                       nq, nt_shard, "top-2 exchanged over peer memory inside the matching kernel + flag-wait merge" if world > 1 else "single GPU, no exchange"),
                    "roofline": {"bound": "int_popc", "achieved": gcmp * 8, "peak": gpopc * world, "unit": "Gpopc/s",
                                 "frac": gcmp * 8 / (gpopc * world),
                                 "note": "ALGORITHMIC work of 8 POPC per 256-bit comparison (SURVEY.md 8d) against the register-only POPC "
                                         "microbenchmark (hamx_popc_peak) per GPU x n_gpus; frac > 1 because the kernel issues only 5 POPC per "
                                         "comparison after carry-save compression on the LOP3 pipe (csrc/hamming.cu ham256)"}}
+        # BASELINE.json configs[3]: map-vs-frame tracking match, 200k map descriptors x 2000 queries, train set sharded over the ranks
+        mq = q[:2000].contiguous()
+        m_nt = 200000 // world
+        gm = torch.Generator(device=dev); gm.manual_seed(90 + rank)
+        m_shard = torch.randint(0, 256, (m_nt, 32), dtype=torch.uint8, device=dev, generator=gm)
+        variants = {"peer_memory" if world > 1 else "single_gpu": sm}
+        if world > 1:
+            variants["nccl_all_gather"] = ShardedMatcher(matcher, p2p=False)
+        mvf = {"nq": 2000, "nt_total": m_nt * world, "unit": "us per call (device time, max over ranks)"}
+        for name, mm in variants.items():
+            def step_mvf():
+                out["m"] = mm.knn2(mq, m_shard, rank * m_nt)
+            mvf_ms, _ = timed(step_mvf, 50, 5)
+            mvf[name] = max_over_ranks(mvf_ms) / 50 * 1e3
+        hamming["map_vs_frame"] = mvf
+        sm.close()
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores
     cpu = None

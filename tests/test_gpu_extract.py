@@ -244,3 +244,24 @@ def test_bgr_input_golden(golden_dir):
     k1, d1 = orb.detectAndCompute(oracle.bgr2gray(big))
     assert_keypoints_equal(k1, g["big_kp"], "gray after bgr")
     orb.close()
+
+
+@pytest.mark.parametrize("name", ["l4_s15", "l1", "l12_s11_t30", "t10_fast", "l3_s20_t5", "l16_s105"])
+def test_parameter_surface_golden(golden_dir, name):
+    """Every runtime parameter orbx_create accepts, away from its default, against cv2's output (params_cases.npz)."""
+    g = np.load(os.path.join(golden_dir, "params_cases.npz"))
+    img = syn.frame(9, 640, 480)
+    nf, sf, nl, st, thr = g[name + "_params"]
+    orb = ORB(nfeatures=int(nf), scaleFactor=float(sf), nlevels=int(nl), scoreType=int(st), fastThreshold=int(thr), max_size=(640, 480),
+              max_batch=2)
+    k, d = orb.detectAndCompute(img)
+    assert_keypoints_equal(k, g[name + "_kp"], name)
+    assert_descriptors_equal(d, g[name + "_desc"], name)
+    k2 = orb.detect(img)
+    k2, d2 = orb.compute(img, k2)
+    assert_keypoints_equal(k2, g[name + "_kp"], name + " detect->compute")
+    assert_descriptors_equal(d2, g[name + "_desc"], name + " detect->compute")
+    kps, desc, counts = orb.extract_batch([img, img])
+    assert_keypoints_equal(kps[1, :counts[1]], g[name + "_kp"], name + " batch")
+    assert_descriptors_equal(desc[1, :counts[1]], g[name + "_desc"], name + " batch")
+    orb.close()

@@ -125,3 +125,19 @@ def test_bgr_input(golden_dir):
     k, d = oracle.detect_and_compute(big, oracle.Params(nfeatures=1000))
     assert_keypoints_equal(k, g["big_kp"], "bgr 640x480")
     assert_descriptors_equal(d, g["big_desc"], "bgr 640x480")
+
+
+PARAM_CASES = ["l4_s15", "l1", "l12_s11_t30", "t10_fast", "l3_s20_t5", "l16_s105"]
+
+
+@pytest.mark.parametrize("name", PARAM_CASES)
+def test_parameter_surface(golden_dir, name):
+    """nlevels / scaleFactor / fastThreshold / scoreType / nfeatures other than the defaults (cv2 golden)."""
+    g = np.load(os.path.join(golden_dir, "params_cases.npz"))
+    img = syn.frame(9, 640, 480)
+    assert sha(img) == str(g["img_sha"])
+    nf, sf, nl, st, thr = g[name + "_params"]
+    P = oracle.Params(nfeatures=int(nf), scale_factor=float(sf), nlevels=int(nl), score_type=int(st), fast_threshold=int(thr))
+    k, d = oracle.detect_and_compute(img, P)
+    assert_keypoints_equal(k, g[name + "_kp"], name)
+    assert_descriptors_equal(d, g[name + "_desc"], name)

@@ -47,6 +47,7 @@ struct orbx_lane {
     int64_t* ngood;
 };
 constexpr int ORBX_LANES = 2;
+constexpr int ORBX_SPLIT_MIN = 8;       // a batch is split in two when each half has at least this many frames
 
 struct orbx_context {
     int device;
@@ -87,6 +88,10 @@ struct orbx_context {
     orbx_dmatch* d_good;
     int64_t* d_ngood;
     int64_t* h_ngood;
+    // two-way split of large batches (run_extract)
+    bool split;
+    cudaStream_t sub_stream[2];
+    cudaEvent_t fork_event, join_event[2];
     // 3-channel input (orbx_set_input_channels): packed BGR staging for the host paths, allocated on first use
     int channels;
     uint8_t* d_bgr;
@@ -307,6 +312,15 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    {
+        const char* e = getenv("ORBX_SPLIT");
+        h->split = !(e && e[0] == '0');
+        for (int i = 0; i < 2; i++) {
+            ORBX_CUDA(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));
+            ORBX_CUDA(cudaEventCreateWithFlags(&h->join_event[i], cudaEventDisableTiming));
+        }
+        ORBX_CUDA(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+    }
     for (int l = 0; l < ORBX_LANES; l++) {
         ORBX_CUDA(cudaEventCreateWithFlags(&h->lanes[l].uploaded, cudaEventDisableTiming));
         ORBX_CUDA(cudaEventCreateWithFlags(&h->lanes[l].computed, cudaEventDisableTiming));
@@ -364,6 +378,11 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+    for (int i = 0; i < 2; i++) {
+        if (h->sub_stream[i]) { cudaStreamSynchronize(h->sub_stream[i]); cudaStreamDestroy(h->sub_stream[i]); }
+        if (h->join_event[i]) cudaEventDestroy(h->join_event[i]);
+    }
+    if (h->fork_event) cudaEventDestroy(h->fork_event);
     for (int l = 0; l < ORBX_LANES; l++) {
         if (h->lanes[l].uploaded) cudaEventDestroy(h->lanes[l].uploaded);
         if (h->lanes[l].computed) cudaEventDestroy(h->lanes[l].computed);
@@ -472,31 +491,54 @@ static int stage_mark(orbx_handle h)
     return ORBX_OK;
 }
 
-// frames [f0, f0 + nframes) of the handle's slots; d_out / d_desc / d_counts are the arrays of the WHOLE batch
-static int run_extract(orbx_handle h, int f0, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
+// frames [f0, f0 + nframes) of the handle's slots on stream s; d_out / d_desc / d_counts are the arrays of the WHOLE batch
+static int run_extract_on(orbx_handle h, int f0, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts,
+                          cudaStream_t s, bool mark)
 {
     uint8_t* slots = h->d_slots + (size_t)f0 * h->slot_stride;
     Cand* cand = h->d_cand + (size_t)f0 * h->cand_stride;
     Cand* surv = h->d_surv + (size_t)f0 * h->surv_stride;
     Sel* sel = h->d_sel + (size_t)f0 * h->sel_stride;
     FrameCounters* ctr = h->d_ctr + f0;
-    ORBX_CUDA(cudaMemsetAsync(ctr, 0, (size_t)nframes * sizeof(FrameCounters), h->stream));
-    int rc = stage_mark(h);
-    if (rc) return rc;
-    rc = build_pyramids(h, f0, nframes);
-    if (rc) return rc;
-    if ((rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_fast(h->g, slots, h->slot_stride, cand, h->cand_stride, ctr, nframes, h->stream));
-    if ((rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_select(h->g, cand, h->cand_stride, surv, h->surv_stride, ctr, nframes, h->stream));
-    if ((rc = stage_mark(h))) return rc;
+    int rc = ORBX_OK;
+    ORBX_CUDA(cudaMemsetAsync(ctr, 0, (size_t)nframes * sizeof(FrameCounters), s));
+    if (mark && (rc = stage_mark(h))) return rc;
+    for (int l = 1; l < h->g.nlevels; l++)
+        ORBX_CUDA(launch_pyr_down_level(slots, h->slot_stride, h->g.lv[l - 1], h->g.lv[l], h->pyr_sw[l], h->pyr_sh[l], nframes, s));
+    if (mark && (rc = stage_mark(h))) return rc;
+    ORBX_CUDA(launch_fast(h->g, slots, h->slot_stride, cand, h->cand_stride, ctr, nframes, s));
+    if (mark && (rc = stage_mark(h))) return rc;
+    ORBX_CUDA(launch_select(h->g, cand, h->cand_stride, surv, h->surv_stride, ctr, nframes, s));
+    if (mark && (rc = stage_mark(h))) return rc;
     ORBX_CUDA(launch_harris_select(h->g, slots, h->slot_stride, surv, h->surv_stride, sel, h->sel_stride, ctr, nframes,
-                                   h->max_surv_cap, h->harris_s4, h->stream));
-    if ((rc = stage_mark(h))) return rc;
+                                   h->max_surv_cap, h->harris_s4, s));
+    if (mark && (rc = stage_mark(h))) return rc;
     ORBX_CUDA(launch_orient_describe(h->g, slots, h->slot_stride, sel, h->sel_stride, ctr, d_out + (size_t)f0 * cap,
                                      (mode & ORBX_DO_DESC) ? d_desc + (size_t)f0 * cap * 32 : nullptr, cap, d_counts + f0, nframes,
-                                     mode, h->stream));
-    return stage_mark(h);
+                                     mode, s));
+    if (mark && (rc = stage_mark(h))) return rc;
+    return ORBX_OK;
+}
+
+// The stages of one frame depend on each other, the frames of a batch do not.  Large batches are therefore cut in two
+// halves that run on two internal streams (forked from / joined to the handle's stream with events): the short,
+// latency-bound launches of one half (small pyramid levels, score cut, Harris selection) and the tails of its big ones
+// overlap the bulk kernels of the other half.  Stage profiling keeps one stream so its per-stage events stay meaningful.
+static int run_extract(orbx_handle h, int f0, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
+{
+    if (h->profiling || !h->split || nframes < 2 * ORBX_SPLIT_MIN)
+        return run_extract_on(h, f0, nframes, mode, d_out, d_desc, cap, d_counts, h->stream, h->profiling);
+    ORBX_CUDA(cudaEventRecord(h->fork_event, h->stream));
+    const int half = (nframes + 1) / 2;
+    for (int i = 0; i < 2; i++) {
+        const int b = i * half, n = i == 0 ? half : nframes - half;
+        ORBX_CUDA(cudaStreamWaitEvent(h->sub_stream[i], h->fork_event, 0));
+        int rc = run_extract_on(h, f0 + b, n, mode, d_out, d_desc, cap, d_counts, h->sub_stream[i], false);
+        if (rc) return rc;
+        ORBX_CUDA(cudaEventRecord(h->join_event[i], h->sub_stream[i]));
+        ORBX_CUDA(cudaStreamWaitEvent(h->stream, h->join_event[i], 0));
+    }
+    return ORBX_OK;
 }
 
 extern "C" int orbx_set_profiling(orbx_handle h, int enabled)

@@ -29,7 +29,14 @@ namespace {
 
 constexpr int FT_TW = 124;
 constexpr int FT_TH = 30;
-constexpr int FT_THREADS = 256;
+#ifndef FT_THREADS_N
+#define FT_THREADS_N 128
+#endif
+#ifndef FT_MINB
+#define FT_MINB 8
+#endif
+constexpr int FT_THREADS = FT_THREADS_N;
+constexpr int FT_NW = FT_THREADS / 32;
 constexpr int FT_SP = 160;               // smem pitch (image and score share column coordinates): <= 15 + 4 + 124 + 4
 constexpr int FT_SH = FT_TH + 8;         // 38 image rows
 constexpr int FT_CH = FT_TH + 2;         // 32 score rows = 8 warps x 4
@@ -101,13 +108,15 @@ __device__ __forceinline__ uint32_t arc_strength2(const uint32_t (&r)[16], uint3
     return __vimax3_s16x2(bright, dark, K) - K;
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 5)
+__global__ void __launch_bounds__(FT_THREADS, FT_MINB)
 k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, size_t slot_stride, Cand* __restrict__ cand,
        size_t cand_stride, FrameCounters* __restrict__ ctr)
 {
     __shared__ __align__(16) uint16_t s_img[FT_SH * FT_SP];       // pixels widened to 16 bits
     __shared__ __align__(16) uint16_t s_score[FT_CH * FT_SP];     // m - thr for corners (1 .. 255 - thr), 0 otherwise
-    __shared__ Cand s_emit[FT_EMIT];
+    // the survivor list reuses the image tile: no thread reads s_img after the barrier that ends the scoring pass
+    static_assert(sizeof(Cand) * FT_EMIT <= sizeof(uint16_t) * FT_SH * FT_SP, "survivor list must fit in the image tile");
+    Cand* s_emit = reinterpret_cast<Cand*>(s_img);
     __shared__ int s_en, s_base;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -144,8 +153,8 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
     const int c = (ox - 3 - gx0) + 4 * lane;   // smem column of the group's first pixel (multiple of 4)
     const uint32_t K = (uint32_t)(thr + 256) * 0x00010001u;
 #pragma unroll 1
-    for (int it = 0; it < FT_CH / 8; it++) {
-        const int sr = wid + 8 * it;            // score row; its centre pixels sit in image smem row sr + 3
+    for (int it = 0; it < FT_CH / FT_NW; it++) {
+        const int sr = wid + FT_NW * it;            // score row; its centre pixels sit in image smem row sr + 3
         // pixel pairs of row dy: q[i] = pixels (c - 4 + 2i, c - 3 + 2i), i = 0..5, as s16x2 registers
         const uint2* base = reinterpret_cast<const uint2*>(s_img + (sr + 3) * FT_SP + c - 4);
         auto P = [&](int dy, int i) { return base[dy * (FT_SP / 4) + i]; };
@@ -195,8 +204,8 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
     // ---- 2: non-max suppression on the tile proper: same thread -> group mapping as above, score rows 1 .. 30
     const int cx0 = ox - gx0;                         // smem column of the tile's first pixel
 #pragma unroll 1
-    for (int it = 0; it < FT_CH / 8; it++) {
-        const int sr = wid + 8 * it;
+    for (int it = 0; it < FT_CH / FT_NW; it++) {
+        const int sr = wid + FT_NW * it;
         const int y = oy - 1 + sr;
         if (sr == 0 || sr == FT_CH - 1 || y >= h - 31) continue;
         const uint16_t* rowp = s_score + sr * FT_SP + c;

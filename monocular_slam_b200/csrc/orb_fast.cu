@@ -17,10 +17,13 @@
 //      m = max(max_k min9(ring) - c, c - min_k max9(ring)) exactly -- no corner pre-test, no divergence.  A warp
 //      covers one score row (32 groups of 4 pixels); 21 aligned 64-bit shared-memory loads and 18 byte-permutes feed
 //      4 pixels (ring columns at even offsets are register operands as loaded);
-//   2. NMS on the score tile, again four pixels per thread in packed u16x2 lanes: the 8-neighbour maximum is three
-//      3-input VIMNMX per pixel pair and "strictly greater" is one subtraction + sign test; survivors are staged in shared
-//      memory, the CTA reserves its range of the level's candidate list with ONE global atomic and writes
-//      (x, y, score); the per-level score histogram used by the retainBest cut (K3) gets one RED per survivor.
+//   2. NMS on the score tile, again four pixels per thread in packed u16x2 lanes: each warp walks its rows with a rolling
+//      3-row window of horizontal maxima, so the 8-neighbour maximum costs one 3-input VIMNMX per pixel pair, and
+//      "strictly greater" is one subtraction + bit test; survivors are compacted per row with two warp ballots (a lane
+//      keeps at most 2 of its 4 pixels) into a shared-memory list that reuses the image tile, the CTA reserves its range
+//      of the level's candidate list with ONE global atomic and writes (x, y, score); the per-level score histogram used
+//      by the retainBest cut (K3) gets one RED per survivor.
+// CTAs are 128 threads (4 warps x 8 rows): small barrier domains, 8 CTAs per SM.
 // Bound: integer ALU issue (VIMNMX/PRMT), not HBM: each level byte is read once from HBM and ~1.4x from L2.
 #include "common.cuh"
 
@@ -201,47 +204,67 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
     }
     __syncthreads();
 
-    // ---- 2: non-max suppression on the tile proper: same thread -> group mapping as above, score rows 1 .. 30
-    const int cx0 = ox - gx0;                         // smem column of the tile's first pixel
-#pragma unroll 1
-    for (int it = 0; it < FT_CH / FT_NW; it++) {
-        const int sr = wid + FT_NW * it;
-        const int y = oy - 1 + sr;
-        if (sr == 0 || sr == FT_CH - 1 || y >= h - 31) continue;
-        const uint16_t* rowp = s_score + sr * FT_SP + c;
-        const uint2 mid = *reinterpret_cast<const uint2*>(rowp);             // pairs A = (c, c+1), B = (c+2, c+3)
-        if ((mid.x | mid.y) == 0) continue;                                    // no corner among the four pixels
-        uint32_t nA, nB;                                                       // maximum over the 8 neighbours, per lane
-        {
-            const uint32_t l = *reinterpret_cast<const uint32_t*>(rowp - 2), r = *reinterpret_cast<const uint32_t*>(rowp + 4);
-            const uint32_t z = straddle(mid.x, mid.y);
-            nA = __vmaxu2(straddle(l, mid.x), z);
-            nB = __vmaxu2(z, straddle(mid.y, r));
-        }
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy += 2) {
-            const uint16_t* q = rowp + dy * FT_SP;
-            const uint2 m2 = *reinterpret_cast<const uint2*>(q);
-            const uint32_t l = *reinterpret_cast<const uint32_t*>(q - 2), r = *reinterpret_cast<const uint32_t*>(q + 4);
-            const uint32_t z = straddle(m2.x, m2.y);
-            nA = __vmaxu2(nA, __vmaxu2(__vmaxu2(straddle(l, m2.x), m2.x), z));
-            nB = __vmaxu2(nB, __vmaxu2(__vmaxu2(z, m2.y), straddle(m2.y, r)));
-        }
-        // strictly greater than every neighbour <=> score - nmax > 0 (lanes are in [0, 255], so plain 32-bit
-        // subtraction of (nmax) from (score + 256) cannot borrow across lanes)
-        const uint32_t fA = (mid.x | 0x01000100u) - nA, fB = (mid.y | 0x01000100u) - nB;
-        const uint32_t lanes[4] = { fA & 0xFFFFu, fA >> 16, fB & 0xFFFFu, fB >> 16 };
-        const uint32_t sc[4] = { mid.x & 0xFFFFu, mid.x >> 16, mid.y & 0xFFFFu, mid.y >> 16 };
+    // ---- 2: non-max suppression on the tile proper.  Warp w owns the output rows [RPW*w, RPW*(w+1)) of score rows 1 .. 30
+    // and walks them top to bottom with a rolling 3-row window of horizontal maxima, four pixels per lane in packed
+    // u16x2 lanes (same lane -> column mapping as above):  per row, hx = max(left, right) and h3 = max(hx, centre);
+    // the 8-neighbour maximum of row y is max3(hx[y], h3[y-1], h3[y+1]).
+    {
+        constexpr int RPW = FT_CH / FT_NW;
+        const int cx0 = ox - gx0;                     // smem column of the tile's first pixel
+        uint32_t colmask = 0;                          // which of this lane's four columns belong to the tile and the interior
 #pragma unroll
         for (int bq = 0; bq < 4; bq++) {
-            const int cc = c + bq, x = gx0 + cc;
-            if (lanes[bq] > 256u && cc >= cx0 && cc < cx0 + FT_TW && x < w - 31) {
-                int pos = atomicAdd(&s_en, 1);
-                Cand cnd;
-                cnd.xy = ((uint32_t)y << 16) | (uint32_t)x;
-                cnd.score = sc[bq] + (uint32_t)thr - 1u;   // FAST score = m - 1
-                s_emit[pos] = cnd;
+            const int cc = c + bq;
+            if (cc >= cx0 && cc < cx0 + FT_TW && gx0 + cc < w - 31) colmask |= 1u << bq;
+        }
+        struct Row { uint32_t mA, mB, hxA, hxB, h3A, h3B; };
+        auto load_row = [&](int sr) {
+            const uint16_t* rowp = s_score + sr * FT_SP + c;
+            const uint2 mid = *reinterpret_cast<const uint2*>(rowp);             // pairs A = (c, c+1), B = (c+2, c+3)
+            const uint32_t l = *reinterpret_cast<const uint32_t*>(rowp - 2), r = *reinterpret_cast<const uint32_t*>(rowp + 4);
+            const uint32_t z = straddle(mid.x, mid.y);
+            Row R;
+            R.mA = mid.x; R.mB = mid.y;
+            R.hxA = __vmaxu2(straddle(l, mid.x), z);
+            R.hxB = __vmaxu2(z, straddle(mid.y, r));
+            R.h3A = __vmaxu2(R.hxA, mid.x);
+            R.h3B = __vmaxu2(R.hxB, mid.y);
+            return R;
+        };
+        const int r_begin = max(RPW * wid, 1), r_end = min(RPW * wid + RPW, FT_CH - 1);
+        Row prev = load_row(r_begin - 1), cur = load_row(r_begin);
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 2
+        for (int sr = r_begin; sr < r_end; sr++) {
+            const Row next = load_row(sr + 1);
+            const int y = oy - 1 + sr;
+            const uint32_t nA = __vimax3_u16x2(cur.hxA, prev.h3A, next.h3A), nB = __vimax3_u16x2(cur.hxB, prev.h3B, next.h3B);
+            // strictly greater than all 8 neighbours  <=>  score - nmax >= 1  <=>  bit 8 of (score + 256 - nmax - 1);
+            // every lane stays in [0, 510], so the 32-bit subtractions never borrow across lanes
+            const uint32_t fA = (cur.mA | 0x01000100u) - nA - 0x00010001u, fB = (cur.mB | 0x01000100u) - nB - 0x00010001u;
+            uint32_t km = ((fA >> 8) & 1u) | ((fA >> 23) & 2u) | ((fB >> 6) & 4u) | ((fB >> 21) & 8u);
+            km = (y < h - 31) ? (km & colmask) : 0u;
+            // two horizontally adjacent pixels cannot both be strict maxima: a lane keeps at most 2 of its 4 pixels
+            const int n = __popc(km);
+            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, n >= 1);
+            if (b0) {                                  // uniform over the warp
+                const uint32_t b1 = __ballot_sync(0xFFFFFFFFu, n >= 2);
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_en, __popc(b0) + __popc(b1));
+                pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(b0 & lt) + __popc(b1 & lt);
+                uint32_t m = km;
+                while (m) {
+                    const int bq = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t pair = (bq & 2) ? cur.mB : cur.mA;
+                    Cand cnd;
+                    cnd.xy = ((uint32_t)y << 16) | (uint32_t)(gx0 + c + bq);
+                    cnd.score = ((pair >> (16 * (bq & 1))) & 0xFFFFu) + (uint32_t)thr - 1u;   // FAST score = m - 1
+                    s_emit[pos++] = cnd;
+                }
             }
+            prev = cur;
+            cur = next;
         }
     }
     __syncthreads();

@@ -15,6 +15,7 @@
 // lexicographically smallest (distance, trainIdx) pairs.  Packing key = distance << 23 | trainIdx makes that a
 // plain unsigned min: best1 = min(best1, max(best0, key)); best0 = min(best0, key).  Train sets larger than 2^23
 // rows are processed in chunks by the host and merged with the same rule on 64-bit keys.
+#include <stdlib.h>
 #include <algorithm>
 
 #include "common.cuh"
@@ -565,7 +566,9 @@ static int fill_absent(hamx_handle h, hamx_top2* d_out, int64_t nq)
 
 static void plan_split(int sm_count, int64_t nqb, int ntiles, int64_t npairs, int* nsplit_out, int* tps_out)
 {
-    const int64_t target = (int64_t)sm_count * 8;
+    static int mult = 0;
+    if (mult == 0) { const char* e = getenv("HAMX_SPLIT_MULT"); mult = e ? atoi(e) : 24; if (mult < 1) mult = 24; }
+    const int64_t target = (int64_t)sm_count * mult;
     int64_t nsplit = nqb * npairs >= target ? 1 : (target + nqb * npairs - 1) / (nqb * npairs);
     if (nsplit > ntiles) nsplit = ntiles;
     if (nsplit > 65535) nsplit = 65535;

@@ -20,7 +20,7 @@ namespace {
 
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_CHUNKS = 8;
-constexpr int HS_THREADS = 1024;
+constexpr int HS_THREADS = 512;
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select(const __grid_constant__ FrameGeom g, const Cand* __restrict__ cand, size_t cand_stride, Cand* __restrict__ surv,
@@ -97,23 +97,35 @@ __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img
     return __fmul_rn(__fsub_rn(det, __fmul_rn(__fmul_rn(0.04f, tr), tr)), s4);
 }
 
+// float -> unsigned key with the same order (zero canonicalised to +0)
+__device__ __forceinline__ uint32_t ordered_key(float f)
+{
+    uint32_t u = __float_as_uint(f == 0.f ? 0.f : f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
 __global__ void __launch_bounds__(HS_THREADS)
 k_harris_select(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, size_t slot_stride,
                 const Cand* __restrict__ surv, size_t surv_stride, Sel* __restrict__ sel, size_t sel_stride,
                 FrameCounters* __restrict__ ctr, int smem_cap, float s4)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    float* s_resp = reinterpret_cast<float*>(smem);                       // [smem_cap]
-    uint32_t* s_xy = reinterpret_cast<uint32_t*>(smem + 4 * (size_t)smem_cap);   // [smem_cap]
-    uint8_t* s_keep = smem + 8 * (size_t)smem_cap;                         // [smem_cap]
-    __shared__ int s_nsel;
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(smem);                              // [smem_cap] ordered response keys
+    uint32_t* s_xy = reinterpret_cast<uint32_t*>(smem + 4 * (size_t)smem_cap);        // [smem_cap]
+    uint16_t* s_kept = reinterpret_cast<uint16_t*>(smem + 8 * (size_t)smem_cap);      // [smem_cap] indices of the kept points
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    __shared__ int s_nkept;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g.lv[level];
     FrameCounters& C = ctr[frame];
     const int m = min(min(C.nsurv[level], L.surv_cap), smem_cap);
-    if (tid == 0) s_nsel = 0;
     if (m == 0) { if (tid == 0) C.nsel[level] = 0; return; }
 
     const uint8_t* img = slots + frame * slot_stride + L.img_off;
@@ -122,39 +134,78 @@ k_harris_select(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__
     for (int i = tid; i < m; i += HS_THREADS) {
         const Cand c = in[i];
         s_xy[i] = c.xy;
-        s_resp[i] = harris ? harris_response(img, L.pitch, (int)(c.xy & 0xFFFFu), (int)(c.xy >> 16), s4) : (float)c.score;
+        s_key[i] = ordered_key(harris ? harris_response(img, L.pitch, (int)(c.xy & 0xFFFFu), (int)(c.xy >> 16), s4) : (float)c.score);
     }
+    if (tid == 0) { s_prefix = 0; s_remaining = (uint32_t)L.quota; s_nkept = 0; }
     __syncthreads();
 
-    const int q = L.quota;
-    for (int i = tid; i < m; i += HS_THREADS) {
-        int keep = 1;
-        if (harris) {
-            const float r = s_resp[i];
-            int greater = 0;
-            for (int j = 0; j < m; j++) greater += (s_resp[j] > r);
-            keep = greater < q;
+    // ---- retainBest(q) on the response: T = key of the q-th largest, found by an 8-bit-per-pass radix select from the
+    // top byte down; every key >= T is kept, so ties at the cut survive like in OpenCV.  (FAST_SCORE: the integer cut of
+    // k_select already was the final one, everything is kept.)
+    uint32_t T = 0;
+    if (harris && L.quota == 0) T = 0xFFFFFFFFu;     // retainBest(0): nothing survives (no finite response maps to this key)
+    else if (harris && m > L.quota) {
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = tid; i < 256; i += HS_THREADS) s_hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix, himask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+            for (int i = tid; i < m; i += HS_THREADS) {
+                const uint32_t k = s_key[i];
+                if ((k & himask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {     // warp 0: the bin in which the count from the top reaches `remaining`
+                const uint32_t remaining = s_remaining;
+                uint32_t above = 0;         // keys of this pass's candidates in bins above the current group of 32
+                for (int base = 224; base >= 0; base -= 32) {
+                    const uint32_t cnt = s_hist[base + lane];
+                    uint32_t suf = cnt;     // inclusive suffix sum over lanes lane .. 31
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_down_sync(0xFFFFFFFFu, suf, o);
+                        if (lane + o < 32) suf += v;
+                    }
+                    const bool hit = above + suf >= remaining && above + suf - cnt < remaining;
+                    const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, hit);
+                    if (hitmask) {
+                        if (hit) {
+                            s_prefix = prefix | ((uint32_t)(base + lane) << shift);
+                            s_remaining = remaining - (above + suf - cnt);
+                        }
+                        break;
+                    }
+                    above += __shfl_sync(0xFFFFFFFFu, suf, 0);
+                }
+            }
+            __syncthreads();
         }
-        s_keep[i] = (uint8_t)keep;
+        T = s_prefix;
+    }
+
+    // ---- compact the kept points, then order them by (y, x) with a rank count among the kept
+    for (int i0 = 0; i0 < m; i0 += HS_THREADS) {
+        const int i = i0 + tid;
+        const bool keep = i < m && s_key[i] >= T;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_nkept, __popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (keep) s_kept[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
     }
     __syncthreads();
-
+    const int nk = s_nkept;
     Sel* out = sel + frame * sel_stride + L.sel_off;
-    int mine = 0;
-    for (int i = tid; i < m; i += HS_THREADS) {
-        if (!s_keep[i]) continue;
+    for (int a = tid; a < nk; a += HS_THREADS) {
+        const int i = s_kept[a];
         const uint32_t key = s_xy[i];
         int rank = 0;
-        for (int j = 0; j < m; j++) rank += (s_keep[j] && s_xy[j] < key);
+        for (int b = 0; b < nk; b++) rank += (s_xy[s_kept[b]] < key);
         Sel s;
         s.xy = key;
-        s.response = s_resp[i];
-        out[rank] = s;      // rank < #kept <= m <= surv_cap == capacity of the selected list
-        mine++;
+        s.response = key_value(s_key[i]);
+        out[rank] = s;      // rank < nk <= m <= surv_cap == capacity of the selected list
     }
-    if (mine) atomicAdd(&s_nsel, mine);
-    __syncthreads();
-    if (tid == 0) C.nsel[level] = s_nsel;
+    if (tid == 0) C.nsel[level] = nk;
 }
 
 }  // namespace
@@ -167,7 +218,7 @@ cudaError_t launch_select(const FrameGeom& g, const Cand* cand, size_t cand_stri
     return cudaGetLastError();
 }
 
-size_t harris_select_smem(int max_surv_cap) { return (size_t)max_surv_cap * 9 + 16; }
+size_t harris_select_smem(int max_surv_cap) { return (size_t)max_surv_cap * 10 + 16; }
 
 cudaError_t harris_select_prepare(int max_surv_cap)
 {

@@ -323,20 +323,21 @@ def run_ours(args, rank, world, local_rank):
     match_ms /= args.steps
 
     # ---- end to end through host buffers: pinned host frames in, keypoints / descriptors / matches back in pinned host
-    # memory.  (a) pipelined: orbx_submit_batch / orbx_wait_batch, two batches in flight, every step still uploads its own
+    # memory.  (a) pipelined: orbx_submit_batch / orbx_wait_batch, orbx_pipeline_depth() batches in flight, every step still uploads its own
     # frames and downloads its own results inside the timed region; (b) blocking: orbx_extract_batch + orbx_match_consecutive.
     def pinned_out():
         return (torch.empty((B, cap, 7), dtype=torch.float32).pin_memory().numpy().view(KEYPOINT_DTYPE).reshape(B, cap),
                 torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory().numpy(), np.zeros(B, np.int32),
                 torch.empty((B, cap, 4), dtype=torch.int32).pin_memory().numpy().view(DMATCH_DTYPE).reshape(B, cap),
                 np.zeros(B, np.int64))
-    outs = [pinned_out(), pinned_out()]
+    depth = orb.pipeline_depth()
+    outs = [pinned_out() for _ in range(depth)]
     pstate = {"k": 0, "last": None}
 
     def step_pipe():
-        if orb.batches_in_flight() == 2:
+        if orb.batches_in_flight() == depth:
             pstate["last"] = orb.wait_batch()
-        orb.submit_batch(frames_np, matcher, RATIO, outs[pstate["k"] & 1])
+        orb.submit_batch(frames_np, matcher, RATIO, outs[pstate["k"] % depth])
         pstate["k"] += 1
 
     def drain():
@@ -469,7 +470,7 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps,
-                        "timing": "host wall clock around orbx_submit_batch / orbx_wait_batch (two batches in flight, drained before the clock stops), max over ranks",
+                        "timing": "host wall clock around orbx_submit_batch / orbx_wait_batch (%d batches in flight, drained before the clock stops)" % depth + ", max over ranks",
                         "blocking_value": blk_value, "blocking_ms_per_step": blk_ms / args.steps,
                         "blocking_note": "orbx_extract_batch + orbx_match_consecutive, each call returns with its results in host memory"},
                 "gpu_launches": launches_per_step * args.steps,

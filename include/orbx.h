@@ -129,12 +129,12 @@ ORBX_API int orbx_check_dev(orbx_handle h);
 ORBX_API int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, orbx_dmatch* good, int64_t* ngood);
 ORBX_API int orbx_reset_sequence(orbx_handle h);
 
-/* Pipelined sequence mode on host buffers: up to two batches in flight.  orbx_submit_batch enqueues, without
+/* Pipelined sequence mode on host buffers: up to orbx_pipeline_depth() (3) batches in flight.  orbx_submit_batch enqueues, without
  * waiting, (1) the upload of the frames, (2) FeatureExtractor::process of every frame (src/FeatureExtractor.cpp:13-31)
  * and, when m != NULL, matchFeatures(frame f, frame f-1, ratio) (src/CameraPoseEstimator.cpp:200-213,409; frame 0 against
  * the last frame of the previous submission), (3) the copy of keypoints [nframes][cap], descriptors [nframes][cap][32]
  * and accepted matches [nframes][cap] back into the caller's buffers (pinned memory keeps the copies asynchronous).
- * The upload of batch k+1 and the download of batch k-1 overlap the kernels of batch k.  orbx_wait_batch blocks until
+ * The uploads of the next batches and the download of batch k-1 overlap the kernels of batch k.  orbx_wait_batch blocks until
  * the OLDEST submitted batch is complete, then fills its counts[] / ngood[] and reports overflows; the buffers passed
  * to orbx_submit_batch must stay valid until then.  cap <= orbx_max_keypoints().  Other entry points of the handle
  * must not be called while a batch is in flight (they return ORBX_E_INVALID). */
@@ -142,6 +142,7 @@ ORBX_API int orbx_submit_batch(orbx_handle h, hamx_handle m, const uint8_t* cons
                       float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts, orbx_dmatch* good, int64_t* ngood);
 ORBX_API int orbx_wait_batch(orbx_handle h);
 ORBX_API int orbx_batches_in_flight(orbx_handle h);
+ORBX_API int orbx_pipeline_depth(orbx_handle h);
 
 /* Per-stage device times (CUDA events on the handle's stream around each stage of every batch while enabled).
  * stage_ms receives ORBX_NSTAGES averages per batch: pyramid, FAST, FAST-score cut, Harris+selection, orient+describe. */

@@ -184,7 +184,7 @@ class ORB:
                                                 ngood.ctypes.data_as(C.POINTER(C.c_int64))))
         return good, ngood
 
-    # -- pipelined sequence mode: two batches in flight (upload / kernels / download overlap across batches)
+    # -- pipelined sequence mode: pipeline_depth() batches in flight (upload / kernels / download overlap across batches)
     def submit_batch(self, frames, matcher, ratio, out):
         """Enqueue extraction (+ consecutive-frame matching when ``matcher`` is given) of a batch and return at once.
         ``out`` = (kps[n, cap], desc[n, cap, 32], counts[n] int32, good[n, cap], ngood[n] int64): caller-owned buffers
@@ -213,6 +213,10 @@ class ORB:
         done = self._inflight.pop(0)[1] if getattr(self, "_inflight", None) else None
         check(status)
         return done
+
+    def pipeline_depth(self):
+        """How many submitted batches may be in flight before wait_batch() has to be called."""
+        return _lib.lib().orbx_pipeline_depth(self._h)
 
     def batches_in_flight(self):
         return _lib.lib().orbx_batches_in_flight(self._h)

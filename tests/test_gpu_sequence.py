@@ -140,7 +140,9 @@ def test_pipelined_submit_wait():
                 torch.zeros((n, cap, 4), dtype=torch.int32).pin_memory().numpy().view(DMATCH_DTYPE).reshape(n, cap),
                 np.zeros(n, np.int64))
 
-    chunks = [(0, 3), (3, 6), (6, 8)]
+    depth = orb.pipeline_depth()
+    assert depth >= 2
+    chunks = [(0, 2), (2, 4), (4, 5), (5, 7), (7, 8)]
     pinned = torch.from_numpy(seq).pin_memory().numpy()
     outs = []
 
@@ -157,11 +159,13 @@ def test_pipelined_submit_wait():
 
     pending = []
     for lo, hi in chunks:
-        if orb.batches_in_flight() == 2:
+        if orb.batches_in_flight() == depth:
             collect(*pending.pop(0))
         orb.submit_batch(list(pinned[lo:hi]), m, 0.8, buffers(hi - lo))
         pending.append((lo, hi))
-    assert orb.batches_in_flight() == 2
+    assert orb.batches_in_flight() == depth
+    with pytest.raises(Exception):              # the pipeline is full
+        orb.submit_batch(list(pinned[0:1]), m, 0.8, buffers(1))
     # the blocking entry points refuse to run while batches are in flight
     with pytest.raises(Exception):
         orb.extract_batch(list(seq[:1]), cap=cap)

@@ -19,29 +19,30 @@ namespace orbx {
 namespace {
 
 constexpr int PD_TW = 128;
-constexpr int PD_TH = 32;
+constexpr int PD_TH = 64;
 constexpr int PD_THREADS = 256;
-constexpr int PD_MAXVEC = 16;            // threads per destination row in the vertical pass (11 vectors at scale 1.2)
 
 __device__ __forceinline__ uint32_t lanes_lo(uint32_t g) { return __byte_perm(g, 0u, 0x4140); }
 __device__ __forceinline__ uint32_t lanes_hi(uint32_t g) { return __byte_perm(g, 0u, 0x4342); }
 
+// PITCH: row pitch of the intermediate in u16 entries, a compile-time constant so that the horizontal pass addresses its
+// rows with immediate offsets (192 covers scale factors up to ~1.37, 320 up to 2).
+template <int PITCH>
 __global__ void __launch_bounds__(PD_THREADS)
 k_pyr_down(uint8_t* __restrict__ slots, size_t slot_stride, size_t src_off, int spitch, int sw, int sh, size_t dst_off,
            int dpitch, int dw, int dh, const int* __restrict__ ofs_x, const uint16_t* __restrict__ c1x,
-           const int* __restrict__ ofs_y, const uint16_t* __restrict__ c1y, int s_w)
+           const int* __restrict__ ofs_y, const uint16_t* __restrict__ c1y)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t* s_v = reinterpret_cast<uint16_t*>(smem);             // [PD_TH][s_w] (+ 8 entries of slack)
+    __shared__ __align__(16) uint16_t s_v[PD_TH * PITCH];
 
     const uint8_t* src = slots + blockIdx.z * slot_stride + src_off;
     uint8_t* dst = slots + blockIdx.z * slot_stride + dst_off;
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * PD_TW, y0 = blockIdx.y * PD_TH;
-    const int x1 = min(x0 + PD_TW, dw);
+    const int x1 = min(x0 + PD_TW, dw), rows = min(PD_TH, dh - y0);
     const int c0 = __ldg(ofs_x + x0) & ~15;                        // first staged source column (16-byte aligned)
     const int c1 = min(__ldg(ofs_x + x1 - 1) + 1, sw - 1);         // last source column any tap reads
-    const int nvec = (c1 - c0) / 16 + 1;
+    const int nvec = (c1 - c0) / 16 + 1;                           // <= PITCH / 16 (checked by the launcher)
 
     // this thread's 4 destination columns (horizontal pass); loaded early so the latency overlaps the vertical pass
     const int tx = tid & 31, ty = tid >> 5;
@@ -55,26 +56,25 @@ k_pyr_down(uint8_t* __restrict__ slots, size_t slot_stride, size_t src_off, int 
         wx1[j] = __ldg(c1x + xi);
     }
 
-    // ---- vertical pass: V[y][c] = w0y * S[oy][c] + w1y * S[oy+1][c]; 16 threads per destination row, 16 pixels each
+    // ---- vertical pass: V[y][c] = w0y * S[oy][c] + w1y * S[oy+1][c]; one item = 16 source pixels of one destination row
     {
-#pragma unroll
-        for (int pass = 0; pass < PD_TH / (PD_THREADS / PD_MAXVEC); pass++) {
-            const int yy = (tid >> 4) + pass * (PD_THREADS / PD_MAXVEC);
-            if (y0 + yy < dh)
-            for (int v = tid & (PD_MAXVEC - 1); v < nvec; v += PD_MAXVEC) {
-                const int oy = __ldg(ofs_y + y0 + yy);
-                const uint32_t w1 = __ldg(c1y + y0 + yy), w0 = 256u - w1;
-                const uint4 a = *reinterpret_cast<const uint4*>(src + (size_t)oy * spitch + c0 + v * 16);
-                const uint4 b = *reinterpret_cast<const uint4*>(src + (size_t)min(oy + 1, sh - 1) * spitch + c0 + v * 16);
-                uint4 lo, hi;
-                lo.x = lanes_lo(a.x) * w0 + lanes_lo(b.x) * w1; lo.y = lanes_hi(a.x) * w0 + lanes_hi(b.x) * w1;
-                lo.z = lanes_lo(a.y) * w0 + lanes_lo(b.y) * w1; lo.w = lanes_hi(a.y) * w0 + lanes_hi(b.y) * w1;
-                hi.x = lanes_lo(a.z) * w0 + lanes_lo(b.z) * w1; hi.y = lanes_hi(a.z) * w0 + lanes_hi(b.z) * w1;
-                hi.z = lanes_lo(a.w) * w0 + lanes_lo(b.w) * w1; hi.w = lanes_hi(a.w) * w0 + lanes_hi(b.w) * w1;
-                uint4* out = reinterpret_cast<uint4*>(s_v + yy * s_w + v * 16);
-                out[0] = lo;
-                out[1] = hi;
-            }
+        const uint32_t rcp = (65536u + nvec - 1) / nvec;           // item / nvec == (item * rcp) >> 16 for item < 64 * 36
+        const int nitems = rows * nvec;
+#pragma unroll 3
+        for (int item = tid; item < nitems; item += PD_THREADS) {
+            const int yy = (int)(((uint32_t)item * rcp) >> 16), v = item - yy * nvec;
+            const int oy = __ldg(ofs_y + y0 + yy);
+            const uint32_t w1 = __ldg(c1y + y0 + yy), w0 = 256u - w1;
+            const uint4 a = *reinterpret_cast<const uint4*>(src + (size_t)oy * spitch + c0 + v * 16);
+            const uint4 b = *reinterpret_cast<const uint4*>(src + (size_t)min(oy + 1, sh - 1) * spitch + c0 + v * 16);
+            uint4 lo, hi;
+            lo.x = lanes_lo(a.x) * w0 + lanes_lo(b.x) * w1; lo.y = lanes_hi(a.x) * w0 + lanes_hi(b.x) * w1;
+            lo.z = lanes_lo(a.y) * w0 + lanes_lo(b.y) * w1; lo.w = lanes_hi(a.y) * w0 + lanes_hi(b.y) * w1;
+            hi.x = lanes_lo(a.z) * w0 + lanes_lo(b.z) * w1; hi.y = lanes_hi(a.z) * w0 + lanes_hi(b.z) * w1;
+            hi.z = lanes_lo(a.w) * w0 + lanes_lo(b.w) * w1; hi.w = lanes_hi(a.w) * w0 + lanes_hi(b.w) * w1;
+            uint4* out = reinterpret_cast<uint4*>(s_v + yy * PITCH + v * 16);
+            out[0] = lo;
+            out[1] = hi;
         }
     }
     __syncthreads();
@@ -82,20 +82,23 @@ k_pyr_down(uint8_t* __restrict__ slots, size_t slot_stride, size_t src_off, int 
     // ---- horizontal pass: 4 adjacent destination pixels per thread, rows ty, ty + 8, ...
     if (x < dw) {
         const uint32_t wa0 = 256u - wx1[0], wa1 = 256u - wx1[1], wa2 = 256u - wx1[2], wa3 = 256u - wx1[3];
+        const uint16_t* p0 = s_v + ty * PITCH + o[0];
+        const uint16_t* p1 = s_v + ty * PITCH + o[1];
+        const uint16_t* p2 = s_v + ty * PITCH + o[2];
+        const uint16_t* p3 = s_v + ty * PITCH + o[3];
+        uint8_t* drow = dst + (size_t)(y0 + ty) * dpitch + x;
 #pragma unroll
         for (int k = 0; k < PD_TH / 8; k++) {
-            const int yy = ty + 8 * k;
-            if (y0 + yy < dh) {
-                const uint16_t* row = s_v + yy * s_w;
+            if (ty + 8 * k < rows) {
                 // the second tap of a clamped column has weight 0 (it may read one entry of slack)
-                const uint32_t t0 = (uint32_t)row[o[0]] * wa0 + ((uint32_t)row[o[0] + 1] * wx1[0] + 32768u);
-                const uint32_t t1 = (uint32_t)row[o[1]] * wa1 + ((uint32_t)row[o[1] + 1] * wx1[1] + 32768u);
-                const uint32_t t2 = (uint32_t)row[o[2]] * wa2 + ((uint32_t)row[o[2] + 1] * wx1[2] + 32768u);
-                const uint32_t t3 = (uint32_t)row[o[3]] * wa3 + ((uint32_t)row[o[3] + 1] * wx1[3] + 32768u);
+                const uint32_t t0 = (uint32_t)p0[8 * k * PITCH] * wa0 + ((uint32_t)p0[8 * k * PITCH + 1] * wx1[0] + 32768u);
+                const uint32_t t1 = (uint32_t)p1[8 * k * PITCH] * wa1 + ((uint32_t)p1[8 * k * PITCH + 1] * wx1[1] + 32768u);
+                const uint32_t t2 = (uint32_t)p2[8 * k * PITCH] * wa2 + ((uint32_t)p2[8 * k * PITCH + 1] * wx1[2] + 32768u);
+                const uint32_t t3 = (uint32_t)p3[8 * k * PITCH] * wa3 + ((uint32_t)p3[8 * k * PITCH + 1] * wx1[3] + 32768u);
                 // result byte = bits 16..23 of each sum
                 const uint32_t p01 = __byte_perm(t0, t1, 0x0062), p23 = __byte_perm(t2, t3, 0x0062);
                 // the row pitch is a multiple of 128, so the 4-byte store stays inside the row even past dw
-                *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + yy) * dpitch + x) = __byte_perm(p01, p23, 0x5410);
+                *reinterpret_cast<uint32_t*>(drow + (size_t)(8 * k) * dpitch) = __byte_perm(p01, p23, 0x5410);
             }
         }
     }
@@ -200,13 +203,14 @@ cudaError_t launch_pyr_down_level(uint8_t* slots, size_t slot_stride, const Leve
 {
     (void)s_h;
     dim3 grid(div_up(dst.w, PD_TW), div_up(dst.h, PD_TH), nframes);
-    size_t smem = ((size_t)PD_TH * s_w + 8) * sizeof(uint16_t);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_pyr_down, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    k_pyr_down<<<grid, PD_THREADS, smem, s>>>(slots, slot_stride, src.img_off, src.pitch, src.w, src.h, dst.img_off, dst.pitch,
-                                               dst.w, dst.h, dst.ofs_x, dst.c1x, dst.ofs_y, dst.c1y, s_w);
+    if (s_w + 8 <= 192)
+        k_pyr_down<192><<<grid, PD_THREADS, 0, s>>>(slots, slot_stride, src.img_off, src.pitch, src.w, src.h, dst.img_off, dst.pitch, dst.w,
+                                                     dst.h, dst.ofs_x, dst.c1x, dst.ofs_y, dst.c1y);
+    else if (s_w + 8 <= 320)
+        k_pyr_down<320><<<grid, PD_THREADS, 0, s>>>(slots, slot_stride, src.img_off, src.pitch, src.w, src.h, dst.img_off, dst.pitch, dst.w,
+                                                     dst.h, dst.ofs_x, dst.c1x, dst.ofs_y, dst.c1y);
+    else
+        return cudaErrorInvalidValue;     // scale factors above 2 are rejected by orbx_create
     return cudaGetLastError();
 }
 

@@ -189,7 +189,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "synthetic 1920x1080 monocular sequence, 2000 kp/frame, consecutive-frame matching (BASELINE.json configs[1]), CPU",
+            "config": {"workload": "synthetic %dx%d monocular sequence, %d kp/frame, consecutive-frame matching (BASELINE.json configs[%d]), CPU"
+                                   % (W, H, NFEAT, 1 if (W, H, NFEAT) == (1920, 1080, 2000) else 2),
                        "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "ratio": RATIO, "frames_per_step": frames // args.steps},
             "cpu_baseline": d,
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -461,7 +462,8 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": "synthetic 1920x1080 monocular sequence, 2000 kp/frame, consecutive-frame matching, ratio 0.75 (BASELINE.json configs[1])",
+                "config": {"workload": "synthetic %dx%d monocular sequence, %d kp/frame, consecutive-frame matching, ratio 0.75 (BASELINE.json configs[%d])"
+                                       % (W, H, NFEAT, 1 if (W, H, NFEAT) == (1920, 1080, 2000) else 2),
                            "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "nlevels": 8, "scale_factor": 1.2, "score_type": "HARRIS",
                            "batch_frames_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                            "l2": "inputs larger than L2: %d frames x %.1f MB = %.0f MB of frames (+%.0f MB of pyramid levels) per step vs 126 MB L2"
@@ -515,7 +517,12 @@ def main():
     ap.add_argument("--ham-nt", type=int, default=125000, help="train rows per GPU")
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--frame", default="1920x1080", help="frame size WxH (default: BASELINE.json configs[1]; 3840x2160 with --nfeatures 8000 is configs[2])")
+    ap.add_argument("--nfeatures", type=int, default=2000)
     args = ap.parse_args()
+    global W, H, NFEAT
+    W, H = (int(v) for v in args.frame.lower().split("x"))
+    NFEAT = args.nfeatures
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -457,7 +457,11 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
     clocks = sampler.summary()
-    launches_per_step = (len(ws) - 1) + 4 + 3    # 7 pyramid levels, FAST, select, Harris+select, orient+describe, pair table, kNN2, ratio
+    # kernels of liborbx.so per timed step: ingest; per half of the batch (the library cuts batches of >= 16 frames in two
+    # halves on two streams unless ORBX_SPLIT=0): 7 pyramid levels, FAST, score cut, Harris selection, orient+describe;
+    # then pair table, kNN2, ratio test
+    halves = 2 if (B >= 16 and os.environ.get("ORBX_SPLIT", "1")[:1] != "0") else 1
+    launches_per_step = 1 + halves * ((len(ws) - 1) + 4) + 3
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",

@@ -381,17 +381,28 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = hbm_peak()
     fast_ms = stages["fast"]
     achieved = level_px * B / (fast_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, issue = None, None
     tp = os.path.join(ROOT, "profiles", "fast_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and (W, H, NFEAT, B) == (1920, 1080, 2000, 64):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            prof = json.load(open(tp))
+            traffic = prof.get("dram_bytes_per_launch")
+            winst = prof.get("warp_instructions_per_launch")
+            if winst:
+                # what actually bounds k_fast: warp instructions per launch (ncu smsp__inst_executed.sum of the same launch,
+                # profiles/) over the live launch time, against 4 schedulers x 1 warp instruction per clock per SM
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+                issue = {"warp_instructions_per_launch": winst, "achieved_gwinst_s": winst / (stages["fast"] * 1e-3) / 1e9,
+                         "peak_gwinst_s": sms * 4 * clk / 1e9, "frac": winst / (stages["fast"] * 1e-3) / (sms * 4 * clk)}
         except Exception:
-            traffic = None
+            traffic, issue = None, None
     roofline = {"kernel": "k_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "launch_ms": fast_ms,
                 "algorithmic_bytes_per_launch": level_px * B,
-                "note": "FAST reads each pyramid-level byte once (3.096 x W x H per frame); it is integer-issue bound, not HBM bound"}
+                "issue": issue,
+                "note": "FAST reads each pyramid-level byte once (3.096 x W x H per frame); it is bound by instruction issue "
+                        "(about 80 instructions per pixel on the integer pipes), not by HBM: see roofline.issue"}
 
     # ---- secondary metric: train-sharded Hamming kNN2, Gcmp/s over all ranks
     hamming = None

@@ -71,6 +71,7 @@ with open(os.path.join(P, "%s_kernels.txt" % tag), "w") as f:
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
             fast = {"kernel": "k_fast", "frames_per_launch": 64, "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                     "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+                    "warp_instructions_per_launch": float(r[H.index("smsp__inst_executed.sum")].replace(",", "")),
                     "source": "profiles/%s_kernels.txt (ncu --set full, gpurun_out/step_%s.ncu-rep)" % (tag, tag)}
 if fast:
     json.dump(fast, open(os.path.join(P, "fast_traffic.json"), "w"), indent=1)

@@ -9,9 +9,9 @@
 // VERTICAL pass first because it vectorises: a thread takes 16 source pixels of the two source rows of a destination
 // row straight from global memory (two 16-byte loads), widens them to 16x2 lanes and forms
 // V = w0y * a + w1y * b with two 32-bit IMADs per lane pair (each lane stays <= 65280, so lanes never carry into each
-// other), and stores V as u16 in shared memory.  The horizontal pass then produces 4 adjacent destination pixels per
-// thread: two u16 loads and two IMADs per pixel, the result byte is byte 2 of the sum, and three PRMTs pack the
-// 32-bit store.  About 10 instructions per destination pixel; HBM/L2-bound (reads the source once from HBM, ~1.6x
+// other), and stores V as u16 in shared memory.  The horizontal pass then produces 2 adjacent destination pixels per
+// thread: two u16 loads and two IMADs per pixel, the result byte is byte 2 of the sum, and one PRMT packs the
+// 16-bit store.  About 10 instructions per destination pixel; HBM/L2-bound (reads the source once from HBM, ~1.6x
 // from L1/L2; writes each destination byte once).
 #include "common.cuh"
 
@@ -44,61 +44,82 @@ k_pyr_down(uint8_t* __restrict__ slots, size_t slot_stride, size_t src_off, int 
     const int c1 = min(__ldg(ofs_x + x1 - 1) + 1, sw - 1);         // last source column any tap reads
     const int nvec = (c1 - c0) / 16 + 1;                           // <= PITCH / 16 (checked by the launcher)
 
-    // this thread's 4 destination columns (horizontal pass); loaded early so the latency overlaps the vertical pass
-    const int tx = tid & 31, ty = tid >> 5;
-    const int x = x0 + 4 * tx;
-    int o[4];
-    uint32_t wx1[4];
+    // this thread's 2 destination columns (horizontal pass); loaded early so the latency overlaps the vertical pass.
+    // Two pixels per lane keep a warp's u16 gathers within ~40 shared-memory words (1-2 wavefronts per load); with four
+    // per lane they spread over ~80 words and the kernel was bound by L1 wavefronts.
+    const int tx = tid & 63, ty = tid >> 6;
+    const int x = x0 + 2 * tx;
+    int o[2];
+    uint32_t wx1[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 2; j++) {
         const int xi = min(x + j, dw - 1);
         o[j] = __ldg(ofs_x + xi) - c0;
         wx1[j] = __ldg(c1x + xi);
     }
 
-    // ---- vertical pass: V[y][c] = w0y * S[oy][c] + w1y * S[oy+1][c]; one item = 16 source pixels of one destination row
+    // ---- vertical pass: V[y][c] = w0y * S[oy][c] + w1y * S[oy+1][c]; one item = 16 source pixels of one destination row.
+    // A thread owns up to ITEMS items; their table lookups, then all their 16-byte pixel loads, are issued back to back
+    // before anything is consumed (item after item would serialise two dependent global-load latencies per item).
     {
+        constexpr int ITEMS = (PD_TH * (PITCH / 16) + PD_THREADS - 1) / PD_THREADS;
         const uint32_t rcp = (65536u + nvec - 1) / nvec;           // item / nvec == (item * rcp) >> 16 for item < 64 * 36
         const int nitems = rows * nvec;
-#pragma unroll 3
-        for (int item = tid; item < nitems; item += PD_THREADS) {
-            const int yy = (int)(((uint32_t)item * rcp) >> 16), v = item - yy * nvec;
+        int sidx[ITEMS];                                           // smem index of the item's first entry, -1: no item
+        uint32_t w1[ITEMS];
+        const uint8_t* pa[ITEMS];
+        const uint8_t* pb[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const int item = tid + i * PD_THREADS;
+            const bool ok = item < nitems;
+            const int yy = ok ? (int)(((uint32_t)item * rcp) >> 16) : 0, v = ok ? item - yy * nvec : 0;
             const int oy = __ldg(ofs_y + y0 + yy);
-            const uint32_t w1 = __ldg(c1y + y0 + yy), w0 = 256u - w1;
-            const uint4 a = *reinterpret_cast<const uint4*>(src + (size_t)oy * spitch + c0 + v * 16);
-            const uint4 b = *reinterpret_cast<const uint4*>(src + (size_t)min(oy + 1, sh - 1) * spitch + c0 + v * 16);
-            uint4 lo, hi;
-            lo.x = lanes_lo(a.x) * w0 + lanes_lo(b.x) * w1; lo.y = lanes_hi(a.x) * w0 + lanes_hi(b.x) * w1;
-            lo.z = lanes_lo(a.y) * w0 + lanes_lo(b.y) * w1; lo.w = lanes_hi(a.y) * w0 + lanes_hi(b.y) * w1;
-            hi.x = lanes_lo(a.z) * w0 + lanes_lo(b.z) * w1; hi.y = lanes_hi(a.z) * w0 + lanes_hi(b.z) * w1;
-            hi.z = lanes_lo(a.w) * w0 + lanes_lo(b.w) * w1; hi.w = lanes_hi(a.w) * w0 + lanes_hi(b.w) * w1;
-            uint4* out = reinterpret_cast<uint4*>(s_v + yy * PITCH + v * 16);
-            out[0] = lo;
-            out[1] = hi;
+            w1[i] = __ldg(c1y + y0 + yy);
+            pa[i] = src + (size_t)oy * spitch + c0 + v * 16;
+            pb[i] = src + (size_t)min(oy + 1, sh - 1) * spitch + c0 + v * 16;
+            sidx[i] = ok ? yy * PITCH + v * 16 : -1;
+        }
+        uint4 a[ITEMS], b[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            if (sidx[i] >= 0) {
+                a[i] = *reinterpret_cast<const uint4*>(pa[i]);
+                b[i] = *reinterpret_cast<const uint4*>(pb[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            if (sidx[i] >= 0) {
+                const uint32_t w0 = 256u - w1[i], ww = w1[i];
+                uint4 lo, hi;
+                lo.x = lanes_lo(a[i].x) * w0 + lanes_lo(b[i].x) * ww; lo.y = lanes_hi(a[i].x) * w0 + lanes_hi(b[i].x) * ww;
+                lo.z = lanes_lo(a[i].y) * w0 + lanes_lo(b[i].y) * ww; lo.w = lanes_hi(a[i].y) * w0 + lanes_hi(b[i].y) * ww;
+                hi.x = lanes_lo(a[i].z) * w0 + lanes_lo(b[i].z) * ww; hi.y = lanes_hi(a[i].z) * w0 + lanes_hi(b[i].z) * ww;
+                hi.z = lanes_lo(a[i].w) * w0 + lanes_lo(b[i].w) * ww; hi.w = lanes_hi(a[i].w) * w0 + lanes_hi(b[i].w) * ww;
+                uint4* out = reinterpret_cast<uint4*>(s_v + sidx[i]);
+                out[0] = lo;
+                out[1] = hi;
+            }
         }
     }
     __syncthreads();
 
-    // ---- horizontal pass: 4 adjacent destination pixels per thread, rows ty, ty + 8, ...
+    // ---- horizontal pass: 2 adjacent destination pixels per thread, rows ty, ty + 4, ...
     if (x < dw) {
-        const uint32_t wa0 = 256u - wx1[0], wa1 = 256u - wx1[1], wa2 = 256u - wx1[2], wa3 = 256u - wx1[3];
+        const uint32_t wa0 = 256u - wx1[0], wa1 = 256u - wx1[1];
         const uint16_t* p0 = s_v + ty * PITCH + o[0];
         const uint16_t* p1 = s_v + ty * PITCH + o[1];
-        const uint16_t* p2 = s_v + ty * PITCH + o[2];
-        const uint16_t* p3 = s_v + ty * PITCH + o[3];
         uint8_t* drow = dst + (size_t)(y0 + ty) * dpitch + x;
 #pragma unroll
-        for (int k = 0; k < PD_TH / 8; k++) {
-            if (ty + 8 * k < rows) {
+        for (int k = 0; k < PD_TH / 4; k++) {
+            if (ty + 4 * k < rows) {
                 // the second tap of a clamped column has weight 0 (it may read one entry of slack)
-                const uint32_t t0 = (uint32_t)p0[8 * k * PITCH] * wa0 + ((uint32_t)p0[8 * k * PITCH + 1] * wx1[0] + 32768u);
-                const uint32_t t1 = (uint32_t)p1[8 * k * PITCH] * wa1 + ((uint32_t)p1[8 * k * PITCH + 1] * wx1[1] + 32768u);
-                const uint32_t t2 = (uint32_t)p2[8 * k * PITCH] * wa2 + ((uint32_t)p2[8 * k * PITCH + 1] * wx1[2] + 32768u);
-                const uint32_t t3 = (uint32_t)p3[8 * k * PITCH] * wa3 + ((uint32_t)p3[8 * k * PITCH + 1] * wx1[3] + 32768u);
-                // result byte = bits 16..23 of each sum
-                const uint32_t p01 = __byte_perm(t0, t1, 0x0062), p23 = __byte_perm(t2, t3, 0x0062);
-                // the row pitch is a multiple of 128, so the 4-byte store stays inside the row even past dw
-                *reinterpret_cast<uint32_t*>(drow + (size_t)(8 * k) * dpitch) = __byte_perm(p01, p23, 0x5410);
+                const uint32_t t0 = (uint32_t)p0[4 * k * PITCH] * wa0 + ((uint32_t)p0[4 * k * PITCH + 1] * wx1[0] + 32768u);
+                const uint32_t t1 = (uint32_t)p1[4 * k * PITCH] * wa1 + ((uint32_t)p1[4 * k * PITCH + 1] * wx1[1] + 32768u);
+                // result byte = bits 16..23 of each sum; the row pitch is a multiple of 128, so the 2-byte store stays inside
+                // the row even past dw
+                *reinterpret_cast<uint16_t*>(drow + (size_t)(4 * k) * dpitch) = (uint16_t)__byte_perm(t0, t1, 0x0062);
             }
         }
     }

@@ -177,7 +177,7 @@ __device__ __forceinline__ float orient_describe_warp(WarpPatch& S, const char4*
             acc = __fmaf_rn(k1, __fadd_rn(f[j + 5], f[j + 1]), acc);
             acc = __fmaf_rn(k0, __fadd_rn(f[j + 6], f[j]), acc);
             int v = __float2int_rn(acc);
-            v = min(max(v, 0), 255);
+            // no clamp: the kernel's weights sum to 1 within 1e-6, so 0 <= acc <= 255.0003 and v is already a valid u8
             const int r = r0 + j;
             if (!interior) {
                 const int gy = yi - OD_BR + r, gx = xi - OD_BR + c;

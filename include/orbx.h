@@ -191,6 +191,22 @@ ORBX_API int hamx_match_consecutive_dev(hamx_handle h, const uint8_t* d_desc, co
                                const uint8_t* d_prev_desc, const int32_t* d_prev_count, float ratio,
                                orbx_dmatch* d_good, int64_t* d_ngood);
 
+/* Steady-state pattern of CameraPoseEstimator::pnpPoseEstimation (src/CameraPoseEstimator.cpp:388,405-409): every frame
+ * is matched, as the query set, against each of its `back` (numBackTraverse = 5) predecessors.  Pair (f, j), j = 1..back,
+ * is matchFeatures(desc[f], desc[f-j], ratio); its accepted matches go to d_good[(f*back + j-1) * cap ..] and their number
+ * to d_ngood[f*back + j-1].  Predecessors before the batch come from the history [nhist][cap][32] (entry 0 = the frame
+ * just before the batch); pairs without a predecessor yield 0 matches.  hamx_update_history_dev writes the history that
+ * follows the batch (the `back` most recent frames, most recent first) into a second buffer. */
+ORBX_API int hamx_match_back_dev(hamx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int back,
+                        const uint8_t* d_hist_desc, const int32_t* d_hist_counts, int nhist, float ratio,
+                        orbx_dmatch* d_good, int64_t* d_ngood);
+ORBX_API int hamx_update_history_dev(hamx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int back,
+                            const uint8_t* d_old_desc, const int32_t* d_old_counts, int nold, uint8_t* d_new_desc, int32_t* d_new_counts);
+/* Host-buffer form for the batch last extracted with orbx_extract_batch: good is [nframes][back][cap] with the cap of
+ * that extract call, ngood [nframes][back]; the handle keeps the history across batches (orbx_reset_sequence forgets it).
+ * back <= 8. */
+ORBX_API int orbx_match_back(orbx_handle h, hamx_handle m, int back, float ratio, orbx_dmatch* good, int64_t* ngood);
+
 /* Train-sharded matching over peer memory (BASELINE configs 4 and 5; one process per GPU of one NVLink box).  The
  * reference has no counterpart (it is single-device); the result is bit-identical to hamx_knn2_dev over the union of
  * the shards.  Setup, once: every rank calls hamx_p2p_export (allocates its gather buffer and returns a 64-byte

@@ -446,6 +446,49 @@ __global__ void k_build_consecutive_pairs(const uint8_t* desc, const int32_t* co
     pairs[f] = p;
 }
 
+// Pair table for the steady-state pattern of CameraPoseEstimator::pnpPoseEstimation (src/CameraPoseEstimator.cpp:405-409):
+// frame f (query) against each of its `back` predecessors f-1 .. f-back (train).  Predecessors before the start of the
+// batch come from the history (hist[0] = most recent frame before the batch); pair index = f * back + (j - 1).
+__global__ void k_build_back_pairs(const uint8_t* desc, const int32_t* counts, int nframes, int cap, int back, const uint8_t* hist_desc,
+                                   const int32_t* hist_counts, int nhist, hamx_pair* pairs)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nframes * back) return;
+    const int f = idx / back, j = idx - f * back + 1;
+    hamx_pair p;
+    p.q = desc + (size_t)f * cap * 32;
+    p.nq = min(counts[f], cap);
+    const int src = f - j;
+    if (src >= 0) {
+        p.t = desc + (size_t)src * cap * 32;
+        p.nt = min(counts[src], cap);
+    } else if (-src - 1 < nhist) {
+        p.t = hist_desc + (size_t)(-src - 1) * cap * 32;
+        p.nt = min(hist_counts[-src - 1], cap);
+    } else {
+        p.t = desc;
+        p.nt = 0;
+        p.nq = 0;   // fewer than j frames exist before frame f
+    }
+    pairs[idx] = p;
+}
+
+// history' = the `back` most recent frames after the batch, most recent first (from the batch, then from the old history)
+__global__ void k_update_history(const uint8_t* desc, const int32_t* counts, int nframes, int cap, const uint8_t* old_desc,
+                                 const int32_t* old_counts, int nold, uint8_t* new_desc, int32_t* new_counts)
+{
+    const int hi = blockIdx.x;
+    const int src = nframes - 1 - hi;
+    const uint8_t* from = nullptr;
+    int n = 0;
+    if (src >= 0) { from = desc + (size_t)src * cap * 32; n = min(counts[src], cap); }
+    else if (-src - 1 < nold) { from = old_desc + (size_t)(-src - 1) * cap * 32; n = min(old_counts[-src - 1], cap); }
+    if (threadIdx.x == 0) new_counts[hi] = n;
+    const uint4* a = reinterpret_cast<const uint4*>(from);
+    uint4* b = reinterpret_cast<uint4*>(new_desc + (size_t)hi * cap * 32);
+    for (int i = threadIdx.x; i < n * 2; i += blockDim.x) b[i] = a[i];
+}
+
 // Register-only POPC throughput probe: 8 independent POPC + 8 XOR per iteration and thread, like the matcher's inner
 // loop without its memory traffic.
 __global__ void __launch_bounds__(1024) k_popc_peak(uint32_t* sink, int iters, uint32_t seed)
@@ -656,6 +699,37 @@ extern "C" int hamx_match_consecutive_dev(hamx_handle h, const uint8_t* d_desc, 
                                                                             h->d_pairs);
     ORBX_CUDA(cudaGetLastError());
     return hamx_match_pairs_dev(h, h->d_pairs, nframes, cap, cap, ratio, d_good, (size_t)cap, d_ngood);
+}
+
+extern "C" int hamx_match_back_dev(hamx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int back,
+                                   const uint8_t* d_hist_desc, const int32_t* d_hist_counts, int nhist, float ratio, orbx_dmatch* d_good,
+                                   int64_t* d_ngood)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_match_back_dev: NULL handle");
+    ORBX_REQUIRE(nframes >= 0 && cap >= 1 && back >= 1 && back <= 64 && nhist >= 0, "hamx_match_back_dev: bad sizes");
+    if (nframes == 0) return ORBX_OK;
+    ORBX_REQUIRE(d_desc && d_counts && d_good && d_ngood && (nhist == 0 || (d_hist_desc && d_hist_counts)), "hamx_match_back_dev: NULL pointer");
+    if ((((uintptr_t)d_desc) | ((uintptr_t)d_hist_desc)) & 15) { set_error("hamx_match_back_dev: descriptor pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int npairs = nframes * back;
+    int rc = grow(&h->d_pairs, &h->pairs_bytes, (size_t)npairs * sizeof(hamx_pair));
+    if (rc) return rc;
+    k_build_back_pairs<<<(npairs + 127) / 128, 128, 0, h->stream>>>(d_desc, d_counts, nframes, cap, back, d_hist_desc, d_hist_counts, nhist, h->d_pairs);
+    ORBX_CUDA(cudaGetLastError());
+    return hamx_match_pairs_dev(h, h->d_pairs, npairs, cap, cap, ratio, d_good, (size_t)cap, d_ngood);
+}
+
+extern "C" int hamx_update_history_dev(hamx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int back,
+                                       const uint8_t* d_old_desc, const int32_t* d_old_counts, int nold, uint8_t* d_new_desc,
+                                       int32_t* d_new_counts)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_update_history_dev: NULL handle");
+    ORBX_REQUIRE(nframes >= 0 && cap >= 1 && back >= 1 && nold >= 0 && d_new_desc && d_new_counts, "hamx_update_history_dev: bad arguments");
+    ORBX_REQUIRE(d_new_desc != d_old_desc, "hamx_update_history_dev: the new history must not alias the old one");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    k_update_history<<<back, 256, 0, h->stream>>>(d_desc, d_counts, nframes, cap, d_old_desc, d_old_counts, nold, d_new_desc, d_new_counts);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
 }
 
 extern "C" int hamx_knn2_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,

@@ -47,6 +47,7 @@ struct orbx_lane {
     int64_t* ngood;
 };
 constexpr int ORBX_LANES = 3;
+constexpr int ORBX_MAX_BACK = 8;
 constexpr int ORBX_SPLIT_MIN = 8;       // a batch is split in two when each half has at least this many frames
 
 struct orbx_context {
@@ -88,6 +89,13 @@ struct orbx_context {
     orbx_dmatch* d_good;
     int64_t* d_ngood;
     int64_t* h_ngood;
+    // orbx_match_back: history of the last ORBX_MAX_BACK frames (double-buffered), allocated on first use
+    uint8_t* d_hist[2];
+    int32_t* d_hist_counts[2];
+    int hist_cur, nhist, hist_cap;
+    orbx_dmatch* d_good_back;
+    int64_t* d_ngood_back;
+    int64_t* h_ngood_back;
     // two-way split of large batches (run_extract)
     bool split;
     cudaStream_t sub_stream[2];
@@ -371,6 +379,9 @@ extern "C" int orbx_destroy(orbx_handle h)
     cudaFree(h->d_slots); cudaFree(h->d_cand); cudaFree(h->d_surv); cudaFree(h->d_sel); cudaFree(h->d_ctr);
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_tab);
     cudaFree(h->d_prev_desc); cudaFree(h->d_prev_count); cudaFree(h->d_good); cudaFree(h->d_ngood); cudaFree(h->d_bgr);
+    cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]); cudaFree(h->d_hist_counts[0]); cudaFree(h->d_hist_counts[1]);
+    cudaFree(h->d_good_back); cudaFree(h->d_ngood_back);
+    if (h->h_ngood_back) cudaFreeHost(h->h_ngood_back);
     if (h->h_ngood) cudaFreeHost(h->h_ngood);
     if (h->events) { for (cudaEvent_t e : *h->events) cudaEventDestroy(e); delete h->events; }
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -768,6 +779,7 @@ extern "C" int orbx_reset_sequence(orbx_handle h)
 {
     ORBX_REQUIRE(h != nullptr, "orbx_reset_sequence: NULL handle");
     h->have_prev = false;
+    h->nhist = 0;
     return ORBX_OK;
 }
 
@@ -793,6 +805,46 @@ extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio,
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     h->have_prev = true;
     for (int f = 0; f < n; f++) ngood[f] = h->h_ngood[f];
+    return ORBX_OK;
+}
+
+extern "C" int orbx_match_back(orbx_handle h, hamx_handle m, int back, float ratio, orbx_dmatch* good, int64_t* ngood)
+{
+    ORBX_REQUIRE(h != nullptr && m != nullptr, "orbx_match_back: NULL handle");
+    ORBX_REQUIRE(good && ngood, "orbx_match_back: NULL pointer");
+    ORBX_REQUIRE(back >= 1 && back <= ORBX_MAX_BACK, "orbx_match_back: back %d outside [1, %d]", back, ORBX_MAX_BACK);
+    ORBX_REQUIRE(h->last_nframes >= 1, "orbx_match_back: no batch with descriptors has been extracted on this handle");
+    { int rc_ = require_idle(h, "orbx_match_back"); if (rc_) return rc_; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int n = h->last_nframes, cap = h->last_cap;
+    if (!h->d_hist[0]) {
+        for (int i = 0; i < 2; i++) {
+            ORBX_CUDA(cudaMalloc((void**)&h->d_hist[i], (size_t)ORBX_MAX_BACK * h->dev_cap * 32 + 256));
+            ORBX_CUDA(cudaMalloc((void**)&h->d_hist_counts[i], 256));
+        }
+        ORBX_CUDA(cudaMalloc((void**)&h->d_good_back, (size_t)h->max_batch * ORBX_MAX_BACK * h->dev_cap * sizeof(orbx_dmatch) + 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_ngood_back, (size_t)h->max_batch * ORBX_MAX_BACK * sizeof(int64_t) + 256));
+        ORBX_CUDA(cudaMallocHost((void**)&h->h_ngood_back, (size_t)h->max_batch * ORBX_MAX_BACK * sizeof(int64_t)));
+        h->nhist = 0;
+        h->hist_cap = 0;
+    }
+    if (h->nhist && h->hist_cap != cap) h->nhist = 0;      // a history laid out for another capacity cannot be indexed
+    int rc = hamx_set_stream(m, (void*)h->stream);
+    if (rc) return rc;
+    const int cur = h->hist_cur;
+    rc = hamx_match_back_dev(m, h->d_desc, h->d_counts, n, cap, back, h->d_hist[cur], h->d_hist_counts[cur], std::min(h->nhist, back), ratio,
+                             h->d_good_back, h->d_ngood_back);
+    if (!rc) rc = hamx_update_history_dev(m, h->d_desc, h->d_counts, n, cap, ORBX_MAX_BACK, h->d_hist[cur], h->d_hist_counts[cur], h->nhist,
+                                          h->d_hist[cur ^ 1], h->d_hist_counts[cur ^ 1]);
+    hamx_set_stream(m, nullptr);
+    if (rc) return rc;
+    h->hist_cur = cur ^ 1;
+    h->nhist = std::min(ORBX_MAX_BACK, h->nhist + n);
+    h->hist_cap = cap;
+    ORBX_CUDA(cudaMemcpyAsync(h->h_ngood_back, h->d_ngood_back, (size_t)n * back * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(good, h->d_good_back, (size_t)n * back * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n * back; i++) ngood[i] = h->h_ngood_back[i];
     return ORBX_OK;
 }
 

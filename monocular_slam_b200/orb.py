@@ -221,6 +221,16 @@ class ORB:
     def batches_in_flight(self):
         return _lib.lib().orbx_batches_in_flight(self._h)
 
+    def match_back(self, matcher, back, ratio, cap, nframes):
+        """matchFeatures(desc[f], desc[f-j], ratio) for j = 1..back and every frame f of the last extract_batch -- the
+        steady-state loop of CameraPoseEstimator::pnpPoseEstimation (numBackTraverse = 5, src/CameraPoseEstimator.cpp:405-409);
+        frames before the batch come from the handle's history.  Returns (good[nframes, back, cap], ngood[nframes, back])."""
+        good = np.zeros((nframes, back, cap), DMATCH_DTYPE)
+        ngood = np.zeros((nframes, back), np.int64)
+        check(_lib.lib().orbx_match_back(self._h, matcher._h, int(back), float(ratio), good.ctypes.data,
+                                         ngood.ctypes.data_as(C.POINTER(C.c_int64))))
+        return good, ngood
+
     def reset_sequence(self):
         check(_lib.lib().orbx_reset_sequence(self._h))
 

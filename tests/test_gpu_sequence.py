@@ -179,3 +179,37 @@ def test_pipelined_submit_wait():
     assert_keypoints_equal(kps[0, :counts[0]], ext[0][0], "blocking after pipelined")
     m.close()
     orb.close()
+
+
+def test_match_back_traverse():
+    """orbx_match_back: every frame against its `back` predecessors (the reference's numBackTraverse loop,
+    src/CameraPoseEstimator.cpp:405-409), across batch borders (history kept by the handle), back larger than a batch."""
+    seq = syn.sequence(9, 640, 480, seed=24)
+    nf, ratio, back = 600, 0.8, 3
+    P = oracle.Params(nfeatures=nf)
+    ext = [oracle.detect_and_compute(f, P) for f in seq]
+    orb = ORB(nfeatures=nf, max_size=(640, 480), max_batch=4)
+    m = BFMatcher()
+    cap = orb.default_cap
+    done = 0
+    for chunk in (list(seq[:4]), list(seq[4:6]), list(seq[6:])):
+        n = len(chunk)
+        kps, desc, counts = orb.extract_batch(chunk, cap=cap)
+        good, ngood = orb.match_back(m, back, ratio, cap, n)
+        for i in range(n):
+            f = done + i
+            assert_descriptors_equal(desc[i, :counts[i]], ext[f][1], "frame %d" % f)
+            for j in range(1, back + 1):
+                if f - j < 0:
+                    assert ngood[i, j - 1] == 0, "frame %d has no predecessor %d" % (f, j)
+                else:
+                    _check_matches(good[i, j - 1], int(ngood[i, j - 1]), oracle.match_features(ext[f][1], ext[f - j][1], ratio))
+        done += n
+    # a new sequence forgets the history
+    orb.reset_sequence()
+    kps, desc, counts = orb.extract_batch(list(seq[:2]), cap=cap)
+    good, ngood = orb.match_back(m, 5, ratio, cap, 2)
+    assert ngood[0].sum() == 0 and ngood[1, 1:].sum() == 0
+    _check_matches(good[1, 0], int(ngood[1, 0]), oracle.match_features(ext[1][1], ext[0][1], ratio))
+    m.close()
+    orb.close()

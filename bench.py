@@ -215,6 +215,10 @@ def run_ours(args, rank, world, local_rank):
     from monocular_slam_b200 import synthetic as syn
     from monocular_slam_b200.sharded import ShardedMatcher, shard_bounds
 
+    from monocular_slam_b200.sharded import bind_to_gpu_numa
+    numa_cpus = None
+    if world > 1 and os.environ.get("ORBX_NUMA_BIND", "1")[:1] != "0":
+        numa_cpus = bind_to_gpu_numa(local_rank)     # before any pinned allocation: host frames live next to their GPU
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -481,6 +485,7 @@ def run_ours(args, rank, world, local_rank):
                                        % (W, H, NFEAT, 1 if (W, H, NFEAT) == (1920, 1080, 2000) else 2),
                            "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "nlevels": 8, "scale_factor": 1.2, "score_type": "HARRIS",
                            "batch_frames_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+                           "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None),
                            "l2": "inputs larger than L2: %d frames x %.1f MB = %.0f MB of frames (+%.0f MB of pyramid levels) per step vs 126 MB L2"
                                  % (B, W * H / 1e6, B * W * H / 1e6, B * (level_px - W * H) / 1e6),
                            "keypoints_per_frame": float(counts.mean()), "matches_per_frame": float(ngood_dev[1:].mean())},

@@ -15,6 +15,28 @@
 import numpy as np
 
 
+def bind_to_gpu_numa(device):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (NVML's ideal affinity), so that the pinned
+    frame buffers it allocates afterwards are first-touched on that node and the H2D copies do not cross sockets.  With
+    one process per GPU on a two-socket box this is what lets the end-to-end path scale.  Returns the CPU list, or None
+    when NVML or the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def shard_bounds(n, world):
     """Contiguous, near-equal ranges: rank r owns [bounds[r], bounds[r+1])."""
     base, extra = divmod(int(n), int(world))

@@ -30,6 +30,10 @@ __device__ __align__(16) const int8_t d_pattern[256 * 4] = {
 namespace {
 
 constexpr int OD_WARPS = 4;
+#ifndef OD_KPW_N
+#define OD_KPW_N 4
+#endif
+constexpr int OD_KPW = OD_KPW_N;         // keypoints per warp in the detect path
 constexpr int OD_THREADS = OD_WARPS * 32;
 constexpr int OD_R = 21;                 // raw patch radius
 constexpr int OD_P = 2 * OD_R + 1;       // 43
@@ -234,12 +238,32 @@ k_orient_describe(const __grid_constant__ FrameGeom g, const uint8_t* __restrict
         if (total > cap) atomicOr(&C.overflow, 4);
     }
     const int limit = min(total, cap);
-    for (int kidx = blockIdx.x * OD_WARPS + wid; kidx < limit; kidx += gridDim.x * OD_WARPS) {
-        int off = 0, level = 0, rank = 0;
+    auto locate = [&](int kidx, int& level, int& rank) {
+        int off = 0;
+        level = 0; rank = 0;
         for (int l = 0; l < g.nlevels; l++) {
             const int n = C.nsel[l];
             if (kidx >= off && kidx < off + n) { level = l; rank = kidx - off; }
             off += n;
+        }
+    };
+    for (int kidx = blockIdx.x * OD_WARPS + wid; kidx < limit; kidx += gridDim.x * OD_WARPS) {
+        int level, rank;
+        locate(kidx, level, rank);
+        {   // pull the NEXT keypoint's patch rows towards L2 while this one is processed (its 43 x 64-byte window)
+            const int knext = kidx + gridDim.x * OD_WARPS;
+            if (knext < limit) {
+                int nl, nr;
+                locate(knext, nl, nr);
+                const LevelGeom& NL = g.lv[nl];
+                const uint32_t nxy = sel[frame * sel_stride + NL.sel_off + nr].xy;
+                const int nx0 = (int)(nxy & 0xFFFFu) - OD_R, ny0 = (int)(nxy >> 16) - OD_R;
+                const uint8_t* base = slots + frame * slot_stride + NL.img_off + (size_t)max(ny0, 0) * NL.pitch + (max(nx0, 0) & ~15);
+                for (int r = lane; r < OD_P && ny0 + r < NL.h; r += 32) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)r * NL.pitch));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)r * NL.pitch + 63));
+                }
+            }
         }
         const LevelGeom& L = g.lv[level];
         const Sel s = sel[frame * sel_stride + L.sel_off + rank];
@@ -284,7 +308,8 @@ cudaError_t launch_orient_describe(const FrameGeom& g, const uint8_t* slots, siz
                                    size_t sel_stride, FrameCounters* ctr, orbx_keypoint* out, uint8_t* desc, int cap,
                                    int32_t* counts, int nframes, int mode, cudaStream_t s)
 {
-    int blocks = (cap + OD_WARPS - 1) / OD_WARPS;
+    // a warp handles OD_KPW keypoints in turn (the next one's patch is prefetched while the current one is processed)
+    int blocks = (cap + OD_WARPS * OD_KPW - 1) / (OD_WARPS * OD_KPW);
     if (blocks > 2048) blocks = 2048;
     dim3 grid(blocks, nframes);
     k_orient_describe<<<grid, OD_THREADS, 0, s>>>(g, slots, slot_stride, sel, sel_stride, ctr, out, desc, cap, counts, mode);

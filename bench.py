@@ -61,7 +61,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self.nv is not None:

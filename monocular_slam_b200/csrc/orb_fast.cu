@@ -158,6 +158,7 @@ k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ slots, s
 #pragma unroll 1
     for (int it = 0; it < FT_CH / FT_NW; it++) {
         const int sr = wid + FT_NW * it;            // score row; its centre pixels sit in image smem row sr + 3
+        if (oy - 1 + sr > h - 31) continue;         // below the last row NMS can look at (bottom tiles of a level); warp-uniform
         // pixel pairs of row dy: q[i] = pixels (c - 4 + 2i, c - 3 + 2i), i = 0..5, as s16x2 registers
         const uint2* base = reinterpret_cast<const uint2*>(s_img + (sr + 3) * FT_SP + c - 4);
         auto P = [&](int dy, int i) { return base[dy * (FT_SP / 4) + i]; };

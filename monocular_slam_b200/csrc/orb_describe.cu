@@ -43,9 +43,11 @@ constexpr int OD_B = 2 * OD_BR + 1;      // 37
 constexpr int OD_BP = 40;                // blurred patch pitch
 constexpr int OD_RUN = 19;               // outputs per lane and run in the blur passes (two overlapping runs cover 37)
 
-struct WarpPatch {
+constexpr int OD_BRP = 38;               // pitch of the row-pass result in floats (even: column pairs are read as float2)
+
+struct __align__(16) WarpPatch {
+    float row[OD_P * OD_BRP];            // first: 8-byte aligned for the float2 accesses
     uint8_t raw[OD_P * OD_RP];
-    float row[OD_P * OD_B];
     uint8_t val[OD_B * OD_BP];
 };
 
@@ -114,15 +116,20 @@ __device__ __forceinline__ float orient_describe_warp(WarpPatch& S, const char4*
         int m10 = 0, m01 = 0;
         const int u = lane - 15;
         if (lane < 31) {
+            // the disc is symmetric under transposition (|u| <= umax[|v|]  <=>  |v| <= umax[|u|]), so column u owns the rows
+            // |v| <= vm: one table lookup per lane, and m10 = u * sum(val) needs no multiply inside the loop
             const uint8_t* col = S.raw + OD_R * OD_RP + a + OD_R + u;
+            const int vm = c_umax[u < 0 ? -u : u];
+            int sum = col[0];
 #pragma unroll
-            for (int v = -15; v <= 15; v++) {
-                if (abs(u) <= c_umax[v < 0 ? -v : v]) {
-                    const int val = col[v * OD_RP];
-                    m10 += u * val;
-                    m01 += v * val;
+            for (int v = 1; v <= 15; v++) {
+                if (v <= vm) {
+                    const int lo = col[-v * OD_RP], hi = col[v * OD_RP];
+                    sum += lo + hi;
+                    m01 += v * (hi - lo);
                 }
             }
+            m10 = u * sum;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -145,14 +152,66 @@ __device__ __forceinline__ float orient_describe_warp(WarpPatch& S, const char4*
 
     // cv::getGaussianKernel(7, 2, CV_32F)
     const float k0 = 0x1.1f5f62p-4f, k1 = 0x1.0c70fcp-3f, k2 = 0x1.869472p-3f, k3 = 0x1.ba95c0p-3f;
-    // ---- blur, row pass: 43 rows x 37 columns as 86 runs of 19 outputs (columns 0..18 and 18..36)
+    if (interior) {
+        // ---- blur on packed fp32x2 (FFMA2: one instruction, two IEEE-exact FMAs).  Row pass: lane p < 22 filters rows 2p and
+        // 2p+1 together, streaming a 7-tap window along the 43 columns; column pass: lane q < 19 filters columns 2q and 2q+1
+        // together down the 43 rows.  Same operation order per element as the scalar path below (and as OpenCV).
+        const float2 K0 = make_float2(k0, k0), K1 = make_float2(k1, k1), K2 = make_float2(k2, k2), K3 = make_float2(k3, k3);
+        if (lane < (OD_P + 1) / 2) {
+            const int r0 = 2 * lane, r1 = min(r0 + 1, OD_P - 1);
+            const uint8_t* s0 = S.raw + r0 * OD_RP + a;
+            const uint8_t* s1 = S.raw + r1 * OD_RP + a;
+            float* o0 = S.row + r0 * OD_BRP;
+            float* o1 = S.row + r1 * OD_BRP;
+            float2 w[7];            // sliding window over the columns (the unrolled loop renames instead of moving)
+#pragma unroll
+            for (int i = 0; i < 6; i++) w[i] = make_float2((float)s0[i], (float)s1[i]);
+#pragma unroll
+            for (int j = 0; j < OD_B; j++) {
+                w[(j + 6) % 7] = make_float2((float)s0[j + 6], (float)s1[j + 6]);
+                float2 acc = __fmul2_rn(K0, w[j % 7]);
+                acc = __ffma2_rn(K1, w[(j + 1) % 7], acc);
+                acc = __ffma2_rn(K2, w[(j + 2) % 7], acc);
+                acc = __ffma2_rn(K3, w[(j + 3) % 7], acc);
+                acc = __ffma2_rn(K2, w[(j + 4) % 7], acc);
+                acc = __ffma2_rn(K1, w[(j + 5) % 7], acc);
+                acc = __ffma2_rn(K0, w[(j + 6) % 7], acc);
+                o0[j] = acc.x;
+                o1[j] = acc.y;      // lane 21: r1 == r0, the same value to the same address
+            }
+        }
+        __syncwarp();
+        if (lane < (OD_B + 1) / 2) {
+            const float2* p = reinterpret_cast<const float2*>(S.row) + lane;      // columns 2q, 2q+1; row stride OD_BRP / 2
+            // round half to even by adding 1.5 * 2^23: the low byte of the sum's bit pattern is the integer (0 <= acc <= 255.0003)
+            const float2 MAGIC = make_float2(12582912.f, 12582912.f);
+            float2 w[7];
+#pragma unroll
+            for (int i = 0; i < 6; i++) w[i] = p[i * (OD_BRP / 2)];
+#pragma unroll
+            for (int j = 0; j < OD_B; j++) {
+                w[(j + 6) % 7] = p[(j + 6) * (OD_BRP / 2)];
+                float2 acc = __fmul2_rn(K3, w[(j + 3) % 7]);
+                acc = __ffma2_rn(K2, __fadd2_rn(w[(j + 4) % 7], w[(j + 2) % 7]), acc);
+                acc = __ffma2_rn(K1, __fadd2_rn(w[(j + 5) % 7], w[(j + 1) % 7]), acc);
+                acc = __ffma2_rn(K0, __fadd2_rn(w[(j + 6) % 7], w[j % 7]), acc);
+                const float2 t = __fadd2_rn(acc, MAGIC);
+                // column 37 (lane 18's second one) does not exist: its byte lands in the padding of the row (pitch 40)
+                *reinterpret_cast<uint16_t*>(S.val + j * OD_BP + 2 * lane) =
+                    (uint16_t)__byte_perm(__float_as_uint(t.x), __float_as_uint(t.y), 0x0040);
+            }
+        }
+        __syncwarp();
+    } else {
+    // ---- scalar path for patches that leave the level (caller-provided keypoints near the border only)
+    // row pass: 43 rows x 37 columns as 86 runs of 19 outputs (columns 0..18 and 18..36)
     for (int id = lane; id < OD_P * 2; id += 32) {
         const int r = id >> 1, c0 = (id & 1) * (OD_B - OD_RUN);
         const uint8_t* s = S.raw + r * OD_RP + a + c0;      // taps c .. c+6 == patch columns (c+3) +- 3
         float f[OD_RUN + 6];
 #pragma unroll
         for (int j = 0; j < OD_RUN + 6; j++) f[j] = (float)s[j];
-        float* o = S.row + r * OD_B + c0;
+        float* o = S.row + r * OD_BRP + c0;
 #pragma unroll
         for (int j = 0; j < OD_RUN; j++) {
             float acc = __fmul_rn(k0, f[j]);
@@ -166,14 +225,14 @@ __device__ __forceinline__ float orient_describe_warp(WarpPatch& S, const char4*
         }
     }
     __syncwarp();
-    // ---- column pass, symmetric form: 37 columns x 2 runs of 19 rows; positions outside the level keep the raw pixel
+    // column pass, symmetric form: 37 columns x 2 runs of 19 rows; positions outside the level keep the raw pixel
     for (int id = lane; id < OD_B * 2; id += 32) {
         const int half = id >= OD_B ? 1 : 0;
         const int c = id - half * OD_B, r0 = half * (OD_B - OD_RUN);
-        const float* p = S.row + r0 * OD_B + c;
+        const float* p = S.row + r0 * OD_BRP + c;
         float f[OD_RUN + 6];
 #pragma unroll
-        for (int j = 0; j < OD_RUN + 6; j++) f[j] = p[j * OD_B];
+        for (int j = 0; j < OD_RUN + 6; j++) f[j] = p[j * OD_BRP];
 #pragma unroll
         for (int j = 0; j < OD_RUN; j++) {
             float acc = __fmul_rn(k3, f[j + 3]);
@@ -183,14 +242,13 @@ __device__ __forceinline__ float orient_describe_warp(WarpPatch& S, const char4*
             int v = __float2int_rn(acc);
             // no clamp: the kernel's weights sum to 1 within 1e-6, so 0 <= acc <= 255.0003 and v is already a valid u8
             const int r = r0 + j;
-            if (!interior) {
-                const int gy = yi - OD_BR + r, gx = xi - OD_BR + c;
-                if (gx < 0 || gx >= w || gy < 0 || gy >= h) v = S.raw[(r + 3) * OD_RP + a + c + 3];
-            }
+            const int gy = yi - OD_BR + r, gx = xi - OD_BR + c;
+            if (gx < 0 || gx >= w || gy < 0 || gy >= h) v = S.raw[(r + 3) * OD_RP + a + c + 3];
             S.val[r * OD_BP + c] = (uint8_t)v;
         }
     }
     __syncwarp();
+    }
 
     // ---- rBRIEF: lane l evaluates tests l, l + 32, ...; word j of the descriptor is the ballot of round j
     uint32_t mine = 0;

@@ -4,15 +4,20 @@
 // reference src/FeatureExtractor.cpp:17,19 (OpenCV orb.cpp ICAngles / computeOrbDescriptors, core fastAtan2,
 // imgproc 7x7 sigma-2 blur).
 //
-// A warp stages the 43x43 level patch around its keypoint in shared memory (the rotated pattern reaches 18 pixels, the
-// blur 3 more) with aligned 16-byte loads (4 per patch row), then, with only __syncwarp between the steps,
-//   K4: integer moments m10 = sum u I, m01 = sum v I over the radius-15 disc (umax table; lane = column u),
-//       shuffle-reduced exactly; angle = fastAtan2(m01, m10): OpenCV's 7th-order polynomial in degrees, every
-//       multiply and add rounded separately (no FMA contraction) so the float result is bit-identical to the CPU.
+// A warp handles its keypoints in turn.  The 43x43 level patch around a keypoint (the rotated pattern reaches 18
+// pixels, the blur 3 more) is fetched with aligned 16-byte loads (4 per patch row) INTO REGISTERS one keypoint ahead, so
+// the global-load latency is hidden behind the previous keypoint's arithmetic, then stored to shared memory.  With only
+// __syncwarp between the steps:
+//   K4: integer moments m10 = sum u I, m01 = sum v I over the radius-15 disc (lane = column u; the disc is symmetric
+//       under transposition, so column u owns rows |v| <= umax[|u|]), shuffle-reduced exactly; angle = fastAtan2(m01,
+//       m10): OpenCV's 7th-order polynomial in degrees, every multiply and add rounded separately (no FMA contraction)
+//       so the float result is bit-identical to the CPU.
 //   K5: the 37x37 neighbourhood is blurred on the fly instead of blurring whole levels.  Row pass
 //       r = k0*S0; r = fma(kj, Sj, r) (left to right), column pass c = k3*R0; c = fma(k3+j, R+j + R-j, c),
-//       round-half-even to u8 -- the exact operation order of the CPU path; each lane produces a run of 19 outputs
-//       from 25 inputs held in registers.  Lane l then evaluates BRIEF tests l, l+32, ...: both pattern points are
+//       round-half-even to u8 -- the exact operation order of the CPU path.  Both passes run on packed fp32x2
+//       (FFMA2 / FADD2: one instruction, two IEEE-exact operations): a lane filters two rows (resp. two columns) at
+//       once with a sliding 7-tap window; the rounding is the add of 1.5 * 2^23 whose low result byte is the integer.
+//       Lane l then evaluates BRIEF tests l, l+32, ...: both pattern points are
 //       rotated in float32 (x = px*a - py*b, unfused), rounded half-even, looked up in the blurred patch, compared,
 //       and a warp ballot assembles 32 tests into one little-endian word of the descriptor.
 // OpenCV blurs only the level image itself, not the reflected border it keeps around it; sample positions that fall
@@ -31,7 +36,7 @@ namespace {
 
 constexpr int OD_WARPS = 4;
 #ifndef OD_KPW_N
-#define OD_KPW_N 4
+#define OD_KPW_N 8
 #endif
 constexpr int OD_KPW = OD_KPW_N;         // keypoints per warp in the detect path
 constexpr int OD_THREADS = OD_WARPS * 32;
@@ -84,17 +89,55 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+// The 43 x 64-byte window of an interior patch as 16-byte vectors held in registers (<= 6 per lane): issued for the
+// NEXT keypoint before the current one is processed, stored to shared memory when its turn comes, so the global-load
+// latency of the patch (the dominant stall of this kernel) is off the critical path.
+constexpr int OD_VEC = OD_P * 4;                       // 172 vectors
+constexpr int OD_VPL = (OD_VEC + 31) / 32;             // 6 per lane
+struct PatchRegs { uint4 q[OD_VPL]; };
+
+__device__ __forceinline__ bool patch_interior(int xi, int yi, int w, int h)
+{
+    return xi - OD_R >= 0 && yi - OD_R >= 0 && xi + OD_R < w && yi + OD_R < h;
+}
+__device__ __forceinline__ void patch_issue(PatchRegs& P, const uint8_t* __restrict__ img, int pitch, int xi, int yi)
+{
+    const int lane = threadIdx.x & 31;
+    const int x0 = xi - OD_R, y0 = yi - OD_R;
+    const uint8_t* src = img + (size_t)y0 * pitch + (x0 & ~15);
+#pragma unroll
+    for (int k = 0; k < OD_VPL; k++) {
+        const int i = lane + 32 * k;
+        if (i < OD_VEC) P.q[k] = *reinterpret_cast<const uint4*>(src + (size_t)(i >> 2) * pitch + 16 * (i & 3));
+    }
+}
+__device__ __forceinline__ void patch_commit(uint8_t* raw, const PatchRegs& P)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < OD_VPL; k++) {
+        const int i = lane + 32 * k;
+        if (i < OD_VEC) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(raw + (i >> 2) * OD_RP + 16 * (i & 3));
+            dst[0] = P.q[k].x; dst[1] = P.q[k].y; dst[2] = P.q[k].z; dst[3] = P.q[k].w;
+        }
+    }
+}
+
 // One warp, one keypoint.  (xi, yi): integer keypoint position on its level.  mode: ORBX_DO_ANGLE computes the angle,
 // else angle_in is used; ORBX_DO_DESC writes the 32 descriptor bytes.  Returns the angle (valid on every lane).
 __device__ __forceinline__ float orient_describe_warp(WarpPatch& S, const char4* __restrict__ s_pat, const uint8_t* __restrict__ img,
                                                       int w, int h, int pitch, int xi, int yi, int mode, float angle_in,
-                                                      uint8_t* __restrict__ desc_row)
+                                                      uint8_t* __restrict__ desc_row, bool staged = false)
 {
+    // staged: the caller has already put the (interior) patch into S.raw with patch_commit
     const int lane = threadIdx.x & 31;
     const int x0 = xi - OD_R, y0 = yi - OD_R;
-    const bool interior = x0 >= 0 && y0 >= 0 && xi + OD_R < w && yi + OD_R < h;
+    const bool interior = patch_interior(xi, yi, w, h);
     int a = 0;   // smem column of patch column 0
-    if (interior) {
+    if (staged) {
+        a = x0 & 15;
+    } else if (interior) {
         a = x0 & 15;
         const uint8_t* src = img + (size_t)y0 * pitch + (x0 - a);     // 16-byte aligned; the 64-byte window holds a + 43 <= 58 bytes
         for (int i = lane; i < OD_P * 4; i += 32) {
@@ -305,38 +348,47 @@ k_orient_describe(const __grid_constant__ FrameGeom g, const uint8_t* __restrict
             off += n;
         }
     };
-    for (int kidx = blockIdx.x * OD_WARPS + wid; kidx < limit; kidx += gridDim.x * OD_WARPS) {
-        int level, rank;
+    // software pipeline over the warp's keypoints: the patch of keypoint i+1 travels from global memory into registers
+    // while keypoint i is processed out of shared memory
+    const int kstep = gridDim.x * OD_WARPS;
+    int kidx = blockIdx.x * OD_WARPS + wid;
+    PatchRegs P;
+    int level = 0, rank = 0;
+    Sel s = { 0u, 0.f };
+    bool staged = false;
+    if (kidx < limit) {
         locate(kidx, level, rank);
-        {   // pull the NEXT keypoint's patch rows towards L2 while this one is processed (its 43 x 64-byte window)
-            const int knext = kidx + gridDim.x * OD_WARPS;
-            if (knext < limit) {
-                int nl, nr;
-                locate(knext, nl, nr);
-                const LevelGeom& NL = g.lv[nl];
-                const uint32_t nxy = sel[frame * sel_stride + NL.sel_off + nr].xy;
-                const int nx0 = (int)(nxy & 0xFFFFu) - OD_R, ny0 = (int)(nxy >> 16) - OD_R;
-                const uint8_t* base = slots + frame * slot_stride + NL.img_off + (size_t)max(ny0, 0) * NL.pitch + (max(nx0, 0) & ~15);
-                for (int r = lane; r < OD_P && ny0 + r < NL.h; r += 32) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)r * NL.pitch));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)r * NL.pitch + 63));
-                }
-            }
-        }
+        s = sel[frame * sel_stride + g.lv[level].sel_off + rank];
         const LevelGeom& L = g.lv[level];
-        const Sel s = sel[frame * sel_stride + L.sel_off + rank];
-        const int xi = (int)(s.xy & 0xFFFFu), yi = (int)(s.xy >> 16);
+        staged = patch_interior((int)(s.xy & 0xFFFFu), (int)(s.xy >> 16), L.w, L.h);
+        if (staged) patch_issue(P, slots + frame * slot_stride + L.img_off, L.pitch, (int)(s.xy & 0xFFFFu), (int)(s.xy >> 16));
+    }
+    for (; kidx < limit; kidx += kstep) {
+        const LevelGeom& L = g.lv[level];
+        const Sel cur = s;
+        const int cur_level = level;
+        const bool cur_staged = staged;
+        if (cur_staged) patch_commit(s_patch[wid].raw, P);
+        __syncwarp();
+        if (kidx + kstep < limit) {         // issue the next keypoint's patch
+            locate(kidx + kstep, level, rank);
+            s = sel[frame * sel_stride + g.lv[level].sel_off + rank];
+            const LevelGeom& NL = g.lv[level];
+            staged = patch_interior((int)(s.xy & 0xFFFFu), (int)(s.xy >> 16), NL.w, NL.h);
+            if (staged) patch_issue(P, slots + frame * slot_stride + NL.img_off, NL.pitch, (int)(s.xy & 0xFFFFu), (int)(s.xy >> 16));
+        }
+        const int xi = (int)(cur.xy & 0xFFFFu), yi = (int)(cur.xy >> 16);
         const uint8_t* img = slots + frame * slot_stride + L.img_off;
         uint8_t* drow = desc ? desc + ((size_t)frame * cap + kidx) * 32 : nullptr;
-        const float angle = orient_describe_warp(s_patch[wid], s_pat, img, L.w, L.h, L.pitch, xi, yi, mode, -1.f, drow);
+        const float angle = orient_describe_warp(s_patch[wid], s_pat, img, L.w, L.h, L.pitch, xi, yi, mode, -1.f, drow, cur_staged);
         if (lane == 0) {
             orbx_keypoint k;
             k.x = __fmul_rn((float)xi, L.scale);
             k.y = __fmul_rn((float)yi, L.scale);
             k.size = __fmul_rn(31.f, L.scale);
             k.angle = angle;
-            k.response = s.response;
-            k.octave = level;
+            k.response = cur.response;
+            k.octave = cur_level;
             k.class_id = -1;
             out[(size_t)frame * cap + kidx] = k;
         }

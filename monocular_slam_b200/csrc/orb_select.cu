@@ -26,7 +26,6 @@ __global__ void __launch_bounds__(SEL_THREADS)
 k_select(const __grid_constant__ FrameGeom g, const Cand* __restrict__ cand, size_t cand_stride, Cand* __restrict__ surv,
          size_t surv_stride, FrameCounters* __restrict__ ctr)
 {
-    __shared__ uint32_t s_hist[256];
     __shared__ int s_thr;
     const int tid = threadIdx.x, lane = tid & 31;
     const int level = blockIdx.y, frame = blockIdx.z;
@@ -36,15 +35,21 @@ k_select(const __grid_constant__ FrameGeom g, const Cand* __restrict__ cand, siz
     if (n == 0) return;
     const int target = g.score_type == ORBX_HARRIS_SCORE ? 2 * L.quota : L.quota;
 
-    s_hist[tid] = C.hist[level][tid];
+    __shared__ uint32_t s_wsum[SEL_THREADS / 32];
+    const uint32_t cnt = C.hist[level][tid];
     if (tid == 0) s_thr = (n <= target) ? 0 : 256;   // 0: keep everything; 256: keep nothing (target == 0)
-    __syncthreads();
-    if (n > target && target > 0) {
-        // S(s) = #candidates with score >= s is non-increasing in s; the cut is the largest s with S(s) >= target
-        uint32_t S = 0, Snext = 0;
-        for (int v = 255; v >= tid; v--) { Snext = S; S += s_hist[v]; }
-        if (S >= (uint32_t)target && (tid == 255 || Snext < (uint32_t)target)) s_thr = tid;
+    // S(s) = #candidates with score >= s (suffix sum of the histogram, non-increasing in s); the cut is the largest s with
+    // S(s) >= target.  Warp-shuffle suffix scan + the totals of the warps above: 256 bins in a few steps.
+    uint32_t S = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xFFFFFFFFu, S, o);
+        if (lane + o < 32) S += v;
     }
+    if (lane == 0) s_wsum[tid >> 5] = S;
+    __syncthreads();
+    for (int wv = (tid >> 5) + 1; wv < SEL_THREADS / 32; wv++) S += s_wsum[wv];
+    if (n > target && target > 0 && S >= (uint32_t)target && S - cnt < (uint32_t)target) s_thr = tid;
     __syncthreads();
     const uint32_t thr = (uint32_t)s_thr;
 

@@ -1,6 +1,7 @@
 // orbx_api.cu -- C ABI of liborbx.so: handle management, level geometry, and the extraction entry points
 // declared in include/orbx.h (the drop-in for reference src/FeatureExtractor.cpp:17,19).
 #include <math.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <algorithm>
 #include <vector>
@@ -96,6 +97,11 @@ struct orbx_context {
     orbx_dmatch* d_good_back;
     int64_t* d_ngood_back;
     int64_t* h_ngood_back;
+    // single-frame path: the launch sequence of run_extract_on(frame 0) captured as CUDA graphs, one per (mode, capacity);
+    // dropped whenever the geometry changes (the resize tables' addresses are baked into the kernel arguments)
+    struct { cudaGraphExec_t exec; int mode, cap; } graphs[4];
+    int ngraphs;
+    bool use_graphs;
     // two-way split of large batches (run_extract)
     bool split;
     cudaStream_t sub_stream[2];
@@ -202,9 +208,16 @@ static size_t table_bytes(const FrameGeom& g)
     return b + 256;
 }
 
+static void drop_graphs(orbx_handle h)
+{
+    for (int i = 0; i < h->ngraphs; i++) cudaGraphExecDestroy(h->graphs[i].exec);
+    h->ngraphs = 0;
+}
+
 static int set_geometry(orbx_handle h, int w, int hh)
 {
     if (h->geom_w == w && h->geom_h == hh) return ORBX_OK;
+    drop_graphs(h);
     ORBX_REQUIRE(w >= 1 && hh >= 1 && w <= h->max_w && hh <= h->max_h, "frame %dx%d outside the handle's limits %dx%d", w, hh,
                  h->max_w, h->max_h);
     FrameGeom g;
@@ -323,6 +336,8 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     {
         const char* e = getenv("ORBX_SPLIT");
         h->split = !(e && e[0] == '0');
+        e = getenv("ORBX_GRAPHS");
+        h->use_graphs = !(e && e[0] == '0');
         for (int i = 0; i < 2; i++) {
             ORBX_CUDA(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));
             ORBX_CUDA(cudaEventCreateWithFlags(&h->join_event[i], cudaEventDisableTiming));
@@ -376,6 +391,7 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (!h) return ORBX_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graphs(h);
     cudaFree(h->d_slots); cudaFree(h->d_cand); cudaFree(h->d_surv); cudaFree(h->d_sel); cudaFree(h->d_ctr);
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_tab);
     cudaFree(h->d_prev_desc); cudaFree(h->d_prev_count); cudaFree(h->d_good); cudaFree(h->d_ngood); cudaFree(h->d_bgr);
@@ -614,6 +630,44 @@ static int common_checks(orbx_handle h, const void* img, int w, int hh, size_t s
     return set_geometry(h, w, hh);
 }
 
+// frame slot 0 through all stages: replay of a captured graph when possible, plain launches otherwise
+static int run_extract_single(orbx_handle h, int mode, int dcap)
+{
+    if (!h->use_graphs || h->profiling)
+        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, h->profiling);
+    for (int i = 0; i < h->ngraphs; i++)
+        if (h->graphs[i].mode == mode && h->graphs[i].cap == dcap) {
+            ORBX_CUDA(cudaGraphLaunch(h->graphs[i].exec, h->stream));
+            return ORBX_OK;
+        }
+    // capture on the handle's own stream (a caller-provided stream may be the legacy default stream, which cannot capture)
+    cudaGraph_t graph = nullptr;
+    ORBX_CUDA(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->own_stream, false);
+    cudaError_t e = cudaStreamEndCapture(h->own_stream, &graph);
+    if (rc || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->use_graphs = false;      // capture is not possible here: fall back to plain launches for good
+        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, false);
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        h->use_graphs = false;
+        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, false);
+    }
+    if (h->ngraphs == 4) { cudaGraphExecDestroy(h->graphs[0].exec); h->graphs[0] = h->graphs[3]; h->ngraphs = 3; }
+    h->graphs[h->ngraphs].exec = exec;
+    h->graphs[h->ngraphs].mode = mode;
+    h->graphs[h->ngraphs].cap = dcap;
+    h->ngraphs++;
+    ORBX_CUDA(cudaGraphLaunch(exec, h->stream));
+    return ORBX_OK;
+}
+
 static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes, int w, int hh, size_t stride, orbx_keypoint* out,
                         uint8_t* desc, int cap, int32_t* counts, int mode, const char* fn)
 {
@@ -624,6 +678,23 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
     int rc = common_checks(h, frames[0], w, hh, stride, fn);
     if (rc) return rc;
     const int dcap = std::min(cap, h->dev_cap);
+    if (nframes == 1) {
+        // one frame per call is the reference's own pattern (src/FeatureExtractor.cpp:17,19): keep it lean -- everything on
+        // one stream, the kernel sequence replayed as a CUDA graph, results copied speculatively at full capacity so that
+        // a single synchronisation ends the call
+        rc = upload_frames(h, frames, 0, 1, w, hh, stride, cudaMemcpyHostToDevice, h->stream);
+        if (rc) return rc;
+        rc = run_extract_single(h, mode, dcap);
+        if (rc) return rc;
+        h->last_nframes = (mode & ORBX_DO_DESC) ? 1 : 0;
+        h->last_cap = dcap;
+        ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, offsetof(FrameCounters, hist), cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(out, h->d_kps, (size_t)dcap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        if (mode & ORBX_DO_DESC) ORBX_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)dcap * 32, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaStreamSynchronize(h->stream));
+        counts[0] = h->h_ctr[0].total;
+        return check_counters(h, 1, dcap);
+    }
     // chunks of 16 frames: the upload of chunk i+1 (copy stream) overlaps the kernels of chunk i (compute stream)
     const int chunk = 16, nchunks = div_up(nframes, chunk);
     while ((int)h->copy_events->size() < nchunks) {

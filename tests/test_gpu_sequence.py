@@ -213,3 +213,45 @@ def test_match_back_traverse():
     _check_matches(good[1, 0], int(ngood[1, 0]), oracle.match_features(ext[1][1], ext[0][1], ratio))
     m.close()
     orb.close()
+
+
+def test_full_size_batch_consistency():
+    """BASELINE configs[1] at full frame size: a 20-frame 1920x1080 batch (cut in two halves on two streams, uploaded in
+    chunks) must equal the single-frame calls (graph replay) frame by frame, the pipelined path must equal the blocking
+    one, and sampled frames must equal the oracle."""
+    import torch
+    seq = syn.sequence(20, 1920, 1080, seed=31)
+    nf = 2000
+    orb = ORB(nfeatures=nf, max_size=(1920, 1080), max_batch=20)
+    m = BFMatcher()
+    cap = orb.default_cap
+    kps, desc, counts = orb.extract_batch(list(seq), cap=cap)
+    good, ngood = orb.match_consecutive(m, 0.75, cap, 20)
+    kps, desc, counts, good, ngood = kps.copy(), desc.copy(), counts.copy(), good.copy(), ngood.copy()
+    P = oracle.Params(nfeatures=nf)
+    for f in (0, 9, 10, 19):          # both halves, both ends
+        ok, od = oracle.detect_and_compute(seq[f], P)
+        assert_keypoints_equal(kps[f, :counts[f]], ok, "frame %d vs oracle" % f)
+        assert_descriptors_equal(desc[f, :counts[f]], od, "frame %d vs oracle" % f)
+    for f in range(20):
+        k1, d1 = orb.detectAndCompute(seq[f])
+        assert_keypoints_equal(k1, kps[f, :counts[f]], "single frame %d" % f)
+        assert_descriptors_equal(d1, desc[f, :counts[f]], "single frame %d" % f)
+    q, t, d = oracle.match_features(desc[10, :counts[10]], desc[9, :counts[9]], 0.75)    # across the split
+    _check_matches(good[10], int(ngood[10]), (q, t, d))
+    # pipelined path, same frames in two submissions
+    orb.reset_sequence()
+    outs = [(np.zeros((10, cap), KEYPOINT_DTYPE), np.zeros((10, cap, 32), np.uint8), np.zeros(10, np.int32),
+             np.zeros((10, cap), DMATCH_DTYPE), np.zeros(10, np.int64)) for _ in range(2)]
+    pinned = torch.from_numpy(seq).pin_memory().numpy()
+    orb.submit_batch(list(pinned[:10]), m, 0.75, outs[0])
+    orb.submit_batch(list(pinned[10:]), m, 0.75, outs[1])
+    for b in range(2):
+        k2, d2, c2, g2, n2 = orb.wait_batch()
+        for i in range(10):
+            f = 10 * b + i
+            assert c2[i] == counts[f]
+            assert np.array_equal(k2[i, :c2[i]], kps[f, :counts[f]]) and np.array_equal(d2[i, :c2[i]], desc[f, :counts[f]])
+            assert n2[i] == ngood[f] and np.array_equal(g2[i, :n2[i]], good[f, :ngood[f]])
+    m.close()
+    orb.close()

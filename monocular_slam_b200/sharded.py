@@ -51,6 +51,67 @@ def frame_block(nframes, rank, world):
     return lo, hi, (lo - 1 if lo > 0 else None)
 
 
+class ShardedSequence:
+    """Frame-sharded extraction + consecutive-frame matching of ONE sequence over the ranks (BASELINE.json configs 2 and 3).
+
+    Rank r owns the contiguous block ``frame_block(nframes, r, world)``.  Frames are independent, so there is no exchange:
+    to match its first frame against the previous rank's last frame, the rank simply extracts that one extra frame
+    itself (1 / block-length of redundant work instead of a 64 KB peer copy and a dependency between ranks).
+
+    ``run(frames)`` walks the block in batches through the pipelined host path (``ORB.submit_batch`` / ``wait_batch``) and
+    yields ``(frame_index, keypoints, descriptors, matches_against_previous_frame)`` in frame order for the rank's own
+    frames.  ``extract_match(frames, first_is_lead_in)`` can be injected to exercise the block logic without a GPU.
+    """
+
+    def __init__(self, orb=None, matcher=None, ratio=0.8, rank=0, world=1, batch=None, extract_match=None):
+        self.orb, self.matcher, self.ratio = orb, matcher, float(ratio)
+        self.rank, self.world = int(rank), int(world)
+        self.batch = int(batch or (orb.max_batch if orb is not None else 16))
+        self._extract_match = extract_match
+        if orb is None and extract_match is None:
+            raise ValueError("ShardedSequence needs an ORB + BFMatcher (CUDA) or an injected extract_match")
+
+    def block(self, nframes):
+        return frame_block(nframes, self.rank, self.world)
+
+    def run(self, frames):
+        lo, hi, prev = self.block(len(frames))
+        if hi <= lo:
+            return
+        start = lo if prev is None else prev          # lead-in frame: extracted, matched against nothing, not reported
+        if self._extract_match is not None:
+            chunks = [(b, min(b + self.batch, hi)) for b in range(start, hi, self.batch)]
+            for b, e in chunks:
+                for off, (k, d, m) in enumerate(self._extract_match(frames[b:e], b == start)):
+                    if b + off >= lo:
+                        yield b + off, k, d, m
+            return
+        import numpy as np
+        from ._lib import DMATCH_DTYPE, KEYPOINT_DTYPE
+        orb, cap, depth = self.orb, self.orb.default_cap, self.orb.pipeline_depth()
+        orb.reset_sequence()
+        pending = []
+
+        def collect():
+            b, n = pending.pop(0)
+            kps, desc, counts, good, ngood = orb.wait_batch()
+            for i in range(n):
+                f = b + i
+                if f >= lo:
+                    yield f, kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy(), good[i, :ngood[i]].copy()
+
+        for b in range(start, hi, self.batch):
+            n = min(self.batch, hi - b)
+            if len(pending) == depth:
+                yield from collect()
+            out = (np.zeros((n, cap), KEYPOINT_DTYPE), np.zeros((n, cap, 32), np.uint8), np.zeros(n, np.int32),
+                   np.zeros((n, cap), DMATCH_DTYPE), np.zeros(n, np.int64))
+            orb.submit_batch(list(frames[b:b + n]), self.matcher, self.ratio, out)
+            pending.append((b, n))
+        while pending:
+            yield from collect()
+
+
 class ShardedMatcher:
     """Train-sharded brute-force Hamming kNN(k=2) (BASELINE.json configs 4 and 5).
 

@@ -255,3 +255,27 @@ def test_full_size_batch_consistency():
             assert n2[i] == ngood[f] and np.array_equal(g2[i, :n2[i]], good[f, :ngood[f]])
     m.close()
     orb.close()
+
+
+def test_sharded_sequence_equals_single_rank():
+    """ShardedSequence on the GPU: the blocks of a 3-rank split (run one after the other on this GPU) reproduce the
+    single-rank run frame by frame, including the matches across block borders."""
+    from monocular_slam_b200.sharded import ShardedSequence
+    seq = syn.sequence(11, 640, 480, seed=41)
+    orb = ORB(nfeatures=500, max_size=(640, 480), max_batch=3)
+    m = BFMatcher()
+    ref = {f: (k, d, g) for f, k, d, g in ShardedSequence(orb, m, 0.8, 0, 1).run(seq)}
+    assert sorted(ref) == list(range(11)) and len(ref[0][2]) == 0
+    P = oracle.Params(nfeatures=500)
+    e4, e5 = oracle.detect_and_compute(seq[4], P), oracle.detect_and_compute(seq[5], P)
+    _check_matches(ref[5][2], len(ref[5][2]), oracle.match_features(e5[1], e4[1], 0.8))
+    got = {}
+    for r in range(3):
+        for f, k, d, g in ShardedSequence(orb, m, 0.8, r, 3).run(seq):
+            assert f not in got
+            got[f] = (k, d, g)
+    assert sorted(got) == list(range(11))
+    for f in range(11):
+        assert np.array_equal(got[f][0], ref[f][0]) and np.array_equal(got[f][1], ref[f][1]) and np.array_equal(got[f][2], ref[f][2]), f
+    m.close()
+    orb.close()

@@ -71,3 +71,33 @@ def test_train_sharded_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_sharded_sequence_blocks_cpu():
+    """ShardedSequence block logic with an injected extract/match (no GPU): every frame is reported exactly once, by the
+    rank that owns it, and each block's first frame is matched against the previous rank's last frame (lead-in frame)."""
+    from monocular_slam_b200.sharded import ShardedSequence
+    nframes, world = 23, 4
+    frames = list(range(nframes))        # a "frame" is its index; the stand-in's "match" records the frame it was matched to
+    calls = []
+
+    def fake(batch, first_is_lead_in):
+        out = []
+        for i, f in enumerate(batch):
+            prev = None if (i == 0 and first_is_lead_in) else f - 1
+            out.append(("kp%d" % f, "desc%d" % f, prev))
+        calls.append((list(batch), first_is_lead_in))
+        return out
+
+    seen = {}
+    for r in range(world):
+        ss = ShardedSequence(rank=r, world=world, batch=4, extract_match=fake)
+        lo, hi, prev = ss.block(nframes)
+        got = list(ss.run(frames))
+        assert [g[0] for g in got] == list(range(lo, hi))
+        for f, k, d, m in got:
+            assert f not in seen
+            seen[f] = m
+            assert k == "kp%d" % f and d == "desc%d" % f
+    assert sorted(seen) == list(range(nframes))
+    assert seen[0] is None and all(seen[f] == f - 1 for f in range(1, nframes))

@@ -305,9 +305,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     dev_ms, _ = timed(step_device, args.steps, args.warmup, sampler)
     orb.check_dev()
-    # per-stage device times: the same steps again with the library's stage events on.  Profiling keeps every launch on one
-    # stream (the timed run above cuts each batch into two halves on two streams), so the stage times add up to slightly
-    # more than ms_per_step.
+    # per-stage device times: the same steps again with the library's stage events on
     orb.set_profiling(True)
     step_device()
     orb.read_profile()     # drop the first batch
@@ -472,10 +470,13 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
     clocks = sampler.summary()
-    # kernels of liborbx.so per timed step: ingest; per half of the batch (the library cuts batches of >= 16 frames in two
-    # halves on two streams unless ORBX_SPLIT=0): 7 pyramid levels, FAST, score cut, Harris selection, orient+describe;
-    # then pair table, kNN2, ratio test
-    halves = 2 if (B >= 16 and os.environ.get("ORBX_SPLIT", "1")[:1] != "0") else 1
+    # kernels of liborbx.so per timed step: ingest; per part of the batch (ORBX_SPLIT=n cuts batches in n parts on n
+    # streams; default 1): 7 pyramid levels, FAST, score cut, Harris selection, orient+describe; then pair table, kNN2,
+    # ratio test
+    try:
+        halves = max(1, min(int(os.environ.get("ORBX_SPLIT", "1")), B // 8))
+    except ValueError:
+        halves = 1
     launches_per_step = 1 + halves * ((len(ws) - 1) + 4) + 3
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

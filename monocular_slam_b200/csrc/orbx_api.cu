@@ -49,7 +49,8 @@ struct orbx_lane {
 };
 constexpr int ORBX_LANES = 3;
 constexpr int ORBX_MAX_BACK = 8;
-constexpr int ORBX_SPLIT_MIN = 8;       // a batch is split in two when each half has at least this many frames
+constexpr int ORBX_SPLIT_MIN = 8;
+constexpr int ORBX_MAX_SPLIT = 8;       // a batch is split in two when each half has at least this many frames
 
 struct orbx_context {
     int device;
@@ -103,9 +104,9 @@ struct orbx_context {
     int ngraphs;
     bool use_graphs;
     // two-way split of large batches (run_extract)
-    bool split;
-    cudaStream_t sub_stream[2];
-    cudaEvent_t fork_event, join_event[2];
+    int split;                                // number of parts (1 = off)
+    cudaStream_t sub_stream[ORBX_MAX_SPLIT];
+    cudaEvent_t fork_event, join_event[ORBX_MAX_SPLIT];
     // 3-channel input (orbx_set_input_channels): packed BGR staging for the host paths, allocated on first use
     int channels;
     uint8_t* d_bgr;
@@ -335,10 +336,12 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     ORBX_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     {
         const char* e = getenv("ORBX_SPLIT");
-        h->split = !(e && e[0] == '0');
+        h->split = e ? atoi(e) : 1;
+        if (h->split < 1) h->split = 1;
+        if (h->split > ORBX_MAX_SPLIT) h->split = ORBX_MAX_SPLIT;
         e = getenv("ORBX_GRAPHS");
         h->use_graphs = !(e && e[0] == '0');
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < ORBX_MAX_SPLIT; i++) {
             ORBX_CUDA(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));
             ORBX_CUDA(cudaEventCreateWithFlags(&h->join_event[i], cudaEventDisableTiming));
         }
@@ -405,7 +408,7 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ORBX_MAX_SPLIT; i++) {
         if (h->sub_stream[i]) { cudaStreamSynchronize(h->sub_stream[i]); cudaStreamDestroy(h->sub_stream[i]); }
         if (h->join_event[i]) cudaEventDestroy(h->join_event[i]);
     }
@@ -557,23 +560,26 @@ static int run_extract_on(orbx_handle h, int f0, int nframes, int mode, orbx_key
     return ORBX_OK;
 }
 
-// The stages of one frame depend on each other, the frames of a batch do not.  Large batches are therefore cut in two
-// halves that run on two internal streams (forked from / joined to the handle's stream with events): the short,
-// latency-bound launches of one half (small pyramid levels, score cut, Harris selection) and the tails of its big ones
-// overlap the bulk kernels of the other half.  Stage profiling keeps one stream so its per-stage events stay meaningful.
+// The stages of one frame depend on each other, the frames of a batch do not.  A large batch can therefore be cut in
+// `split` parts (ORBX_SPLIT=n) that run on as many internal streams (forked from / joined to the handle's stream with
+// events), so that the short, latency-bound launches of one part overlap the bulk kernels of another.  That paid 3 % while
+// the Harris selection and the score cut were slow; with the current kernels one stream is fastest (measured: 24.6 k
+// frames/s unsplit vs 24.1-24.5 k with 2-8 parts), so the default is 1 = off.  Stage profiling always keeps one stream.
 static int run_extract(orbx_handle h, int f0, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
 {
-    if (h->profiling || !h->split || nframes < 2 * ORBX_SPLIT_MIN)
+    int parts = std::min(h->split, nframes / ORBX_SPLIT_MIN);
+    if (h->profiling || parts < 2)
         return run_extract_on(h, f0, nframes, mode, d_out, d_desc, cap, d_counts, h->stream, h->profiling);
     ORBX_CUDA(cudaEventRecord(h->fork_event, h->stream));
-    const int half = (nframes + 1) / 2;
-    for (int i = 0; i < 2; i++) {
-        const int b = i * half, n = i == 0 ? half : nframes - half;
+    int b = 0;
+    for (int i = 0; i < parts; i++) {
+        const int n = (nframes - b) / (parts - i);
         ORBX_CUDA(cudaStreamWaitEvent(h->sub_stream[i], h->fork_event, 0));
         int rc = run_extract_on(h, f0 + b, n, mode, d_out, d_desc, cap, d_counts, h->sub_stream[i], false);
         if (rc) return rc;
         ORBX_CUDA(cudaEventRecord(h->join_event[i], h->sub_stream[i]));
         ORBX_CUDA(cudaStreamWaitEvent(h->stream, h->join_event[i], 0));
+        b += n;
     }
     return ORBX_OK;
 }

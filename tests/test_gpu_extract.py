@@ -265,3 +265,32 @@ def test_parameter_surface_golden(golden_dir, name):
     assert_keypoints_equal(kps[1, :counts[1]], g[name + "_kp"], name + " batch")
     assert_descriptors_equal(desc[1, :counts[1]], g[name + "_desc"], name + " batch")
     orb.close()
+
+
+FUZZ = [  # (w, h, nfeatures, scaleFactor, nlevels, scoreType, fastThreshold, seed)
+    (67, 64, 50, 1.2, 8, 0, 20, 1), (64, 67, 50, 1.2, 3, 1, 5, 2), (130, 95, 200, 1.3, 6, 0, 12, 3), (257, 129, 300, 1.25, 5, 1, 20, 4),
+    (511, 300, 900, 1.2, 8, 0, 30, 5), (640, 65, 120, 1.15, 4, 0, 20, 6), (63, 400, 100, 1.2, 8, 0, 20, 7), (1023, 257, 1500, 1.2, 8, 1, 8, 8),
+    (385, 385, 4000, 1.1, 10, 0, 3, 9), (1280, 720, 1000, 1.41, 6, 0, 20, 10), (129, 128, 500, 2.0, 4, 0, 10, 11), (800, 608, 250, 1.2, 1, 1, 40, 12),
+]
+
+
+@pytest.mark.parametrize("case", FUZZ, ids=lambda c: "%dx%d_nf%d_s%g_l%d_t%d_%d" % (c[0], c[1], c[2], c[3], c[4], c[6], c[5]))
+def test_fuzz_against_oracle(case):
+    """Odd sizes (down to frames with no interior at the coarse levels), every runtime parameter, both score types,
+    dense and sparse thresholds: detectAndCompute == oracle, and detect -> compute == detectAndCompute."""
+    w, h, nf, sf, nl, st, thr, seed = case
+    img = syn.textured_frame(seed, w, h) if seed % 2 else syn.frame(seed, w, h, nrect=max(10, w * h // 4000))
+    P = oracle.Params(nfeatures=nf, scale_factor=sf, nlevels=nl, score_type=st, fast_threshold=thr)
+    ok, od = oracle.detect_and_compute(img, P)
+    orb = ORB(nfeatures=nf, scaleFactor=sf, nlevels=nl, scoreType=st, fastThreshold=thr, max_size=(w, h), max_batch=2)
+    k, d = orb.detectAndCompute(img)
+    assert_keypoints_equal(k, ok, "detectAndCompute")
+    assert_descriptors_equal(d, od, "detectAndCompute")
+    k2 = orb.detect(img)
+    k2, d2 = orb.compute(img, k2)
+    assert_keypoints_equal(k2, ok, "detect->compute")
+    assert_descriptors_equal(d2, od, "detect->compute")
+    kps, desc, counts = orb.extract_batch([img, img])
+    assert_keypoints_equal(kps[1, :counts[1]], ok, "batch")
+    assert_descriptors_equal(desc[1, :counts[1]], od, "batch")
+    orb.close()

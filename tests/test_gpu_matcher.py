@@ -183,3 +183,46 @@ def test_p2p_fused_scatter_merge_single_process(world, nq, nt):
                 assert np.array_equal(got[:, 0], want_dist[:, 0]) and np.array_equal(got[:, 2], want_dist[:, 1])
         for m in ms:
             m.close()
+
+
+def test_train_set_larger_than_index_field():
+    """More than 2^23 train rows: the packed (distance << 23 | index) key covers one chunk, the host splits the train set and
+    merges the chunks with the 64-bit rule.  Planted exact duplicates on both sides of the chunk border pin the tie rule
+    (lowest global index first) and the global offsets; a sample of queries is checked against the oracle on a window."""
+    import torch
+    nt, nq = (1 << 23) + 70001, 512
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device="cuda", generator=g)
+        q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device="cuda", generator=g)
+        border = 1 << 23
+        # query i (< 64) has two exact copies: one just before the border, one after it
+        for i in range(64):
+            t[border - 100 + i] = q[i]
+            t[border + 5000 + i] = q[i]
+        # query 64 + i (< 64): copies only in the second chunk, in descending position
+        for i in range(64):
+            t[border + 60000 - i] = q[64 + i]
+        m = BFMatcher()
+        m.set_stream(stream.cuda_stream)
+        out = torch.empty((nq, 4), dtype=torch.int32, device="cuda")
+        m.knn2_dev(q.data_ptr(), nq, t.data_ptr(), nt, 0, out.data_ptr())
+        stream.synchronize()
+    r = out.cpu().numpy()
+    for i in range(64):
+        assert tuple(r[i]) == (0, border - 100 + i, 0, border + 5000 + i), (i, r[i])
+        assert r[64 + i][0] == 0 and r[64 + i][1] == border + 60000 - i
+    # the rest: compare with the oracle on the rows around the reported neighbours plus a random window (distances must be
+    # true distances and no closer row may exist in the window)
+    th = t.cpu().numpy()
+    qh = q.cpu().numpy()
+    win = np.concatenate([np.arange(0, 200000), np.arange(border - 100000, border + 70001)])
+    oi, od = oracle.knn2(qh[128:192], th[win])
+    for j in range(64):
+        i = 128 + j
+        d0 = int(np.unpackbits(qh[i] ^ th[r[i][1]]).sum())
+        d1 = int(np.unpackbits(qh[i] ^ th[r[i][3]]).sum())
+        assert (d0, d1) == (r[i][0], r[i][2]) and d0 <= d1
+        assert d0 <= od[j, 0] and d1 <= od[j, 1]          # nothing in the window beats the global answer
+    m.close()

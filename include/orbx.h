@@ -82,6 +82,10 @@ typedef struct hamx_context* hamx_handle;
 ORBX_API const char* orbx_last_error(void);
 ORBX_API const char* orbx_version(void);
 ORBX_API int orbx_device_count(void);
+/* Page-locked host memory for frames and result buffers (callers that do not link the CUDA runtime themselves): copies
+ * from / to such memory are asynchronous, which is what lets orbx_submit_batch overlap them with the kernels. */
+ORBX_API int orbx_host_alloc(size_t bytes, void** out);
+ORBX_API int orbx_host_free(void* p);
 ORBX_API void orbx_default_params(orbx_params* p);
 
 /* ------------------------------------------------------------------ extraction (FeatureExtractor) */

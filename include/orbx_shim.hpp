@@ -14,9 +14,11 @@
 // cv::Exception either).  No algorithm runs on the CPU here: every call goes to the GPU through liborbx.so.
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "orbx.h"
@@ -281,6 +283,104 @@ public:
 private:
     OrbFeatureDetector detector;
     OrbDescriptorExtractor extractor;
+};
+
+// The fast path for a loaded sequence (the reference loads every frame before the loop, src/main.cpp:35-37): batches of
+// frames go through orbx_submit_batch / orbx_wait_batch, so uploads, kernels and downloads of consecutive batches overlap,
+// and every frame is matched against its predecessor on the device (matchFeatures(cur, prev), CameraPoseEstimator.cpp:409).
+// Results land where FeatureExtractor::process and matchFeatures would have put them.
+class SequenceFrontEnd {
+public:
+    SequenceFrontEnd(int nfeatures, float ratio, int batch, int width, int height, int device = 0)
+        : orb_(nullptr), bf_(nullptr), ratio_(ratio), batch_(batch), w_(width), h_(height), cap_(0), depth_(0)
+    {
+        orbx_params p;
+        orbx_default_params(&p);
+        p.nfeatures = nfeatures;
+        check(orbx_create(&orb_, &p, device, width, height, batch), "SequenceFrontEnd: orbx_create");
+        check(hamx_create(&bf_, device), "SequenceFrontEnd: hamx_create");
+        cap_ = std::min(orbx_max_keypoints(orb_), nfeatures + std::max(nfeatures / 4, 512));
+        depth_ = orbx_pipeline_depth(orb_);
+        slots_.resize((size_t)depth_);
+        for (size_t i = 0; i < slots_.size(); i++) {
+            Slot& s = slots_[i];
+            check(orbx_host_alloc((size_t)batch * width * height, (void**)&s.frames), "SequenceFrontEnd: pinned frames");
+            check(orbx_host_alloc((size_t)batch * cap_ * sizeof(orbx_keypoint), (void**)&s.kps), "SequenceFrontEnd: pinned keypoints");
+            check(orbx_host_alloc((size_t)batch * cap_ * 32, (void**)&s.desc), "SequenceFrontEnd: pinned descriptors");
+            check(orbx_host_alloc((size_t)batch * cap_ * sizeof(orbx_dmatch), (void**)&s.good), "SequenceFrontEnd: pinned matches");
+            s.counts.resize((size_t)batch);
+            s.ngood.resize((size_t)batch);
+        }
+    }
+    ~SequenceFrontEnd()
+    {
+        while (orb_ && orbx_batches_in_flight(orb_) > 0) orbx_wait_batch(orb_);
+        for (size_t i = 0; i < slots_.size(); i++) {
+            orbx_host_free(slots_[i].frames); orbx_host_free(slots_[i].kps); orbx_host_free(slots_[i].desc); orbx_host_free(slots_[i].good);
+        }
+        if (bf_) hamx_destroy(bf_);
+        if (orb_) orbx_destroy(orb_);
+    }
+    SequenceFrontEnd(const SequenceFrontEnd&) = delete;
+    SequenceFrontEnd& operator=(const SequenceFrontEnd&) = delete;
+
+    // frames [first, first + count) of dm (all width x height, CV_8UC1): fills frames[i].features and matches[i - first]
+    // (frame i against frame i-1; empty for the first frame of a sequence -- call reset() to start a new one)
+    void process(DataManager& dm, int first, int count, std::vector<std::vector<DMatch> >& matches)
+    {
+        matches.assign((size_t)count, std::vector<DMatch>());
+        std::vector<std::pair<int, int> > pending;     // (first frame, count) of the batches in flight, oldest first
+        size_t next_slot = 0, oldest_slot = 0;
+        for (int b = first; b < first + count; b += batch_) {
+            const int n = std::min(batch_, first + count - b);
+            if ((int)pending.size() == depth_) { collect(dm, pending.front(), slots_[oldest_slot], matches, first); pending.erase(pending.begin()); oldest_slot = (oldest_slot + 1) % slots_.size(); }
+            Slot& s = slots_[next_slot];
+            std::vector<const uint8_t*> ptrs((size_t)n);
+            for (int i = 0; i < n; i++) {              // gather into pinned memory (frames of a cv::Mat sequence are pageable)
+                const Mat& fb = dm.frames[(size_t)(b + i)].frameBuffer;
+                if (fb.rows != h_ || fb.cols != w_ || mat_channels(fb) != 1) throw Error(ORBX_E_INVALID, "SequenceFrontEnd: frame size / type mismatch");
+                uint8_t* dst = s.frames + (size_t)i * w_ * h_;
+                for (int y = 0; y < h_; y++) std::memcpy(dst + (size_t)y * w_, fb.ptr(y), (size_t)w_);
+                ptrs[(size_t)i] = dst;
+            }
+            check(orbx_submit_batch(orb_, bf_, ptrs.data(), n, w_, h_, (size_t)w_, ratio_, s.kps, s.desc, cap_, s.counts.data(), s.good,
+                                    s.ngood.data()), "SequenceFrontEnd: orbx_submit_batch");
+            pending.push_back(std::make_pair(b, n));
+            next_slot = (next_slot + 1) % slots_.size();
+        }
+        while (!pending.empty()) { collect(dm, pending.front(), slots_[oldest_slot], matches, first); pending.erase(pending.begin()); oldest_slot = (oldest_slot + 1) % slots_.size(); }
+    }
+    void reset() { check(orbx_reset_sequence(orb_), "SequenceFrontEnd: reset"); }
+
+private:
+    struct Slot {
+        uint8_t* frames; orbx_keypoint* kps; uint8_t* desc; orbx_dmatch* good;
+        std::vector<int32_t> counts; std::vector<int64_t> ngood;
+        Slot() : frames(nullptr), kps(nullptr), desc(nullptr), good(nullptr) {}
+    };
+    void collect(DataManager& dm, std::pair<int, int> batch, Slot& s, std::vector<std::vector<DMatch> >& matches, int first)
+    {
+        check(orbx_wait_batch(orb_), "SequenceFrontEnd: orbx_wait_batch");
+        for (int i = 0; i < batch.second; i++) {
+            Features& ft = dm.frames[(size_t)(batch.first + i)].features;
+            const int n = s.counts[(size_t)i];
+            const orbx_keypoint* k = s.kps + (size_t)i * cap_;
+            ft.positions.resize((size_t)n); ft.scales.resize((size_t)n); ft.mapPointsIndices.assign((size_t)n, -1);
+            for (int j = 0; j < n; j++) {               // FeatureExtractor.cpp:20-25
+                ft.positions[(size_t)j].x = (double)k[j].x; ft.positions[(size_t)j].y = (double)k[j].y;
+                ft.scales[(size_t)j] = (double)k[j].size;
+            }
+            mat_create_u8(ft.descriptors, n, 32);
+            if (n) std::memcpy(ft.descriptors.data, s.desc + (size_t)i * cap_ * 32, (size_t)n * 32);
+            const DMatch* g = reinterpret_cast<const DMatch*>(s.good + (size_t)i * cap_);
+            matches[(size_t)(batch.first + i - first)].assign(g, g + s.ngood[(size_t)i]);
+        }
+    }
+    orbx_handle orb_;
+    hamx_handle bf_;
+    float ratio_;
+    int batch_, w_, h_, cap_, depth_;
+    std::vector<Slot> slots_;
 };
 #endif
 

@@ -28,7 +28,7 @@ SYMBOLS = [
     "hamx_popc_peak", "hamx_match_pairs_dev", "hamx_match_consecutive_dev", "orbx_match_consecutive", "orbx_reset_sequence",
     "orbx_set_profiling", "orbx_read_profile", "orbx_submit_batch", "orbx_wait_batch", "orbx_batches_in_flight",
     "hamx_p2p_export", "hamx_p2p_import", "hamx_p2p_import_ptrs", "hamx_p2p_close", "hamx_knn2_p2p_dev",
-    "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev", "orbx_set_input_channels", "orbx_pipeline_depth", "hamx_match_back_dev", "hamx_update_history_dev", "orbx_match_back",
+    "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev", "orbx_set_input_channels", "orbx_pipeline_depth", "hamx_match_back_dev", "hamx_update_history_dev", "orbx_match_back", "orbx_host_alloc", "orbx_host_free",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -115,6 +115,8 @@ def lib():
     L.orbx_batches_in_flight.argtypes = [vp]
     L.orbx_set_input_channels.argtypes = [vp, C.c_int]
     L.orbx_pipeline_depth.argtypes = [vp]
+    L.orbx_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.orbx_host_free.argtypes = [vp]
     L.hamx_match_back_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_float, vp, vp]
     L.hamx_update_history_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     L.orbx_match_back.argtypes = [vp, vp, C.c_int, C.c_float, vp, i64p]

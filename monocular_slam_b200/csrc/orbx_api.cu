@@ -262,6 +262,21 @@ static int set_geometry(orbx_handle h, int w, int hh)
 extern "C" const char* orbx_last_error(void) { return g_error; }
 extern "C" const char* orbx_version(void) { return "orbx 0.1 (sm_100a)"; }
 
+extern "C" int orbx_host_alloc(size_t bytes, void** out)
+{
+    ORBX_REQUIRE(out != nullptr && bytes > 0, "orbx_host_alloc: bad arguments");
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes);
+    if (e != cudaSuccess) { set_error("orbx_host_alloc: cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); *out = nullptr; return ORBX_E_ALLOC; }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_host_free(void* p)
+{
+    if (p) ORBX_CUDA(cudaFreeHost(p));
+    return ORBX_OK;
+}
+
 extern "C" int orbx_device_count(void)
 {
     int n = 0;

@@ -12,12 +12,12 @@ from monocular_slam_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build_demo(tmpdir):
+def _build_demo(tmpdir, name="shim_demo"):
     _lib.build()
-    exe = os.path.join(str(tmpdir), "shim_demo")
+    exe = os.path.join(str(tmpdir), name)
     libdir = os.path.dirname(_lib.LIB_PATH)
     subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "shim_demo.cpp"), "-o", exe, "-L", libdir, "-lorbx",
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L", libdir, "-lorbx",
                            "-Wl,-rpath," + libdir])
     return exe
 
@@ -32,17 +32,24 @@ def test_shim_compiles_and_fails_loudly_without_gpu(tmp_path):
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
 
 
+def test_pipeline_demo_compiles(tmp_path):
+    _build_demo(tmp_path, "pipeline_demo")
+
+
 @pytest.mark.gpu
-def test_shim_matches_oracle(tmp_path):
+@pytest.mark.parametrize("demo,n,extra", [("shim_demo", 3, []), ("pipeline_demo", 9, ["2"])])
+def test_shim_matches_oracle(tmp_path, demo, n, extra):
+    """shim_demo: the reference's call-by-call surface; pipeline_demo: SequenceFrontEnd (batches of 2 through the pipelined
+    C ABI, two process() calls).  Both must reproduce the oracle frame by frame and match by match."""
     import oracle
     from monocular_slam_b200 import synthetic as syn
-    exe = _build_demo(tmp_path)
-    w, h, n, nf, ratio = 800, 600, 3, 700, 0.8
+    exe = _build_demo(tmp_path, demo)
+    w, h, nf, ratio = 800, 600, 700, 0.8
     seq = syn.sequence(n, w, h, seed=33)
     raw = tmp_path / "frames.raw"
     raw.write_bytes(seq.tobytes())
     out = tmp_path / "out.bin"
-    subprocess.check_call([exe, str(w), str(h), str(n), str(raw), str(out), str(nf), str(ratio)])
+    subprocess.check_call([exe, str(w), str(h), str(n), str(raw), str(out), str(nf), str(ratio)] + extra)
     buf = out.read_bytes()
     off = 0
     P = oracle.Params(nfeatures=nf)

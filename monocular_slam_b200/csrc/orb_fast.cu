@@ -8,11 +8,12 @@
 //   and 31 <= x < w-31, 31 <= y < h-31.
 //
 // A CTA owns a 124x30 tile of the interior [31,w-31) x [31,h-31) of one level.  It stages the tile plus a 4-pixel
-// halo in shared memory with 16-byte loads (rows are 128-byte pitched), widening every pixel to 16 bits on the way so
+// halo in shared memory with 8-byte loads (rows are 128-byte pitched), widening every pixel to 16 bits on the way so
 // that two horizontally adjacent pixels already form one packed s16x2 register operand, then
 //   1. scores the (tile + 1) region branch-free, four horizontally adjacent pixels per thread and two pixels per
 //      instruction: the RAW ring pixels live in packed 16x2 lanes and the sliding 9-of-16 window minimum / maximum
-//      is a network of VIMNMX.S16x2 / VIMNMX3.S16x2 (36 per sign and pixel pair); min/max is shift-invariant, so the
+//      is a network of 36 min/max per sign and pixel pair -- the 16 (min, max) pairs with shared inputs as HFMA2.RELU /
+//      HFMA2 on the FMA pipe, the rest as VIMNMX(3).S16x2 on the ALU pipe; min/max is shift-invariant, so the
 //      centre is subtracted once from the two results instead of from the 16 ring pixels, which yields
 //      m = max(max_k min9(ring) - c, c - min_k max9(ring)) exactly -- no corner pre-test, no divergence.  A warp
 //      covers one score row (32 groups of 4 pixels); 21 aligned 64-bit shared-memory loads and 18 byte-permutes feed
@@ -24,7 +25,8 @@
 //      of the level's candidate list with ONE global atomic and writes (x, y, score); the per-level score histogram used
 //      by the retainBest cut (K3) gets one RED per survivor.
 // CTAs are 128 threads (4 warps x 8 rows): small barrier domains, 8 CTAs per SM.
-// Bound: integer ALU issue (VIMNMX/PRMT), not HBM: each level byte is read once from HBM and ~1.4x from L2.
+// Bound: instruction issue (ncu: issue slots 80 % busy, ALU pipe 71 %), not HBM: each level byte is read once from HBM
+// and ~1.4x from L2.  About 95 instructions per pixel in total.
 #include "common.cuh"
 
 namespace orbx {
@@ -42,7 +44,7 @@ constexpr int FT_THREADS = FT_THREADS_N;
 constexpr int FT_NW = FT_THREADS / 32;
 constexpr int FT_SP = 160;               // smem pitch (image and score share column coordinates): <= 15 + 4 + 124 + 4
 constexpr int FT_SH = FT_TH + 8;         // 38 image rows
-constexpr int FT_CH = FT_TH + 2;         // 32 score rows = 8 warps x 4
+constexpr int FT_CH = FT_TH + 2;         // 32 score rows = 4 warps x 8
 constexpr int FT_EMIT = (FT_TW / 2 + 1) * (FT_TH / 2 + 1);   // NMS allows at most one maximum per 2x2 block
 
 // 16x2 lanes from bytes (0,1) / (2,3) of g

@@ -47,7 +47,10 @@ struct orbx_lane {
     int32_t* counts;      // caller's arrays, filled by orbx_wait_batch
     int64_t* ngood;
 };
-constexpr int ORBX_LANES = 3;
+#ifndef ORBX_LANES_N
+#define ORBX_LANES_N 3
+#endif
+constexpr int ORBX_LANES = ORBX_LANES_N;
 constexpr int ORBX_MAX_BACK = 8;
 constexpr int ORBX_SPLIT_MIN = 8;
 constexpr int ORBX_MAX_SPLIT = 8;       // a batch is split in two when each half has at least this many frames

@@ -406,6 +406,13 @@ def run_ours(args, rank, world, local_rank):
                 "note": "FAST reads each pyramid-level byte once (3.096 x W x H per frame); it is bound by instruction issue "
                         "(about 80 instructions per pixel on the integer pipes), not by HBM: see roofline.issue"}
 
+    # the HBM-bound stage of the path, for the same roofline arithmetic: the pyramid reads levels 0..6 and writes levels 1..7
+    pyr_bytes = int(B * (2 * level_px - W * H - int(ws[-1]) * int(hs[-1])))
+    roofline_pyramid = {"kernel": "k_pyr_down (7 launches)", "bound": "hbm", "achieved": pyr_bytes / (stages["pyramid"] * 1e-3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": pyr_bytes / (stages["pyramid"] * 1e-3) / 1e9 / peak,
+                        "algorithmic_bytes_per_step": pyr_bytes, "ms_per_step": stages["pyramid"],
+                        "note": "bit-exact INTER_LINEAR_EXACT chain; ncu shows it bound by L1 / shared-memory throughput (70 %), not DRAM (14 %)"}
+
     # ---- secondary metric: train-sharded Hamming kNN2, Gcmp/s over all ranks
     hamming = None
     if not args.no_hamming:
@@ -498,6 +505,7 @@ def run_ours(args, rank, world, local_rank):
                         "blocking_note": "orbx_extract_batch + orbx_match_consecutive, each call returns with its results in host memory"},
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": roofline,
+                "roofline_pyramid": roofline_pyramid,
                 "stages_ms_per_step": dict(stages, match=match_ms, profiled_step=prof_ms / args.steps),
                 "cpu_baseline": cpu,
                 "hamming": hamming}

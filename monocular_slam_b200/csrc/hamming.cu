@@ -142,6 +142,8 @@ struct P2PView {
     long long nq_max;
     int world, rank;
     unsigned int epoch;                  // 0: P2P disabled
+    hamx_top2* merge_out;                // non-NULL: the CTA that publishes also waits for the world and merges (small nq)
+    long long merge_nq;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
@@ -162,19 +164,55 @@ __device__ __forceinline__ void p2p_store(const P2PView& pv, long long qi, const
     for (int r = 0; r < pv.world; r++) *reinterpret_cast<uint4*>(pv.gather[r] + slot) = bits;
 }
 
-// called by every CTA that wrote results, after its last p2p_store; `writers` = number of such CTAs in the grid
+__device__ __forceinline__ hamx_top2 p2p_merge_one(const P2PView& pv, long long i)
+{
+    const hamx_top2* base = pv.gather[pv.rank] + (size_t)(pv.epoch & 1u) * pv.world * (size_t)pv.nq_max;
+    unsigned long long m0 = ~0ull, m1 = ~0ull;
+    for (int r = 0; r < pv.world; r++) {
+        const uint4 bits = __ldcg(reinterpret_cast<const uint4*>(base + (size_t)r * pv.nq_max + i));   // written by a peer: skip L1
+        top2_insert64(m0, m1, top2_key64((int32_t)bits.x, (int32_t)bits.y));
+        top2_insert64(m0, m1, top2_key64((int32_t)bits.z, (int32_t)bits.w));
+    }
+    hamx_top2 r;
+    r.dist0 = m0 == ~0ull ? -1 : (int32_t)(m0 >> 32);
+    r.idx0 = m0 == ~0ull ? -1 : (int32_t)(m0 & 0xFFFFFFFFu);
+    r.dist1 = m1 == ~0ull ? -1 : (int32_t)(m1 >> 32);
+    r.idx1 = m1 == ~0ull ? -1 : (int32_t)(m1 & 0xFFFFFFFFu);
+    return r;
+}
+
+__device__ __forceinline__ void p2p_wait_world(const P2PView& pv)
+{
+    if (threadIdx.x < pv.world) {
+        const unsigned int* f = pv.flags[pv.rank] + (pv.epoch & 1u) * pv.world + threadIdx.x;
+        while ((int)(ld_acquire_sys(f) - pv.epoch) < 0) __nanosleep(200);
+    }
+    __syncthreads();
+}
+
+// called by every CTA that wrote results, after its last p2p_store; `writers` = number of such CTAs in the grid.  The
+// last of them publishes this rank's epoch to the world.  With pv.merge_out set (small query sets) that same CTA -- by
+// then the only one of the kernel still running -- also waits for the world's flags and does the merge, so one kernel
+// launch per rank computes, exchanges and reduces.
 __device__ __forceinline__ void p2p_publish(const P2PView& pv, unsigned int writers)
 {
+    __shared__ int s_final;
     __threadfence_system();     // this thread's peer stores are visible system-wide before the flag can be
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int prev = atomicAdd(pv.done, 1u);
-        if (prev == writers - 1) {
+        s_final = prev == writers - 1;
+        if (s_final) {
             *pv.done = 0;       // ready for the next launch (stream-ordered)
             __threadfence_system();
             for (int r = 0; r < pv.world; r++) st_release_sys(pv.flags[r] + (pv.epoch & 1u) * pv.world + pv.rank, pv.epoch);
         }
     }
+    if (pv.merge_out == nullptr) return;
+    __syncthreads();
+    if (!s_final) return;
+    p2p_wait_world(pv);
+    for (long long i = threadIdx.x; i < pv.merge_nq; i += blockDim.x) pv.merge_out[i] = p2p_merge_one(pv, i);
 }
 
 // grid = (query blocks, train splits, pairs).  partial is [pair][nsplit][nq_stride] (only touched when nsplit > 1); the
@@ -322,26 +360,9 @@ __global__ void __launch_bounds__(256) k_scatter_p2p(const hamx_top2* __restrict
 // Waits until every rank has published `epoch`, then merges the world's slots of this rank's gather buffer.
 __global__ void __launch_bounds__(256) k_merge_top2_p2p(long long nq, hamx_top2* __restrict__ out, const __grid_constant__ P2PView pv)
 {
-    if (threadIdx.x < pv.world) {
-        const unsigned int* f = pv.flags[pv.rank] + (pv.epoch & 1u) * pv.world + threadIdx.x;
-        while ((int)(ld_acquire_sys(f) - pv.epoch) < 0) __nanosleep(200);
-    }
-    __syncthreads();
+    p2p_wait_world(pv);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const hamx_top2* base = pv.gather[pv.rank] + (size_t)(pv.epoch & 1u) * pv.world * (size_t)pv.nq_max;
-    unsigned long long m0 = ~0ull, m1 = ~0ull;
-    for (int r = 0; r < pv.world; r++) {
-        const uint4 bits = __ldcg(reinterpret_cast<const uint4*>(base + (size_t)r * pv.nq_max + i));   // written by a peer: skip L1
-        top2_insert64(m0, m1, top2_key64((int32_t)bits.x, (int32_t)bits.y));
-        top2_insert64(m0, m1, top2_key64((int32_t)bits.z, (int32_t)bits.w));
-    }
-    hamx_top2 r;
-    r.dist0 = m0 == ~0ull ? -1 : (int32_t)(m0 >> 32);
-    r.idx0 = m0 == ~0ull ? -1 : (int32_t)(m0 & 0xFFFFFFFFu);
-    r.dist1 = m1 == ~0ull ? -1 : (int32_t)(m1 >> 32);
-    r.idx1 = m1 == ~0ull ? -1 : (int32_t)(m1 & 0xFFFFFFFFu);
-    out[i] = r;
+    if (i < nq) out[i] = p2p_merge_one(pv, i);
 }
 
 // parts is [nparts][nq]; lexicographic (distance, index) merge, identical to a single-device run over the union.
@@ -970,8 +991,14 @@ extern "C" int hamx_p2p_merge_dev(hamx_handle h, int64_t nq, hamx_top2* d_out)
 extern "C" int hamx_knn2_p2p_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
                                  hamx_top2* d_out)
 {
+    ORBX_REQUIRE(h != nullptr && d_out != nullptr, "hamx_knn2_p2p_dev: NULL argument");
+    // small query sets on a shard that one launch covers: the matching kernel also waits for the world and merges
+    const bool fuse = nq <= 16384 && nt > 0 && nt <= (1ll << HT_IDX_BITS) && h->p2p_buf != nullptr;
+    if (fuse) { h->pv.merge_out = d_out; h->pv.merge_nq = nq; }
     int rc = hamx_knn2_p2p_scatter_dev(h, d_q, nq, d_t, nt, train_offset);
-    if (rc) return rc;
+    h->pv.merge_out = nullptr;
+    h->pv.merge_nq = 0;
+    if (rc || fuse) return rc;
     return hamx_p2p_merge_dev(h, nq, d_out);
 }
 

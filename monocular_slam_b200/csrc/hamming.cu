@@ -336,7 +336,17 @@ k_hamming_knn2(const hamx_pair one, const hamx_pair* __restrict__ pairs, int til
     for (int k = 0; k < HT_QPT; k++) {
         if (qi[k] >= nq) continue;
         uint32_t m0 = HT_NONE, m1 = HT_NONE;
-        for (int s = 0; s < nsplit; s++) {
+        // the loads are independent (only the cheap min/max chain is serial): keep 8 in flight, or a merge over a few
+        // hundred splits costs a few hundred L2 round trips at the tail of the kernel
+        int s = 0;
+        for (; s + 8 <= nsplit; s += 8) {
+            uint2 p[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) p[u] = __ldcg(&partial[(size_t)(s + u) * nq_stride + qi[k]]);
+#pragma unroll
+            for (int u = 0; u < 8; u++) { top2_insert(m0, m1, p[u].x); top2_insert(m0, m1, p[u].y); }
+        }
+        for (; s < nsplit; s++) {
             uint2 p = __ldcg(&partial[(size_t)s * nq_stride + qi[k]]);
             top2_insert(m0, m1, p.x);
             top2_insert(m0, m1, p.y);

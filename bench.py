@@ -34,8 +34,8 @@ HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback, use
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml, else nvidia-smi)."""
 
-    def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+    def __init__(self, index, period=0.002):
+        self.index, self.samples, self.reasons, self.max_mhz, self.period = index, [], set(), None, period
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -61,7 +61,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.002)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         if self.nv is not None:
@@ -429,7 +429,7 @@ def run_ours(args, rank, world, local_rank):
         def step_ham():
             out["r"] = sm.knn2(q, t_shard, rank * nt_shard)
         ham_steps = max(2, min(args.steps, 3))
-        ham_sampler = ClockSampler(local_rank)
+        ham_sampler = ClockSampler(local_rank, period=0.02)
         ham_ms, _ = timed(step_ham, ham_steps, 1, ham_sampler)
         ham_ms = max_over_ranks(ham_ms) / ham_steps
         gpopc, _ = popc_peak(local_rank)

@@ -236,6 +236,47 @@ ORBX_API int hamx_p2p_merge_dev(hamx_handle h, int64_t nq, hamx_top2* d_out);
  * gpopc_per_s = 32-bit POPC results per second / 1e9, over the whole device. */
 ORBX_API int hamx_popc_peak(int device, double* gpopc_per_s, double* elapsed_ms);
 
+/* ------------------------------------------------------------------ outlier filter (computeFundamentalMatrix)
+ * The step after matchFeatures for every matched frame pair (src/CameraPoseEstimator.cpp:545-586, called at :291, :419):
+ *     F = findFundamentalMat(inputs1, inputs2, CV_FM_RANSAC, MAX_DISTANCE, CONFIDENCE, status);   (:563)
+ *     F = findFundamentalMat(inliers1, inliers2, CV_FM_8POINT);                                     (:585)
+ * One CUDA block per pair reproduces OpenCV's sequential RANSAC (same random sample sequence, same candidate order,
+ * same best-update and iteration-budget rule), so `status` is the mask OpenCV returns; F is the 8-point matrix of the
+ * inliers, scaled to F[8] = 1 (row-major double[9]; all zeros when there is no result).  Pairs with fewer than 15
+ * correspondences report no model (OpenCV switches to LMedS / the bare 7-point solver there, whose outcome is decided
+ * by rounding noise).  max_distance <= 0 means 3, confidence outside (0, 1) means 0.99, as in OpenCV; the reference passes
+ * MAX_DISTANCE = 3 and CONFIDENCE = 0.85 (src/ParamConfig.h:24-25). */
+typedef struct fmx_context* fmx_handle;
+ORBX_API int fmx_create(fmx_handle* out, int device);
+ORBX_API int fmx_destroy(fmx_handle h);
+ORBX_API int fmx_set_stream(fmx_handle h, void* cuda_stream);
+ORBX_API int fmx_synchronize(fmx_handle h);
+/* The reference's own signature for one pair: keypoints of both frames and the DMatch list (queryIdx -> kps1, trainIdx -> kps2).
+ * status gets nm bytes (0/1), F 9 doubles, *ninliers the number of set status bytes. */
+ORBX_API int fmx_compute_fundamental(fmx_handle h, const orbx_keypoint* kps1, int n1, const orbx_keypoint* kps2, int n2,
+                            const orbx_dmatch* matches, int nm, double max_distance, double confidence,
+                            uint8_t* status, double* F, int32_t* ninliers);
+/* npairs independent pairs in one launch.  pts1 / pts2: [npairs][cap][2] float (x, y) correspondences, counts[p] of them
+ * valid; status [npairs][cap], F [npairs][9], ninliers [npairs]. */
+ORBX_API int fmx_fundamental_batch(fmx_handle h, const float* pts1, const float* pts2, const int32_t* counts, int npairs, int cap,
+                          double max_distance, double confidence, uint8_t* status, double* F, int32_t* ninliers);
+/* Per pair {inliers, RANSAC iterations run, candidate matrices scored, 1 if F was produced} of the last fmx_fundamental_batch. */
+ORBX_API int fmx_last_info(fmx_handle h, int npairs, int32_t* info /* npairs * 4 */);
+/* Device-resident form (asynchronous on the handle's stream); d_info is [npairs][4] as fmx_last_info returns it. */
+ORBX_API int fmx_fundamental_batch_dev(fmx_handle h, const float* d_pts1, const float* d_pts2, const int32_t* d_counts, int npairs, int cap,
+                              double max_distance, double confidence, uint8_t* d_status, double* d_F, int32_t* d_info);
+/* Sequence mode on the device: pair f = (frame f, frame f-1) of a batch whose keypoints [nframes][cap] and consecutive-frame
+ * match lists [nframes][cap] / d_ngood[nframes] are device-resident (hamx_match_consecutive_dev); frame 0 pairs with
+ * d_prev_kps (the last frame of the previous batch) or, when that is NULL, reports no model.  status byte i of pair f
+ * belongs to d_good[f*cap + i]. */
+ORBX_API int fmx_filter_consecutive_dev(fmx_handle h, const orbx_keypoint* d_kps, const orbx_keypoint* d_prev_kps, int nframes, int cap,
+                               const orbx_dmatch* d_good, const int64_t* d_ngood, double max_distance, double confidence,
+                               uint8_t* d_status, double* d_F, int32_t* d_info);
+/* Host-buffer form for the batch last passed to orbx_extract_batch + orbx_match_consecutive on `h`: status [nframes][cap]
+ * (cap of that extract call), F [nframes][9], ninliers [nframes].  The matches never leave the device in between. */
+ORBX_API int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence,
+                            uint8_t* status, double* F, int32_t* ninliers);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,5 +6,5 @@ path over the GPUs of one box; synthetic.py generates the benchmark inputs.  Not
 algorithm on the CPU.
 """
 from ._lib import (DMATCH_DTYPE, FAST_SCORE, HARRIS_SCORE, KEYPOINT_DTYPE, LIB_PATH, TOP2_DTYPE, OrbxError, Params, build)  # noqa: F401
-from .orb import (NORM_HAMMING, ORB, BFMatcher, DataManager, FeatureExtractor, Features, Frame, ORB_create,  # noqa: F401
-                  OrbDescriptorExtractor, OrbFeatureDetector, match_features, popc_peak)
+from .orb import (NORM_HAMMING, ORB, BFMatcher, DataManager, FeatureExtractor, Features, Frame, FundamentalFilter,  # noqa: F401
+                  ORB_create, OrbDescriptorExtractor, OrbFeatureDetector, match_features, popc_peak)

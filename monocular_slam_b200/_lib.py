@@ -29,6 +29,8 @@ SYMBOLS = [
     "orbx_set_profiling", "orbx_read_profile", "orbx_submit_batch", "orbx_wait_batch", "orbx_batches_in_flight",
     "hamx_p2p_export", "hamx_p2p_import", "hamx_p2p_import_ptrs", "hamx_p2p_close", "hamx_knn2_p2p_dev",
     "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev", "orbx_set_input_channels", "orbx_pipeline_depth", "hamx_match_back_dev", "hamx_update_history_dev", "orbx_match_back", "orbx_host_alloc", "orbx_host_free",
+    "fmx_create", "fmx_destroy", "fmx_set_stream", "fmx_synchronize", "fmx_compute_fundamental", "fmx_fundamental_batch",
+    "fmx_last_info", "fmx_fundamental_batch_dev", "fmx_filter_consecutive_dev", "orbx_filter_consecutive",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -127,6 +129,16 @@ def lib():
     L.hamx_knn2_p2p_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64, vp]
     L.hamx_knn2_p2p_scatter_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64]
     L.hamx_p2p_merge_dev.argtypes = [vp, C.c_int64, vp]
+    L.fmx_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.fmx_destroy.argtypes = [vp]
+    L.fmx_set_stream.argtypes = [vp, vp]
+    L.fmx_synchronize.argtypes = [vp]
+    L.fmx_compute_fundamental.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_double, C.c_double, vp, dp, i32p]
+    L.fmx_fundamental_batch.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp]
+    L.fmx_last_info.argtypes = [vp, C.c_int, vp]
+    L.fmx_fundamental_batch_dev.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp]
+    L.fmx_filter_consecutive_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double, vp, vp, vp]
+    L.orbx_filter_consecutive.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp, vp]
     L.orbx_set_profiling.argtypes = [vp, C.c_int]
     L.orbx_read_profile.argtypes = [vp, fp, ip]
     _lib = L

@@ -1,0 +1,799 @@
+// fmat.cu -- fundamental-matrix outlier filter for batches of matched frame pairs (sm_100a).
+//
+// Replaces computeFundamentalMatrix (reference src/CameraPoseEstimator.cpp:545-586), the step that follows matchFeatures
+// for every matched frame pair (:291, :419):
+//     F = findFundamentalMat(inputs1, inputs2, CV_FM_RANSAC, MAX_DISTANCE, CONFIDENCE, status)     (:563)
+//     F = findFundamentalMat(inliers1, inliers2, CV_FM_8POINT)                                     (:585)
+// OpenCV's RANSAC is sequential: sample 7 points, solve the cubic (<= 3 candidate matrices), count inliers, keep the best,
+// shrink the iteration budget.  The result only depends on (a) the sample sequence, which is a function of the random
+// generator and the points alone, and (b) the inlier count of every candidate.  So one CTA per pair
+//   1. draws the samples of the next `chunk` iterations (one thread; cv::RNG + the duplicate / collinearity rejections),
+//   2. solves them in parallel (one thread per sample; Householder null space + cv::solveCubic, double precision),
+//   3. counts inliers of all candidates in parallel (one warp per candidate; OpenCV's double arithmetic rounded to float),
+//   4. replays OpenCV's sequential best-update / iteration-budget rule over the chunk in order (one thread),
+// until the budget is exhausted -- same status mask as the sequential loop.  Candidates that cannot beat the best count known
+// at the start of the chunk are abandoned early (their exact count is never needed).  The CTA then marks the inliers of the
+// winning matrix and runs the normalised 8-point algorithm on them (block reduction of the 9x9 normal matrix, warp-parallel
+// cyclic Jacobi for its smallest eigenvector, rank-2 projection).
+//
+// Double-precision arithmetic is IEEE, compiled without FMA contraction (build.sh: -fmad=false) like the x86 baseline build of
+// OpenCV, so candidate matrices agree with the CPU to rounding of the transcendental calls and the inlier tests are the same.
+#include "common.cuh"
+
+#include <float.h>
+#include <algorithm>
+
+namespace orbx {
+namespace {
+
+constexpr int FM_THREADS = 256;
+constexpr int FM_WARPS = FM_THREADS / 32;
+constexpr int FM_MAXCHUNK = 128;      // iterations solved + scored per round
+constexpr int FM_FIRSTCHUNK = 16;     // a short first round establishes a count that lets later rounds abandon bad candidates early
+constexpr int FM_MODEL_POINTS = 7;
+constexpr int FM_SMEM_POINTS = 9000;  // pairs with at most this many correspondences keep them in shared memory (16 B each)
+
+struct FmShared {
+    double models[FM_MAXCHUNK][27];
+    double best[9];
+    double red[FM_WARPS][48];
+    double A[81], V[81];
+    double norm[6];                   // c1x c1y s1 c2x c2y s2
+    unsigned long long rng;
+    int idx[FM_MAXCHUNK][FM_MODEL_POINTS];
+    int nmodels[FM_MAXCHUNK];
+    int count[FM_MAXCHUNK][3];
+    int iter, niters, maxgood, chunk, stop, have, next, ninl, ok8;
+};
+
+__device__ __forceinline__ unsigned rng_next(unsigned long long& s)
+{
+    s = (unsigned long long)(unsigned)s * 4164903690ULL + (unsigned)(s >> 32);     // cv::RNG, multiply with carry
+    return (unsigned)s;
+}
+
+__device__ bool have_collinear(const float2* p)
+{
+    const int i = FM_MODEL_POINTS - 1;
+    for (int j = 0; j < i; j++) {
+        const double dx1 = (double)p[j].x - (double)p[i].x, dy1 = (double)p[j].y - (double)p[i].y;
+        for (int k = 0; k < j; k++) {
+            const double dx2 = (double)p[k].x - (double)p[i].x, dy2 = (double)p[k].y - (double)p[i].y;
+            if (fabs(dx2 * dy1 - dy2 * dx1) <= (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) return true;
+        }
+    }
+    return false;
+}
+
+// RANSACPointSetRegistrator::getSubset: 7 distinct indices whose last point is not collinear with two earlier ones
+__device__ bool get_subset(const float2* P1, const float2* P2, int n, unsigned long long& rng, int* out)
+{
+    int idx[FM_MODEL_POINTS];
+    float2 a[FM_MODEL_POINTS], b[FM_MODEL_POINTS];
+    for (int iters = 0; iters < 10000; iters++) {
+        for (int i = 0; i < FM_MODEL_POINTS;) {
+            const int v = (int)(rng_next(rng) % (unsigned)n);
+            int j;
+            for (j = 0; j < i; j++)
+                if (v == idx[j]) break;
+            if (j < i) continue;
+            idx[i] = v; a[i] = P1[v]; b[i] = P2[v];
+            i++;
+        }
+        if (have_collinear(a) || have_collinear(b)) continue;
+        for (int i = 0; i < FM_MODEL_POINTS; i++) out[i] = idx[i];
+        return true;
+    }
+    return false;
+}
+
+// cv::solveCubic, real roots in OpenCV's order
+__device__ int solve_cubic(const double* c, double* x)
+{
+    double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+    if (a0 == 0) {
+        if (a1 == 0) {
+            if (a2 == 0) return a3 == 0 ? -1 : 0;
+            x[0] = -a3 / a2;
+            return 1;
+        }
+        double d = a2 * a2 - 4 * a1 * a3;
+        if (d < 0) return 0;
+        d = sqrt(d);
+        const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+        if (fabs(q1) > fabs(q2)) { x[0] = q1 / a1; x[1] = a3 / q1; }
+        else { x[0] = q2 / a1; x[1] = a3 / q2; }
+        return d > 0 ? 2 : 1;
+    }
+    a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
+    const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+    const double R = (a1 * (2 * a1 * a1 - 9 * a2) + 27 * a3) * (1. / 54);
+    const double Qcubed = Q * Q * Q;
+    const double d = Qcubed - R * R;
+    if (d > 0) {
+        const double theta = acos(R / sqrt(Qcubed)), sqrtQ = sqrt(Q);
+        const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+        x[0] = t0 * cos(t1) - t2;
+        x[1] = t0 * cos(t1 + (2. * 3.14159265358979323846 / 3)) - t2;
+        x[2] = t0 * cos(t1 + (4. * 3.14159265358979323846 / 3)) - t2;
+        return 3;
+    }
+    if (d == 0) {
+        if (R >= 0) { x[0] = -2 * pow(R, 1. / 3) - a1 / 3; x[1] = pow(R, 1. / 3) - a1 / 3; }
+        else { x[0] = 2 * pow(-R, 1. / 3) - a1 / 3; x[1] = -pow(-R, 1. / 3) - a1 / 3; }
+        return 2;
+    }
+    double e = pow(sqrt(-d) + fabs(R), 1. / 3);
+    if (R > 0) e = -e;
+    x[0] = (e + Q / e) - a1 * (1. / 3);
+    return 1;
+}
+
+// F <- T2' F T1 (T = [s 0 -s cx; 0 s -s cy; 0 0 1]), then scaled to F[8] = 1 when |F[8]| > FLT_EPSILON
+__device__ void denormalise(double* F, double c1x, double c1y, double s1, double c2x, double c2y, double s2)
+{
+    const double T1[9] = {s1, 0, -s1 * c1x, 0, s1, -s1 * c1y, 0, 0, 1}, T2[9] = {s2, 0, -s2 * c2x, 0, s2, -s2 * c2y, 0, 0, 1};
+    double G[9], H[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) s += T2[k * 3 + i] * F[k * 3 + j];
+            G[i * 3 + j] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) s += G[i * 3 + k] * T1[k * 3 + j];
+            H[i * 3 + j] = s;
+        }
+    double t = 1.;
+    if (fabs(H[8]) > (double)FLT_EPSILON) t = 1. / H[8];
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = H[i] * t;
+}
+
+// run7Point: candidate matrices of one 7-point sample
+__device__ int solve7(const float2* P1, const float2* P2, const int* idx, double* models)
+{
+    double m[9][7], v[7][9];       // transposed system and the Householder vectors (local memory)
+    double c1x = 0, c1y = 0, c2x = 0, c2y = 0, s1 = 0, s2 = 0;
+    float2 a[7], b[7];
+    for (int i = 0; i < 7; i++) {
+        a[i] = P1[idx[i]]; b[i] = P2[idx[i]];
+        c1x += a[i].x; c1y += a[i].y; c2x += b[i].x; c2y += b[i].y;
+    }
+    const double t = 1. / 7;
+    c1x *= t; c1y *= t; c2x *= t; c2y *= t;
+    for (int i = 0; i < 7; i++) {
+        const double dx1 = a[i].x - c1x, dy1 = a[i].y - c1y, dx2 = b[i].x - c2x, dy2 = b[i].y - c2y;
+        s1 += sqrt(dx1 * dx1 + dy1 * dy1);
+        s2 += sqrt(dx2 * dx2 + dy2 * dy2);
+    }
+    s1 *= t; s2 *= t;
+    if (s1 < (double)FLT_EPSILON || s2 < (double)FLT_EPSILON) return 0;
+    s1 = sqrt(2.) / s1; s2 = sqrt(2.) / s2;
+    for (int i = 0; i < 7; i++) {
+        const double x0 = (a[i].x - c1x) * s1, y0 = (a[i].y - c1y) * s1, x1 = (b[i].x - c2x) * s2, y1 = (b[i].y - c2y) * s2;
+        m[0][i] = x1 * x0; m[1][i] = x1 * y0; m[2][i] = x1;
+        m[3][i] = y1 * x0; m[4][i] = y1 * y0; m[5][i] = y1;
+        m[6][i] = x0; m[7][i] = y0; m[8][i] = 1;
+    }
+    // Householder QR of the 9x7 transposed system; the last two columns of Q span the null space
+    for (int k = 0; k < 7; k++) {
+        double norm = 0;
+        for (int i = k; i < 9; i++) norm += m[i][k] * m[i][k];
+        norm = sqrt(norm);
+        for (int i = 0; i < 9; i++) v[k][i] = 0;
+        if (norm == 0) continue;
+        const double alpha = m[k][k] > 0 ? -norm : norm;
+        for (int i = k; i < 9; i++) v[k][i] = m[i][k];
+        v[k][k] -= alpha;
+        double vn = 0;
+        for (int i = k; i < 9; i++) vn += v[k][i] * v[k][i];
+        if (vn == 0) continue;
+        vn = 1. / sqrt(vn);
+        for (int i = k; i < 9; i++) v[k][i] *= vn;
+        for (int c = k; c < 7; c++) {
+            double dot = 0;
+            for (int i = k; i < 9; i++) dot += v[k][i] * m[i][c];
+            for (int i = k; i < 9; i++) m[i][c] -= 2 * dot * v[k][i];
+        }
+    }
+    double f1[9], f2[9];
+    for (int j = 0; j < 2; j++) {
+        double* q = j ? f2 : f1;
+        for (int i = 0; i < 9; i++) q[i] = i == 7 + j;
+        for (int k = 6; k >= 0; k--) {
+            double dot = 0;
+            for (int i = k; i < 9; i++) dot += v[k][i] * q[i];
+            for (int i = k; i < 9; i++) q[i] -= 2 * dot * v[k][i];
+        }
+    }
+    // F = lambda f1 + (1 - lambda) f2, det F = 0: cubic in lambda
+    for (int i = 0; i < 9; i++) f1[i] -= f2[i];
+    double c[4], r[3] = {0, 0, 0};
+    double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
+    c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+    c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+           f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) - f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+           f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+           f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+    t0 = f1[4] * f1[8] - f1[5] * f1[7]; t1 = f1[3] * f1[8] - f1[5] * f1[6]; t2 = f1[3] * f1[7] - f1[4] * f1[6];
+    c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+    c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+           f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) - f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+           f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+           f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+    const int n = solve_cubic(c, r);
+    if (n < 1 || n > 3) return 0;
+    for (int k = 0; k < n; k++) {
+        double F[9];
+        double lambda = r[k], mu = 1.;
+        const double s = f1[8] * r[k] + f2[8];
+        if (fabs(s) > DBL_EPSILON) { mu = 1. / s; lambda *= mu; F[8] = 1.; }
+        else F[8] = 0.;
+        for (int i = 0; i < 8; i++) F[i] = f1[i] * lambda + f2[i] * mu;
+        denormalise(F, c1x, c1y, s1, c2x, c2y, s2);
+        for (int i = 0; i < 9; i++) models[9 * k + i] = F[i];
+    }
+    return n;
+}
+
+// FMEstimatorCallback::computeError for one correspondence, then findInliers' test (float compare)
+__device__ __forceinline__ bool is_inlier(const double* F, float2 p1, float2 p2, float t2)
+{
+    const double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
+    double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+    const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
+    a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+    const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
+    const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+    return __double2float_rn(e1 < e2 ? e2 : e1) <= t2;       // std::max(e1, e2)
+}
+
+// RANSACUpdateNumIters
+__device__ int update_num_iters(double p, double ep, int max_iters)
+{
+    p = fmin(fmax(p, 0.), 1.);
+    ep = fmin(fmax(ep, 0.), 1.);
+    double num = fmax(1. - p, DBL_MIN);
+    double denom = 1. - pow(1. - ep, (double)FM_MODEL_POINTS);
+    if (denom < DBL_MIN) return 0;
+    num = log(num);
+    denom = log(denom);
+    return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : __double2int_rn(num / denom);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sums `NV` per-thread values over the CTA; the totals land in sh.red[0][0..NV)
+template <int NV>
+__device__ void block_sum(FmShared& sh, const double* v)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) sh.red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < FM_WARPS; w++) s += sh.red[w][threadIdx.x];
+        sh.red[0][threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// cyclic Jacobi on the symmetric 9x9 sh.A (warp 0, lanes 0..8 own one row / column element each); eigenvectors = rows of sh.V
+__device__ void jacobi9_warp(FmShared& sh, int lane)
+{
+    for (int i = lane; i < 81; i += 32) sh.V[i] = (i / 9 == i % 9) ? 1. : 0.;
+    __syncwarp();
+    for (int sweep = 0; sweep < 40; sweep++) {
+        double off = 0, diag = 0;
+        for (int i = lane; i < 81; i += 32) {
+            const double x = sh.A[i] * sh.A[i];
+            if (i / 9 == i % 9) diag += x; else off += x;
+        }
+        off = warp_sum(off); diag = warp_sum(diag);
+        if (off == 0 || off <= 1e-36 * diag) break;
+        for (int p = 0; p < 8; p++)
+            for (int q = p + 1; q < 9; q++) {
+                const double apq = sh.A[p * 9 + q];
+                if (apq == 0) continue;                                    // uniform over the warp
+                const double theta = (sh.A[q * 9 + q] - sh.A[p * 9 + p]) / (2 * apq);
+                const double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double cs = 1. / sqrt(t * t + 1), sn = t * cs;
+                __syncwarp();
+                if (lane < 9) {
+                    const double akp = sh.A[lane * 9 + p], akq = sh.A[lane * 9 + q];
+                    sh.A[lane * 9 + p] = cs * akp - sn * akq;
+                    sh.A[lane * 9 + q] = sn * akp + cs * akq;
+                }
+                __syncwarp();
+                if (lane < 9) {
+                    const double apk = sh.A[p * 9 + lane], aqk = sh.A[q * 9 + lane];
+                    sh.A[p * 9 + lane] = cs * apk - sn * aqk;
+                    sh.A[q * 9 + lane] = sn * apk + cs * aqk;
+                    const double vpk = sh.V[p * 9 + lane], vqk = sh.V[q * 9 + lane];
+                    sh.V[p * 9 + lane] = cs * vpk - sn * vqk;
+                    sh.V[q * 9 + lane] = sn * vpk + cs * vqk;
+                }
+                __syncwarp();
+            }
+    }
+    __syncwarp();
+}
+
+// Jacobi on a symmetric 3x3 (one thread); returns the eigenvector of the smallest eigenvalue in vs
+__device__ void smallest_eigvec3(double* G, double* vs)
+{
+    double V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int sweep = 0; sweep < 40; sweep++) {
+        const double off = G[1] * G[1] + G[2] * G[2] + G[5] * G[5], diag = G[0] * G[0] + G[4] * G[4] + G[8] * G[8];
+        if (off == 0 || off <= 1e-36 * diag) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                const double apq = G[p * 3 + q];
+                if (apq == 0) continue;
+                const double theta = (G[q * 3 + q] - G[p * 3 + p]) / (2 * apq);
+                const double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double cs = 1. / sqrt(t * t + 1), sn = t * cs;
+                for (int k = 0; k < 3; k++) {
+                    const double akp = G[k * 3 + p], akq = G[k * 3 + q];
+                    G[k * 3 + p] = cs * akp - sn * akq; G[k * 3 + q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < 3; k++) {
+                    const double apk = G[p * 3 + k], aqk = G[q * 3 + k];
+                    G[p * 3 + k] = cs * apk - sn * aqk; G[q * 3 + k] = sn * apk + cs * aqk;
+                    const double vpk = V[p * 3 + k], vqk = V[q * 3 + k];
+                    V[p * 3 + k] = cs * vpk - sn * vqk; V[q * 3 + k] = sn * vpk + cs * vqk;
+                }
+            }
+    }
+    int m = 0;
+    if (G[4] < G[m * 4]) m = 1;
+    if (G[8] < G[m * 4]) m = 2;
+    for (int k = 0; k < 3; k++) vs[k] = V[m * 3 + k];
+}
+
+// One CTA per pair.  pts1/pts2: npairs x cap correspondences (float x, y); counts[pair] of them valid.
+// status: npairs x cap bytes (0/1); F: npairs x 9 doubles (zeros: no result); info: npairs x 4 ints
+// {inliers, iterations run, candidates scored, 0}.
+template <bool SMEM_POINTS>
+__global__ void __launch_bounds__(FM_THREADS, 2)
+k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ counts, int cap,
+            double thr, double conf, int max_iters, uint8_t* __restrict__ status, double* __restrict__ Fout, int32_t* __restrict__ info)
+{
+    extern __shared__ __align__(16) unsigned char fm_smem[];
+    FmShared& sh = *reinterpret_cast<FmShared*>(fm_smem);
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(counts[pair], cap);
+    const float2* P1 = pts1 + (size_t)pair * cap;
+    const float2* P2 = pts2 + (size_t)pair * cap;
+    uint8_t* st = status + (size_t)pair * cap;
+    double* Fo = Fout + (size_t)pair * 9;
+    int32_t* inf = info + (size_t)pair * 4;
+
+    for (int i = tid; i < cap; i += FM_THREADS) st[i] = 0;
+    if (tid < 9) Fo[tid] = 0.;
+    if (tid < 4) inf[tid] = 0;
+    // OpenCV: fewer than 7 points -> empty result; exactly 7 -> the 7-point solver alone; 8..14 -> LMedS, whose choice among
+    // exact-fit candidates is decided by rounding noise (median of <= 14 errors, 7 of them ~1e-25).  None of these is usable
+    // for pose estimation; the filter reports "no model" (0 inliers) for fewer than 15 correspondences.
+    if (n < 15) return;
+
+    if (SMEM_POINTS) {
+        float2* s1 = reinterpret_cast<float2*>(fm_smem + sizeof(FmShared));
+        float2* s2 = s1 + n;
+        for (int i = tid; i < n; i += FM_THREADS) { s1[i] = P1[i]; s2[i] = P2[i]; }
+        P1 = s1; P2 = s2;
+    }
+    if (thr <= 0) thr = 3;
+    if (conf < DBL_EPSILON || conf > 1 - DBL_EPSILON) conf = 0.99;
+    const float t2 = __double2float_rn(thr * thr);
+    if (tid == 0) {
+        sh.rng = 0xffffffffffffffffULL;
+        sh.iter = 0; sh.niters = max_iters; sh.maxgood = 0; sh.stop = 0; sh.have = 0; sh.ninl = 0; sh.ok8 = 0;
+    }
+    __syncthreads();
+
+    int scored = 0;
+    for (int round = 0;; round++) {
+        // ---- 1. samples of the next chunk of iterations
+        if (tid == 0) {
+            int chunk = min(round == 0 ? FM_FIRSTCHUNK : FM_MAXCHUNK, sh.niters - sh.iter);
+            unsigned long long rng = sh.rng;
+            for (int i = 0; i < chunk; i++)
+                if (!get_subset(P1, P2, n, rng, sh.idx[i])) { chunk = i; sh.stop = 1; break; }     // OpenCV leaves its loop here
+            sh.rng = rng;
+            sh.chunk = chunk;
+            sh.next = 0;
+        }
+        __syncthreads();
+        const int chunk = sh.chunk;
+        if (chunk == 0) break;
+        // ---- 2. one thread per sample: candidate matrices
+        if (tid < chunk) sh.nmodels[tid] = solve7(P1, P2, sh.idx[tid], sh.models[tid]);
+        __syncthreads();
+        // ---- 3. one warp per candidate: inlier count (abandoned as soon as it cannot exceed `bound`)
+        const int bound = max(sh.maxgood, FM_MODEL_POINTS - 1);
+        for (;;) {
+            int m = 0;
+            if (lane == 0) m = atomicAdd(&sh.next, 1);
+            m = __shfl_sync(0xffffffffu, m, 0);
+            if (m >= 3 * chunk) break;
+            const int it = m / 3, k = m - 3 * it;
+            if (k >= sh.nmodels[it]) continue;
+            double F[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) F[i] = sh.models[it][9 * k + i];
+            int cnt = 0;
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                const bool in = i < n && is_inlier(F, P1[i], P2[i], t2);
+                cnt += __popc(__ballot_sync(0xffffffffu, in));
+                if (cnt + max(n - base - 32, 0) <= bound) { cnt = 0; break; }
+            }
+            if (lane == 0) sh.count[it][k] = cnt;
+            scored++;
+        }
+        __syncthreads();
+        // ---- 4. OpenCV's sequential update rule over the chunk
+        if (tid == 0) {
+            int iter = sh.iter, niters = sh.niters, maxgood = sh.maxgood;
+            for (int i = 0; i < chunk && iter < niters; i++, iter++) {
+                for (int k = 0; k < sh.nmodels[i]; k++) {
+                    const int good = sh.count[i][k];
+                    if (good > max(maxgood, FM_MODEL_POINTS - 1)) {
+                        maxgood = good;
+                        for (int j = 0; j < 9; j++) sh.best[j] = sh.models[i][9 * k + j];
+                        sh.have = 1;
+                        niters = update_num_iters(conf, (double)(n - good) / n, niters);
+                    }
+                }
+            }
+            sh.iter = iter; sh.niters = niters; sh.maxgood = maxgood;
+            if (iter >= niters) sh.stop = 1;
+        }
+        __syncthreads();
+        if (sh.stop) break;
+    }
+    if (lane == 0 && scored) atomicAdd(&inf[2], scored);
+    if (!sh.have) {
+        if (tid == 0) inf[1] = sh.iter;
+        return;
+    }
+
+    // ---- status mask of the winning matrix
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = sh.best[i];
+    // ---- normalised 8-point on the inliers (run8Point).  Sums run in a fixed tree order, not OpenCV's sequential one.
+    double acc[4] = {0, 0, 0, 0};
+    int mine = 0;
+    for (int i = tid; i < n; i += FM_THREADS) {
+        const float2 a = P1[i], b = P2[i];
+        const bool in = is_inlier(F, a, b, t2);
+        st[i] = in;
+        if (in) { acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; mine++; }
+    }
+    {
+        double v[5] = {acc[0], acc[1], acc[2], acc[3], (double)mine};
+        block_sum<5>(sh, v);
+    }
+    const int k = (int)sh.red[0][4];
+    const double tk = 1. / k;
+    const double c1x = sh.red[0][0] * tk, c1y = sh.red[0][1] * tk, c2x = sh.red[0][2] * tk, c2y = sh.red[0][3] * tk;
+    if (tid == 0) { inf[0] = k; inf[1] = sh.iter; }
+    if (k < 8) return;                                   // 7 inliers: OpenCV's FM_8POINT call degenerates to the 7-point solver
+    {
+        double v[2] = {0, 0};
+        for (int i = tid; i < n; i += FM_THREADS) {
+            if (st[i]) {
+                const float2 a = P1[i], b = P2[i];
+                const double dx1 = a.x - c1x, dy1 = a.y - c1y, dx2 = b.x - c2x, dy2 = b.y - c2y;
+                v[0] += sqrt(dx1 * dx1 + dy1 * dy1);
+                v[1] += sqrt(dx2 * dx2 + dy2 * dy2);
+            }
+        }
+        block_sum<2>(sh, v);
+    }
+    double s1 = sh.red[0][0] * tk, s2 = sh.red[0][1] * tk;
+    if (s1 < (double)FLT_EPSILON || s2 < (double)FLT_EPSILON) return;
+    s1 = sqrt(2.) / s1; s2 = sqrt(2.) / s2;
+    {
+        double v[45];
+#pragma unroll
+        for (int i = 0; i < 45; i++) v[i] = 0;
+        for (int i = tid; i < n; i += FM_THREADS) {
+            if (st[i]) {
+                const float2 a = P1[i], b = P2[i];
+                const double x1 = (a.x - c1x) * s1, y1 = (a.y - c1y) * s1, x2 = (b.x - c2x) * s2, y2 = (b.y - c2y) * s2;
+                const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
+                int e = 0;
+#pragma unroll
+                for (int p = 0; p < 9; p++)
+#pragma unroll
+                    for (int q = p; q < 9; q++) v[e++] += r[p] * r[q];
+            }
+        }
+        block_sum<45>(sh, v);
+    }
+    if (tid < 45) {
+        int p = 0, e = tid;
+        while (e >= 9 - p) { e -= 9 - p; p++; }
+        const int q = p + e;
+        const double x = sh.red[0][tid];
+        sh.A[p * 9 + q] = x;
+        sh.A[q * 9 + p] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        jacobi9_warp(sh, lane);
+        if (lane == 0) {
+            int small = 0, m = 0;
+            for (int i = 0; i < 9; i++) {
+                if (fabs(sh.A[i * 10]) < DBL_EPSILON) small++;
+                if (sh.A[i * 10] < sh.A[m * 10]) m = i;
+            }
+            if (small < 2) {                                   // run8Point: the 8 largest eigenvalues must be non-zero
+                double F0[9], G[9], vs[3];
+                for (int i = 0; i < 9; i++) F0[i] = sh.V[m * 9 + i];
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++) {
+                        double s = 0;
+                        for (int c = 0; c < 3; c++) s += F0[c * 3 + a] * F0[c * 3 + b];
+                        G[a * 3 + b] = s;
+                    }
+                smallest_eigvec3(G, vs);
+                // rank 2: F0 - (F0 v) v' == U diag(w0, w1, 0) V'
+                for (int a = 0; a < 3; a++) {
+                    const double fv = F0[a * 3] * vs[0] + F0[a * 3 + 1] * vs[1] + F0[a * 3 + 2] * vs[2];
+                    for (int b = 0; b < 3; b++) F0[a * 3 + b] -= fv * vs[b];
+                }
+                denormalise(F0, c1x, c1y, s1, c2x, c2y, s2);
+                for (int i = 0; i < 9; i++) Fo[i] = F0[i];
+                inf[3] = 1;
+            }
+        }
+    }
+}
+
+// correspondences of consecutive frames from the device-resident keypoints and match lists of the sequence mode
+__global__ void k_fm_gather(const orbx_keypoint* __restrict__ kps, const orbx_keypoint* __restrict__ prev_kps, int cap,
+                            const orbx_dmatch* __restrict__ good, const long long* __restrict__ ngood,
+                            float2* __restrict__ pts1, float2* __restrict__ pts2, int32_t* __restrict__ counts)
+{
+    const int f = blockIdx.y;
+    const orbx_keypoint* kq = kps + (size_t)f * cap;
+    const orbx_keypoint* kt = f ? kps + (size_t)(f - 1) * cap : prev_kps;
+    const int n = kt ? (int)min((long long)cap, ngood[f]) : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[f] = n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const orbx_dmatch m = good[(size_t)f * cap + i];
+        const orbx_keypoint a = kq[m.query_idx], b = kt[m.train_idx];
+        pts1[(size_t)f * cap + i] = make_float2(a.x, a.y);
+        pts2[(size_t)f * cap + i] = make_float2(b.x, b.y);
+    }
+}
+
+}  // namespace
+}  // namespace orbx
+
+using namespace orbx;
+
+struct fmx_context {
+    int device;
+    cudaStream_t own_stream, stream;
+    float2* d_p1; size_t p1_bytes;
+    float2* d_p2; size_t p2_bytes;
+    int32_t* d_counts; size_t counts_bytes;
+    uint8_t* d_status; size_t status_bytes;
+    double* d_F; size_t F_bytes;
+    int32_t* d_info; size_t info_bytes;
+    int32_t* h_info; size_t h_info_n;
+    size_t smem_optin;
+};
+
+template <typename T>
+static int fm_grow(T** p, size_t* have, size_t want)
+{
+    if (*have >= want && *p) return ORBX_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *have = 0; }
+    const size_t bytes = align_up(want + want / 4, 256);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ORBX_E_ALLOC; }
+    *have = bytes;
+    return ORBX_OK;
+}
+
+extern "C" int fmx_create(fmx_handle* out, int device)
+{
+    ORBX_REQUIRE(out != nullptr, "fmx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { set_error("fmx_create: no CUDA device (%s); liborbx has no CPU fallback", cudaGetErrorString(e)); return ORBX_E_CUDA; }
+    ORBX_REQUIRE(device >= 0 && device < ndev, "fmx_create: device %d out of range [0,%d)", device, ndev);
+    ORBX_CUDA(cudaSetDevice(device));
+    fmx_context* h = new fmx_context();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    int optin = 0;
+    ORBX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    h->smem_optin = (size_t)optin;
+    ORBX_CUDA(cudaFuncSetAttribute(k_fm_ransac<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    ORBX_CUDA(cudaFuncSetAttribute(k_fm_ransac<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FmShared)));
+    *out = h;
+    return ORBX_OK;
+}
+
+extern "C" int fmx_destroy(fmx_handle h)
+{
+    if (!h) return ORBX_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_counts); cudaFree(h->d_status); cudaFree(h->d_F); cudaFree(h->d_info);
+    if (h->h_info) cudaFreeHost(h->h_info);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return ORBX_OK;
+}
+
+extern "C" int fmx_set_stream(fmx_handle h, void* cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr, "fmx_set_stream: NULL handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ORBX_OK;
+}
+
+extern "C" int fmx_synchronize(fmx_handle h)
+{
+    ORBX_REQUIRE(h != nullptr, "fmx_synchronize: NULL handle");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+// max_count: the largest counts[] value if the caller knows it (sizes the shared-memory copy of the points), else `cap`
+static int fm_launch(fmx_handle h, const float* d_pts1, const float* d_pts2, const int32_t* d_counts, int npairs, int cap, int max_count,
+                     double max_distance, double confidence, uint8_t* d_status, double* d_F, int32_t* d_info)
+{
+    if (npairs == 0) return ORBX_OK;
+    const bool in_smem = max_count <= FM_SMEM_POINTS && sizeof(FmShared) + (size_t)max_count * 16 <= h->smem_optin;
+    const size_t smem = sizeof(FmShared) + (in_smem ? (size_t)max_count * 16 : 0);
+    if (in_smem)
+        k_fm_ransac<true><<<npairs, FM_THREADS, smem, h->stream>>>((const float2*)d_pts1, (const float2*)d_pts2, d_counts, cap, max_distance,
+                                                                    confidence, 1000, d_status, d_F, d_info);
+    else
+        k_fm_ransac<false><<<npairs, FM_THREADS, smem, h->stream>>>((const float2*)d_pts1, (const float2*)d_pts2, d_counts, cap, max_distance,
+                                                                     confidence, 1000, d_status, d_F, d_info);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int fmx_fundamental_batch_dev(fmx_handle h, const float* d_pts1, const float* d_pts2, const int32_t* d_counts, int npairs, int cap,
+                                         double max_distance, double confidence, uint8_t* d_status, double* d_F, int32_t* d_info)
+{
+    ORBX_REQUIRE(h != nullptr, "fmx_fundamental_batch_dev: NULL handle");
+    ORBX_REQUIRE(npairs >= 0 && cap >= 1, "fmx_fundamental_batch_dev: npairs %d / cap %d out of range", npairs, cap);
+    ORBX_REQUIRE(d_pts1 && d_pts2 && d_counts && d_status && d_F && d_info, "fmx_fundamental_batch_dev: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    return fm_launch(h, d_pts1, d_pts2, d_counts, npairs, cap, cap, max_distance, confidence, d_status, d_F, d_info);
+}
+
+extern "C" int fmx_fundamental_batch(fmx_handle h, const float* pts1, const float* pts2, const int32_t* counts, int npairs, int cap,
+                                     double max_distance, double confidence, uint8_t* status, double* F, int32_t* ninliers)
+{
+    ORBX_REQUIRE(h != nullptr, "fmx_fundamental_batch: NULL handle");
+    ORBX_REQUIRE(npairs >= 0 && cap >= 1, "fmx_fundamental_batch: npairs %d / cap %d out of range", npairs, cap);
+    if (npairs == 0) return ORBX_OK;
+    ORBX_REQUIRE(pts1 && pts2 && counts && status && F && ninliers, "fmx_fundamental_batch: NULL pointer");
+    int max_count = 0;
+    for (int i = 0; i < npairs; i++) {
+        ORBX_REQUIRE(counts[i] >= 0 && counts[i] <= cap, "fmx_fundamental_batch: counts[%d] = %d outside [0, cap = %d]", i, counts[i], cap);
+        max_count = std::max(max_count, counts[i]);
+    }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t np = (size_t)npairs, pts_bytes = np * cap * sizeof(float2);
+    int rc = fm_grow(&h->d_p1, &h->p1_bytes, pts_bytes);
+    if (!rc) rc = fm_grow(&h->d_p2, &h->p2_bytes, pts_bytes);
+    if (!rc) rc = fm_grow(&h->d_counts, &h->counts_bytes, np * sizeof(int32_t));
+    if (!rc) rc = fm_grow(&h->d_status, &h->status_bytes, np * cap);
+    if (!rc) rc = fm_grow(&h->d_F, &h->F_bytes, np * 9 * sizeof(double));
+    if (!rc) rc = fm_grow(&h->d_info, &h->info_bytes, np * 4 * sizeof(int32_t));
+    if (rc) return rc;
+    if (h->h_info_n < np * 4) {
+        if (h->h_info) cudaFreeHost(h->h_info);
+        h->h_info = nullptr; h->h_info_n = 0;
+        ORBX_CUDA(cudaMallocHost((void**)&h->h_info, np * 4 * sizeof(int32_t) * 2));
+        h->h_info_n = np * 8;
+    }
+    ORBX_CUDA(cudaMemcpyAsync(h->d_p1, pts1, pts_bytes, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_p2, pts2, pts_bytes, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_counts, counts, np * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    rc = fm_launch(h, (const float*)h->d_p1, (const float*)h->d_p2, h->d_counts, npairs, cap, std::max(max_count, 1), max_distance, confidence,
+                   h->d_status, h->d_F, h->d_info);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(status, h->d_status, np * cap, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(F, h->d_F, np * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->h_info, h->d_info, np * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < npairs; i++) ninliers[i] = h->h_info[4 * i];
+    return ORBX_OK;
+}
+
+extern "C" int fmx_last_info(fmx_handle h, int npairs, int32_t* info)
+{
+    ORBX_REQUIRE(h != nullptr && info != nullptr, "fmx_last_info: NULL argument");
+    ORBX_REQUIRE(npairs >= 0 && (size_t)npairs * 4 <= h->h_info_n, "fmx_last_info: npairs %d exceeds the last batch", npairs);
+    memcpy(info, h->h_info, (size_t)npairs * 4 * sizeof(int32_t));
+    return ORBX_OK;
+}
+
+extern "C" int fmx_compute_fundamental(fmx_handle h, const orbx_keypoint* kps1, int n1, const orbx_keypoint* kps2, int n2,
+                                       const orbx_dmatch* matches, int nm, double max_distance, double confidence, uint8_t* status, double* F,
+                                       int32_t* ninliers)
+{
+    ORBX_REQUIRE(h != nullptr, "fmx_compute_fundamental: NULL handle");
+    ORBX_REQUIRE(nm >= 0 && n1 >= 0 && n2 >= 0, "fmx_compute_fundamental: negative size");
+    ORBX_REQUIRE(F && ninliers && (nm == 0 || (kps1 && kps2 && matches && status)), "fmx_compute_fundamental: NULL pointer");
+    *ninliers = 0;
+    for (int i = 0; i < 9; i++) F[i] = 0.;
+    if (nm == 0) return ORBX_OK;
+    float* pts = nullptr;
+    ORBX_CUDA(cudaMallocHost((void**)&pts, (size_t)nm * 4 * sizeof(float)));
+    float* a = pts;
+    float* b = pts + 2 * (size_t)nm;
+    for (int i = 0; i < nm; i++) {
+        const int q = matches[i].query_idx, t = matches[i].train_idx;
+        if (q < 0 || q >= n1 || t < 0 || t >= n2) {
+            cudaFreeHost(pts);
+            set_error("fmx_compute_fundamental: match %d indexes (%d, %d) outside (%d, %d) keypoints", i, q, t, n1, n2);
+            return ORBX_E_INVALID;
+        }
+        a[2 * i] = kps1[q].x; a[2 * i + 1] = kps1[q].y;
+        b[2 * i] = kps2[t].x; b[2 * i + 1] = kps2[t].y;
+    }
+    const int32_t count = nm;
+    const int rc = fmx_fundamental_batch(h, a, b, &count, 1, nm, max_distance, confidence, status, F, ninliers);
+    cudaFreeHost(pts);
+    return rc;
+}
+
+extern "C" int fmx_filter_consecutive_dev(fmx_handle h, const orbx_keypoint* d_kps, const orbx_keypoint* d_prev_kps, int nframes, int cap,
+                                          const orbx_dmatch* d_good, const int64_t* d_ngood, double max_distance, double confidence,
+                                          uint8_t* d_status, double* d_F, int32_t* d_info)
+{
+    ORBX_REQUIRE(h != nullptr, "fmx_filter_consecutive_dev: NULL handle");
+    ORBX_REQUIRE(nframes >= 0 && cap >= 1, "fmx_filter_consecutive_dev: nframes %d / cap %d out of range", nframes, cap);
+    if (nframes == 0) return ORBX_OK;
+    ORBX_REQUIRE(d_kps && d_good && d_ngood && d_status && d_F && d_info, "fmx_filter_consecutive_dev: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t np = (size_t)nframes, pts_bytes = np * cap * sizeof(float2);
+    int rc = fm_grow(&h->d_p1, &h->p1_bytes, pts_bytes);
+    if (!rc) rc = fm_grow(&h->d_p2, &h->p2_bytes, pts_bytes);
+    if (!rc) rc = fm_grow(&h->d_counts, &h->counts_bytes, np * sizeof(int32_t));
+    if (rc) return rc;
+    k_fm_gather<<<dim3(div_up(cap, 256 * 2), nframes), 256, 0, h->stream>>>(d_kps, d_prev_kps, cap, d_good, (const long long*)d_ngood,
+                                                                           h->d_p1, h->d_p2, h->d_counts);
+    ORBX_CUDA(cudaGetLastError());
+    return fm_launch(h, (const float*)h->d_p1, (const float*)h->d_p2, h->d_counts, nframes, cap, cap, max_distance, confidence, d_status, d_F,
+                     d_info);
+}

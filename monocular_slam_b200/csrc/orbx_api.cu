@@ -94,6 +94,12 @@ struct orbx_context {
     orbx_dmatch* d_good;
     int64_t* d_ngood;
     int64_t* h_ngood;
+    // orbx_filter_consecutive: keypoints of the last frame of the previous batch (double-buffered, allocated on first match)
+    orbx_keypoint* d_prev_kps[2];
+    int prev_kps_cur;
+    const orbx_keypoint* filter_prev_kps;     // what frame 0 of the batch last matched pairs with (NULL: nothing)
+    int filter_nframes, filter_cap;           // batch orbx_match_consecutive last ran on (0: none)
+    uint8_t* d_fstatus; double* d_fF; int32_t* d_finfo; int32_t* h_finfo;
     // orbx_match_back: history of the last ORBX_MAX_BACK frames (double-buffered), allocated on first use
     uint8_t* d_hist[2];
     int32_t* d_hist_counts[2];
@@ -416,6 +422,8 @@ extern "C" int orbx_destroy(orbx_handle h)
     cudaFree(h->d_slots); cudaFree(h->d_cand); cudaFree(h->d_surv); cudaFree(h->d_sel); cudaFree(h->d_ctr);
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_tab);
     cudaFree(h->d_prev_desc); cudaFree(h->d_prev_count); cudaFree(h->d_good); cudaFree(h->d_ngood); cudaFree(h->d_bgr);
+    cudaFree(h->d_prev_kps[0]); cudaFree(h->d_prev_kps[1]); cudaFree(h->d_fstatus); cudaFree(h->d_fF); cudaFree(h->d_finfo);
+    if (h->h_finfo) cudaFreeHost(h->h_finfo);
     cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]); cudaFree(h->d_hist_counts[0]); cudaFree(h->d_hist_counts[1]);
     cudaFree(h->d_good_back); cudaFree(h->d_ngood_back);
     if (h->h_ngood_back) cudaFreeHost(h->h_ngood_back);
@@ -711,6 +719,7 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
         rc = run_extract_single(h, mode, dcap);
         if (rc) return rc;
         h->last_nframes = (mode & ORBX_DO_DESC) ? 1 : 0;
+        h->filter_nframes = 0;
         h->last_cap = dcap;
         ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, offsetof(FrameCounters, hist), cudaMemcpyDeviceToHost, h->stream));
         ORBX_CUDA(cudaMemcpyAsync(out, h->d_kps, (size_t)dcap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->stream));
@@ -741,6 +750,7 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
         if (rc) return rc;
     }
     h->last_nframes = (mode & ORBX_DO_DESC) ? nframes : 0;
+    h->filter_nframes = 0;
     h->last_cap = dcap;
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
@@ -894,12 +904,49 @@ extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio,
     if (rc) return rc;
     ORBX_CUDA(cudaMemcpyAsync(h->h_ngood, h->d_ngood, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(good, h->d_good, (size_t)n * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
-    // keep the last frame's descriptors for the next batch
+    // keep the last frame's descriptors (and keypoints, for orbx_filter_consecutive) for the next batch
     ORBX_CUDA(cudaMemcpyAsync(h->d_prev_desc, h->d_desc + (size_t)(n - 1) * cap * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(h->d_prev_count, h->d_counts + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    if (!h->d_prev_kps[0])
+        for (int i = 0; i < 2; i++) ORBX_CUDA(cudaMalloc((void**)&h->d_prev_kps[i], (size_t)h->dev_cap * sizeof(orbx_keypoint) + 256));
+    h->filter_prev_kps = h->have_prev ? h->d_prev_kps[h->prev_kps_cur] : nullptr;
+    h->prev_kps_cur ^= 1;
+    ORBX_CUDA(cudaMemcpyAsync(h->d_prev_kps[h->prev_kps_cur], h->d_kps + (size_t)(n - 1) * cap, (size_t)cap * sizeof(orbx_keypoint),
+                              cudaMemcpyDeviceToDevice, h->stream));
+    h->filter_nframes = n;
+    h->filter_cap = cap;
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     h->have_prev = true;
     for (int f = 0; f < n; f++) ngood[f] = h->h_ngood[f];
+    return ORBX_OK;
+}
+
+extern "C" int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence, uint8_t* status, double* F,
+                                       int32_t* ninliers)
+{
+    ORBX_REQUIRE(h != nullptr && fm != nullptr, "orbx_filter_consecutive: NULL handle");
+    ORBX_REQUIRE(status && F && ninliers, "orbx_filter_consecutive: NULL pointer");
+    ORBX_REQUIRE(h->filter_nframes >= 1, "orbx_filter_consecutive: orbx_match_consecutive has not run on this handle's last batch");
+    { int rc_ = require_idle(h, "orbx_filter_consecutive"); if (rc_) return rc_; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int n = h->filter_nframes, cap = h->filter_cap;
+    if (!h->d_fstatus) {
+        ORBX_CUDA(cudaMalloc((void**)&h->d_fstatus, (size_t)h->max_batch * h->dev_cap + 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_fF, (size_t)h->max_batch * 9 * sizeof(double) + 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_finfo, (size_t)h->max_batch * 4 * sizeof(int32_t) + 256));
+        ORBX_CUDA(cudaMallocHost((void**)&h->h_finfo, (size_t)h->max_batch * 4 * sizeof(int32_t)));
+    }
+    int rc = fmx_set_stream(fm, (void*)h->stream);
+    if (rc) return rc;
+    rc = fmx_filter_consecutive_dev(fm, h->d_kps, h->filter_prev_kps, n, cap, h->d_good, h->d_ngood, max_distance, confidence,
+                                    h->d_fstatus, h->d_fF, h->d_finfo);
+    fmx_set_stream(fm, nullptr);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus, (size_t)n * cap, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->h_finfo, h->d_finfo, (size_t)n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < n; f++) ninliers[f] = h->h_finfo[4 * f];
     return ORBX_OK;
 }
 
@@ -1005,6 +1052,7 @@ extern "C" int orbx_submit_batch(orbx_handle h, hamx_handle m, const uint8_t* co
     L.counts = counts;
     L.ngood = m ? ngood : nullptr;
     h->last_nframes = 0;            // orbx_match_consecutive pairs with orbx_extract_batch only
+    h->filter_nframes = 0;
     h->lane_next = (li + 1) % ORBX_LANES;
     return ORBX_OK;
 }

@@ -184,6 +184,17 @@ class ORB:
                                                 ngood.ctypes.data_as(C.POINTER(C.c_int64))))
         return good, ngood
 
+    def filter_consecutive(self, fundamental, cap, nframes, max_distance=3.0, confidence=0.85):
+        """computeFundamentalMatrix (src/CameraPoseEstimator.cpp:545-586) for every (frame f, frame f-1) pair of the batch
+        match_consecutive just ran on; the match lists stay on the device in between.
+        Returns (status[nframes, cap] uint8 aligned with good[f], F[nframes, 3, 3], ninliers[nframes])."""
+        status = np.zeros((nframes, cap), np.uint8)
+        F = np.zeros((nframes, 3, 3), np.float64)
+        ninl = np.zeros(nframes, np.int32)
+        check(_lib.lib().orbx_filter_consecutive(self._h, fundamental._h, float(max_distance), float(confidence),
+                                                 status.ctypes.data, F.ctypes.data, ninl.ctypes.data))
+        return status, F, ninl
+
     # -- pipelined sequence mode: pipeline_depth() batches in flight (upload / kernels / download overlap across batches)
     def submit_batch(self, frames, matcher, ratio, out):
         """Enqueue extraction (+ consecutive-frame matching when ``matcher`` is given) of a batch and return at once.
@@ -392,6 +403,77 @@ def match_features(descriptors1, descriptors2, ratio=0.8, device=0):
     if m is None:
         m = _default_matcher[device] = BFMatcher(NORM_HAMMING, False, device=device)
     return m.match_ratio(descriptors1, descriptors2, ratio)
+
+
+MAX_DISTANCE, CONFIDENCE = 3.0, 0.85      # src/ParamConfig.h:24-25
+
+
+class FundamentalFilter:
+    """The outlier filter CameraPoseEstimator runs after matchFeatures: findFundamentalMat(FM_RANSAC) for the status mask,
+    then findFundamentalMat(FM_8POINT) on the inliers (computeFundamentalMatrix, src/CameraPoseEstimator.cpp:545-586)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self.device = device
+        check(_lib.lib().fmx_create(C.byref(self._h), device))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().fmx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(_lib.lib().fmx_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(_lib.lib().fmx_synchronize(self._h))
+
+    def compute_fundamental(self, keypoints1, keypoints2, matches, max_distance=MAX_DISTANCE, confidence=CONFIDENCE):
+        """One pair, the reference's arguments: KEYPOINT_DTYPE arrays of both frames and a DMATCH_DTYPE list
+        (queryIdx -> keypoints1, trainIdx -> keypoints2).  Returns (F 3x3 (zeros: none), status uint8[len(matches)], ninliers)."""
+        k1 = np.ascontiguousarray(keypoints1, _lib.KEYPOINT_DTYPE)
+        k2 = np.ascontiguousarray(keypoints2, _lib.KEYPOINT_DTYPE)
+        m = np.ascontiguousarray(matches, DMATCH_DTYPE)
+        status = np.zeros(max(len(m), 1), np.uint8)
+        F = np.zeros(9, np.float64)
+        ninl = C.c_int32(0)
+        check(_lib.lib().fmx_compute_fundamental(self._h, k1.ctypes.data, len(k1), k2.ctypes.data, len(k2), m.ctypes.data, len(m),
+                                                 float(max_distance), float(confidence), status.ctypes.data,
+                                                 F.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ninl)))
+        return F.reshape(3, 3), status[:len(m)], int(ninl.value)
+
+    def find_batch(self, pts1, pts2, counts, max_distance=MAX_DISTANCE, confidence=CONFIDENCE):
+        """npairs independent pairs: pts1 / pts2 float32 [npairs, cap, 2], counts int32 [npairs].
+        Returns (status[npairs, cap] uint8, F[npairs, 3, 3], ninliers[npairs] int32)."""
+        p1 = np.ascontiguousarray(pts1, np.float32)
+        p2 = np.ascontiguousarray(pts2, np.float32)
+        cnt = np.ascontiguousarray(counts, np.int32)
+        npairs, cap = p1.shape[0], p1.shape[1]
+        if p1.shape != p2.shape or p1.ndim != 3 or p1.shape[2] != 2 or cnt.shape != (npairs,):
+            raise ValueError("pts1 / pts2 must be [npairs, cap, 2] and counts [npairs]")
+        status = np.zeros((npairs, cap), np.uint8)
+        F = np.zeros((npairs, 3, 3), np.float64)
+        ninl = np.zeros(npairs, np.int32)
+        check(_lib.lib().fmx_fundamental_batch(self._h, p1.ctypes.data, p2.ctypes.data, cnt.ctypes.data, npairs, cap,
+                                               float(max_distance), float(confidence), status.ctypes.data, F.ctypes.data,
+                                               ninl.ctypes.data))
+        return status, F, ninl
+
+    def last_info(self, npairs):
+        """Per pair of the last find_batch: [inliers, RANSAC iterations run, candidate matrices scored, F produced]."""
+        info = np.zeros((npairs, 4), np.int32)
+        check(_lib.lib().fmx_last_info(self._h, npairs, info.ctypes.data))
+        return info
+
+    def find_batch_dev(self, d_pts1, d_pts2, d_counts, npairs, cap, max_distance, confidence, d_status, d_F, d_info):
+        check(_lib.lib().fmx_fundamental_batch_dev(self._h, d_pts1, d_pts2, d_counts, npairs, cap, float(max_distance),
+                                                   float(confidence), d_status, d_F, d_info))
 
 
 def popc_peak(device=0):

@@ -94,3 +94,26 @@ def planted_queries(seed, train, nq, frac=0.5, max_flips=20):
 def bgr_frame(seed, w, h):
     """A 3-channel (BGR, 8UC3) frame: three differently seeded gray frames as channels, so the gray conversion matters."""
     return np.ascontiguousarray(np.stack([frame(seed + 101 * c, w, h, nrect=120) for c in range(3)], axis=2))
+
+
+def two_view_matches(seed, n, inlier_ratio=0.7, noise=0.5, size=(1920, 1080)):
+    """Matched keypoint positions of a synthetic two-view pair: ``n`` 3-D points seen by two cameras (small rotation +
+    translation, focal 900 px), Gaussian pixel noise, and a fraction ``1 - inlier_ratio`` of the second view replaced by
+    uniform positions (wrong matches).  Returns float32 (pts1[n, 2], pts2[n, 2]) -- the `inputs1` / `inputs2` arrays
+    computeFundamentalMatrix builds (src/CameraPoseEstimator.cpp:555-560)."""
+    r = np.random.default_rng(seed)
+    w, h = size
+    X = np.c_[r.uniform(-4, 4, n), r.uniform(-3, 3, n), r.uniform(4, 12, n)]
+    K = np.array([[900.0, 0, w / 2], [0, 900.0, h / 2], [0, 0, 1]])
+    a = 0.05
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    t = np.array([0.4, 0.05, 0.1])
+    p1 = (K @ X.T).T
+    p1 = p1[:, :2] / p1[:, 2:]
+    p2 = (K @ (R @ X.T + t[:, None])).T
+    p2 = p2[:, :2] / p2[:, 2:]
+    p1 += r.normal(0, noise, p1.shape)
+    p2 += r.normal(0, noise, p2.shape)
+    bad = r.random(n) > inlier_ratio
+    p2[bad] = np.c_[r.uniform(0, w, bad.sum()), r.uniform(0, h, bad.sum())]
+    return p1.astype(np.float32), p2.astype(np.float32)

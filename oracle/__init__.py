@@ -44,8 +44,8 @@ class Params(C.Structure):
 
 def build(force=False):
     """Compile liborb_oracle.so with the committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "orb_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "fmat_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -85,6 +85,15 @@ def lib():
         L.orc_bgr2gray.restype = None
         L.orc_ratio_test.restype = C.c_int64
         L.orc_ratio_test.argtypes = [i32p, i32p, C.c_int64, C.c_float, i32p, i32p, i32p]
+        f64p = C.POINTER(C.c_double)
+        L.orc_solve_cubic.argtypes = [f64p, f64p]
+        L.orc_fm_7point.argtypes = [f32p, f32p, f64p]
+        L.orc_fm_8point.argtypes = [f32p, f32p, C.c_int, f64p]
+        L.orc_fm_errors.argtypes = [f32p, f32p, C.c_int, f64p, f32p]
+        L.orc_fm_errors.restype = None
+        L.orc_fm_ransac.argtypes = [f32p, f32p, C.c_int, C.c_double, C.c_double, C.c_int, u8p, f64p, i32p]
+        L.orc_compute_fundamental.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                              u8p, f64p]
         _lib = L
     return _lib
 
@@ -262,3 +271,79 @@ def match_features(d1, d2, ratio=0.8):
     """matchFeatures(descriptors1, descriptors2, matches, ratio) of src/CameraPoseEstimator.cpp:200-213."""
     idx, dist = knn2(d1, d2)
     return ratio_test(idx, dist, ratio)
+
+
+# ---- fundamental-matrix outlier filter (fmat_oracle.c) ----
+
+def _f32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _f64(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _pts(p):
+    p = np.ascontiguousarray(p, np.float32).reshape(-1, 2)
+    return p
+
+
+def solve_cubic(coeffs):
+    """cv::solveCubic: real roots in OpenCV's order."""
+    c = np.ascontiguousarray(coeffs, np.float64)
+    x = np.zeros(3)
+    n = lib().orc_solve_cubic(_f64(c), _f64(x))
+    return x[:max(n, 0)].copy()
+
+
+def fm_7point(m1, m2):
+    """run7Point on 7 correspondences: (k, 3, 3) candidate matrices, k <= 3."""
+    m1, m2 = _pts(m1), _pts(m2)
+    assert len(m1) == 7 and len(m2) == 7
+    out = np.zeros(27)
+    n = lib().orc_fm_7point(_f32(m1), _f32(m2), _f64(out))
+    return out[:9 * n].reshape(n, 3, 3).copy()
+
+
+def fm_8point(m1, m2):
+    """findFundamentalMat(m1, m2, FM_8POINT) (src/CameraPoseEstimator.cpp:585): 3x3 or None."""
+    m1, m2 = _pts(m1), _pts(m2)
+    F = np.zeros(9)
+    ok = lib().orc_fm_8point(_f32(m1), _f32(m2), len(m1), _f64(F))
+    return F.reshape(3, 3) if ok else None
+
+
+def fm_errors(m1, m2, F):
+    m1, m2 = _pts(m1), _pts(m2)
+    F = np.ascontiguousarray(F, np.float64).reshape(9)
+    err = np.empty(len(m1), np.float32)
+    lib().orc_fm_errors(_f32(m1), _f32(m2), len(m1), _f64(F), _f32(err))
+    return err
+
+
+def fm_ransac(m1, m2, thr=3.0, conf=0.85, max_iters=1000):
+    """findFundamentalMat(m1, m2, FM_RANSAC, thr, conf, status) (src/CameraPoseEstimator.cpp:563) for >= 8 points:
+    (F or None, mask uint8[n], iterations run)."""
+    m1, m2 = _pts(m1), _pts(m2)
+    n = len(m1)
+    assert n >= 8
+    mask = np.zeros(n, np.uint8)
+    F = np.zeros(9)
+    info = np.zeros(2, np.int32)
+    ok = lib().orc_fm_ransac(_f32(m1), _f32(m2), n, float(thr), float(conf), int(max_iters), _u8(mask), _f64(F), _i32(info))
+    return (F.reshape(3, 3) if ok else None), mask, int(info[0])
+
+
+def compute_fundamental(pos1, pos2, matches, thr=3.0, conf=0.85):
+    """computeFundamentalMatrix (src/CameraPoseEstimator.cpp:545-586): pos1/pos2 float32 (n, 2) keypoint positions,
+    matches a structured/int array of (query_idx, train_idx, img_idx, distance) rows (16 bytes each).
+    Returns (F 3x3 (zeros if none), status uint8[len(matches)], ninliers)."""
+    pos1, pos2 = _pts(pos1), _pts(pos2)
+    matches = np.ascontiguousarray(matches)
+    assert matches.dtype.itemsize * (matches.shape[1] if matches.ndim == 2 else 1) == 16
+    nm = len(matches)
+    status = np.zeros(max(nm, 1), np.uint8)
+    F = np.zeros(9)
+    ninl = lib().orc_compute_fundamental(_f32(pos1), 2, _f32(pos2), 2, matches.ctypes.data, nm, float(thr), float(conf),
+                                         _u8(status), _f64(F))
+    return F.reshape(3, 3), status[:nm], int(ninl)

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _header_symbols():
     src = open(os.path.join(ROOT, "include", "orbx.h")).read()
-    return re.findall(r"ORBX_API\s+[\w\s\*]+?\b((?:orbx|hamx)_\w+)\s*\(", src)
+    return re.findall(r"ORBX_API\s+[\w\s\*]+?\b((?:orbx|hamx|fmx)_\w+)\s*\(", src)
 
 
 def test_library_builds_and_exports_header():
@@ -48,12 +48,14 @@ def test_sass_is_blackwell_native():
 
 @pytest.mark.skipif(_lib.lib().orbx_device_count() > 0, reason="a GPU is present")
 def test_no_cpu_fallback():
-    from monocular_slam_b200 import ORB, BFMatcher, OrbxError
+    from monocular_slam_b200 import ORB, BFMatcher, FundamentalFilter, OrbxError
     with pytest.raises(OrbxError) as e:
         ORB(nfeatures=500)
     assert e.value.status == _lib.E_CUDA and "no CPU fallback" in str(e.value)
     with pytest.raises(OrbxError):
         BFMatcher()
+    with pytest.raises(OrbxError):
+        FundamentalFilter()
 
 
 def test_product_never_imports_oracle():

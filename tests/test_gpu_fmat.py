@@ -1,0 +1,167 @@
+"""GPU: the fundamental-matrix outlier filter (monocular_slam_b200/csrc/fmat.cu through the C ABI) against the cv2 golden
+vectors and the CPU oracle.  Status masks and inlier counts: identical.  F: relative Frobenius error <= 1e-6."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from monocular_slam_b200 import DMATCH_DTYPE, KEYPOINT_DTYPE, BFMatcher, FundamentalFilter, ORB
+from monocular_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "fmat_cases.npz"))
+NAMES = [str(n) for n in GOLD["names"]]
+F_RTOL = 1e-6
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def case(name):
+    seed, n, inl, noise, thr, conf = GOLD[name + "_cfg"]
+    p1, p2 = syn.two_view_matches(int(seed), int(n), float(inl), float(noise))
+    return p1, p2, float(thr), float(conf), np.unpackbits(GOLD[name + "_mask"])[:int(n)], GOLD[name + "_F8"]
+
+
+@pytest.fixture(scope="module")
+def fm():
+    f = FundamentalFilter()
+    yield f
+    f.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_single_pair(fm, name):
+    p1, p2, thr, conf, mask, F8 = case(name)
+    status, F, ninl = fm.find_batch(p1[None], p2[None], [len(p1)], thr, conf)
+    assert np.array_equal(status[0], mask), "%s: %d status bytes differ" % (name, int((status[0] != mask).sum()))
+    assert ninl[0] == mask.sum()
+    assert rel(F[0], F8) <= F_RTOL
+    info = fm.last_info(1)[0]
+    assert info[0] == ninl[0] and 1 <= info[1] <= 1000 and info[3] == 1
+
+
+def test_golden_cases_as_one_ragged_batch(fm):
+    cases = [case(n) for n in NAMES if GOLD[n + "_cfg"][4] == 3.0 and GOLD[n + "_cfg"][5] == 0.85]
+    cap = max(len(c[0]) for c in cases) + 37
+    p1 = np.full((len(cases), cap, 2), np.nan, np.float32)        # slack past counts[] must never be read
+    p2 = np.full((len(cases), cap, 2), np.nan, np.float32)
+    for i, c in enumerate(cases):
+        p1[i, :len(c[0])] = c[0]
+        p2[i, :len(c[0])] = c[1]
+    status, F, ninl = fm.find_batch(p1, p2, [len(c[0]) for c in cases], 3.0, 0.85)
+    for i, c in enumerate(cases):
+        n = len(c[0])
+        assert np.array_equal(status[i, :n], c[4]) and not status[i, n:].any()
+        assert rel(F[i], c[5]) <= F_RTOL
+
+
+def test_reference_signature_with_keypoints_and_dmatches(fm):
+    p1, p2, thr, conf, mask, F8 = case("n500")
+    n = len(p1)
+    perm = np.random.default_rng(2).permutation(n)
+    k1 = np.zeros(n + 11, KEYPOINT_DTYPE)
+    k2 = np.zeros(n + 5, KEYPOINT_DTYPE)
+    k1["x"][perm], k1["y"][perm] = p1[:, 0], p1[:, 1]
+    k2["x"][:n], k2["y"][:n] = p2[:, 0], p2[:, 1]
+    m = np.zeros(n, DMATCH_DTYPE)
+    m["query_idx"], m["train_idx"] = perm, np.arange(n)
+    F, status, ninl = fm.compute_fundamental(k1, k2, m, thr, conf)
+    assert np.array_equal(status, mask) and ninl == mask.sum() and rel(F, F8) <= F_RTOL
+    Fo, so, no = oracle.compute_fundamental(np.c_[k1["x"], k1["y"]], np.c_[k2["x"], k2["y"]], m, thr, conf)
+    assert np.array_equal(status, so) and ninl == no and rel(F, Fo) <= F_RTOL
+    m["query_idx"][3] = n + 11
+    with pytest.raises(Exception):
+        fm.compute_fundamental(k1, k2, m, thr, conf)
+
+
+def test_random_scenes_against_oracle(fm):
+    r = np.random.default_rng(77)
+    npairs, cap = 48, 1500
+    counts = r.integers(15, cap + 1, npairs).astype(np.int32)
+    p1 = np.zeros((npairs, cap, 2), np.float32)
+    p2 = np.zeros((npairs, cap, 2), np.float32)
+    for i in range(npairs):
+        a, b = syn.two_view_matches(500 + i, int(counts[i]), float(r.uniform(0.3, 0.95)), float(r.uniform(0.2, 1.2)))
+        p1[i, :counts[i]], p2[i, :counts[i]] = a, b
+    for thr, conf in ((3.0, 0.85), (2.0, 0.99)):
+        status, F, ninl = fm.find_batch(p1, p2, counts, thr, conf)
+        info = fm.last_info(npairs)
+        for i in range(npairs):
+            n = int(counts[i])
+            Fr, mo, iters = oracle.fm_ransac(p1[i, :n], p2[i, :n], thr, conf)
+            assert np.array_equal(status[i, :n], mo), "pair %d: %d status bytes differ" % (i, int((status[i, :n] != mo).sum()))
+            assert info[i, 1] == iters and ninl[i] == mo.sum()
+            if mo.sum() >= 8:
+                assert rel(F[i], oracle.fm_8point(p1[i, :n][mo > 0], p2[i, :n][mo > 0])) <= F_RTOL
+
+
+def test_small_sets_degenerate_sets_and_empty_batch(fm):
+    p1, p2 = syn.two_view_matches(1, 14, 1.0, 0.1)
+    status, F, ninl = fm.find_batch(p1[None], p2[None], [14])          # < 15 correspondences: no model (see include/orbx.h)
+    assert ninl[0] == 0 and not status.any() and not F.any()
+    status, F, ninl = fm.find_batch(np.zeros((3, 64, 2), np.float32), np.zeros((3, 64, 2), np.float32), [0, 64, 20])
+    assert not ninl.any() and not F.any()                               # identical points: every sample is rejected as collinear
+    r = np.random.default_rng(5)
+    a = r.uniform(0, 1000, (1, 300, 2)).astype(np.float32)
+    b = r.uniform(0, 1000, (1, 300, 2)).astype(np.float32)
+    status, F, ninl = fm.find_batch(a, b, [300])                        # pure outliers: 1000 iterations, same mask as the CPU
+    Fo, mo, iters = oracle.fm_ransac(a[0], b[0], 3.0, 0.85)
+    assert np.array_equal(status[0], mo) and fm.last_info(1)[0, 1] == iters == 1000
+    status, F, ninl = fm.find_batch(np.zeros((0, 8, 2), np.float32), np.zeros((0, 8, 2), np.float32), np.zeros(0, np.int32))
+    assert status.shape == (0, 8)
+    with pytest.raises(Exception):
+        fm.find_batch(a, b, [301])
+
+
+def test_full_size_batch_properties(fm):
+    """BASELINE-sized batch (64 frames x 5 predecessors, ~1000 matches per pair): permuting the pairs permutes the results,
+    a second run is identical, and every reported inlier satisfies the epipolar test of the returned 8-point matrix's
+    RANSAC parent (checked through the oracle on a sample of pairs)."""
+    npairs, cap = 320, 1200
+    r = np.random.default_rng(9)
+    counts = r.integers(600, cap + 1, npairs).astype(np.int32)
+    p1 = np.zeros((npairs, cap, 2), np.float32)
+    p2 = np.zeros((npairs, cap, 2), np.float32)
+    for i in range(npairs):
+        a, b = syn.two_view_matches(2000 + i, int(counts[i]), 0.55 + 0.4 * (i % 7) / 7, 0.5)
+        p1[i, :counts[i]], p2[i, :counts[i]] = a, b
+    s1, F1, n1 = fm.find_batch(p1, p2, counts)
+    s2, F2, n2 = fm.find_batch(p1, p2, counts)
+    assert np.array_equal(s1, s2) and np.array_equal(F1, F2) and np.array_equal(n1, n2)
+    perm = r.permutation(npairs)
+    s3, F3, n3 = fm.find_batch(p1[perm], p2[perm], counts[perm])
+    assert np.array_equal(s3, s1[perm]) and np.array_equal(F3, F1[perm]) and np.array_equal(n3, n1[perm])
+    assert np.array_equal(s1.sum(1), n1) and (n1 >= 0.5 * 0.55 * counts).all()
+    for i in range(0, npairs, 23):
+        n = int(counts[i])
+        _, mo, _ = oracle.fm_ransac(p1[i, :n], p2[i, :n], 3.0, 0.85)
+        assert np.array_equal(s1[i, :n], mo)
+
+
+def test_filter_consecutive_keeps_matches_on_device(fm):
+    """orbx_filter_consecutive == fmx_compute_fundamental on the downloaded keypoints and match lists of every pair."""
+    w, h, n, nf = 640, 480, 5, 800
+    frames = syn.sequence(2 * n, w, h, seed=3)
+    orb = ORB(nfeatures=nf, max_size=(w, h), max_batch=n)
+    bf = BFMatcher()
+    prev_kps = None
+    for b in range(2):
+        kps, desc, counts = orb.extract_batch(frames[b * n:(b + 1) * n])
+        cap = kps.shape[1]
+        good, ngood = orb.match_consecutive(bf, 0.8, cap, n)
+        status, F, ninl = orb.filter_consecutive(fm, cap, n)
+        for f in range(n):
+            kt = kps[f - 1] if f else prev_kps
+            if kt is None:
+                assert ninl[f] == 0 and not status[f].any()
+                continue
+            Fh, sh, nh = fm.compute_fundamental(kps[f], kt, good[f, :ngood[f]])
+            assert np.array_equal(status[f, :ngood[f]], sh) and ninl[f] == nh and np.array_equal(F[f], Fh)
+            assert not status[f, ngood[f]:].any()
+        prev_kps = kps[n - 1].copy()
+    orb.close()
+    bf.close()

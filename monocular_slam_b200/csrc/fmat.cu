@@ -26,7 +26,7 @@
 namespace orbx {
 namespace {
 
-constexpr int FM_THREADS = 256;
+constexpr int FM_THREADS = 128;       // 4 CTAs (pairs) per SM: the serial parts of one pair overlap the parallel parts of the others
 constexpr int FM_WARPS = FM_THREADS / 32;
 constexpr int FM_MAXCHUNK = 128;      // iterations solved + scored per round
 constexpr int FM_FIRSTCHUNK = 16;     // a short first round establishes a count that lets later rounds abandon bad candidates early
@@ -38,12 +38,14 @@ struct FmShared {
     double best[9];
     double red[FM_WARPS][48];
     double A[81], V[81];
-    double norm[6];                   // c1x c1y s1 c2x c2y s2
+    double rot_cs[4], rot_sn[4];      // the 4 concurrent Jacobi rotations of one round
     unsigned long long rng;
+    unsigned long long rng_at[FM_MAXCHUNK];   // generator state before each sample of the chunk (restart point for the slow path)
     int idx[FM_MAXCHUNK][FM_MODEL_POINTS];
     int nmodels[FM_MAXCHUNK];
     int count[FM_MAXCHUNK][3];
-    int iter, niters, maxgood, chunk, stop, have, next, ninl, ok8;
+    int rot_p[4], rot_q[4];
+    int iter, niters, maxgood, chunk, stop, have, next, first_bad;
 };
 
 __device__ __forceinline__ unsigned rng_next(unsigned long long& s)
@@ -63,6 +65,33 @@ __device__ bool have_collinear(const float2* p)
         }
     }
     return false;
+}
+
+// x % n with a precomputed m = floor(2^32 / n): the quotient estimate is at most one too small
+__device__ __forceinline__ int fast_mod(unsigned x, unsigned n, unsigned m)
+{
+    unsigned r = x - __umulhi(x, m) * n;
+    if (r >= n) r -= n;
+    if (r >= n) r -= n;
+    return (int)r;
+}
+
+// the index draws of getSubset alone (7 distinct indices); the collinearity test is done in parallel afterwards
+__device__ __forceinline__ void draw_indices(int n, unsigned m, unsigned long long& rng, int* out)
+{
+    int idx[FM_MODEL_POINTS];
+#pragma unroll
+    for (int i = 0; i < FM_MODEL_POINTS; i++) {
+        for (;;) {
+            const int v = n == 1 ? 0 : fast_mod(rng_next(rng), (unsigned)n, m);
+            bool dup = false;
+#pragma unroll
+            for (int j = 0; j < i; j++) dup |= v == idx[j];
+            if (!dup) { idx[i] = v; break; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FM_MODEL_POINTS; i++) out[i] = idx[i];
 }
 
 // RANSACPointSetRegistrator::getSubset: 7 distinct indices whose last point is not collinear with two earlier ones
@@ -245,16 +274,40 @@ __device__ int solve7(const float2* P1, const float2* P2, const int* idx, double
     return n;
 }
 
-// FMEstimatorCallback::computeError for one correspondence, then findInliers' test (float compare)
-__device__ __forceinline__ bool is_inlier(const double* F, float2 p1, float2 p2, float t2)
+// FMEstimatorCallback::computeError for one correspondence, then findInliers' test `(float)max(d1*d1*s1, d2*d2*s2) <= t2`
+// with s = 1/(a*a + b*b), exactly as OpenCV evaluates it (Fm: the matrix in shared memory).
+__device__ __noinline__ bool is_inlier_exact(const double* Fm, float2 p1, float2 p2, float t2)
 {
     const double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
-    double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+    double a = Fm[0] * x1 + Fm[1] * y1 + Fm[2], b = Fm[3] * x1 + Fm[4] * y1 + Fm[5], c = Fm[6] * x1 + Fm[7] * y1 + Fm[8];
     const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
-    a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+    a = Fm[0] * x2 + Fm[3] * y2 + Fm[6]; b = Fm[1] * x2 + Fm[4] * y2 + Fm[7]; c = Fm[2] * x2 + Fm[5] * y2 + Fm[8];
     const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
     const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
     return __double2float_rn(e1 < e2 ? e2 : e1) <= t2;       // std::max(e1, e2)
+}
+
+// The two divisions are only needed for points within 1e-6 (relative) of the threshold: with the same a, b, d as OpenCV
+// computes, q = d*d <= t2*(1 - 1e-9)*den implies q*fl(1/den) < t2, and q >= t2*(1 + 1e-6)*den implies it exceeds the largest
+// double that still rounds to the float t2.  Branch-free: 1 inlier, 0 outlier, -1 undecided (-> is_inlier_exact).
+__device__ __forceinline__ int classify(const double* F, float2 p1, float2 p2, double tlo, double thi)
+{
+    const double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
+    double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+    const double den2 = a * a + b * b, d2 = x2 * a + y2 * b + c;
+    a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+    const double den1 = a * a + b * b, d1 = x1 * a + y1 * b + c;
+    const double q1 = d1 * d1, q2 = d2 * d2;
+    const bool regular = den1 > 0 && den1 < 1e300 && den2 > 0 && den2 < 1e300;
+    const bool in = q1 <= tlo * den1 && q2 <= tlo * den2;
+    const bool out = q1 >= thi * den1 || q2 >= thi * den2;
+    return regular && (in || out) ? (in ? 1 : 0) : -1;
+}
+
+__device__ __forceinline__ bool is_inlier(const double* F, const double* Fm, float2 p1, float2 p2, float t2, double tlo, double thi)
+{
+    const int c = classify(F, p1, p2, tlo, thi);
+    return c >= 0 ? c != 0 : is_inlier_exact(Fm, p1, p2, t2);
 }
 
 // RANSACUpdateNumIters
@@ -298,43 +351,58 @@ __device__ void block_sum(FmShared& sh, const double* v)
     __syncthreads();
 }
 
-// cyclic Jacobi on the symmetric 9x9 sh.A (warp 0, lanes 0..8 own one row / column element each); eigenvectors = rows of sh.V
+// Jacobi on the symmetric 9x9 sh.A by warp 0; eigenvectors = rows of sh.V.  Round-robin ordering: each of the 9 rounds of a
+// sweep applies 4 rotations on disjoint index pairs at once -- lanes 0..3 compute the angles, then 36 lanes update the
+// 4 x 9 column pairs, then the row pairs (and V).
 __device__ void jacobi9_warp(FmShared& sh, int lane)
 {
     for (int i = lane; i < 81; i += 32) sh.V[i] = (i / 9 == i % 9) ? 1. : 0.;
     __syncwarp();
-    for (int sweep = 0; sweep < 40; sweep++) {
+    for (int sweep = 0; sweep < 30; sweep++) {
         double off = 0, diag = 0;
         for (int i = lane; i < 81; i += 32) {
             const double x = sh.A[i] * sh.A[i];
             if (i / 9 == i % 9) diag += x; else off += x;
         }
         off = warp_sum(off); diag = warp_sum(diag);
-        if (off == 0 || off <= 1e-36 * diag) break;
-        for (int p = 0; p < 8; p++)
-            for (int q = p + 1; q < 9; q++) {
+        if (off <= 1e-31 * diag) break;                    // off-diagonal entries at the rounding floor of the diagonal
+        for (int r = 0; r < 9; r++) {
+            if (lane < 4) {
+                const int a = (r + lane + 1) % 9, b = (r + 8 - lane) % 9;
+                const int p = min(a, b), q = max(a, b);
                 const double apq = sh.A[p * 9 + q];
-                if (apq == 0) continue;                                    // uniform over the warp
-                const double theta = (sh.A[q * 9 + q] - sh.A[p * 9 + p]) / (2 * apq);
-                const double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
-                const double cs = 1. / sqrt(t * t + 1), sn = t * cs;
-                __syncwarp();
-                if (lane < 9) {
-                    const double akp = sh.A[lane * 9 + p], akq = sh.A[lane * 9 + q];
-                    sh.A[lane * 9 + p] = cs * akp - sn * akq;
-                    sh.A[lane * 9 + q] = sn * akp + cs * akq;
+                double cs = 1., sn = 0.;
+                if (apq != 0) {
+                    const double theta = (sh.A[q * 9 + q] - sh.A[p * 9 + p]) / (2 * apq);
+                    const double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
+                    cs = rsqrt(t * t + 1);
+                    sn = t * cs;
                 }
-                __syncwarp();
-                if (lane < 9) {
-                    const double apk = sh.A[p * 9 + lane], aqk = sh.A[q * 9 + lane];
-                    sh.A[p * 9 + lane] = cs * apk - sn * aqk;
-                    sh.A[q * 9 + lane] = sn * apk + cs * aqk;
-                    const double vpk = sh.V[p * 9 + lane], vqk = sh.V[q * 9 + lane];
-                    sh.V[p * 9 + lane] = cs * vpk - sn * vqk;
-                    sh.V[q * 9 + lane] = sn * vpk + cs * vqk;
-                }
-                __syncwarp();
+                sh.rot_p[lane] = p; sh.rot_q[lane] = q; sh.rot_cs[lane] = cs; sh.rot_sn[lane] = sn;
             }
+            __syncwarp();
+#pragma unroll
+            for (int t = lane; t < 36; t += 32) {
+                const int k = t / 9, i = t - 9 * k, p = sh.rot_p[k], q = sh.rot_q[k];
+                const double cs = sh.rot_cs[k], sn = sh.rot_sn[k];
+                const double akp = sh.A[i * 9 + p], akq = sh.A[i * 9 + q];
+                sh.A[i * 9 + p] = cs * akp - sn * akq;
+                sh.A[i * 9 + q] = sn * akp + cs * akq;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = lane; t < 36; t += 32) {
+                const int k = t / 9, i = t - 9 * k, p = sh.rot_p[k], q = sh.rot_q[k];
+                const double cs = sh.rot_cs[k], sn = sh.rot_sn[k];
+                const double apk = sh.A[p * 9 + i], aqk = sh.A[q * 9 + i];
+                sh.A[p * 9 + i] = cs * apk - sn * aqk;
+                sh.A[q * 9 + i] = sn * apk + cs * aqk;
+                const double vpk = sh.V[p * 9 + i], vqk = sh.V[q * 9 + i];
+                sh.V[p * 9 + i] = cs * vpk - sn * vqk;
+                sh.V[q * 9 + i] = sn * vpk + cs * vqk;
+            }
+            __syncwarp();
+        }
     }
     __syncwarp();
 }
@@ -375,7 +443,7 @@ __device__ void smallest_eigvec3(double* G, double* vs)
 // status: npairs x cap bytes (0/1); F: npairs x 9 doubles (zeros: no result); info: npairs x 4 ints
 // {inliers, iterations run, candidates scored, 0}.
 template <bool SMEM_POINTS>
-__global__ void __launch_bounds__(FM_THREADS, 2)
+__global__ void __launch_bounds__(FM_THREADS, 4)
 k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ counts, int cap,
             double thr, double conf, int max_iters, uint8_t* __restrict__ status, double* __restrict__ Fout, int32_t* __restrict__ info)
 {
@@ -406,25 +474,51 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     if (thr <= 0) thr = 3;
     if (conf < DBL_EPSILON || conf > 1 - DBL_EPSILON) conf = 0.99;
     const float t2 = __double2float_rn(thr * thr);
+    const double tlo = (double)t2 * (1. - 1e-9), thi = (double)t2 * (1. + 1e-6);
+    const unsigned nmod = (unsigned)(0x100000000ULL / (unsigned)n);
     if (tid == 0) {
         sh.rng = 0xffffffffffffffffULL;
-        sh.iter = 0; sh.niters = max_iters; sh.maxgood = 0; sh.stop = 0; sh.have = 0; sh.ninl = 0; sh.ok8 = 0;
+        sh.iter = 0; sh.niters = max_iters; sh.maxgood = 0; sh.stop = 0; sh.have = 0;
     }
     __syncthreads();
 
     int scored = 0;
     for (int round = 0;; round++) {
-        // ---- 1. samples of the next chunk of iterations
+        // ---- 1. samples of the next chunk of iterations: one thread draws the index tuples (integer work only), then every
+        // sample's collinearity test runs in parallel.  A rejected sample (rare: three points exactly on a line, or
+        // coincident points) changes what the generator produces next, so the chunk is redone from there by the
+        // sequential rule.
         if (tid == 0) {
-            int chunk = min(round == 0 ? FM_FIRSTCHUNK : FM_MAXCHUNK, sh.niters - sh.iter);
+            const int chunk = min(round == 0 ? FM_FIRSTCHUNK : FM_MAXCHUNK, sh.niters - sh.iter);
             unsigned long long rng = sh.rng;
-            for (int i = 0; i < chunk; i++)
-                if (!get_subset(P1, P2, n, rng, sh.idx[i])) { chunk = i; sh.stop = 1; break; }     // OpenCV leaves its loop here
+            for (int i = 0; i < chunk; i++) {
+                sh.rng_at[i] = rng;
+                draw_indices(n, nmod, rng, sh.idx[i]);
+            }
             sh.rng = rng;
             sh.chunk = chunk;
             sh.next = 0;
+            sh.first_bad = chunk;
         }
         __syncthreads();
+        if (tid < sh.chunk) {
+            float2 a[FM_MODEL_POINTS], b[FM_MODEL_POINTS];
+#pragma unroll
+            for (int i = 0; i < FM_MODEL_POINTS; i++) { a[i] = P1[sh.idx[tid][i]]; b[i] = P2[sh.idx[tid][i]]; }
+            if (have_collinear(a) || have_collinear(b)) atomicMin(&sh.first_bad, tid);
+        }
+        __syncthreads();
+        if (sh.first_bad < sh.chunk) {
+            if (tid == 0) {
+                int chunk = sh.chunk;
+                unsigned long long rng = sh.rng_at[sh.first_bad];
+                for (int i = sh.first_bad; i < chunk; i++)
+                    if (!get_subset(P1, P2, n, rng, sh.idx[i])) { chunk = i; sh.stop = 1; break; }     // OpenCV leaves its loop here
+                sh.rng = rng;
+                sh.chunk = chunk;
+            }
+            __syncthreads();
+        }
         const int chunk = sh.chunk;
         if (chunk == 0) break;
         // ---- 2. one thread per sample: candidate matrices
@@ -442,12 +536,17 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             double F[9];
 #pragma unroll
             for (int i = 0; i < 9; i++) F[i] = sh.models[it][9 * k + i];
+            const double* Fm = sh.models[it] + 9 * k;
             int cnt = 0;
-            for (int base = 0; base < n; base += 32) {
-                const int i = base + lane;
-                const bool in = i < n && is_inlier(F, P1[i], P2[i], t2);
-                cnt += __popc(__ballot_sync(0xffffffffu, in));
-                if (cnt + max(n - base - 32, 0) <= bound) { cnt = 0; break; }
+            for (int base = 0; base < n; base += 64) {                // two independent points per lane and step
+                const int i0 = base + lane, i1 = i0 + 32;
+                const int j0 = min(i0, n - 1), j1 = min(i1, n - 1);
+                const float2 a0 = P1[j0], b0 = P2[j0], a1 = P1[j1], b1 = P2[j1];
+                int c0 = classify(F, a0, b0, tlo, thi), c1 = classify(F, a1, b1, tlo, thi);
+                if (c0 < 0) c0 = is_inlier_exact(Fm, a0, b0, t2);
+                if (c1 < 0) c1 = is_inlier_exact(Fm, a1, b1, t2);
+                cnt += __popc(__ballot_sync(0xffffffffu, c0 && i0 < n)) + __popc(__ballot_sync(0xffffffffu, c1 && i1 < n));
+                if (cnt + max(n - base - 64, 0) <= bound) { cnt = 0; break; }
             }
             if (lane == 0) sh.count[it][k] = cnt;
             scored++;
@@ -488,7 +587,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     int mine = 0;
     for (int i = tid; i < n; i += FM_THREADS) {
         const float2 a = P1[i], b = P2[i];
-        const bool in = is_inlier(F, a, b, t2);
+        const bool in = is_inlier(F, sh.best, a, b, t2, tlo, thi);
         st[i] = in;
         if (in) { acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; mine++; }
     }

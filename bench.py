@@ -459,6 +459,71 @@ def run_ours(args, rank, world, local_rank):
         hamming["map_vs_frame"] = mvf
         sm.close()
 
+    # ---- the next stage of the reference after matching: computeFundamentalMatrix for every matched pair,
+    # RANSAC status + 8-point F, one CUDA block per pair.  Workload: B frames x numBackTraverse = 5 predecessors per step.
+    fundamental = None
+    if not args.no_fundamental:
+        from monocular_slam_b200 import FundamentalFilter
+        fpairs, fn = B * 5, 1000
+        p1 = np.zeros((fpairs, fn, 2), np.float32)
+        p2 = np.zeros((fpairs, fn, 2), np.float32)
+        for i in range(fpairs):
+            p1[i], p2[i] = syn.two_view_matches(1000 * rank + i, fn, 0.7, 0.5, (W, H))
+        fcounts = np.full(fpairs, fn, np.int32)
+        fm = FundamentalFilter(device=local_rank)
+        fm.set_stream(stream.cuda_stream)
+        fd1, fd2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
+        fdc = torch.from_numpy(fcounts).to(dev)
+        fds = torch.zeros((fpairs, fn), dtype=torch.uint8, device=dev)
+        fdF = torch.zeros((fpairs, 9), dtype=torch.float64, device=dev)
+        fdi = torch.zeros((fpairs, 4), dtype=torch.int32, device=dev)
+
+        def step_fm():
+            fm.find_batch_dev(fd1.data_ptr(), fd2.data_ptr(), fdc.data_ptr(), fpairs, fn, 3.0, 0.85, fds.data_ptr(), fdF.data_ptr(), fdi.data_ptr())
+        fm_ms, _ = timed(step_fm, args.steps, args.warmup)
+        fm_ms = max_over_ranks(fm_ms) / args.steps
+        finfo = fdi.cpu().numpy()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fm.find_batch(p1, p2, fcounts, 3.0, 0.85)
+        fm_host_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+        fundamental = {"value": world * fpairs / (fm_ms * 1e-3), "unit": "pairs/s", "ms_per_step": fm_ms,
+                       "workload": "%d pairs per GPU and step (%d frames x 5 predecessors) x %d matches, 70 %% inliers, 0.5 px noise; "
+                                   "findFundamentalMat(FM_RANSAC, 3, 0.85) status + FM_8POINT on the inliers" % (fpairs, B, fn),
+                       "ransac_iterations_mean": float(finfo[:, 1].mean()), "candidates_scored_mean": float(finfo[:, 2].mean()),
+                       "inliers_mean": float(finfo[:, 0].mean()),
+                       "e2e": {"value": world * fpairs / (fm_host_ms * 1e-3), "unit": "pairs/s", "ms_per_step": fm_host_ms,
+                               "h2d_bytes_per_step": int(p1.nbytes + p2.nbytes + fcounts.nbytes),
+                               "d2h_bytes_per_step": int(fpairs * fn + fpairs * 72 + fpairs * 16),
+                               "timing": "host wall clock around fmx_fundamental_batch (pageable host buffers), max over ranks"}}
+        if world == 1 and not args.no_cpu:
+            try:
+                import oracle
+                ns = 16
+                t0 = time.perf_counter()
+                for i in range(ns):
+                    _, m, _ = oracle.fm_ransac(p1[i], p2[i], 3.0, 0.85)
+                    oracle.fm_8point(p1[i][m > 0], p2[i][m > 0])
+                o_ms = (time.perf_counter() - t0) * 1e3 / ns
+                fundamental["cpu_baseline"] = {"value": 1e3 / o_ms, "unit": "pairs/s", "cores": 1, "kind": "port",
+                                               "sample": "oracle/fmat_oracle.c on the first %d pairs of the step, one thread" % ns}
+                try:
+                    import cv2
+                    cv2.setNumThreads(1)
+                    t0 = time.perf_counter()
+                    for i in range(ns):
+                        a, b = p1[i].astype(np.float64), p2[i].astype(np.float64)
+                        _, m = cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, 3.0, 0.85)
+                        cv2.findFundamentalMat(a[m.ravel() > 0], b[m.ravel() > 0], cv2.FM_8POINT)
+                    c_ms = (time.perf_counter() - t0) * 1e3 / ns
+                    fundamental["cpu_baseline_cv2"] = {"value": 1e3 / c_ms, "unit": "pairs/s", "cores": 1, "kind": "reference",
+                                                       "sample": "cv2 %s findFundamentalMat x2 on the same %d pairs, one thread" % (cv2.__version__, ns)}
+                except ImportError:
+                    pass
+            except Exception as e:
+                fundamental["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
+        fm.close()
+
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -508,7 +573,8 @@ def run_ours(args, rank, world, local_rank):
                 "roofline_pyramid": roofline_pyramid,
                 "stages_ms_per_step": dict(stages, match=match_ms, profiled_step=prof_ms / args.steps),
                 "cpu_baseline": cpu,
-                "hamming": hamming}
+                "hamming": hamming,
+                "fundamental": fundamental}
         emit(line)
     matcher.close()
     orb.close()
@@ -545,6 +611,7 @@ def main():
     ap.add_argument("--ham-nq", type=int, default=1 << 20)
     ap.add_argument("--ham-nt", type=int, default=125000, help="train rows per GPU")
     ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-fundamental", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--frame", default="1920x1080", help="frame size WxH (default: BASELINE.json configs[1]; 3840x2160 with --nfeatures 8000 is configs[2])")
     ap.add_argument("--nfeatures", type=int, default=2000)

@@ -26,8 +26,9 @@
 namespace orbx {
 namespace {
 
-constexpr int FM_THREADS = 128;       // 4 CTAs (pairs) per SM: the serial parts of one pair overlap the parallel parts of the others
-constexpr int FM_WARPS = FM_THREADS / 32;
+// CTA size: 128 threads (4 pairs per SM, the serial parts of one pair overlap the parallel parts of the others) when the batch
+// fills the device that way, 256 threads (more warps scoring one pair's candidates) for small batches.
+constexpr int FM_MAXWARPS = 8;
 constexpr int FM_MAXCHUNK = 128;      // iterations solved + scored per round
 constexpr int FM_FIRSTCHUNK = 16;     // a short first round establishes a count that lets later rounds abandon bad candidates early
 constexpr int FM_MODEL_POINTS = 7;
@@ -36,7 +37,7 @@ constexpr int FM_SMEM_POINTS = 9000;  // pairs with at most this many correspond
 struct FmShared {
     double models[FM_MAXCHUNK][27];
     double best[9];
-    double red[FM_WARPS][48];
+    double red[FM_MAXWARPS][48];
     double A[81], V[81];
     double rot_cs[4], rot_sn[4];      // the 4 concurrent Jacobi rotations of one round
     unsigned long long rng;
@@ -331,7 +332,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // sums `NV` per-thread values over the CTA; the totals land in sh.red[0][0..NV)
-template <int NV>
+template <int NV, int FM_WARPS>
 __device__ void block_sum(FmShared& sh, const double* v)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -442,8 +443,8 @@ __device__ void smallest_eigvec3(double* G, double* vs)
 // One CTA per pair.  pts1/pts2: npairs x cap correspondences (float x, y); counts[pair] of them valid.
 // status: npairs x cap bytes (0/1); F: npairs x 9 doubles (zeros: no result); info: npairs x 4 ints
 // {inliers, iterations run, candidates scored, 0}.
-template <bool SMEM_POINTS>
-__global__ void __launch_bounds__(FM_THREADS, 4)
+template <bool SMEM_POINTS, int FM_THREADS>
+__global__ void __launch_bounds__(FM_THREADS, 512 / FM_THREADS)
 k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ counts, int cap,
             double thr, double conf, int max_iters, uint8_t* __restrict__ status, double* __restrict__ Fout, int32_t* __restrict__ info)
 {
@@ -593,7 +594,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     }
     {
         double v[5] = {acc[0], acc[1], acc[2], acc[3], (double)mine};
-        block_sum<5>(sh, v);
+        block_sum<5, FM_THREADS / 32>(sh, v);
     }
     const int k = (int)sh.red[0][4];
     const double tk = 1. / k;
@@ -610,7 +611,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
                 v[1] += sqrt(dx2 * dx2 + dy2 * dy2);
             }
         }
-        block_sum<2>(sh, v);
+        block_sum<2, FM_THREADS / 32>(sh, v);
     }
     double s1 = sh.red[0][0] * tk, s2 = sh.red[0][1] * tk;
     if (s1 < (double)FLT_EPSILON || s2 < (double)FLT_EPSILON) return;
@@ -631,7 +632,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
                     for (int q = p; q < 9; q++) v[e++] += r[p] * r[q];
             }
         }
-        block_sum<45>(sh, v);
+        block_sum<45, FM_THREADS / 32>(sh, v);
     }
     if (tid < 45) {
         int p = 0, e = tid;
@@ -707,6 +708,7 @@ struct fmx_context {
     int32_t* d_info; size_t info_bytes;
     int32_t* h_info; size_t h_info_n;
     size_t smem_optin;
+    int sm_count;
 };
 
 template <typename T>
@@ -737,8 +739,9 @@ extern "C" int fmx_create(fmx_handle* out, int device)
     int optin = 0;
     ORBX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     h->smem_optin = (size_t)optin;
-    ORBX_CUDA(cudaFuncSetAttribute(k_fm_ransac<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    ORBX_CUDA(cudaFuncSetAttribute(k_fm_ransac<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FmShared)));
+    ORBX_CUDA(cudaFuncSetAttribute(k_fm_ransac<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    ORBX_CUDA(cudaFuncSetAttribute(k_fm_ransac<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    ORBX_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     *out = h;
     return ORBX_OK;
 }
@@ -777,12 +780,15 @@ static int fm_launch(fmx_handle h, const float* d_pts1, const float* d_pts2, con
     if (npairs == 0) return ORBX_OK;
     const bool in_smem = max_count <= FM_SMEM_POINTS && sizeof(FmShared) + (size_t)max_count * 16 <= h->smem_optin;
     const size_t smem = sizeof(FmShared) + (in_smem ? (size_t)max_count * 16 : 0);
-    if (in_smem)
-        k_fm_ransac<true><<<npairs, FM_THREADS, smem, h->stream>>>((const float2*)d_pts1, (const float2*)d_pts2, d_counts, cap, max_distance,
-                                                                    confidence, 1000, d_status, d_F, d_info);
-    else
-        k_fm_ransac<false><<<npairs, FM_THREADS, smem, h->stream>>>((const float2*)d_pts1, (const float2*)d_pts2, d_counts, cap, max_distance,
-                                                                     confidence, 1000, d_status, d_F, d_info);
+    const float2* p1 = (const float2*)d_pts1;
+    const float2* p2 = (const float2*)d_pts2;
+    const bool wide = npairs <= 2 * h->sm_count;
+#define FM_LAUNCH(SM, T) k_fm_ransac<SM, T><<<npairs, T, smem, h->stream>>>(p1, p2, d_counts, cap, max_distance, confidence, 1000, d_status, d_F, d_info)
+    if (in_smem && wide) FM_LAUNCH(true, 256);
+    else if (in_smem) FM_LAUNCH(true, 128);
+    else if (wide) FM_LAUNCH(false, 256);
+    else FM_LAUNCH(false, 128);
+#undef FM_LAUNCH
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }

@@ -35,6 +35,7 @@ using cv::DMatch;
 using cv::KeyPoint;
 using cv::Mat;
 using cv::NORM_HAMMING;
+using cv::Point2d;
 static inline const uint8_t* mat_ptr(const Mat& m) { return m.data; }
 static inline void mat_create_u8(Mat& m, int rows, int cols) { m.create(rows, cols, CV_8UC1); }
 static inline size_t mat_step(const Mat& m) { return m.step; }
@@ -234,6 +235,67 @@ static inline void matchFeatures(const Mat& descriptors1, const Mat& descriptors
         if (raw_matches[i][0].distance < raw_matches[i][1].distance * ratio) matches.push_back(raw_matches[i][0]);
     }
 }
+
+// computeFundamentalMatrix (src/CameraPoseEstimator.cpp:545-586): RANSAC status of the matches + the 8-point matrix of the
+// inliers, on the GPU (fmx_fundamental_batch).  F is row-major 3x3 (all zeros when there is no model).  MAX_DISTANCE and
+// CONFIDENCE are the reference's constants (src/ParamConfig.h:24-25).
+class FundamentalFilter {
+public:
+    explicit FundamentalFilter(int device = 0) : h_(nullptr) { check(fmx_create(&h_, device), "FundamentalFilter"); }
+    ~FundamentalFilter() { if (h_) fmx_destroy(h_); }
+    FundamentalFilter(const FundamentalFilter&) = delete;
+    FundamentalFilter& operator=(const FundamentalFilter&) = delete;
+
+    void compute(const std::vector<Point2d>& positions1, const std::vector<Point2d>& positions2, const std::vector<DMatch>& matches,
+                 std::vector<Point2d>& inlierPositions1, std::vector<Point2d>& inlierPositions2, double F[9],
+                 std::vector<unsigned char>& status, double maxDistance = 3., double confidence = 0.85)
+    {
+        const size_t n = matches.size();
+        std::vector<float> a(2 * n + 2), b(2 * n + 2);
+        for (size_t i = 0; i < n; i++) {
+            const Point2d& p = positions1.at((size_t)matches[i].queryIdx);
+            const Point2d& q = positions2.at((size_t)matches[i].trainIdx);
+            a[2 * i] = (float)p.x; a[2 * i + 1] = (float)p.y;          // findFundamentalMat converts its inputs to CV_32F
+            b[2 * i] = (float)q.x; b[2 * i + 1] = (float)q.y;
+        }
+        status.assign(n ? n : 1, 0);
+        const int32_t count = (int32_t)n;
+        int32_t ninl = 0;
+        check(fmx_fundamental_batch(h_, a.data(), b.data(), &count, 1, n ? (int)n : 1, maxDistance, confidence, status.data(), F, &ninl),
+              "computeFundamentalMatrix");
+        status.resize(n);
+        inlierPositions1.clear();
+        inlierPositions2.clear();
+        for (size_t i = 0; i < n; i++)
+            if (status[i]) {
+                inlierPositions1.push_back(positions1[(size_t)matches[i].queryIdx]);
+                inlierPositions2.push_back(positions2[(size_t)matches[i].trainIdx]);
+            }
+    }
+    fmx_handle handle() { return h_; }
+
+private:
+    fmx_handle h_;
+};
+
+static inline void computeFundamentalMatrix(const std::vector<Point2d>& positions1, const std::vector<Point2d>& positions2,
+                                            const std::vector<DMatch>& matches, std::vector<Point2d>& inlierPositions1,
+                                            std::vector<Point2d>& inlierPositions2, double F[9], std::vector<unsigned char>& status)
+{
+    FundamentalFilter f;
+    f.compute(positions1, positions2, matches, inlierPositions1, inlierPositions2, F, status);
+}
+#ifdef ORBX_SHIM_USE_OPENCV
+static inline void computeFundamentalMatrix(const std::vector<Point2d>& positions1, const std::vector<Point2d>& positions2,
+                                            const std::vector<DMatch>& matches, std::vector<Point2d>& inlierPositions1,
+                                            std::vector<Point2d>& inlierPositions2, Mat& F, std::vector<unsigned char>& status)
+{
+    double f[9];
+    computeFundamentalMatrix(positions1, positions2, matches, inlierPositions1, inlierPositions2, f, status);
+    F.create(3, 3, CV_64F);
+    std::memcpy(F.data, f, sizeof(f));
+}
+#endif
 
 #ifndef ORBX_SHIM_USE_OPENCV
 // ---- the slice of the reference's data model and node API that the front-end touches

@@ -73,3 +73,32 @@ def test_shim_matches_oracle(tmp_path, demo, n, extra):
             assert np.array_equal(dm["distance"].astype(np.int32), gd)
         prev = od
     assert off == len(buf)
+
+
+def test_fmat_demo_compiles(tmp_path):
+    _build_demo(tmp_path, "fmat_demo")
+
+
+@pytest.mark.gpu
+def test_shim_compute_fundamental_matrix_matches_oracle(tmp_path):
+    """computeFundamentalMatrix through the C++ shim: status, aligned inlier positions and F as the oracle computes them."""
+    import oracle
+    from monocular_slam_b200 import synthetic as syn
+    exe = _build_demo(tmp_path, "fmat_demo")
+    n = 700
+    p1, p2 = syn.two_view_matches(21, n, 0.65, 0.5)
+    pts = tmp_path / "pts.bin"
+    pts.write_bytes(np.c_[p1, p2].astype(np.float64).tobytes())
+    out = tmp_path / "out.bin"
+    subprocess.check_call([exe, str(n), str(pts), str(out)])
+    buf = out.read_bytes()
+    (ni,) = struct.unpack_from("<i", buf, 0)
+    status = np.frombuffer(buf, np.uint8, n, 4)
+    in1 = np.frombuffer(buf, "<f8", ni * 2, 4 + n).reshape(ni, 2)
+    in2 = np.frombuffer(buf, "<f8", ni * 2, 4 + n + ni * 16).reshape(ni, 2)
+    F = np.frombuffer(buf, "<f8", 9, 4 + n + ni * 32).reshape(3, 3)
+    _, mo, _ = oracle.fm_ransac(p1, p2, 3.0, 0.85)
+    assert np.array_equal(status, mo) and ni == mo.sum()
+    assert np.array_equal(in1, p1[mo > 0].astype(np.float64)) and np.array_equal(in2, p2[mo > 0].astype(np.float64))
+    Fo = oracle.fm_8point(p1[mo > 0], p2[mo > 0])
+    assert np.linalg.norm(F - Fo) / np.linalg.norm(Fo) <= 1e-6

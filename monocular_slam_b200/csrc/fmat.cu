@@ -21,13 +21,13 @@
 #include "common.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace orbx {
 namespace {
 
-// CTA size: 128 threads (4 pairs per SM, the serial parts of one pair overlap the parallel parts of the others) when the batch
-// fills the device that way, 256 threads (more warps scoring one pair's candidates) for small batches.
+// CTA size: 256 threads by default (2 pairs per SM), 128 as a tuning alternative (4 pairs per SM); see fm_launch.
 constexpr int FM_MAXWARPS = 8;
 constexpr int FM_MAXCHUNK = 128;      // iterations solved + scored per round
 constexpr int FM_FIRSTCHUNK = 16;     // a short first round establishes a count that lets later rounds abandon bad candidates early
@@ -490,7 +490,10 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         // coincident points) changes what the generator produces next, so the chunk is redone from there by the
         // sequential rule.
         if (tid == 0) {
-            const int chunk = min(round == 0 ? FM_FIRSTCHUNK : FM_MAXCHUNK, sh.niters - sh.iter);
+            // iterations per round: a quarter of the remaining budget (the budget usually collapses as soon as a good sample is
+            // scored, and everything scored past that point is wasted), between FM_FIRSTCHUNK and FM_MAXCHUNK
+            const int remaining = sh.niters - sh.iter;
+            const int chunk = min(remaining, round == 0 ? FM_FIRSTCHUNK : min(FM_MAXCHUNK, max(FM_FIRSTCHUNK, remaining / 4)));
             unsigned long long rng = sh.rng;
             for (int i = 0; i < chunk; i++) {
                 sh.rng_at[i] = rng;
@@ -782,7 +785,11 @@ static int fm_launch(fmx_handle h, const float* d_pts1, const float* d_pts2, con
     const size_t smem = sizeof(FmShared) + (in_smem ? (size_t)max_count * 16 : 0);
     const float2* p1 = (const float2*)d_pts1;
     const float2* p2 = (const float2*)d_pts2;
-    const bool wide = npairs <= 2 * h->sm_count;
+    // 256-thread CTAs (8 warps score one pair's candidates) measured faster than 128 at every batch size tried (64..640 pairs):
+    // the batch ends with its slowest pairs, and those finish sooner with more warps each.  ORBX_FM_THREADS=128 selects the
+    // small CTA for experiments.
+    bool wide = true;
+    if (const char* e = getenv("ORBX_FM_THREADS")) wide = atoi(e) >= 256;
 #define FM_LAUNCH(SM, T) k_fm_ransac<SM, T><<<npairs, T, smem, h->stream>>>(p1, p2, d_counts, cap, max_distance, confidence, 1000, d_status, d_F, d_info)
     if (in_smem && wide) FM_LAUNCH(true, 256);
     else if (in_smem) FM_LAUNCH(true, 128);

@@ -46,7 +46,7 @@ struct FmShared {
     int nmodels[FM_MAXCHUNK];
     int count[FM_MAXCHUNK][3];
     int rot_p[4], rot_q[4];
-    int iter, niters, maxgood, chunk, stop, have, next, first_bad;
+    int iter, niters, maxgood, chunk, stop, have, next, first_bad, run_max, iter_limit;
 };
 
 __device__ __forceinline__ unsigned rng_next(unsigned long long& s)
@@ -503,6 +503,8 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             sh.chunk = chunk;
             sh.next = 0;
             sh.first_bad = chunk;
+            sh.run_max = max(sh.maxgood, FM_MODEL_POINTS - 1);
+            sh.iter_limit = sh.niters;
         }
         __syncthreads();
         if (tid < sh.chunk) {
@@ -525,18 +527,31 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         }
         const int chunk = sh.chunk;
         if (chunk == 0) break;
+        const int iter0 = sh.iter, niters0 = sh.niters;
         // ---- 2. one thread per sample: candidate matrices
         if (tid < chunk) sh.nmodels[tid] = solve7(P1, P2, sh.idx[tid], sh.models[tid]);
         __syncthreads();
-        // ---- 3. one warp per candidate: inlier count (abandoned as soon as it cannot exceed `bound`)
-        const int bound = max(sh.maxgood, FM_MODEL_POINTS - 1);
+        // ---- 3. one warp per candidate, handed out in sequence order: inlier count.
+        // Two facts a warp reads BEFORE it takes the next candidate let it do less without changing what the sequential rule
+        // (step 4) will decide.  Every candidate completed by then precedes the one taken (candidates are handed out in order),
+        // so (a) a count that cannot exceed sh.run_max -- the best exact count completed so far -- can never become the best:
+        // the candidate is abandoned as soon as that is certain; (b) once a completed count c bounds the iteration budget by
+        // update_num_iters(c), a candidate of a later iteration is never reached and is skipped altogether.
         for (;;) {
-            int m = 0;
-            if (lane == 0) m = atomicAdd(&sh.next, 1);
+            int m = 0, bound = 0, limit = 0;
+            if (lane == 0) {
+                bound = *(volatile int*)&sh.run_max;
+                limit = *(volatile int*)&sh.iter_limit;
+                __threadfence_block();
+                m = atomicAdd(&sh.next, 1);
+            }
             m = __shfl_sync(0xffffffffu, m, 0);
+            bound = __shfl_sync(0xffffffffu, bound, 0);
+            limit = __shfl_sync(0xffffffffu, limit, 0);
             if (m >= 3 * chunk) break;
             const int it = m / 3, k = m - 3 * it;
             if (k >= sh.nmodels[it]) continue;
+            if (iter0 + it >= limit) { if (lane == 0) sh.count[it][k] = 0; continue; }
             double F[9];
 #pragma unroll
             for (int i = 0; i < 9; i++) F[i] = sh.models[it][9 * k + i];
@@ -552,7 +567,11 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
                 cnt += __popc(__ballot_sync(0xffffffffu, c0 && i0 < n)) + __popc(__ballot_sync(0xffffffffu, c1 && i1 < n));
                 if (cnt + max(n - base - 64, 0) <= bound) { cnt = 0; break; }
             }
-            if (lane == 0) sh.count[it][k] = cnt;
+            if (lane == 0) {
+                sh.count[it][k] = cnt;
+                if (cnt > bound && cnt > atomicMax(&sh.run_max, cnt))
+                    atomicMin(&sh.iter_limit, update_num_iters(conf, (double)(n - cnt) / n, niters0));
+            }
             scored++;
         }
         __syncthreads();

@@ -335,12 +335,12 @@ def run_ours(args, rank, world, local_rank):
                 np.zeros(B, np.int64))
     depth = orb.pipeline_depth()
     outs = [pinned_out() for _ in range(depth)]
-    pstate = {"k": 0, "last": None}
+    pstate = {"k": 0, "last": None, "outs": outs, "fm": None}
 
     def step_pipe():
         if orb.batches_in_flight() == depth:
             pstate["last"] = orb.wait_batch()
-        orb.submit_batch(frames_np, matcher, RATIO, outs[pstate["k"] % depth])
+        orb.submit_batch(frames_np, matcher, RATIO, pstate["outs"][pstate["k"] % depth], fundamental=pstate["fm"])
         pstate["k"] += 1
 
     def drain():
@@ -496,6 +496,22 @@ def run_ours(args, rank, world, local_rank):
                                "h2d_bytes_per_step": int(p1.nbytes + p2.nbytes + fcounts.nbytes),
                                "d2h_bytes_per_step": int(fpairs * fn + fpairs * 72 + fpairs * 16),
                                "timing": "host wall clock around fmx_fundamental_batch (pageable host buffers), max over ranks"}}
+        # the sequence pipeline with the filter appended to every batch (orbx_submit_batch_filtered): frames in, keypoints,
+        # descriptors, consecutive-frame matches, their RANSAC status and F out
+        pstate["outs"] = [o + (torch.empty((B, cap), dtype=torch.uint8).pin_memory().numpy(),
+                               torch.zeros((B, 3, 3), dtype=torch.float64).pin_memory().numpy(), np.zeros(B, np.int32)) for o in outs]
+        pstate["fm"] = fm
+        orb.reset_sequence()
+        pf_ms = max_over_ranks(timed_pipe(args.steps, max(args.warmup, 2)))
+        pstate["fm"] = None
+        last = pstate["last"]
+        fundamental["sequence_pipeline"] = {
+            "value": world * B * args.steps / (pf_ms * 1e-3), "unit": "frames/s", "ms_per_step": pf_ms / args.steps,
+            "what": "e2e loop of this bench with computeFundamentalMatrix of every (frame, predecessor) pair added on the device "
+                    "(orbx_submit_batch_filtered); compare with e2e.value",
+            "matches_per_pair": float(last[4][1:].mean()), "inliers_per_pair": float(last[7][1:].mean()),
+            "note": "the synthetic sequence is a translating texture, i.e. a planar scene: F is degenerate there, the numbers time the "
+                    "filter on real match lists but say nothing about pose quality"}
         if world == 1 and not args.no_cpu:
             try:
                 import oracle

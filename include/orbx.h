@@ -276,6 +276,12 @@ ORBX_API int fmx_filter_consecutive_dev(fmx_handle h, const orbx_keypoint* d_kps
  * (cap of that extract call), F [nframes][9], ninliers [nframes].  The matches never leave the device in between. */
 ORBX_API int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence,
                             uint8_t* status, double* F, int32_t* ninliers);
+/* orbx_submit_batch with the outlier filter appended to the batch's device work (fm may be NULL: plain orbx_submit_batch):
+ * status [nframes][cap] and F [nframes][9] are written before the matching orbx_wait_batch returns, ninliers [nframes] by it. */
+ORBX_API int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_handle fm, const uint8_t* const* frames, int nframes, int w, int h_,
+                               size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts,
+                               orbx_dmatch* good, int64_t* ngood, double max_distance, double confidence, uint8_t* status,
+                               double* F, int32_t* ninliers);
 
 #ifdef __cplusplus
 }

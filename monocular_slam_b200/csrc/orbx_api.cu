@@ -46,6 +46,7 @@ struct orbx_lane {
     cudaEvent_t uploaded, computed, done;
     int32_t* counts;      // caller's arrays, filled by orbx_wait_batch
     int64_t* ngood;
+    int32_t* ninliers;
 };
 #ifndef ORBX_LANES_N
 #define ORBX_LANES_N 3
@@ -888,6 +889,8 @@ extern "C" int orbx_reset_sequence(orbx_handle h)
     return ORBX_OK;
 }
 
+static int ensure_filter_buffers(orbx_handle h);
+
 extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, orbx_dmatch* good, int64_t* ngood)
 {
     ORBX_REQUIRE(h != nullptr && m != nullptr, "orbx_match_consecutive: NULL handle");
@@ -907,8 +910,7 @@ extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio,
     // keep the last frame's descriptors (and keypoints, for orbx_filter_consecutive) for the next batch
     ORBX_CUDA(cudaMemcpyAsync(h->d_prev_desc, h->d_desc + (size_t)(n - 1) * cap * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(h->d_prev_count, h->d_counts + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
-    if (!h->d_prev_kps[0])
-        for (int i = 0; i < 2; i++) ORBX_CUDA(cudaMalloc((void**)&h->d_prev_kps[i], (size_t)h->dev_cap * sizeof(orbx_keypoint) + 256));
+    { int rc_ = ensure_filter_buffers(h); if (rc_) return rc_; }
     h->filter_prev_kps = h->have_prev ? h->d_prev_kps[h->prev_kps_cur] : nullptr;
     h->prev_kps_cur ^= 1;
     ORBX_CUDA(cudaMemcpyAsync(h->d_prev_kps[h->prev_kps_cur], h->d_kps + (size_t)(n - 1) * cap, (size_t)cap * sizeof(orbx_keypoint),
@@ -921,6 +923,21 @@ extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio,
     return ORBX_OK;
 }
 
+// outputs of the outlier filter for every lane's slots, and the keypoints of the frame before the batch
+static int ensure_filter_buffers(orbx_handle h)
+{
+    if (!h->d_fstatus) {
+        const size_t slots = (size_t)ORBX_LANES * h->max_batch;
+        ORBX_CUDA(cudaMalloc((void**)&h->d_fstatus, slots * h->dev_cap + 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_fF, slots * 9 * sizeof(double) + 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_finfo, slots * 4 * sizeof(int32_t) + 256));
+        ORBX_CUDA(cudaMallocHost((void**)&h->h_finfo, slots * 4 * sizeof(int32_t)));
+    }
+    if (!h->d_prev_kps[0])
+        for (int i = 0; i < 2; i++) ORBX_CUDA(cudaMalloc((void**)&h->d_prev_kps[i], (size_t)h->dev_cap * sizeof(orbx_keypoint) + 256));
+    return ORBX_OK;
+}
+
 extern "C" int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence, uint8_t* status, double* F,
                                        int32_t* ninliers)
 {
@@ -930,13 +947,9 @@ extern "C" int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_
     { int rc_ = require_idle(h, "orbx_filter_consecutive"); if (rc_) return rc_; }
     ORBX_CUDA(cudaSetDevice(h->device));
     const int n = h->filter_nframes, cap = h->filter_cap;
-    if (!h->d_fstatus) {
-        ORBX_CUDA(cudaMalloc((void**)&h->d_fstatus, (size_t)h->max_batch * h->dev_cap + 256));
-        ORBX_CUDA(cudaMalloc((void**)&h->d_fF, (size_t)h->max_batch * 9 * sizeof(double) + 256));
-        ORBX_CUDA(cudaMalloc((void**)&h->d_finfo, (size_t)h->max_batch * 4 * sizeof(int32_t) + 256));
-        ORBX_CUDA(cudaMallocHost((void**)&h->h_finfo, (size_t)h->max_batch * 4 * sizeof(int32_t)));
-    }
-    int rc = fmx_set_stream(fm, (void*)h->stream);
+    int rc = ensure_filter_buffers(h);
+    if (rc) return rc;
+    rc = fmx_set_stream(fm, (void*)h->stream);
     if (rc) return rc;
     rc = fmx_filter_consecutive_dev(fm, h->d_kps, h->filter_prev_kps, n, cap, h->d_good, h->d_ngood, max_distance, confidence,
                                     h->d_fstatus, h->d_fF, h->d_finfo);
@@ -998,8 +1011,18 @@ extern "C" int orbx_submit_batch(orbx_handle h, hamx_handle m, const uint8_t* co
                                  float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts, orbx_dmatch* good,
                                  int64_t* ngood)
 {
+    return orbx_submit_batch_filtered(h, m, nullptr, frames, nframes, w, hh, stride, ratio, out, desc, cap, counts, good, ngood, 0., 0.,
+                                      nullptr, nullptr, nullptr);
+}
+
+extern "C" int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_handle fm, const uint8_t* const* frames, int nframes, int w, int hh,
+                                          size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts,
+                                          orbx_dmatch* good, int64_t* ngood, double max_distance, double confidence, uint8_t* status,
+                                          double* F, int32_t* ninliers)
+{
     ORBX_REQUIRE(h != nullptr, "orbx_submit_batch: NULL handle");
     ORBX_REQUIRE(frames && out && desc && counts && (m == nullptr || (good && ngood)), "orbx_submit_batch: NULL pointer");
+    ORBX_REQUIRE(fm == nullptr || (m != nullptr && status && F && ninliers), "orbx_submit_batch_filtered: the filter needs a matcher and its output buffers");
     ORBX_REQUIRE(nframes >= 1 && nframes <= h->max_batch, "orbx_submit_batch: %d frames outside [1, max_batch=%d]", nframes, h->max_batch);
     ORBX_REQUIRE(cap >= 1 && cap <= h->dev_cap, "orbx_submit_batch: capacity %d outside [1, %d]", cap, h->dev_cap);
     ORBX_REQUIRE(frames[0] && w >= 1 && hh >= 1 && stride >= (size_t)w * h->channels, "orbx_submit_batch: bad image geometry %dx%d stride %zu", w, hh, stride);
@@ -1034,6 +1057,22 @@ extern "C" int orbx_submit_batch(orbx_handle h, hamx_handle m, const uint8_t* co
         if (rc) return rc;
         ORBX_CUDA(cudaMemcpyAsync(h->d_prev_desc, d_desc + (size_t)(nframes - 1) * cap * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, h->stream));
         ORBX_CUDA(cudaMemcpyAsync(h->d_prev_count, h->d_counts + s0 + (nframes - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+        // computeFundamentalMatrix of every (frame, predecessor) pair; the keypoints of the batch's last frame are kept for
+        // the next batch either way (stream order: the filter reads the old copy before it is overwritten)
+        rc = ensure_filter_buffers(h);
+        if (rc) return rc;
+        orbx_keypoint* prev_kps = h->d_prev_kps[h->prev_kps_cur];
+        if (fm) {
+            rc = fmx_set_stream(fm, (void*)h->stream);
+            if (rc) return rc;
+            rc = fmx_filter_consecutive_dev(fm, h->d_kps + (size_t)s0 * cap, h->have_prev ? prev_kps : nullptr, nframes, cap, d_good,
+                                            h->d_ngood + s0, max_distance, confidence, h->d_fstatus + (size_t)s0 * cap,
+                                            h->d_fF + (size_t)s0 * 9, h->d_finfo + (size_t)s0 * 4);
+            fmx_set_stream(fm, nullptr);
+            if (rc) return rc;
+        }
+        ORBX_CUDA(cudaMemcpyAsync(prev_kps, h->d_kps + ((size_t)s0 + nframes - 1) * cap, (size_t)cap * sizeof(orbx_keypoint),
+                                  cudaMemcpyDeviceToDevice, h->stream));
         h->have_prev = true;
     }
     ORBX_CUDA(cudaEventRecord(L.computed, h->stream));
@@ -1045,12 +1084,19 @@ extern "C" int orbx_submit_batch(orbx_handle h, hamx_handle m, const uint8_t* co
         ORBX_CUDA(cudaMemcpyAsync(good, d_good, (size_t)nframes * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->d2h_stream));
         ORBX_CUDA(cudaMemcpyAsync(h->h_ngood + s0, h->d_ngood + s0, (size_t)nframes * sizeof(int64_t), cudaMemcpyDeviceToHost, h->d2h_stream));
     }
+    if (fm) {
+        ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus + (size_t)s0 * cap, (size_t)nframes * cap, cudaMemcpyDeviceToHost, h->d2h_stream));
+        ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF + (size_t)s0 * 9, (size_t)nframes * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+        ORBX_CUDA(cudaMemcpyAsync(h->h_finfo + (size_t)s0 * 4, h->d_finfo + (size_t)s0 * 4, (size_t)nframes * 4 * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
     ORBX_CUDA(cudaEventRecord(L.done, h->d2h_stream));
     L.busy = true;
     L.nframes = nframes;
     L.cap = cap;
     L.counts = counts;
     L.ngood = m ? ngood : nullptr;
+    L.ninliers = fm ? ninliers : nullptr;
     h->last_nframes = 0;            // orbx_match_consecutive pairs with orbx_extract_batch only
     h->filter_nframes = 0;
     h->lane_next = (li + 1) % ORBX_LANES;
@@ -1071,6 +1117,7 @@ extern "C" int orbx_wait_batch(orbx_handle h)
     for (int f = 0; f < L.nframes; f++) {
         L.counts[f] = h->h_ctr[s0 + f].total;
         if (L.ngood) L.ngood[f] = h->h_ngood[s0 + f];
+        if (L.ninliers) L.ninliers[f] = h->h_finfo[(size_t)(s0 + f) * 4];
     }
     return check_counters(h, L.nframes, L.cap, s0);
 }

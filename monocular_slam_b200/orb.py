@@ -196,10 +196,12 @@ class ORB:
         return status, F, ninl
 
     # -- pipelined sequence mode: pipeline_depth() batches in flight (upload / kernels / download overlap across batches)
-    def submit_batch(self, frames, matcher, ratio, out):
+    def submit_batch(self, frames, matcher, ratio, out, fundamental=None, max_distance=3.0, confidence=0.85):
         """Enqueue extraction (+ consecutive-frame matching when ``matcher`` is given) of a batch and return at once.
         ``out`` = (kps[n, cap], desc[n, cap, 32], counts[n] int32, good[n, cap], ngood[n] int64): caller-owned buffers
-        (pinned for real overlap) that are complete after the matching ``wait_batch()``."""
+        (pinned for real overlap) that are complete after the matching ``wait_batch()``.  With ``fundamental`` (a
+        FundamentalFilter) the outlier filter of every (frame, predecessor) pair runs in the same submission and ``out``
+        carries three more buffers: status[n, cap] uint8, F[n, 3, 3] float64, ninliers[n] int32."""
         frames = [_gray(f) for f in frames]
         self._set_channels(frames[0])
         n = len(frames)
@@ -207,15 +209,24 @@ class ORB:
         stride = frames[0].strides[0]
         if any(f.shape != frames[0].shape or f.strides[0] != stride for f in frames):
             raise ValueError("all frames of a batch must share one shape and stride")
-        kps, desc, counts, good, ngood = out
+        kps, desc, counts, good, ngood = out[:5]
         cap = kps.shape[1]
         if kps.shape[0] < n or desc.shape[:2] != kps.shape[:2] or counts.dtype != np.int32 or ngood.dtype != np.int64:
             raise ValueError("bad output buffers")
         ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
         self._inflight = getattr(self, "_inflight", [])
-        check(_lib.lib().orbx_submit_batch(self._h, matcher._h if matcher is not None else None, ptrs, n, w, h, stride,
-                                           float(ratio), kps.ctypes.data, desc.ctypes.data, cap, counts.ctypes.data,
-                                           good.ctypes.data, ngood.ctypes.data))
+        if fundamental is not None:
+            status, F, ninl = out[5:8]
+            if status.shape[:2] != kps.shape[:2] or status.dtype != np.uint8 or F.dtype != np.float64 or ninl.dtype != np.int32:
+                raise ValueError("bad filter output buffers")
+            check(_lib.lib().orbx_submit_batch_filtered(self._h, matcher._h, fundamental._h, ptrs, n, w, h, stride, float(ratio),
+                                                        kps.ctypes.data, desc.ctypes.data, cap, counts.ctypes.data, good.ctypes.data,
+                                                        ngood.ctypes.data, float(max_distance), float(confidence), status.ctypes.data,
+                                                        F.ctypes.data, ninl.ctypes.data))
+        else:
+            check(_lib.lib().orbx_submit_batch(self._h, matcher._h if matcher is not None else None, ptrs, n, w, h, stride,
+                                               float(ratio), kps.ctypes.data, desc.ctypes.data, cap, counts.ctypes.data,
+                                               good.ctypes.data, ngood.ctypes.data))
         self._inflight.append((frames, out))     # keep the buffers alive until the batch is collected
 
     def wait_batch(self):

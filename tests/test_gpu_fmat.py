@@ -165,3 +165,37 @@ def test_filter_consecutive_keeps_matches_on_device(fm):
         prev_kps = kps[n - 1].copy()
     orb.close()
     bf.close()
+
+
+def test_pipelined_submission_with_filter_equals_blocking_calls(fm):
+    """orbx_submit_batch_filtered over 3 batches in flight == extract_batch + match_consecutive + filter_consecutive."""
+    w, h, n, nf, nb = 640, 480, 4, 800, 4
+    frames = syn.sequence(nb * n, w, h, seed=8)
+    orb = ORB(nfeatures=nf, max_size=(w, h), max_batch=n)
+    bf = BFMatcher()
+    want = []
+    for b in range(nb):
+        kps, desc, counts = orb.extract_batch(frames[b * n:(b + 1) * n])
+        cap = kps.shape[1]
+        good, ngood = orb.match_consecutive(bf, 0.8, cap, n)
+        want.append((kps, counts, good, ngood) + orb.filter_consecutive(fm, cap, n))
+    orb.reset_sequence()
+    outs = [(np.zeros((n, cap), KEYPOINT_DTYPE), np.zeros((n, cap, 32), np.uint8), np.zeros(n, np.int32), np.zeros((n, cap), DMATCH_DTYPE),
+             np.zeros(n, np.int64), np.zeros((n, cap), np.uint8), np.zeros((n, 3, 3)), np.zeros(n, np.int32)) for _ in range(nb)]
+    got = []
+    for b in range(nb):
+        if orb.batches_in_flight() == orb.pipeline_depth():
+            got.append(orb.wait_batch())
+        orb.submit_batch(frames[b * n:(b + 1) * n], bf, 0.8, outs[b], fundamental=fm)
+    while orb.batches_in_flight():
+        got.append(orb.wait_batch())
+    assert len(got) == nb
+    for b in range(nb):
+        kps, counts, good, ngood, status, F, ninl = want[b]
+        o = got[b]
+        assert np.array_equal(o[2], counts) and np.array_equal(o[4], ngood)
+        assert np.array_equal(o[5], status) and np.array_equal(o[6], F) and np.array_equal(o[7], ninl)
+        if b:
+            assert (ninl >= 0).all()
+    orb.close()
+    bf.close()

@@ -30,7 +30,13 @@ namespace {
 // CTA size: 256 threads by default (2 pairs per SM), 128 as a tuning alternative (4 pairs per SM); see fm_launch.
 constexpr int FM_MAXWARPS = 8;
 constexpr int FM_MAXCHUNK = 128;      // iterations solved + scored per round
-constexpr int FM_FIRSTCHUNK = 16;     // a short first round establishes a count that lets later rounds abandon bad candidates early
+#ifndef FM_FIRSTCHUNK_N
+#define FM_FIRSTCHUNK_N 16
+#endif
+#ifndef FM_CHUNKDIV
+#define FM_CHUNKDIV 4
+#endif
+constexpr int FM_FIRSTCHUNK = FM_FIRSTCHUNK_N;     // a short first round establishes a count that lets later rounds abandon bad candidates early
 constexpr int FM_MODEL_POINTS = 7;
 constexpr int FM_SMEM_POINTS = 9000;  // pairs with at most this many correspondences keep them in shared memory (16 B each)
 
@@ -493,7 +499,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             // iterations per round: a quarter of the remaining budget (the budget usually collapses as soon as a good sample is
             // scored, and everything scored past that point is wasted), between FM_FIRSTCHUNK and FM_MAXCHUNK
             const int remaining = sh.niters - sh.iter;
-            const int chunk = min(remaining, round == 0 ? FM_FIRSTCHUNK : min(FM_MAXCHUNK, max(FM_FIRSTCHUNK, remaining / 4)));
+            const int chunk = min(remaining, round == 0 ? FM_FIRSTCHUNK : min(FM_MAXCHUNK, max(FM_FIRSTCHUNK, remaining / FM_CHUNKDIV)));
             unsigned long long rng = sh.rng;
             for (int i = 0; i < chunk; i++) {
                 sh.rng_at[i] = rng;

@@ -1,4 +1,5 @@
-"""ctypes wrapper around oracle/liborb_oracle.so (CPU restatement of the reference's ORB + BF-Hamming path).
+"""ctypes wrapper around oracle/liborb_oracle.so (CPU restatement of the reference's ORB + BF-Hamming path and of the
+fundamental-matrix outlier filter that follows it: orb_oracle.c, fmat_oracle.c).
 
 TEST INFRASTRUCTURE ONLY -- see the header of oracle/orb_oracle.c.  The product package
 (monocular_slam_b200) never imports this module; tests/, __graft_entry__.smoke() and

@@ -31,12 +31,12 @@ namespace {
 constexpr int FM_MAXWARPS = 8;
 constexpr int FM_MAXCHUNK = 128;      // iterations solved + scored per round
 #ifndef FM_FIRSTCHUNK_N
-#define FM_FIRSTCHUNK_N 16
+#define FM_FIRSTCHUNK_N 64
 #endif
 #ifndef FM_CHUNKDIV
-#define FM_CHUNKDIV 4
+#define FM_CHUNKDIV 2
 #endif
-constexpr int FM_FIRSTCHUNK = FM_FIRSTCHUNK_N;     // a short first round establishes a count that lets later rounds abandon bad candidates early
+constexpr int FM_FIRSTCHUNK = FM_FIRSTCHUNK_N;     // iterations of the first round (64 / half the remaining budget measured best: profiles/README.md)
 constexpr int FM_MODEL_POINTS = 7;
 constexpr int FM_SMEM_POINTS = 9000;  // pairs with at most this many correspondences keep them in shared memory (16 B each)
 
@@ -496,8 +496,9 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         // coincident points) changes what the generator produces next, so the chunk is redone from there by the
         // sequential rule.
         if (tid == 0) {
-            // iterations per round: a quarter of the remaining budget (the budget usually collapses as soon as a good sample is
-            // scored, and everything scored past that point is wasted), between FM_FIRSTCHUNK and FM_MAXCHUNK
+            // iterations per round: 1/FM_CHUNKDIV of the remaining budget, between FM_FIRSTCHUNK and FM_MAXCHUNK.  The budget
+            // usually collapses as soon as a good sample is scored; candidates past that point are skipped by the running
+            // iteration limit of step 3, so a long round costs little, and it has fewer serial sections than several short ones.
             const int remaining = sh.niters - sh.iter;
             const int chunk = min(remaining, round == 0 ? FM_FIRSTCHUNK : min(FM_MAXCHUNK, max(FM_FIRSTCHUNK, remaining / FM_CHUNKDIV)));
             unsigned long long rng = sh.rng;

@@ -199,3 +199,25 @@ def test_pipelined_submission_with_filter_equals_blocking_calls(fm):
             assert (ninl >= 0).all()
     orb.close()
     bf.close()
+
+
+def test_large_pairs_use_the_global_memory_path(fm):
+    """More than 9000 correspondences per pair (BASELINE configs[2]: 4K frames, 8000 keypoints, map-sized match lists) do not fit the
+    shared-memory copy of the points; the kernel then reads them from global memory -- same results."""
+    n = 9600
+    p1, p2 = syn.two_view_matches(41, n, 0.6, 0.6, (3840, 2160))
+    status, F, ninl = fm.find_batch(p1[None], p2[None], [n])
+    Fo, mo, iters = oracle.fm_ransac(p1, p2, 3.0, 0.85)
+    assert np.array_equal(status[0], mo) and fm.last_info(1)[0, 1] == iters
+    assert rel(F[0], oracle.fm_8point(p1[mo > 0], p2[mo > 0])) <= F_RTOL
+    # the same pair inside a batch whose other pairs are small
+    q1 = np.zeros((3, n, 2), np.float32)
+    q2 = np.zeros((3, n, 2), np.float32)
+    q1[1], q2[1] = p1, p2
+    q1[0, :500], q2[0, :500] = syn.two_view_matches(42, 500, 0.7, 0.5)
+    q1[2, :20], q2[2, :20] = syn.two_view_matches(43, 20, 0.9, 0.3)
+    s3, F3, n3 = fm.find_batch(q1, q2, [500, n, 20])
+    assert np.array_equal(s3[1], status[0]) and np.array_equal(F3[1], F[0])
+    for i, cnt in ((0, 500), (2, 20)):
+        _, m_i, _ = oracle.fm_ransac(q1[i, :cnt], q2[i, :cnt], 3.0, 0.85)
+        assert np.array_equal(s3[i, :cnt], m_i)

@@ -272,10 +272,20 @@ ORBX_API int fmx_fundamental_batch_dev(fmx_handle h, const float* d_pts1, const 
 ORBX_API int fmx_filter_consecutive_dev(fmx_handle h, const orbx_keypoint* d_kps, const orbx_keypoint* d_prev_kps, int nframes, int cap,
                                const orbx_dmatch* d_good, const int64_t* d_ngood, double max_distance, double confidence,
                                uint8_t* d_status, double* d_F, int32_t* d_info);
+/* The same for the steady-state pattern of hamx_match_back_dev: pair (f, j) = (frame f, frame f-j), j = 1..back, at index
+ * f*back + j-1 of d_good [nframes*back][cap] / d_ngood / d_status / d_F / d_info; predecessors before the batch come from the
+ * keypoint history d_hist_kps [nhist][cap] (entry 0 = the frame just before the batch). */
+ORBX_API int fmx_filter_back_dev(fmx_handle h, const orbx_keypoint* d_kps, int nframes, int cap, int back, const orbx_keypoint* d_hist_kps,
+                        int nhist, const orbx_dmatch* d_good, const int64_t* d_ngood, double max_distance, double confidence,
+                        uint8_t* d_status, double* d_F, int32_t* d_info);
 /* Host-buffer form for the batch last passed to orbx_extract_batch + orbx_match_consecutive on `h`: status [nframes][cap]
  * (cap of that extract call), F [nframes][9], ninliers [nframes].  The matches never leave the device in between. */
 ORBX_API int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence,
                             uint8_t* status, double* F, int32_t* ninliers);
+/* The filter for the pairs orbx_match_back just matched: status [nframes][back][cap], F [nframes][back][9], ninliers [nframes][back]
+ * (computeFundamentalMatrix as called in the loop at src/CameraPoseEstimator.cpp:405-419). */
+ORBX_API int orbx_filter_back(orbx_handle h, fmx_handle fm, double max_distance, double confidence, uint8_t* status, double* F,
+                     int32_t* ninliers);
 /* orbx_submit_batch with the outlier filter appended to the batch's device work (fm may be NULL: plain orbx_submit_batch):
  * status [nframes][cap] and F [nframes][9] are written before the matching orbx_wait_batch returns, ninliers [nframes] by it. */
 ORBX_API int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_handle fm, const uint8_t* const* frames, int nframes, int w, int h_,

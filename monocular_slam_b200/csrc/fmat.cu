@@ -703,21 +703,25 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     }
 }
 
-// correspondences of consecutive frames from the device-resident keypoints and match lists of the sequence mode
-__global__ void k_fm_gather(const orbx_keypoint* __restrict__ kps, const orbx_keypoint* __restrict__ prev_kps, int cap,
+// Correspondences from the device-resident keypoints and match lists of the sequence mode.  Pair p = f*back + (j-1) is
+// (frame f, its j-th predecessor), j = 1..back; predecessors before the batch come from the history [nhist][cap]
+// (entry 0 = the frame just before the batch); pairs without a predecessor get count 0.
+__global__ void k_fm_gather(const orbx_keypoint* __restrict__ kps, const orbx_keypoint* __restrict__ hist_kps, int nhist, int back, int cap,
                             const orbx_dmatch* __restrict__ good, const long long* __restrict__ ngood,
                             float2* __restrict__ pts1, float2* __restrict__ pts2, int32_t* __restrict__ counts)
 {
-    const int f = blockIdx.y;
+    const int p = blockIdx.y, f = p / back, j = p - f * back + 1;
     const orbx_keypoint* kq = kps + (size_t)f * cap;
-    const orbx_keypoint* kt = f ? kps + (size_t)(f - 1) * cap : prev_kps;
-    const int n = kt ? (int)min((long long)cap, ngood[f]) : 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) counts[f] = n;
+    const orbx_keypoint* kt = nullptr;
+    if (f - j >= 0) kt = kps + (size_t)(f - j) * cap;
+    else if (hist_kps && j - f - 1 < nhist) kt = hist_kps + (size_t)(j - f - 1) * cap;
+    const int n = kt ? (int)min((long long)cap, ngood[p]) : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[p] = n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const orbx_dmatch m = good[(size_t)f * cap + i];
+        const orbx_dmatch m = good[(size_t)p * cap + i];
         const orbx_keypoint a = kq[m.query_idx], b = kt[m.train_idx];
-        pts1[(size_t)f * cap + i] = make_float2(a.x, a.y);
-        pts2[(size_t)f * cap + i] = make_float2(b.x, b.y);
+        pts1[(size_t)p * cap + i] = make_float2(a.x, a.y);
+        pts2[(size_t)p * cap + i] = make_float2(b.x, b.y);
     }
 }
 
@@ -915,23 +919,33 @@ extern "C" int fmx_compute_fundamental(fmx_handle h, const orbx_keypoint* kps1, 
     return rc;
 }
 
-extern "C" int fmx_filter_consecutive_dev(fmx_handle h, const orbx_keypoint* d_kps, const orbx_keypoint* d_prev_kps, int nframes, int cap,
-                                          const orbx_dmatch* d_good, const int64_t* d_ngood, double max_distance, double confidence,
-                                          uint8_t* d_status, double* d_F, int32_t* d_info)
+extern "C" int fmx_filter_back_dev(fmx_handle h, const orbx_keypoint* d_kps, int nframes, int cap, int back, const orbx_keypoint* d_hist_kps,
+                                   int nhist, const orbx_dmatch* d_good, const int64_t* d_ngood, double max_distance, double confidence,
+                                   uint8_t* d_status, double* d_F, int32_t* d_info)
 {
-    ORBX_REQUIRE(h != nullptr, "fmx_filter_consecutive_dev: NULL handle");
-    ORBX_REQUIRE(nframes >= 0 && cap >= 1, "fmx_filter_consecutive_dev: nframes %d / cap %d out of range", nframes, cap);
+    ORBX_REQUIRE(h != nullptr, "fmx_filter_back_dev: NULL handle");
+    ORBX_REQUIRE(nframes >= 0 && cap >= 1 && back >= 1 && nhist >= 0, "fmx_filter_back_dev: nframes %d / cap %d / back %d / nhist %d out of range",
+                 nframes, cap, back, nhist);
     if (nframes == 0) return ORBX_OK;
-    ORBX_REQUIRE(d_kps && d_good && d_ngood && d_status && d_F && d_info, "fmx_filter_consecutive_dev: NULL pointer");
+    ORBX_REQUIRE(d_kps && d_good && d_ngood && d_status && d_F && d_info, "fmx_filter_back_dev: NULL pointer");
     ORBX_CUDA(cudaSetDevice(h->device));
-    const size_t np = (size_t)nframes, pts_bytes = np * cap * sizeof(float2);
+    const int npairs = nframes * back;
+    const size_t np = (size_t)npairs, pts_bytes = np * cap * sizeof(float2);
     int rc = fm_grow(&h->d_p1, &h->p1_bytes, pts_bytes);
     if (!rc) rc = fm_grow(&h->d_p2, &h->p2_bytes, pts_bytes);
     if (!rc) rc = fm_grow(&h->d_counts, &h->counts_bytes, np * sizeof(int32_t));
     if (rc) return rc;
-    k_fm_gather<<<dim3(div_up(cap, 256 * 2), nframes), 256, 0, h->stream>>>(d_kps, d_prev_kps, cap, d_good, (const long long*)d_ngood,
-                                                                           h->d_p1, h->d_p2, h->d_counts);
+    k_fm_gather<<<dim3(div_up(cap, 256 * 2), npairs), 256, 0, h->stream>>>(d_kps, d_hist_kps, nhist, back, cap, d_good, (const long long*)d_ngood,
+                                                                          h->d_p1, h->d_p2, h->d_counts);
     ORBX_CUDA(cudaGetLastError());
-    return fm_launch(h, (const float*)h->d_p1, (const float*)h->d_p2, h->d_counts, nframes, cap, cap, max_distance, confidence, d_status, d_F,
+    return fm_launch(h, (const float*)h->d_p1, (const float*)h->d_p2, h->d_counts, npairs, cap, cap, max_distance, confidence, d_status, d_F,
                      d_info);
+}
+
+extern "C" int fmx_filter_consecutive_dev(fmx_handle h, const orbx_keypoint* d_kps, const orbx_keypoint* d_prev_kps, int nframes, int cap,
+                                          const orbx_dmatch* d_good, const int64_t* d_ngood, double max_distance, double confidence,
+                                          uint8_t* d_status, double* d_F, int32_t* d_info)
+{
+    return fmx_filter_back_dev(h, d_kps, nframes, cap, 1, d_prev_kps, d_prev_kps ? 1 : 0, d_good, d_ngood, max_distance, confidence, d_status,
+                               d_F, d_info);
 }

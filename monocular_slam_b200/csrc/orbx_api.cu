@@ -108,6 +108,10 @@ struct orbx_context {
     orbx_dmatch* d_good_back;
     int64_t* d_ngood_back;
     int64_t* h_ngood_back;
+    // orbx_filter_back: keypoint history parallel to d_hist, and the geometry of the batch orbx_match_back last ran on
+    orbx_keypoint* d_hist_kps[2];
+    int back_n, back_back, back_cap, back_nhist;
+    uint8_t* d_fstatus_back; double* d_fF_back; int32_t* d_finfo_back; int32_t* h_finfo_back;
     // single-frame path: the launch sequence of run_extract_on(frame 0) captured as CUDA graphs, one per (mode, capacity);
     // dropped whenever the geometry changes (the resize tables' addresses are baked into the kernel arguments)
     struct { cudaGraphExec_t exec; int mode, cap; } graphs[4];
@@ -427,6 +431,8 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (h->h_finfo) cudaFreeHost(h->h_finfo);
     cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]); cudaFree(h->d_hist_counts[0]); cudaFree(h->d_hist_counts[1]);
     cudaFree(h->d_good_back); cudaFree(h->d_ngood_back);
+    cudaFree(h->d_hist_kps[0]); cudaFree(h->d_hist_kps[1]); cudaFree(h->d_fstatus_back); cudaFree(h->d_fF_back); cudaFree(h->d_finfo_back);
+    if (h->h_finfo_back) cudaFreeHost(h->h_finfo_back);
     if (h->h_ngood_back) cudaFreeHost(h->h_ngood_back);
     if (h->h_ngood) cudaFreeHost(h->h_ngood);
     if (h->events) { for (cudaEvent_t e : *h->events) cudaEventDestroy(e); delete h->events; }
@@ -721,6 +727,7 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
         if (rc) return rc;
         h->last_nframes = (mode & ORBX_DO_DESC) ? 1 : 0;
         h->filter_nframes = 0;
+        h->back_n = 0;
         h->last_cap = dcap;
         ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, offsetof(FrameCounters, hist), cudaMemcpyDeviceToHost, h->stream));
         ORBX_CUDA(cudaMemcpyAsync(out, h->d_kps, (size_t)dcap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->stream));
@@ -752,6 +759,7 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
     }
     h->last_nframes = (mode & ORBX_DO_DESC) ? nframes : 0;
     h->filter_nframes = 0;
+    h->back_n = 0;
     h->last_cap = dcap;
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
@@ -963,6 +971,37 @@ extern "C" int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_
     return ORBX_OK;
 }
 
+extern "C" int orbx_filter_back(orbx_handle h, fmx_handle fm, double max_distance, double confidence, uint8_t* status, double* F,
+                                int32_t* ninliers)
+{
+    ORBX_REQUIRE(h != nullptr && fm != nullptr, "orbx_filter_back: NULL handle");
+    ORBX_REQUIRE(status && F && ninliers, "orbx_filter_back: NULL pointer");
+    ORBX_REQUIRE(h->back_n >= 1, "orbx_filter_back: orbx_match_back has not run on this handle's last batch");
+    { int rc_ = require_idle(h, "orbx_filter_back"); if (rc_) return rc_; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int n = h->back_n, back = h->back_back, cap = h->back_cap, npairs = n * back;
+    if (!h->d_fstatus_back) {
+        const size_t slots = (size_t)h->max_batch * ORBX_MAX_BACK;
+        ORBX_CUDA(cudaMalloc((void**)&h->d_fstatus_back, slots * h->dev_cap + 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_fF_back, slots * 9 * sizeof(double) + 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_finfo_back, slots * 4 * sizeof(int32_t) + 256));
+        ORBX_CUDA(cudaMallocHost((void**)&h->h_finfo_back, slots * 4 * sizeof(int32_t)));
+    }
+    int rc = fmx_set_stream(fm, (void*)h->stream);
+    if (rc) return rc;
+    // orbx_match_back matched against the history that is now the inactive buffer (hist_cur was flipped after the update)
+    rc = fmx_filter_back_dev(fm, h->d_kps, n, cap, back, h->d_hist_kps[h->hist_cur ^ 1], h->back_nhist, h->d_good_back, h->d_ngood_back,
+                             max_distance, confidence, h->d_fstatus_back, h->d_fF_back, h->d_finfo_back);
+    fmx_set_stream(fm, nullptr);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus_back, (size_t)npairs * cap, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF_back, (size_t)npairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->h_finfo_back, h->d_finfo_back, (size_t)npairs * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < npairs; i++) ninliers[i] = h->h_finfo_back[4 * i];
+    return ORBX_OK;
+}
+
 extern "C" int orbx_match_back(orbx_handle h, hamx_handle m, int back, float ratio, orbx_dmatch* good, int64_t* ngood)
 {
     ORBX_REQUIRE(h != nullptr && m != nullptr, "orbx_match_back: NULL handle");
@@ -976,6 +1015,7 @@ extern "C" int orbx_match_back(orbx_handle h, hamx_handle m, int back, float rat
         for (int i = 0; i < 2; i++) {
             ORBX_CUDA(cudaMalloc((void**)&h->d_hist[i], (size_t)ORBX_MAX_BACK * h->dev_cap * 32 + 256));
             ORBX_CUDA(cudaMalloc((void**)&h->d_hist_counts[i], 256));
+            ORBX_CUDA(cudaMalloc((void**)&h->d_hist_kps[i], (size_t)ORBX_MAX_BACK * h->dev_cap * sizeof(orbx_keypoint) + 256));
         }
         ORBX_CUDA(cudaMalloc((void**)&h->d_good_back, (size_t)h->max_batch * ORBX_MAX_BACK * h->dev_cap * sizeof(orbx_dmatch) + 256));
         ORBX_CUDA(cudaMalloc((void**)&h->d_ngood_back, (size_t)h->max_batch * ORBX_MAX_BACK * sizeof(int64_t) + 256));
@@ -993,6 +1033,14 @@ extern "C" int orbx_match_back(orbx_handle h, hamx_handle m, int back, float rat
                                           h->d_hist[cur ^ 1], h->d_hist_counts[cur ^ 1]);
     hamx_set_stream(m, nullptr);
     if (rc) return rc;
+    // the keypoint history follows the descriptor history (most recent frame first), for orbx_filter_back
+    for (int hi = 0; hi < ORBX_MAX_BACK; hi++) {
+        const int src = n - 1 - hi;
+        const orbx_keypoint* from = src >= 0 ? h->d_kps + (size_t)src * cap : (-src - 1 < h->nhist ? h->d_hist_kps[cur] + (size_t)(-src - 1) * cap : nullptr);
+        if (from)
+            ORBX_CUDA(cudaMemcpyAsync(h->d_hist_kps[cur ^ 1] + (size_t)hi * cap, from, (size_t)cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->back_n = n; h->back_back = back; h->back_cap = cap; h->back_nhist = std::min(h->nhist, back);
     h->hist_cur = cur ^ 1;
     h->nhist = std::min(ORBX_MAX_BACK, h->nhist + n);
     h->hist_cap = cap;
@@ -1099,6 +1147,7 @@ extern "C" int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_hand
     L.ninliers = fm ? ninliers : nullptr;
     h->last_nframes = 0;            // orbx_match_consecutive pairs with orbx_extract_batch only
     h->filter_nframes = 0;
+    h->back_n = 0;
     h->lane_next = (li + 1) % ORBX_LANES;
     return ORBX_OK;
 }

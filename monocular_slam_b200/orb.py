@@ -195,6 +195,16 @@ class ORB:
                                                  status.ctypes.data, F.ctypes.data, ninl.ctypes.data))
         return status, F, ninl
 
+    def filter_back(self, fundamental, back, cap, nframes, max_distance=3.0, confidence=0.85):
+        """computeFundamentalMatrix for every (frame f, frame f-j) pair match_back just matched (the loop at
+        src/CameraPoseEstimator.cpp:405-419).  Returns (status[nframes, back, cap], F[nframes, back, 3, 3], ninliers[nframes, back])."""
+        status = np.zeros((nframes, back, cap), np.uint8)
+        F = np.zeros((nframes, back, 3, 3), np.float64)
+        ninl = np.zeros((nframes, back), np.int32)
+        check(_lib.lib().orbx_filter_back(self._h, fundamental._h, float(max_distance), float(confidence), status.ctypes.data,
+                                          F.ctypes.data, ninl.ctypes.data))
+        return status, F, ninl
+
     # -- pipelined sequence mode: pipeline_depth() batches in flight (upload / kernels / download overlap across batches)
     def submit_batch(self, frames, matcher, ratio, out, fundamental=None, max_distance=3.0, confidence=0.85):
         """Enqueue extraction (+ consecutive-frame matching when ``matcher`` is given) of a batch and return at once.

@@ -221,3 +221,35 @@ def test_large_pairs_use_the_global_memory_path(fm):
     for i, cnt in ((0, 500), (2, 20)):
         _, m_i, _ = oracle.fm_ransac(q1[i, :cnt], q2[i, :cnt], 3.0, 0.85)
         assert np.array_equal(s3[i, :cnt], m_i)
+
+
+def test_filter_back_matches_per_pair_calls(fm):
+    """orbx_filter_back (frame f against its 3 predecessors, history carried across batches) == fmx_compute_fundamental on the
+    downloaded keypoints and match lists of every pair."""
+    w, h, n, nf, back = 640, 480, 4, 800, 3
+    frames = syn.sequence(3 * n, w, h, seed=13)
+    orb = ORB(nfeatures=nf, max_size=(w, h), max_batch=n)
+    bf = BFMatcher()
+    all_kps = []
+    for b in range(3):
+        kps, desc, counts = orb.extract_batch(frames[b * n:(b + 1) * n])
+        cap = kps.shape[1]
+        good, ngood = orb.match_back(bf, back, 0.8, cap, n)
+        good = good.reshape(n, back, cap)
+        ngood = ngood.reshape(n, back)
+        status, F, ninl = orb.filter_back(fm, back, cap, n)
+        all_kps.extend(kps[i].copy() for i in range(n))
+        for f in range(n):
+            g = b * n + f
+            for j in range(1, back + 1):
+                if g - j < 0:
+                    assert ninl[f, j - 1] == 0 and not status[f, j - 1].any() and ngood[f, j - 1] == 0
+                    continue
+                m = good[f, j - 1, :ngood[f, j - 1]]
+                Fh, sh, nh = fm.compute_fundamental(all_kps[g], all_kps[g - j], m)
+                assert np.array_equal(status[f, j - 1, :len(m)], sh) and ninl[f, j - 1] == nh and np.array_equal(F[f, j - 1], Fh)
+    with pytest.raises(Exception):
+        orb.extract_batch(frames[:n])
+        orb.filter_back(fm, back, cap, n)           # no match_back on the new batch yet
+    orb.close()
+    bf.close()

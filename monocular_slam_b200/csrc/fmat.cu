@@ -40,6 +40,13 @@ constexpr int FM_FIRSTCHUNK = FM_FIRSTCHUNK_N;     // iterations of the first ro
 constexpr int FM_MODEL_POINTS = 7;
 constexpr int FM_SMEM_POINTS = 9000;  // pairs with at most this many correspondences keep them in shared memory (16 B each)
 
+#ifdef FM_PROFILE
+__device__ unsigned long long g_fm_prof[8];     // cycles of thread 0 per phase, summed over CTAs (debug builds only)
+#define FM_TICK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_fm_prof[k], (unsigned long long)(now_ - tick_)); tick_ = now_; } } while (0)
+#else
+#define FM_TICK(k) do { } while (0)
+#endif
+
 struct FmShared {
     double models[FM_MAXCHUNK][27];
     double best[9];
@@ -52,6 +59,7 @@ struct FmShared {
     int nmodels[FM_MAXCHUNK];
     int count[FM_MAXCHUNK][3];
     int rot_p[4], rot_q[4];
+    int cmax[4];                      // largest |x1| |y1| |x2| |y2| of the pair (float bits; non-negative floats order like ints)
     int iter, niters, maxgood, chunk, stop, have, next, first_bad, run_max, iter_limit;
 };
 
@@ -311,9 +319,62 @@ __device__ __forceinline__ int classify(const double* F, float2 p1, float2 p2, d
     return regular && (in || out) ? (in ? 1 : 0) : -1;
 }
 
+// Single-precision pre-classification of the same test, with rigorous error bounds (u = 2^-24):
+//   a_f = fma(F0f, x, fma(F1f, y, F2f)) differs from the value OpenCV computes in double by at most 3u(|F0 x| + |F1 y| + |F2|);
+//   d_f = fma(x', a_f, fma(y', b_f, c_f)) by at most 5u(|x'| A + |y'| B + C), A, B, C being those magnitude sums.
+// The magnitude sums are bounded once per candidate with the largest coordinates of the pair (Cand32), with 4u / 8u instead of
+// 3u / 5u.  A point is decided here only if it is inside (outside) for every value within the bounds, against thresholds moved
+// by a further 4e-6 (covers the roundings of the bound arithmetic itself); otherwise -1 -> the double-precision classify.
+struct Cand32 {
+    float F[9];
+    float ea2, eb2, E2;      // side 2: line F p1, distance of p2
+    float ea1, eb1, E1;      // side 1: line F' p2, distance of p1
+};
+
+__device__ __forceinline__ void cand32_init(Cand32& c, const double* F, const float* cmax /* X1 Y1 X2 Y2 */)
+{
+#pragma unroll
+    for (int i = 0; i < 9; i++) c.F[i] = __double2float_rn(F[i]);
+    const float X1 = cmax[0], Y1 = cmax[1], X2 = cmax[2], Y2 = cmax[3], tiny = 1e-30f;
+    const float u4 = 2.384185791015625e-07f, u8 = 4.76837158203125e-07f;       // 4 * 2^-24, 8 * 2^-24
+    const float A2 = fmaf(fabsf(c.F[0]), X1, fmaf(fabsf(c.F[1]), Y1, fabsf(c.F[2]))) + tiny;
+    const float B2 = fmaf(fabsf(c.F[3]), X1, fmaf(fabsf(c.F[4]), Y1, fabsf(c.F[5]))) + tiny;
+    const float C2 = fmaf(fabsf(c.F[6]), X1, fmaf(fabsf(c.F[7]), Y1, fabsf(c.F[8]))) + tiny;
+    c.ea2 = u4 * A2; c.eb2 = u4 * B2; c.E2 = u8 * fmaf(X2, A2, fmaf(Y2, B2, C2));
+    const float A1 = fmaf(fabsf(c.F[0]), X2, fmaf(fabsf(c.F[3]), Y2, fabsf(c.F[6]))) + tiny;
+    const float B1 = fmaf(fabsf(c.F[1]), X2, fmaf(fabsf(c.F[4]), Y2, fabsf(c.F[7]))) + tiny;
+    const float C1 = fmaf(fabsf(c.F[2]), X2, fmaf(fabsf(c.F[5]), Y2, fabsf(c.F[8]))) + tiny;
+    c.ea1 = u4 * A1; c.eb1 = u4 * B1; c.E1 = u8 * fmaf(X1, A1, fmaf(Y1, B1, C1));
+}
+
+// one side: 1 surely inside, 0 surely outside, -1 undecided
+__device__ __forceinline__ int side32(float a, float b, float d, float ea, float eb, float E, float tlo32, float thi32)
+{
+    const float la = fmaxf(fabsf(a) - ea, 0.f), lb = fmaxf(fabsf(b) - eb, 0.f), ha = fabsf(a) + ea, hb = fabsf(b) + eb;
+    const float den_lo = fmaf(la, la, lb * lb), den_hi = fmaf(ha, ha, hb * hb);
+    const float dhi = fabsf(d) + E, dlo = fmaxf(fabsf(d) - E, 0.f);
+    const bool regular = den_lo > 1e-30f && den_hi < 1e30f && dhi < 1e15f;        // no overflow / underflow anywhere above
+    const bool in = dhi * dhi <= tlo32 * den_lo, out = dlo * dlo >= thi32 * den_hi;
+    return regular ? (in ? 1 : (out ? 0 : -1)) : -1;
+}
+
+__device__ __forceinline__ int classify32(const Cand32& c, float2 p1, float2 p2, float tlo32, float thi32)
+{
+    const float x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
+    const float a2 = fmaf(c.F[0], x1, fmaf(c.F[1], y1, c.F[2])), b2 = fmaf(c.F[3], x1, fmaf(c.F[4], y1, c.F[5]));
+    const float c2 = fmaf(c.F[6], x1, fmaf(c.F[7], y1, c.F[8])), d2 = fmaf(x2, a2, fmaf(y2, b2, c2));
+    const float a1 = fmaf(c.F[0], x2, fmaf(c.F[3], y2, c.F[6])), b1 = fmaf(c.F[1], x2, fmaf(c.F[4], y2, c.F[7]));
+    const float c1 = fmaf(c.F[2], x2, fmaf(c.F[5], y2, c.F[8])), d1 = fmaf(x1, a1, fmaf(y1, b1, c1));
+    const int s2 = side32(a2, b2, d2, c.ea2, c.eb2, c.E2, tlo32, thi32), s1 = side32(a1, b1, d1, c.ea1, c.eb1, c.E1, tlo32, thi32);
+    // inlier needs both sides inside; one side outside is enough for an outlier
+    return (s1 == 0 || s2 == 0) ? 0 : ((s1 == 1 && s2 == 1) ? 1 : -1);
+}
+
+// double-precision decision for one point: division-free classification, then OpenCV's own expression (F: the matrix in
+// registers, or NULL to read it from Fm)
 __device__ __forceinline__ bool is_inlier(const double* F, const double* Fm, float2 p1, float2 p2, float t2, double tlo, double thi)
 {
-    const int c = classify(F, p1, p2, tlo, thi);
+    const int c = classify(F ? F : Fm, p1, p2, tlo, thi);
     return c >= 0 ? c != 0 : is_inlier_exact(Fm, p1, p2, t2);
 }
 
@@ -380,8 +441,12 @@ __device__ void jacobi9_warp(FmShared& sh, int lane)
                 const double apq = sh.A[p * 9 + q];
                 double cs = 1., sn = 0.;
                 if (apq != 0) {
-                    const double theta = (sh.A[q * 9 + q] - sh.A[p * 9 + p]) / (2 * apq);
-                    const double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
+                    // The tangent only has to be good enough for the iteration to converge (an error of 1e-7 leaves that much of
+                    // a_pq for the next sweep), so it is computed in single precision; the rotation itself is orthogonal to
+                    // double precision because cs and sn are derived from that one t in double.
+                    const float theta = (float)(sh.A[q * 9 + q] - sh.A[p * 9 + p]) / (2.f * (float)apq);
+                    const float tf = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));
+                    const double t = (theta == theta) ? (double)tf : 0.;           // 0/0 or inf/inf in float: skip this pair
                     cs = rsqrt(t * t + 1);
                     sn = t * cs;
                 }
@@ -472,16 +537,31 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     // for pose estimation; the filter reports "no model" (0 inliers) for fewer than 15 correspondences.
     if (n < 15) return;
 
-    if (SMEM_POINTS) {
+    if (tid < 4) sh.cmax[tid] = 0;
+    __syncthreads();
+    {
         float2* s1 = reinterpret_cast<float2*>(fm_smem + sizeof(FmShared));
         float2* s2 = s1 + n;
-        for (int i = tid; i < n; i += FM_THREADS) { s1[i] = P1[i]; s2[i] = P2[i]; }
-        P1 = s1; P2 = s2;
+        float mx[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = tid; i < n; i += FM_THREADS) {
+            const float2 a = P1[i], b = P2[i];
+            if (SMEM_POINTS) { s1[i] = a; s2[i] = b; }
+            mx[0] = fmaxf(mx[0], fabsf(a.x)); mx[1] = fmaxf(mx[1], fabsf(a.y));
+            mx[2] = fmaxf(mx[2], fabsf(b.x)); mx[3] = fmaxf(mx[3], fabsf(b.y));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+            if (lane == 0) atomicMax(&sh.cmax[k], __float_as_int(mx[k]));
+        }
+        if (SMEM_POINTS) { P1 = s1; P2 = s2; }
     }
     if (thr <= 0) thr = 3;
     if (conf < DBL_EPSILON || conf > 1 - DBL_EPSILON) conf = 0.99;
     const float t2 = __double2float_rn(thr * thr);
     const double tlo = (double)t2 * (1. - 1e-9), thi = (double)t2 * (1. + 1e-6);
+    const float tlo32 = __double2float_rd(tlo * (1. - 4e-6)), thi32 = __double2float_ru(thi * (1. + 4e-6));
     const unsigned nmod = (unsigned)(0x100000000ULL / (unsigned)n);
     if (tid == 0) {
         sh.rng = 0xffffffffffffffffULL;
@@ -489,7 +569,11 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     }
     __syncthreads();
 
+#ifdef FM_PROFILE
+    long long tick_ = clock64();
+#endif
     int scored = 0;
+    const float cm[4] = {__int_as_float(sh.cmax[0]), __int_as_float(sh.cmax[1]), __int_as_float(sh.cmax[2]), __int_as_float(sh.cmax[3])};
     for (int round = 0;; round++) {
         // ---- 1. samples of the next chunk of iterations: one thread draws the index tuples (integer work only), then every
         // sample's collinearity test runs in parallel.  A rejected sample (rare: three points exactly on a line, or
@@ -513,6 +597,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             sh.run_max = max(sh.maxgood, FM_MODEL_POINTS - 1);
             sh.iter_limit = sh.niters;
         }
+        FM_TICK(0);
         __syncthreads();
         if (tid < sh.chunk) {
             float2 a[FM_MODEL_POINTS], b[FM_MODEL_POINTS];
@@ -533,11 +618,13 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             __syncthreads();
         }
         const int chunk = sh.chunk;
+        FM_TICK(1);
         if (chunk == 0) break;
         const int iter0 = sh.iter, niters0 = sh.niters;
         // ---- 2. one thread per sample: candidate matrices
         if (tid < chunk) sh.nmodels[tid] = solve7(P1, P2, sh.idx[tid], sh.models[tid]);
         __syncthreads();
+        FM_TICK(2);
         // ---- 3. one warp per candidate, handed out in sequence order: inlier count.
         // Two facts a warp reads BEFORE it takes the next candidate let it do less without changing what the sequential rule
         // (step 4) will decide.  Every candidate completed by then precedes the one taken (candidates are handed out in order),
@@ -559,20 +646,28 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             const int it = m / 3, k = m - 3 * it;
             if (k >= sh.nmodels[it]) continue;
             if (iter0 + it >= limit) { if (lane == 0) sh.count[it][k] = 0; continue; }
-            double F[9];
-#pragma unroll
-            for (int i = 0; i < 9; i++) F[i] = sh.models[it][9 * k + i];
             const double* Fm = sh.models[it] + 9 * k;
+            Cand32 c32;
+            cand32_init(c32, Fm, cm);
             int cnt = 0;
-            for (int base = 0; base < n; base += 64) {                // two independent points per lane and step
-                const int i0 = base + lane, i1 = i0 + 32;
-                const int j0 = min(i0, n - 1), j1 = min(i1, n - 1);
-                const float2 a0 = P1[j0], b0 = P2[j0], a1 = P1[j1], b1 = P2[j1];
-                int c0 = classify(F, a0, b0, tlo, thi), c1 = classify(F, a1, b1, tlo, thi);
-                if (c0 < 0) c0 = is_inlier_exact(Fm, a0, b0, t2);
-                if (c1 < 0) c1 = is_inlier_exact(Fm, a1, b1, t2);
-                cnt += __popc(__ballot_sync(0xffffffffu, c0 && i0 < n)) + __popc(__ballot_sync(0xffffffffu, c1 && i1 < n));
-                if (cnt + max(n - base - 64, 0) <= bound) { cnt = 0; break; }
+            for (int base = 0; base < n; base += 128) {               // four independent points per lane and step
+                int c[4];
+                float2 pa[4], pb[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int j = min(base + 32 * r + lane, n - 1);
+                    pa[r] = P1[j]; pb[r] = P2[j];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) c[r] = classify32(c32, pa[r], pb[r], tlo32, thi32);
+                if (__any_sync(0xffffffffu, (c[0] | c[1] | c[2] | c[3]) < 0)) {      // rare: a point within ~1e-4 of the threshold
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (c[r] < 0) c[r] = is_inlier(nullptr, Fm, pa[r], pb[r], t2, tlo, thi);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) cnt += __popc(__ballot_sync(0xffffffffu, c[r] && base + 32 * r + lane < n));
+                if (cnt + max(n - base - 128, 0) <= bound) { cnt = 0; break; }
             }
             if (lane == 0) {
                 sh.count[it][k] = cnt;
@@ -582,6 +677,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             scored++;
         }
         __syncthreads();
+        FM_TICK(3);
         // ---- 4. OpenCV's sequential update rule over the chunk
         if (tid == 0) {
             int iter = sh.iter, niters = sh.niters, maxgood = sh.maxgood;
@@ -599,6 +695,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             sh.iter = iter; sh.niters = niters; sh.maxgood = maxgood;
             if (iter >= niters) sh.stop = 1;
         }
+        FM_TICK(4);
         __syncthreads();
         if (sh.stop) break;
     }
@@ -672,8 +769,10 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         sh.A[q * 9 + p] = x;
     }
     __syncthreads();
+    FM_TICK(5);
     if (warp == 0) {
         jacobi9_warp(sh, lane);
+        FM_TICK(6);
         if (lane == 0) {
             int small = 0, m = 0;
             for (int i = 0; i < 9; i++) {
@@ -949,3 +1048,13 @@ extern "C" int fmx_filter_consecutive_dev(fmx_handle h, const orbx_keypoint* d_k
     return fmx_filter_back_dev(h, d_kps, nframes, cap, 1, d_prev_kps, d_prev_kps ? 1 : 0, d_good, d_ngood, max_distance, confidence, d_status,
                                d_F, d_info);
 }
+
+#ifdef FM_PROFILE
+extern "C" __attribute__((visibility("default"))) int fmx_debug_profile(unsigned long long* out8, int reset)
+{
+    ORBX_CUDA(cudaDeviceSynchronize());
+    ORBX_CUDA(cudaMemcpyFromSymbol(out8, g_fm_prof, sizeof(g_fm_prof)));
+    if (reset) { unsigned long long z[8] = {0}; ORBX_CUDA(cudaMemcpyToSymbol(g_fm_prof, z, sizeof(z))); }
+    return ORBX_OK;
+}
+#endif

@@ -253,3 +253,26 @@ def test_filter_back_matches_per_pair_calls(fm):
         orb.filter_back(fm, back, cap, n)           # no match_back on the new batch yet
     orb.close()
     bf.close()
+
+
+@pytest.mark.parametrize("thr,conf,size", [(0.5, 0.85, (1241, 376)), (1.0, 0.99, (1920, 1080)), (3.0, 0.85, (3840, 2160)), (10.0, 0.95, (640, 480))])
+def test_fuzz_thresholds_and_image_sizes(fm, thr, conf, size):
+    """160 small pairs per configuration (thresholds from 0.5 to 10 px, coordinates up to 4K): every status mask equals the
+    oracle's -- the single-precision pre-classification and the division-free test never decide a point differently."""
+    npairs, cap = 160, 320
+    r = np.random.default_rng(int(thr * 100) + size[0])
+    counts = r.integers(15, cap + 1, npairs).astype(np.int32)
+    p1 = np.zeros((npairs, cap, 2), np.float32)
+    p2 = np.zeros((npairs, cap, 2), np.float32)
+    for i in range(npairs):
+        a, b = syn.two_view_matches(7000 + 13 * i + size[1], int(counts[i]), float(r.uniform(0.25, 0.98)), float(r.uniform(0.05, 2.0)), size)
+        p1[i, :counts[i]], p2[i, :counts[i]] = a, b
+    status, F, ninl = fm.find_batch(p1, p2, counts, thr, conf)
+    info = fm.last_info(npairs)
+    bad = []
+    for i in range(npairs):
+        n = int(counts[i])
+        _, mo, iters = oracle.fm_ransac(p1[i, :n], p2[i, :n], thr, conf)
+        if not np.array_equal(status[i, :n], mo) or info[i, 1] != iters:
+            bad.append(i)
+    assert not bad, "pairs with a different status mask or iteration count: %s" % bad

@@ -839,6 +839,7 @@ struct fmx_context {
     double* d_F; size_t F_bytes;
     int32_t* d_info; size_t info_bytes;
     int32_t* h_info; size_t h_info_n;
+    float* h_pts; size_t h_pts_n;            // pinned staging of fmx_compute_fundamental (grow-only)
     size_t smem_optin;
     int sm_count;
 };
@@ -885,6 +886,7 @@ extern "C" int fmx_destroy(fmx_handle h)
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_counts); cudaFree(h->d_status); cudaFree(h->d_F); cudaFree(h->d_info);
     if (h->h_info) cudaFreeHost(h->h_info);
+    if (h->h_pts) cudaFreeHost(h->h_pts);
     cudaStreamDestroy(h->own_stream);
     delete h;
     return ORBX_OK;
@@ -998,14 +1000,18 @@ extern "C" int fmx_compute_fundamental(fmx_handle h, const orbx_keypoint* kps1, 
     *ninliers = 0;
     for (int i = 0; i < 9; i++) F[i] = 0.;
     if (nm == 0) return ORBX_OK;
-    float* pts = nullptr;
-    ORBX_CUDA(cudaMallocHost((void**)&pts, (size_t)nm * 4 * sizeof(float)));
-    float* a = pts;
-    float* b = pts + 2 * (size_t)nm;
+    if (h->h_pts_n < (size_t)nm * 4) {
+        if (h->h_pts) cudaFreeHost(h->h_pts);
+        h->h_pts = nullptr; h->h_pts_n = 0;
+        const size_t want = (size_t)nm * 4 + (size_t)nm;
+        ORBX_CUDA(cudaMallocHost((void**)&h->h_pts, want * sizeof(float)));
+        h->h_pts_n = want;
+    }
+    float* a = h->h_pts;
+    float* b = h->h_pts + 2 * (size_t)nm;
     for (int i = 0; i < nm; i++) {
         const int q = matches[i].query_idx, t = matches[i].train_idx;
         if (q < 0 || q >= n1 || t < 0 || t >= n2) {
-            cudaFreeHost(pts);
             set_error("fmx_compute_fundamental: match %d indexes (%d, %d) outside (%d, %d) keypoints", i, q, t, n1, n2);
             return ORBX_E_INVALID;
         }
@@ -1013,9 +1019,7 @@ extern "C" int fmx_compute_fundamental(fmx_handle h, const orbx_keypoint* kps1, 
         b[2 * i] = kps2[t].x; b[2 * i + 1] = kps2[t].y;
     }
     const int32_t count = nm;
-    const int rc = fmx_fundamental_batch(h, a, b, &count, 1, nm, max_distance, confidence, status, F, ninliers);
-    cudaFreeHost(pts);
-    return rc;
+    return fmx_fundamental_batch(h, a, b, &count, 1, nm, max_distance, confidence, status, F, ninliers);
 }
 
 extern "C" int fmx_filter_back_dev(fmx_handle h, const orbx_keypoint* d_kps, int nframes, int cap, int back, const orbx_keypoint* d_hist_kps,

@@ -22,3 +22,11 @@ print("match_ratio 2kx2k %.3f ms" % t(lambda: m.match_ratio(d1, d0, 0.8)))
 print("knnMatch 2kx2k    %.3f ms" % t(lambda: m.knnMatch(d1, d0, 2)))
 pin = torch.from_numpy(img).pin_memory().numpy()
 print("detectAndCompute (pinned frame) %.3f ms" % t(lambda: orb.detectAndCompute(pin)))
+# the call after matching: computeFundamentalMatrix of one pair (1000 matches, 70 % inliers), the reference's argument list
+from monocular_slam_b200 import DMATCH_DTYPE, KEYPOINT_DTYPE, FundamentalFilter
+fm = FundamentalFilter()
+p1, p2 = syn.two_view_matches(3, 1000, 0.7, 0.5)
+ka = np.zeros(1000, KEYPOINT_DTYPE); kb = np.zeros(1000, KEYPOINT_DTYPE)
+ka["x"], ka["y"], kb["x"], kb["y"] = p1[:, 0], p1[:, 1], p2[:, 0], p2[:, 1]
+mt = np.zeros(1000, DMATCH_DTYPE); mt["query_idx"] = mt["train_idx"] = np.arange(1000)
+print("computeFundamentalMatrix 1 pair x 1000 matches %.3f ms" % t(lambda: fm.compute_fundamental(ka, kb, mt)))

@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <float.h>
+#include <limits.h>
 #include <stdlib.h>
 #include <algorithm>
 
@@ -378,17 +379,24 @@ __device__ __forceinline__ bool is_inlier(const double* F, const double* Fm, flo
     return c >= 0 ? c != 0 : is_inlier_exact(Fm, p1, p2, t2);
 }
 
-// RANSACUpdateNumIters
-__device__ int update_num_iters(double p, double ep, int max_iters)
+// min(n0, RANSACUpdateNumIters(p, (n - good) / n, .)): the iteration budget after a candidate with `good` inliers became the best,
+// given a budget n0 before.  lognum = log(max(1 - p, DBL_MIN)).  The budget formula log(1 - p) / log(1 - w^7), w = good / n, is far
+// above n0 for most candidates; a single-precision estimate (relative error < 1e-2 wherever it is used to decide) screens those
+// out, only estimates below 2 n0 + 2 take OpenCV's double-precision expression.
+__device__ int iter_limit_of(double lognum, int n, int good, int n0)
 {
-    p = fmin(fmax(p, 0.), 1.);
+    const float w = (float)good / (float)n, w2 = w * w, w7 = w2 * w2 * w2 * w, df = 1.f - w7;
+    if (df >= 1.f) return n0;                                       // w^7 < 6e-8: the formula exceeds 1e7
+    const float qf = (float)lognum / logf(df);                      // df == 0: -0 -> not screened out
+    if (!(qf < 2.f * (float)n0 + 2.f)) return n0;
+    double ep = (double)(n - good) / n;
     ep = fmin(fmax(ep, 0.), 1.);
-    double num = fmax(1. - p, DBL_MIN);
     double denom = 1. - pow(1. - ep, (double)FM_MODEL_POINTS);
     if (denom < DBL_MIN) return 0;
-    num = log(num);
     denom = log(denom);
-    return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : __double2int_rn(num / denom);
+    if (denom >= 0) return n0;
+    const double q = lognum / denom;
+    return q >= (double)n0 ? n0 : min(n0, __double2int_rn(q));
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -563,6 +571,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     const double tlo = (double)t2 * (1. - 1e-9), thi = (double)t2 * (1. + 1e-6);
     const float tlo32 = __double2float_rd(tlo * (1. - 4e-6)), thi32 = __double2float_ru(thi * (1. + 4e-6));
     const unsigned nmod = (unsigned)(0x100000000ULL / (unsigned)n);
+    const double lognum = log(fmax(1. - fmin(fmax(conf, 0.), 1.), DBL_MIN));
     if (tid == 0) {
         sh.rng = 0xffffffffffffffffULL;
         sh.iter = 0; sh.niters = max_iters; sh.maxgood = 0; sh.stop = 0; sh.have = 0;
@@ -630,7 +639,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         // (step 4) will decide.  Every candidate completed by then precedes the one taken (candidates are handed out in order),
         // so (a) a count that cannot exceed sh.run_max -- the best exact count completed so far -- can never become the best:
         // the candidate is abandoned as soon as that is certain; (b) once a completed count c bounds the iteration budget by
-        // update_num_iters(c), a candidate of a later iteration is never reached and is skipped altogether.
+        // iter_limit_of(c), a candidate of a later iteration is never reached and is skipped altogether.
         for (;;) {
             int m = 0, bound = 0, limit = 0;
             if (lane == 0) {
@@ -672,28 +681,86 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             if (lane == 0) {
                 sh.count[it][k] = cnt;
                 if (cnt > bound && cnt > atomicMax(&sh.run_max, cnt))
-                    atomicMin(&sh.iter_limit, update_num_iters(conf, (double)(n - cnt) / n, niters0));
+                    atomicMin(&sh.iter_limit, iter_limit_of(lognum, n, cnt, niters0));
             }
             scored++;
         }
         __syncthreads();
         FM_TICK(3);
-        // ---- 4. OpenCV's sequential update rule over the chunk
-        if (tid == 0) {
-            int iter = sh.iter, niters = sh.niters, maxgood = sh.maxgood;
-            for (int i = 0; i < chunk && iter < niters; i++, iter++) {
-                for (int k = 0; k < sh.nmodels[i]; k++) {
-                    const int good = sh.count[i][k];
-                    if (good > max(maxgood, FM_MODEL_POINTS - 1)) {
-                        maxgood = good;
-                        for (int j = 0; j < 9; j++) sh.best[j] = sh.models[i][9 * k + j];
-                        sh.have = 1;
-                        niters = update_num_iters(conf, (double)(n - good) / n, niters);
-                    }
+        // ---- 4. OpenCV's sequential update rule over the chunk, evaluated by warp 0 in parallel.  In sequence order a
+        // candidate becomes the best iff its count exceeds every earlier one (and the floor): an exclusive prefix maximum.
+        // Each such improvement j lowers the iteration budget to min(budget, r_j), r_j = RANSACUpdateNumIters' closed form, and
+        // the loop reaches it iff its iteration index is below the budget left by the improvements before it: an exclusive
+        // prefix minimum.  Budgets only shrink and indices only grow, so the improvements reached form a prefix; the last one
+        // reached is the result of the round.
+        if (warp == 0) {
+            static_assert(FM_MAXCHUNK == 128, "4 iterations per lane");
+            const int N0 = sh.niters, floor0 = max(sh.maxgood, FM_MODEL_POINTS - 1);
+            int cnt[12], lim[12], lmax = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = lane * 4 + j;
+                const int nm = i < chunk ? sh.nmodels[i] : 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int c = k < nm ? sh.count[i][k] : 0;
+                    cnt[3 * j + k] = c;
+                    lmax = max(lmax, c);
                 }
             }
-            sh.iter = iter; sh.niters = niters; sh.maxgood = maxgood;
-            if (iter >= niters) sh.stop = 1;
+            int incl = lmax;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl = max(incl, v);
+            }
+            int run = __shfl_up_sync(0xffffffffu, incl, 1);
+            run = max(lane ? run : 0, floor0);
+            int lmin = INT_MAX;
+#pragma unroll
+            for (int e = 0; e < 12; e++) {
+                lim[e] = INT_MAX;
+                if (cnt[e] > run) {
+                    run = cnt[e];
+                    lim[e] = iter_limit_of(lognum, n, cnt[e], N0);
+                    lmin = min(lmin, lim[e]);
+                } else {
+                    cnt[e] = -1;                                   // not an improvement
+                }
+            }
+            int pmin = lmin;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pmin, o);
+                if (lane >= o) pmin = min(pmin, v);
+            }
+            int P = __shfl_up_sync(0xffffffffu, pmin, 1);
+            P = min(lane ? P : INT_MAX, N0);
+            int last = -1, last_cnt = 0, last_n = 0;
+#pragma unroll
+            for (int e = 0; e < 12; e++) {
+                if (cnt[e] >= 0) {
+                    if (iter0 + lane * 4 + e / 3 < P) { last = lane * 12 + e; last_cnt = cnt[e]; last_n = min(P, lim[e]); }
+                    P = min(P, lim[e]);
+                }
+            }
+            int g = last;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) g = max(g, __shfl_xor_sync(0xffffffffu, g, o));
+            if (g >= 0 && g == last) {                             // the lane that owns the last improvement reached
+                const double* m = sh.models[g / 3] + 9 * (g % 3);
+                for (int j = 0; j < 9; j++) sh.best[j] = m[j];
+                sh.have = 1;
+                sh.maxgood = last_cnt;
+                sh.niters = last_n;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const int nf = sh.niters;
+                const int done = min(chunk, max(g >= 0 ? g / 3 + 1 : 0, nf - iter0));     // iterations the sequential loop executes
+                sh.iter = iter0 + done;
+                if (sh.iter >= nf) sh.stop = 1;
+            }
         }
         FM_TICK(4);
         __syncthreads();

@@ -60,10 +60,15 @@ class ShardedSequence:
 
     ``run(frames)`` walks the block in batches through the pipelined host path (``ORB.submit_batch`` / ``wait_batch``) and
     yields ``(frame_index, keypoints, descriptors, matches_against_previous_frame)`` in frame order for the rank's own
-    frames.  ``extract_match(frames, first_is_lead_in)`` can be injected to exercise the block logic without a GPU.
+    frames.  With ``fundamental`` (a FundamentalFilter) the outlier filter runs in the same submissions and two more items are
+    yielded per frame: the RANSAC status of the matches and the 8-point F (computeFundamentalMatrix,
+    src/CameraPoseEstimator.cpp:545-586).  ``extract_match(frames, first_is_lead_in)`` can be injected to exercise the block
+    logic without a GPU.
     """
 
-    def __init__(self, orb=None, matcher=None, ratio=0.8, rank=0, world=1, batch=None, extract_match=None):
+    def __init__(self, orb=None, matcher=None, ratio=0.8, rank=0, world=1, batch=None, extract_match=None, fundamental=None,
+                 max_distance=3.0, confidence=0.85):
+        self.fundamental, self.max_distance, self.confidence = fundamental, float(max_distance), float(confidence)
         self.orb, self.matcher, self.ratio = orb, matcher, float(ratio)
         self.rank, self.world = int(rank), int(world)
         self.batch = int(batch or (orb.max_batch if orb is not None else 16))
@@ -94,11 +99,15 @@ class ShardedSequence:
 
         def collect():
             b, n = pending.pop(0)
-            kps, desc, counts, good, ngood = orb.wait_batch()
+            res = orb.wait_batch()
+            kps, desc, counts, good, ngood = res[:5]
             for i in range(n):
                 f = b + i
                 if f >= lo:
-                    yield f, kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy(), good[i, :ngood[i]].copy()
+                    item = (f, kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy(), good[i, :ngood[i]].copy())
+                    if self.fundamental is not None:
+                        item += (res[5][i, :ngood[i]].copy(), res[6][i].copy())
+                    yield item
 
         for b in range(start, hi, self.batch):
             n = min(self.batch, hi - b)
@@ -106,7 +115,10 @@ class ShardedSequence:
                 yield from collect()
             out = (np.zeros((n, cap), KEYPOINT_DTYPE), np.zeros((n, cap, 32), np.uint8), np.zeros(n, np.int32),
                    np.zeros((n, cap), DMATCH_DTYPE), np.zeros(n, np.int64))
-            orb.submit_batch(list(frames[b:b + n]), self.matcher, self.ratio, out)
+            if self.fundamental is not None:
+                out += (np.zeros((n, cap), np.uint8), np.zeros((n, 3, 3), np.float64), np.zeros(n, np.int32))
+            orb.submit_batch(list(frames[b:b + n]), self.matcher, self.ratio, out, fundamental=self.fundamental,
+                             max_distance=self.max_distance, confidence=self.confidence)
             pending.append((b, n))
         while pending:
             yield from collect()

@@ -279,3 +279,31 @@ def test_sharded_sequence_equals_single_rank():
         assert np.array_equal(got[f][0], ref[f][0]) and np.array_equal(got[f][1], ref[f][1]) and np.array_equal(got[f][2], ref[f][2]), f
     m.close()
     orb.close()
+
+
+def test_sharded_sequence_with_outlier_filter():
+    """The filter rides along in ShardedSequence: per-frame status / F of a 2-rank split equal the single-rank run (the pair across
+    the block border is computed by the rank that owns the later frame, from its own lead-in extraction)."""
+    from monocular_slam_b200 import FundamentalFilter
+    from monocular_slam_b200.sharded import ShardedSequence
+    seq = syn.sequence(9, 640, 480, seed=43)
+    orb = ORB(nfeatures=600, max_size=(640, 480), max_batch=4)
+    m = BFMatcher()
+    fm = FundamentalFilter()
+    ref = {it[0]: it[1:] for it in ShardedSequence(orb, m, 0.8, 0, 1, fundamental=fm).run(seq)}
+    assert sorted(ref) == list(range(9)) and len(ref[0][2]) == 0 and not ref[0][4].any()
+    for f in range(1, 9):
+        k, d, g, status, F = ref[f]
+        Fh, sh, nh = fm.compute_fundamental(k, ref[f - 1][0], g)
+        assert np.array_equal(status, sh) and np.array_equal(F, Fh)
+    got = {}
+    for r in range(2):
+        for it in ShardedSequence(orb, m, 0.8, r, 2, fundamental=fm).run(seq):
+            got[it[0]] = it[1:]
+    assert sorted(got) == list(range(9))
+    for f in range(9):
+        for a, b in zip(got[f], ref[f]):
+            assert np.array_equal(a, b), f
+    fm.close()
+    m.close()
+    orb.close()

@@ -354,7 +354,8 @@ private:
 class SequenceFrontEnd {
 public:
     SequenceFrontEnd(int nfeatures, float ratio, int batch, int width, int height, int device = 0)
-        : orb_(nullptr), bf_(nullptr), ratio_(ratio), batch_(batch), w_(width), h_(height), cap_(0), depth_(0)
+        : orb_(nullptr), bf_(nullptr), fm_(nullptr), ratio_(ratio), batch_(batch), w_(width), h_(height), cap_(0), depth_(0),
+          device_(device), max_distance_(3.), confidence_(0.85), status_out_(nullptr), F_out_(nullptr)
     {
         orbx_params p;
         orbx_default_params(&p);
@@ -379,17 +380,47 @@ public:
         while (orb_ && orbx_batches_in_flight(orb_) > 0) orbx_wait_batch(orb_);
         for (size_t i = 0; i < slots_.size(); i++) {
             orbx_host_free(slots_[i].frames); orbx_host_free(slots_[i].kps); orbx_host_free(slots_[i].desc); orbx_host_free(slots_[i].good);
+            if (slots_[i].status) orbx_host_free(slots_[i].status);
+            if (slots_[i].F) orbx_host_free(slots_[i].F);
         }
+        if (fm_) fmx_destroy(fm_);
         if (bf_) hamx_destroy(bf_);
         if (orb_) orbx_destroy(orb_);
     }
     SequenceFrontEnd(const SequenceFrontEnd&) = delete;
     SequenceFrontEnd& operator=(const SequenceFrontEnd&) = delete;
 
+    // Append computeFundamentalMatrix (src/CameraPoseEstimator.cpp:545-586) of every (frame, predecessor) pair to each batch:
+    // process() then also fills status[i - first] (one byte per match, OpenCV's RANSAC mask) and F[i - first] (9 doubles,
+    // the 8-point matrix of the inliers; all zeros when there is no model).
+    void enableFilter(double maxDistance = 3., double confidence = 0.85)
+    {
+        if (!fm_) check(fmx_create(&fm_, device_), "SequenceFrontEnd: fmx_create");
+        max_distance_ = maxDistance;
+        confidence_ = confidence;
+        for (size_t i = 0; i < slots_.size(); i++) {
+            Slot& s = slots_[i];
+            if (!s.status) check(orbx_host_alloc((size_t)batch_ * cap_, (void**)&s.status), "SequenceFrontEnd: pinned status");
+            if (!s.F) check(orbx_host_alloc((size_t)batch_ * 9 * sizeof(double), (void**)&s.F), "SequenceFrontEnd: pinned F");
+            s.ninl.resize((size_t)batch_);
+        }
+    }
+
     // frames [first, first + count) of dm (all width x height, CV_8UC1): fills frames[i].features and matches[i - first]
     // (frame i against frame i-1; empty for the first frame of a sequence -- call reset() to start a new one)
     void process(DataManager& dm, int first, int count, std::vector<std::vector<DMatch> >& matches)
     {
+        std::vector<std::vector<unsigned char> > status;
+        std::vector<std::vector<double> > F;
+        process(dm, first, count, matches, status, F);
+    }
+    void process(DataManager& dm, int first, int count, std::vector<std::vector<DMatch> >& matches,
+                 std::vector<std::vector<unsigned char> >& status, std::vector<std::vector<double> >& F)
+    {
+        status_out_ = fm_ ? &status : nullptr;
+        F_out_ = fm_ ? &F : nullptr;
+        status.assign(fm_ ? (size_t)count : 0, std::vector<unsigned char>());
+        F.assign(fm_ ? (size_t)count : 0, std::vector<double>(9, 0.));
         matches.assign((size_t)count, std::vector<DMatch>());
         std::vector<std::pair<int, int> > pending;     // (first frame, count) of the batches in flight, oldest first
         size_t next_slot = 0, oldest_slot = 0;
@@ -405,8 +436,9 @@ public:
                 for (int y = 0; y < h_; y++) std::memcpy(dst + (size_t)y * w_, fb.ptr(y), (size_t)w_);
                 ptrs[(size_t)i] = dst;
             }
-            check(orbx_submit_batch(orb_, bf_, ptrs.data(), n, w_, h_, (size_t)w_, ratio_, s.kps, s.desc, cap_, s.counts.data(), s.good,
-                                    s.ngood.data()), "SequenceFrontEnd: orbx_submit_batch");
+            check(orbx_submit_batch_filtered(orb_, bf_, fm_, ptrs.data(), n, w_, h_, (size_t)w_, ratio_, s.kps, s.desc, cap_, s.counts.data(),
+                                             s.good, s.ngood.data(), max_distance_, confidence_, s.status, s.F,
+                                             fm_ ? s.ninl.data() : nullptr), "SequenceFrontEnd: orbx_submit_batch");
             pending.push_back(std::make_pair(b, n));
             next_slot = (next_slot + 1) % slots_.size();
         }
@@ -418,7 +450,8 @@ private:
     struct Slot {
         uint8_t* frames; orbx_keypoint* kps; uint8_t* desc; orbx_dmatch* good;
         std::vector<int32_t> counts; std::vector<int64_t> ngood;
-        Slot() : frames(nullptr), kps(nullptr), desc(nullptr), good(nullptr) {}
+        uint8_t* status; double* F; std::vector<int32_t> ninl;
+        Slot() : frames(nullptr), kps(nullptr), desc(nullptr), good(nullptr), status(nullptr), F(nullptr) {}
     };
     void collect(DataManager& dm, std::pair<int, int> batch, Slot& s, std::vector<std::vector<DMatch> >& matches, int first)
     {
@@ -436,12 +469,21 @@ private:
             if (n) std::memcpy(ft.descriptors.data, s.desc + (size_t)i * cap_ * 32, (size_t)n * 32);
             const DMatch* g = reinterpret_cast<const DMatch*>(s.good + (size_t)i * cap_);
             matches[(size_t)(batch.first + i - first)].assign(g, g + s.ngood[(size_t)i]);
+            if (status_out_) {
+                const uint8_t* st = s.status + (size_t)i * cap_;
+                (*status_out_)[(size_t)(batch.first + i - first)].assign(st, st + s.ngood[(size_t)i]);
+                (*F_out_)[(size_t)(batch.first + i - first)].assign(s.F + (size_t)i * 9, s.F + (size_t)i * 9 + 9);
+            }
         }
     }
     orbx_handle orb_;
     hamx_handle bf_;
+    fmx_handle fm_;
     float ratio_;
-    int batch_, w_, h_, cap_, depth_;
+    int batch_, w_, h_, cap_, depth_, device_;
+    double max_distance_, confidence_;
+    std::vector<std::vector<unsigned char> >* status_out_;
+    std::vector<std::vector<double> >* F_out_;
     std::vector<Slot> slots_;
 };
 #endif

@@ -102,3 +102,38 @@ def test_shim_compute_fundamental_matrix_matches_oracle(tmp_path):
     assert np.array_equal(in1, p1[mo > 0].astype(np.float64)) and np.array_equal(in2, p2[mo > 0].astype(np.float64))
     Fo = oracle.fm_8point(p1[mo > 0], p2[mo > 0])
     assert np.linalg.norm(F - Fo) / np.linalg.norm(Fo) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_sequence_front_end_with_filter(tmp_path):
+    """SequenceFrontEnd::enableFilter: per-frame status / F out of the pipelined C++ path equal fmx_compute_fundamental on the
+    keypoints and matches the same run reports (the filter's own parity with the oracle is covered in test_gpu_fmat.py)."""
+    from monocular_slam_b200 import FundamentalFilter, KEYPOINT_DTYPE
+    from monocular_slam_b200 import synthetic as syn
+    exe = _build_demo(tmp_path, "pipeline_demo")
+    w, h, nf, ratio, n = 800, 600, 700, 0.8, 7
+    seq = syn.sequence(n, w, h, seed=35)
+    raw = tmp_path / "frames.raw"
+    raw.write_bytes(seq.tobytes())
+    out = tmp_path / "out.bin"
+    subprocess.check_call([exe, str(w), str(h), str(n), str(raw), str(out), str(nf), str(ratio), "3", "filter"])
+    buf = out.read_bytes()
+    off = 0
+    fm = FundamentalFilter()
+    prev = None
+    for i in range(n):
+        (cnt,) = struct.unpack_from("<i", buf, off); off += 4
+        pos = np.frombuffer(buf, "<f8", cnt * 2, off).reshape(cnt, 2); off += cnt * 16
+        off += cnt * 8 + cnt * 4 + cnt * 32
+        kps = np.zeros(cnt, KEYPOINT_DTYPE)
+        kps["x"], kps["y"] = pos[:, 0], pos[:, 1]
+        if i > 0:
+            (m,) = struct.unpack_from("<i", buf, off); off += 4
+            dm = np.frombuffer(buf, _lib.DMATCH_DTYPE, m, off); off += m * 16
+            status = np.frombuffer(buf, np.uint8, m, off); off += m
+            F = np.frombuffer(buf, "<f8", 9, off).reshape(3, 3); off += 72
+            Fh, sh, nh = fm.compute_fundamental(kps, prev, dm)
+            assert m > 100 and np.array_equal(status, sh) and np.array_equal(F, Fh)
+        prev = kps
+    assert off == len(buf)
+    fm.close()

@@ -39,6 +39,10 @@ constexpr int FM_MAXCHUNK = 128;      // iterations solved + scored per round
 #endif
 constexpr int FM_FIRSTCHUNK = FM_FIRSTCHUNK_N;     // iterations of the first round (64 / half the remaining budget measured best: profiles/README.md)
 constexpr int FM_MODEL_POINTS = 7;
+#ifndef FM_PPL_N
+#define FM_PPL_N 4
+#endif
+constexpr int FM_PPL = FM_PPL_N;            // points per lane and scoring step (independent dependency chains)
 constexpr int FM_SMEM_POINTS = 9000;  // pairs with at most this many correspondences keep them in shared memory (16 B each)
 
 #ifdef FM_PROFILE
@@ -659,24 +663,25 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             Cand32 c32;
             cand32_init(c32, Fm, cm);
             int cnt = 0;
-            for (int base = 0; base < n; base += 128) {               // four independent points per lane and step
-                int c[4];
-                float2 pa[4], pb[4];
+            for (int base = 0; base < n; base += 32 * FM_PPL) {       // FM_PPL independent points per lane and step
+                int c[FM_PPL];
+                float2 pa[FM_PPL], pb[FM_PPL];
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
+                for (int r = 0; r < FM_PPL; r++) {
                     const int j = min(base + 32 * r + lane, n - 1);
                     pa[r] = P1[j]; pb[r] = P2[j];
                 }
+                int any = 0;
 #pragma unroll
-                for (int r = 0; r < 4; r++) c[r] = classify32(c32, pa[r], pb[r], tlo32, thi32);
-                if (__any_sync(0xffffffffu, (c[0] | c[1] | c[2] | c[3]) < 0)) {      // rare: a point within ~1e-4 of the threshold
+                for (int r = 0; r < FM_PPL; r++) { c[r] = classify32(c32, pa[r], pb[r], tlo32, thi32); any |= c[r]; }
+                if (__any_sync(0xffffffffu, any < 0)) {                // rare: a point within ~1e-4 of the threshold
 #pragma unroll
-                    for (int r = 0; r < 4; r++)
+                    for (int r = 0; r < FM_PPL; r++)
                         if (c[r] < 0) c[r] = is_inlier(nullptr, Fm, pa[r], pb[r], t2, tlo, thi);
                 }
 #pragma unroll
-                for (int r = 0; r < 4; r++) cnt += __popc(__ballot_sync(0xffffffffu, c[r] && base + 32 * r + lane < n));
-                if (cnt + max(n - base - 128, 0) <= bound) { cnt = 0; break; }
+                for (int r = 0; r < FM_PPL; r++) cnt += __popc(__ballot_sync(0xffffffffu, c[r] && base + 32 * r + lane < n));
+                if (cnt + max(n - base - 32 * FM_PPL, 0) <= bound) { cnt = 0; break; }
             }
             if (lane == 0) {
                 sh.count[it][k] = cnt;

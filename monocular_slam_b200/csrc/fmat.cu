@@ -6,15 +6,19 @@
 //     F = findFundamentalMat(inliers1, inliers2, CV_FM_8POINT)                                     (:585)
 // OpenCV's RANSAC is sequential: sample 7 points, solve the cubic (<= 3 candidate matrices), count inliers, keep the best,
 // shrink the iteration budget.  The result only depends on (a) the sample sequence, which is a function of the random
-// generator and the points alone, and (b) the inlier count of every candidate.  So one CTA per pair
-//   1. draws the samples of the next `chunk` iterations (one thread; cv::RNG + the duplicate / collinearity rejections),
-//   2. solves them in parallel (one thread per sample; Householder null space + cv::solveCubic, double precision),
-//   3. counts inliers of all candidates in parallel (one warp per candidate; OpenCV's double arithmetic rounded to float),
-//   4. replays OpenCV's sequential best-update / iteration-budget rule over the chunk in order (one thread),
-// until the budget is exhausted -- same status mask as the sequential loop.  Candidates that cannot beat the best count known
-// at the start of the chunk are abandoned early (their exact count is never needed).  The CTA then marks the inliers of the
-// winning matrix and runs the normalised 8-point algorithm on them (block reduction of the 9x9 normal matrix, warp-parallel
-// cyclic Jacobi for its smallest eigenvector, rank-2 projection).
+// generator and the points alone, and (b) the inlier count of every candidate.  So one CTA per pair works in rounds of up to
+// 128 iterations:
+//   1. one thread draws the index tuples of the round (cv::RNG, duplicate-free draws); the collinearity rejection is tested
+//      for all samples in parallel, and the rare rejected sample makes one thread redo the rest of the round sequentially;
+//   2. the samples are solved in parallel (one thread per sample; Householder null space + cv::solveCubic, double precision);
+//   3. the candidates are scored one per warp, handed out in sequence order (single-precision classification with rigorous
+//      error bounds, double precision for the few points near the threshold -- the decision is always OpenCV's);
+//   4. warp 0 evaluates OpenCV's sequential best-update / iteration-budget rule over the round with two prefix scans,
+// until the budget is exhausted -- same status mask as the sequential loop.  Candidates that cannot beat the best count
+// completed before them are abandoned early, candidates beyond the budget that count implies are skipped (neither can be
+// reached / chosen by the sequential loop).  The CTA then marks the inliers of the winning matrix and runs the normalised
+// 8-point algorithm on them (block reduction of the 9x9 normal matrix, round-robin warp Jacobi for its smallest eigenvector,
+// rank-2 projection).
 //
 // Double-precision arithmetic is IEEE, compiled without FMA contraction (build.sh: -fmad=false) like the x86 baseline build of
 // OpenCV, so candidate matrices agree with the CPU to rounding of the transcendental calls and the inlier tests are the same.

@@ -117,3 +117,22 @@ def two_view_matches(seed, n, inlier_ratio=0.7, noise=0.5, size=(1920, 1080)):
     bad = r.random(n) > inlier_ratio
     p2[bad] = np.c_[r.uniform(0, w, bad.sum()), r.uniform(0, h, bad.sum())]
     return p1.astype(np.float32), p2.astype(np.float32)
+
+
+def layered_pair(seed, w, h, nlayers=4, motion=(2, 5)):
+    """Two views (h x w uint8 each) of a scene of fronto-parallel layers at different depths under a sideways camera
+    translation: every layer is a horizontal band of one big texture and shifts by its own multiple of ``motion`` (dy, dx).
+    The flow vectors are parallel but of different lengths, i.e. a non-planar scene with the epipole at infinity -- unlike
+    ``sequence`` (one translating plane), its fundamental matrix is well defined."""
+    r = np.random.default_rng(seed)
+    dy, dx = abs(int(motion[0])), abs(int(motion[1]))
+    big = frame(seed, w + nlayers * dx + 8, h + nlayers * dy + 8)
+    a = big[:h, :w].copy()
+    b = np.empty_like(a)
+    edges = np.linspace(0, h, nlayers + 1).astype(int)
+    mult = r.permutation(np.arange(1, nlayers + 1))
+    for layer in range(nlayers):
+        sy, sx = dy * int(mult[layer]), dx * int(mult[layer])
+        y0, y1 = int(edges[layer]), int(edges[layer + 1])
+        b[y0:y1] = big[y0 + sy:y1 + sy, sx:sx + w]
+    return a, b

@@ -276,3 +276,36 @@ def test_fuzz_thresholds_and_image_sizes(fm, thr, conf, size):
         if not np.array_equal(status[i, :n], mo) or info[i, 1] != iters:
             bad.append(i)
     assert not bad, "pairs with a different status mask or iteration count: %s" % bad
+
+
+CHAIN = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain_cases.npz"))
+
+
+@pytest.mark.parametrize("name", [str(n) for n in CHAIN["names"]])
+def test_whole_chain_on_images_matches_cv2(fm, name):
+    """The reference's bootstrap sequence on image data, GPU end to end against the cv2 golden (make_golden_chain.py):
+    extraction, matchFeatures, computeFundamentalMatrix -- match list and RANSAC status identical, F within tolerance; once
+    call by call through host buffers, once in sequence mode with everything resident on the device."""
+    seed, w, h, layers, my, mx, nf, ratio = CHAIN[name + "_cfg"]
+    w, h, nf, ratio = int(w), int(h), int(nf), float(ratio)
+    prev, cur = syn.layered_pair(int(seed), w, h, int(layers), (int(my), int(mx)))
+    good = CHAIN[name + "_good"]
+    mask = np.unpackbits(CHAIN[name + "_mask"])[:len(good)]
+    orb = ORB(nfeatures=nf, max_size=(w, h), max_batch=2)
+    bf = BFMatcher()
+    kp, dp = orb.detectAndCompute(prev)
+    kc, dc = orb.detectAndCompute(cur)
+    m = bf.match_ratio(dc, dp, ratio)
+    assert list(CHAIN[name + "_counts"][:3]) == [len(kp), len(kc), len(m)]
+    assert np.array_equal(m["query_idx"], good[:, 0]) and np.array_equal(m["train_idx"], good[:, 1])
+    F, status, ninl = fm.compute_fundamental(kc, kp, m, 3.0, 0.85)
+    assert np.array_equal(status, mask) and ninl == CHAIN[name + "_counts"][3]
+    assert rel(F, CHAIN[name + "_F8"]) <= F_RTOL
+    # sequence mode: both frames as one batch, matches and keypoints never leave the device before the filter
+    kps, desc, counts = orb.extract_batch([prev, cur])
+    cap = kps.shape[1]
+    g, ng = orb.match_consecutive(bf, ratio, cap, 2)
+    st, Fs, ni = orb.filter_consecutive(fm, cap, 2, 3.0, 0.85)
+    assert ng[1] == len(good) and np.array_equal(st[1, :ng[1]], mask) and np.array_equal(Fs[1], F) and ni[0] == 0
+    orb.close()
+    bf.close()

@@ -91,3 +91,27 @@ def test_all_outliers_and_small_sets():
     assert iters == 1000 and (F is None or m.sum() >= 7)
     F, status, ninl = oracle.compute_fundamental(p1[:5], p2[:5], np.zeros((5, 4), np.int32), 3.0, 0.85)
     assert ninl == 0 and not F.any()
+
+
+CHAIN = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain_cases.npz"))
+
+
+@pytest.mark.parametrize("name", [str(n) for n in CHAIN["names"]])
+def test_whole_chain_on_images_matches_cv2(name):
+    """extract -> matchFeatures -> computeFundamentalMatrix on two views of a layered-depth scene, oracle vs the cv2 golden
+    (tests/golden/make_golden_chain.py): same match list, same RANSAC status, same 8-point matrix."""
+    seed, w, h, layers, my, mx, nf, ratio = CHAIN[name + "_cfg"]
+    prev, cur = syn.layered_pair(int(seed), int(w), int(h), int(layers), (int(my), int(mx)))
+    P = oracle.Params(nfeatures=int(nf))
+    kp, dp = oracle.detect_and_compute(prev, P)
+    kc, dc = oracle.detect_and_compute(cur, P)
+    gq, gt, gd = oracle.match_features(dc, dp, float(ratio))
+    good = CHAIN[name + "_good"]
+    assert list(CHAIN[name + "_counts"][:3]) == [len(kp), len(kc), len(gq)]
+    assert np.array_equal(gq, good[:, 0]) and np.array_equal(gt, good[:, 1]) and np.array_equal(gd, good[:, 2])
+    matches = np.zeros((len(gq), 4), np.int32)
+    matches[:, 0], matches[:, 1] = gq, gt
+    F, status, ninl = oracle.compute_fundamental(np.c_[kc["x"], kc["y"]], np.c_[kp["x"], kp["y"]], matches, 3.0, 0.85)
+    mask = np.unpackbits(CHAIN[name + "_mask"])[:len(gq)]
+    assert np.array_equal(status, mask) and ninl == CHAIN[name + "_counts"][3]
+    assert rel(F, CHAIN[name + "_F8"]) <= F_RTOL

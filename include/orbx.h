@@ -292,6 +292,14 @@ ORBX_API int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_handle
                                size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts,
                                orbx_dmatch* good, int64_t* ngood, double max_distance, double confidence, uint8_t* status,
                                double* F, int32_t* ninliers);
+/* The pipelined form of the steady-state loop (src/CameraPoseEstimator.cpp:405-419): every frame of the batch against its `back`
+ * (<= 8) predecessors, matchFeatures and -- when fm is not NULL -- computeFundamentalMatrix per pair.  good / status are
+ * [nframes][back][cap], ngood / ninliers [nframes][back], F [nframes][back][9]; pair (f, j) at index f*back + j-1 as in
+ * hamx_match_back_dev.  The history of the frames before the batch lives on the device (orbx_reset_sequence forgets it). */
+ORBX_API int orbx_submit_batch_back(orbx_handle h, hamx_handle m, fmx_handle fm, int back, const uint8_t* const* frames, int nframes, int w,
+                           int h_, size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts,
+                           orbx_dmatch* good, int64_t* ngood, double max_distance, double confidence, uint8_t* status, double* F,
+                           int32_t* ninliers);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ SYMBOLS = [
     "hamx_p2p_export", "hamx_p2p_import", "hamx_p2p_import_ptrs", "hamx_p2p_close", "hamx_knn2_p2p_dev",
     "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev", "orbx_set_input_channels", "orbx_pipeline_depth", "hamx_match_back_dev", "hamx_update_history_dev", "orbx_match_back", "orbx_host_alloc", "orbx_host_free",
     "fmx_create", "fmx_destroy", "fmx_set_stream", "fmx_synchronize", "fmx_compute_fundamental", "fmx_fundamental_batch",
-    "fmx_last_info", "fmx_fundamental_batch_dev", "fmx_filter_consecutive_dev", "orbx_filter_consecutive", "orbx_submit_batch_filtered", "fmx_filter_back_dev", "orbx_filter_back",
+    "fmx_last_info", "fmx_fundamental_batch_dev", "fmx_filter_consecutive_dev", "orbx_filter_consecutive", "orbx_submit_batch_filtered", "fmx_filter_back_dev", "orbx_filter_back", "orbx_submit_batch_back",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -140,6 +140,8 @@ def lib():
     L.fmx_filter_consecutive_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     L.orbx_filter_consecutive.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp, vp]
     L.orbx_filter_back.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp, vp]
+    L.orbx_submit_batch_back.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_float, vp, vp, C.c_int, vp,
+                                         vp, vp, C.c_double, C.c_double, vp, vp, vp]
     L.fmx_filter_back_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     L.orbx_submit_batch_filtered.argtypes = [vp, vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_float, vp, vp, C.c_int, vp, vp,
                                              vp, C.c_double, C.c_double, vp, vp, vp]

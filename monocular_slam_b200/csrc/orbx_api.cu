@@ -47,6 +47,7 @@ struct orbx_lane {
     int32_t* counts;      // caller's arrays, filled by orbx_wait_batch
     int64_t* ngood;
     int32_t* ninliers;
+    int back;             // 0: consecutive pairs (one per frame); >= 1: `back` pairs per frame (orbx_submit_batch_back)
 };
 #ifndef ORBX_LANES_N
 #define ORBX_LANES_N 3
@@ -899,6 +900,28 @@ extern "C" int orbx_reset_sequence(orbx_handle h)
 
 static int ensure_filter_buffers(orbx_handle h);
 
+// history (descriptors, counts, keypoints; double-buffered) and the per-lane result buffers of the `back`-predecessor mode
+static int ensure_back_buffers(orbx_handle h)
+{
+    if (h->d_hist[0]) return ORBX_OK;
+    for (int i = 0; i < 2; i++) {
+        ORBX_CUDA(cudaMalloc((void**)&h->d_hist[i], (size_t)ORBX_MAX_BACK * h->dev_cap * 32 + 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_hist_counts[i], 256));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_hist_kps[i], (size_t)ORBX_MAX_BACK * h->dev_cap * sizeof(orbx_keypoint) + 256));
+    }
+    const size_t slots = (size_t)ORBX_LANES * h->max_batch * ORBX_MAX_BACK;
+    ORBX_CUDA(cudaMalloc((void**)&h->d_good_back, slots * h->dev_cap * sizeof(orbx_dmatch) + 256));
+    ORBX_CUDA(cudaMalloc((void**)&h->d_ngood_back, slots * sizeof(int64_t) + 256));
+    ORBX_CUDA(cudaMallocHost((void**)&h->h_ngood_back, slots * sizeof(int64_t)));
+    ORBX_CUDA(cudaMalloc((void**)&h->d_fstatus_back, slots * h->dev_cap + 256));
+    ORBX_CUDA(cudaMalloc((void**)&h->d_fF_back, slots * 9 * sizeof(double) + 256));
+    ORBX_CUDA(cudaMalloc((void**)&h->d_finfo_back, slots * 4 * sizeof(int32_t) + 256));
+    ORBX_CUDA(cudaMallocHost((void**)&h->h_finfo_back, slots * 4 * sizeof(int32_t)));
+    h->nhist = 0;
+    h->hist_cap = 0;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, orbx_dmatch* good, int64_t* ngood)
 {
     ORBX_REQUIRE(h != nullptr && m != nullptr, "orbx_match_consecutive: NULL handle");
@@ -980,13 +1003,7 @@ extern "C" int orbx_filter_back(orbx_handle h, fmx_handle fm, double max_distanc
     { int rc_ = require_idle(h, "orbx_filter_back"); if (rc_) return rc_; }
     ORBX_CUDA(cudaSetDevice(h->device));
     const int n = h->back_n, back = h->back_back, cap = h->back_cap, npairs = n * back;
-    if (!h->d_fstatus_back) {
-        const size_t slots = (size_t)h->max_batch * ORBX_MAX_BACK;
-        ORBX_CUDA(cudaMalloc((void**)&h->d_fstatus_back, slots * h->dev_cap + 256));
-        ORBX_CUDA(cudaMalloc((void**)&h->d_fF_back, slots * 9 * sizeof(double) + 256));
-        ORBX_CUDA(cudaMalloc((void**)&h->d_finfo_back, slots * 4 * sizeof(int32_t) + 256));
-        ORBX_CUDA(cudaMallocHost((void**)&h->h_finfo_back, slots * 4 * sizeof(int32_t)));
-    }
+    { int rc_ = ensure_back_buffers(h); if (rc_) return rc_; }
     int rc = fmx_set_stream(fm, (void*)h->stream);
     if (rc) return rc;
     // orbx_match_back matched against the history that is now the inactive buffer (hist_cur was flipped after the update)
@@ -1011,18 +1028,7 @@ extern "C" int orbx_match_back(orbx_handle h, hamx_handle m, int back, float rat
     { int rc_ = require_idle(h, "orbx_match_back"); if (rc_) return rc_; }
     ORBX_CUDA(cudaSetDevice(h->device));
     const int n = h->last_nframes, cap = h->last_cap;
-    if (!h->d_hist[0]) {
-        for (int i = 0; i < 2; i++) {
-            ORBX_CUDA(cudaMalloc((void**)&h->d_hist[i], (size_t)ORBX_MAX_BACK * h->dev_cap * 32 + 256));
-            ORBX_CUDA(cudaMalloc((void**)&h->d_hist_counts[i], 256));
-            ORBX_CUDA(cudaMalloc((void**)&h->d_hist_kps[i], (size_t)ORBX_MAX_BACK * h->dev_cap * sizeof(orbx_keypoint) + 256));
-        }
-        ORBX_CUDA(cudaMalloc((void**)&h->d_good_back, (size_t)h->max_batch * ORBX_MAX_BACK * h->dev_cap * sizeof(orbx_dmatch) + 256));
-        ORBX_CUDA(cudaMalloc((void**)&h->d_ngood_back, (size_t)h->max_batch * ORBX_MAX_BACK * sizeof(int64_t) + 256));
-        ORBX_CUDA(cudaMallocHost((void**)&h->h_ngood_back, (size_t)h->max_batch * ORBX_MAX_BACK * sizeof(int64_t)));
-        h->nhist = 0;
-        h->hist_cap = 0;
-    }
+    { int rc_ = ensure_back_buffers(h); if (rc_) return rc_; }
     if (h->nhist && h->hist_cap != cap) h->nhist = 0;      // a history laid out for another capacity cannot be indexed
     int rc = hamx_set_stream(m, (void*)h->stream);
     if (rc) return rc;
@@ -1063,10 +1069,33 @@ extern "C" int orbx_submit_batch(orbx_handle h, hamx_handle m, const uint8_t* co
                                       nullptr, nullptr, nullptr);
 }
 
+static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, const uint8_t* const* frames, int nframes, int w, int hh,
+                       size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts, orbx_dmatch* good,
+                       int64_t* ngood, double max_distance, double confidence, uint8_t* status, double* F, int32_t* ninliers);
+
 extern "C" int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_handle fm, const uint8_t* const* frames, int nframes, int w, int hh,
                                           size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts,
                                           orbx_dmatch* good, int64_t* ngood, double max_distance, double confidence, uint8_t* status,
                                           double* F, int32_t* ninliers)
+{
+    return submit_impl(h, m, fm, 0, frames, nframes, w, hh, stride, ratio, out, desc, cap, counts, good, ngood, max_distance, confidence,
+                       status, F, ninliers);
+}
+
+extern "C" int orbx_submit_batch_back(orbx_handle h, hamx_handle m, fmx_handle fm, int back, const uint8_t* const* frames, int nframes, int w,
+                                      int hh, size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts,
+                                      orbx_dmatch* good, int64_t* ngood, double max_distance, double confidence, uint8_t* status, double* F,
+                                      int32_t* ninliers)
+{
+    ORBX_REQUIRE(m != nullptr, "orbx_submit_batch_back: a matcher is required");
+    ORBX_REQUIRE(back >= 1 && back <= ORBX_MAX_BACK, "orbx_submit_batch_back: back %d outside [1, %d]", back, ORBX_MAX_BACK);
+    return submit_impl(h, m, fm, back, frames, nframes, w, hh, stride, ratio, out, desc, cap, counts, good, ngood, max_distance, confidence,
+                       status, F, ninliers);
+}
+
+static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, const uint8_t* const* frames, int nframes, int w, int hh,
+                       size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts, orbx_dmatch* good,
+                       int64_t* ngood, double max_distance, double confidence, uint8_t* status, double* F, int32_t* ninliers)
 {
     ORBX_REQUIRE(h != nullptr, "orbx_submit_batch: NULL handle");
     ORBX_REQUIRE(frames && out && desc && counts && (m == nullptr || (good && ngood)), "orbx_submit_batch: NULL pointer");
@@ -1096,7 +1125,44 @@ extern "C" int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_hand
     if (rc) return rc;
     uint8_t* d_desc = h->d_desc + (size_t)s0 * cap * 32;
     orbx_dmatch* d_good = h->d_good + (size_t)s0 * cap;
-    if (m) {
+    const size_t b0 = (size_t)s0 * ORBX_MAX_BACK;          // this lane's first pair in the `back` buffers
+    if (m && back >= 1) {
+        // the steady-state loop of pnpPoseEstimation (src/CameraPoseEstimator.cpp:405-419): every frame against its `back`
+        // predecessors, matchFeatures + computeFundamentalMatrix per pair; the history (descriptors, keypoints) of the
+        // frames before the batch is double-buffered on the device and advanced in stream order
+        rc = ensure_back_buffers(h);
+        if (rc) return rc;
+        if (h->nhist && h->hist_cap != cap) h->nhist = 0;
+        const int cur = h->hist_cur, nh = std::min(h->nhist, back);
+        rc = hamx_set_stream(m, (void*)h->stream);
+        if (rc) return rc;
+        rc = hamx_match_back_dev(m, d_desc, h->d_counts + s0, nframes, cap, back, h->d_hist[cur], h->d_hist_counts[cur], nh, ratio,
+                                 h->d_good_back + b0 * cap, h->d_ngood_back + b0);
+        if (!rc) rc = hamx_update_history_dev(m, d_desc, h->d_counts + s0, nframes, cap, ORBX_MAX_BACK, h->d_hist[cur], h->d_hist_counts[cur],
+                                              h->nhist, h->d_hist[cur ^ 1], h->d_hist_counts[cur ^ 1]);
+        hamx_set_stream(m, nullptr);
+        if (rc) return rc;
+        if (fm) {
+            rc = fmx_set_stream(fm, (void*)h->stream);
+            if (rc) return rc;
+            rc = fmx_filter_back_dev(fm, h->d_kps + (size_t)s0 * cap, nframes, cap, back, h->d_hist_kps[cur], nh, h->d_good_back + b0 * cap,
+                                     h->d_ngood_back + b0, max_distance, confidence, h->d_fstatus_back + b0 * cap, h->d_fF_back + b0 * 9,
+                                     h->d_finfo_back + b0 * 4);
+            fmx_set_stream(fm, nullptr);
+            if (rc) return rc;
+        }
+        for (int hi = 0; hi < ORBX_MAX_BACK; hi++) {
+            const int src = nframes - 1 - hi;
+            const orbx_keypoint* from = src >= 0 ? h->d_kps + ((size_t)s0 + src) * cap
+                                                 : (-src - 1 < h->nhist ? h->d_hist_kps[cur] + (size_t)(-src - 1) * cap : nullptr);
+            if (from)
+                ORBX_CUDA(cudaMemcpyAsync(h->d_hist_kps[cur ^ 1] + (size_t)hi * cap, from, (size_t)cap * sizeof(orbx_keypoint),
+                                          cudaMemcpyDeviceToDevice, h->stream));
+        }
+        h->hist_cur = cur ^ 1;
+        h->nhist = std::min(ORBX_MAX_BACK, h->nhist + nframes);
+        h->hist_cap = cap;
+    } else if (m) {
         rc = hamx_set_stream(m, (void*)h->stream);
         if (rc) return rc;
         rc = hamx_match_consecutive_dev(m, d_desc, h->d_counts + s0, nframes, cap, h->have_prev ? h->d_prev_desc : nullptr,
@@ -1128,11 +1194,21 @@ extern "C" int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_hand
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr + s0, h->d_ctr + s0, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->d2h_stream));
     ORBX_CUDA(cudaMemcpyAsync(out, h->d_kps + (size_t)s0 * cap, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->d2h_stream));
     ORBX_CUDA(cudaMemcpyAsync(desc, d_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, h->d2h_stream));
-    if (m) {
+    if (m && back >= 1) {
+        const size_t np = (size_t)nframes * back;
+        ORBX_CUDA(cudaMemcpyAsync(good, h->d_good_back + b0 * cap, np * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->d2h_stream));
+        ORBX_CUDA(cudaMemcpyAsync(h->h_ngood_back + b0, h->d_ngood_back + b0, np * sizeof(int64_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (fm) {
+            ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus_back + b0 * cap, np * cap, cudaMemcpyDeviceToHost, h->d2h_stream));
+            ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF_back + b0 * 9, np * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+            ORBX_CUDA(cudaMemcpyAsync(h->h_finfo_back + b0 * 4, h->d_finfo_back + b0 * 4, np * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                      h->d2h_stream));
+        }
+    } else if (m) {
         ORBX_CUDA(cudaMemcpyAsync(good, d_good, (size_t)nframes * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->d2h_stream));
         ORBX_CUDA(cudaMemcpyAsync(h->h_ngood + s0, h->d_ngood + s0, (size_t)nframes * sizeof(int64_t), cudaMemcpyDeviceToHost, h->d2h_stream));
     }
-    if (fm) {
+    if (fm && back == 0) {
         ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus + (size_t)s0 * cap, (size_t)nframes * cap, cudaMemcpyDeviceToHost, h->d2h_stream));
         ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF + (size_t)s0 * 9, (size_t)nframes * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
         ORBX_CUDA(cudaMemcpyAsync(h->h_finfo + (size_t)s0 * 4, h->d_finfo + (size_t)s0 * 4, (size_t)nframes * 4 * sizeof(int32_t),
@@ -1145,6 +1221,7 @@ extern "C" int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_hand
     L.counts = counts;
     L.ngood = m ? ngood : nullptr;
     L.ninliers = fm ? ninliers : nullptr;
+    L.back = m ? back : 0;
     h->last_nframes = 0;            // orbx_match_consecutive pairs with orbx_extract_batch only
     h->filter_nframes = 0;
     h->back_n = 0;
@@ -1165,8 +1242,16 @@ extern "C" int orbx_wait_batch(orbx_handle h)
     const int s0 = li * h->max_batch;
     for (int f = 0; f < L.nframes; f++) {
         L.counts[f] = h->h_ctr[s0 + f].total;
+        if (L.back) continue;
         if (L.ngood) L.ngood[f] = h->h_ngood[s0 + f];
         if (L.ninliers) L.ninliers[f] = h->h_finfo[(size_t)(s0 + f) * 4];
+    }
+    if (L.back) {
+        const size_t b0 = (size_t)s0 * ORBX_MAX_BACK;
+        for (int p = 0; p < L.nframes * L.back; p++) {
+            L.ngood[p] = h->h_ngood_back[b0 + p];
+            if (L.ninliers) L.ninliers[p] = h->h_finfo_back[(b0 + p) * 4];
+        }
     }
     return check_counters(h, L.nframes, L.cap, s0);
 }

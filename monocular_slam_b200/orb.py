@@ -206,12 +206,14 @@ class ORB:
         return status, F, ninl
 
     # -- pipelined sequence mode: pipeline_depth() batches in flight (upload / kernels / download overlap across batches)
-    def submit_batch(self, frames, matcher, ratio, out, fundamental=None, max_distance=3.0, confidence=0.85):
+    def submit_batch(self, frames, matcher, ratio, out, fundamental=None, max_distance=3.0, confidence=0.85, back=0):
         """Enqueue extraction (+ consecutive-frame matching when ``matcher`` is given) of a batch and return at once.
         ``out`` = (kps[n, cap], desc[n, cap, 32], counts[n] int32, good[n, cap], ngood[n] int64): caller-owned buffers
         (pinned for real overlap) that are complete after the matching ``wait_batch()``.  With ``fundamental`` (a
         FundamentalFilter) the outlier filter of every (frame, predecessor) pair runs in the same submission and ``out``
-        carries three more buffers: status[n, cap] uint8, F[n, 3, 3] float64, ninliers[n] int32."""
+        carries three more buffers: status[n, cap] uint8, F[n, 3, 3] float64, ninliers[n] int32.  With ``back`` >= 1 every
+        frame is paired with its ``back`` predecessors instead (the numBackTraverse loop, src/CameraPoseEstimator.cpp:405-419):
+        good[n, back, cap], ngood[n, back], status[n, back, cap], F[n, back, 3, 3], ninliers[n, back]."""
         frames = [_gray(f) for f in frames]
         self._set_channels(frames[0])
         n = len(frames)
@@ -225,7 +227,20 @@ class ORB:
             raise ValueError("bad output buffers")
         ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
         self._inflight = getattr(self, "_inflight", [])
-        if fundamental is not None:
+        if back:
+            if good.shape[1:] != (back, cap) or ngood.shape[1:] != (back,):
+                raise ValueError("bad match output buffers for back = %d" % back)
+            st = F = ni = None
+            if fundamental is not None:
+                st, F, ni = out[5:8]
+                if st.shape[1:] != (back, cap) or st.dtype != np.uint8 or F.dtype != np.float64 or ni.dtype != np.int32:
+                    raise ValueError("bad filter output buffers")
+            check(_lib.lib().orbx_submit_batch_back(self._h, matcher._h, fundamental._h if fundamental is not None else None, int(back),
+                                                    ptrs, n, w, h, stride, float(ratio), kps.ctypes.data, desc.ctypes.data, cap,
+                                                    counts.ctypes.data, good.ctypes.data, ngood.ctypes.data, float(max_distance),
+                                                    float(confidence), st.ctypes.data if st is not None else None,
+                                                    F.ctypes.data if F is not None else None, ni.ctypes.data if ni is not None else None))
+        elif fundamental is not None:
             status, F, ninl = out[5:8]
             if status.shape[:2] != kps.shape[:2] or status.dtype != np.uint8 or F.dtype != np.float64 or ninl.dtype != np.int32:
                 raise ValueError("bad filter output buffers")

@@ -309,3 +309,48 @@ def test_whole_chain_on_images_matches_cv2(fm, name):
     assert ng[1] == len(good) and np.array_equal(st[1, :ng[1]], mask) and np.array_equal(Fs[1], F) and ni[0] == 0
     orb.close()
     bf.close()
+
+
+def test_pipelined_back_submission_equals_blocking_calls(fm):
+    """orbx_submit_batch_back (3 predecessors per frame, matcher + filter, 3 batches in flight) == extract_batch + match_back +
+    filter_back per batch, history carried across batches in both."""
+    w, h, n, nf, nb, back = 640, 480, 3, 700, 5, 3
+    frames = syn.sequence(nb * n, w, h, seed=17)
+    orb = ORB(nfeatures=nf, max_size=(w, h), max_batch=n)
+    bf = BFMatcher()
+    want = []
+    for b in range(nb):
+        kps, desc, counts = orb.extract_batch(frames[b * n:(b + 1) * n])
+        cap = kps.shape[1]
+        good, ngood = orb.match_back(bf, back, 0.8, cap, n)
+        want.append((counts.copy(), good.copy(), ngood.copy()) + orb.filter_back(fm, back, cap, n))
+    orb.reset_sequence()
+
+    def bufs():
+        return (np.zeros((n, cap), KEYPOINT_DTYPE), np.zeros((n, cap, 32), np.uint8), np.zeros(n, np.int32), np.zeros((n, back, cap), DMATCH_DTYPE),
+                np.zeros((n, back), np.int64), np.zeros((n, back, cap), np.uint8), np.zeros((n, back, 3, 3)), np.zeros((n, back), np.int32))
+    got = []
+    for b in range(nb):
+        if orb.batches_in_flight() == orb.pipeline_depth():
+            got.append(orb.wait_batch())
+        orb.submit_batch(frames[b * n:(b + 1) * n], bf, 0.8, bufs(), fundamental=fm, back=back)
+    while orb.batches_in_flight():
+        got.append(orb.wait_batch())
+    for b in range(nb):
+        counts, good, ngood, status, F, ninl = want[b]
+        o = got[b]
+        assert np.array_equal(o[2], counts) and np.array_equal(o[4], ngood)
+        for f in range(n):
+            for j in range(back):
+                k = ngood[f, j]
+                assert np.array_equal(o[3][f, j, :k], good[f, j, :k]) and np.array_equal(o[5][f, j, :k], status[f, j, :k])
+        assert np.array_equal(o[6], F) and np.array_equal(o[7], ninl)
+    assert want[-1][2].min() > 100 and want[-1][5].min() >= 0
+    # matcher only (no filter) through the same entry point
+    orb.reset_sequence()
+    o = bufs()[:5]
+    orb.submit_batch(frames[:n], bf, 0.8, o, back=back)
+    orb.wait_batch()
+    assert np.array_equal(o[4], want[0][2])
+    orb.close()
+    bf.close()

@@ -335,12 +335,12 @@ def run_ours(args, rank, world, local_rank):
                 np.zeros(B, np.int64))
     depth = orb.pipeline_depth()
     outs = [pinned_out() for _ in range(depth)]
-    pstate = {"k": 0, "last": None, "outs": outs, "fm": None}
+    pstate = {"k": 0, "last": None, "outs": outs, "fm": None, "back": 0}
 
     def step_pipe():
         if orb.batches_in_flight() == depth:
             pstate["last"] = orb.wait_batch()
-        orb.submit_batch(frames_np, matcher, RATIO, pstate["outs"][pstate["k"] % depth], fundamental=pstate["fm"])
+        orb.submit_batch(frames_np, matcher, RATIO, pstate["outs"][pstate["k"] % depth], fundamental=pstate["fm"], back=pstate["back"])
         pstate["k"] += 1
 
     def drain():
@@ -525,6 +525,26 @@ def run_ours(args, rank, world, local_rank):
             "matches_per_pair": float(last[4][1:].mean()), "inliers_per_pair": float(last[7][1:].mean()),
             "note": "the synthetic sequence is a translating texture, i.e. a planar scene: F is degenerate there, the numbers time the "
                     "filter on real match lists but say nothing about pose quality"}
+        # the reference's steady-state loop (src/CameraPoseEstimator.cpp:405-419) through orbx_submit_batch_back: every frame
+        # extracted, matched against its 5 predecessors and each of the 5 match lists filtered, host buffers in and out
+        nb_ = 5
+
+        def pinned(shape, dtype):
+            return torch.zeros(shape, dtype=dtype).pin_memory().numpy()
+        pstate["outs"] = [o[:3] + (pinned((B, nb_, cap, 4), torch.int32).view(DMATCH_DTYPE).reshape(B, nb_, cap), np.zeros((B, nb_), np.int64),
+                                   pinned((B, nb_, cap), torch.uint8), pinned((B, nb_, 3, 3), torch.float64), np.zeros((B, nb_), np.int32))
+                          for o in outs]
+        pstate["fm"], pstate["back"] = fm, nb_
+        orb.reset_sequence()
+        ss_ms = max_over_ranks(timed_pipe(args.steps, max(args.warmup, 2)))
+        pstate["fm"], pstate["back"] = None, 0
+        last = pstate["last"]
+        fundamental["steady_state_pipeline"] = {
+            "value": world * B * args.steps / (ss_ms * 1e-3), "unit": "frames/s", "ms_per_step": ss_ms / args.steps,
+            "what": "per frame: extraction + matchFeatures against the 5 previous frames + computeFundamentalMatrix of the 5 match lists "
+                    "(orbx_submit_batch_back, 3 batches in flight, pinned host buffers in and out)",
+            "pairs_per_step": B * nb_, "matches_per_pair": float(last[4].mean()), "inliers_per_pair": float(last[7].mean()),
+            "d2h_bytes_per_step": int(B * cap * 60 + B * nb_ * cap * 17 + B * nb_ * 88)}
         if world == 1 and not args.no_cpu:
             try:
                 import oracle

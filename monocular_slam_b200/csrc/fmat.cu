@@ -612,7 +612,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             sh.next = 0;
             sh.first_bad = chunk;
             sh.run_max = max(sh.maxgood, FM_MODEL_POINTS - 1);
-            sh.iter_limit = sh.niters;
+            sh.iter_limit = (sh.niters << 8) | 0xff;        // (budget << 8) | iteration of the candidate that implied it
         }
         FM_TICK(0);
         __syncthreads();
@@ -647,7 +647,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         // (step 4) will decide.  Every candidate completed by then precedes the one taken (candidates are handed out in order),
         // so (a) a count that cannot exceed sh.run_max -- the best exact count completed so far -- can never become the best:
         // the candidate is abandoned as soon as that is certain; (b) once a completed count c bounds the iteration budget by
-        // iter_limit_of(c), a candidate of a later iteration is never reached and is skipped altogether.
+        // iter_limit_of(c), a candidate of a later iteration at or beyond that budget is never reached and is skipped altogether.
         for (;;) {
             int m = 0, bound = 0, limit = 0;
             if (lane == 0) {
@@ -662,7 +662,9 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             if (m >= 3 * chunk) break;
             const int it = m / 3, k = m - 3 * it;
             if (k >= sh.nmodels[it]) continue;
-            if (iter0 + it >= limit) { if (lane == 0) sh.count[it][k] = 0; continue; }
+            // the budget a completed candidate implies takes effect at the top of the NEXT iteration: it only rules out
+            // candidates of strictly later iterations (the other models of its own iteration are still scored by OpenCV)
+            if ((limit & 0xff) < it && iter0 + it >= (limit >> 8)) { if (lane == 0) sh.count[it][k] = 0; continue; }
             const double* Fm = sh.models[it] + 9 * k;
             Cand32 c32;
             cand32_init(c32, Fm, cm);
@@ -690,7 +692,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             if (lane == 0) {
                 sh.count[it][k] = cnt;
                 if (cnt > bound && cnt > atomicMax(&sh.run_max, cnt))
-                    atomicMin(&sh.iter_limit, iter_limit_of(lognum, n, cnt, niters0));
+                    atomicMin(&sh.iter_limit, (iter_limit_of(lognum, n, cnt, niters0) << 8) | it);    // it < 128; smallest budget wins
             }
             scored++;
         }
@@ -699,8 +701,8 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         // ---- 4. OpenCV's sequential update rule over the chunk, evaluated by warp 0 in parallel.  In sequence order a
         // candidate becomes the best iff its count exceeds every earlier one (and the floor): an exclusive prefix maximum.
         // Each such improvement j lowers the iteration budget to min(budget, r_j), r_j = RANSACUpdateNumIters' closed form, and
-        // the loop reaches it iff its iteration index is below the budget left by the improvements before it: an exclusive
-        // prefix minimum.  Budgets only shrink and indices only grow, so the improvements reached form a prefix; the last one
+        // the loop reaches it iff its iteration index is below the budget left by the improvements of EARLIER ITERATIONS (the
+        // budget is checked once per iteration, not per model): an exclusive prefix minimum over iterations.  Budgets only shrink and indices only grow, so the improvements reached form a prefix; the last one
         // reached is the result of the round.
         if (warp == 0) {
             static_assert(FM_MAXCHUNK == 128, "4 iterations per lane");
@@ -745,12 +747,16 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             }
             int P = __shfl_up_sync(0xffffffffu, pmin, 1);
             P = min(lane ? P : INT_MAX, N0);
-            int last = -1, last_cnt = 0, last_n = 0;
+            // P: budget in force at the top of the iteration being looked at (improvements of strictly earlier iterations);
+            // Q: budget including the improvements of this iteration seen so far -- OpenCV checks the budget once per iteration,
+            // so the models of one iteration are all scored and may improve one after the other
+            int last = -1, last_cnt = 0, last_n = 0, Q = P;
 #pragma unroll
             for (int e = 0; e < 12; e++) {
+                if (e % 3 == 0) P = Q;
                 if (cnt[e] >= 0) {
-                    if (iter0 + lane * 4 + e / 3 < P) { last = lane * 12 + e; last_cnt = cnt[e]; last_n = min(P, lim[e]); }
-                    P = min(P, lim[e]);
+                    if (iter0 + lane * 4 + e / 3 < P) { last = lane * 12 + e; last_cnt = cnt[e]; last_n = min(Q, lim[e]); }
+                    Q = min(Q, lim[e]);
                 }
             }
             int g = last;

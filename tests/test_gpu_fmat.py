@@ -354,3 +354,15 @@ def test_pipelined_back_submission_equals_blocking_calls(fm):
     assert np.array_equal(o[4], want[0][2])
     orb.close()
     bf.close()
+
+
+def test_regression_two_improvements_in_one_iteration(fm):
+    """Found by tools/fmat_soak.py: iteration 12 of this pair yields candidates with 10, 67 and 71 inliers.  The 67 lowers the budget
+    to 8 (< 12), but OpenCV checks the budget once per iteration, so the 71 of the same iteration is still scored and wins.
+    (cv2 mask in tests/golden/fmat_regressions.npz.)"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fmat_regressions.npz"))
+    p1, p2 = g["two_improvements_in_one_iteration_p1"], g["two_improvements_in_one_iteration_p2"]
+    thr, conf = g["two_improvements_in_one_iteration_cfg"]
+    status, F, ninl = fm.find_batch(p1[None], p2[None], [len(p1)], float(thr), float(conf))
+    assert np.array_equal(status[0], g["two_improvements_in_one_iteration_mask"]) and ninl[0] == 71
+    assert fm.last_info(1)[0, 1] == 13

@@ -115,3 +115,12 @@ def test_whole_chain_on_images_matches_cv2(name):
     mask = np.unpackbits(CHAIN[name + "_mask"])[:len(gq)]
     assert np.array_equal(status, mask) and ninl == CHAIN[name + "_counts"][3]
     assert rel(F, CHAIN[name + "_F8"]) <= F_RTOL
+
+
+def test_regression_two_improvements_in_one_iteration():
+    """The budget is checked once per iteration: a second improvement inside the iteration that exhausted it still counts."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fmat_regressions.npz"))
+    p1, p2 = g["two_improvements_in_one_iteration_p1"], g["two_improvements_in_one_iteration_p2"]
+    thr, conf = g["two_improvements_in_one_iteration_cfg"]
+    F, m, iters = oracle.fm_ransac(p1, p2, float(thr), float(conf))
+    assert np.array_equal(m, g["two_improvements_in_one_iteration_mask"]) and iters == 13

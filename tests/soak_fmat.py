@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Soak comparison of the fundamental-matrix filter on the GPU against the CPU oracle: many random two-view match sets
 (sizes, inlier ratios, noise, thresholds, confidences, image sizes), every status mask and iteration count compared.
-Usage: python tools/fmat_soak.py [npairs_total]"""
+Not collected by pytest (minutes of CPU oracle time): run by hand on a GPU box.
+Usage: python tests/soak_fmat.py [npairs_total]"""
 import os
 import sys
 import time

@@ -2,7 +2,8 @@
 """Soak comparison of the ORB extraction and the Hamming matcher on the GPU against the CPU oracle: random frame sizes,
 textures and runtime parameters (keypoints, responses, angles, descriptors bit for bit), then random descriptor sets with
 planted duplicates (kNN2 indices / distances and the ratio-filtered list).
-Usage: python tools/orb_soak.py [nframes] [nmatch_cases]"""
+Not collected by pytest (minutes of CPU oracle time): run by hand on a GPU box.
+Usage: python tests/soak_orb.py [nframes] [nmatch_cases]"""
 import os
 import sys
 import time

@@ -357,7 +357,7 @@ def test_pipelined_back_submission_equals_blocking_calls(fm):
 
 
 def test_regression_two_improvements_in_one_iteration(fm):
-    """Found by tools/fmat_soak.py: iteration 12 of this pair yields candidates with 10, 67 and 71 inliers.  The 67 lowers the budget
+    """Found by tests/soak_fmat.py: iteration 12 of this pair yields candidates with 10, 67 and 71 inliers.  The 67 lowers the budget
     to 8 (< 12), but OpenCV checks the budget once per iteration, so the 71 of the same iteration is still scored and wins.
     (cv2 mask in tests/golden/fmat_regressions.npz.)"""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fmat_regressions.npz"))

@@ -1,15 +1,13 @@
 #!/usr/bin/env python
-"""Device time of the fundamental-matrix outlier filter (k_fm_ransac) on BASELINE-shaped batches, with the CPU oracle and
-cv2-free baseline beside it.  Usage: python tools/fmat_probe.py [npairs] [matches per pair] [inlier ratio]"""
+"""Device time of the fundamental-matrix outlier filter (k_fm_ransac) on BASELINE-shaped batches (the CPU baselines beside it
+are in bench.py's `fundamental` section).  Usage: python tools/fmat_probe.py [npairs] [matches per pair] [inlier ratio]"""
 import os
 import sys
-import time
 
 import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle  # noqa: E402  (CPU baseline only)
 from monocular_slam_b200 import FundamentalFilter  # noqa: E402
 from monocular_slam_b200 import synthetic as syn  # noqa: E402
 
@@ -45,16 +43,8 @@ def main():
             stream.synchronize()
         ms = e0.elapsed_time(e1) / reps
         info = di.cpu().numpy()
-        t0 = time.perf_counter()
-        ncpu = min(npairs, 16)
-        for i in range(ncpu):
-            _, m, _ = oracle.fm_ransac(p1[i], p2[i], 3.0, conf)
-            oracle.fm_8point(p1[i][m > 0], p2[i][m > 0])
-        cpu_ms = (time.perf_counter() - t0) * 1e3 / ncpu
         print("conf %.2f: %d pairs x %d matches (inlier ratio %.2f): %.3f ms per batch = %.0f pairs/s; iterations mean %.1f max %d, "
-              "candidates scored mean %.1f; CPU oracle %.3f ms per pair (1 core) -> %.0fx"
-              % (conf, npairs, n, inl, ms, npairs / ms * 1e3, info[:, 1].mean(), info[:, 1].max(), info[:, 2].mean(), cpu_ms,
-                 cpu_ms * npairs / ms))
+              "candidates scored mean %.1f" % (conf, npairs, n, inl, ms, npairs / ms * 1e3, info[:, 1].mean(), info[:, 1].max(), info[:, 2].mean()))
 
 
 if __name__ == "__main__":

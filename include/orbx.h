@@ -242,9 +242,10 @@ ORBX_API int hamx_popc_peak(int device, double* gpopc_per_s, double* elapsed_ms)
  *     F = findFundamentalMat(inliers1, inliers2, CV_FM_8POINT);                                     (:585)
  * One CUDA block per pair reproduces OpenCV's sequential RANSAC (same random sample sequence, same candidate order,
  * same best-update and iteration-budget rule), so `status` is the mask OpenCV returns; F is the 8-point matrix of the
- * inliers, scaled to F[8] = 1 (row-major double[9]; all zeros when there is no result).  Pairs with fewer than 15
- * correspondences report no model (OpenCV switches to LMedS / the bare 7-point solver there, whose outcome is decided
- * by rounding noise).  max_distance <= 0 means 3, confidence outside (0, 1) means 0.99, as in OpenCV; the reference passes
+ * inliers, scaled to F[8] = 1 (row-major double[9]; all zeros when there is no result).  With 8..14
+ * correspondences OpenCV runs least-median-of-squares instead of RANSAC (same sampler, fixed iteration count); so does
+ * the kernel -- identical to OpenCV with 14, a valid LMedS answer with 8..13 (there OpenCV's own winner is decided by
+ * 1e-25-level rounding noise).  Fewer than 8 correspondences report no model.  max_distance <= 0 means 3, confidence outside (0, 1) means 0.99, as in OpenCV; the reference passes
  * MAX_DISTANCE = 3 and CONFIDENCE = 0.85 (src/ParamConfig.h:24-25). */
 typedef struct fmx_context* fmx_handle;
 ORBX_API int fmx_create(fmx_handle* out, int device);

@@ -70,6 +70,8 @@ struct FmShared {
     int rot_p[4], rot_q[4];
     int cmax[4];                      // largest |x1| |y1| |x2| |y2| of the pair (float bits; non-negative floats order like ints)
     int iter, niters, maxgood, chunk, stop, have, next, first_bad, run_max, iter_limit;
+    int min_median;                   // LMedS: float bits of the smallest median so far (+inf bits: none)
+    float lmeds_t2;                   // LMedS: squared inlier threshold derived from it
 };
 
 __device__ __forceinline__ unsigned rng_next(unsigned long long& s)
@@ -119,11 +121,11 @@ __device__ __forceinline__ void draw_indices(int n, unsigned m, unsigned long lo
 }
 
 // RANSACPointSetRegistrator::getSubset: 7 distinct indices whose last point is not collinear with two earlier ones
-__device__ bool get_subset(const float2* P1, const float2* P2, int n, unsigned long long& rng, int* out)
+__device__ bool get_subset(const float2* P1, const float2* P2, int n, unsigned long long& rng, int* out, int max_attempts)
 {
     int idx[FM_MODEL_POINTS];
     float2 a[FM_MODEL_POINTS], b[FM_MODEL_POINTS];
-    for (int iters = 0; iters < 10000; iters++) {
+    for (int iters = 0; iters < max_attempts; iters++) {
         for (int i = 0; i < FM_MODEL_POINTS;) {
             const int v = (int)(rng_next(rng) % (unsigned)n);
             int j;
@@ -300,7 +302,7 @@ __device__ int solve7(const float2* P1, const float2* P2, const int* idx, double
 
 // FMEstimatorCallback::computeError for one correspondence, then findInliers' test `(float)max(d1*d1*s1, d2*d2*s2) <= t2`
 // with s = 1/(a*a + b*b), exactly as OpenCV evaluates it (Fm: the matrix in shared memory).
-__device__ __noinline__ bool is_inlier_exact(const double* Fm, float2 p1, float2 p2, float t2)
+__device__ __noinline__ float epi_error(const double* Fm, float2 p1, float2 p2)
 {
     const double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
     double a = Fm[0] * x1 + Fm[1] * y1 + Fm[2], b = Fm[3] * x1 + Fm[4] * y1 + Fm[5], c = Fm[6] * x1 + Fm[7] * y1 + Fm[8];
@@ -308,8 +310,10 @@ __device__ __noinline__ bool is_inlier_exact(const double* Fm, float2 p1, float2
     a = Fm[0] * x2 + Fm[3] * y2 + Fm[6]; b = Fm[1] * x2 + Fm[4] * y2 + Fm[7]; c = Fm[2] * x2 + Fm[5] * y2 + Fm[8];
     const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
     const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
-    return __double2float_rn(e1 < e2 ? e2 : e1) <= t2;       // std::max(e1, e2)
+    return __double2float_rn(e1 < e2 ? e2 : e1);             // (float)std::max(e1, e2)
 }
+
+__device__ __forceinline__ bool is_inlier_exact(const double* Fm, float2 p1, float2 p2, float t2) { return epi_error(Fm, p1, p2) <= t2; }
 
 // The two divisions are only needed for points within 1e-6 (relative) of the threshold: with the same a, b, d as OpenCV
 // computes, q = d*d <= t2*(1 - 1e-9)*den implies q*fl(1/den) < t2, and q >= t2*(1 + 1e-6)*den implies it exceeds the largest
@@ -548,10 +552,14 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     for (int i = tid; i < cap; i += FM_THREADS) st[i] = 0;
     if (tid < 9) Fo[tid] = 0.;
     if (tid < 4) inf[tid] = 0;
-    // OpenCV: fewer than 7 points -> empty result; exactly 7 -> the 7-point solver alone; 8..14 -> LMedS, whose choice among
-    // exact-fit candidates is decided by rounding noise (median of <= 14 errors, 7 of them ~1e-25).  None of these is usable
-    // for pose estimation; the filter reports "no model" (0 inliers) for fewer than 15 correspondences.
-    if (n < 15) return;
+    // OpenCV: fewer than 7 points -> empty result; exactly 7 -> the bare 7-point solver (up to three stacked matrices the
+    // reference cannot use): both report "no model" here.  8..14 points -> least median of squares instead of RANSAC
+    // (findFundamentalMat: `npoints >= 15` selects RANSAC): same sampler, a fixed iteration count, the candidate with the
+    // smallest median error wins.  (With fewer than 14 points that median is the error of a point the candidate was fitted
+    // to, ~1e-25, so OpenCV's own choice is decided by rounding noise; the result is a valid LMedS answer, not necessarily
+    // OpenCV's.  With 14 it is reproducible, and tested.)
+    if (n < 8) return;
+    const bool lmeds = n < 15;
 
     if (tid < 4) sh.cmax[tid] = 0;
     __syncthreads();
@@ -575,14 +583,20 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     }
     if (thr <= 0) thr = 3;
     if (conf < DBL_EPSILON || conf > 1 - DBL_EPSILON) conf = 0.99;
-    const float t2 = __double2float_rn(thr * thr);
-    const double tlo = (double)t2 * (1. - 1e-9), thi = (double)t2 * (1. + 1e-6);
+    float t2 = __double2float_rn(thr * thr);
+    double tlo = (double)t2 * (1. - 1e-9), thi = (double)t2 * (1. + 1e-6);
     const float tlo32 = __double2float_rd(tlo * (1. - 4e-6)), thi32 = __double2float_ru(thi * (1. + 4e-6));
     const unsigned nmod = (unsigned)(0x100000000ULL / (unsigned)n);
     const double lognum = log(fmax(1. - fmin(fmax(conf, 0.), 1.), DBL_MIN));
     if (tid == 0) {
         sh.rng = 0xffffffffffffffffULL;
         sh.iter = 0; sh.niters = max_iters; sh.maxgood = 0; sh.stop = 0; sh.have = 0;
+        sh.min_median = 0x7f800000;
+        if (lmeds) {        // LMeDSPointSetRegistrator: RANSACUpdateNumIters(confidence, outlierRatio = 0.45, 7, maxIters), at least 3
+            const double denom = log(1. - pow(1. - 0.45, (double)FM_MODEL_POINTS));
+            const double q = lognum / denom;
+            sh.niters = max(3, q >= (double)max_iters ? max_iters : __double2int_rn(q));
+        }
     }
     __syncthreads();
 
@@ -601,7 +615,8 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             // usually collapses as soon as a good sample is scored; candidates past that point are skipped by the running
             // iteration limit of step 3, so a long round costs little, and it has fewer serial sections than several short ones.
             const int remaining = sh.niters - sh.iter;
-            const int chunk = min(remaining, round == 0 ? FM_FIRSTCHUNK : min(FM_MAXCHUNK, max(FM_FIRSTCHUNK, remaining / FM_CHUNKDIV)));
+            const int chunk = lmeds ? min(remaining, FM_MAXCHUNK)
+                                    : min(remaining, round == 0 ? FM_FIRSTCHUNK : min(FM_MAXCHUNK, max(FM_FIRSTCHUNK, remaining / FM_CHUNKDIV)));
             unsigned long long rng = sh.rng;
             for (int i = 0; i < chunk; i++) {
                 sh.rng_at[i] = rng;
@@ -628,7 +643,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
                 int chunk = sh.chunk;
                 unsigned long long rng = sh.rng_at[sh.first_bad];
                 for (int i = sh.first_bad; i < chunk; i++)
-                    if (!get_subset(P1, P2, n, rng, sh.idx[i])) { chunk = i; sh.stop = 1; break; }     // OpenCV leaves its loop here
+                    if (!get_subset(P1, P2, n, rng, sh.idx[i], lmeds ? 1000 : 10000)) { chunk = i; sh.stop = 1; break; }     // OpenCV leaves its loop here
                 sh.rng = rng;
                 sh.chunk = chunk;
             }
@@ -642,6 +657,56 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         if (tid < chunk) sh.nmodels[tid] = solve7(P1, P2, sh.idx[tid], sh.models[tid]);
         __syncthreads();
         FM_TICK(2);
+        if (lmeds) {
+            // ---- 3'/4' (8..14 points): one thread per candidate computes OpenCV's float errors and their median (element n/2 of
+            // the errors sorted as integers, as LMeDSPointSetRegistrator does); warp 0 then takes the first candidate in sequence
+            // order whose median is below every earlier one.
+            for (int m = tid; m < 3 * chunk; m += FM_THREADS) {
+                const int it = m / 3, k = m - 3 * it;
+                int med = 0x7fffffff;
+                if (k < sh.nmodels[it]) {
+                    const double* Fm = sh.models[it] + 9 * k;
+                    int e[14];
+                    for (int i = 0; i < n; i++) {
+                        const int v = __float_as_int(epi_error(Fm, P1[i], P2[i]));
+                        int j = i;
+                        for (; j > 0 && e[j - 1] > v; j--) e[j] = e[j - 1];
+                        e[j] = v;
+                    }
+                    med = e[n / 2];
+                    scored++;
+                }
+                sh.count[it][k] = med;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                unsigned long long best = ~0ULL;
+#pragma unroll
+                for (int e = 0; e < 12; e++) {
+                    const int i = lane * 4 + e / 3;
+                    if (i < chunk) {
+                        const unsigned long long key = ((unsigned long long)(unsigned)sh.count[i][e % 3] << 32) | (unsigned)(lane * 12 + e);
+                        best = min(best, key);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                if (lane == 0) {
+                    const int bits = (int)(best >> 32), g = (int)(best & 0xffffffffu);
+                    if (bits >= 0 && bits < sh.min_median) {          // `median < minMedian`; NaN / inf medians never qualify
+                        sh.min_median = bits;
+                        const double* m = sh.models[g / 3] + 9 * (g % 3);
+                        for (int j = 0; j < 9; j++) sh.best[j] = m[j];
+                        sh.have = 1;
+                    }
+                    sh.iter = iter0 + chunk;
+                    if (sh.iter >= sh.niters) sh.stop = 1;
+                }
+            }
+            __syncthreads();
+            if (sh.stop) break;
+            continue;
+        }
         // ---- 3. one warp per candidate, handed out in sequence order: inlier count.
         // Two facts a warp reads BEFORE it takes the next candidate let it do less without changing what the sequential rule
         // (step 4) will decide.  Every candidate completed by then precedes the one taken (candidates are handed out in order),
@@ -786,6 +851,18 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
         if (tid == 0) inf[1] = sh.iter;
         return;
     }
+    if (lmeds) {
+        // inlier threshold of LMedS: sigma = 2.5 * 1.4826 * (1 + 5 / (n - 7)) * sqrt(minMedian), at least 0.001
+        if (tid == 0) {
+            double sigma = 2.5 * 1.4826 * (1. + 5. / (n - FM_MODEL_POINTS)) * sqrt((double)__int_as_float(sh.min_median));
+            sigma = fmax(sigma, 0.001);
+            sh.lmeds_t2 = __double2float_rn(sigma * sigma);
+        }
+        __syncthreads();
+        t2 = sh.lmeds_t2;
+        tlo = (double)t2 * (1. - 1e-9);
+        thi = (double)t2 * (1. + 1e-6);
+    }
 
     // ---- status mask of the winning matrix
     double F[9];
@@ -807,6 +884,11 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     const int k = (int)sh.red[0][4];
     const double tk = 1. / k;
     const double c1x = sh.red[0][0] * tk, c1y = sh.red[0][1] * tk, c2x = sh.red[0][2] * tk, c2y = sh.red[0][3] * tk;
+    if (lmeds && k < FM_MODEL_POINTS) {                  // LMeDSPointSetRegistrator: result = count >= modelPoints
+        for (int i = tid; i < n; i += FM_THREADS) st[i] = 0;
+        if (tid == 0) inf[1] = sh.iter;
+        return;
+    }
     if (tid == 0) { inf[0] = k; inf[1] = sh.iter; }
     if (k < 8) return;                                   // 7 inliers: OpenCV's FM_8POINT call degenerates to the 7-point solver
     {

@@ -26,7 +26,7 @@ def main():
         thr = float(r.choice([0.5, 1.0, 2.0, 3.0, 5.0]))
         conf = float(r.choice([0.85, 0.95, 0.99]))
         size = [(640, 480), (1241, 376), (1920, 1080), (3840, 2160)][int(r.integers(0, 4))]
-        counts = r.integers(15, cap + 1, npairs).astype(np.int32)
+        counts = r.integers(14, cap + 1, npairs).astype(np.int32)         # 14: the LMedS path
         p1 = np.zeros((npairs, cap, 2), np.float32)
         p2 = np.zeros((npairs, cap, 2), np.float32)
         for i in range(npairs):

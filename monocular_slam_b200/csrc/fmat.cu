@@ -398,9 +398,15 @@ __device__ __forceinline__ bool is_inlier(const double* F, const double* Fm, flo
 __device__ int iter_limit_of(double lognum, int n, int good, int n0)
 {
     const float w = (float)good / (float)n, w2 = w * w, w7 = w2 * w2 * w2 * w, df = 1.f - w7;
-    if (df >= 1.f) return n0;                                       // w^7 < 6e-8: the formula exceeds 1e7
-    const float qf = (float)lognum / logf(df);                      // df == 0: -0 -> not screened out
-    if (!(qf < 2.f * (float)n0 + 2.f)) return n0;
+    const float lim = 2.f * (float)n0 + 2.f;
+    if (df >= 1.f) {
+        // w^7 <= 3e-8 is below single-precision resolution next to 1: the formula is at least |lognum| / 3.1e-8, which only
+        // decides the matter for confidences that are not tiny; otherwise fall through to the double-precision expression
+        if ((float)(-lognum) >= lim * 1.2e-7f) return n0;
+    } else {
+        const float qf = (float)lognum / logf(df);                  // df == 0: -0 -> not screened out
+        if (!(qf < lim)) return n0;                                 // df is within a factor 1.5 of 1 - w^7 in its log: 2 n0 suffices
+    }
     double ep = (double)(n - good) / n;
     ep = fmin(fmax(ep, 0.), 1.);
     double denom = 1. - pow(1. - ep, (double)FM_MODEL_POINTS);

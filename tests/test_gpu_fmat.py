@@ -391,3 +391,22 @@ def test_least_median_path_for_8_to_14_points(fm):
         assert not status[i, counts[i]:].any() and ninl[i] == status[i].sum() and (ninl[i] == 0 or ninl[i] >= 7)
         if ninl[i] >= 8:
             assert abs(np.linalg.det(F[i] / np.linalg.norm(F[i]))) < 1e-9
+
+
+@pytest.mark.parametrize("conf", [1e-9, 1e-4, 0.3, 1.0 - 1e-12])
+def test_extreme_confidences(fm, conf):
+    """Confidence only enters through the iteration budget log(1 - conf) / log(1 - w^7): tiny values end the loop after a handful of
+    iterations, values next to 1 run it to the cap.  The budget screen in single precision must never change the count."""
+    npairs, cap = 24, 400
+    r = np.random.default_rng(11)
+    counts = r.integers(15, cap + 1, npairs).astype(np.int32)
+    p1 = np.zeros((npairs, cap, 2), np.float32)
+    p2 = np.zeros((npairs, cap, 2), np.float32)
+    for i in range(npairs):
+        p1[i, :counts[i]], p2[i, :counts[i]] = syn.two_view_matches(8100 + i, int(counts[i]), float(r.uniform(0.1, 0.95)), 0.5)
+    status, F, ninl = fm.find_batch(p1, p2, counts, 3.0, conf)
+    info = fm.last_info(npairs)
+    for i in range(npairs):
+        n = int(counts[i])
+        _, mo, iters = oracle.fm_ransac(p1[i, :n], p2[i, :n], 3.0, conf)
+        assert info[i, 1] == iters and np.array_equal(status[i, :n], mo), (i, info[i, 1], iters)

@@ -410,3 +410,26 @@ def test_extreme_confidences(fm, conf):
         n = int(counts[i])
         _, mo, iters = oracle.fm_ransac(p1[i, :n], p2[i, :n], 3.0, conf)
         assert info[i, 1] == iters and np.array_equal(status[i, :n], mo), (i, info[i, 1], iters)
+
+
+@pytest.mark.parametrize("step", [8, 32, 64])
+def test_collinear_rejections_on_grid_points(fm, step):
+    """Positions snapped to a coarse grid make 3 % (step 8) to 50 % (step 64) of the drawn samples fail OpenCV's collinearity test.
+    The kernel draws a round's samples assuming none is rejected and redoes the round from the first rejected one with the
+    sequential rule; the generator state must continue exactly as in the sequential loop -- same status masks and iteration
+    counts as the oracle."""
+    npairs, cap = 32, 400
+    r = np.random.default_rng(step)
+    counts = r.integers(60, cap + 1, npairs).astype(np.int32)
+    p1 = np.zeros((npairs, cap, 2), np.float32)
+    p2 = np.zeros((npairs, cap, 2), np.float32)
+    for i in range(npairs):
+        a, b = syn.two_view_matches(9100 + i, int(counts[i]), float(r.uniform(0.3, 0.9)), 0.3, (640, 480))
+        p1[i, :counts[i]], p2[i, :counts[i]] = np.round(a / step) * step, np.round(b / step) * step
+    thr = max(3.0, step / 2)
+    status, F, ninl = fm.find_batch(p1, p2, counts, thr, 0.95)
+    info = fm.last_info(npairs)
+    for i in range(npairs):
+        n = int(counts[i])
+        _, mo, iters = oracle.fm_ransac(p1[i, :n], p2[i, :n], thr, 0.95)
+        assert info[i, 1] == iters and np.array_equal(status[i, :n], mo), (i, int(info[i, 1]), iters)

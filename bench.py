@@ -503,6 +503,8 @@ def run_ours(args, rank, world, local_rank):
         fundamental = {"value": world * fpairs / (fm_ms * 1e-3), "unit": "pairs/s", "ms_per_step": fm_ms,
                        "workload": "%d pairs per GPU and step (%d frames x 5 predecessors) x %d matches, 70 %% inliers, 0.5 px noise; "
                                    "findFundamentalMat(FM_RANSAC, 3, 0.85) status + FM_8POINT on the inliers" % (fpairs, B, fn),
+                       "l2": "the correspondences of a step (%.1f MB) are L2-resident between launches; the kernel keeps them in shared memory and "
+                             "is bound by per-pair latency, not by memory (profiles/r1g_fmat.txt: 7.6 MB of DRAM traffic per launch)" % ((p1.nbytes + p2.nbytes) / 1e6),
                        "ransac_iterations_mean": float(finfo[:, 1].mean()), "candidates_scored_mean": float(finfo[:, 2].mean()),
                        "inliers_mean": float(finfo[:, 0].mean()),
                        "e2e": {"value": world * fpairs / (fm_host_ms * 1e-3), "unit": "pairs/s", "ms_per_step": fm_host_ms,

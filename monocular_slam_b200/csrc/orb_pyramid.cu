@@ -63,7 +63,7 @@ k_pyr_down(uint8_t* __restrict__ slots, size_t slot_stride, size_t src_off, int 
     // before anything is consumed (item after item would serialise two dependent global-load latencies per item).
     {
         constexpr int ITEMS = (PD_TH * (PITCH / 16) + PD_THREADS - 1) / PD_THREADS;
-        const uint32_t rcp = (65536u + nvec - 1) / nvec;           // item / nvec == (item * rcp) >> 16 for item < 64 * 36
+        const uint32_t rcp = (65536u + nvec - 1) / nvec;           // item / nvec == (item * rcp) >> 16 for item < 64 * nvec, nvec <= 36 (checked exhaustively)
         const int nitems = rows * nvec;
         int sidx[ITEMS];                                           // smem index of the item's first entry, -1: no item
         uint32_t w1[ITEMS];

@@ -69,7 +69,7 @@ struct FmShared {
     int count[FM_MAXCHUNK][3];
     int rot_p[4], rot_q[4];
     int cmax[4];                      // largest |x1| |y1| |x2| |y2| of the pair (float bits; non-negative floats order like ints)
-    int iter, niters, maxgood, chunk, stop, have, next, first_bad, run_max, iter_limit;
+    int iter, niters, maxgood, chunk, chunk_redo, stop, have, next, first_bad, run_max, iter_limit;
     int min_median;                   // LMedS: float bits of the smallest median so far (+inf bits: none)
     float lmeds_t2;                   // LMedS: squared inlier threshold derived from it
 };
@@ -644,18 +644,21 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
             if (have_collinear(a) || have_collinear(b)) atomicMin(&sh.first_bad, tid);
         }
         __syncthreads();
-        if (sh.first_bad < sh.chunk) {
+        // (thread 0 publishes the redone round's length in a separate word: the other threads may still be reading sh.chunk and
+        // sh.first_bad for the branch below while it is already working)
+        const int drawn = sh.chunk, first_bad = sh.first_bad;
+        if (first_bad < drawn) {
             if (tid == 0) {
-                int chunk = sh.chunk;
-                unsigned long long rng = sh.rng_at[sh.first_bad];
-                for (int i = sh.first_bad; i < chunk; i++)
+                int chunk = drawn;
+                unsigned long long rng = sh.rng_at[first_bad];
+                for (int i = first_bad; i < chunk; i++)
                     if (!get_subset(P1, P2, n, rng, sh.idx[i], lmeds ? 1000 : 10000)) { chunk = i; sh.stop = 1; break; }     // OpenCV leaves its loop here
                 sh.rng = rng;
-                sh.chunk = chunk;
+                sh.chunk_redo = chunk;
             }
             __syncthreads();
         }
-        const int chunk = sh.chunk;
+        const int chunk = first_bad < drawn ? sh.chunk_redo : drawn;
         FM_TICK(1);
         if (chunk == 0) break;
         const int iter0 = sh.iter, niters0 = sh.niters;

@@ -128,9 +128,11 @@ ORBX_API int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, size
 ORBX_API int orbx_check_dev(orbx_handle h);
 
 /* Sequence mode on host buffers: match every frame of the batch last extracted with orbx_extract_batch against its
- * predecessor (frame 0 against the last frame of the previous batch; orbx_reset_sequence forgets it) without moving
- * the descriptors back to the device.  good is [nframes][cap] with the cap of that extract call, ngood [nframes]. */
-ORBX_API int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, orbx_dmatch* good, int64_t* ngood);
+ * predecessor (frame 0 against the last frame of the previous batch; orbx_reset_sequence forgets it, and so does a batch
+ * extracted with another cap) without moving the descriptors back to the device.  The caller states the geometry of its
+ * buffers: good is [nframes][cap], ngood [nframes]; nframes must be the size of that batch and cap at least
+ * min(its cap, orbx_max_keypoints()), otherwise ORBX_E_INVALID (nothing is written). */
+ORBX_API int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, int nframes, int cap, orbx_dmatch* good, int64_t* ngood);
 ORBX_API int orbx_reset_sequence(orbx_handle h);
 
 /* Pipelined sequence mode on host buffers: up to orbx_pipeline_depth() (3) batches in flight.  orbx_submit_batch enqueues, without
@@ -163,8 +165,16 @@ ORBX_API int orbx_debug_fast_level(orbx_handle h, const uint8_t* gray, int w, in
 
 ORBX_API int hamx_create(hamx_handle* out, int device);
 ORBX_API int hamx_destroy(hamx_handle h);
+/* The matcher's kernels run on this cudaStream_t (NULL: the handle's own).  A handle's workspaces are shared by all its
+ * calls, so one handle must not be used on two streams concurrently.  The orbx_* sequence entry points that take a matcher
+ * run it on the extractor's stream for the duration of the call and put the stream installed here back afterwards. */
 ORBX_API int hamx_set_stream(hamx_handle h, void* cuda_stream);
+ORBX_API int hamx_get_stream(hamx_handle h, void** cuda_stream);
 ORBX_API int hamx_synchronize(hamx_handle h);
+/* Workspaces grow on demand, and growing frees and allocates device memory, which synchronises the whole device.
+ * hamx_reserve sizes them once for every later call with at most nq queries, nt train rows and npairs batched pairs, so
+ * that the _dev entry points stay asynchronous. */
+ORBX_API int hamx_reserve(hamx_handle h, int64_t nq, int64_t nt, int npairs);
 
 /* BFMatcher(NORM_HAMMING,false).knnMatch(q, t, out, 2): q is nq x 32 bytes, t is nt x 32 bytes.
  * out holds nq*2 entries; out_counts[i] = min(nt, 2) entries of row i are valid, sorted by (distance, trainIdx). */
@@ -206,10 +216,10 @@ ORBX_API int hamx_match_back_dev(hamx_handle h, const uint8_t* d_desc, const int
                         orbx_dmatch* d_good, int64_t* d_ngood);
 ORBX_API int hamx_update_history_dev(hamx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int back,
                             const uint8_t* d_old_desc, const int32_t* d_old_counts, int nold, uint8_t* d_new_desc, int32_t* d_new_counts);
-/* Host-buffer form for the batch last extracted with orbx_extract_batch: good is [nframes][back][cap] with the cap of
- * that extract call, ngood [nframes][back]; the handle keeps the history across batches (orbx_reset_sequence forgets it).
- * back <= 8. */
-ORBX_API int orbx_match_back(orbx_handle h, hamx_handle m, int back, float ratio, orbx_dmatch* good, int64_t* ngood);
+/* Host-buffer form for the batch last extracted with orbx_extract_batch: good is [nframes][back][cap], ngood
+ * [nframes][back] (nframes / cap: the caller's buffer geometry, checked like orbx_match_consecutive's); the handle keeps
+ * the history across batches (orbx_reset_sequence forgets it).  back <= 8. */
+ORBX_API int orbx_match_back(orbx_handle h, hamx_handle m, int back, float ratio, int nframes, int cap, orbx_dmatch* good, int64_t* ngood);
 
 /* Train-sharded matching over peer memory (BASELINE configs 4 and 5; one process per GPU of one NVLink box).  The
  * reference has no counterpart (it is single-device); the result is bit-identical to hamx_knn2_dev over the union of
@@ -250,7 +260,8 @@ ORBX_API int hamx_popc_peak(int device, double* gpopc_per_s, double* elapsed_ms)
 typedef struct fmx_context* fmx_handle;
 ORBX_API int fmx_create(fmx_handle* out, int device);
 ORBX_API int fmx_destroy(fmx_handle h);
-ORBX_API int fmx_set_stream(fmx_handle h, void* cuda_stream);
+ORBX_API int fmx_set_stream(fmx_handle h, void* cuda_stream);     /* same rules as hamx_set_stream */
+ORBX_API int fmx_get_stream(fmx_handle h, void** cuda_stream);
 ORBX_API int fmx_synchronize(fmx_handle h);
 /* The reference's own signature for one pair: keypoints of both frames and the DMatch list (queryIdx -> kps1, trainIdx -> kps2).
  * status gets nm bytes (0/1), F 9 doubles, *ninliers the number of set status bytes. */
@@ -280,13 +291,14 @@ ORBX_API int fmx_filter_back_dev(fmx_handle h, const orbx_keypoint* d_kps, int n
                         int nhist, const orbx_dmatch* d_good, const int64_t* d_ngood, double max_distance, double confidence,
                         uint8_t* d_status, double* d_F, int32_t* d_info);
 /* Host-buffer form for the batch last passed to orbx_extract_batch + orbx_match_consecutive on `h`: status [nframes][cap]
- * (cap of that extract call), F [nframes][9], ninliers [nframes].  The matches never leave the device in between. */
-ORBX_API int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence,
+ * (the caller's buffer geometry, checked like orbx_match_consecutive's), F [nframes][9], ninliers [nframes].  The matches
+ * never leave the device in between. */
+ORBX_API int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence, int nframes, int cap,
                             uint8_t* status, double* F, int32_t* ninliers);
 /* The filter for the pairs orbx_match_back just matched: status [nframes][back][cap], F [nframes][back][9], ninliers [nframes][back]
  * (computeFundamentalMatrix as called in the loop at src/CameraPoseEstimator.cpp:405-419). */
-ORBX_API int orbx_filter_back(orbx_handle h, fmx_handle fm, double max_distance, double confidence, uint8_t* status, double* F,
-                     int32_t* ninliers);
+ORBX_API int orbx_filter_back(orbx_handle h, fmx_handle fm, double max_distance, double confidence, int nframes, int back, int cap,
+                     uint8_t* status, double* F, int32_t* ninliers);
 /* orbx_submit_batch with the outlier filter appended to the batch's device work (fm may be NULL: plain orbx_submit_batch):
  * status [nframes][cap] and F [nframes][9] are written before the matching orbx_wait_batch returns, ninliers [nframes] by it. */
 ORBX_API int orbx_submit_batch_filtered(orbx_handle h, hamx_handle m, fmx_handle fm, const uint8_t* const* frames, int nframes, int w, int h_,

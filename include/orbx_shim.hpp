@@ -222,11 +222,18 @@ private:
     hamx_handle h_;
 };
 
-// The reference's routine, line for line in behaviour (src/CameraPoseEstimator.cpp:200-213).  It constructs a matcher
-// per call like the reference does; hold a BFMatcher and call matchRatio() to avoid that.
+// The reference's routine, line for line in behaviour (src/CameraPoseEstimator.cpp:200-213).  The reference constructs a
+// BFMatcher per call, which costs nothing on the CPU; here a matcher owns a CUDA stream and device workspaces, and the
+// reference calls matchFeatures 5 times per frame (:405-409), so one matcher per host thread is created on first use and
+// kept (the reference's pipeline is single-threaded, src/main.cpp:49-51).
+static inline BFMatcher& threadMatcher()
+{
+    static thread_local BFMatcher matcher(NORM_HAMMING, false);
+    return matcher;
+}
 static inline void matchFeatures(const Mat& descriptors1, const Mat& descriptors2, std::vector<DMatch>& matches, float ratio = 0.8f)
 {
-    BFMatcher matcher(NORM_HAMMING, false);
+    BFMatcher& matcher = threadMatcher();
     std::vector<std::vector<DMatch> > raw_matches;
     matcher.knnMatch(descriptors1, descriptors2, raw_matches, 2);
     matches.clear();
@@ -282,7 +289,7 @@ static inline void computeFundamentalMatrix(const std::vector<Point2d>& position
                                             const std::vector<DMatch>& matches, std::vector<Point2d>& inlierPositions1,
                                             std::vector<Point2d>& inlierPositions2, double F[9], std::vector<unsigned char>& status)
 {
-    FundamentalFilter f;
+    static thread_local FundamentalFilter f;     // one per host thread, kept: see threadMatcher()
     f.compute(positions1, positions2, matches, inlierPositions1, inlierPositions2, F, status);
 }
 #ifdef ORBX_SHIM_USE_OPENCV

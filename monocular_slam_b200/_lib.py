@@ -31,6 +31,7 @@ SYMBOLS = [
     "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev", "orbx_set_input_channels", "orbx_pipeline_depth", "hamx_match_back_dev", "hamx_update_history_dev", "orbx_match_back", "orbx_host_alloc", "orbx_host_free",
     "fmx_create", "fmx_destroy", "fmx_set_stream", "fmx_synchronize", "fmx_compute_fundamental", "fmx_fundamental_batch",
     "fmx_last_info", "fmx_fundamental_batch_dev", "fmx_filter_consecutive_dev", "orbx_filter_consecutive", "orbx_submit_batch_filtered", "fmx_filter_back_dev", "orbx_filter_back", "orbx_submit_batch_back",
+    "hamx_get_stream", "fmx_get_stream", "hamx_reserve",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -101,6 +102,9 @@ def lib():
     L.hamx_create.argtypes = [C.POINTER(vp), C.c_int]
     L.hamx_destroy.argtypes = [vp]
     L.hamx_set_stream.argtypes = [vp, vp]
+    L.hamx_reserve.argtypes = [vp, C.c_int64, C.c_int64, C.c_int]
+    L.hamx_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.fmx_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.hamx_synchronize.argtypes = [vp]
     L.hamx_knn2.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, i32p]
     L.hamx_match_ratio.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_float, vp, i64p]
@@ -110,7 +114,7 @@ def lib():
     L.hamx_popc_peak.argtypes = [C.c_int, dp, dp]
     L.hamx_match_pairs_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_size_t, vp]
     L.hamx_match_consecutive_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_float, vp, vp]
-    L.orbx_match_consecutive.argtypes = [vp, vp, C.c_float, vp, i64p]
+    L.orbx_match_consecutive.argtypes = [vp, vp, C.c_float, C.c_int, C.c_int, vp, i64p]
     L.orbx_reset_sequence.argtypes = [vp]
     L.orbx_submit_batch.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_float, vp, vp, C.c_int, vp, vp, vp]
     L.orbx_wait_batch.argtypes = [vp]
@@ -121,7 +125,7 @@ def lib():
     L.orbx_host_free.argtypes = [vp]
     L.hamx_match_back_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_float, vp, vp]
     L.hamx_update_history_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
-    L.orbx_match_back.argtypes = [vp, vp, C.c_int, C.c_float, vp, i64p]
+    L.orbx_match_back.argtypes = [vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp, i64p]
     L.hamx_p2p_export.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.hamx_p2p_import.argtypes = [vp, vp]
     L.hamx_p2p_import_ptrs.argtypes = [vp, C.POINTER(vp)]
@@ -138,8 +142,8 @@ def lib():
     L.fmx_last_info.argtypes = [vp, C.c_int, vp]
     L.fmx_fundamental_batch_dev.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp]
     L.fmx_filter_consecutive_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double, vp, vp, vp]
-    L.orbx_filter_consecutive.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp, vp]
-    L.orbx_filter_back.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp, vp]
+    L.orbx_filter_consecutive.argtypes = [vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp]
+    L.orbx_filter_back.argtypes = [vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.orbx_submit_batch_back.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_float, vp, vp, C.c_int, vp,
                                          vp, vp, C.c_double, C.c_double, vp, vp, vp]
     L.fmx_filter_back_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_double, vp, vp, vp]

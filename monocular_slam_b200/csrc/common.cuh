@@ -23,6 +23,17 @@ void set_error(const char* fmt, ...);
         }                                                                                        \
     } while (0)
 
+// The same for constructors: `cleanup` (e.g. orbx_destroy(h)) releases what has been allocated so far.
+#define ORBX_CUDA_OR(call, cleanup)                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            orbx::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            cleanup;                                                                             \
+            return ORBX_E_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
 #define ORBX_REQUIRE(cond, ...)            \
     do {                                   \
         if (!(cond)) {                     \

@@ -1040,14 +1040,14 @@ extern "C" int fmx_create(fmx_handle* out, int device)
     fmx_context* h = new fmx_context();
     memset(h, 0, sizeof(*h));
     h->device = device;
-    ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), fmx_destroy(h));
     h->stream = h->own_stream;
     int optin = 0;
-    ORBX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    ORBX_CUDA_OR(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), fmx_destroy(h));
     h->smem_optin = (size_t)optin;
-    ORBX_CUDA(cudaFuncSetAttribute(k_fm_ransac<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    ORBX_CUDA(cudaFuncSetAttribute(k_fm_ransac<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    ORBX_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_fm_ransac<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin), fmx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_fm_ransac<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin), fmx_destroy(h));
+    ORBX_CUDA_OR(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), fmx_destroy(h));
     *out = h;
     return ORBX_OK;
 }
@@ -1056,11 +1056,11 @@ extern "C" int fmx_destroy(fmx_handle h)
 {
     if (!h) return ORBX_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_counts); cudaFree(h->d_status); cudaFree(h->d_F); cudaFree(h->d_info);
     if (h->h_info) cudaFreeHost(h->h_info);
     if (h->h_pts) cudaFreeHost(h->h_pts);
-    cudaStreamDestroy(h->own_stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ORBX_OK;
 }
@@ -1069,6 +1069,13 @@ extern "C" int fmx_set_stream(fmx_handle h, void* cuda_stream)
 {
     ORBX_REQUIRE(h != nullptr, "fmx_set_stream: NULL handle");
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ORBX_OK;
+}
+
+extern "C" int fmx_get_stream(fmx_handle h, void** cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr && cuda_stream != nullptr, "fmx_get_stream: NULL argument");
+    *cuda_stream = (void*)h->stream;
     return ORBX_OK;
 }
 

@@ -594,10 +594,10 @@ extern "C" int hamx_create(hamx_handle* out, int device)
     hamx_context* h = new hamx_context();
     memset(h, 0, sizeof(*h));
     h->device = device;
-    ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), hamx_destroy(h));
     h->stream = h->own_stream;
-    ORBX_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
-    ORBX_CUDA(cudaMalloc((void**)&h->d_ngood, sizeof(long long)));
+    ORBX_CUDA_OR(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), hamx_destroy(h));
+    ORBX_CUDA_OR(cudaMalloc((void**)&h->d_ngood, sizeof(long long)), hamx_destroy(h));
     *out = h;
     return ORBX_OK;
 }
@@ -606,12 +606,12 @@ extern "C" int hamx_destroy(hamx_handle h)
 {
     if (!h) return ORBX_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_partial); cudaFree(h->d_arrivals); cudaFree(h->d_top2);
     cudaFree(h->d_parts); cudaFree(h->d_dm); cudaFree(h->d_counts); cudaFree(h->d_ngood); cudaFree(h->d_pairs);
     hamx_p2p_close(h);
     cudaFree(h->d_p2p_local);
-    cudaStreamDestroy(h->own_stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ORBX_OK;
 }
@@ -620,6 +620,13 @@ extern "C" int hamx_set_stream(hamx_handle h, void* cuda_stream)
 {
     ORBX_REQUIRE(h != nullptr, "hamx_set_stream: NULL handle");
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ORBX_OK;
+}
+
+extern "C" int hamx_get_stream(hamx_handle h, void** cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr && cuda_stream != nullptr, "hamx_get_stream: NULL argument");
+    *cuda_stream = (void*)h->stream;
     return ORBX_OK;
 }
 
@@ -638,11 +645,12 @@ static int fill_absent(hamx_handle h, hamx_top2* d_out, int64_t nq)
     return ORBX_OK;
 }
 
+// CTAs wanted per SM before the train range stops being split (measured on B200, 2000 x 2000 pairs and 2000 x 200 k: 24)
+constexpr int HT_SPLIT_MULT = 24;
+
 static void plan_split(int sm_count, int64_t nqb, int ntiles, int64_t npairs, int* nsplit_out, int* tps_out)
 {
-    static int mult = 0;
-    if (mult == 0) { const char* e = getenv("HAMX_SPLIT_MULT"); mult = e ? atoi(e) : 24; if (mult < 1) mult = 24; }
-    const int64_t target = (int64_t)sm_count * mult;
+    const int64_t target = (int64_t)sm_count * HT_SPLIT_MULT;
     int64_t nsplit = nqb * npairs >= target ? 1 : (target + nqb * npairs - 1) / (nqb * npairs);
     if (nsplit > ntiles) nsplit = ntiles;
     if (nsplit > 65535) nsplit = 65535;
@@ -678,6 +686,29 @@ static int launch_chunk(hamx_handle h, const uint8_t* d_q, int64_t nq, const uin
         k_hamming_knn2<false><<<grid, HT_THREADS, 0, h->stream>>>(one, nullptr, tps, h->d_partial, (size_t)nq, h->d_arrivals, (int)nqb,
                                                                    d_out, 0, offset, kNoP2P);
     ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// Pre-size every workspace the _dev entry points can need for problems of up to nq queries, nt train rows and npairs
+// batched pairs, so that none of them allocates (cudaFree / cudaMalloc synchronise the whole device) once a pipeline runs.
+extern "C" int hamx_reserve(hamx_handle h, int64_t nq, int64_t nt, int npairs)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_reserve: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nq < (1ll << 31) && nt >= 0 && npairs >= 0, "hamx_reserve: bad sizes");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int64_t np = std::max(npairs, 1);
+    const int64_t nqb = (nq + HT_QB - 1) / HT_QB;
+    // plan_split: nsplit <= target / (nqb * np) + 1, hence np * nsplit * nq <= target * HT_QB + np * nq for every smaller problem too
+    const size_t partial = ((size_t)h->sm_count * HT_SPLIT_MULT * HT_QB + (size_t)np * (size_t)nq) * sizeof(uint2);
+    int rc = grow(&h->d_partial, &h->partial_bytes, partial);
+    if (!rc) rc = grow(&h->d_arrivals, &h->arrivals_n, (size_t)np * std::max<int64_t>(nqb, 1) * sizeof(unsigned int), true, h->stream);
+    if (!rc) rc = grow(&h->d_top2, &h->top2_bytes, (size_t)np * nq * sizeof(hamx_top2) + 16);
+    if (!rc) rc = grow(&h->d_pairs, &h->pairs_bytes, (size_t)np * sizeof(hamx_pair));
+    const int64_t chunk = 1ll << HT_IDX_BITS;
+    if (!rc && nt > chunk) rc = grow(&h->d_parts, &h->parts_bytes, (size_t)((nt + chunk - 1) / chunk) * nq * sizeof(hamx_top2));
+    if (!rc && h->p2p_buf) rc = grow(&h->d_p2p_local, &h->p2p_local_bytes, (size_t)nq * sizeof(hamx_top2));
+    if (rc) return rc;
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
     return ORBX_OK;
 }
 
@@ -896,10 +927,10 @@ extern "C" int hamx_p2p_export(hamx_handle h, int64_t nq_max, int world, int ran
     h->p2p_bytes = p2p_flag_bytes(world) + (size_t)2 * world * (size_t)nq_max * sizeof(hamx_top2);
     cudaError_t e = cudaMalloc(&h->p2p_buf, h->p2p_bytes);
     if (e != cudaSuccess) { h->p2p_buf = nullptr; set_error("hamx_p2p_export: cudaMalloc(%zu) failed: %s", h->p2p_bytes, cudaGetErrorString(e)); return ORBX_E_ALLOC; }
-    ORBX_CUDA(cudaMemset(h->p2p_buf, 0, p2p_flag_bytes(world)));     // epoch 0 = nothing published
-    ORBX_CUDA(cudaMalloc((void**)&h->pv.done, 256));
-    ORBX_CUDA(cudaMemset(h->pv.done, 0, 256));
-    ORBX_CUDA(cudaDeviceSynchronize());
+    ORBX_CUDA_OR(cudaMemset(h->p2p_buf, 0, p2p_flag_bytes(world)), hamx_p2p_close(h));     // epoch 0 = nothing published
+    ORBX_CUDA_OR(cudaMalloc((void**)&h->pv.done, 256), hamx_p2p_close(h));
+    ORBX_CUDA_OR(cudaMemset(h->pv.done, 0, 256), hamx_p2p_close(h));
+    ORBX_CUDA_OR(cudaDeviceSynchronize(), hamx_p2p_close(h));
     p2p_set_view(h, rank, h->p2p_buf);
     if (ipc_handle) {
         cudaIpcMemHandle_t ih;
@@ -943,7 +974,7 @@ extern "C" int hamx_p2p_close(hamx_handle h)
 {
     if (!h) return ORBX_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     for (int r = 0; r < HT_MAX_WORLD; r++)
         if (h->p2p_opened[r]) { cudaIpcCloseMemHandle(h->p2p_opened[r]); h->p2p_opened[r] = nullptr; }
     if (h->pv.done) cudaFree(h->pv.done);

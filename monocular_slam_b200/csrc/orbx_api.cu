@@ -87,12 +87,13 @@ struct orbx_context {
     FrameCounters* h_ctr;
     int32_t* h_counts;
     std::vector<uint8_t>* h_tab;
-    bool dev_pending;   // a _dev submission has not been checked for overflow yet
+    int dev_pending;    // > 0: _dev submissions of up to this many frames have not been checked for overflow yet
     // sequence mode (orbx_match_consecutive)
     int last_nframes, last_cap;
     uint8_t* d_prev_desc;
     int32_t* d_prev_count;
     bool have_prev;
+    int prev_cap;                             // row capacity the kept previous frame was extracted with
     orbx_dmatch* d_good;
     int64_t* d_ngood;
     int64_t* h_ngood;
@@ -137,6 +138,20 @@ struct orbx_context {
 
 static inline int rne_f(float v) { return (int)lrintf(v); }
 static int require_idle(orbx_handle h, const char* fn);
+
+// The sequence entry points run the caller's matcher / filter on the extractor's stream (ordered after the extraction,
+// no extra synchronisation) for the duration of one call; the stream the caller installed on that handle is put back
+// when the scope ends, so later hamx_*_dev / fmx_*_dev calls stay ordered on the caller's stream.
+struct ScopedHamxStream {
+    hamx_handle m; void* saved; int rc;
+    ScopedHamxStream(hamx_handle m_, cudaStream_t s) : m(m_), saved(nullptr), rc(hamx_get_stream(m_, &saved)) { if (!rc) rc = hamx_set_stream(m, (void*)s); }
+    ~ScopedHamxStream() { if (m) hamx_set_stream(m, saved); }
+};
+struct ScopedFmxStream {
+    fmx_handle m; void* saved; int rc;
+    ScopedFmxStream(fmx_handle m_, cudaStream_t s) : m(m_), saved(nullptr), rc(fmx_get_stream(m_, &saved)) { if (!rc) rc = fmx_set_stream(m, (void*)s); }
+    ~ScopedFmxStream() { if (m) fmx_set_stream(m, saved); }
+};
 
 // Level sizes, quotas, list capacities and buffer offsets for a w x h frame.
 static int build_geometry(const orbx_params& p, int w, int h, FrameGeom* g)
@@ -361,9 +376,9 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     h->tab_bytes = table_bytes(h->gmax) + 4096;
     h->h_tab = new std::vector<uint8_t>(h->tab_bytes);
 
-    ORBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    ORBX_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    ORBX_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), orbx_destroy(h));
+    ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), orbx_destroy(h));
+    ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking), orbx_destroy(h));
     {
         const char* e = getenv("ORBX_SPLIT");
         h->split = e ? atoi(e) : 1;
@@ -372,18 +387,18 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
         e = getenv("ORBX_GRAPHS");
         h->use_graphs = !(e && e[0] == '0');
         for (int i = 0; i < ORBX_MAX_SPLIT; i++) {
-            ORBX_CUDA(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));
-            ORBX_CUDA(cudaEventCreateWithFlags(&h->join_event[i], cudaEventDisableTiming));
+            ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking), orbx_destroy(h));
+            ORBX_CUDA_OR(cudaEventCreateWithFlags(&h->join_event[i], cudaEventDisableTiming), orbx_destroy(h));
         }
-        ORBX_CUDA(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+        ORBX_CUDA_OR(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming), orbx_destroy(h));
     }
     for (int l = 0; l < ORBX_LANES; l++) {
-        ORBX_CUDA(cudaEventCreateWithFlags(&h->lanes[l].uploaded, cudaEventDisableTiming));
-        ORBX_CUDA(cudaEventCreateWithFlags(&h->lanes[l].computed, cudaEventDisableTiming));
-        ORBX_CUDA(cudaEventCreateWithFlags(&h->lanes[l].done, cudaEventDisableTiming));
+        ORBX_CUDA_OR(cudaEventCreateWithFlags(&h->lanes[l].uploaded, cudaEventDisableTiming), orbx_destroy(h));
+        ORBX_CUDA_OR(cudaEventCreateWithFlags(&h->lanes[l].computed, cudaEventDisableTiming), orbx_destroy(h));
+        ORBX_CUDA_OR(cudaEventCreateWithFlags(&h->lanes[l].done, cudaEventDisableTiming), orbx_destroy(h));
     }
     h->copy_events = new std::vector<cudaEvent_t>();
-    ORBX_CUDA(cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming));
+    ORBX_CUDA_OR(cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming), orbx_destroy(h));
     h->stream = h->own_stream;
     const size_t B = (size_t)max_batch * ORBX_LANES;   // blocking calls use lane 0 only
 #define ORBX_ALLOC(ptr, bytes)                                                                            \
@@ -409,12 +424,12 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     ORBX_ALLOC(h->d_good, B * (size_t)h->dev_cap * sizeof(orbx_dmatch) + 256);
     ORBX_ALLOC(h->d_ngood, B * sizeof(int64_t) + 256);
 #undef ORBX_ALLOC
-    ORBX_CUDA(cudaMallocHost((void**)&h->h_ngood, B * sizeof(int64_t)));
+    ORBX_CUDA_OR(cudaMallocHost((void**)&h->h_ngood, B * sizeof(int64_t)), orbx_destroy(h));
     h->events = new std::vector<cudaEvent_t>();
-    ORBX_CUDA(cudaMemset(h->d_slots, 0, B * h->slot_stride));   // padding bytes are read (never used) by vector loads
-    ORBX_CUDA(cudaMallocHost((void**)&h->h_ctr, B * sizeof(FrameCounters)));
-    ORBX_CUDA(cudaMallocHost((void**)&h->h_counts, B * sizeof(int32_t)));
-    ORBX_CUDA(harris_select_prepare(h->max_surv_cap));
+    ORBX_CUDA_OR(cudaMemset(h->d_slots, 0, B * h->slot_stride), orbx_destroy(h));   // padding bytes are read (never used) by vector loads
+    ORBX_CUDA_OR(cudaMallocHost((void**)&h->h_ctr, B * sizeof(FrameCounters)), orbx_destroy(h));
+    ORBX_CUDA_OR(cudaMallocHost((void**)&h->h_counts, B * sizeof(int32_t)), orbx_destroy(h));
+    ORBX_CUDA_OR(harris_select_prepare(h->max_surv_cap), orbx_destroy(h));
     *out = h;
     return ORBX_OK;
 }
@@ -565,9 +580,10 @@ static int stage_mark(orbx_handle h)
     return ORBX_OK;
 }
 
-// frames [f0, f0 + nframes) of the handle's slots on stream s; d_out / d_desc / d_counts are the arrays of the WHOLE batch
+// frames [f0, f0 + nframes) of the handle's slots on stream s; their results go to rows [o0, o0 + nframes) of d_out
+// ([.][cap]) / d_desc ([.][cap][32]) / d_counts
 static int run_extract_on(orbx_handle h, int f0, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts,
-                          cudaStream_t s, bool mark)
+                          cudaStream_t s, bool mark, int o0)
 {
     uint8_t* slots = h->d_slots + (size_t)f0 * h->slot_stride;
     Cand* cand = h->d_cand + (size_t)f0 * h->cand_stride;
@@ -587,8 +603,8 @@ static int run_extract_on(orbx_handle h, int f0, int nframes, int mode, orbx_key
     ORBX_CUDA(launch_harris_select(h->g, slots, h->slot_stride, surv, h->surv_stride, sel, h->sel_stride, ctr, nframes,
                                    h->max_surv_cap, h->harris_s4, s));
     if (mark && (rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_orient_describe(h->g, slots, h->slot_stride, sel, h->sel_stride, ctr, d_out + (size_t)f0 * cap,
-                                     (mode & ORBX_DO_DESC) ? d_desc + (size_t)f0 * cap * 32 : nullptr, cap, d_counts + f0, nframes,
+    ORBX_CUDA(launch_orient_describe(h->g, slots, h->slot_stride, sel, h->sel_stride, ctr, d_out + (size_t)o0 * cap,
+                                     (mode & ORBX_DO_DESC) ? d_desc + (size_t)o0 * cap * 32 : nullptr, cap, d_counts + o0, nframes,
                                      mode, s));
     if (mark && (rc = stage_mark(h))) return rc;
     return ORBX_OK;
@@ -599,17 +615,17 @@ static int run_extract_on(orbx_handle h, int f0, int nframes, int mode, orbx_key
 // events), so that the short, latency-bound launches of one part overlap the bulk kernels of another.  That paid 3 % while
 // the Harris selection and the score cut were slow; with the current kernels one stream is fastest (measured: 24.6 k
 // frames/s unsplit vs 24.1-24.5 k with 2-8 parts), so the default is 1 = off.  Stage profiling always keeps one stream.
-static int run_extract(orbx_handle h, int f0, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts)
+static int run_extract(orbx_handle h, int f0, int nframes, int mode, orbx_keypoint* d_out, uint8_t* d_desc, int cap, int32_t* d_counts, int o0)
 {
     int parts = std::min(h->split, nframes / ORBX_SPLIT_MIN);
     if (h->profiling || parts < 2)
-        return run_extract_on(h, f0, nframes, mode, d_out, d_desc, cap, d_counts, h->stream, h->profiling);
+        return run_extract_on(h, f0, nframes, mode, d_out, d_desc, cap, d_counts, h->stream, h->profiling, o0);
     ORBX_CUDA(cudaEventRecord(h->fork_event, h->stream));
     int b = 0;
     for (int i = 0; i < parts; i++) {
         const int n = (nframes - b) / (parts - i);
         ORBX_CUDA(cudaStreamWaitEvent(h->sub_stream[i], h->fork_event, 0));
-        int rc = run_extract_on(h, f0 + b, n, mode, d_out, d_desc, cap, d_counts, h->sub_stream[i], false);
+        int rc = run_extract_on(h, f0 + b, n, mode, d_out, d_desc, cap, d_counts, h->sub_stream[i], false, o0 + b);
         if (rc) return rc;
         ORBX_CUDA(cudaEventRecord(h->join_event[i], h->sub_stream[i]));
         ORBX_CUDA(cudaStreamWaitEvent(h->stream, h->join_event[i], 0));
@@ -674,7 +690,7 @@ static int common_checks(orbx_handle h, const void* img, int w, int hh, size_t s
 static int run_extract_single(orbx_handle h, int mode, int dcap)
 {
     if (!h->use_graphs || h->profiling)
-        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, h->profiling);
+        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, h->profiling, 0);
     for (int i = 0; i < h->ngraphs; i++)
         if (h->graphs[i].mode == mode && h->graphs[i].cap == dcap) {
             ORBX_CUDA(cudaGraphLaunch(h->graphs[i].exec, h->stream));
@@ -683,13 +699,13 @@ static int run_extract_single(orbx_handle h, int mode, int dcap)
     // capture on the handle's own stream (a caller-provided stream may be the legacy default stream, which cannot capture)
     cudaGraph_t graph = nullptr;
     ORBX_CUDA(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->own_stream, false);
+    int rc = run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->own_stream, false, 0);
     cudaError_t e = cudaStreamEndCapture(h->own_stream, &graph);
     if (rc || e != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
         h->use_graphs = false;      // capture is not possible here: fall back to plain launches for good
-        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, false);
+        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, false, 0);
     }
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, graph, 0);
@@ -697,7 +713,7 @@ static int run_extract_single(orbx_handle h, int mode, int dcap)
     if (e != cudaSuccess) {
         cudaGetLastError();
         h->use_graphs = false;
-        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, false);
+        return run_extract_on(h, 0, 1, mode, h->d_kps, h->d_desc, dcap, h->d_counts, h->stream, false, 0);
     }
     if (h->ngraphs == 4) { cudaGraphExecDestroy(h->graphs[0].exec); h->graphs[0] = h->graphs[3]; h->ngraphs = 3; }
     h->graphs[h->ngraphs].exec = exec;
@@ -755,7 +771,7 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
     for (int c = 0; c < nchunks; c++) {
         const int f0 = c * chunk, n = std::min(chunk, nframes - f0);
         ORBX_CUDA(cudaStreamWaitEvent(h->stream, (*h->copy_events)[c], 0));
-        rc = run_extract(h, f0, n, mode, h->d_kps, h->d_desc, dcap, h->d_counts);
+        rc = run_extract(h, f0, n, mode, h->d_kps, h->d_desc, dcap, h->d_counts, f0);
         if (rc) return rc;
     }
     h->last_nframes = (mode & ORBX_DO_DESC) ? nframes : 0;
@@ -829,9 +845,10 @@ extern "C" int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, si
         ORBX_CUDA(launch_ingest_bgr(d_frames, frame_pitch_bytes, stride, w, hh, h->d_slots, h->slot_stride, h->g.lv[0], nframes, h->stream));
     else
         ORBX_CUDA(launch_ingest(d_frames, frame_pitch_bytes, stride, w, hh, h->d_slots, h->slot_stride, h->g.lv[0], nframes, h->stream));
-    rc = run_extract(h, 0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_out, d_desc, cap, d_counts);
+    rc = run_extract(h, 0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_out, d_desc, cap, d_counts, 0);
     if (rc) return rc;
-    h->dev_pending = true;
+    h->dev_pending = std::max(h->dev_pending, nframes);
+    h->last_nframes = h->filter_nframes = h->back_n = 0;     // the handle's own arrays were not written
     return ORBX_OK;
 }
 
@@ -840,10 +857,12 @@ extern "C" int orbx_check_dev(orbx_handle h)
     ORBX_REQUIRE(h != nullptr, "orbx_check_dev: NULL handle");
     ORBX_CUDA(cudaSetDevice(h->device));
     if (!h->dev_pending) { ORBX_CUDA(cudaStreamSynchronize(h->stream)); return ORBX_OK; }
-    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)h->max_batch * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
+    // only the slots the unchecked submissions used: a flag left in a higher slot by an earlier, larger batch is stale
+    const int n = h->dev_pending;
+    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)n * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
-    h->dev_pending = false;
-    for (int f = 0; f < h->max_batch; f++)
+    h->dev_pending = 0;
+    for (int f = 0; f < n; f++)
         if (h->h_ctr[f].overflow) {
             set_error("orbx_check_dev: frame slot %d overflowed (flags %d, %d keypoints)", f, h->h_ctr[f].overflow, h->h_ctr[f].total);
             return ORBX_E_CAPACITY;
@@ -875,6 +894,7 @@ extern "C" int orbx_compute(orbx_handle h, const uint8_t* gray, int w, int hh, s
     *n = m;
     if (m == 0) return ORBX_OK;
     memcpy(kps, kept.data(), (size_t)m * sizeof(orbx_keypoint));
+    h->last_nframes = h->filter_nframes = h->back_n = 0;    // slot 0 and d_kps / d_desc are overwritten below
     const uint8_t* frames[1] = { gray };
     rc = upload_frames(h, frames, 0, 1, w, hh, stride, cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;
@@ -922,34 +942,55 @@ static int ensure_back_buffers(orbx_handle h)
     return ORBX_OK;
 }
 
-extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, orbx_dmatch* good, int64_t* ngood)
+// D2H of a [rows][dcap] device array into the caller's [rows][cap] array (cap >= dcap), `elem` bytes per entry
+static cudaError_t copy_rows_d2h(void* dst, int cap, const void* src, int dcap, size_t rows, size_t elem, cudaStream_t s)
+{
+    if (cap == dcap) return cudaMemcpyAsync(dst, src, rows * (size_t)cap * elem, cudaMemcpyDeviceToHost, s);
+    return cudaMemcpy2DAsync(dst, (size_t)cap * elem, src, (size_t)dcap * elem, (size_t)dcap * elem, rows, cudaMemcpyDeviceToHost, s);
+}
+
+// the caller states the geometry of its buffers; it must be the batch the handle holds
+static int check_seq_buffers(int nframes, int cap, int have_n, int have_cap, const char* fn)
+{
+    ORBX_REQUIRE(nframes == have_n, "%s: the caller's buffers are for %d frames, the handle's last batch has %d", fn, nframes, have_n);
+    ORBX_REQUIRE(cap >= have_cap, "%s: the caller's rows hold %d entries, the handle's last batch has rows of %d (the cap of that extract call, "
+                 "limited to orbx_max_keypoints())", fn, cap, have_cap);
+    return ORBX_OK;
+}
+
+extern "C" int orbx_match_consecutive(orbx_handle h, hamx_handle m, float ratio, int nframes, int cap, orbx_dmatch* good, int64_t* ngood)
 {
     ORBX_REQUIRE(h != nullptr && m != nullptr, "orbx_match_consecutive: NULL handle");
     ORBX_REQUIRE(good && ngood, "orbx_match_consecutive: NULL pointer");
     ORBX_REQUIRE(h->last_nframes >= 1, "orbx_match_consecutive: no batch with descriptors has been extracted on this handle");
     { int rc_ = require_idle(h, "orbx_match_consecutive"); if (rc_) return rc_; }
+    { int rc_ = check_seq_buffers(nframes, cap, h->last_nframes, h->last_cap, "orbx_match_consecutive"); if (rc_) return rc_; }
     ORBX_CUDA(cudaSetDevice(h->device));
-    const int n = h->last_nframes, cap = h->last_cap;
-    int rc = hamx_set_stream(m, (void*)h->stream);   // same stream as the extraction: ordered after it, no extra sync
-    if (rc) return rc;
-    rc = hamx_match_consecutive_dev(m, h->d_desc, h->d_counts, n, cap, h->have_prev ? h->d_prev_desc : nullptr,
-                                    h->have_prev ? h->d_prev_count : nullptr, ratio, h->d_good, h->d_ngood);
-    hamx_set_stream(m, nullptr);
+    const int n = h->last_nframes, dcap = h->last_cap;
+    if (h->have_prev && h->prev_cap != dcap) h->have_prev = false;     // the kept frame was cut at another capacity
+    int rc;
+    {
+        ScopedHamxStream on(m, h->stream);   // same stream as the extraction: ordered after it, no extra sync
+        if (on.rc) return on.rc;
+        rc = hamx_match_consecutive_dev(m, h->d_desc, h->d_counts, n, dcap, h->have_prev ? h->d_prev_desc : nullptr,
+                                        h->have_prev ? h->d_prev_count : nullptr, ratio, h->d_good, h->d_ngood);
+    }
     if (rc) return rc;
     ORBX_CUDA(cudaMemcpyAsync(h->h_ngood, h->d_ngood, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    ORBX_CUDA(cudaMemcpyAsync(good, h->d_good, (size_t)n * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(copy_rows_d2h(good, cap, h->d_good, dcap, (size_t)n, sizeof(orbx_dmatch), h->stream));
     // keep the last frame's descriptors (and keypoints, for orbx_filter_consecutive) for the next batch
-    ORBX_CUDA(cudaMemcpyAsync(h->d_prev_desc, h->d_desc + (size_t)(n - 1) * cap * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_prev_desc, h->d_desc + (size_t)(n - 1) * dcap * 32, (size_t)dcap * 32, cudaMemcpyDeviceToDevice, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(h->d_prev_count, h->d_counts + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
     { int rc_ = ensure_filter_buffers(h); if (rc_) return rc_; }
     h->filter_prev_kps = h->have_prev ? h->d_prev_kps[h->prev_kps_cur] : nullptr;
     h->prev_kps_cur ^= 1;
-    ORBX_CUDA(cudaMemcpyAsync(h->d_prev_kps[h->prev_kps_cur], h->d_kps + (size_t)(n - 1) * cap, (size_t)cap * sizeof(orbx_keypoint),
+    ORBX_CUDA(cudaMemcpyAsync(h->d_prev_kps[h->prev_kps_cur], h->d_kps + (size_t)(n - 1) * dcap, (size_t)dcap * sizeof(orbx_keypoint),
                               cudaMemcpyDeviceToDevice, h->stream));
     h->filter_nframes = n;
-    h->filter_cap = cap;
+    h->filter_cap = dcap;
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     h->have_prev = true;
+    h->prev_cap = dcap;
     for (int f = 0; f < n; f++) ngood[f] = h->h_ngood[f];
     return ORBX_OK;
 }
@@ -969,24 +1010,26 @@ static int ensure_filter_buffers(orbx_handle h)
     return ORBX_OK;
 }
 
-extern "C" int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence, uint8_t* status, double* F,
-                                       int32_t* ninliers)
+extern "C" int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_distance, double confidence, int nframes, int cap,
+                                       uint8_t* status, double* F, int32_t* ninliers)
 {
     ORBX_REQUIRE(h != nullptr && fm != nullptr, "orbx_filter_consecutive: NULL handle");
     ORBX_REQUIRE(status && F && ninliers, "orbx_filter_consecutive: NULL pointer");
     ORBX_REQUIRE(h->filter_nframes >= 1, "orbx_filter_consecutive: orbx_match_consecutive has not run on this handle's last batch");
     { int rc_ = require_idle(h, "orbx_filter_consecutive"); if (rc_) return rc_; }
+    { int rc_ = check_seq_buffers(nframes, cap, h->filter_nframes, h->filter_cap, "orbx_filter_consecutive"); if (rc_) return rc_; }
     ORBX_CUDA(cudaSetDevice(h->device));
-    const int n = h->filter_nframes, cap = h->filter_cap;
+    const int n = h->filter_nframes, dcap = h->filter_cap;
     int rc = ensure_filter_buffers(h);
     if (rc) return rc;
-    rc = fmx_set_stream(fm, (void*)h->stream);
+    {
+        ScopedFmxStream on(fm, h->stream);
+        if (on.rc) return on.rc;
+        rc = fmx_filter_consecutive_dev(fm, h->d_kps, h->filter_prev_kps, n, dcap, h->d_good, h->d_ngood, max_distance, confidence,
+                                        h->d_fstatus, h->d_fF, h->d_finfo);
+    }
     if (rc) return rc;
-    rc = fmx_filter_consecutive_dev(fm, h->d_kps, h->filter_prev_kps, n, cap, h->d_good, h->d_ngood, max_distance, confidence,
-                                    h->d_fstatus, h->d_fF, h->d_finfo);
-    fmx_set_stream(fm, nullptr);
-    if (rc) return rc;
-    ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus, (size_t)n * cap, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(copy_rows_d2h(status, cap, h->d_fstatus, dcap, (size_t)n, 1, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(h->h_finfo, h->d_finfo, (size_t)n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
@@ -994,24 +1037,28 @@ extern "C" int orbx_filter_consecutive(orbx_handle h, fmx_handle fm, double max_
     return ORBX_OK;
 }
 
-extern "C" int orbx_filter_back(orbx_handle h, fmx_handle fm, double max_distance, double confidence, uint8_t* status, double* F,
-                                int32_t* ninliers)
+extern "C" int orbx_filter_back(orbx_handle h, fmx_handle fm, double max_distance, double confidence, int nframes, int back, int cap,
+                                uint8_t* status, double* F, int32_t* ninliers)
 {
     ORBX_REQUIRE(h != nullptr && fm != nullptr, "orbx_filter_back: NULL handle");
     ORBX_REQUIRE(status && F && ninliers, "orbx_filter_back: NULL pointer");
     ORBX_REQUIRE(h->back_n >= 1, "orbx_filter_back: orbx_match_back has not run on this handle's last batch");
     { int rc_ = require_idle(h, "orbx_filter_back"); if (rc_) return rc_; }
+    { int rc_ = check_seq_buffers(nframes, cap, h->back_n, h->back_cap, "orbx_filter_back"); if (rc_) return rc_; }
+    ORBX_REQUIRE(back == h->back_back, "orbx_filter_back: the caller's buffers are for %d predecessors, orbx_match_back ran with %d", back, h->back_back);
     ORBX_CUDA(cudaSetDevice(h->device));
-    const int n = h->back_n, back = h->back_back, cap = h->back_cap, npairs = n * back;
+    const int n = h->back_n, dcap = h->back_cap, npairs = n * back;
     { int rc_ = ensure_back_buffers(h); if (rc_) return rc_; }
-    int rc = fmx_set_stream(fm, (void*)h->stream);
+    int rc;
+    {
+        ScopedFmxStream on(fm, h->stream);
+        if (on.rc) return on.rc;
+        // orbx_match_back matched against the history that is now the inactive buffer (hist_cur was flipped after the update)
+        rc = fmx_filter_back_dev(fm, h->d_kps, n, dcap, back, h->d_hist_kps[h->hist_cur ^ 1], h->back_nhist, h->d_good_back, h->d_ngood_back,
+                                 max_distance, confidence, h->d_fstatus_back, h->d_fF_back, h->d_finfo_back);
+    }
     if (rc) return rc;
-    // orbx_match_back matched against the history that is now the inactive buffer (hist_cur was flipped after the update)
-    rc = fmx_filter_back_dev(fm, h->d_kps, n, cap, back, h->d_hist_kps[h->hist_cur ^ 1], h->back_nhist, h->d_good_back, h->d_ngood_back,
-                             max_distance, confidence, h->d_fstatus_back, h->d_fF_back, h->d_finfo_back);
-    fmx_set_stream(fm, nullptr);
-    if (rc) return rc;
-    ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus_back, (size_t)npairs * cap, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(copy_rows_d2h(status, cap, h->d_fstatus_back, dcap, (size_t)npairs, 1, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF_back, (size_t)npairs * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(h->h_finfo_back, h->d_finfo_back, (size_t)npairs * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
@@ -1019,39 +1066,42 @@ extern "C" int orbx_filter_back(orbx_handle h, fmx_handle fm, double max_distanc
     return ORBX_OK;
 }
 
-extern "C" int orbx_match_back(orbx_handle h, hamx_handle m, int back, float ratio, orbx_dmatch* good, int64_t* ngood)
+extern "C" int orbx_match_back(orbx_handle h, hamx_handle m, int back, float ratio, int nframes, int cap, orbx_dmatch* good, int64_t* ngood)
 {
     ORBX_REQUIRE(h != nullptr && m != nullptr, "orbx_match_back: NULL handle");
     ORBX_REQUIRE(good && ngood, "orbx_match_back: NULL pointer");
     ORBX_REQUIRE(back >= 1 && back <= ORBX_MAX_BACK, "orbx_match_back: back %d outside [1, %d]", back, ORBX_MAX_BACK);
     ORBX_REQUIRE(h->last_nframes >= 1, "orbx_match_back: no batch with descriptors has been extracted on this handle");
     { int rc_ = require_idle(h, "orbx_match_back"); if (rc_) return rc_; }
+    { int rc_ = check_seq_buffers(nframes, cap, h->last_nframes, h->last_cap, "orbx_match_back"); if (rc_) return rc_; }
     ORBX_CUDA(cudaSetDevice(h->device));
-    const int n = h->last_nframes, cap = h->last_cap;
+    const int n = h->last_nframes, dcap = h->last_cap;
     { int rc_ = ensure_back_buffers(h); if (rc_) return rc_; }
-    if (h->nhist && h->hist_cap != cap) h->nhist = 0;      // a history laid out for another capacity cannot be indexed
-    int rc = hamx_set_stream(m, (void*)h->stream);
-    if (rc) return rc;
+    if (h->nhist && h->hist_cap != dcap) h->nhist = 0;      // a history laid out for another capacity cannot be indexed
     const int cur = h->hist_cur;
-    rc = hamx_match_back_dev(m, h->d_desc, h->d_counts, n, cap, back, h->d_hist[cur], h->d_hist_counts[cur], std::min(h->nhist, back), ratio,
-                             h->d_good_back, h->d_ngood_back);
-    if (!rc) rc = hamx_update_history_dev(m, h->d_desc, h->d_counts, n, cap, ORBX_MAX_BACK, h->d_hist[cur], h->d_hist_counts[cur], h->nhist,
-                                          h->d_hist[cur ^ 1], h->d_hist_counts[cur ^ 1]);
-    hamx_set_stream(m, nullptr);
+    int rc;
+    {
+        ScopedHamxStream on(m, h->stream);
+        if (on.rc) return on.rc;
+        rc = hamx_match_back_dev(m, h->d_desc, h->d_counts, n, dcap, back, h->d_hist[cur], h->d_hist_counts[cur], std::min(h->nhist, back), ratio,
+                                 h->d_good_back, h->d_ngood_back);
+        if (!rc) rc = hamx_update_history_dev(m, h->d_desc, h->d_counts, n, dcap, ORBX_MAX_BACK, h->d_hist[cur], h->d_hist_counts[cur], h->nhist,
+                                              h->d_hist[cur ^ 1], h->d_hist_counts[cur ^ 1]);
+    }
     if (rc) return rc;
     // the keypoint history follows the descriptor history (most recent frame first), for orbx_filter_back
     for (int hi = 0; hi < ORBX_MAX_BACK; hi++) {
         const int src = n - 1 - hi;
-        const orbx_keypoint* from = src >= 0 ? h->d_kps + (size_t)src * cap : (-src - 1 < h->nhist ? h->d_hist_kps[cur] + (size_t)(-src - 1) * cap : nullptr);
+        const orbx_keypoint* from = src >= 0 ? h->d_kps + (size_t)src * dcap : (-src - 1 < h->nhist ? h->d_hist_kps[cur] + (size_t)(-src - 1) * dcap : nullptr);
         if (from)
-            ORBX_CUDA(cudaMemcpyAsync(h->d_hist_kps[cur ^ 1] + (size_t)hi * cap, from, (size_t)cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToDevice, h->stream));
+            ORBX_CUDA(cudaMemcpyAsync(h->d_hist_kps[cur ^ 1] + (size_t)hi * dcap, from, (size_t)dcap * sizeof(orbx_keypoint), cudaMemcpyDeviceToDevice, h->stream));
     }
-    h->back_n = n; h->back_back = back; h->back_cap = cap; h->back_nhist = std::min(h->nhist, back);
+    h->back_n = n; h->back_back = back; h->back_cap = dcap; h->back_nhist = std::min(h->nhist, back);
     h->hist_cur = cur ^ 1;
     h->nhist = std::min(ORBX_MAX_BACK, h->nhist + n);
-    h->hist_cap = cap;
+    h->hist_cap = dcap;
     ORBX_CUDA(cudaMemcpyAsync(h->h_ngood_back, h->d_ngood_back, (size_t)n * back * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    ORBX_CUDA(cudaMemcpyAsync(good, h->d_good_back, (size_t)n * back * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(copy_rows_d2h(good, cap, h->d_good_back, dcap, (size_t)n * back, sizeof(orbx_dmatch), h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < n * back; i++) ngood[i] = h->h_ngood_back[i];
     return ORBX_OK;
@@ -1121,11 +1171,17 @@ static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, co
     if (rc) return rc;
     ORBX_CUDA(cudaEventRecord(L.uploaded, h->copy_stream));
     ORBX_CUDA(cudaStreamWaitEvent(h->stream, L.uploaded, 0));
-    rc = run_extract(h, s0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, h->d_kps, h->d_desc, cap, h->d_counts);
+    // every lane owns max_batch rows of dev_cap entries of the per-frame arrays; the rows of this batch have stride `cap`
+    // inside the lane's region, so batches in flight with different capacities cannot overlap
+    const size_t l0 = (size_t)s0 * h->dev_cap;
+    orbx_keypoint* d_kps = h->d_kps + l0;
+    uint8_t* d_desc = h->d_desc + l0 * 32;
+    orbx_dmatch* d_good = h->d_good + l0;
+    uint8_t* d_fstatus = h->d_fstatus ? h->d_fstatus + l0 : nullptr;
+    rc = run_extract(h, s0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_kps, d_desc, cap, h->d_counts + s0, 0);
     if (rc) return rc;
-    uint8_t* d_desc = h->d_desc + (size_t)s0 * cap * 32;
-    orbx_dmatch* d_good = h->d_good + (size_t)s0 * cap;
     const size_t b0 = (size_t)s0 * ORBX_MAX_BACK;          // this lane's first pair in the `back` buffers
+    const size_t bl0 = b0 * h->dev_cap;
     if (m && back >= 1) {
         // the steady-state loop of pnpPoseEstimation (src/CameraPoseEstimator.cpp:405-419): every frame against its `back`
         // predecessors, matchFeatures + computeFundamentalMatrix per pair; the history (descriptors, keypoints) of the
@@ -1134,26 +1190,26 @@ static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, co
         if (rc) return rc;
         if (h->nhist && h->hist_cap != cap) h->nhist = 0;
         const int cur = h->hist_cur, nh = std::min(h->nhist, back);
-        rc = hamx_set_stream(m, (void*)h->stream);
-        if (rc) return rc;
-        rc = hamx_match_back_dev(m, d_desc, h->d_counts + s0, nframes, cap, back, h->d_hist[cur], h->d_hist_counts[cur], nh, ratio,
-                                 h->d_good_back + b0 * cap, h->d_ngood_back + b0);
-        if (!rc) rc = hamx_update_history_dev(m, d_desc, h->d_counts + s0, nframes, cap, ORBX_MAX_BACK, h->d_hist[cur], h->d_hist_counts[cur],
-                                              h->nhist, h->d_hist[cur ^ 1], h->d_hist_counts[cur ^ 1]);
-        hamx_set_stream(m, nullptr);
+        {
+            ScopedHamxStream on(m, h->stream);
+            if (on.rc) return on.rc;
+            rc = hamx_match_back_dev(m, d_desc, h->d_counts + s0, nframes, cap, back, h->d_hist[cur], h->d_hist_counts[cur], nh, ratio,
+                                     h->d_good_back + bl0, h->d_ngood_back + b0);
+            if (!rc) rc = hamx_update_history_dev(m, d_desc, h->d_counts + s0, nframes, cap, ORBX_MAX_BACK, h->d_hist[cur], h->d_hist_counts[cur],
+                                                  h->nhist, h->d_hist[cur ^ 1], h->d_hist_counts[cur ^ 1]);
+        }
         if (rc) return rc;
         if (fm) {
-            rc = fmx_set_stream(fm, (void*)h->stream);
-            if (rc) return rc;
-            rc = fmx_filter_back_dev(fm, h->d_kps + (size_t)s0 * cap, nframes, cap, back, h->d_hist_kps[cur], nh, h->d_good_back + b0 * cap,
-                                     h->d_ngood_back + b0, max_distance, confidence, h->d_fstatus_back + b0 * cap, h->d_fF_back + b0 * 9,
+            ScopedFmxStream on(fm, h->stream);
+            if (on.rc) return on.rc;
+            rc = fmx_filter_back_dev(fm, d_kps, nframes, cap, back, h->d_hist_kps[cur], nh, h->d_good_back + bl0,
+                                     h->d_ngood_back + b0, max_distance, confidence, h->d_fstatus_back + bl0, h->d_fF_back + b0 * 9,
                                      h->d_finfo_back + b0 * 4);
-            fmx_set_stream(fm, nullptr);
             if (rc) return rc;
         }
         for (int hi = 0; hi < ORBX_MAX_BACK; hi++) {
             const int src = nframes - 1 - hi;
-            const orbx_keypoint* from = src >= 0 ? h->d_kps + ((size_t)s0 + src) * cap
+            const orbx_keypoint* from = src >= 0 ? d_kps + (size_t)src * cap
                                                  : (-src - 1 < h->nhist ? h->d_hist_kps[cur] + (size_t)(-src - 1) * cap : nullptr);
             if (from)
                 ORBX_CUDA(cudaMemcpyAsync(h->d_hist_kps[cur ^ 1] + (size_t)hi * cap, from, (size_t)cap * sizeof(orbx_keypoint),
@@ -1163,11 +1219,13 @@ static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, co
         h->nhist = std::min(ORBX_MAX_BACK, h->nhist + nframes);
         h->hist_cap = cap;
     } else if (m) {
-        rc = hamx_set_stream(m, (void*)h->stream);
-        if (rc) return rc;
-        rc = hamx_match_consecutive_dev(m, d_desc, h->d_counts + s0, nframes, cap, h->have_prev ? h->d_prev_desc : nullptr,
-                                        h->have_prev ? h->d_prev_count : nullptr, ratio, d_good, h->d_ngood + s0);
-        hamx_set_stream(m, nullptr);
+        if (h->have_prev && h->prev_cap != cap) h->have_prev = false;     // the kept frame is laid out for another capacity
+        {
+            ScopedHamxStream on(m, h->stream);
+            if (on.rc) return on.rc;
+            rc = hamx_match_consecutive_dev(m, d_desc, h->d_counts + s0, nframes, cap, h->have_prev ? h->d_prev_desc : nullptr,
+                                            h->have_prev ? h->d_prev_count : nullptr, ratio, d_good, h->d_ngood + s0);
+        }
         if (rc) return rc;
         ORBX_CUDA(cudaMemcpyAsync(h->d_prev_desc, d_desc + (size_t)(nframes - 1) * cap * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, h->stream));
         ORBX_CUDA(cudaMemcpyAsync(h->d_prev_count, h->d_counts + s0 + (nframes - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
@@ -1175,31 +1233,32 @@ static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, co
         // the next batch either way (stream order: the filter reads the old copy before it is overwritten)
         rc = ensure_filter_buffers(h);
         if (rc) return rc;
+        d_fstatus = h->d_fstatus + l0;
         orbx_keypoint* prev_kps = h->d_prev_kps[h->prev_kps_cur];
         if (fm) {
-            rc = fmx_set_stream(fm, (void*)h->stream);
-            if (rc) return rc;
-            rc = fmx_filter_consecutive_dev(fm, h->d_kps + (size_t)s0 * cap, h->have_prev ? prev_kps : nullptr, nframes, cap, d_good,
-                                            h->d_ngood + s0, max_distance, confidence, h->d_fstatus + (size_t)s0 * cap,
+            ScopedFmxStream on(fm, h->stream);
+            if (on.rc) return on.rc;
+            rc = fmx_filter_consecutive_dev(fm, d_kps, h->have_prev ? prev_kps : nullptr, nframes, cap, d_good,
+                                            h->d_ngood + s0, max_distance, confidence, d_fstatus,
                                             h->d_fF + (size_t)s0 * 9, h->d_finfo + (size_t)s0 * 4);
-            fmx_set_stream(fm, nullptr);
             if (rc) return rc;
         }
-        ORBX_CUDA(cudaMemcpyAsync(prev_kps, h->d_kps + ((size_t)s0 + nframes - 1) * cap, (size_t)cap * sizeof(orbx_keypoint),
+        ORBX_CUDA(cudaMemcpyAsync(prev_kps, d_kps + (size_t)(nframes - 1) * cap, (size_t)cap * sizeof(orbx_keypoint),
                                   cudaMemcpyDeviceToDevice, h->stream));
         h->have_prev = true;
+        h->prev_cap = cap;
     }
     ORBX_CUDA(cudaEventRecord(L.computed, h->stream));
     ORBX_CUDA(cudaStreamWaitEvent(h->d2h_stream, L.computed, 0));
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr + s0, h->d_ctr + s0, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->d2h_stream));
-    ORBX_CUDA(cudaMemcpyAsync(out, h->d_kps + (size_t)s0 * cap, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->d2h_stream));
+    ORBX_CUDA(cudaMemcpyAsync(out, d_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->d2h_stream));
     ORBX_CUDA(cudaMemcpyAsync(desc, d_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, h->d2h_stream));
     if (m && back >= 1) {
         const size_t np = (size_t)nframes * back;
-        ORBX_CUDA(cudaMemcpyAsync(good, h->d_good_back + b0 * cap, np * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->d2h_stream));
+        ORBX_CUDA(cudaMemcpyAsync(good, h->d_good_back + bl0, np * cap * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->d2h_stream));
         ORBX_CUDA(cudaMemcpyAsync(h->h_ngood_back + b0, h->d_ngood_back + b0, np * sizeof(int64_t), cudaMemcpyDeviceToHost, h->d2h_stream));
         if (fm) {
-            ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus_back + b0 * cap, np * cap, cudaMemcpyDeviceToHost, h->d2h_stream));
+            ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus_back + bl0, np * cap, cudaMemcpyDeviceToHost, h->d2h_stream));
             ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF_back + b0 * 9, np * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
             ORBX_CUDA(cudaMemcpyAsync(h->h_finfo_back + b0 * 4, h->d_finfo_back + b0 * 4, np * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                       h->d2h_stream));
@@ -1209,7 +1268,7 @@ static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, co
         ORBX_CUDA(cudaMemcpyAsync(h->h_ngood + s0, h->d_ngood + s0, (size_t)nframes * sizeof(int64_t), cudaMemcpyDeviceToHost, h->d2h_stream));
     }
     if (fm && back == 0) {
-        ORBX_CUDA(cudaMemcpyAsync(status, h->d_fstatus + (size_t)s0 * cap, (size_t)nframes * cap, cudaMemcpyDeviceToHost, h->d2h_stream));
+        ORBX_CUDA(cudaMemcpyAsync(status, d_fstatus, (size_t)nframes * cap, cudaMemcpyDeviceToHost, h->d2h_stream));
         ORBX_CUDA(cudaMemcpyAsync(F, h->d_fF + (size_t)s0 * 9, (size_t)nframes * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
         ORBX_CUDA(cudaMemcpyAsync(h->h_finfo + (size_t)s0 * 4, h->d_finfo + (size_t)s0 * 4, (size_t)nframes * 4 * sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, h->d2h_stream));
@@ -1272,6 +1331,7 @@ extern "C" int orbx_debug_pyramid_level(orbx_handle h, const uint8_t* gray, int 
     int rc = common_checks(h, gray, w, hh, stride, "orbx_debug_pyramid_level");
     if (rc) return rc;
     ORBX_REQUIRE(out && level >= 0 && level < h->g.nlevels, "orbx_debug_pyramid_level: bad level %d", level);
+    h->last_nframes = h->filter_nframes = h->back_n = 0;
     const uint8_t* frames[1] = { gray };
     rc = upload_frames(h, frames, 0, 1, w, hh, stride, cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;
@@ -1289,6 +1349,7 @@ extern "C" int orbx_debug_fast_level(orbx_handle h, const uint8_t* gray, int w, 
     int rc = common_checks(h, gray, w, hh, stride, "orbx_debug_fast_level");
     if (rc) return rc;
     ORBX_REQUIRE(xs && ys && scores && n && level >= 0 && level < h->g.nlevels, "orbx_debug_fast_level: bad arguments");
+    h->last_nframes = h->filter_nframes = h->back_n = 0;
     const uint8_t* frames[1] = { gray };
     rc = upload_frames(h, frames, 0, 1, w, hh, stride, cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;

@@ -102,6 +102,7 @@ class ORB:
     def detect(self, image, cap=None):
         img = _gray(image)
         self._set_channels(img)
+        self._last_batch = None
 
         def run(cap):
             kps = np.zeros(cap, KEYPOINT_DTYPE)
@@ -116,6 +117,7 @@ class ORB:
     def compute(self, image, keypoints):
         img = _gray(image)
         self._set_channels(img)
+        self._last_batch = None
         kps = np.array(keypoints, dtype=KEYPOINT_DTYPE, copy=True)
         n = C.c_int(len(kps))
         desc = np.zeros((max(len(kps), 1), 32), np.uint8)
@@ -126,6 +128,7 @@ class ORB:
     def detectAndCompute(self, image, cap=None):
         img = _gray(image)
         self._set_channels(img)
+        self._last_batch = None
 
         def run(cap):
             kps = np.zeros(cap, KEYPOINT_DTYPE)
@@ -157,11 +160,27 @@ class ORB:
                 kps = np.zeros((n, cap), KEYPOINT_DTYPE)
                 desc = np.zeros((n, cap, 32), np.uint8)
                 counts = np.zeros(n, np.int32)
+            self._last_batch = None
             check(_lib.lib().orbx_extract_batch(self._h, ptrs, n, w, h, stride, kps.ctypes.data, desc.ctypes.data, cap,
                                                 counts.ctypes.data_as(C.POINTER(C.c_int32))))
+            # the geometry the sequence calls below size their buffers from: _retry may have raised the capacity
+            self._last_batch = (n, cap)
             return kps, desc, counts
 
         return self._retry(run, cap or self.default_cap)
+
+    def _seq_geometry(self, cap, nframes, what):
+        """(nframes, cap) of the batch the handle holds; the optional caller values must agree with it (the library checks
+        the same through its own arguments, so a stale value fails instead of overflowing a buffer)."""
+        last = getattr(self, "_last_batch", None)
+        if last is None:
+            raise ValueError("%s: no batch has been extracted with extract_batch on this ORB object" % what)
+        n, c = last
+        if nframes is not None and nframes != n:
+            raise ValueError("%s: nframes = %d, but the last extract_batch held %d frames" % (what, nframes, n))
+        if cap is not None and cap != c:
+            raise ValueError("%s: cap = %d, but the last extract_batch ran with cap %d (a capacity retry raises it)" % (what, cap, c))
+        return n, c
 
     def extract_batch_dev(self, d_frames_ptr, frame_pitch, nframes, w, h, stride, d_kps_ptr, d_desc_ptr, cap, d_counts_ptr):
         """Device-resident variant (raw device pointers, asynchronous on the handle's stream)."""
@@ -172,37 +191,44 @@ class ORB:
         check(_lib.lib().orbx_check_dev(self._h))
 
     # -- sequence mode: consecutive-frame matching of the batch last extracted, descriptors stay on the device
-    def match_consecutive(self, matcher, ratio, cap, nframes, out=None):
+    def match_consecutive(self, matcher, ratio, cap=None, nframes=None, out=None):
         """matchFeatures(desc[f], desc[f-1], ratio) for every frame f of the last extract_batch (frame 0 against the last
-        frame of the previous batch).  Returns (good[nframes, cap] DMATCH_DTYPE, ngood[nframes])."""
+        frame of the previous batch).  Returns (good[nframes, cap] DMATCH_DTYPE, ngood[nframes]); the buffers are sized from
+        the geometry of that extract_batch, ``cap`` / ``nframes`` are only cross-checked against it."""
+        n, c = self._seq_geometry(cap, nframes, "match_consecutive")
         if out is not None:
             good, ngood = out
+            if good.shape != (n, c) or good.dtype != DMATCH_DTYPE or ngood.shape != (n,) or ngood.dtype != np.int64 \
+                    or not good.flags.c_contiguous:
+                raise ValueError("match_consecutive: out must be (good[%d, %d] DMATCH_DTYPE, ngood[%d] int64)" % (n, c, n))
         else:
-            good = np.zeros((nframes, cap), DMATCH_DTYPE)
-            ngood = np.zeros(nframes, np.int64)
-        check(_lib.lib().orbx_match_consecutive(self._h, matcher._h, float(ratio), good.ctypes.data,
+            good = np.zeros((n, c), DMATCH_DTYPE)
+            ngood = np.zeros(n, np.int64)
+        check(_lib.lib().orbx_match_consecutive(self._h, matcher._h, float(ratio), n, c, good.ctypes.data,
                                                 ngood.ctypes.data_as(C.POINTER(C.c_int64))))
         return good, ngood
 
-    def filter_consecutive(self, fundamental, cap, nframes, max_distance=3.0, confidence=0.85):
+    def filter_consecutive(self, fundamental, cap=None, nframes=None, max_distance=3.0, confidence=0.85):
         """computeFundamentalMatrix (src/CameraPoseEstimator.cpp:545-586) for every (frame f, frame f-1) pair of the batch
         match_consecutive just ran on; the match lists stay on the device in between.
         Returns (status[nframes, cap] uint8 aligned with good[f], F[nframes, 3, 3], ninliers[nframes])."""
-        status = np.zeros((nframes, cap), np.uint8)
-        F = np.zeros((nframes, 3, 3), np.float64)
-        ninl = np.zeros(nframes, np.int32)
-        check(_lib.lib().orbx_filter_consecutive(self._h, fundamental._h, float(max_distance), float(confidence),
+        n, c = self._seq_geometry(cap, nframes, "filter_consecutive")
+        status = np.zeros((n, c), np.uint8)
+        F = np.zeros((n, 3, 3), np.float64)
+        ninl = np.zeros(n, np.int32)
+        check(_lib.lib().orbx_filter_consecutive(self._h, fundamental._h, float(max_distance), float(confidence), n, c,
                                                  status.ctypes.data, F.ctypes.data, ninl.ctypes.data))
         return status, F, ninl
 
-    def filter_back(self, fundamental, back, cap, nframes, max_distance=3.0, confidence=0.85):
+    def filter_back(self, fundamental, back, cap=None, nframes=None, max_distance=3.0, confidence=0.85):
         """computeFundamentalMatrix for every (frame f, frame f-j) pair match_back just matched (the loop at
         src/CameraPoseEstimator.cpp:405-419).  Returns (status[nframes, back, cap], F[nframes, back, 3, 3], ninliers[nframes, back])."""
-        status = np.zeros((nframes, back, cap), np.uint8)
-        F = np.zeros((nframes, back, 3, 3), np.float64)
-        ninl = np.zeros((nframes, back), np.int32)
-        check(_lib.lib().orbx_filter_back(self._h, fundamental._h, float(max_distance), float(confidence), status.ctypes.data,
-                                          F.ctypes.data, ninl.ctypes.data))
+        n, c = self._seq_geometry(cap, nframes, "filter_back")
+        status = np.zeros((n, back, c), np.uint8)
+        F = np.zeros((n, back, 3, 3), np.float64)
+        ninl = np.zeros((n, back), np.int32)
+        check(_lib.lib().orbx_filter_back(self._h, fundamental._h, float(max_distance), float(confidence), n, int(back), c,
+                                          status.ctypes.data, F.ctypes.data, ninl.ctypes.data))
         return status, F, ninl
 
     # -- pipelined sequence mode: pipeline_depth() batches in flight (upload / kernels / download overlap across batches)
@@ -226,6 +252,7 @@ class ORB:
         if kps.shape[0] < n or desc.shape[:2] != kps.shape[:2] or counts.dtype != np.int32 or ngood.dtype != np.int64:
             raise ValueError("bad output buffers")
         ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        self._last_batch = None          # match_consecutive / match_back pair with extract_batch only
         self._inflight = getattr(self, "_inflight", [])
         if back:
             if good.shape[1:] != (back, cap) or ngood.shape[1:] != (back,):
@@ -268,13 +295,14 @@ class ORB:
     def batches_in_flight(self):
         return _lib.lib().orbx_batches_in_flight(self._h)
 
-    def match_back(self, matcher, back, ratio, cap, nframes):
+    def match_back(self, matcher, back, ratio, cap=None, nframes=None):
         """matchFeatures(desc[f], desc[f-j], ratio) for j = 1..back and every frame f of the last extract_batch -- the
         steady-state loop of CameraPoseEstimator::pnpPoseEstimation (numBackTraverse = 5, src/CameraPoseEstimator.cpp:405-409);
         frames before the batch come from the handle's history.  Returns (good[nframes, back, cap], ngood[nframes, back])."""
-        good = np.zeros((nframes, back, cap), DMATCH_DTYPE)
-        ngood = np.zeros((nframes, back), np.int64)
-        check(_lib.lib().orbx_match_back(self._h, matcher._h, int(back), float(ratio), good.ctypes.data,
+        n, c = self._seq_geometry(cap, nframes, "match_back")
+        good = np.zeros((n, back, c), DMATCH_DTYPE)
+        ngood = np.zeros((n, back), np.int64)
+        check(_lib.lib().orbx_match_back(self._h, matcher._h, int(back), float(ratio), n, c, good.ctypes.data,
                                          ngood.ctypes.data_as(C.POINTER(C.c_int64))))
         return good, ngood
 
@@ -350,6 +378,10 @@ class BFMatcher:
 
     def synchronize(self):
         check(_lib.lib().hamx_synchronize(self._h))
+
+    def reserve(self, nq, nt, npairs=1):
+        """Size the workspaces once so that later *_dev calls of up to this shape never allocate (hamx_reserve)."""
+        check(_lib.lib().hamx_reserve(self._h, int(nq), int(nt), int(npairs)))
 
     @staticmethod
     def _desc(d):

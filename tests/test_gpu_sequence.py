@@ -307,3 +307,119 @@ def test_sharded_sequence_with_outlier_filter():
     fm.close()
     m.close()
     orb.close()
+
+
+# ---------------------------------------------------------------------------------------------- boundary regressions
+def test_sequence_buffers_follow_the_capacity_retry():
+    """extract_batch retries with the maximum capacity after ORBX_E_CAPACITY; the sequence calls size their buffers from
+    the batch the handle holds, and a stale (cap, nframes) is refused by Python and by the C ABI instead of overflowing."""
+    import ctypes as C
+    from monocular_slam_b200 import _lib
+    seq = syn.sequence(3, 640, 480, seed=5)
+    ext, matches = _oracle_sequence(seq, 500, 0.8)
+    orb = ORB(nfeatures=500, max_size=(640, 480), max_batch=3)
+    m = BFMatcher()
+    kps, desc, counts = orb.extract_batch(list(seq), cap=100)          # too small: retried at max_keypoints
+    assert kps.shape[1] == orb.max_keypoints
+    with pytest.raises(ValueError):
+        orb.match_consecutive(m, 0.8, 100, 3)                           # the cap the caller asked for is stale
+    with pytest.raises(ValueError):
+        orb.match_consecutive(m, 0.8, None, 2)
+    good = np.zeros((3, 100), DMATCH_DTYPE)
+    ngood = np.zeros(3, np.int64)
+    rc = _lib.lib().orbx_match_consecutive(orb._h, m._h, 0.8, 3, 100, good.ctypes.data, ngood.ctypes.data_as(C.POINTER(C.c_int64)))
+    assert rc == _lib.E_INVALID and not good.view(np.uint8).any()
+    good, ngood = orb.match_consecutive(m, 0.8)
+    assert good.shape == (3, orb.max_keypoints)
+    for f in (1, 2):
+        _check_matches(good[f], int(ngood[f]), matches[f])
+    # rows wider than the device rows: [n][cap] host layout, only the device's columns are written
+    wide = np.zeros((3, orb.max_keypoints + 7), DMATCH_DTYPE)
+    orb.extract_batch(list(seq), cap=orb.max_keypoints)
+    orb.reset_sequence()
+    rc = _lib.lib().orbx_match_consecutive(orb._h, m._h, 0.8, 3, orb.max_keypoints + 7, wide.ctypes.data,
+                                           ngood.ctypes.data_as(C.POINTER(C.c_int64)))
+    assert rc == 0
+    for f in (1, 2):
+        _check_matches(wide[f], int(ngood[f]), matches[f])
+    m.close()
+    orb.close()
+
+
+def test_sequence_calls_keep_the_callers_stream():
+    """orbx_match_consecutive / orbx_filter_consecutive / orbx_submit_batch run the matcher and the filter on the
+    extractor's stream for one call and must put back the stream the caller installed on those handles."""
+    import ctypes as C
+    import torch
+    from monocular_slam_b200 import FundamentalFilter, _lib
+    seq = syn.sequence(2, 640, 480, seed=6)
+    orb = ORB(nfeatures=500, max_size=(640, 480), max_batch=2)
+    m, fm = BFMatcher(), FundamentalFilter()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    m.set_stream(s1.cuda_stream)
+    fm.set_stream(s2.cuda_stream)
+
+    def streams():
+        a, b = C.c_void_p(), C.c_void_p()
+        _lib.check(_lib.lib().hamx_get_stream(m._h, C.byref(a)))
+        _lib.check(_lib.lib().fmx_get_stream(fm._h, C.byref(b)))
+        return a.value, b.value
+    want = (s1.cuda_stream, s2.cuda_stream)
+    assert streams() == want
+    orb.extract_batch(list(seq))
+    orb.match_consecutive(m, 0.8)
+    orb.filter_consecutive(fm)
+    assert streams() == want
+    orb.extract_batch(list(seq))
+    orb.match_back(m, 2, 0.8)
+    orb.filter_back(fm, 2)
+    assert streams() == want
+    cap = orb.default_cap
+    out = (np.zeros((2, cap), KEYPOINT_DTYPE), np.zeros((2, cap, 32), np.uint8), np.zeros(2, np.int32), np.zeros((2, cap), DMATCH_DTYPE),
+           np.zeros(2, np.int64), np.zeros((2, cap), np.uint8), np.zeros((2, 3, 3), np.float64), np.zeros(2, np.int32))
+    orb.submit_batch(list(seq), m, 0.8, out, fundamental=fm)
+    orb.wait_batch()
+    assert streams() == want
+    m.close(); fm.close(); orb.close()
+
+
+def test_pipeline_lanes_with_different_capacities():
+    """Batches in flight with different capacities live in disjoint lane regions: results equal the blocking path's."""
+    seq = syn.sequence(6, 640, 480, seed=8)
+    ext, matches = _oracle_sequence(seq, 500, 0.8)
+    orb = ORB(nfeatures=500, max_size=(640, 480), max_batch=2)
+    m = BFMatcher()
+    caps = [orb.default_cap, orb.max_keypoints, orb.default_cap + 64]
+    outs = [(np.zeros((2, c), KEYPOINT_DTYPE), np.zeros((2, c, 32), np.uint8), np.zeros(2, np.int32), np.zeros((2, c), DMATCH_DTYPE),
+             np.zeros(2, np.int64)) for c in caps]
+    for b in range(3):
+        orb.submit_batch(list(seq[2 * b:2 * b + 2]), m, 0.8, outs[b])
+    for b in range(3):
+        kps, desc, counts, good, ngood = orb.wait_batch()
+        for i in range(2):
+            f = 2 * b + i
+            assert_keypoints_equal(kps[i, :counts[i]], ext[f][0], "frame %d" % f)
+            assert_descriptors_equal(desc[i, :counts[i]], ext[f][1], "frame %d" % f)
+            if i == 1:            # the link to the previous batch is dropped when the capacity changes (include/orbx.h)
+                _check_matches(good[i], int(ngood[i]), matches[f])
+    m.close()
+    orb.close()
+
+
+def test_check_dev_ignores_stale_overflow_flags():
+    """An overflow left in a high frame slot by an earlier, larger _dev batch must not fail later, smaller batches."""
+    import torch
+    from monocular_slam_b200 import OrbxError
+    seq = syn.sequence(4, 640, 480, seed=9)
+    orb = ORB(nfeatures=500, max_size=(640, 480), max_batch=4)
+    d_frames = torch.from_numpy(seq).cuda()
+    cap = orb.default_cap
+    kps = torch.zeros((4, cap, 7), dtype=torch.float32, device="cuda")
+    desc = torch.zeros((4, cap, 32), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    orb.extract_batch_dev(d_frames.data_ptr(), 640 * 480, 4, 640, 480, 640, kps.data_ptr(), desc.data_ptr(), 16, cnt.data_ptr())
+    with pytest.raises(OrbxError):
+        orb.check_dev()                     # 16 rows cannot hold 500 keypoints
+    orb.extract_batch_dev(d_frames.data_ptr(), 640 * 480, 1, 640, 480, 640, kps.data_ptr(), desc.data_ptr(), cap, cnt.data_ptr())
+    orb.check_dev()                         # slots 1..3 still carry the old flag; only slot 0 is in use
+    orb.close()

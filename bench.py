@@ -81,18 +81,41 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------------------------ shared config
+def level_pixels():
+    """Pixels of all 8 pyramid levels of a W x H frame (cv::ORB's level sizes: round(W / scale_l), float32 scale)."""
+    px = 0
+    for l in range(8):
+        sc = np.float32(np.float64(np.float32(1.2)) ** l)
+        px += int(np.rint(np.float32(W) / sc)) * int(np.rint(np.float32(H) / sc))
+    return px
+
+
+def workload_config(world, B):
+    """`config` of the JSON line, identical for both arms (the reference arm processes the same frames on the host)."""
+    level_px = level_pixels()
+    cfg = {"workload": "synthetic %dx%d monocular sequence, %d kp/frame, consecutive-frame matching, ratio 0.75 (BASELINE.json configs[%d])"
+                       % (W, H, NFEAT, 1 if (W, H, NFEAT) == (1920, 1080, 2000) else 2),
+           "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "nlevels": 8, "scale_factor": 1.2, "score_type": "HARRIS",
+           "batch_frames_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+           "frames_seed": "synthetic.sequence(B, W, H, seed=100 + rank)"}
+    if True:
+        cfg["l2"] = ("inputs larger than L2: %d frames x %.1f MB = %.0f MB of frames (+%.0f MB of pyramid levels) per step vs 126 MB L2"
+                     % (B, W * H / 1e6, B * W * H / 1e6, B * (level_px - W * H) / 1e6))
+    return cfg
+
+
 # ------------------------------------------------------------------------------------------------ CPU reference path
 _W = {}
 
 
-def _cpu_worker_init(seed, nframes, w, h, nfeat, use_cv2):
-    """Runs in a worker process: build this worker's own frames (no big pickles) and its extractor."""
-    from monocular_slam_b200 import synthetic as syn
-    _W["frames"] = syn.sequence(nframes, w, h, seed=seed)
-    _W["use_cv2"] = use_cv2
+def _cpu_worker_init(frames, lead_in, nfeat, use_cv2, threads=1):
+    """Runs in a worker process: this worker's frames of the step's sequence (+ the frame before them, to match the
+    first one against) and its extractor."""
+    _W["frames"], _W["lead_in"], _W["use_cv2"] = frames, lead_in, use_cv2
     if use_cv2:
         import cv2
-        cv2.setNumThreads(1)
+        cv2.setNumThreads(threads)
         _W["cv2"] = cv2
         _W["orb"] = cv2.ORB_create(nfeatures=nfeat)
         _W["bf"] = cv2.BFMatcher(cv2.NORM_HAMMING, False)
@@ -101,37 +124,49 @@ def _cpu_worker_init(seed, nframes, w, h, nfeat, use_cv2):
         _W["oracle"] = oracle
         _W["params"] = oracle.Params(nfeatures=nfeat)
     _W["prev"] = None
+    if lead_in is not None:                     # its descriptors are what the previous worker computes for its last frame
+        _W["prev"] = _cpu_extract(lead_in)[1]
+    _W["prev0"] = _W["prev"]
     return True
+
+
+def _cpu_extract(img):
+    """The reference's call order: detect, compute (src/FeatureExtractor.cpp:17,19)."""
+    if _W["use_cv2"]:
+        kp = _W["orb"].detect(img, None)
+        return _W["orb"].compute(img, kp)
+    return _W["oracle"].detect_and_compute(img, _W["params"])
 
 
 def _cpu_worker_step(_):
     """One bounded sample: extract every frame of the worker's block and match it against its predecessor, exactly in
-    the reference's call order (detect, compute: src/FeatureExtractor.cpp:17,19; knnMatch k=2 + ratio:
-    src/CameraPoseEstimator.cpp:200-213)."""
+    the reference's call order (knnMatch k=2 + ratio: src/CameraPoseEstimator.cpp:200-213)."""
     t0 = time.perf_counter()
+    prev, nkp, nmatch, npairs = _W["prev0"], 0, 0, 0
     for img in _W["frames"]:
-        if _W["use_cv2"]:
-            kp = _W["orb"].detect(img, None)
-            kp, des = _W["orb"].compute(img, kp)
-            if _W["prev"] is not None and des is not None:
-                raw = _W["bf"].knnMatch(des, _W["prev"], 2)
-                _W["good"] = [r[0] for r in raw if len(r) == 2 and r[0].distance < r[1].distance * np.float32(RATIO)]
-            _W["prev"] = des
-        else:
-            kp, des = _W["oracle"].detect_and_compute(img, _W["params"])
-            if _W["prev"] is not None:
-                _W["oracle"].match_features(des, _W["prev"], RATIO)
-            _W["prev"] = des
-    return len(_W["frames"]), time.perf_counter() - t0
+        kp, des = _cpu_extract(img)
+        nkp += len(kp)
+        if prev is not None and des is not None:
+            if _W["use_cv2"]:
+                raw = _W["bf"].knnMatch(des, prev, 2)
+                good = [r[0] for r in raw if len(r) == 2 and r[0].distance < r[1].distance * np.float32(RATIO)]
+                nmatch += len(good)
+            else:
+                nmatch += len(_W["oracle"].match_features(des, prev, RATIO)[0])
+            npairs += 1
+        prev = des
+    return len(_W["frames"]), time.perf_counter() - t0, nkp, nmatch, npairs
 
 
 class CpuReference:
     """The reference's CPU extract+match path on all host cores: one process per core, each running OpenCV's ORB /
     BFMatcher single-threaded (cv2 is the library the reference calls; if it cannot be imported the C oracle port is
-    timed instead and `kind` says "port")."""
+    timed instead and `kind` says "port").  A step is the SAME batch of frames the GPU arm's rank 0 processes
+    (synthetic.sequence(B, W, H, seed=100)), dealt to the workers in contiguous blocks."""
 
-    def __init__(self, frames_per_worker=2, max_workers=128):
+    def __init__(self, nframes, max_workers=128, threads=1, workers=None):
         import multiprocessing as mp
+        from monocular_slam_b200 import synthetic as syn
         try:
             import cv2  # noqa: F401
             self.use_cv2 = True
@@ -143,20 +178,28 @@ class CpuReference:
             ncpu = len(os.sched_getaffinity(0))
         except Exception:
             ncpu = os.cpu_count() or 1
-        self.workers = max(1, min(ncpu, max_workers))
-        self.frames_per_worker = frames_per_worker
+        self.workers = workers or max(1, min(ncpu, max_workers, nframes))
+        self.threads = threads
+        self.nframes = nframes
+        seq = syn.sequence(nframes, W, H, seed=100)
+        bounds = np.linspace(0, nframes, self.workers + 1).astype(int)
         ctx = mp.get_context("spawn")
         self.pools = []
         # one single-process pool per worker so that each keeps its own frames and every step reaches every worker
         for i in range(self.workers):
-            self.pools.append(ctx.Pool(1, initializer=_cpu_worker_init, initargs=(1000 + i, frames_per_worker, W, H, NFEAT, self.use_cv2)))
-        for p in self.pools:
-            p.apply(_cpu_worker_step, (0,))   # first touch: imports, page-in, first matches
+            lo, hi = int(bounds[i]), int(bounds[i + 1])
+            self.pools.append(ctx.Pool(1, initializer=_cpu_worker_init,
+                                       initargs=(seq[lo:hi].copy(), seq[lo - 1].copy() if lo > 0 else None, NFEAT, self.use_cv2, threads)))
+        self.stats = None
+        self.step()   # first touch: imports, page-in, first matches
 
     def step(self):
         t0 = time.perf_counter()
         res = [p.apply_async(_cpu_worker_step, (0,)) for p in self.pools]
-        n = sum(r.get()[0] for r in res)
+        res = [r.get() for r in res]
+        n = sum(r[0] for r in res)
+        self.stats = {"keypoints_per_frame": sum(r[2] for r in res) / max(n, 1),
+                      "matches_per_frame": sum(r[3] for r in res) / max(sum(r[4] for r in res), 1)}
         return n, time.perf_counter() - t0
 
     def close(self):
@@ -164,17 +207,37 @@ class CpuReference:
             p.terminate()
 
     def describe(self):
-        return {"kind": "reference" if self.use_cv2 else "port", "cores": self.workers,
-                "sample": "%d frames of %dx%d per step (%d per worker process, %s single-threaded per process), detect+compute+knnMatch(k=2)+ratio %.2f against the previous frame"
-                          % (self.workers * self.frames_per_worker, W, H, self.frames_per_worker,
+        return {"kind": "reference" if self.use_cv2 else "port", "cores": self.workers * self.threads,
+                "sample": "%d frames of %dx%d per step, %d worker process(es) x %d thread(s), %s; detect+compute+knnMatch(k=2)+ratio %.2f against the previous frame"
+                          % (self.nframes, W, H, self.workers, self.threads,
                              "cv2 %s ORB/BFMatcher" % __import__("cv2").__version__ if self.use_cv2 else "oracle/orb_oracle.c", RATIO)}
+
+
+def cpu_thread_settings(nframes=2):
+    """the same calls with cv2.setNumThreads(1) and cv2.setNumThreads(all cores) in ONE process
+    (frames/s each), reported beside the process pool."""
+    out = {}
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        ncpu = os.cpu_count() or 1
+    for name, thr in (("one_process_1_thread", 1), ("one_process_all_threads", ncpu)):
+        try:
+            ref = CpuReference(nframes, threads=thr, workers=1)
+            best = min(ref.step()[1] for _ in range(2))
+            ref.close()
+            out[name] = nframes / best
+        except Exception:
+            out[name] = None
+    out["threads_all"] = ncpu
+    return out
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    ref = CpuReference(frames_per_worker=2)
-    for _ in range(args.warmup):
+    ref = CpuReference(args.batch)
+    for _ in range(max(args.warmup - 1, 0)):
         ref.step()
     frames, elapsed = 0, 0.0
     for _ in range(args.steps):
@@ -186,12 +249,11 @@ def run_reference(args, rank):
     d = ref.describe()
     d["value"] = value
     d["unit"] = "frames/s"
+    cfg = workload_config(args.gpus, args.batch)
+    cfg.update(ref.stats)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "synthetic %dx%d monocular sequence, %d kp/frame, consecutive-frame matching (BASELINE.json configs[%d]), CPU"
-                                   % (W, H, NFEAT, 1 if (W, H, NFEAT) == (1920, 1080, 2000) else 2),
-                       "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "ratio": RATIO, "frames_per_step": frames // args.steps},
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
             "cpu_baseline": d,
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -206,6 +268,73 @@ def hbm_peak():
         except Exception:
             pass
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def run_cfg3(torch, syn, ORB, matcher, dev, local_rank, rank, world, stream, timed, max_over_ranks, barrier, args):
+    """BASELINE.json configs[2]: 3840x2160 frames, 8000 keypoints per frame, frames sharded over the ranks (every rank its own
+    block of 16 frames, consecutive-frame matching inside the block).  Device-resident and end-to-end (pipelined host path)
+    frames/s, a few steps each."""
+    from monocular_slam_b200 import DMATCH_DTYPE, KEYPOINT_DTYPE
+    w3, h3, nf3, b3, steps3 = 3840, 2160, 8000, 16, 5
+    seq3 = syn.sequence(b3, w3, h3, seed=500 + rank)
+    h_fr = torch.from_numpy(seq3).pin_memory()
+    d_fr = h_fr.to(dev, non_blocking=True)
+    orb3 = ORB(nfeatures=nf3, max_size=(w3, h3), max_batch=b3, device=local_rank)
+    orb3.set_stream(stream.cuda_stream)
+    cap = orb3.default_cap
+    d_kps = torch.empty((b3, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.empty((b3, cap, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(b3, dtype=torch.int32, device=dev)
+    d_good = torch.empty((b3, cap, 4), dtype=torch.int32, device=dev)
+    d_ngood = torch.zeros(b3, dtype=torch.int64, device=dev)
+
+    def step_dev():
+        orb3.extract_batch_dev(d_fr.data_ptr(), w3 * h3, b3, w3, h3, w3, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
+        matcher.match_consecutive_dev(d_desc.data_ptr(), d_cnt.data_ptr(), b3, cap, 0, 0, RATIO, d_good.data_ptr(), d_ngood.data_ptr())
+    ms, _ = timed(step_dev, steps3, 3)
+    orb3.check_dev()
+    ms = max_over_ranks(ms)
+    counts, ngood = d_cnt.cpu().numpy(), d_ngood.cpu().numpy()
+    depth = orb3.pipeline_depth()
+    frames_np = [h_fr[i].numpy() for i in range(b3)]
+    outs = [(torch.empty((b3, cap, 7), dtype=torch.float32).pin_memory().numpy().view(KEYPOINT_DTYPE).reshape(b3, cap),
+             torch.empty((b3, cap, 32), dtype=torch.uint8).pin_memory().numpy(), np.zeros(b3, np.int32),
+             torch.empty((b3, cap, 4), dtype=torch.int32).pin_memory().numpy().view(DMATCH_DTYPE).reshape(b3, cap),
+             np.zeros(b3, np.int64)) for _ in range(depth)]
+    k = [0]
+
+    def step_pipe():
+        if orb3.batches_in_flight() == depth:
+            orb3.wait_batch()
+        orb3.submit_batch(frames_np, matcher, RATIO, outs[k[0] % depth])
+        k[0] += 1
+
+    def drain():
+        last = None
+        while orb3.batches_in_flight():
+            last = orb3.wait_batch()
+        return last
+    orb3.reset_sequence()
+    for _ in range(3):
+        step_pipe()
+    drain()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps3):
+        step_pipe()
+    last = drain()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    assert np.array_equal(last[2], counts), "config 3: host and device paths disagree on keypoint counts"
+    assert np.array_equal(last[4][1:], ngood[1:]), "config 3: host and device paths disagree on match counts"
+    orb3.close()
+    return {"workload": "synthetic %dx%d sequence, %d kp/frame, %d frames per GPU and step, consecutive-frame matching (BASELINE.json configs[2])"
+                        % (w3, h3, nf3, b3),
+            "value": world * b3 * steps3 / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps3, "steps": steps3,
+            "keypoints_per_frame": float(counts.mean()), "matches_per_frame": float(ngood[1:].mean()),
+            "e2e": {"value": world * b3 * steps3 / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms / steps3,
+                    "h2d_bytes_per_step": b3 * w3 * h3, "d2h_bytes_per_step": b3 * cap * 76 + b3 * 8 + b3 * 16584}}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -377,6 +506,32 @@ def run_ours(args, rank, world, local_rank):
     assert np.array_equal(h_cnt, counts), "host and device paths disagree on keypoint counts"
     assert np.array_equal(h_ngood[1:], ngood_dev[1:]), "host and device paths disagree on match counts"
 
+    # ---- the floor under the end-to-end step: the same bytes as plain copies, timed in the same run with every rank copying
+    # at once (pinned host <-> device, one cudaMemcpyAsync each way per step, CUDA events on this rank's stream)
+    d2h_dev = torch.empty(d2h, dtype=torch.uint8, device=dev)
+    d2h_host = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+    d_floor = torch.empty_like(d_frames)
+
+    def step_h2d():
+        d_floor.copy_(h_frames, non_blocking=True)
+
+    def step_d2h():
+        d2h_host.copy_(d2h_dev, non_blocking=True)
+    h2d_floor_ms = max_over_ranks(timed(step_h2d, args.steps, 2)[0]) / args.steps
+    d2h_floor_ms = max_over_ranks(timed(step_d2h, args.steps, 2)[0]) / args.steps
+    del d_floor, d2h_dev, d2h_host
+
+    # ---- sustained: >= 2 s of back-to-back device-resident steps (the headline above is a 50 ms burst)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(2.2e3 / max(dev_ms / args.steps, 1e-3)))
+        sus_sampler = ClockSampler(local_rank, period=0.01)
+        sus_ms, _ = timed(step_device, n_sus, 0, sus_sampler)
+        orb.check_dev()
+        sus_ms = max_over_ranks(sus_ms)
+        sustained = {"value": world * B * n_sus / (sus_ms * 1e-3), "unit": "frames/s", "steps": n_sus, "seconds": sus_ms * 1e-3,
+                     "ms_per_step": sus_ms / n_sus, "clocks": sus_sampler.summary()}
+
     # ---- roofline of the dominant kernel (FAST): algorithmic bytes = every level pixel read once
     ws, hs, _, _ = orb.level_info(W, H)
     level_px = int((ws.astype(np.int64) * hs).sum())
@@ -402,6 +557,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"kernel": "k_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "launch_ms": fast_ms,
                 "algorithmic_bytes_per_launch": level_px * B,
+                "issue_frac": issue["frac"] if issue else None,
                 "issue": issue,
                 "note": "FAST reads each pyramid-level byte once (3.096 x W x H per frame); it is bound by instruction issue "
                         "(about 80 instructions per pixel on the integer pipes), not by HBM: see roofline.issue"}
@@ -413,6 +569,67 @@ def run_ours(args, rank, world, local_rank):
                         "algorithmic_bytes_per_step": pyr_bytes, "ms_per_step": stages["pyramid"],
                         "note": "bit-exact INTER_LINEAR_EXACT chain; ncu shows it bound by L1 / shared-memory throughput (70 %), not DRAM (14 %)"}
 
+    # ---- the same step on frames with camera-image statistics (synthetic.natural_frame: 0.25 % FAST corners instead of the
+    # 18 % of the Appendix-B stress generator the headline uses)
+    natural = None
+    if not args.no_natural:
+        nat = torch.from_numpy(syn.sequence(B, W, H, seed=300 + rank, generator=syn.natural_frame)).pin_memory()
+        d_keep = d_frames
+        d_frames = nat.to(dev, non_blocking=True)
+        state["have_prev"] = False
+        nat_ms, _ = timed(step_device, args.steps, args.warmup)
+        orb.check_dev()
+        nat_ms = max_over_ranks(nat_ms)
+        orb.set_profiling(True)
+        step_device()
+        orb.read_profile()
+        timed(step_device, max(args.steps // 2, 2), 0)
+        nat_stages, _ = orb.read_profile()
+        orb.set_profiling(False)
+        nat_counts, nat_good = d_cnt.cpu().numpy(), d_ngood.cpu().numpy()
+        natural = {"value": world * B * args.steps / (nat_ms * 1e-3), "unit": "frames/s", "ms_per_step": nat_ms / args.steps,
+                   "generator": "synthetic.natural_frame (1/f shading, flat objects, textured patches, lens blur, sensor noise)",
+                   "stages_ms_per_step": nat_stages, "keypoints_per_frame": float(nat_counts.mean()),
+                   "matches_per_frame": float(nat_good[1:].mean())}
+        d_frames = d_keep
+        state["have_prev"] = False
+        del nat
+
+    # ---- BASELINE.json configs[2]: 3840x2160 frames, 8000 keypoints, frame-sharded over the ranks (a short leg)
+    cfg3 = None
+    if not args.no_cfg3 and (W, H, NFEAT) == (1920, 1080, 2000):
+        cfg3 = run_cfg3(torch, syn, ORB, matcher, dev, local_rank, rank, world, stream, timed, max_over_ranks, barrier, args)
+
+    # ---- the reference's unmodified call-by-call loop, one frame at a time through the drop-in calls: detect, compute
+    # (src/FeatureExtractor.cpp:17,19), then matchFeatures + computeFundamentalMatrix against the 5 previous frames
+    # (src/CameraPoseEstimator.cpp:405-419); host wall clock per frame, results in host memory after every call
+    single = None
+    if not args.no_single:
+        from monocular_slam_b200 import FundamentalFilter
+        orb1 = ORB(nfeatures=NFEAT, max_size=(W, H), max_batch=1, device=local_rank)
+        fm1 = FundamentalFilter(device=local_rank)
+        hist = []
+        nfr = min(B, 24)
+
+        def one_frame(img):
+            kp = orb1.detect(img)
+            kp, des = orb1.compute(img, kp)
+            for pk, pd in hist[-5:][::-1]:
+                good = matcher.match_ratio(des, pd, 0.8)
+                fm1.compute_fundamental(kp, pk, good)
+            hist.append((kp, des))
+        for i in range(6):
+            one_frame(seq[i])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(6, nfr):
+            one_frame(seq[i])
+        single_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / (nfr - 6))
+        single = {"ms_per_frame": single_ms, "frames": nfr - 6,
+                  "calls_per_frame": "orbx_detect + orbx_compute + 5 x hamx_match_ratio + 5 x fmx_compute_fundamental, blocking, pageable host buffers"}
+        fm1.close()
+        orb1.close()
+
     # ---- secondary metric: train-sharded Hamming kNN2, Gcmp/s over all ranks
     hamming = None
     if not args.no_hamming:
@@ -423,8 +640,42 @@ def run_ours(args, rank, world, local_rank):
         t_shard = torch.randint(0, 256, (nt_shard, 32), dtype=torch.uint8, device=dev, generator=gt)
         # product exchange: peer memory (the matching kernel scatters its top-2 into every rank's gather buffer, flag-wait
         # merge); with one rank there is nothing to exchange and the plain kernel runs
+        matcher.reserve(nq, max(nt_shard * world, 200000), 1)     # no allocation (device-wide sync) inside the timed calls
         sm = ShardedMatcher(matcher, p2p=world > 1, nq_max=nq)
         out = {}
+
+        def check_sharded(mm, qs, shard, shard_rows, seed0, what):
+            """The sharded result must equal a single-device pass over the concatenation of every rank's shard (regenerated
+            here from the ranks' seeds); with one rank, a torch XOR + popcount reference on a few queries."""
+            got = mm.knn2(qs, shard, rank * shard_rows)
+            if world > 1:
+                parts = []
+                for r in range(world):
+                    g = torch.Generator(device=dev); g.manual_seed(seed0 + r)
+                    parts.append(torch.randint(0, 256, (shard_rows, 32), dtype=torch.uint8, device=dev, generator=g))
+                full = torch.cat(parts)
+                want = torch.empty_like(got)
+                matcher.set_stream(stream.cuda_stream)
+                matcher.knn2_dev(qs.data_ptr(), qs.shape[0], full.data_ptr(), full.shape[0], 0, want.data_ptr())
+                ok = bool(torch.equal(got, want))
+            else:
+                lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int32, device=dev)
+                sub = qs[:32]
+                dist = lut[(sub[:, None, :] ^ shard[None, :, :]).long()].sum(-1)                       # [32, nt]
+                key = dist.long() * (1 << 32) + torch.arange(shard.shape[0], device=dev)[None, :]
+                k2 = torch.topk(key, 2, dim=1, largest=False).values
+                want = torch.stack([k2[:, 0] >> 32, k2[:, 0] & 0xFFFFFFFF, k2[:, 1] >> 32, k2[:, 1] & 0xFFFFFFFF], 1).int()
+                ok = bool(torch.equal(got[:32], want))
+            t = torch.tensor([1 if ok else 0], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) != 1:
+                print("bench.py: %s: the train-sharded top-2 differs from the single-device pass (rank %d ok=%s)" % (what, rank, ok), file=sys.stderr)
+                if world > 1:
+                    dist.barrier()
+                sys.exit(3)
+            return True
+        parity_ok = check_sharded(sm, q[:4096].contiguous(), t_shard, nt_shard, 60, "config 5 (%d x %d per GPU)" % (nq, nt_shard))
 
         def step_ham():
             out["r"] = sm.knn2(q, t_shard, rank * nt_shard)
@@ -452,11 +703,21 @@ def run_ours(args, rank, world, local_rank):
             variants["nccl_all_gather"] = ShardedMatcher(matcher, p2p=False)
         mvf = {"nq": 2000, "nt_total": m_nt * world, "unit": "us per call (device time, max over ranks)"}
         for name, mm in variants.items():
+            parity_ok = check_sharded(mm, mq, m_shard, m_nt, 90, "config 4 (%s)" % name) and parity_ok
             def step_mvf():
                 out["m"] = mm.knn2(mq, m_shard, rank * m_nt)
             mvf_ms, _ = timed(step_mvf, 50, 5)
             mvf[name] = max_over_ranks(mvf_ms) / 50 * 1e3
         hamming["map_vs_frame"] = mvf
+        hamming["parity_ok"] = parity_ok
+        hamming["parity_check"] = ("sharded top-2 (4096 / 2000 queries) == hamx_knn2_dev over the concatenation of all ranks' shards, regenerated "
+                                   "from their seeds on every rank" if world > 1 else "first 32 queries == torch XOR + popcount + topk over the shard")
+        # flat scalars for the driver's record (it keeps scalars inside `roofline` only)
+        roofline.update({"hamming_gcmp_s": gcmp, "hamming_ms_per_step": ham_ms, "hamming_frac_algorithmic": gcmp * 8 / (gpopc * world),
+                         "hamming_frac_popc_pipe": gcmp * 5 / (gpopc * world), "hamming_popc_peak_gpopc_s_per_gpu": gpopc,
+                         "hamming_sm_mhz": ham_sampler.summary().get("sm_mhz"),
+                         "hamming_parity_ok": 1 if parity_ok else 0,
+                         "mvf_us_peer": mvf.get("peer_memory", mvf.get("single_gpu")), "mvf_us_nccl": mvf.get("nccl_all_gather")})
         sm.close()
 
     # ---- the next stage of the reference after matching: computeFundamentalMatrix for every matched pair,
@@ -575,12 +836,12 @@ def run_ours(args, rank, world, local_rank):
                 fundamental["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
         fm.close()
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores -- the same B frames the GPU step
+    # processes, dealt to one single-threaded cv2 process per core; plus the two thread settings BASELINE.md asks for
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
-            ref = CpuReference(frames_per_worker=2)
-            ref.step()
+            ref = CpuReference(B)
             n, dt = 0, 0.0
             for _ in range(2):
                 a, b = ref.step()
@@ -589,6 +850,8 @@ def run_ours(args, rank, world, local_rank):
             ref.close()
             cpu = ref.describe()
             cpu.update({"value": n / dt, "unit": "frames/s"})
+            cpu.update({"ref_" + k: v for k, v in ref.stats.items()})
+            cpu.update(cpu_thread_settings())
         except Exception as e:   # the baseline is reporting only; never fail the GPU measurement for it
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
@@ -602,28 +865,44 @@ def run_ours(args, rank, world, local_rank):
         halves = 1
     launches_per_step = 1 + halves * ((len(ws) - 1) + 4) + 3
     if rank == 0:
+        assert level_px == level_pixels()
+        cfg = workload_config(world, B)
+        cfg.update({"keypoints_per_frame": float(counts.mean()), "matches_per_frame": float(ngood_dev[1:].mean())})
+        e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_ms / args.steps,
+               "timing": "host wall clock around orbx_submit_batch / orbx_wait_batch (%d batches in flight, drained before the clock stops)" % depth + ", max over ranks",
+               "blocking_value": blk_value, "blocking_ms_per_step": blk_ms / args.steps,
+               "blocking_note": "orbx_extract_batch + orbx_match_consecutive, each call returns with its results in host memory",
+               # the same bytes as plain pinned copies in the same run, every rank at once: what the box's PCIe path allows
+               "h2d_floor_ms": h2d_floor_ms, "d2h_floor_ms": d2h_floor_ms, "h2d_floor_gbs_per_gpu": h2d / (h2d_floor_ms * 1e-3) / 1e9,
+               "over_h2d_floor": (e2e_ms / args.steps) / h2d_floor_ms,
+               "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None)}
+        if single:
+            e2e["single_frame_ms"] = single["ms_per_frame"]
+        if cfg3:
+            e2e["cfg3_e2e_fps"] = cfg3["e2e"]["value"]
+            roofline["cfg3_fps"] = cfg3["value"]
+        if sustained:
+            roofline.update({"sustained_fps": sustained["value"], "sustained_seconds": sustained["seconds"],
+                             "sustained_sm_mhz": sustained["clocks"].get("sm_mhz")})
+        if natural:
+            roofline.update({"natural_fps": natural["value"], "natural_fast_ms": natural["stages_ms_per_step"]["fast"],
+                             "dense_fast_ms": stages["fast"]})
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": "synthetic %dx%d monocular sequence, %d kp/frame, consecutive-frame matching, ratio 0.75 (BASELINE.json configs[%d])"
-                                       % (W, H, NFEAT, 1 if (W, H, NFEAT) == (1920, 1080, 2000) else 2),
-                           "frame_w": W, "frame_h": H, "nfeatures": NFEAT, "nlevels": 8, "scale_factor": 1.2, "score_type": "HARRIS",
-                           "batch_frames_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
-                           "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None),
-                           "l2": "inputs larger than L2: %d frames x %.1f MB = %.0f MB of frames (+%.0f MB of pyramid levels) per step vs 126 MB L2"
-                                 % (B, W * H / 1e6, B * W * H / 1e6, B * (level_px - W * H) / 1e6),
-                           "keypoints_per_frame": float(counts.mean()), "matches_per_frame": float(ngood_dev[1:].mean())},
+                "config": cfg,
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps,
-                        "timing": "host wall clock around orbx_submit_batch / orbx_wait_batch (%d batches in flight, drained before the clock stops)" % depth + ", max over ranks",
-                        "blocking_value": blk_value, "blocking_ms_per_step": blk_ms / args.steps,
-                        "blocking_note": "orbx_extract_batch + orbx_match_consecutive, each call returns with its results in host memory"},
+                "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": roofline,
                 "roofline_pyramid": roofline_pyramid,
                 "stages_ms_per_step": dict(stages, match=match_ms, profiled_step=prof_ms / args.steps),
                 "cpu_baseline": cpu,
+                "sustained": sustained,
+                "natural_images": natural,
+                "config3": cfg3,
+                "single_frame": single,
                 "hamming": hamming,
                 "fundamental": fundamental}
         emit(line)
@@ -664,6 +943,10 @@ def main():
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-fundamental", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-natural", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--frame", default="1920x1080", help="frame size WxH (default: BASELINE.json configs[1]; 3840x2160 with --nfeatures 8000 is configs[2])")
     ap.add_argument("--nfeatures", type=int, default=2000)
     args = ap.parse_args()

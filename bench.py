@@ -834,7 +834,121 @@ def run_ours(args, rank, world, local_rank):
                     pass
             except Exception as e:
                 fundamental["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
+        # ---- the consumer of the filter's status masks: triangulation of every inlier of every pair,
+        # TriangulateSinglePointFromTwoView (src/CameraPoseEstimator.cpp:86-132) one thread per correspondence
+        if not args.no_triangulation:
+            from monocular_slam_b200 import CAMERAS_DTYPE, Triangulator
+            tri = Triangulator(device=local_rank)
+            tri.set_stream(stream.cuda_stream)
+            a = 0.05
+            K = np.array([[900.0, 0, W / 2], [0, 900.0, H / 2], [0, 0, 1]])       # the cameras synthetic.two_view_matches projects with
+            R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+            cam = np.zeros(fpairs, CAMERAS_DTYPE)
+            cam["Rt1"], cam["Rt2"], cam["K1"], cam["K2"] = np.c_[np.eye(3), np.zeros(3)], np.c_[R, np.array([0.4, 0.05, 0.1])], K, K
+            d_cam = torch.from_numpy(cam.view(np.float64).reshape(fpairs, 42)).to(dev)
+            tX = torch.zeros((fpairs, fn, 3), dtype=torch.float64, device=dev)
+            tF = torch.zeros((fpairs, fn), dtype=torch.uint8, device=dev)
+            tN = torch.zeros(fpairs, dtype=torch.int32, device=dev)
+
+            def step_tri():
+                tri.triangulate_batch_dev(fd1.data_ptr(), fd2.data_ptr(), fdc.data_ptr(), fds.data_ptr(), fpairs, fn, d_cam.data_ptr(), 1,
+                                          tX.data_ptr(), tF.data_ptr(), tN.data_ptr())
+            tri_ms = max_over_ranks(timed(step_tri, args.steps, args.warmup)[0]) / args.steps
+            npts = int(fds.sum().item())
+            nfront = int(tN.sum().item())
+            hsel = fds.cpu().numpy()
+
+            def tri_host():
+                return tri.triangulate_batch(hp1, hp2, fcounts, cam, select=hsel)
+            tri_host()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                hX, hFr, hN = tri_host()
+            tri_host_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+            assert int(hN.sum()) == nfront, "host and device paths of the triangulation disagree"
+            triangulation = {"value": world * npts / (tri_ms * 1e-3) / 1e6, "unit": "Mpoints/s", "ms_per_step": tri_ms,
+                             "workload": "the %d pairs of the fundamental leg: every RANSAC inlier triangulated (%d points per GPU and step, %d in front of both cameras)"
+                                         % (fpairs, npts, nfront),
+                             "e2e": {"value": world * npts / (tri_host_ms * 1e-3) / 1e6, "unit": "Mpoints/s", "ms_per_step": tri_host_ms,
+                                     "h2d_bytes_per_step": int(2 * p1.nbytes + fcounts.nbytes + hsel.nbytes + cam.nbytes),
+                                     "d2h_bytes_per_step": int(fpairs * fn * 25 + fpairs * 4),
+                                     "timing": "host wall clock around trx_triangulate_batch (pageable numpy buffers), max over ranks"}}
+            if world == 1 and not args.no_cpu:
+                try:
+                    import oracle
+                    ns = 16
+                    t0 = time.perf_counter()
+                    for i in range(ns):
+                        sel = hsel[i, :fn] > 0
+                        oracle.triangulate(p1[i][sel].astype(np.float64), p2[i][sel].astype(np.float64), cam[i]["Rt1"], cam[i]["Rt2"], K, K)
+                    o_s = time.perf_counter() - t0
+                    pts = int(hsel[:ns].sum())
+                    triangulation["cpu_baseline"] = {"value": pts / o_s / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+                                                     "sample": "oracle/tri_oracle.c on the inliers of the first %d pairs, one thread" % ns}
+                    try:
+                        import cv2
+                        cv2.setNumThreads(1)
+                        P1, P2 = K @ cam[0]["Rt1"], K @ cam[0]["Rt2"]
+                        t0 = time.perf_counter()
+                        for i in range(ns):
+                            sel = hsel[i, :fn] > 0
+                            cv2.triangulatePoints(P1, P2, p1[i][sel].astype(np.float64).T.copy(), p2[i][sel].astype(np.float64).T.copy())
+                        c_s = time.perf_counter() - t0
+                        triangulation["cpu_baseline_cv2"] = {"value": pts / c_s / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "reference",
+                                                             "sample": "cv2 %s triangulatePoints (the same per-point 4x4 cv::SVD) on the same points, one thread" % cv2.__version__}
+                    except ImportError:
+                        pass
+                except Exception as e:
+                    triangulation["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
+            tri.close()
+            fundamental["triangulation"] = triangulation
+            roofline.update({"tri_mpoints_s": triangulation["value"], "tri_ms_per_step": tri_ms})
         fm.close()
+
+    # ---- loop-closure candidate scoring: the current frame's descriptors against 1000 stored frames of
+    # 2000 descriptors in one launch (LoopCloser::DetectLoop, src/LoopCloser.cpp:19-51); stored frames sharded by frame over
+    # the ranks (fixed total: strong scaling), per-frame scores exchanged with one all-gather
+    loop = None
+    if not args.no_loop:
+        from monocular_slam_b200.sharded import ShardedLoopScorer
+        lf_total, lcap, lnq, ln, lthr = 1000, 2000, 2000, 10, 40
+        lb = shard_bounds(lf_total, world)
+        llo, lhi = int(lb[rank]), int(lb[rank + 1])
+        gl = torch.Generator(device=dev); gl.manual_seed(17)
+        lq = torch.randint(0, 256, (lnq, 32), dtype=torch.uint8, device=dev, generator=gl)
+        gs = torch.Generator(device=dev); gs.manual_seed(1700 + rank)
+        lframes = torch.randint(0, 256, (lhi - llo, lcap, 32), dtype=torch.uint8, device=dev, generator=gs)
+        lcounts = torch.full((lhi - llo,), lcap, dtype=torch.int32, device=dev)
+        revisit = 617                                   # one stored frame is a noisy copy of the current one
+        if llo <= revisit < lhi:
+            lframes[revisit - llo, :lnq] = lq
+            lframes[revisit - llo, :lnq, 5] ^= 0x0F
+        scorer = ShardedLoopScorer(matcher, n=ln, thr=lthr)
+        lout = {}
+
+        def step_loop():
+            lout["r"] = scorer.score(lq, lframes, lcounts, lf_total)
+        loop_ms = max_over_ranks(timed(step_loop, 5, 2)[0]) / 5
+        lscores, lbest = lout["r"]
+        assert int(lbest[0]) == revisit and int(lbest[1]) == lnq, "loop scoring did not find the revisited frame"
+        loop = {"value": lnq * lcap * lf_total / (loop_ms * 1e-3) / 1e9, "unit": "Gcmp/s", "ms_per_query_frame": loop_ms,
+                "workload": "%d descriptors of the current frame x %d stored frames x %d descriptors, n-best = %d, threshold %d bits; frames "
+                            "sharded over %d GPU(s), 4-byte scores all-gathered" % (lnq, lf_total, lcap, ln, lthr, world),
+                "best_frame": int(lbest[0]), "stored_descriptor_mb": lf_total * lcap * 32 / 1e6}
+        if world == 1 and not args.no_cpu:
+            try:
+                import oracle
+                ns = 2
+                t0 = time.perf_counter()
+                oracle.loop_score(lq.cpu().numpy(), lframes[:ns].cpu().numpy(), np.full(ns, lcap, np.int32), ln, lthr)
+                o_s = time.perf_counter() - t0
+                loop["cpu_baseline"] = {"value": lnq * lcap * ns / o_s / 1e9, "unit": "Gcmp/s", "cores": 1, "kind": "port",
+                                        "sample": "oracle/loop_oracle.c (NBestMatches lists + count) on the first %d stored frames, one thread" % ns}
+            except Exception as e:
+                loop["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
+        roofline.update({"loop_gcmp_s": loop["value"], "loop_ms_per_query_frame": loop_ms})
+        del lframes
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores -- the same B frames the GPU step
     # processes, dealt to one single-threaded cv2 process per core; plus the two thread settings BASELINE.md asks for
@@ -904,7 +1018,8 @@ def run_ours(args, rank, world, local_rank):
                 "config3": cfg3,
                 "single_frame": single,
                 "hamming": hamming,
-                "fundamental": fundamental}
+                "fundamental": fundamental,
+                "loop_closure": loop}
         emit(line)
     matcher.close()
     orb.close()
@@ -947,6 +1062,8 @@ def main():
     ap.add_argument("--no-natural", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true")
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--no-triangulation", action="store_true")
+    ap.add_argument("--no-loop", action="store_true")
     ap.add_argument("--frame", default="1920x1080", help="frame size WxH (default: BASELINE.json configs[1]; 3840x2160 with --nfeatures 8000 is configs[2])")
     ap.add_argument("--nfeatures", type=int, default=2000)
     args = ap.parse_args()

@@ -242,6 +242,25 @@ ORBX_API int hamx_knn2_p2p_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, co
 ORBX_API int hamx_knn2_p2p_scatter_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset);
 ORBX_API int hamx_p2p_merge_dev(hamx_handle h, int64_t nq, hamx_top2* d_out);
 
+/* Loop-closure candidate scoring (reference src/LoopCloser.cpp:19-105, "as the authors intended": the
+ * distance is the 256-bit Hamming distance the reference defines for ORB descriptors, ThirdParty/DBoW2/DBoW2/FORB.cpp:81-101,
+ * instead of a float norm over CV_8U rows, and thr is a number of bits).
+ *   hamx_nbest[_dev]      = LoopCloser::NBestMatches(descriptors1, descriptors2, n, distances, indices) (:53-105): for every
+ *                           query row the n (<= 16) best train rows, ascending, filled by the reference's own insertion rule
+ *                           (ties: see csrc/hamming.cu k_nbest); dist / idx are [nq][n], absent entries -1.
+ *   hamx_loop_score[_dev] = the loop of LoopCloser::DetectLoop (:30-47): the current frame's descriptors against nframes
+ *                           stored frames ([nframes][cap][32] bytes, counts[f] rows valid) in ONE launch; scores[f] = number
+ *                           of n-best distances below thr, best = the first frame with the strictly largest non-zero score
+ *                           (-1: none).  d_best (may be NULL) receives {frame, score}.
+ *   hamx_loop_best_dev    = that arg-max alone, e.g. over scores gathered from several GPUs (stored frames sharded by frame). */
+ORBX_API int hamx_nbest(hamx_handle h, const uint8_t* q, int nq, const uint8_t* t, int nt, int n, int32_t* dist, int32_t* idx);
+ORBX_API int hamx_nbest_dev(hamx_handle h, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int n, int32_t* d_dist, int32_t* d_idx);
+ORBX_API int hamx_loop_score(hamx_handle h, const uint8_t* q, int nq, const uint8_t* frames, const int32_t* counts, int nframes, int cap, int n,
+                    int thr, int32_t* scores, int32_t* best_frame);
+ORBX_API int hamx_loop_score_dev(hamx_handle h, const uint8_t* d_q, int nq, const uint8_t* d_frames, const int32_t* d_counts, int nframes, int cap,
+                        int n, int thr, int32_t* d_scores, int32_t* d_best);
+ORBX_API int hamx_loop_best_dev(hamx_handle h, const int32_t* d_scores, int nframes, int32_t* d_best);
+
 /* Register-only popcount microbenchmark: the measured integer-pipe peak used as the matcher's roofline denominator.
  * gpopc_per_s = 32-bit POPC results per second / 1e9, over the whole device. */
 ORBX_API int hamx_popc_peak(int device, double* gpopc_per_s, double* elapsed_ms);
@@ -313,6 +332,68 @@ ORBX_API int orbx_submit_batch_back(orbx_handle h, hamx_handle m, fmx_handle fm,
                            int h_, size_t stride, float ratio, orbx_keypoint* out, uint8_t* desc, int cap, int32_t* counts,
                            orbx_dmatch* good, int64_t* ngood, double max_distance, double confidence, uint8_t* status, double* F,
                            int32_t* ninliers);
+
+/* ------------------------------------------------------------------ triangulation and map-point association
+ * The consumers of the filtered match lists, batched on the device so that the lists need not leave it:
+ *   TriangulateSinglePointFromTwoView / TriangulateMultiplePointsFromTwoView     src/CameraPoseEstimator.cpp:86-152
+ *   the bootstrap's test of the four [R|t] candidates by points in front         src/CameraPoseEstimator.cpp:334-349
+ *   the association loop of pnpPoseEstimation                                    src/CameraPoseEstimator.cpp:402-455
+ *   the new-map-point loop                                                       src/CameraPoseEstimator.cpp:488-512
+ * X is the dehomogenised null direction of the reference's 4x4 system (cv::SVD in the reference, a one-sided Jacobi SVD in
+ * double here: X agrees with OpenCV to ~1e-14 relative on well-posed pairs; the parity tests ask for 1e-9); the
+ * front-of-both-cameras flags and their counts are identical.  All matrices are row-major doubles. */
+typedef struct trx_context* trx_handle;
+/* the Rt1, Rt2 (3x4), K1, K2 (3x3) arguments of :86-88 for one problem */
+typedef struct { double Rt1[12], Rt2[12], K1[9], K2[9]; } trx_cameras;
+
+ORBX_API int trx_create(trx_handle* out, int device);
+ORBX_API int trx_destroy(trx_handle h);
+ORBX_API int trx_set_stream(trx_handle h, void* cuda_stream);     /* same rules as hamx_set_stream */
+ORBX_API int trx_get_stream(trx_handle h, void** cuda_stream);
+ORBX_API int trx_synchronize(trx_handle h);
+/* TriangulateMultiplePointsFromTwoView(pts1, pts2, Rt1, Rt2, K1, K2, result, countFront = true): pts are n x 2 doubles
+ * (vector<Point2d>), X receives n x 3 doubles (vector<Point3d>), front n bytes (may be NULL), *nfront the return value. */
+ORBX_API int trx_triangulate(trx_handle h, const double* pts1, const double* pts2, int n, const double* Rt1, const double* Rt2, const double* K1,
+                    const double* K2, double* X, uint8_t* front, int32_t* nfront);
+/* The loop at :334-349: the same correspondences under nhyp candidate [R|t] for the second view (Rts: nhyp x 12).  counts[i] =
+ * points in front under candidate i, *best = the first maximum (`if (maxCount < count)`), X (may be NULL) = the points of the
+ * winner. */
+ORBX_API int trx_triangulate_hypotheses(trx_handle h, const double* pts1, const double* pts2, int n, const double* Rt1, const double* Rts, int nhyp,
+                               const double* K1, const double* K2, double* X, int32_t* counts, int32_t* best);
+/* nprob problems in one launch, nhyp camera hypotheses each (cams is [nprob][nhyp]).  pts1 / pts2: [nprob][cap][2] float
+ * (keypoint positions are float; the reference widens them to double, src/FeatureExtractor.cpp:20-22), counts[p] of them
+ * valid; select (may be NULL) [nprob][cap]: only entries with a non-zero byte are triangulated (e.g. the RANSAC status).
+ * X [nprob][nhyp][cap][3], front [nprob][nhyp][cap], nfront [nprob][nhyp]; best (may be NULL) [nprob].  Entries that are
+ * not triangulated get X = 0, front = 0. */
+ORBX_API int trx_triangulate_batch(trx_handle h, const float* pts1, const float* pts2, const int32_t* counts, const uint8_t* select, int nprob,
+                          int cap, const trx_cameras* cams, int nhyp, double* X, uint8_t* front, int32_t* nfront, int32_t* best);
+ORBX_API int trx_triangulate_batch_dev(trx_handle h, const float* d_pts1, const float* d_pts2, const int32_t* d_counts, const uint8_t* d_select,
+                              int nprob, int cap, const trx_cameras* d_cams, int nhyp, double* d_X, uint8_t* d_front, int32_t* d_nfront,
+                              int32_t* d_best);
+/* Sequence mode on the device, fed by hamx_match_back_dev / fmx_filter_back_dev: pair (f, j) at index f*back + j-1 joins,
+ * for every match of its list with a non-zero d_select byte (NULL: all), keypoint train_idx of frame f-j as view 1 and
+ * keypoint query_idx of frame f as view 2 (the argument order of :504-506); d_cams[f*back + j-1] holds the two cameras.
+ * X [nframes*back][cap][3], front [nframes*back][cap], nfront [nframes*back]. */
+ORBX_API int trx_triangulate_back_dev(trx_handle h, const orbx_keypoint* d_kps, int nframes, int cap, int back, const orbx_keypoint* d_hist_kps,
+                             int nhist, const orbx_dmatch* d_good, const int64_t* d_ngood, const uint8_t* d_select, const trx_cameras* d_cams,
+                             double* d_X, uint8_t* d_front, int32_t* d_nfront);
+/* The association loop (:402-455) for nprob independent current frames.  Problem p has `back` match lists: list l (the
+ * matches against predecessor l, most recent first) at d_good + (p*back + l)*cap with d_ngood[p*back + l] entries, of which
+ * only those with a non-zero d_status byte take part (NULL: all; the FILTERING_WITH_F block :412-424 drops the others), and
+ * d_premap[(p*back + l)*cap + t] = map-point index of the predecessor's feature t, -1 for none.  d_ncur[p] = features of the
+ * current frame.  Outputs: d_cur_map [nprob][cap] = the map point each current feature inherits (-1: none),
+ * d_assoc_q / d_assoc_mp [nprob][cap] = the associations (current feature, map point) in the order the reference makes
+ * them -- the order of mapPoints / imagePoints handed to solvePnPRansac (:447-449, :472) -- and d_nassoc[p] their number. */
+ORBX_API int trx_associate_dev(trx_handle h, const orbx_dmatch* d_good, const int64_t* d_ngood, const uint8_t* d_status, const int32_t* d_premap,
+                      const int32_t* d_ncur, int nprob, int back, int cap, int32_t* d_cur_map, int32_t* d_assoc_q, int32_t* d_assoc_mp,
+                      int32_t* d_nassoc);
+/* The new-map-point loop (:488-512) over the same lists: d_accept [nprob][back][cap] marks the matches the reference
+ * triangulates (both features without a map point when the sequential walk reaches them); d_premap and d_cur_map are
+ * updated in place the way registerNewMapPoint does (:235-243), new indices counted from d_next_id[p] (NULL: 0) in the order
+ * of the walk; d_nnew[p] = number of new points.  Feed d_accept to trx_triangulate_back_dev as d_select. */
+ORBX_API int trx_select_new_dev(trx_handle h, const orbx_dmatch* d_good, const int64_t* d_ngood, const uint8_t* d_status, int32_t* d_premap,
+                       int32_t* d_cur_map, const int32_t* d_ncur, const int32_t* d_next_id, int nprob, int back, int cap,
+                       uint8_t* d_accept, int32_t* d_nnew);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,8 @@
 //   src/FeatureExtractor.cpp:17,19    detector.detect(frameBuffer, keypoints);  extractor.compute(frameBuffer, keypoints, descriptor);
 //   src/CameraPoseEstimator.cpp:200-213   static void matchFeatures(const Mat&, const Mat&, vector<DMatch>&, float ratio = 0.8)
 //                                          { BFMatcher matcher(NORM_HAMMING, false); matcher.knnMatch(d1, d2, raw, 2); ... }
+//   src/CameraPoseEstimator.cpp:545-586   static void computeFundamentalMatrix(positions1, positions2, matches, ..., F, status)
+//   src/CameraPoseEstimator.cpp:134-152   static int TriangulateMultiplePointsFromTwoView(pts1, pts2, Rt1, Rt2, K1, K2, result, countFront)
 //
 // Without OpenCV headers (this image has none) the POD mirrors below stand in for cv::KeyPoint / cv::DMatch / cv::Mat;
 // define ORBX_SHIM_USE_OPENCV before including to bind to the real cv types instead (same memory layouts:
@@ -36,6 +38,7 @@ using cv::KeyPoint;
 using cv::Mat;
 using cv::NORM_HAMMING;
 using cv::Point2d;
+using cv::Point3d;
 static inline const uint8_t* mat_ptr(const Mat& m) { return m.data; }
 static inline void mat_create_u8(Mat& m, int rows, int cols) { m.create(rows, cols, CV_8UC1); }
 static inline size_t mat_step(const Mat& m) { return m.step; }
@@ -44,6 +47,7 @@ static inline int mat_channels(const Mat& m) { return m.channels(); }
 enum { NORM_HAMMING = 6 };
 struct Point2f { float x, y; };
 struct Point2d { double x, y; };
+struct Point3d { double x, y, z; };
 struct KeyPoint {               // field order and size of cv::KeyPoint (28 bytes)
     Point2f pt; float size, angle, response; int octave, class_id;
 };
@@ -73,6 +77,7 @@ static inline int mat_channels(const Mat& m) { return m.nchannels; }
 
 static_assert(sizeof(KeyPoint) == sizeof(orbx_keypoint), "KeyPoint must have cv::KeyPoint's layout");
 static_assert(sizeof(DMatch) == sizeof(orbx_dmatch), "DMatch must have cv::DMatch's layout");
+static_assert(sizeof(Point2d) == 16 && sizeof(Point3d) == 24, "Point2d / Point3d must be packed doubles");
 
 struct Error : std::runtime_error {
     int status;
@@ -201,7 +206,7 @@ public:
         for (int i = 0; i < query.rows; i++)
             for (int j = 0; j < counts[(size_t)i]; j++) {
                 DMatch m;
-                std::memcpy(&m, &flat[(size_t)2 * i + j], sizeof(m));
+                std::memcpy(static_cast<void*>(&m), &flat[(size_t)2 * i + j], sizeof(m));   // same layout (static_assert above)
                 matches[(size_t)i].push_back(m);
             }
     }
@@ -213,7 +218,7 @@ public:
         int64_t n = 0;
         check(hamx_match_ratio(h_, mat_ptr(d1), d1.rows, mat_ptr(d2), d2.rows, ratio, good.data(), &n), "BFMatcher::matchRatio");
         matches.resize((size_t)n);
-        if (n) std::memcpy(matches.data(), good.data(), (size_t)n * sizeof(DMatch));
+        if (n) std::memcpy(static_cast<void*>(matches.data()), good.data(), (size_t)n * sizeof(DMatch));
     }
 
     hamx_handle handle() { return h_; }
@@ -301,6 +306,70 @@ static inline void computeFundamentalMatrix(const std::vector<Point2d>& position
     computeFundamentalMatrix(positions1, positions2, matches, inlierPositions1, inlierPositions2, f, status);
     F.create(3, 3, CV_64F);
     std::memcpy(F.data, f, sizeof(f));
+}
+#endif
+
+// TriangulateMultiplePointsFromTwoView (src/CameraPoseEstimator.cpp:134-152) and the four-candidate test built on it
+// (:334-349), on the GPU (trx_triangulate / trx_triangulate_hypotheses).  Rt are 3x4, K 3x3, row-major doubles.
+class Triangulator {
+public:
+    explicit Triangulator(int device = 0) : h_(nullptr) { check(trx_create(&h_, device), "Triangulator"); }
+    ~Triangulator() { if (h_) trx_destroy(h_); }
+    Triangulator(const Triangulator&) = delete;
+    Triangulator& operator=(const Triangulator&) = delete;
+
+    int triangulate(const std::vector<Point2d>& pts1, const std::vector<Point2d>& pts2, const double* Rt1, const double* Rt2,
+                    const double* K1, const double* K2, std::vector<Point3d>& result, bool countFront)
+    {
+        if (pts1.size() != pts2.size()) throw Error(ORBX_E_INVALID, "TriangulateMultiplePointsFromTwoView: pts1 and pts2 differ in length");
+        result.assign(pts1.size(), Point3d());
+        int32_t nfront = 0;
+        check(trx_triangulate(h_, reinterpret_cast<const double*>(pts1.data()), reinterpret_cast<const double*>(pts2.data()), (int)pts1.size(),
+                              Rt1, Rt2, K1, K2, reinterpret_cast<double*>(result.data()), nullptr, &nfront),
+              "TriangulateMultiplePointsFromTwoView");
+        return countFront ? (int)nfront : 0;       // the reference returns 0 unless asked to count (:150-151)
+    }
+    // index of the candidate with the most points in front (first maximum), its points in `result`, all counts in `counts`
+    int bestHypothesis(const std::vector<Point2d>& pts1, const std::vector<Point2d>& pts2, const double* Rt1, const double* Rts, int nhyp,
+                       const double* K1, const double* K2, std::vector<Point3d>& result, std::vector<int>& counts)
+    {
+        if (pts1.size() != pts2.size()) throw Error(ORBX_E_INVALID, "bestHypothesis: pts1 and pts2 differ in length");
+        result.assign(pts1.size(), Point3d());
+        std::vector<int32_t> c((size_t)nhyp);
+        int32_t best = -1;
+        check(trx_triangulate_hypotheses(h_, reinterpret_cast<const double*>(pts1.data()), reinterpret_cast<const double*>(pts2.data()),
+                                         (int)pts1.size(), Rt1, Rts, nhyp, K1, K2, reinterpret_cast<double*>(result.data()), c.data(), &best),
+              "bestHypothesis");
+        counts.assign(c.begin(), c.end());
+        return (int)best;
+    }
+    trx_handle handle() { return h_; }
+
+private:
+    trx_handle h_;
+};
+
+static inline int TriangulateMultiplePointsFromTwoView(const std::vector<Point2d>& pts1, const std::vector<Point2d>& pts2, const double* Rt1,
+                                                       const double* Rt2, const double* K1, const double* K2, std::vector<Point3d>& result,
+                                                       bool countFront = false)
+{
+    static thread_local Triangulator t;          // one per host thread, kept: see threadMatcher()
+    return t.triangulate(pts1, pts2, Rt1, Rt2, K1, K2, result, countFront);
+}
+#ifdef ORBX_SHIM_USE_OPENCV
+// the reference's own argument list (const Mat& Rt1, Rt2, K1, K2: CV_64F, 3x4 and 3x3)
+static inline const double* mat_f64(const Mat& m, int rows, int cols, const char* what)
+{
+    if (m.rows != rows || m.cols != cols || m.channels() != 1 || m.elemSize() != 8 || (size_t)m.step != (size_t)cols * 8)
+        throw Error(ORBX_E_INVALID, std::string(what) + ": expected a continuous CV_64F matrix");
+    return reinterpret_cast<const double*>(m.data);
+}
+static inline int TriangulateMultiplePointsFromTwoView(const std::vector<Point2d>& pts1, const std::vector<Point2d>& pts2, const Mat& Rt1,
+                                                       const Mat& Rt2, const Mat& K1, const Mat& K2, std::vector<Point3d>& result,
+                                                       bool countFront = false)
+{
+    return TriangulateMultiplePointsFromTwoView(pts1, pts2, mat_f64(Rt1, 3, 4, "Rt1"), mat_f64(Rt2, 3, 4, "Rt2"), mat_f64(K1, 3, 3, "K1"),
+                                                mat_f64(K2, 3, 3, "K2"), result, countFront);
 }
 #endif
 

@@ -5,6 +5,6 @@ Only the hot path named by BASELINE.json is here: csrc/ holds the sm_100a CUDA k
 path over the GPUs of one box; synthetic.py generates the benchmark inputs.  Nothing in this package runs the
 algorithm on the CPU.
 """
-from ._lib import (DMATCH_DTYPE, FAST_SCORE, HARRIS_SCORE, KEYPOINT_DTYPE, LIB_PATH, TOP2_DTYPE, OrbxError, Params, build)  # noqa: F401
+from ._lib import (CAMERAS_DTYPE, DMATCH_DTYPE, FAST_SCORE, HARRIS_SCORE, KEYPOINT_DTYPE, LIB_PATH, TOP2_DTYPE, OrbxError, Params, build)  # noqa: F401
 from .orb import (NORM_HAMMING, ORB, BFMatcher, DataManager, FeatureExtractor, Features, Frame, FundamentalFilter,  # noqa: F401
-                  ORB_create, OrbDescriptorExtractor, OrbFeatureDetector, match_features, popc_peak)
+                  ORB_create, OrbDescriptorExtractor, OrbFeatureDetector, Triangulator, match_features, popc_peak)

@@ -520,6 +520,158 @@ __global__ void k_update_history(const uint8_t* desc, const int32_t* counts, int
     for (int i = threadIdx.x; i < n * 2; i += blockDim.x) b[i] = a[i];
 }
 
+// ---- loop-closure candidate scoring (LoopCloser::DetectLoop / NBestMatches, reference src/LoopCloser.cpp:19-105) ---------
+// Every thread walks the train rows [0, nt) of one set in ascending order through the same TMA ring as k_hamming_knn2 and
+// calls row(j, a, b) for each (a, b = the two halves of train row j; the same row for all threads of the CTA).
+template <class Row>
+__device__ __forceinline__ void ham_stream_rows(const uint4* __restrict__ t, int nt, uint4 (*s_tile)[HT_TT * 2], uint64_t* s_full, Row row)
+{
+    const int tid = threadIdx.x;
+    const int ntiles = (nt + HT_TT - 1) / HT_TT;
+    if (tid == 0) {
+        for (int s = 0; s < HT_STAGES; s++) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int i) {
+        const int rows = min(HT_TT, nt - i * HT_TT);
+        const uint32_t bytes = (uint32_t)rows * 32u;
+        const int st = i % HT_STAGES;
+        mbar_expect_tx(&s_full[st], bytes);
+        tma_bulk_g2s(&s_tile[st][0], t + (size_t)i * HT_TT * 2, bytes, &s_full[st]);
+    };
+    if (tid == 0)
+        for (int i = 0; i < HT_STAGES && i < ntiles; i++) issue(i);
+    for (int i = 0; i < ntiles; i++) {
+        const int st = i % HT_STAGES;
+        mbar_wait(&s_full[st], (uint32_t)(i / HT_STAGES) & 1u);
+        const uint4* ts = &s_tile[st][0];
+        const int rows = min(HT_TT, nt - i * HT_TT);
+        if (rows == HT_TT) {
+#pragma unroll 4
+            for (int j = 0; j < HT_TT; j++) row(i * HT_TT + j, ts[2 * j], ts[2 * j + 1]);
+        } else {
+            for (int j = 0; j < rows; j++) row(i * HT_TT + j, ts[2 * j], ts[2 * j + 1]);
+        }
+        __syncthreads();
+        if (tid == 0 && i + HT_STAGES < ntiles) issue(i + HT_STAGES);
+    }
+}
+
+// DetectLoop's score of one stored frame (:34-41) is the number of n-best distances below the threshold, summed over the
+// current frame's descriptors.  The n best distances of a query are its n smallest, so that number is
+// min(n, #{train rows closer than thr}) -- no list has to be built (tests/test_oracle_tri.py checks the identity against the
+// literal lists).  grid = (query blocks, stored frames); a CTA counts for 256 queries in registers, clips, reduces and adds
+// its sum to the frame's score.
+__global__ void __launch_bounds__(HT_THREADS)
+k_loop_score(const uint8_t* __restrict__ q_, int nq, const uint8_t* __restrict__ frames, const int32_t* __restrict__ counts, int cap, int nbest,
+             uint32_t thr, int32_t* __restrict__ scores)
+{
+    __shared__ __align__(128) uint4 s_tile[HT_STAGES][HT_TT * 2];
+    __shared__ __align__(8) uint64_t s_full[HT_STAGES];
+    __shared__ int s_sum;
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int nt = min(counts[f], cap);
+    if (nt <= 0) return;
+    if (tid == 0) s_sum = 0;
+    const uint4* __restrict__ q = reinterpret_cast<const uint4*>(q_);
+    uint32_t qr[HT_QPT][8];
+    uint32_t cnt[HT_QPT];
+    bool live[HT_QPT];
+#pragma unroll
+    for (int k = 0; k < HT_QPT; k++) {
+        const int qi = blockIdx.x * HT_QB + k * HT_THREADS + tid;
+        live[k] = qi < nq;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (live[k]) { lo = q[2 * (size_t)qi]; hi = q[2 * (size_t)qi + 1]; }
+        qr[k][0] = lo.x; qr[k][1] = lo.y; qr[k][2] = lo.z; qr[k][3] = lo.w;
+        qr[k][4] = hi.x; qr[k][5] = hi.y; qr[k][6] = hi.z; qr[k][7] = hi.w;
+        cnt[k] = 0;
+    }
+    ham_stream_rows(reinterpret_cast<const uint4*>(frames + (size_t)f * cap * 32), nt, s_tile, s_full, [&](int, const uint4& a, const uint4& b) {
+#pragma unroll
+        for (int k = 0; k < HT_QPT; k++) cnt[k] += ham256(qr[k], a, b) < thr ? 1u : 0u;
+    });
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < HT_QPT; k++) sum += live[k] ? (int)min(cnt[k], (uint32_t)nbest) : 0;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if ((tid & 31) == 0 && sum) atomicAdd(&s_sum, sum);
+    __syncthreads();
+    if (tid == 0 && s_sum) atomicAdd(&scores[f], s_sum);
+}
+
+// :42-46 -- `if (count > count_max)` with count_max starting at 0: the first frame with the strictly largest non-zero score.
+// best[0] = that frame (-1: every score is zero), best[1] = its score.
+__global__ void __launch_bounds__(256) k_loop_best(const int32_t* __restrict__ scores, int nframes, int32_t* __restrict__ best)
+{
+    __shared__ unsigned long long s_key[256];
+    // larger score wins, then the LOWER index: key = score << 32 | ~index, maximised
+    unsigned long long key = 0;
+    for (int i = threadIdx.x; i < nframes; i += blockDim.x) {
+        const int sc = scores[i];
+        if (sc > 0) {
+            const unsigned long long k = ((unsigned long long)(uint32_t)sc << 32) | (uint32_t)~(uint32_t)i;
+            key = k > key ? k : key;
+        }
+    }
+    s_key[threadIdx.x] = key;
+    __syncthreads();
+    for (int d = 128; d >= 1; d >>= 1) {
+        if (threadIdx.x < d) { const unsigned long long o = s_key[threadIdx.x + d]; if (o > s_key[threadIdx.x]) s_key[threadIdx.x] = o; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long k = s_key[0];
+        best[0] = k ? (int32_t)~(uint32_t)(k & 0xFFFFFFFFu) : -1;
+        best[1] = (int32_t)(k >> 32);
+    }
+}
+
+// NBestMatches itself (:53-105): one thread per query walks the train rows in order and inserts each candidate exactly like
+// the reference -- it takes the first slot whose distance it is strictly below and the displaced entry is carried down
+// under the same strict test (:86-101).  Among equal distances that is not the lexicographic order of k_hamming_knn2 (a
+// displaced entry skips its equals and may be the one that drops out), so the insertion is reproduced literally rather
+// than through packed keys; a candidate that is not below the last slot cannot enter and is skipped.
+template <int N>
+__global__ void __launch_bounds__(HT_THREADS)
+k_nbest(const uint8_t* __restrict__ q_, int nq, const uint8_t* __restrict__ t_, int nt, int n, int32_t* __restrict__ dist, int32_t* __restrict__ idx)
+{
+    __shared__ __align__(128) uint4 s_tile[HT_STAGES][HT_TT * 2];
+    __shared__ __align__(8) uint64_t s_full[HT_STAGES];
+    const int qi = blockIdx.x * HT_THREADS + threadIdx.x;
+    const uint4* __restrict__ q = reinterpret_cast<const uint4*>(q_);
+    uint32_t qr[8];
+    {
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (qi < nq) { lo = q[2 * (size_t)qi]; hi = q[2 * (size_t)qi + 1]; }
+        qr[0] = lo.x; qr[1] = lo.y; qr[2] = lo.z; qr[3] = lo.w; qr[4] = hi.x; qr[5] = hi.y; qr[6] = hi.z; qr[7] = hi.w;
+    }
+    int32_t cd[N], ci[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) { cd[k] = 0x7FFFFFFF; ci[k] = -1; }
+    ham_stream_rows(reinterpret_cast<const uint4*>(t_), nt, s_tile, s_full, [&](int j, const uint4& a, const uint4& b) {
+        int32_t d = (int32_t)ham256(qr, a, b), c = j;
+        if (d < cd[N - 1]) {
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                const bool lt = d < cd[k];
+                const int32_t od = cd[k], oi = ci[k];
+                cd[k] = lt ? d : od; ci[k] = lt ? c : oi;
+                d = lt ? od : d; c = lt ? oi : c;
+            }
+        }
+    });
+    if (qi >= nq) return;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        if (k < n) {
+            dist[(size_t)qi * n + k] = ci[k] < 0 ? -1 : cd[k];
+            idx[(size_t)qi * n + k] = ci[k];
+        }
+}
+
 // Register-only POPC throughput probe: 8 independent POPC + 8 XOR per iteration and thread, like the matcher's inner
 // loop without its memory traffic.
 __global__ void __launch_bounds__(1024) k_popc_peak(uint32_t* sink, int iters, uint32_t seed)
@@ -903,6 +1055,102 @@ extern "C" int hamx_match_ratio(hamx_handle h, const uint8_t* q, int64_t nq, con
     if (n) ORBX_CUDA(cudaMemcpyAsync(good, h->d_dm, (size_t)n * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     *ngood = n;
+    return ORBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ loop-closure scoring
+extern "C" int hamx_loop_score_dev(hamx_handle h, const uint8_t* d_q, int nq, const uint8_t* d_frames, const int32_t* d_counts, int nframes, int cap,
+                                   int n, int thr, int32_t* d_scores, int32_t* d_best)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_loop_score_dev: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nframes >= 0 && nframes <= 65535 && cap >= 1 && n >= 1 && thr >= 0, "hamx_loop_score_dev: bad sizes (nframes <= 65535 per call)");
+    ORBX_REQUIRE(d_scores != nullptr || nframes == 0, "hamx_loop_score_dev: NULL output");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    if (nframes) ORBX_CUDA(cudaMemsetAsync(d_scores, 0, (size_t)nframes * sizeof(int32_t), h->stream));
+    if (nframes && nq) {
+        ORBX_REQUIRE(d_q && d_frames && d_counts, "hamx_loop_score_dev: NULL pointer");
+        if ((((uintptr_t)d_q) | ((uintptr_t)d_frames)) & 15) { set_error("hamx_loop_score_dev: descriptor pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
+        const dim3 grid((unsigned)((nq + HT_QB - 1) / HT_QB), (unsigned)nframes);
+        k_loop_score<<<grid, HT_THREADS, 0, h->stream>>>(d_q, nq, d_frames, d_counts, cap, n, (uint32_t)thr, d_scores);
+        ORBX_CUDA(cudaGetLastError());
+    }
+    if (d_best) return hamx_loop_best_dev(h, d_scores, nframes, d_best);
+    return ORBX_OK;
+}
+
+extern "C" int hamx_loop_best_dev(hamx_handle h, const int32_t* d_scores, int nframes, int32_t* d_best)
+{
+    ORBX_REQUIRE(h != nullptr && d_best != nullptr && nframes >= 0 && (nframes == 0 || d_scores), "hamx_loop_best_dev: bad arguments");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    k_loop_best<<<1, 256, 0, h->stream>>>(d_scores, nframes, d_best);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int hamx_nbest_dev(hamx_handle h, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int n, int32_t* d_dist, int32_t* d_idx)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_nbest_dev: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nt >= 0 && n >= 1 && n <= 16, "hamx_nbest_dev: bad sizes (1 <= n <= 16)");
+    if (nq == 0) return ORBX_OK;
+    ORBX_REQUIRE(d_q && d_dist && d_idx && (nt == 0 || d_t), "hamx_nbest_dev: NULL pointer");
+    if ((((uintptr_t)d_q) | ((uintptr_t)d_t)) & 15) { set_error("hamx_nbest_dev: descriptor pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const unsigned int blocks = (unsigned int)((nq + HT_THREADS - 1) / HT_THREADS);
+    if (n <= 4) k_nbest<4><<<blocks, HT_THREADS, 0, h->stream>>>(d_q, nq, d_t, nt, n, d_dist, d_idx);
+    else if (n <= 10) k_nbest<10><<<blocks, HT_THREADS, 0, h->stream>>>(d_q, nq, d_t, nt, n, d_dist, d_idx);
+    else k_nbest<16><<<blocks, HT_THREADS, 0, h->stream>>>(d_q, nq, d_t, nt, n, d_dist, d_idx);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// Host-buffer form of LoopCloser::DetectLoop's scoring: descriptors of the current frame against nframes stored frames.
+extern "C" int hamx_loop_score(hamx_handle h, const uint8_t* q, int nq, const uint8_t* frames, const int32_t* counts, int nframes, int cap, int n,
+                               int thr, int32_t* scores, int32_t* best_frame)
+{
+    ORBX_REQUIRE(h != nullptr && best_frame != nullptr, "hamx_loop_score: NULL argument");
+    ORBX_REQUIRE(nq >= 0 && nframes >= 0 && cap >= 1, "hamx_loop_score: bad sizes");
+    *best_frame = -1;
+    if (nframes == 0) return ORBX_OK;
+    ORBX_REQUIRE(scores && counts && frames && (nq == 0 || q), "hamx_loop_score: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int rc = grow(&h->d_q, &h->q_bytes, (size_t)nq * 32 + 32);
+    if (!rc) rc = grow(&h->d_t, &h->t_bytes, (size_t)nframes * cap * 32 + 32);
+    if (!rc) rc = grow(&h->d_counts, &h->counts_bytes, ((size_t)2 * nframes + 2) * sizeof(int32_t));
+    if (rc) return rc;
+    int32_t* d_cnt = h->d_counts;
+    int32_t* d_sc = h->d_counts + nframes;
+    if (nq) ORBX_CUDA(cudaMemcpyAsync(h->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_t, frames, (size_t)nframes * cap * 32, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(d_cnt, counts, (size_t)nframes * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int32_t* d_best = reinterpret_cast<int32_t*>(h->d_ngood);       // 8 bytes: {frame, score}
+    rc = hamx_loop_score_dev(h, h->d_q, nq, h->d_t, d_cnt, nframes, cap, n, thr, d_sc, d_best);
+    if (rc) return rc;
+    int32_t best[2] = { -1, 0 };
+    ORBX_CUDA(cudaMemcpyAsync(scores, d_sc, (size_t)nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(best, d_best, sizeof(best), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    *best_frame = best[0];
+    return ORBX_OK;
+}
+
+// NBestMatches(descriptors1, descriptors2, n, distances, indices) on host buffers.
+extern "C" int hamx_nbest(hamx_handle h, const uint8_t* q, int nq, const uint8_t* t, int nt, int n, int32_t* dist, int32_t* idx)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_nbest: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nt >= 0 && n >= 1 && n <= 16, "hamx_nbest: bad sizes (1 <= n <= 16)");
+    if (nq == 0) return ORBX_OK;
+    ORBX_REQUIRE(q && dist && idx && (nt == 0 || t), "hamx_nbest: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int rc = upload_sets(h, q, nq, t, nt);
+    if (!rc) rc = grow(&h->d_dm, &h->dm_bytes, (size_t)nq * n * 2 * sizeof(int32_t));
+    if (rc) return rc;
+    int32_t* d_dist = reinterpret_cast<int32_t*>(h->d_dm);
+    int32_t* d_idx = d_dist + (size_t)nq * n;
+    rc = hamx_nbest_dev(h, h->d_q, nq, h->d_t, nt, n, d_dist, d_idx);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(dist, d_dist, (size_t)nq * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(idx, d_idx, (size_t)nq * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
     return ORBX_OK;
 }
 

@@ -412,6 +412,40 @@ class BFMatcher:
                                           C.byref(n)))
         return good[:n.value].copy()
 
+    # -- loop-closure candidate scoring (src/LoopCloser.cpp:19-105 with the Hamming distance)
+    def NBestMatches(self, descriptors1, descriptors2, n=10):
+        """LoopCloser::NBestMatches: (distances[nq, n] int32, indices[nq, n] int32), ascending, absent entries -1."""
+        q, t = self._desc(descriptors1), self._desc(descriptors2)
+        dist = np.full((len(q), n), -1, np.int32)
+        idx = np.full((len(q), n), -1, np.int32)
+        check(_lib.lib().hamx_nbest(self._h, q.ctypes.data, len(q), t.ctypes.data, len(t), int(n), dist.ctypes.data, idx.ctypes.data))
+        return dist, idx
+
+    def loop_score(self, descriptors1, frames_desc, frame_counts, n=10, thr=40):
+        """The loop of LoopCloser::DetectLoop over all stored frames in one launch: frames_desc uint8 [nframes, cap, 32],
+        frame_counts [nframes].  Returns (scores[nframes] int32, best frame or -1)."""
+        q = self._desc(descriptors1)
+        fd = np.ascontiguousarray(frames_desc, np.uint8)
+        if fd.ndim != 3 or fd.shape[2] != 32:
+            raise ValueError("frames_desc must be [nframes, cap, 32] uint8")
+        fc = np.ascontiguousarray(frame_counts, np.int32)
+        if fc.shape != (fd.shape[0],):
+            raise ValueError("frame_counts must be [nframes]")
+        scores = np.zeros(max(fd.shape[0], 1), np.int32)
+        best = C.c_int32(-1)
+        check(_lib.lib().hamx_loop_score(self._h, q.ctypes.data, len(q), fd.ctypes.data, fc.ctypes.data, fd.shape[0], max(fd.shape[1], 1), int(n),
+                                         int(thr), scores.ctypes.data, C.byref(best)))
+        return scores[:fd.shape[0]], int(best.value)
+
+    def loop_score_dev(self, d_q, nq, d_frames, d_counts, nframes, cap, n, thr, d_scores, d_best=0):
+        check(_lib.lib().hamx_loop_score_dev(self._h, d_q, nq, d_frames, d_counts, nframes, cap, int(n), int(thr), d_scores, d_best or None))
+
+    def loop_best_dev(self, d_scores, nframes, d_best):
+        check(_lib.lib().hamx_loop_best_dev(self._h, d_scores, nframes, d_best))
+
+    def nbest_dev(self, d_q, nq, d_t, nt, n, d_dist, d_idx):
+        check(_lib.lib().hamx_nbest_dev(self._h, d_q, nq, d_t, nt, int(n), d_dist, d_idx))
+
     # device-resident pieces (raw device pointers; asynchronous on the handle's stream)
     def knn2_dev(self, d_q, nq, d_t, nt, train_offset, d_out):
         check(_lib.lib().hamx_knn2_dev(self._h, d_q, nq, d_t, nt, train_offset, d_out))
@@ -542,6 +576,123 @@ class FundamentalFilter:
     def find_batch_dev(self, d_pts1, d_pts2, d_counts, npairs, cap, max_distance, confidence, d_status, d_F, d_info):
         check(_lib.lib().fmx_fundamental_batch_dev(self._h, d_pts1, d_pts2, d_counts, npairs, cap, float(max_distance),
                                                    float(confidence), d_status, d_F, d_info))
+
+
+class Triangulator:
+    """The consumers of the match lists in CameraPoseEstimator, on the device (include/orbx.h "trx_*"):
+    TriangulateMultiplePointsFromTwoView (src/CameraPoseEstimator.cpp:134-152), the bootstrap's four-hypothesis test
+    (:334-349), the association loop (:402-455) and the new-map-point loop (:488-512)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self.device = device
+        check(_lib.lib().trx_create(C.byref(self._h), device))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().trx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(_lib.lib().trx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(_lib.lib().trx_synchronize(self._h))
+
+    @staticmethod
+    def _mat(a, shape):
+        a = np.ascontiguousarray(a, np.float64)
+        if a.shape != shape:
+            raise ValueError("expected a %s matrix, got %s" % (shape, a.shape))
+        return a
+
+    def TriangulateMultiplePointsFromTwoView(self, pts1, pts2, Rt1, Rt2, K1, K2, countFront=False):
+        """The reference's routine: pts n x 2 (Point2d), Rt 3x4, K 3x3.  Returns (result[n, 3] Point3d, count) with count = 0
+        unless countFront, exactly like :134-152."""
+        X, front, n = self.triangulate(pts1, pts2, Rt1, Rt2, K1, K2)
+        return X, (n if countFront else 0)
+
+    def triangulate(self, pts1, pts2, Rt1, Rt2, K1, K2):
+        """(X[n, 3], front[n] uint8, number in front of both cameras)."""
+        p1 = np.ascontiguousarray(pts1, np.float64).reshape(-1, 2)
+        p2 = np.ascontiguousarray(pts2, np.float64).reshape(-1, 2)
+        if p1.shape != p2.shape:
+            raise ValueError("pts1 and pts2 must have the same length")
+        n = len(p1)
+        X = np.zeros((n, 3), np.float64)
+        front = np.zeros(max(n, 1), np.uint8)
+        nf = C.c_int32(0)
+        check(_lib.lib().trx_triangulate(self._h, p1.ctypes.data, p2.ctypes.data, n, self._mat(Rt1, (3, 4)).ctypes.data,
+                                         self._mat(Rt2, (3, 4)).ctypes.data, self._mat(K1, (3, 3)).ctypes.data,
+                                         self._mat(K2, (3, 3)).ctypes.data, X.ctypes.data, front.ctypes.data, C.byref(nf)))
+        return X, front[:n], int(nf.value)
+
+    def triangulate_hypotheses(self, pts1, pts2, Rt1, Rts, K1, K2):
+        """The loop at :334-349: (best index, counts[nhyp], X[n, 3] of the winner)."""
+        p1 = np.ascontiguousarray(pts1, np.float64).reshape(-1, 2)
+        p2 = np.ascontiguousarray(pts2, np.float64).reshape(-1, 2)
+        R = np.ascontiguousarray(Rts, np.float64)
+        if R.ndim != 3 or R.shape[1:] != (3, 4):
+            raise ValueError("Rts must be [nhyp, 3, 4]")
+        n, nh = len(p1), R.shape[0]
+        X = np.zeros((max(n, 1), 3), np.float64)
+        counts = np.zeros(nh, np.int32)
+        best = C.c_int32(-1)
+        check(_lib.lib().trx_triangulate_hypotheses(self._h, p1.ctypes.data, p2.ctypes.data, n, self._mat(Rt1, (3, 4)).ctypes.data,
+                                                    R.ctypes.data, nh, self._mat(K1, (3, 3)).ctypes.data, self._mat(K2, (3, 3)).ctypes.data,
+                                                    X.ctypes.data, counts.ctypes.data, C.byref(best)))
+        return int(best.value), counts, X[:n]
+
+    def triangulate_batch(self, pts1, pts2, counts, cams, select=None, want_best=False):
+        """nprob problems x nhyp hypotheses: pts float32 [nprob, cap, 2], counts int32 [nprob], cams CAMERAS_DTYPE [nprob, nhyp]
+        (or [nprob]), select uint8 [nprob, cap] or None.  Returns (X[nprob, nhyp, cap, 3], front[nprob, nhyp, cap], nfront[nprob, nhyp]
+        [, best[nprob]])."""
+        p1 = np.ascontiguousarray(pts1, np.float32)
+        p2 = np.ascontiguousarray(pts2, np.float32)
+        cnt = np.ascontiguousarray(counts, np.int32)
+        cm = np.ascontiguousarray(cams, _lib.CAMERAS_DTYPE)
+        nprob, cap = p1.shape[0], p1.shape[1]
+        if cm.ndim == 1:
+            cm = cm.reshape(nprob, 1)
+        nh = cm.shape[1]
+        if p1.shape != p2.shape or p1.ndim != 3 or p1.shape[2] != 2 or cnt.shape != (nprob,) or cm.shape[0] != nprob:
+            raise ValueError("pts1 / pts2 must be [nprob, cap, 2], counts [nprob], cams [nprob(, nhyp)]")
+        sel = None
+        if select is not None:
+            sel = np.ascontiguousarray(select, np.uint8)
+            if sel.shape != (nprob, cap):
+                raise ValueError("select must be [nprob, cap]")
+        X = np.zeros((nprob, nh, cap, 3), np.float64)
+        front = np.zeros((nprob, nh, cap), np.uint8)
+        nfront = np.zeros((nprob, nh), np.int32)
+        best = np.zeros(nprob, np.int32) if want_best else None
+        check(_lib.lib().trx_triangulate_batch(self._h, p1.ctypes.data, p2.ctypes.data, cnt.ctypes.data, sel.ctypes.data if sel is not None else None,
+                                               nprob, cap, cm.ctypes.data, nh, X.ctypes.data, front.ctypes.data, nfront.ctypes.data,
+                                               best.ctypes.data if want_best else None))
+        return (X, front, nfront, best) if want_best else (X, front, nfront)
+
+    # device-resident pieces (raw device pointers; asynchronous on the handle's stream)
+    def triangulate_batch_dev(self, d_pts1, d_pts2, d_counts, d_select, nprob, cap, d_cams, nhyp, d_X, d_front, d_nfront, d_best=None):
+        check(_lib.lib().trx_triangulate_batch_dev(self._h, d_pts1, d_pts2, d_counts, d_select or None, nprob, cap, d_cams, nhyp, d_X, d_front,
+                                                   d_nfront, d_best or None))
+
+    def triangulate_back_dev(self, d_kps, nframes, cap, back, d_hist_kps, nhist, d_good, d_ngood, d_select, d_cams, d_X, d_front, d_nfront):
+        check(_lib.lib().trx_triangulate_back_dev(self._h, d_kps, nframes, cap, back, d_hist_kps or None, nhist, d_good, d_ngood,
+                                                  d_select or None, d_cams, d_X, d_front, d_nfront))
+
+    def associate_dev(self, d_good, d_ngood, d_status, d_premap, d_ncur, nprob, back, cap, d_cur_map, d_assoc_q, d_assoc_mp, d_nassoc):
+        check(_lib.lib().trx_associate_dev(self._h, d_good, d_ngood, d_status or None, d_premap, d_ncur, nprob, back, cap, d_cur_map,
+                                           d_assoc_q, d_assoc_mp, d_nassoc))
+
+    def select_new_dev(self, d_good, d_ngood, d_status, d_premap, d_cur_map, d_ncur, d_next_id, nprob, back, cap, d_accept, d_nnew):
+        check(_lib.lib().trx_select_new_dev(self._h, d_good, d_ngood, d_status or None, d_premap, d_cur_map, d_ncur, d_next_id or None,
+                                            nprob, back, cap, d_accept, d_nnew))
 
 
 def popc_peak(device=0):

@@ -213,3 +213,72 @@ class ShardedMatcher:
         b = shard_bounds(t_full.shape[0], self.world)
         lo, hi = int(b[self.rank]), int(b[self.rank + 1])
         return self.knn2(q, t_full[lo:hi].contiguous(), lo)
+
+
+class ShardedLoopScorer:
+    """Loop-closure candidate scoring (LoopCloser::DetectLoop, src/LoopCloser.cpp:19-51) with the stored frames sharded BY
+    FRAME over the ranks: every rank scores its own contiguous block of frames against the (replicated) descriptors of the
+    current frame in one launch, the per-frame scores -- 4 bytes per stored frame -- are exchanged with one all-gather, and
+    every rank takes the same arg-max (first frame with the strictly largest non-zero score).  The scores of different
+    frames are independent, so the result equals a single-device pass over all frames.
+
+    ``local_scores(q, frames, counts) -> int32 tensor [nlocal]`` and ``best(scores) -> (frame, score)`` default to the CUDA
+    kernels of a ``BFMatcher``; stand-ins can be injected to exercise the exchange on CPU (gloo)."""
+
+    def __init__(self, matcher=None, n=10, thr=40, group=None, local_scores=None, best=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.matcher, self.n, self.thr = matcher, int(n), int(thr)
+        self._local = local_scores or self._local_cuda
+        self._best = best or self._best_cuda
+        if matcher is None and (local_scores is None or best is None):
+            raise ValueError("ShardedLoopScorer needs a BFMatcher (CUDA); there is no CPU implementation in this package")
+
+    def _stream(self):
+        import torch
+        s = torch.cuda.current_stream().cuda_stream
+        if s == 0:
+            raise RuntimeError("run ShardedLoopScorer under a non-default torch stream")
+        self.matcher.set_stream(s)
+
+    def _local_cuda(self, q, frames, counts):
+        import torch
+        self._stream()
+        scores = torch.empty(max(frames.shape[0], 1), dtype=torch.int32, device=q.device)
+        self.matcher.loop_score_dev(q.data_ptr(), q.shape[0], frames.data_ptr(), counts.data_ptr(), frames.shape[0], frames.shape[1],
+                                    self.n, self.thr, scores.data_ptr())
+        return scores[:frames.shape[0]]
+
+    def _best_cuda(self, scores):
+        import torch
+        self._stream()
+        out = torch.empty(2, dtype=torch.int32, device=scores.device)
+        self.matcher.loop_best_dev(scores.data_ptr(), scores.shape[0], out.data_ptr())
+        return out
+
+    def score(self, q, frames_shard, counts_shard, nframes_total):
+        """q [nq, 32] uint8 (replicated); frames_shard [nlocal, cap, 32] / counts_shard [nlocal]: this rank's block
+        ``shard_bounds(nframes_total, world)``.  Returns (scores[nframes_total] int32 tensor, best[2] = {frame, score})."""
+        import torch
+        b = shard_bounds(nframes_total, self.world)
+        lo, hi = int(b[self.rank]), int(b[self.rank + 1])
+        if frames_shard.shape[0] != hi - lo:
+            raise ValueError("rank %d owns frames [%d, %d) but was given %d" % (self.rank, lo, hi, frames_shard.shape[0]))
+        local = self._local(q, frames_shard, counts_shard)
+        if self.world == 1:
+            return local, self._best(local)
+        width = int((b[1:] - b[:-1]).max())
+        padded = torch.zeros(width, dtype=torch.int32, device=local.device)
+        padded[:hi - lo] = local
+        if self.dist.get_backend(self.group) == "gloo" and padded.is_cuda:
+            # plumbing fallback (several ranks on one GPU in the tests: NCCL refuses that): 4 bytes per frame through the host
+            parts = [torch.empty(width, dtype=torch.int32) for _ in range(self.world)]
+            self.dist.all_gather(parts, padded.cpu(), group=self.group)
+            flat = torch.cat(parts).to(local.device)
+        else:
+            flat = torch.empty(self.world * width, dtype=torch.int32, device=local.device)
+            self.dist.all_gather_into_tensor(flat, padded, group=self.group)
+        scores = torch.cat([flat[r * width:r * width + int(b[r + 1] - b[r])] for r in range(self.world)])
+        return scores, self._best(scores)

@@ -45,7 +45,7 @@ class Params(C.Structure):
 
 def build(force=False):
     """Compile liborb_oracle.so with the committed Makefile (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "fmat_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "fmat_oracle.c", "tri_oracle.c", "loop_oracle.c")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -95,6 +95,13 @@ def lib():
         L.orc_fm_ransac.argtypes = [f32p, f32p, C.c_int, C.c_double, C.c_double, C.c_int, u8p, f64p, i32p]
         L.orc_compute_fundamental.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                               u8p, f64p]
+        L.orc_triangulate.argtypes = [f64p, f64p, C.c_int, f64p, f64p, f64p, f64p, f64p, u8p]
+        L.orc_triangulate_best.argtypes = [f64p, f64p, C.c_int, f64p, f64p, C.c_int, f64p, f64p, f64p, i32p]
+        L.orc_associate.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, i32p, C.c_int, i32p, i32p, i32p]
+        L.orc_select_new.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, i32p, i32p, C.c_int32, u8p]
+        L.orc_nbest.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, i32p, i32p]
+        L.orc_nbest.restype = None
+        L.orc_loop_score.argtypes = [u8p, C.c_int, u8p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
         _lib = L
     return _lib
 
@@ -348,3 +355,90 @@ def compute_fundamental(pos1, pos2, matches, thr=3.0, conf=0.85):
     ninl = lib().orc_compute_fundamental(_f32(pos1), 2, _f32(pos2), 2, matches.ctypes.data, nm, float(thr), float(conf),
                                          _u8(status), _f64(F))
     return F.reshape(3, 3), status[:nm], int(ninl)
+
+
+# ------------------------------------------------------------------------------------------------ triangulation / association
+def _d(a, shape=None):
+    a = np.ascontiguousarray(a, np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def triangulate(pts1, pts2, Rt1, Rt2, K1, K2):
+    """TriangulateMultiplePointsFromTwoView (src/CameraPoseEstimator.cpp:134-152) with countFront: (X[n,3], front[n] uint8, count)."""
+    p1, pp1 = _d(pts1)
+    p2, pp2 = _d(pts2)
+    n = len(p1)
+    X = np.zeros((n, 3), np.float64)
+    front = np.zeros(max(n, 1), np.uint8)
+    cnt = lib().orc_triangulate(pp1, pp2, n, _d(Rt1, 12)[1], _d(Rt2, 12)[1], _d(K1, 9)[1], _d(K2, 9)[1],
+                                X.ctypes.data_as(C.POINTER(C.c_double)), _u8(front))
+    return X, front[:n], int(cnt)
+
+
+def triangulate_best(pts1, pts2, Rt1, Rts, K1, K2):
+    """The four-hypothesis test of the bootstrap (src/CameraPoseEstimator.cpp:334-349): (best index, counts[nhyp], X of the winner)."""
+    p1, pp1 = _d(pts1)
+    p2, pp2 = _d(pts2)
+    R, pR = _d(Rts)
+    nh = R.size // 12
+    n = len(p1)
+    X = np.zeros((n, 3), np.float64)
+    counts = np.zeros(nh, np.int32)
+    best = lib().orc_triangulate_best(pp1, pp2, n, _d(Rt1, 12)[1], pR, nh, _d(K1, 9)[1], _d(K2, 9)[1],
+                                      X.ctypes.data_as(C.POINTER(C.c_double)), _i32(counts))
+    return int(best), counts, X
+
+
+_DMATCH = np.dtype([("query_idx", "<i4"), ("train_idx", "<i4"), ("img_idx", "<i4"), ("distance", "<f4")])
+
+
+def associate(matches, counts, premap, ncur):
+    """The association loop (src/CameraPoseEstimator.cpp:402-455) of one frame: matches [back, cap] DMatch (inliers only),
+    counts [back], premap [back, cap] int32.  Returns (cur_map[ncur], assoc_q[k], assoc_mp[k])."""
+    m = np.ascontiguousarray(matches, _DMATCH)
+    back, cap = m.shape
+    n = np.ascontiguousarray(counts, np.int32)
+    pm = np.ascontiguousarray(premap, np.int32)
+    assert pm.shape == (back, cap)
+    cur = np.zeros(max(ncur, 1), np.int32)
+    aq, amp = np.zeros(max(ncur, 1), np.int32), np.zeros(max(ncur, 1), np.int32)
+    k = lib().orc_associate(m.ctypes.data, _i32(n), back, cap, _i32(pm), ncur, _i32(cur), _i32(aq), _i32(amp))
+    return cur[:ncur], aq[:k], amp[:k]
+
+
+def select_new(matches, counts, premap, cur_map, next_id=0):
+    """The new-map-point loop (src/CameraPoseEstimator.cpp:488-512): returns (accept[back, cap] uint8, premap', cur_map', n_new)."""
+    m = np.ascontiguousarray(matches, _DMATCH)
+    back, cap = m.shape
+    n = np.ascontiguousarray(counts, np.int32)
+    pm = np.array(premap, np.int32, copy=True)
+    cm = np.array(cur_map, np.int32, copy=True)
+    acc = np.zeros((back, cap), np.uint8)
+    k = lib().orc_select_new(m.ctypes.data, _i32(n), back, cap, _i32(pm), _i32(cm), int(next_id), _u8(acc))
+    return acc, pm, cm, int(k)
+
+
+# ------------------------------------------------------------------------------------------------ loop-closure scoring
+def nbest(d1, d2, n=10):
+    """LoopCloser::NBestMatches (src/LoopCloser.cpp:53-105) with the Hamming distance: (dist[nq, n] int32, idx[nq, n] int32),
+    ascending, absent entries (fewer than n train rows) dist = -1 / idx = -1."""
+    q, t = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+    dist = np.zeros((len(q), n), np.int32)
+    idx = np.zeros((len(q), n), np.int32)
+    if len(q):
+        lib().orc_nbest(_u8(q), len(q), _u8(t), len(t), n, _i32(dist), _i32(idx))
+    return dist, idx
+
+
+def loop_score(d1, frames_desc, frame_counts, n=10, thr=40):
+    """LoopCloser::DetectLoop's scoring (src/LoopCloser.cpp:19-51): for every stored frame the number of n-best distances
+    below thr; returns (counts[nframes] int32, index of the first maximum or -1)."""
+    q = np.ascontiguousarray(d1, np.uint8)
+    fd = np.ascontiguousarray(frames_desc, np.uint8)
+    nf, cap = fd.shape[0], fd.shape[1]
+    fc = np.ascontiguousarray(frame_counts, np.int32)
+    counts = np.zeros(max(nf, 1), np.int32)
+    best = lib().orc_loop_score(_u8(q), len(q), _u8(fd), _i32(fc), nf, cap, n, thr, _i32(counts))
+    return counts[:nf], int(best)

@@ -1,7 +1,12 @@
-"""Multi-process check of the train-sharded matcher on real GPUs (run under torchrun, one rank per GPU):
-peer-memory (fused scatter + flag-wait merge) and NCCL all-gather exchanges must both equal a single-device pass.
-Launched by tests/test_gpu_multi.py when the box has >= 2 GPUs; also usable by hand:
+"""Multi-process check of the sharded paths on real GPUs (run under torchrun, one rank per GPU):
+* train-sharded matcher: peer-memory (fused scatter + flag-wait merge) and NCCL all-gather exchanges must both equal a
+  single-device pass;
+* frame-sharded loop-closure scoring: per-frame scores and the winning frame must equal a single-device pass.
+Launched by tests/test_gpu_multi.py; also usable by hand:
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mp_sharded_check.py
+With ORBX_MP_SAME_DEVICE=1 every rank uses GPU 0 (a 1-GPU box): the processes still exchange through cudaIpc-mapped peer
+memory and device-side flags -- the kernels of the two contexts are time-sliced by the driver -- while torch.distributed
+runs over gloo (NCCL refuses two ranks on one device), so the NCCL variant and the timing loop are skipped there.
 """
 import os
 import sys
@@ -19,18 +24,27 @@ from monocular_slam_b200.sharded import ShardedMatcher, shard_bounds
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    same = os.environ.get("ORBX_MP_SAME_DEVICE", "0") == "1"
+    if same:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if same:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     m = BFMatcher(device=local)
     m.set_stream(stream.cuda_stream)
     nq_max = 70000
     p2p = ShardedMatcher(m, p2p=True, nq_max=nq_max)
-    nccl = ShardedMatcher(m, p2p=False)
-    timings = {}
-    for case, (nq, nt) in enumerate([(2000, 200000), (1, 17), (257, 1000), (65536, 100003), (2000, 200000)]):
+    nccl = None if same else ShardedMatcher(m, p2p=False)
+    timings = {"p2p": float("nan"), "nccl": float("nan")}
+    cases = [(2000, 200000), (1, 17), (257, 1000), (65536, 100003), (2000, 200000)]
+    if same:
+        cases = [(2000, 20000), (1, 17), (257, 1000), (20000, 3003)]      # time-sliced contexts: keep the spins short
+    for case, (nq, nt) in enumerate(cases):
         g = torch.Generator(device=dev)
         g.manual_seed(1000 + case)                          # same data on every rank
         q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=g)
@@ -44,12 +58,12 @@ def main():
         m.knn2_dev(q.data_ptr(), nq, t.data_ptr(), nt, 0, ref.data_ptr())
         for rep in range(3):
             a = p2p.knn2(q, shard, lo)
-            c = nccl.knn2(q, shard, lo)
+            c = nccl.knn2(q, shard, lo) if nccl is not None else ref
             stream.synchronize()
             assert torch.equal(a, ref), "rank %d case %d rep %d: peer-memory result differs from the single-device pass" % (rank, case, rep)
             assert torch.equal(c, ref), "rank %d case %d rep %d: all-gather result differs from the single-device pass" % (rank, case, rep)
         # device time of the two exchanges for the map-vs-frame shape (BASELINE config 4), max over ranks
-        if (nq, nt) == (2000, 200000):
+        if (nq, nt) == (2000, 200000) and not same:
             for name, sm in (("p2p", p2p), ("nccl", nccl)):
                 for _ in range(5):
                     sm.knn2(q, shard, lo)
@@ -66,6 +80,27 @@ def main():
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
                 timings[name] = float(ms.item())
                 print("rank %d %s %.3f us" % (rank, name, mine * 1e3), file=sys.stderr, flush=True)
+    # frame-sharded loop-closure scoring: 37 stored frames (uneven blocks) of up to 600 descriptors
+    from monocular_slam_b200.sharded import ShardedLoopScorer
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+    nf, cap, nq = 37, 600, 500
+    q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=g)
+    frames = torch.randint(0, 256, (nf, cap, 32), dtype=torch.uint8, device=dev, generator=g)
+    counts = torch.randint(0, cap + 1, (nf,), dtype=torch.int32, device=dev, generator=g)
+    for f in (9, 30):
+        frames[f, :nq] = q
+        frames[f, :nq, 0] ^= 3
+        counts[f] = cap
+    want = torch.empty(nf, dtype=torch.int32, device=dev)
+    wbest = torch.empty(2, dtype=torch.int32, device=dev)
+    m.loop_score_dev(q.data_ptr(), nq, frames.data_ptr(), counts.data_ptr(), nf, cap, 10, 40, want.data_ptr(), wbest.data_ptr())
+    b = shard_bounds(nf, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    sl = ShardedLoopScorer(m, n=10, thr=40)
+    scores, best = sl.score(q, frames[lo:hi].contiguous(), counts[lo:hi].contiguous(), nf)
+    stream.synchronize()
+    assert torch.equal(scores, want) and torch.equal(best, wbest) and int(best[0]) == 9, "rank %d: frame-sharded loop scores differ" % rank
     p2p.close()
     m.close()
     dist.barrier()

@@ -12,14 +12,36 @@ from monocular_slam_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build_demo(tmpdir, name="shim_demo"):
+def _build_demo(tmpdir, name="shim_demo", extra_includes=()):
     _lib.build()
     exe = os.path.join(str(tmpdir), name)
     libdir = os.path.dirname(_lib.LIB_PATH)
-    subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L", libdir, "-lorbx",
-                           "-Wl,-rpath," + libdir])
+    inc = []
+    for d in (os.path.join(ROOT, "include"),) + tuple(extra_includes):
+        inc += ["-I", d]
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-Werror"] + inc +
+                          [os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L", libdir, "-lorbx", "-Wl,-rpath," + libdir])
     return exe
+
+
+STUB_OPENCV = os.path.join(ROOT, "tests", "cpp", "stub_opencv")
+
+
+def test_opencv_branch_of_the_shim_compiles(tmp_path):
+    """The ORBX_SHIM_USE_OPENCV form of the shim (what a maintainer of the reference builds) against a stub of the OpenCV 2.4
+    headers; without a GPU the program must fail loudly instead of falling back."""
+    exe = _build_demo(tmp_path, "shim_opencv_demo", (STUB_OPENCV,))
+    if _lib.lib().orbx_device_count() > 0:
+        pytest.skip("a GPU is present; covered by the gpu test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_opencv_branch_of_the_shim_runs(tmp_path):
+    exe = _build_demo(tmp_path, "shim_opencv_demo", (STUB_OPENCV,))
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok:"), r.stdout + r.stderr
 
 
 def test_shim_compiles_and_fails_loudly_without_gpu(tmp_path):

@@ -101,3 +101,44 @@ def test_sharded_sequence_blocks_cpu():
             assert k == "kp%d" % f and d == "desc%d" % f
     assert sorted(seen) == list(range(nframes))
     assert seen[0] is None and all(seen[f] == f - 1 for f in range(1, nframes))
+
+
+def _loop_worker(rank, world, port, ret):
+    """Frame-sharded loop-closure scoring over gloo with the oracle standing in for the scoring kernel."""
+    from monocular_slam_b200.sharded import ShardedLoopScorer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r = np.random.default_rng(5)
+    nf, cap, nq, n, thr = 7, 40, 30, 10, 110             # 7 frames over 2 ranks: uneven blocks (4 + 3)
+    q = r.integers(0, 256, (nq, 32), dtype=np.uint8)
+    frames = r.integers(0, 256, (nf, cap, 32), dtype=np.uint8)
+    counts = np.array([40, 12, 0, 40, 33, 40, 5], np.int32)
+    frames[5, :15] = q[:15]
+    frames[3, :15] = q[:15]
+
+    def local(qt, ft, ct):
+        return torch.from_numpy(oracle.loop_score(qt.numpy(), ft.numpy(), ct.numpy(), n, thr)[0].astype(np.int32))
+
+    def best(sc):
+        s = sc.numpy()
+        return torch.tensor([int(np.argmax(s)) if s.max() > 0 else -1, int(s.max())], dtype=torch.int32)
+    b = shard_bounds(nf, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    sl = ShardedLoopScorer(matcher=None, n=n, thr=thr, local_scores=local, best=best)
+    scores, bst = sl.score(torch.from_numpy(q), torch.from_numpy(frames[lo:hi]), torch.from_numpy(counts[lo:hi]), nf)
+    want, wb = oracle.loop_score(q, frames, counts, n, thr)
+    ret[rank] = bool(np.array_equal(scores.numpy(), want) and int(bst[0]) == wb == 3)
+    dist.destroy_process_group()
+
+
+def test_frame_sharded_loop_scoring_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    oracle.build()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_loop_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -661,8 +661,8 @@ def run_ours(args, rank, world, local_rank):
             else:
                 lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int32, device=dev)
                 sub = qs[:32]
-                dist = lut[(sub[:, None, :] ^ shard[None, :, :]).long()].sum(-1)                       # [32, nt]
-                key = dist.long() * (1 << 32) + torch.arange(shard.shape[0], device=dev)[None, :]
+                dmat = lut[(sub[:, None, :] ^ shard[None, :, :]).long()].sum(-1)                       # [32, nt]
+                key = dmat.long() * (1 << 32) + torch.arange(shard.shape[0], device=dev)[None, :]
                 k2 = torch.topk(key, 2, dim=1, largest=False).values
                 want = torch.stack([k2[:, 0] >> 32, k2[:, 0] & 0xFFFFFFFF, k2[:, 1] >> 32, k2[:, 1] & 0xFFFFFFFF], 1).int()
                 ok = bool(torch.equal(got[:32], want))

@@ -148,6 +148,25 @@ def two_view_matches(seed, n, inlier_ratio=0.7, noise=0.5, size=(1920, 1080)):
     return p1.astype(np.float32), p2.astype(np.float32)
 
 
+def layered_views(seed, w, h, nviews, nlayers=4, motion=(2, 5)):
+    """``nviews`` views of the scene of ``layered_pair`` along the same sideways translation: in view v every layer is shifted
+    by v times its own multiple of ``motion``.  View 0 and view 1 are exactly ``layered_pair(seed, w, h, nlayers, motion)``
+    when nviews == 2."""
+    r = np.random.default_rng(seed)
+    dy, dx = abs(int(motion[0])), abs(int(motion[1]))
+    big = frame(seed, w + (nviews - 1) * nlayers * dx + 8, h + (nviews - 1) * nlayers * dy + 8)
+    edges = np.linspace(0, h, nlayers + 1).astype(int)
+    mult = r.permutation(np.arange(1, nlayers + 1))
+    out = np.empty((nviews, h, w), np.uint8)
+    out[0] = big[:h, :w]
+    for v in range(1, nviews):
+        for layer in range(nlayers):
+            sy, sx = v * dy * int(mult[layer]), v * dx * int(mult[layer])
+            y0, y1 = int(edges[layer]), int(edges[layer + 1])
+            out[v, y0:y1] = big[y0 + sy:y1 + sy, sx:sx + w]
+    return out
+
+
 def layered_pair(seed, w, h, nlayers=4, motion=(2, 5)):
     """Two views (h x w uint8 each) of a scene of fronto-parallel layers at different depths under a sideways camera
     translation: every layer is a horizontal band of one big texture and shifts by its own multiple of ``motion`` (dy, dx).

@@ -87,14 +87,14 @@ def test_loop_score_no_candidate_and_first_maximum(bf):
 def test_loop_score_on_orb_descriptors(bf):
     """Real descriptors: a revisited view must outscore unrelated frames, and the scores equal the oracle's."""
     from monocular_slam_b200 import ORB
-    seqa = syn.sequence(3, 640, 480, seed=41)
-    seqb = syn.sequence(3, 640, 480, seed=42)
+    seqa = syn.sequence(5, 640, 480, seed=41)          # one texture: frames 0..2 are stored, frame 4 comes back to it
+    seqb = syn.sequence(3, 640, 480, seed=42)          # another place
     orb = ORB(nfeatures=500, max_size=(640, 480), max_batch=6)
-    kps, desc, counts = orb.extract_batch(list(seqb) + list(seqa))
-    cur = orb.extract_batch([syn.sequence(5, 640, 480, seed=41)[4]])   # same texture as seqa, a few pixels further on
+    kps, desc, counts = orb.extract_batch(list(seqb) + list(seqa[:3]))
+    cur = orb.extract_batch([seqa[4]])
     q = cur[1][0, :cur[2][0]]
-    scores, best = bf.loop_score(q, desc, counts, 10, 50)
-    want, wb = oracle.loop_score(q, desc, counts, 10, 50)
+    scores, best = bf.loop_score(q, desc, counts, 10, 30)
+    want, wb = oracle.loop_score(q, desc, counts, 10, 30)
     assert np.array_equal(scores, want) and best == wb and best >= 3
-    assert scores[3:].min() > 4 * max(scores[:3].max(), 1)
+    assert scores[3:].min() > 2 * max(scores[:3].max(), 1)
     orb.close()

@@ -168,9 +168,7 @@ def test_device_chain_filter_to_triangulation(tri):
     from monocular_slam_b200 import ORB, BFMatcher, FundamentalFilter
     from monocular_slam_b200 import synthetic as syn
     dev = "cuda"
-    a, b = syn.layered_pair(4, 640, 480)
-    c = syn.layered_pair(4, 640, 480, motion=(4, 10))[1]
-    frames = np.stack([a, b, c])
+    frames = syn.layered_views(4, 640, 480, 3)
     n, back, W, H = 3, 2, 640, 480
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):

@@ -88,10 +88,12 @@ struct FrameCounters {
 };
 
 // kernel launchers (defined next to their kernels)
+// fast_hint: one int per level in device memory, written by K3 (launch_select) and read by the next K2 launch: non-zero =
+// the level is corner-dense, skip K2's compass pre-test (a speed hint; may be NULL)
 cudaError_t launch_fast(const FrameGeom& g, uint8_t* slots, size_t slot_stride, Cand* cand, size_t cand_stride,
-                        FrameCounters* ctr, int nframes, cudaStream_t s);
+                        FrameCounters* ctr, int nframes, const int32_t* fast_hint, cudaStream_t s);
 cudaError_t launch_select(const FrameGeom& g, const Cand* cand, size_t cand_stride, Cand* surv, size_t surv_stride,
-                          FrameCounters* ctr, int nframes, cudaStream_t s);
+                          FrameCounters* ctr, int nframes, int32_t* fast_hint, cudaStream_t s);
 // mode bits for launch_orient_describe
 enum { ORBX_DO_ANGLE = 1, ORBX_DO_DESC = 2 };
 cudaError_t launch_orient_describe(const FrameGeom& g, const uint8_t* slots, size_t slot_stride, const Sel* sel,

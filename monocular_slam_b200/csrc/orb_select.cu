@@ -24,13 +24,18 @@ constexpr int HS_THREADS = 512;
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_select(const __grid_constant__ FrameGeom g, const Cand* __restrict__ cand, size_t cand_stride, Cand* __restrict__ surv,
-         size_t surv_stride, FrameCounters* __restrict__ ctr)
+         size_t surv_stride, FrameCounters* __restrict__ ctr, int32_t* __restrict__ fast_hint)
 {
     __shared__ int s_thr;
     const int tid = threadIdx.x, lane = tid & 31;
     const int level = blockIdx.y, frame = blockIdx.z;
     const LevelGeom& L = g.lv[level];
     FrameCounters& C = ctr[frame];
+    // what K2 found on this level, for K2's next launch: with more than 2.5 % of the interior pixels surviving NMS (the
+    // Appendix-B stress frames: 3 %; camera-like frames: 0.1 %) its compass pre-test costs more than it saves (orb_fast.cu).
+    // A speed hint only: the scores do not depend on it.
+    if (fast_hint && frame == 0 && blockIdx.x == 0 && tid == 0)
+        fast_hint[level] = (long long)C.ncand[level] * 40 > (long long)max(L.w - 62, 0) * max(L.h - 62, 0) ? 1 : 0;
     const int n = min(C.ncand[level], L.cand_cap);
     if (n == 0) return;
     const int target = g.score_type == ORBX_HARRIS_SCORE ? 2 * L.quota : L.quota;
@@ -216,10 +221,10 @@ k_harris_select(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__
 }  // namespace
 
 cudaError_t launch_select(const FrameGeom& g, const Cand* cand, size_t cand_stride, Cand* surv, size_t surv_stride,
-                          FrameCounters* ctr, int nframes, cudaStream_t s)
+                          FrameCounters* ctr, int nframes, int32_t* fast_hint, cudaStream_t s)
 {
     dim3 grid(SEL_CHUNKS, g.nlevels, nframes);
-    k_select<<<grid, SEL_THREADS, 0, s>>>(g, cand, cand_stride, surv, surv_stride, ctr);
+    k_select<<<grid, SEL_THREADS, 0, s>>>(g, cand, cand_stride, surv, surv_stride, ctr, fast_hint);
     return cudaGetLastError();
 }
 

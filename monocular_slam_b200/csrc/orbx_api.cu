@@ -83,6 +83,7 @@ struct orbx_context {
     int32_t* d_counts;
     uint8_t* d_tab;
     size_t tab_bytes;
+    int32_t* d_fast_hint;                     // per level: corner-dense in the previous batch (K3 -> K2 speed hint)
     // pinned host memory
     FrameCounters* h_ctr;
     int32_t* h_counts;
@@ -419,6 +420,7 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
     ORBX_ALLOC(h->d_desc, B * (size_t)h->dev_cap * 32 + 256);
     ORBX_ALLOC(h->d_counts, B * sizeof(int32_t) + 256);
     ORBX_ALLOC(h->d_tab, h->tab_bytes);
+    ORBX_ALLOC(h->d_fast_hint, ORBX_MAX_LEVELS * sizeof(int32_t));
     ORBX_ALLOC(h->d_prev_desc, (size_t)h->dev_cap * 32 + 256);
     ORBX_ALLOC(h->d_prev_count, 256);
     ORBX_ALLOC(h->d_good, B * (size_t)h->dev_cap * sizeof(orbx_dmatch) + 256);
@@ -426,7 +428,8 @@ extern "C" int orbx_create(orbx_handle* out, const orbx_params* params, int devi
 #undef ORBX_ALLOC
     ORBX_CUDA_OR(cudaMallocHost((void**)&h->h_ngood, B * sizeof(int64_t)), orbx_destroy(h));
     h->events = new std::vector<cudaEvent_t>();
-    ORBX_CUDA_OR(cudaMemset(h->d_slots, 0, B * h->slot_stride), orbx_destroy(h));   // padding bytes are read (never used) by vector loads
+    ORBX_CUDA_OR(cudaMemset(h->d_slots, 0, B * h->slot_stride), orbx_destroy(h));
+    ORBX_CUDA_OR(cudaMemset(h->d_fast_hint, 0, ORBX_MAX_LEVELS * sizeof(int32_t)), orbx_destroy(h));   // padding bytes are read (never used) by vector loads
     ORBX_CUDA_OR(cudaMallocHost((void**)&h->h_ctr, B * sizeof(FrameCounters)), orbx_destroy(h));
     ORBX_CUDA_OR(cudaMallocHost((void**)&h->h_counts, B * sizeof(int32_t)), orbx_destroy(h));
     ORBX_CUDA_OR(harris_select_prepare(h->max_surv_cap), orbx_destroy(h));
@@ -441,7 +444,7 @@ extern "C" int orbx_destroy(orbx_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_graphs(h);
     cudaFree(h->d_slots); cudaFree(h->d_cand); cudaFree(h->d_surv); cudaFree(h->d_sel); cudaFree(h->d_ctr);
-    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_tab);
+    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_tab); cudaFree(h->d_fast_hint);
     cudaFree(h->d_prev_desc); cudaFree(h->d_prev_count); cudaFree(h->d_good); cudaFree(h->d_ngood); cudaFree(h->d_bgr);
     cudaFree(h->d_prev_kps[0]); cudaFree(h->d_prev_kps[1]); cudaFree(h->d_fstatus); cudaFree(h->d_fF); cudaFree(h->d_finfo);
     if (h->h_finfo) cudaFreeHost(h->h_finfo);
@@ -596,9 +599,9 @@ static int run_extract_on(orbx_handle h, int f0, int nframes, int mode, orbx_key
     for (int l = 1; l < h->g.nlevels; l++)
         ORBX_CUDA(launch_pyr_down_level(slots, h->slot_stride, h->g.lv[l - 1], h->g.lv[l], h->pyr_sw[l], h->pyr_sh[l], nframes, s));
     if (mark && (rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_fast(h->g, slots, h->slot_stride, cand, h->cand_stride, ctr, nframes, s));
+    ORBX_CUDA(launch_fast(h->g, slots, h->slot_stride, cand, h->cand_stride, ctr, nframes, h->d_fast_hint, s));
     if (mark && (rc = stage_mark(h))) return rc;
-    ORBX_CUDA(launch_select(h->g, cand, h->cand_stride, surv, h->surv_stride, ctr, nframes, s));
+    ORBX_CUDA(launch_select(h->g, cand, h->cand_stride, surv, h->surv_stride, ctr, nframes, h->d_fast_hint, s));
     if (mark && (rc = stage_mark(h))) return rc;
     ORBX_CUDA(launch_harris_select(h->g, slots, h->slot_stride, surv, h->surv_stride, sel, h->sel_stride, ctr, nframes,
                                    h->max_surv_cap, h->harris_s4, s));
@@ -1356,7 +1359,7 @@ extern "C" int orbx_debug_fast_level(orbx_handle h, const uint8_t* gray, int w, 
     ORBX_CUDA(cudaMemsetAsync(h->d_ctr, 0, sizeof(FrameCounters), h->stream));
     rc = build_pyramids(h, 0, 1);
     if (rc) return rc;
-    ORBX_CUDA(launch_fast(h->g, h->d_slots, h->slot_stride, h->d_cand, h->cand_stride, h->d_ctr, 1, h->stream));
+    ORBX_CUDA(launch_fast(h->g, h->d_slots, h->slot_stride, h->d_cand, h->cand_stride, h->d_ctr, 1, nullptr, h->stream));
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     const LevelGeom& L = h->g.lv[level];

@@ -294,3 +294,30 @@ def test_fuzz_against_oracle(case):
     assert_keypoints_equal(kps[1, :counts[1]], ok, "batch")
     assert_descriptors_equal(desc[1, :counts[1]], od, "batch")
     orb.close()
+
+
+@pytest.mark.parametrize("kind", ["dense", "natural", "flat_then_dense", "mixed"])
+def test_fast_density_paths_are_bit_exact(kind):
+    """K2 scores a group of pixels either after a compass pre-test (sparse levels) or exhaustively (levels K3 found
+    corner-dense in the previous batch, or rows in which nearly every group passes).  Which path runs depends on the
+    image content and on the handle's history; the candidate lists must not: every call below -- first call of a fresh
+    handle, repeated calls, a switch between frame kinds -- reproduces the oracle's FAST list level by level."""
+    w, h = 900, 600
+    dense, natural = syn.frame(3, w, h), syn.natural_frame(3, w, h)
+    flat = np.full((h, w), 90, np.uint8)
+    mixed = natural.copy()
+    mixed[:, w // 2:] = dense[:, w // 2:]              # half of every row corner-dense: per-row decisions differ inside a tile
+    plan = {"dense": [dense, dense, dense], "natural": [natural, natural], "flat_then_dense": [flat, dense, natural, dense],
+            "mixed": [mixed, mixed, dense, mixed]}[kind]
+    orb = _orb(1500, HARRIS_SCORE, (w, h))
+    P = oracle.Params(nfeatures=1500)
+    for step, img in enumerate(plan):
+        k, d = orb.detectAndCompute(img)              # runs K2 + K3 on every level: sets the hint for the next call
+        ok, od = oracle.detect_and_compute(img, P)
+        assert_keypoints_equal(k, ok, "%s step %d" % (kind, step))
+        assert_descriptors_equal(d, od, "%s step %d" % (kind, step))
+    for level in (0, 3):
+        xs, ys, sc = orb.debug_fast_level(plan[-1], level)
+        ox, oy, osc = oracle.level_fast(plan[-1], P, level)
+        assert np.array_equal(xs, ox) and np.array_equal(ys, oy) and np.array_equal(sc, osc)
+    orb.close()

@@ -694,6 +694,8 @@ __global__ void __launch_bounds__(1024) k_popc_peak(uint32_t* sink, int iters, u
 }  // namespace
 }  // namespace orbx
 
+#include "hamming_tc.cuh"
+
 // ------------------------------------------------------------------------------------------------ host side
 using namespace orbx;
 
@@ -718,6 +720,9 @@ struct hamx_context {
     size_t p2p_bytes;
     void* p2p_opened[HT_MAX_WORLD];    // peer mappings opened through cudaIpc (closed by hamx_p2p_close)
     hamx_top2* d_p2p_local; size_t p2p_local_bytes;
+    // tensor-core path: the train set expanded to +-1 bytes in the MMA operand image (hamming_tc.cuh)
+    uint8_t* d_texp; size_t texp_bytes;
+    bool tc_ready;
 };
 
 static const P2PView kNoP2P = {};
@@ -763,6 +768,7 @@ extern "C" int hamx_destroy(hamx_handle h)
     cudaFree(h->d_parts); cudaFree(h->d_dm); cudaFree(h->d_counts); cudaFree(h->d_ngood); cudaFree(h->d_pairs);
     hamx_p2p_close(h);
     cudaFree(h->d_p2p_local);
+    cudaFree(h->d_texp);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ORBX_OK;
@@ -1055,6 +1061,48 @@ extern "C" int hamx_match_ratio(hamx_handle h, const uint8_t* q, int64_t nq, con
     if (n) ORBX_CUDA(cudaMemcpyAsync(good, h->d_dm, (size_t)n * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     *ngood = n;
+    return ORBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tensor-core path
+// hamx_knn2_dev's contract, computed by k_hamming_tc (hamming_tc.cuh).  nt <= 2^23.
+extern "C" int hamx_knn2_tc_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
+                                hamx_top2* d_out)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_knn2_tc_dev: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nt >= 0 && nt <= (1ll << HT_IDX_BITS), "hamx_knn2_tc_dev: sizes out of range (nt <= 2^23)");
+    ORBX_REQUIRE(nq < (1ll << 31) && nt + train_offset < (1ll << 31) && train_offset >= 0, "hamx_knn2_tc_dev: indices must fit int32");
+    if (nq == 0) return ORBX_OK;
+    ORBX_REQUIRE(d_q && d_out && (nt == 0 || d_t), "hamx_knn2_tc_dev: NULL pointer");
+    if ((((uintptr_t)d_q) | ((uintptr_t)d_t) | ((uintptr_t)d_out)) & 15) { set_error("hamx_knn2_tc_dev: device pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    if (nt == 0) return fill_absent(h, d_out, nq);
+    if (!h->tc_ready) {
+        ORBX_CUDA(cudaFuncSetAttribute(k_hamming_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        h->tc_ready = true;
+    }
+    const int ntiles = (int)((nt + TC_TN - 1) / TC_TN);
+    int rc = grow(&h->d_texp, &h->texp_bytes, (size_t)ntiles * TC_TILE_BYTES);
+    if (rc) return rc;
+    const long long units = (long long)ntiles * (TC_TILE_BYTES / 16);
+    k_expand_train<<<(unsigned int)((units + 255) / 256), 256, 0, h->stream>>>(d_t, (int)nt, reinterpret_cast<uint4*>(h->d_texp));
+    ORBX_CUDA(cudaGetLastError());
+    const int64_t nqb = (nq + TC_QB - 1) / TC_QB;
+    // one CTA per SM: split the train range until every SM has a CTA (a few, for balance, when there are few query blocks)
+    int nsplit = nqb >= 2 * h->sm_count ? 1 : (int)std::min<int64_t>((2 * h->sm_count + nqb - 1) / nqb, ntiles);
+    if (nsplit > 65535) nsplit = 65535;
+    int tps = (ntiles + nsplit - 1) / nsplit;
+    nsplit = (ntiles + tps - 1) / tps;
+    if (nsplit > 1) {
+        rc = grow(&h->d_partial, &h->partial_bytes, (size_t)nsplit * nq * sizeof(uint2));
+        if (rc) return rc;
+        rc = grow(&h->d_arrivals, &h->arrivals_n, (size_t)nqb * sizeof(unsigned int), true, h->stream);
+        if (rc) return rc;
+    }
+    dim3 grid((unsigned int)nqb, (unsigned int)nsplit, 1);
+    k_hamming_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, (int)nt, tps, -128, h->d_partial, (size_t)nq, h->d_arrivals,
+                                                               d_out, train_offset);
+    ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }
 

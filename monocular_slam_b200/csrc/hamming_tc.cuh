@@ -1,0 +1,267 @@
+// hamming_tc.cuh -- K6 on the 5th-generation tensor cores (included by hamming.cu; sm_100a only).
+//
+// The 256-bit Hamming distance is a contraction: with the bits mapped to +-1, s = sum_k q'_k t'_k = 256 - 2 ham(q, t), exact in
+// int32.  So the distance matrix of a block of queries against a tile of train rows is one int8 GEMM with K = 256, and
+// tcgen05.mma (kind::i8, operands in shared memory, accumulators in tensor memory) produces 128 x 128 distances per 8
+// instructions while the integer pipes only have to fold them into the per-query top-2 (2.5 min/max per distance instead of
+// the ~20 operations the XOR/POPC formulation spends on computing each one).  Results are identical to k_hamming_knn2: the
+// key of train row n of a tile is 256 ham + n (one IMAD on the accumulator), which orders like (distance, trainIdx).
+//
+// Layout.  Operands are K-major, no swizzle ("interleaved" canonical layout): 8 rows x 16 bytes form a contiguous 128-byte core
+// matrix; a 128-row x 256-byte tile is stored as [row / 8][k / 16][row % 8][16 B] = 32 KB, i.e. leading-dimension (K) byte
+// offset 128, stride-dimension (8-row group) byte offset 2048; K-step j of an MMA (32 bytes) starts 256 j bytes in.
+// k_expand_train writes the train set in exactly this image, one contiguous 32 KB block per tile, so a tile arrives with ONE
+// bulk copy (cp.async.bulk + mbarrier, no tensor map).  The CTA's 256 queries are expanded into shared memory by the CTA itself.
+//
+// CTA = 10 warps: warps 0-7 fold accumulators (warp w owns TMEM lanes 32 (w % 4) .. +31 of query block w / 4), warp 8 lane 0
+// streams train tiles (3-stage ring), warp 9 lane 0 issues the MMAs and owns the TMEM allocation (512 columns: 2 query blocks
+// x 128 columns x 2 accumulator stages, so the MMAs of tile i+1 run while tile i is being folded).
+#pragma once
+
+namespace orbx {
+namespace {
+
+constexpr int TC_THREADS = 320;
+constexpr int TC_QB = 256;                 // queries per CTA (two MMA row blocks of 128)
+constexpr int TC_TN = 128;                 // train rows per tile (MMA N)
+constexpr int TC_TILE_BYTES = TC_TN * 256; // 32 KB
+constexpr int TC_STAGES = 3;
+constexpr uint32_t TC_LBO = 128, TC_SBO = 2048;
+constexpr int TC_NONE_KEY = 0x7FFFFFFF;
+// kind::i8 instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8-bit (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
+// N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TN >> 3) << 17) | ((128u >> 4) << 24);
+constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_TILE_BYTES + (size_t)TC_STAGES * TC_TILE_BYTES + 1024;
+
+// 16 descriptor bits -> 16 bytes of +-1 (bit i of the pair of bytes -> byte i)
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t nib)
+{
+    const uint32_t w = (nib * 0x00204081u) & 0x01010101u;          // byte i = bit i of the nibble
+    return 0x01010101u | ((w ^ 0x01010101u) * 0xFEu);               // 1 -> 0x01 (+1), 0 -> 0xFF (-1); no carries between bytes
+}
+__device__ __forceinline__ uint4 expand_bits16(uint32_t bits)
+{
+    return make_uint4(expand_nibble(bits & 15u), expand_nibble((bits >> 4) & 15u), expand_nibble((bits >> 8) & 15u), expand_nibble((bits >> 12) & 15u));
+}
+
+// out: ceil(nt / 128) tiles of 32 KB in the shared-memory image described above; rows beyond nt are zero (masked by the consumer)
+__global__ void __launch_bounds__(256) k_expand_train(const uint8_t* __restrict__ t, int nt, uint4* __restrict__ out)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte unit each
+    const long long ntiles = (nt + TC_TN - 1) / TC_TN;
+    if (u >= ntiles * (TC_TILE_BYTES / 16)) return;
+    const int tile = (int)(u / (TC_TILE_BYTES / 16)), r = (int)(u % (TC_TILE_BYTES / 16));
+    const int n1 = r >> 7, kc = (r >> 3) & 15, n0 = r & 7;
+    const int row = tile * TC_TN + n1 * 8 + n0;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < nt) v = expand_bits16(*reinterpret_cast<const uint16_t*>(t + (size_t)row * 32 + 2 * kc));
+    out[u] = v;
+}
+
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr)
+{
+    // start address >> 4 | LBO >> 4 at bit 16 | SBO >> 4 at bit 32 | descriptor version 1 at bit 46 | no swizzle (bits 61-63 = 0)
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Same launch geometry and split / merge protocol as k_hamming_knn2 (grid = (query blocks of 256, train splits)); `texp` is the
+// expanded train set of k_expand_train, `neg128` holds -128 (a register operand keeps key = acc * -128 + n one IMAD on the FMA
+// pipe instead of a shift and an add on the pipe the min/max run on).
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restrict__ texp, int nt, int tiles_per_split, int neg128,
+             uint2* partial, size_t nq_stride, unsigned int* arrivals, hamx_top2* __restrict__ out, int64_t idx_offset)
+{
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                  // 2 x 32 KB: the CTA's queries, expanded
+    uint8_t* sB = smem + 2 * TC_TILE_BYTES;              // TC_STAGES x 32 KB: train tiles
+
+    const int ntiles_all = (nt + TC_TN - 1) / TC_TN;
+    const int tile_begin = blockIdx.y * tiles_per_split;
+    const int ntiles = max(min(tile_begin + tiles_per_split, ntiles_all) - tile_begin, 0);
+    const int nsplit = gridDim.y;
+    const int64_t qbase = (int64_t)blockIdx.x * TC_QB;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 9) {      // the allocating warp also frees; all 512 columns (the kernel runs one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the CTA's queries -> +-1 bytes in the operand image (rows beyond nq: zeros, never written out)
+    {
+        const uint8_t* __restrict__ q = q_;
+        for (int u = tid; u < TC_QB * 16; u += TC_THREADS) {
+            const int row = u >> 4, kc = u & 15;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (qbase + row < nq) v = expand_bits16(*reinterpret_cast<const uint16_t*>(q + (size_t)(qbase + row) * 32 + 2 * kc));
+            const int blk = row >> 7, r = row & 127;
+            *reinterpret_cast<uint4*>(sA + blk * TC_TILE_BYTES + (r >> 3) * TC_SBO + kc * TC_LBO + (r & 7) * 16) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's reads
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    int g0 = TC_NONE_KEY, g1 = TC_NONE_KEY;      // (the epilogue warps') global top-2 in k_hamming_knn2's key format, as signed ints
+    uint32_t gk0 = HT_NONE, gk1 = HT_NONE;
+
+    if (wid == 8) {
+        if (lane == 0) {
+            for (int i = 0; i < ntiles; i++) {
+                const int s = i % TC_STAGES;
+                mbar_wait(&s_empty[s], ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
+                mbar_expect_tx(&s_full[s], (uint32_t)TC_TILE_BYTES);
+                tma_bulk_g2s(sB + s * TC_TILE_BYTES, texp + (size_t)(tile_begin + i) * TC_TILE_BYTES, (uint32_t)TC_TILE_BYTES, &s_full[s]);
+            }
+        }
+    } else if (wid == 9) {
+        if (lane == 0) {
+            const uint64_t adesc0 = tc_smem_desc(smem_u32(sA)), adesc1 = tc_smem_desc(smem_u32(sA + TC_TILE_BYTES));
+            for (int i = 0; i < ntiles; i++) {
+                const int s = i % TC_STAGES, a = i & 1;
+                mbar_wait(&s_full[s], (uint32_t)(i / TC_STAGES) & 1u);
+                mbar_wait(&s_tempty[a], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint64_t bdesc = tc_smem_desc(smem_u32(sB + s * TC_TILE_BYTES));
+                const uint32_t d0 = tmem_base + (uint32_t)(a * 256), d1 = d0 + 128u;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {     // K step of 32 bytes = 2 core matrices = 256 bytes further on (16 in descriptor units)
+                    tc_mma_i8(d0, adesc0 + (uint64_t)(16 * k), bdesc + (uint64_t)(16 * k), TC_IDESC, k > 0);
+                    tc_mma_i8(d1, adesc1 + (uint64_t)(16 * k), bdesc + (uint64_t)(16 * k), TC_IDESC, k > 0);
+                }
+                tc_commit(&s_empty[s]);           // the stage may be refilled once these MMAs have read it
+                tc_commit(&s_tfull[a]);           // and the accumulators are complete
+            }
+        }
+    } else {
+        const int blk = wid >> 2;
+        const uint32_t lane_base = (uint32_t)(32 * (wid & 3)) << 16;
+        for (int i = 0; i < ntiles; i++) {
+            const int a = i & 1;
+            mbar_wait(&s_tfull[a], (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const int tile = tile_begin + i;
+            const int valid = min(TC_TN, nt - tile * TC_TN);
+            int t0 = TC_NONE_KEY, t1 = TC_NONE_KEY;
+#pragma unroll 1
+            for (int c = 0; c < TC_TN / 32; c++) {
+                int v[32];
+                tc_ld32(tmem_base + lane_base + (uint32_t)(a * 256 + blk * 128 + c * 32), v);
+                if (valid == TC_TN) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const int x = v[j] * neg128 + (c * 32 + j), y = v[j + 1] * neg128 + (c * 32 + j + 1);
+                        const int lo = min(x, y), hi = max(x, y);
+                        const int m = max(t0, lo);
+                        t0 = min(t0, lo);
+                        t1 = __vimin3_s32(t1, m, hi);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int n = c * 32 + j;
+                        const int x = n < valid ? v[j] * neg128 + n : TC_NONE_KEY;
+                        const int m = max(t0, x);
+                        t0 = min(t0, x);
+                        t1 = min(t1, m);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_tempty[a]);
+            // tile-local keys 256 ham - 32768 + n  ->  ham << 23 | (tile * 128 + n), folded into the running top-2
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int k = e ? t1 : t0;
+                if (k != TC_NONE_KEY) {
+                    const uint32_t u = (uint32_t)(k + 32768);
+                    top2_insert(gk0, gk1, ((u >> 8) << HT_IDX_BITS) + ((uint32_t)tile * TC_TN + (u & 255u)));
+                }
+            }
+        }
+    }
+    (void)g0; (void)g1;
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+
+    // ---- results: thread -> query (epilogue threads only hold one)
+    const bool holder = wid < 8;
+    const int64_t qi = qbase + (wid >> 2) * 128 + 32 * (wid & 3) + lane;
+    if (nsplit == 1) {
+        if (holder && qi < nq) out[qi] = decode_top2(gk0, gk1, idx_offset);
+        return;
+    }
+    if (holder && qi < nq) __stcg(&partial[(size_t)blockIdx.y * nq_stride + qi], make_uint2(gk0, gk1));
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(&arrivals[blockIdx.x], 1u);
+        s_last = (prev == (unsigned int)(nsplit - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (holder && qi < nq) {
+        uint32_t m0 = HT_NONE, m1 = HT_NONE;
+        for (int s = 0; s < nsplit; s++) {
+            const uint2 p = __ldcg(&partial[(size_t)s * nq_stride + qi]);
+            top2_insert(m0, m1, p.x);
+            top2_insert(m0, m1, p.y);
+        }
+        out[qi] = decode_top2(m0, m1, idx_offset);
+    }
+    if (tid == 0) arrivals[blockIdx.x] = 0;
+}
+
+}  // namespace
+}  // namespace orbx

@@ -450,6 +450,9 @@ class BFMatcher:
     def knn2_dev(self, d_q, nq, d_t, nt, train_offset, d_out):
         check(_lib.lib().hamx_knn2_dev(self._h, d_q, nq, d_t, nt, train_offset, d_out))
 
+    def knn2_tc_dev(self, d_q, nq, d_t, nt, train_offset, d_out):
+        check(_lib.lib().hamx_knn2_tc_dev(self._h, d_q, nq, d_t, nt, train_offset, d_out))
+
     # -- train-sharded matching over peer memory (include/orbx.h "hamx_p2p_*")
     def p2p_export(self, nq_max, world, rank):
         """Allocate this rank's gather buffer; returns (64-byte cudaIpc handle as bytes, local device base address)."""

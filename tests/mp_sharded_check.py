@@ -4,9 +4,6 @@
 * frame-sharded loop-closure scoring: per-frame scores and the winning frame must equal a single-device pass.
 Launched by tests/test_gpu_multi.py; also usable by hand:
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mp_sharded_check.py
-With ORBX_MP_SAME_DEVICE=1 every rank uses GPU 0 (a 1-GPU box): the processes still exchange through cudaIpc-mapped peer
-memory and device-side flags -- the kernels of the two contexts are time-sliced by the driver -- while torch.distributed
-runs over gloo (NCCL refuses two ranks on one device), so the NCCL variant and the timing loop are skipped there.
 """
 import os
 import sys
@@ -24,15 +21,10 @@ from monocular_slam_b200.sharded import ShardedMatcher, shard_bounds
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    same = os.environ.get("ORBX_MP_SAME_DEVICE", "0") == "1"
-    if same:
-        local = 0
+    same = False      # one rank per GPU only: ranks that spin on each other's flags must not share a device
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if same:
-        dist.init_process_group("gloo")
-    else:
-        dist.init_process_group("nccl", device_id=dev)
+    dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     m = BFMatcher(device=local)

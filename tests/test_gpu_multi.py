@@ -1,5 +1,10 @@
 """Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the train-sharded matcher over peer memory and over
-NCCL equals a single-device pass -- tests/mp_sharded_check.py under torchrun, one process per GPU."""
+NCCL equals a single-device pass -- tests/mp_sharded_check.py under torchrun, one process per GPU.
+
+Not run with several ranks on ONE GPU: kernels of different processes that wait on each other's flags are not guaranteed
+to run at the same time there (B200_PROFILING.md: context-switch timeouts).  On a 1-GPU box the exchange is covered by
+tests/test_gpu_matcher.py::test_p2p_fused_scatter_merge_single_process (ranks emulated by handles of one process, no kernel
+waiting on a later launch), and every multi-GPU run of bench.py checks the sharded result itself (hamming_parity_ok)."""
 import os
 import signal
 import subprocess
@@ -33,9 +38,3 @@ def test_sharded_matcher_multi_process():
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     _run(min(n, 8), {}, 600)
-
-
-def test_sharded_matcher_two_processes_one_gpu():
-    """The same exchange between two PROCESSES that share GPU 0 (what a 1-GPU box can run): cudaIpc-mapped gather buffers,
-    device-side flags, kernels of the two contexts time-sliced by the driver."""
-    _run(2, {"ORBX_MP_SAME_DEVICE": "1"}, 240)

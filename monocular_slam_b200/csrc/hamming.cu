@@ -1100,8 +1100,8 @@ extern "C" int hamx_knn2_tc_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, c
         if (rc) return rc;
     }
     dim3 grid((unsigned int)nqb, (unsigned int)nsplit, 1);
-    k_hamming_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, (int)nt, tps, -128, h->d_partial, (size_t)nq, h->d_arrivals,
-                                                               d_out, train_offset);
+    k_hamming_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, (int)nt, tps, h->d_partial, (size_t)nq, h->d_arrivals, d_out,
+                                                               train_offset);
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }

@@ -5,56 +5,72 @@
 // tcgen05.mma (kind::i8, operands in shared memory, accumulators in tensor memory) produces 128 x 128 distances per 8
 // instructions while the integer pipes only have to fold them into the per-query top-2 (2.5 min/max per distance instead of
 // the ~20 operations the XOR/POPC formulation spends on computing each one).  Results are identical to k_hamming_knn2: the
-// key of train row n of a tile is 256 ham + n (one IMAD on the accumulator), which orders like (distance, trainIdx).
+// train side carries -64 t'_k, and one more K step (query side 1, train side the row's index n inside its tile, 0..127)
+// makes the accumulator itself the key  -64 s + n = 128 ham - 16384 + n,  which orders like (distance, trainIdx) -- the
+// epilogue does not touch the value before comparing it.
 //
 // Layout.  Operands are K-major, no swizzle ("interleaved" canonical layout): 8 rows x 16 bytes form a contiguous 128-byte core
-// matrix; a 128-row x 256-byte tile is stored as [row / 8][k / 16][row % 8][16 B] = 32 KB, i.e. leading-dimension (K) byte
-// offset 128, stride-dimension (8-row group) byte offset 2048; K-step j of an MMA (32 bytes) starts 256 j bytes in.
-// k_expand_train writes the train set in exactly this image, one contiguous 32 KB block per tile, so a tile arrives with ONE
-// bulk copy (cp.async.bulk + mbarrier, no tensor map).  The CTA's 256 queries are expanded into shared memory by the CTA itself.
+// matrix; a 128-row x 288-byte tile (256 bit bytes + the 32-byte index step) is stored as [row / 8][k / 16][row % 8][16 B] =
+// 36 KB, i.e. leading-dimension (K) byte offset 128, stride-dimension (8-row group) byte offset 2304; K step j of an MMA
+// (32 bytes) starts 256 j bytes in.  k_expand_train writes the train set in exactly this image, one contiguous 36 KB block per
+// tile, so a tile arrives with ONE bulk copy (cp.async.bulk + mbarrier, no tensor map).  The CTA's 256 queries are expanded
+// into shared memory by the CTA itself.
 //
-// CTA = 10 warps: warps 0-7 fold accumulators (warp w owns TMEM lanes 32 (w % 4) .. +31 of query block w / 4), warp 8 lane 0
-// streams train tiles (3-stage ring), warp 9 lane 0 issues the MMAs and owns the TMEM allocation (512 columns: 2 query blocks
-// x 128 columns x 2 accumulator stages, so the MMAs of tile i+1 run while tile i is being folded).
+// CTA = 18 warps: warps 0-15 fold accumulators (warp w owns TMEM lanes 32 (w % 4) .. +31 of query block (w / 4) % 2, columns
+// [64 (w / 8), +64) of every tile), warp 16 lane 0 streams train tiles (3-stage ring), warp 17 lane 0 issues the MMAs and owns
+// the TMEM allocation (512 columns: 2 query blocks x 128 columns x 2 accumulator stages, so the MMAs of tile i+1 run while
+// tile i is being folded).  Tensor memory can be read at 64 bytes per clock and SM, i.e. 16 accumulators: that, not the MMA
+// rate and not the integer pipes, is what bounds this formulation with 32-bit accumulators.
 #pragma once
 
 namespace orbx {
 namespace {
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_QB = 256;                 // queries per CTA (two MMA row blocks of 128)
 constexpr int TC_TN = 128;                 // train rows per tile (MMA N)
-constexpr int TC_TILE_BYTES = TC_TN * 256; // 32 KB
+constexpr int TC_KC = 18;                  // 16-byte K chunks per row: 16 of descriptor bits, 1 with the index byte, 1 of zeros
+constexpr int TC_KSTEPS = TC_KC / 2;       // MMA K steps (32 bytes each)
+constexpr uint32_t TC_LBO = 128, TC_SBO = TC_KC * 128;
+constexpr int TC_TILE_BYTES = 16 * (int)TC_SBO;   // 36 KB
 constexpr int TC_STAGES = 3;
-constexpr uint32_t TC_LBO = 128, TC_SBO = 2048;
 constexpr int TC_NONE_KEY = 0x7FFFFFFF;
 // kind::i8 instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8-bit (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
 // N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TN >> 3) << 17) | ((128u >> 4) << 24);
 constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_TILE_BYTES + (size_t)TC_STAGES * TC_TILE_BYTES + 1024;
+static_assert(TC_SMEM_BYTES <= 227 * 1024, "operand images must fit the shared memory of one SM");
 
-// 16 descriptor bits -> 16 bytes of +-1 (bit i of the pair of bytes -> byte i)
+// 16 descriptor bits -> 16 bytes (bit i of the pair of bytes -> byte i): queries +1 / -1, train rows -64 / +64
+template <bool TRAIN>
 __device__ __forceinline__ uint32_t expand_nibble(uint32_t nib)
 {
     const uint32_t w = (nib * 0x00204081u) & 0x01010101u;          // byte i = bit i of the nibble
-    return 0x01010101u | ((w ^ 0x01010101u) * 0xFEu);               // 1 -> 0x01 (+1), 0 -> 0xFF (-1); no carries between bytes
+    if (TRAIN) return 0x40404040u + w * 0x80u;                      // 1 -> 0xC0 (-64), 0 -> 0x40 (+64); no carries between bytes
+    return 0x01010101u | ((w ^ 0x01010101u) * 0xFEu);               // 1 -> 0x01 (+1), 0 -> 0xFF (-1)
 }
+template <bool TRAIN>
 __device__ __forceinline__ uint4 expand_bits16(uint32_t bits)
 {
-    return make_uint4(expand_nibble(bits & 15u), expand_nibble((bits >> 4) & 15u), expand_nibble((bits >> 8) & 15u), expand_nibble((bits >> 12) & 15u));
+    return make_uint4(expand_nibble<TRAIN>(bits & 15u), expand_nibble<TRAIN>((bits >> 4) & 15u), expand_nibble<TRAIN>((bits >> 8) & 15u),
+                      expand_nibble<TRAIN>((bits >> 12) & 15u));
 }
 
-// out: ceil(nt / 128) tiles of 32 KB in the shared-memory image described above; rows beyond nt are zero (masked by the consumer)
+// out: ceil(nt / 128) tiles of 36 KB in the shared-memory image described above; rows beyond nt are zero (masked by the consumer)
 __global__ void __launch_bounds__(256) k_expand_train(const uint8_t* __restrict__ t, int nt, uint4* __restrict__ out)
 {
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte unit each
     const long long ntiles = (nt + TC_TN - 1) / TC_TN;
     if (u >= ntiles * (TC_TILE_BYTES / 16)) return;
     const int tile = (int)(u / (TC_TILE_BYTES / 16)), r = (int)(u % (TC_TILE_BYTES / 16));
-    const int n1 = r >> 7, kc = (r >> 3) & 15, n0 = r & 7;
-    const int row = tile * TC_TN + n1 * 8 + n0;
+    const int n1 = r / (TC_KC * 8), kc = (r / 8) % TC_KC, n0 = r & 7;
+    const int nl = n1 * 8 + n0, row = tile * TC_TN + nl;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < nt) v = expand_bits16(*reinterpret_cast<const uint16_t*>(t + (size_t)row * 32 + 2 * kc));
+    if (row < nt) {
+        if (kc < 16) v = expand_bits16<true>(*reinterpret_cast<const uint16_t*>(t + (size_t)row * 32 + 2 * kc));
+        else if (kc == 16) v.x = (uint32_t)nl;       // byte 0 of the index step: the row's index inside the tile (query side: 1)
+    }
     out[u] = v;
 }
 
@@ -99,21 +115,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32])
 }
 
 // Same launch geometry and split / merge protocol as k_hamming_knn2 (grid = (query blocks of 256, train splits)); `texp` is the
-// expanded train set of k_expand_train, `neg128` holds -128 (a register operand keeps key = acc * -128 + n one IMAD on the FMA
-// pipe instead of a shift and an add on the pipe the min/max run on).
+// expanded train set of k_expand_train.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restrict__ texp, int nt, int tiles_per_split, int neg128,
+k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restrict__ texp, int nt, int tiles_per_split,
              uint2* partial, size_t nq_stride, unsigned int* arrivals, hamx_top2* __restrict__ out, int64_t idx_offset)
 {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_last;
+    __shared__ uint2 s_half[TC_QB];       // top-2 of the warps that fold columns 64..127, handed to their partners
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                                  // 2 x 32 KB: the CTA's queries, expanded
-    uint8_t* sB = smem + 2 * TC_TILE_BYTES;              // TC_STAGES x 32 KB: train tiles
+    uint8_t* sA = smem;                                  // 2 x 36 KB: the CTA's queries, expanded
+    uint8_t* sB = smem + 2 * TC_TILE_BYTES;              // TC_STAGES x 36 KB: train tiles
 
     const int ntiles_all = (nt + TC_TN - 1) / TC_TN;
     const int tile_begin = blockIdx.y * tiles_per_split;
@@ -123,20 +139,23 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], 8); }
+        for (int a = 0; a < 2; a++) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (wid == 9) {      // the allocating warp also frees; all 512 columns (the kernel runs one CTA per SM)
+    if (wid == TC_EPI_WARPS + 1) {      // the allocating warp also frees; all 512 columns (the kernel runs one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // the CTA's queries -> +-1 bytes in the operand image (rows beyond nq: zeros, never written out)
+    // the CTA's queries -> +-1 bytes in the operand image, index step = (1, 0, ..); rows beyond nq: zeros, never written out
     {
         const uint8_t* __restrict__ q = q_;
-        for (int u = tid; u < TC_QB * 16; u += TC_THREADS) {
-            const int row = u >> 4, kc = u & 15;
+        for (int u = tid; u < TC_QB * TC_KC; u += TC_THREADS) {
+            const int row = u / TC_KC, kc = u - row * TC_KC;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (qbase + row < nq) v = expand_bits16(*reinterpret_cast<const uint16_t*>(q + (size_t)(qbase + row) * 32 + 2 * kc));
+            if (qbase + row < nq) {
+                if (kc < 16) v = expand_bits16<false>(*reinterpret_cast<const uint16_t*>(q + (size_t)(qbase + row) * 32 + 2 * kc));
+                else if (kc == 16) v.x = 1u;
+            }
             const int blk = row >> 7, r = row & 127;
             *reinterpret_cast<uint4*>(sA + blk * TC_TILE_BYTES + (r >> 3) * TC_SBO + kc * TC_LBO + (r & 7) * 16) = v;
         }
@@ -147,10 +166,9 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
-    int g0 = TC_NONE_KEY, g1 = TC_NONE_KEY;      // (the epilogue warps') global top-2 in k_hamming_knn2's key format, as signed ints
-    uint32_t gk0 = HT_NONE, gk1 = HT_NONE;
+    uint32_t gk0 = HT_NONE, gk1 = HT_NONE;       // the folding warps' running top-2 in k_hamming_knn2's key format
 
-    if (wid == 8) {
+    if (wid == TC_EPI_WARPS) {
         if (lane == 0) {
             for (int i = 0; i < ntiles; i++) {
                 const int s = i % TC_STAGES;
@@ -159,7 +177,7 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
                 tma_bulk_g2s(sB + s * TC_TILE_BYTES, texp + (size_t)(tile_begin + i) * TC_TILE_BYTES, (uint32_t)TC_TILE_BYTES, &s_full[s]);
             }
         }
-    } else if (wid == 9) {
+    } else if (wid == TC_EPI_WARPS + 1) {
         if (lane == 0) {
             const uint64_t adesc0 = tc_smem_desc(smem_u32(sA)), adesc1 = tc_smem_desc(smem_u32(sA + TC_TILE_BYTES));
             for (int i = 0; i < ntiles; i++) {
@@ -170,7 +188,7 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
                 const uint64_t bdesc = tc_smem_desc(smem_u32(sB + s * TC_TILE_BYTES));
                 const uint32_t d0 = tmem_base + (uint32_t)(a * 256), d1 = d0 + 128u;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {     // K step of 32 bytes = 2 core matrices = 256 bytes further on (16 in descriptor units)
+                for (int k = 0; k < TC_KSTEPS; k++) {     // K step of 32 bytes = 2 core matrices = 256 bytes further on (16 in descriptor units)
                     tc_mma_i8(d0, adesc0 + (uint64_t)(16 * k), bdesc + (uint64_t)(16 * k), TC_IDESC, k > 0);
                     tc_mma_i8(d1, adesc1 + (uint64_t)(16 * k), bdesc + (uint64_t)(16 * k), TC_IDESC, k > 0);
                 }
@@ -179,7 +197,7 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
             }
         }
     } else {
-        const int blk = wid >> 2;
+        const int blk = (wid >> 2) & 1, half = wid >> 3;
         const uint32_t lane_base = (uint32_t)(32 * (wid & 3)) << 16;
         for (int i = 0; i < ntiles; i++) {
             const int a = i & 1;
@@ -187,25 +205,29 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
             tc_fence_after();
             const int tile = tile_begin + i;
             const int valid = min(TC_TN, nt - tile * TC_TN);
-            int t0 = TC_NONE_KEY, t1 = TC_NONE_KEY;
-#pragma unroll 1
-            for (int c = 0; c < TC_TN / 32; c++) {
-                int v[32];
-                tc_ld32(tmem_base + lane_base + (uint32_t)(a * 256 + blk * 128 + c * 32), v);
-                if (valid == TC_TN) {
+            // two independent insertion chains (even / odd column pairs) keep the min/max pipe busy; merged per tile
+            int t0 = TC_NONE_KEY, t1 = TC_NONE_KEY, u0 = TC_NONE_KEY, u1 = TC_NONE_KEY;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int x = v[j] * neg128 + (c * 32 + j), y = v[j + 1] * neg128 + (c * 32 + j + 1);
-                        const int lo = min(x, y), hi = max(x, y);
+            for (int c = 0; c < 2; c++) {
+                const int col0 = half * 64 + c * 32;
+                int v[32];
+                tc_ld32(tmem_base + lane_base + (uint32_t)(a * 256 + blk * 128 + col0), v);
+                if (col0 + 32 <= valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int lo = min(v[j], v[j + 1]), hi = max(v[j], v[j + 1]);
                         const int m = max(t0, lo);
                         t0 = min(t0, lo);
                         t1 = __vimin3_s32(t1, m, hi);
+                        const int lo2 = min(v[j + 2], v[j + 3]), hi2 = max(v[j + 2], v[j + 3]);
+                        const int m2 = max(u0, lo2);
+                        u0 = min(u0, lo2);
+                        u1 = __vimin3_s32(u1, m2, hi2);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        const int n = c * 32 + j;
-                        const int x = n < valid ? v[j] * neg128 + n : TC_NONE_KEY;
+                        const int x = col0 + j < valid ? v[j] : TC_NONE_KEY;
                         const int m = max(t0, x);
                         t0 = min(t0, x);
                         t1 = min(t1, m);
@@ -215,28 +237,38 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_tempty[a]);
-            // tile-local keys 256 ham - 32768 + n  ->  ham << 23 | (tile * 128 + n), folded into the running top-2
+            {   // (t0 <= t1) and (u0 <= u1) -> the two smallest of the four
+                const int lo = min(t0, u0), m = max(t0, u0);
+                t1 = __vimin3_s32(t1, u1, m);
+                t0 = lo;
+            }
+            // tile-local keys 128 ham - 16384 + n  ->  ham << 23 | (tile * 128 + n), folded into the running top-2
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int k = e ? t1 : t0;
                 if (k != TC_NONE_KEY) {
-                    const uint32_t u = (uint32_t)(k + 32768);
-                    top2_insert(gk0, gk1, ((u >> 8) << HT_IDX_BITS) + ((uint32_t)tile * TC_TN + (u & 255u)));
+                    const uint32_t u = (uint32_t)(k + 16384);
+                    top2_insert(gk0, gk1, ((u >> 7) << HT_IDX_BITS) + ((uint32_t)tile * TC_TN + (u & 127u)));
                 }
             }
         }
+        if (half) s_half[tid - 256] = make_uint2(gk0, gk1);
     }
-    (void)g0; (void)g1;
     tc_fence_before();
     __syncthreads();
-    if (wid == 9) {
+    if (wid == TC_EPI_WARPS + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 
-    // ---- results: thread -> query (epilogue threads only hold one)
+    // ---- results: thread -> query (threads of warps 0-7 hold one; their partners' halves come through shared memory)
     const bool holder = wid < 8;
-    const int64_t qi = qbase + (wid >> 2) * 128 + 32 * (wid & 3) + lane;
+    const int64_t qi = qbase + tid;            // warp w < 8: block w / 4, lanes 32 (w % 4) ..  ==  row tid of the CTA's 256
+    if (holder) {
+        const uint2 o = s_half[tid];
+        top2_insert(gk0, gk1, o.x);
+        top2_insert(gk0, gk1, o.y);
+    }
     if (nsplit == 1) {
         if (holder && qi < nq) out[qi] = decode_top2(gk0, gk1, idx_offset);
         return;

@@ -187,10 +187,15 @@ ORBX_API int hamx_match_ratio(hamx_handle h, const uint8_t* q, int64_t nq, const
 /* Device-resident pieces (asynchronous on the handle's stream; pointers must be 16-byte aligned). */
 ORBX_API int hamx_knn2_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
                   hamx_top2* d_out);
-/* The same result through the tensor cores: the distance matrix as an int8 contraction of +-1-expanded descriptors (tcgen05.mma,
- * accumulators in tensor memory), the integer pipes only fold it into the top-2.  nt <= 2^23 per call. */
-ORBX_API int hamx_knn2_tc_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
-                     hamx_top2* d_out);
+/* Two kernels compute the same bit-identical result.  HAMX_KERNEL_TENSOR: the distance matrix as an int8 contraction of
+ * +-1-expanded descriptors on the tensor cores (tcgen05.mma, accumulators in tensor memory), the integer pipes only fold it
+ * into the top-2 -- 5.5x the throughput on large problems.  HAMX_KERNEL_INTEGER: XOR + POPC on the integer pipes, no set-up
+ * cost -- faster on small ones and the only kernel behind the batched frame-pair entry points.  HAMX_KERNEL_AUTO (default)
+ * picks per call by problem size. */
+#define HAMX_KERNEL_AUTO 0
+#define HAMX_KERNEL_INTEGER 1
+#define HAMX_KERNEL_TENSOR 2
+ORBX_API int hamx_set_kernel(hamx_handle h, int mode);
 /* Merge nparts per-shard results laid out [part][nq] (e.g. the output of an all-gather) into d_out[nq]. */
 ORBX_API int hamx_merge_top2_dev(hamx_handle h, const hamx_top2* d_parts, int nparts, int64_t nq, hamx_top2* d_out);
 /* Ratio test + ordered compaction: d_good gets the accepted matches, *d_ngood their number. */

@@ -17,6 +17,7 @@ CAMERAS_DTYPE = np.dtype([("Rt1", "<f8", (3, 4)), ("Rt2", "<f8", (3, 4)), ("K1",
 assert KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DTYPE.itemsize == 16 and CAMERAS_DTYPE.itemsize == 336
 
 HARRIS_SCORE, FAST_SCORE = 0, 1
+KERNEL_AUTO, KERNEL_INTEGER, KERNEL_TENSOR = 0, 1, 2     # hamx_set_kernel
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_ALLOC, E_ALIGN = 0, -1, -2, -3, -4, -5
 
 # every symbol include/orbx.h declares (tests/test_abi.py checks the header against this list and the built library)
@@ -32,7 +33,7 @@ SYMBOLS = [
     "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev", "orbx_set_input_channels", "orbx_pipeline_depth", "hamx_match_back_dev", "hamx_update_history_dev", "orbx_match_back", "orbx_host_alloc", "orbx_host_free",
     "fmx_create", "fmx_destroy", "fmx_set_stream", "fmx_synchronize", "fmx_compute_fundamental", "fmx_fundamental_batch",
     "fmx_last_info", "fmx_fundamental_batch_dev", "fmx_filter_consecutive_dev", "orbx_filter_consecutive", "orbx_submit_batch_filtered", "fmx_filter_back_dev", "orbx_filter_back", "orbx_submit_batch_back",
-    "hamx_get_stream", "fmx_get_stream", "hamx_reserve", "hamx_knn2_tc_dev", "hamx_nbest", "hamx_nbest_dev", "hamx_loop_score", "hamx_loop_score_dev", "hamx_loop_best_dev",
+    "hamx_get_stream", "fmx_get_stream", "hamx_reserve", "hamx_set_kernel", "hamx_nbest", "hamx_nbest_dev", "hamx_loop_score", "hamx_loop_score_dev", "hamx_loop_best_dev",
     "trx_create", "trx_destroy", "trx_set_stream", "trx_get_stream", "trx_synchronize", "trx_triangulate", "trx_triangulate_hypotheses",
     "trx_triangulate_batch", "trx_triangulate_batch_dev", "trx_triangulate_back_dev", "trx_associate_dev", "trx_select_new_dev",
 ]
@@ -122,7 +123,7 @@ def lib():
     L.hamx_loop_score.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, i32p]
     L.hamx_loop_score_dev.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.hamx_loop_best_dev.argtypes = [vp, vp, C.c_int, vp]
-    L.hamx_knn2_tc_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int64, vp]
+    L.hamx_set_kernel.argtypes = [vp, C.c_int]
     L.hamx_reserve.argtypes = [vp, C.c_int64, C.c_int64, C.c_int]
     L.hamx_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.fmx_get_stream.argtypes = [vp, C.POINTER(vp)]

@@ -723,6 +723,7 @@ struct hamx_context {
     // tensor-core path: the train set expanded to +-1 bytes in the MMA operand image (hamming_tc.cuh)
     uint8_t* d_texp; size_t texp_bytes;
     bool tc_ready;
+    int kernel_mode;                   // HAMX_KERNEL_*
 };
 
 static const P2PView kNoP2P = {};
@@ -781,6 +782,14 @@ extern "C" int hamx_set_stream(hamx_handle h, void* cuda_stream)
     return ORBX_OK;
 }
 
+extern "C" int hamx_set_kernel(hamx_handle h, int mode)
+{
+    ORBX_REQUIRE(h != nullptr, "hamx_set_kernel: NULL handle");
+    ORBX_REQUIRE(mode == HAMX_KERNEL_AUTO || mode == HAMX_KERNEL_INTEGER || mode == HAMX_KERNEL_TENSOR, "hamx_set_kernel: unknown mode %d", mode);
+    h->kernel_mode = mode;
+    return ORBX_OK;
+}
+
 extern "C" int hamx_get_stream(hamx_handle h, void** cuda_stream)
 {
     ORBX_REQUIRE(h != nullptr && cuda_stream != nullptr, "hamx_get_stream: NULL argument");
@@ -821,9 +830,58 @@ static void plan_split(int sm_count, int64_t nqb, int ntiles, int64_t npairs, in
     *tps_out = tps;
 }
 
+// ---- tensor-core path (hamming_tc.cuh): the same contract as launch_chunk's integer-pipe kernel
+static int launch_chunk_tc(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int nt, int64_t offset, hamx_top2* d_out,
+                           const P2PView* pv)
+{
+    if (!h->tc_ready) {
+        ORBX_CUDA(cudaFuncSetAttribute(k_hamming_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        ORBX_CUDA(cudaFuncSetAttribute(k_hamming_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        h->tc_ready = true;
+    }
+    const int ntiles = (nt + TC_TN - 1) / TC_TN;
+    int rc = grow(&h->d_texp, &h->texp_bytes, (size_t)ntiles * TC_TILE_BYTES);
+    if (rc) return rc;
+    const long long units = (long long)ntiles * (TC_TILE_BYTES / 16);
+    k_expand_train<<<(unsigned int)((units + 255) / 256), 256, 0, h->stream>>>(d_t, nt, reinterpret_cast<uint4*>(h->d_texp));
+    ORBX_CUDA(cudaGetLastError());
+    const int64_t nqb = (nq + TC_QB - 1) / TC_QB;
+    // one CTA per SM: split the train range until every SM has a CTA (a few, for balance, when there are few query blocks)
+    int nsplit = nqb >= 2 * h->sm_count ? 1 : (int)std::min<int64_t>((2 * h->sm_count + nqb - 1) / nqb, ntiles);
+    if (nsplit > 65535) nsplit = 65535;
+    const int tps = (ntiles + nsplit - 1) / nsplit;
+    nsplit = (ntiles + tps - 1) / tps;
+    if (nsplit > 1) {
+        rc = grow(&h->d_partial, &h->partial_bytes, (size_t)nsplit * nq * sizeof(uint2));
+        if (rc) return rc;
+        rc = grow(&h->d_arrivals, &h->arrivals_n, (size_t)nqb * sizeof(unsigned int), true, h->stream);
+        if (rc) return rc;
+    }
+    const dim3 grid((unsigned int)nqb, (unsigned int)nsplit, 1);
+    if (pv)
+        k_hamming_tc<true><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, nt, tps, h->d_partial, (size_t)nq, h->d_arrivals,
+                                                                           d_out, offset, *pv);
+    else
+        k_hamming_tc<false><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, nt, tps, h->d_partial, (size_t)nq, h->d_arrivals,
+                                                                            d_out, offset, kNoP2P);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// Which kernel computes a single (query set, train set) problem.  The tensor-core kernel pays a fixed price per CTA (TMEM
+// allocation, expanding 256 queries, the train set expanded once per call); below ~4 M comparisons the integer-pipe kernel
+// is as fast or faster.
+static bool use_tensor_cores(hamx_handle h, int64_t nq, int nt)
+{
+    if (h->kernel_mode == HAMX_KERNEL_INTEGER) return false;
+    if (h->kernel_mode == HAMX_KERNEL_TENSOR) return true;
+    return nq * (int64_t)nt >= (1ll << 22);
+}
+
 static int launch_chunk(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int nt, int64_t offset, hamx_top2* d_out,
                         const P2PView* pv = nullptr)
 {
+    if (use_tensor_cores(h, nq, nt)) return launch_chunk_tc(h, d_q, nq, d_t, nt, offset, d_out, pv);
     const int64_t nqb = (nq + HT_QB - 1) / HT_QB;
     const int ntiles = (nt + HT_TT - 1) / HT_TT;
     int nsplit, tps;
@@ -865,6 +923,11 @@ extern "C" int hamx_reserve(hamx_handle h, int64_t nq, int64_t nt, int npairs)
     const int64_t chunk = 1ll << HT_IDX_BITS;
     if (!rc && nt > chunk) rc = grow(&h->d_parts, &h->parts_bytes, (size_t)((nt + chunk - 1) / chunk) * nq * sizeof(hamx_top2));
     if (!rc && h->p2p_buf) rc = grow(&h->d_p2p_local, &h->p2p_local_bytes, (size_t)nq * sizeof(hamx_top2));
+    if (!rc && h->kernel_mode != HAMX_KERNEL_INTEGER) {      // tensor-core path: expanded train set, and its own split plan
+        const int64_t tiles = (std::min<int64_t>(nt, chunk) + TC_TN - 1) / TC_TN;
+        rc = grow(&h->d_texp, &h->texp_bytes, (size_t)std::max<int64_t>(tiles, 1) * TC_TILE_BYTES);
+        if (!rc) rc = grow(&h->d_partial, &h->partial_bytes, std::max(partial, ((size_t)2 * h->sm_count * TC_QB + (size_t)nq) * sizeof(uint2)));
+    }
     if (rc) return rc;
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     return ORBX_OK;
@@ -1061,48 +1124,6 @@ extern "C" int hamx_match_ratio(hamx_handle h, const uint8_t* q, int64_t nq, con
     if (n) ORBX_CUDA(cudaMemcpyAsync(good, h->d_dm, (size_t)n * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     *ngood = n;
-    return ORBX_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ tensor-core path
-// hamx_knn2_dev's contract, computed by k_hamming_tc (hamming_tc.cuh).  nt <= 2^23.
-extern "C" int hamx_knn2_tc_dev(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int64_t nt, int64_t train_offset,
-                                hamx_top2* d_out)
-{
-    ORBX_REQUIRE(h != nullptr, "hamx_knn2_tc_dev: NULL handle");
-    ORBX_REQUIRE(nq >= 0 && nt >= 0 && nt <= (1ll << HT_IDX_BITS), "hamx_knn2_tc_dev: sizes out of range (nt <= 2^23)");
-    ORBX_REQUIRE(nq < (1ll << 31) && nt + train_offset < (1ll << 31) && train_offset >= 0, "hamx_knn2_tc_dev: indices must fit int32");
-    if (nq == 0) return ORBX_OK;
-    ORBX_REQUIRE(d_q && d_out && (nt == 0 || d_t), "hamx_knn2_tc_dev: NULL pointer");
-    if ((((uintptr_t)d_q) | ((uintptr_t)d_t) | ((uintptr_t)d_out)) & 15) { set_error("hamx_knn2_tc_dev: device pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
-    ORBX_CUDA(cudaSetDevice(h->device));
-    if (nt == 0) return fill_absent(h, d_out, nq);
-    if (!h->tc_ready) {
-        ORBX_CUDA(cudaFuncSetAttribute(k_hamming_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        h->tc_ready = true;
-    }
-    const int ntiles = (int)((nt + TC_TN - 1) / TC_TN);
-    int rc = grow(&h->d_texp, &h->texp_bytes, (size_t)ntiles * TC_TILE_BYTES);
-    if (rc) return rc;
-    const long long units = (long long)ntiles * (TC_TILE_BYTES / 16);
-    k_expand_train<<<(unsigned int)((units + 255) / 256), 256, 0, h->stream>>>(d_t, (int)nt, reinterpret_cast<uint4*>(h->d_texp));
-    ORBX_CUDA(cudaGetLastError());
-    const int64_t nqb = (nq + TC_QB - 1) / TC_QB;
-    // one CTA per SM: split the train range until every SM has a CTA (a few, for balance, when there are few query blocks)
-    int nsplit = nqb >= 2 * h->sm_count ? 1 : (int)std::min<int64_t>((2 * h->sm_count + nqb - 1) / nqb, ntiles);
-    if (nsplit > 65535) nsplit = 65535;
-    int tps = (ntiles + nsplit - 1) / nsplit;
-    nsplit = (ntiles + tps - 1) / tps;
-    if (nsplit > 1) {
-        rc = grow(&h->d_partial, &h->partial_bytes, (size_t)nsplit * nq * sizeof(uint2));
-        if (rc) return rc;
-        rc = grow(&h->d_arrivals, &h->arrivals_n, (size_t)nqb * sizeof(unsigned int), true, h->stream);
-        if (rc) return rc;
-    }
-    dim3 grid((unsigned int)nqb, (unsigned int)nsplit, 1);
-    k_hamming_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, (int)nt, tps, h->d_partial, (size_t)nq, h->d_arrivals, d_out,
-                                                               train_offset);
-    ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }
 

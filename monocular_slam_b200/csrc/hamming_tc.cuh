@@ -116,9 +116,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32])
 
 // Same launch geometry and split / merge protocol as k_hamming_knn2 (grid = (query blocks of 256, train splits)); `texp` is the
 // expanded train set of k_expand_train.
+template <bool P2P>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restrict__ texp, int nt, int tiles_per_split,
-             uint2* partial, size_t nq_stride, unsigned int* arrivals, hamx_top2* __restrict__ out, int64_t idx_offset)
+             uint2* partial, size_t nq_stride, unsigned int* arrivals, hamx_top2* __restrict__ out, int64_t idx_offset,
+             const __grid_constant__ P2PView pv)
 {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
@@ -270,7 +272,12 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
         top2_insert(gk0, gk1, o.y);
     }
     if (nsplit == 1) {
-        if (holder && qi < nq) out[qi] = decode_top2(gk0, gk1, idx_offset);
+        if (holder && qi < nq) {
+            const hamx_top2 v = decode_top2(gk0, gk1, idx_offset);
+            if (P2P) p2p_store(pv, qi, v);
+            else out[qi] = v;
+        }
+        if (P2P) p2p_publish(pv, gridDim.x);
         return;
     }
     if (holder && qi < nq) __stcg(&partial[(size_t)blockIdx.y * nq_stride + qi], make_uint2(gk0, gk1));
@@ -285,14 +292,25 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
     __threadfence();
     if (holder && qi < nq) {
         uint32_t m0 = HT_NONE, m1 = HT_NONE;
-        for (int s = 0; s < nsplit; s++) {
+        int s = 0;
+        for (; s + 8 <= nsplit; s += 8) {      // independent loads in flight, as in k_hamming_knn2
+            uint2 p[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) p[u] = __ldcg(&partial[(size_t)(s + u) * nq_stride + qi]);
+#pragma unroll
+            for (int u = 0; u < 8; u++) { top2_insert(m0, m1, p[u].x); top2_insert(m0, m1, p[u].y); }
+        }
+        for (; s < nsplit; s++) {
             const uint2 p = __ldcg(&partial[(size_t)s * nq_stride + qi]);
             top2_insert(m0, m1, p.x);
             top2_insert(m0, m1, p.y);
         }
-        out[qi] = decode_top2(m0, m1, idx_offset);
+        const hamx_top2 v = decode_top2(m0, m1, idx_offset);
+        if (P2P) p2p_store(pv, qi, v);
+        else out[qi] = v;
     }
-    if (tid == 0) arrivals[blockIdx.x] = 0;
+    if (tid == 0) arrivals[blockIdx.x] = 0;   // ready for the next launch
+    if (P2P) p2p_publish(pv, gridDim.x);      // one merging CTA per query block
 }
 
 }  // namespace

@@ -450,8 +450,10 @@ class BFMatcher:
     def knn2_dev(self, d_q, nq, d_t, nt, train_offset, d_out):
         check(_lib.lib().hamx_knn2_dev(self._h, d_q, nq, d_t, nt, train_offset, d_out))
 
-    def knn2_tc_dev(self, d_q, nq, d_t, nt, train_offset, d_out):
-        check(_lib.lib().hamx_knn2_tc_dev(self._h, d_q, nq, d_t, nt, train_offset, d_out))
+    def set_kernel(self, mode):
+        """_lib.KERNEL_AUTO (by problem size), KERNEL_INTEGER (XOR + POPC) or KERNEL_TENSOR (tcgen05 int8 contraction); the
+        results are identical."""
+        check(_lib.lib().hamx_set_kernel(self._h, int(mode)))
 
     # -- train-sharded matching over peer memory (include/orbx.h "hamx_p2p_*")
     def p2p_export(self, nq_max, world, rank):

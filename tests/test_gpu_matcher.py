@@ -7,7 +7,7 @@ import pytest
 
 import oracle
 from helpers import knn_arrays
-from monocular_slam_b200 import BFMatcher, DMATCH_DTYPE, TOP2_DTYPE, match_features
+from monocular_slam_b200 import BFMatcher, DMATCH_DTYPE, TOP2_DTYPE, _lib, match_features
 from monocular_slam_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
@@ -15,9 +15,15 @@ pytestmark = pytest.mark.gpu
 MATCH = ["planted", "dup_rows", "zeros", "nt1", "nt2", "low_entropy", "ragged_33x65"]
 
 
-@pytest.fixture(scope="module")
-def matcher():
+KERNELS = {"auto": _lib.KERNEL_AUTO, "integer": _lib.KERNEL_INTEGER, "tensor": _lib.KERNEL_TENSOR}
+
+
+@pytest.fixture(scope="module", params=list(KERNELS))
+def matcher(request):
+    """Every test below runs against the integer-pipe kernel (XOR + POPC), the tensor-core kernel (tcgen05 int8 contraction)
+    and the size-based choice between them: the results must be the same bits."""
     m = BFMatcher()
+    m.set_kernel(KERNELS[request.param])
     yield m
     m.close()
 
@@ -145,8 +151,9 @@ def test_large_properties(matcher):
     assert np.array_equal(i2[::-1], idx) and np.array_equal(d2[::-1], dist)
 
 
+@pytest.mark.parametrize("kernel", list(KERNELS))
 @pytest.mark.parametrize("world,nq,nt", [(1, 300, 1000), (2, 2000, 5001), (3, 777, 130), (4, 257, 4096), (8, 2000, 200000)])
-def test_p2p_fused_scatter_merge_single_process(world, nq, nt):
+def test_p2p_fused_scatter_merge_single_process(world, nq, nt, kernel):
     """hamx_knn2_p2p_*: `world` ranks emulated by `world` handles of one process on one GPU (same-process pointer import).
     All scatters are queued before any merge, so no kernel ever waits on a later launch.  Twice, to cover both buffer
     parities and the reuse of the completion counter."""
@@ -162,6 +169,7 @@ def test_p2p_fused_scatter_merge_single_process(world, nq, nt):
         ms = [BFMatcher() for _ in range(world)]
         for m in ms:
             m.set_stream(stream.cuda_stream)
+            m.set_kernel(KERNELS[kernel])
         bases = [m.p2p_export(nq + 13, world, r)[1] for r, m in enumerate(ms)]
         for m in ms:
             m.p2p_import_ptrs(bases)
@@ -185,7 +193,8 @@ def test_p2p_fused_scatter_merge_single_process(world, nq, nt):
             m.close()
 
 
-def test_train_set_larger_than_index_field():
+@pytest.mark.parametrize("kernel", ["integer", "tensor"])
+def test_train_set_larger_than_index_field(kernel):
     """More than 2^23 train rows: the packed (distance << 23 | index) key covers one chunk, the host splits the train set and
     merges the chunks with the 64-bit rule.  Planted exact duplicates on both sides of the chunk border pin the tie rule
     (lowest global index first) and the global offsets; a sample of queries is checked against the oracle on a window."""
@@ -206,6 +215,7 @@ def test_train_set_larger_than_index_field():
             t[border + 60000 - i] = q[64 + i]
         m = BFMatcher()
         m.set_stream(stream.cuda_stream)
+        m.set_kernel(KERNELS[kernel])
         out = torch.empty((nq, 4), dtype=torch.int32, device="cuda")
         m.knn2_dev(q.data_ptr(), nq, t.data_ptr(), nt, 0, out.data_ptr())
         stream.synchronize()
@@ -226,3 +236,31 @@ def test_train_set_larger_than_index_field():
         assert (d0, d1) == (r[i][0], r[i][2]) and d0 <= d1
         assert d0 <= od[j, 0] and d1 <= od[j, 1]          # nothing in the window beats the global answer
     m.close()
+
+
+def test_kernels_agree_on_the_benchmark_shape():
+    """1 M x 125 k per GPU (BASELINE config 5): far beyond the oracle; the two kernels, which share no arithmetic (XOR + POPC
+    vs a +-1 int8 contraction), must produce identical top-2 for every query, and a sample must equal the oracle."""
+    import torch
+    nq, nt = 1 << 18, 125000
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device="cuda"); g.manual_seed(9)
+        q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device="cuda", generator=g)
+        t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device="cuda", generator=g)
+        t[::1013] = t[7]                                  # equal rows: ties by lowest index, in both kernels
+        outs = []
+        for mode in ("integer", "tensor"):
+            m = BFMatcher()
+            m.set_stream(stream.cuda_stream)
+            m.set_kernel(KERNELS[mode])
+            o = torch.empty((nq, 4), dtype=torch.int32, device="cuda")
+            m.knn2_dev(q.data_ptr(), nq, t.data_ptr(), nt, 3, o.data_ptr())
+            stream.synchronize()
+            outs.append(o)
+            m.close()
+    assert torch.equal(outs[0], outs[1])
+    sample = np.random.default_rng(1).choice(nq, 64, replace=False)
+    oi, od = oracle.knn2(q.cpu().numpy()[sample], t.cpu().numpy())
+    r = outs[1].cpu().numpy()[sample]
+    assert np.array_equal(r[:, [1, 3]], oi + 3) and np.array_equal(r[:, [0, 2]], od)

@@ -5,7 +5,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from monocular_slam_b200 import BFMatcher
+from monocular_slam_b200 import BFMatcher, _lib
 
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream()
@@ -18,7 +18,8 @@ g.manual_seed(1)
 q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=g)
 t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device=dev, generator=g)
 o = torch.empty((nq, 4), dtype=torch.int32, device=dev)
-fn = m.knn2_dev if len(sys.argv) > 1 and sys.argv[1] == "int" else m.knn2_tc_dev
+m.set_kernel(_lib.KERNEL_INTEGER if len(sys.argv) > 1 and sys.argv[1] == "int" else _lib.KERNEL_TENSOR)
+fn = m.knn2_dev
 for _ in range(3):
     fn(q.data_ptr(), nq, t.data_ptr(), nt, 0, o.data_ptr())
 stream.synchronize()

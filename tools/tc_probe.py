@@ -7,13 +7,18 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from monocular_slam_b200 import BFMatcher
+from monocular_slam_b200 import BFMatcher, _lib
 
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 m = BFMatcher()
 m.set_stream(stream.cuda_stream)
+mt = BFMatcher()
+mt.set_stream(stream.cuda_stream)
+m.set_kernel(_lib.KERNEL_INTEGER)
+mt.set_kernel(_lib.KERNEL_TENSOR)
+m.knn2_tc_dev = mt.knn2_dev
 
 
 def run(nq, nt, seed=0, dup=True):

@@ -586,6 +586,7 @@ def run_ours(args, rank, world, local_rank):
         timed(step_device, max(args.steps // 2, 2), 0)
         nat_stages, _ = orb.read_profile()
         orb.set_profiling(False)
+        orb.check_dev()
         nat_counts, nat_good = d_cnt.cpu().numpy(), d_ngood.cpu().numpy()
         natural = {"value": world * B * args.steps / (nat_ms * 1e-3), "unit": "frames/s", "ms_per_step": nat_ms / args.steps,
                    "generator": "synthetic.natural_frame (1/f shading, flat objects, textured patches, lens blur, sensor noise)",
@@ -679,20 +680,45 @@ def run_ours(args, rank, world, local_rank):
 
         def step_ham():
             out["r"] = sm.knn2(q, t_shard, rank * nt_shard)
+        from monocular_slam_b200 import _lib as _K
         ham_steps = max(2, min(args.steps, 3))
-        ham_sampler = ClockSampler(local_rank, period=0.02)
-        ham_ms, _ = timed(step_ham, ham_steps, 1, ham_sampler)
-        ham_ms = max_over_ranks(ham_ms) / ham_steps
+        # the integer-pipe kernel (XOR + POPC: what the roofline of SURVEY.md 8d describes) beside the product's choice, the
+        # tensor-core kernel; same call, same exchange, identical results
+        matcher.set_kernel(_K.KERNEL_INTEGER)
+        int_ms = max_over_ranks(timed(step_ham, 2, 1)[0]) / 2
+        r_int = out["r"].clone()
+        matcher.set_kernel(_K.KERNEL_AUTO)
+        ham_sampler = ClockSampler(local_rank, period=0.01)
+        ham_ms, _ = timed(step_ham, ham_steps * 3, 2, ham_sampler)
+        ham_ms = max_over_ranks(ham_ms) / (ham_steps * 3)
+        assert torch.equal(out["r"], r_int), "tensor-core and integer-pipe kernels disagree"
         gpopc, _ = popc_peak(local_rank)
         gcmp = world * nq * nt_shard / (ham_ms * 1e-3) / 1e9
+        gcmp_int = world * nq * nt_shard / (int_ms * 1e-3) / 1e9
+        ham_clk = (ham_sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        tmem_peak = world * sms * 64 * ham_clk / 4 / 1e9        # accumulators per second readable from tensor memory (64 B / clk / SM)
+        int8_peak = None
+        try:
+            int8_peak = 2 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) * world
+        except Exception:
+            pass
         hamming = {"value": gcmp, "unit": "Gcmp/s", "nq": nq, "nt_per_gpu": nt_shard, "ms_per_step": ham_ms, "clocks": ham_sampler.summary(),
+                   "kernel": "tensor cores: +-1 int8 contraction (tcgen05.mma kind::i8, accumulators in tensor memory), integer pipes fold the top-2",
                    "workload": "%d queries x %d train rows per GPU (train-sharded; %s)" % (
                        nq, nt_shard, "top-2 exchanged over peer memory inside the matching kernel + flag-wait merge" if world > 1 else "single GPU, no exchange"),
+                   "integer_pipe_kernel": {"value": gcmp_int, "unit": "Gcmp/s", "ms_per_step": int_ms, "frac_popc_pipe": gcmp_int * 5 / (gpopc * world),
+                                           "frac_algorithmic": gcmp_int * 8 / (gpopc * world)},
                    "roofline": {"bound": "int_popc", "achieved": gcmp * 8, "peak": gpopc * world, "unit": "Gpopc/s",
                                 "frac": gcmp * 8 / (gpopc * world),
                                 "note": "ALGORITHMIC work of 8 POPC per 256-bit comparison (SURVEY.md 8d) against the register-only POPC "
-                                        "microbenchmark (hamx_popc_peak) per GPU x n_gpus; frac > 1 because the kernel issues only 5 POPC per "
-                                        "comparison after carry-save compression on the LOP3 pipe (csrc/hamming.cu ham256)"}}
+                                        "microbenchmark (hamx_popc_peak) per GPU x n_gpus.  The product kernel issues no POPC at all (the distances "
+                                        "come out of the tensor cores), hence frac >> 1; what bounds it is the tensor-memory read path: see roofline_tmem"},
+                   "roofline_tmem": {"bound": "tensor memory read (64 B / clk / SM: 16 int32 accumulators)", "achieved": gcmp, "peak": tmem_peak,
+                                     "unit": "G accumulators/s", "frac": gcmp / tmem_peak},
+                   "roofline_tensor": {"bound": "tensor", "achieved": gcmp * 2 * 288 / 1e3, "peak": int8_peak, "unit": "TOP/s (int8, 288-byte K incl. the index step)",
+                                       "frac": (gcmp * 2 * 288 / 1e3 / int8_peak) if int8_peak else None,
+                                       "peak_source": "2 x the measured bf16 GEMM burst of MEASURED_PEAKS.json (no int8 measurement exists; nominal ratio)"}}
         # BASELINE.json configs[3]: map-vs-frame tracking match, 200k map descriptors x 2000 queries, train set sharded over the ranks
         mq = q[:2000].contiguous()
         m_nt = 200000 // world
@@ -714,7 +740,9 @@ def run_ours(args, rank, world, local_rank):
                                    "from their seeds on every rank" if world > 1 else "first 32 queries == torch XOR + popcount + topk over the shard")
         # flat scalars for the driver's record (it keeps scalars inside `roofline` only)
         roofline.update({"hamming_gcmp_s": gcmp, "hamming_ms_per_step": ham_ms, "hamming_frac_algorithmic": gcmp * 8 / (gpopc * world),
-                         "hamming_frac_popc_pipe": gcmp * 5 / (gpopc * world), "hamming_popc_peak_gpopc_s_per_gpu": gpopc,
+                         "hamming_frac_tmem_read": gcmp / tmem_peak, "hamming_frac_tensor": hamming["roofline_tensor"]["frac"],
+                         "hamming_int_kernel_gcmp_s": gcmp_int, "hamming_int_kernel_frac_popc_pipe": gcmp_int * 5 / (gpopc * world),
+                         "hamming_kernels_agree": 1, "hamming_popc_peak_gpopc_s_per_gpu": gpopc,
                          "hamming_sm_mhz": ham_sampler.summary().get("sm_mhz"),
                          "hamming_parity_ok": 1 if parity_ok else 0,
                          "mvf_us_peer": mvf.get("peer_memory", mvf.get("single_gpu")), "mvf_us_nccl": mvf.get("nccl_all_gather")})

@@ -831,19 +831,25 @@ static void plan_split(int sm_count, int64_t nqb, int ntiles, int64_t npairs, in
 }
 
 // ---- tensor-core path (hamming_tc.cuh): the same contract as launch_chunk's integer-pipe kernel
+static int tc_prepare(hamx_handle h)
+{
+    if (h->tc_ready) return ORBX_OK;
+    ORBX_CUDA(cudaFuncSetAttribute(k_hamming_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    ORBX_CUDA(cudaFuncSetAttribute(k_hamming_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    h->tc_ready = true;
+    return ORBX_OK;
+}
+
 static int launch_chunk_tc(hamx_handle h, const uint8_t* d_q, int64_t nq, const uint8_t* d_t, int nt, int64_t offset, hamx_top2* d_out,
                            const P2PView* pv)
 {
-    if (!h->tc_ready) {
-        ORBX_CUDA(cudaFuncSetAttribute(k_hamming_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        ORBX_CUDA(cudaFuncSetAttribute(k_hamming_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        h->tc_ready = true;
-    }
+    int rc = tc_prepare(h);
+    if (rc) return rc;
     const int ntiles = (nt + TC_TN - 1) / TC_TN;
-    int rc = grow(&h->d_texp, &h->texp_bytes, (size_t)ntiles * TC_TILE_BYTES);
+    rc = grow(&h->d_texp, &h->texp_bytes, (size_t)ntiles * TC_TILE_BYTES);
     if (rc) return rc;
     const long long units = (long long)ntiles * (TC_TILE_BYTES / 16);
-    k_expand_train<<<(unsigned int)((units + 255) / 256), 256, 0, h->stream>>>(d_t, nt, reinterpret_cast<uint4*>(h->d_texp));
+    k_expand_train<<<(unsigned int)((units + 255) / 256), 256, 0, h->stream>>>(d_t, nt, nullptr, 0, reinterpret_cast<uint4*>(h->d_texp));
     ORBX_CUDA(cudaGetLastError());
     const int64_t nqb = (nq + TC_QB - 1) / TC_QB;
     // one CTA per SM: split the train range until every SM has a CTA (a few, for balance, when there are few query blocks)
@@ -859,11 +865,11 @@ static int launch_chunk_tc(hamx_handle h, const uint8_t* d_q, int64_t nq, const 
     }
     const dim3 grid((unsigned int)nqb, (unsigned int)nsplit, 1);
     if (pv)
-        k_hamming_tc<true><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, nt, tps, h->d_partial, (size_t)nq, h->d_arrivals,
-                                                                           d_out, offset, *pv);
+        k_hamming_tc<true><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, nt, nullptr, 0, tps, h->d_partial, (size_t)nq,
+                                                                           h->d_arrivals, (int)nqb, d_out, 0, offset, *pv);
     else
-        k_hamming_tc<false><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, nt, tps, h->d_partial, (size_t)nq, h->d_arrivals,
-                                                                            d_out, offset, kNoP2P);
+        k_hamming_tc<false><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, nt, nullptr, 0, tps, h->d_partial, (size_t)nq,
+                                                                            h->d_arrivals, (int)nqb, d_out, 0, offset, kNoP2P);
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }
@@ -923,10 +929,10 @@ extern "C" int hamx_reserve(hamx_handle h, int64_t nq, int64_t nt, int npairs)
     const int64_t chunk = 1ll << HT_IDX_BITS;
     if (!rc && nt > chunk) rc = grow(&h->d_parts, &h->parts_bytes, (size_t)((nt + chunk - 1) / chunk) * nq * sizeof(hamx_top2));
     if (!rc && h->p2p_buf) rc = grow(&h->d_p2p_local, &h->p2p_local_bytes, (size_t)nq * sizeof(hamx_top2));
-    if (!rc && h->kernel_mode != HAMX_KERNEL_INTEGER) {      // tensor-core path: expanded train set, and its own split plan
+    if (!rc && h->kernel_mode != HAMX_KERNEL_INTEGER) {      // tensor-core path: expanded train set(s), and its own split plan
         const int64_t tiles = (std::min<int64_t>(nt, chunk) + TC_TN - 1) / TC_TN;
-        rc = grow(&h->d_texp, &h->texp_bytes, (size_t)std::max<int64_t>(tiles, 1) * TC_TILE_BYTES);
-        if (!rc) rc = grow(&h->d_partial, &h->partial_bytes, std::max(partial, ((size_t)2 * h->sm_count * TC_QB + (size_t)nq) * sizeof(uint2)));
+        rc = grow(&h->d_texp, &h->texp_bytes, (size_t)np * (size_t)std::max<int64_t>(tiles, 1) * TC_TILE_BYTES);
+        if (!rc) rc = grow(&h->d_partial, &h->partial_bytes, std::max(partial, ((size_t)2 * h->sm_count * TC_QB + (size_t)np * (size_t)nq) * sizeof(uint2)));
     }
     if (rc) return rc;
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
@@ -944,11 +950,41 @@ extern "C" int hamx_match_pairs_dev(hamx_handle h, const hamx_pair* d_pairs, int
     ORBX_CUDA(cudaSetDevice(h->device));
     if (max_nq == 0) { ORBX_CUDA(cudaMemsetAsync(d_ngood, 0, (size_t)npairs * sizeof(int64_t), h->stream)); return ORBX_OK; }
     const int64_t nqb = (max_nq + HT_QB - 1) / HT_QB;
+    int rc = grow(&h->d_top2, &h->top2_bytes, (size_t)npairs * max_nq * sizeof(hamx_top2) + 16);
+    if (rc) return rc;
+    if (h->kernel_mode != HAMX_KERNEL_INTEGER && max_nt > 0 && (h->kernel_mode == HAMX_KERNEL_TENSOR || (int64_t)max_nq * max_nt >= (1ll << 20))) {
+        // tensor-core kernel, one launch for all pairs: every pair's train set is expanded into its own operand image first
+        rc = tc_prepare(h);
+        if (rc) return rc;
+        const int tiles = (max_nt + TC_TN - 1) / TC_TN;
+        const size_t pair_bytes = (size_t)tiles * TC_TILE_BYTES;
+        rc = grow(&h->d_texp, &h->texp_bytes, (size_t)npairs * pair_bytes);
+        if (rc) return rc;
+        const long long units = (long long)tiles * (TC_TILE_BYTES / 16);
+        k_expand_train<<<dim3((unsigned int)((units + 255) / 256), (unsigned int)npairs), 256, 0, h->stream>>>(nullptr, 0, d_pairs, pair_bytes / 16,
+                                                                                                          reinterpret_cast<uint4*>(h->d_texp));
+        ORBX_CUDA(cudaGetLastError());
+        int nsplit = nqb * npairs >= 2 * h->sm_count ? 1 : (int)std::min<int64_t>((2 * h->sm_count + nqb * npairs - 1) / (nqb * npairs), tiles);
+        const int tps = (tiles + nsplit - 1) / nsplit;
+        nsplit = (tiles + tps - 1) / tps;
+        if (nsplit > 1) {
+            rc = grow(&h->d_partial, &h->partial_bytes, (size_t)npairs * nsplit * max_nq * sizeof(uint2));
+            if (rc) return rc;
+            rc = grow(&h->d_arrivals, &h->arrivals_n, (size_t)npairs * nqb * sizeof(unsigned int), true, h->stream);
+            if (rc) return rc;
+        }
+        const dim3 grid((unsigned int)nqb, (unsigned int)nsplit, (unsigned int)npairs);
+        k_hamming_tc<false><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(nullptr, 0, h->d_texp, 0, d_pairs, pair_bytes, tps, h->d_partial,
+                                                                            (size_t)max_nq, h->d_arrivals, (int)nqb, h->d_top2, (size_t)max_nq, 0,
+                                                                            kNoP2P);
+        ORBX_CUDA(cudaGetLastError());
+        k_ratio_compact<<<npairs, 1024, 0, h->stream>>>(h->d_top2, (size_t)max_nq, 0, d_pairs, ratio, d_good, good_stride, (long long*)d_ngood);
+        ORBX_CUDA(cudaGetLastError());
+        return ORBX_OK;
+    }
     const int ntiles = max_nt > 0 ? (max_nt + HT_TT - 1) / HT_TT : 1;
     int nsplit, tps;
     plan_split(h->sm_count, nqb, ntiles, npairs, &nsplit, &tps);
-    int rc = grow(&h->d_top2, &h->top2_bytes, (size_t)npairs * max_nq * sizeof(hamx_top2) + 16);
-    if (rc) return rc;
     if (nsplit > 1) {
         rc = grow(&h->d_partial, &h->partial_bytes, (size_t)npairs * nsplit * max_nq * sizeof(uint2));
         if (rc) return rc;

@@ -57,9 +57,17 @@ __device__ __forceinline__ uint4 expand_bits16(uint32_t bits)
                       expand_nibble<TRAIN>((bits >> 12) & 15u));
 }
 
-// out: ceil(nt / 128) tiles of 36 KB in the shared-memory image described above; rows beyond nt are zero (masked by the consumer)
-__global__ void __launch_bounds__(256) k_expand_train(const uint8_t* __restrict__ t, int nt, uint4* __restrict__ out)
+// out: ceil(nt / 128) tiles of 36 KB in the shared-memory image described above; rows beyond nt are zero (masked by the consumer).
+// With a pair table (batched frame pairs) blockIdx.y selects the pair, whose image starts pair_stride 16-byte units further on.
+__global__ void __launch_bounds__(256) k_expand_train(const uint8_t* __restrict__ t, int nt, const hamx_pair* __restrict__ pairs,
+                                                      size_t pair_stride, uint4* __restrict__ out)
 {
+    if (pairs) {
+        const hamx_pair pd = pairs[blockIdx.y];
+        t = pd.nq > 0 ? pd.t : nullptr;
+        nt = pd.nq > 0 ? pd.nt : 0;
+        out += (size_t)blockIdx.y * pair_stride;
+    }
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte unit each
     const long long ntiles = (nt + TC_TN - 1) / TC_TN;
     if (u >= ntiles * (TC_TILE_BYTES / 16)) return;
@@ -114,14 +122,25 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Same launch geometry and split / merge protocol as k_hamming_knn2 (grid = (query blocks of 256, train splits)); `texp` is the
-// expanded train set of k_expand_train.
+// Same launch geometry and split / merge protocol as k_hamming_knn2 (grid = (query blocks of 256, train splits, pairs)); `texp`
+// is the expanded train set of k_expand_train.  With `pairs` the launch handles pair blockIdx.z of a device-resident table.
 template <bool P2P>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restrict__ texp, int nt, int tiles_per_split,
-             uint2* partial, size_t nq_stride, unsigned int* arrivals, hamx_top2* __restrict__ out, int64_t idx_offset,
-             const __grid_constant__ P2PView pv)
+k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restrict__ texp, int nt, const hamx_pair* __restrict__ pairs,
+             size_t texp_pair_stride, int tiles_per_split, uint2* partial, size_t nq_stride, unsigned int* arrivals, int qblocks_stride,
+             hamx_top2* __restrict__ out, size_t out_stride, int64_t idx_offset, const __grid_constant__ P2PView pv)
 {
+    if (pairs) {
+        const hamx_pair pd = pairs[blockIdx.z];
+        q_ = pd.q;
+        nq = pd.nq;
+        nt = pd.nt;
+        if ((int64_t)blockIdx.x * TC_QB >= nq) return;    // batched launches are sized for the largest pair
+        texp += (size_t)blockIdx.z * texp_pair_stride;
+        out += (size_t)blockIdx.z * out_stride;
+        partial += (size_t)blockIdx.z * gridDim.y * nq_stride;
+        arrivals += (size_t)blockIdx.z * qblocks_stride;
+    }
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem_base;

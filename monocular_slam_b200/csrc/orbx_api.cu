@@ -89,6 +89,7 @@ struct orbx_context {
     int32_t* h_counts;
     std::vector<uint8_t>* h_tab;
     int dev_pending;    // > 0: _dev submissions of up to this many frames have not been checked for overflow yet
+    bool dev_unordered; // such a submission may still be running and the copy stream has not been ordered behind it yet
     // sequence mode (orbx_match_consecutive)
     int last_nframes, last_cap;
     uint8_t* d_prev_desc;
@@ -851,6 +852,7 @@ extern "C" int orbx_extract_batch_dev(orbx_handle h, const uint8_t* d_frames, si
     rc = run_extract(h, 0, nframes, ORBX_DO_ANGLE | ORBX_DO_DESC, d_out, d_desc, cap, d_counts, 0);
     if (rc) return rc;
     h->dev_pending = std::max(h->dev_pending, nframes);
+    h->dev_unordered = true;
     h->last_nframes = h->filter_nframes = h->back_n = 0;     // the handle's own arrays were not written
     return ORBX_OK;
 }
@@ -865,6 +867,7 @@ extern "C" int orbx_check_dev(orbx_handle h)
     ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)n * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     h->dev_pending = 0;
+    h->dev_unordered = false;
     for (int f = 0; f < n; f++)
         if (h->h_ctr[f].overflow) {
             set_error("orbx_check_dev: frame slot %d overflowed (flags %d, %d keypoints)", f, h->h_ctr[f].overflow, h->h_ctr[f].total);
@@ -1166,9 +1169,10 @@ static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, co
     // the lane's slots are free: its previous batch was collected by orbx_wait_batch and the blocking entry points drain
     // the compute stream before they return.  Only an unchecked asynchronous _dev submission can still be using lane 0;
     // then (and only then: the wait would also serialise this upload behind the other lane's kernels) order behind it.
-    if (h->dev_pending) {
+    if (h->dev_unordered) {     // once: later uploads follow this one on the copy stream
         ORBX_CUDA(cudaEventRecord(h->order_event, h->stream));
         ORBX_CUDA(cudaStreamWaitEvent(h->copy_stream, h->order_event, 0));
+        h->dev_unordered = false;
     }
     rc = upload_frames(h, frames, 0, nframes, w, hh, stride, cudaMemcpyHostToDevice, h->copy_stream, s0);
     if (rc) return rc;

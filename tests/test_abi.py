@@ -40,10 +40,11 @@ def test_pod_layouts():
 
 
 def test_sass_is_blackwell_native():
-    """The matcher must be built for sm_100a and stage its train tiles with the TMA bulk-copy engine."""
+    """The matcher must be built for sm_100a, stage its train tiles with the TMA bulk-copy engine and use the 5th-generation tensor cores."""
     sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
     assert "sm_100a" in sass or "SM100" in sass.upper()
     assert "UBLKCP" in sass and "POPC" in sass and "SYNCS" in sass
+    assert "UTCIMMA" in sass and "LDTM" in sass          # tcgen05.mma (kind::i8) and tcgen05.ld: the tensor-core matcher
 
 
 @pytest.mark.skipif(_lib.lib().orbx_device_count() > 0, reason="a GPU is present")

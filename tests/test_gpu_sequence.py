@@ -27,11 +27,16 @@ def _check_matches(good_row, n, want):
     assert np.array_equal(g["distance"].astype(np.int32), d) and (g["img_idx"] == 0).all()
 
 
-def test_sequence_host_path():
+@pytest.mark.parametrize("kernel", ["auto", "integer", "tensor"])
+def test_sequence_host_path(kernel):
+    """Batched frame-pair matching runs on the tensor-core kernel when the pairs are large enough, on the integer-pipe kernel
+    otherwise (hamx_set_kernel): all three settings must reproduce the oracle."""
+    from monocular_slam_b200 import _lib
     seq = syn.sequence(7, 800, 600, seed=21)
     ext, matches = _oracle_sequence(seq, 1000, 0.8)
     orb = ORB(nfeatures=1000, max_size=(800, 600), max_batch=4)
     m = BFMatcher()
+    m.set_kernel({"auto": _lib.KERNEL_AUTO, "integer": _lib.KERNEL_INTEGER, "tensor": _lib.KERNEL_TENSOR}[kernel])
     cap = orb.default_cap
     # two submissions (4 + 3 frames): frame 4 must be matched against frame 3 of the previous batch
     done = 0

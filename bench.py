@@ -1028,8 +1028,16 @@ def run_ours(args, rank, world, local_rank):
             roofline.update({"sustained_fps": sustained["value"], "sustained_seconds": sustained["seconds"],
                              "sustained_sm_mhz": sustained["clocks"].get("sm_mhz")})
         if natural:
-            roofline.update({"natural_fps": natural["value"], "natural_fast_ms": natural["stages_ms_per_step"]["fast"],
-                             "dense_fast_ms": stages["fast"]})
+            nat_fast = natural["stages_ms_per_step"]["fast"]
+            nat_traffic = None
+            try:
+                nat_traffic = json.load(open(tp)).get("natural", {}).get("dram_bytes_per_launch") if (W, H, NFEAT, B) == (1920, 1080, 2000, 64) else None
+            except Exception:
+                pass
+            natural["roofline"] = {"kernel": "k_fast", "bound": "hbm", "achieved": level_px * B / (nat_fast * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": level_px * B / (nat_fast * 1e-3) / 1e9 / peak, "traffic": nat_traffic, "launch_ms": nat_fast}
+            roofline.update({"natural_fps": natural["value"], "natural_fast_ms": nat_fast, "dense_fast_ms": stages["fast"],
+                             "natural_fast_frac": natural["roofline"]["frac"], "natural_fast_traffic": nat_traffic})
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",

@@ -722,7 +722,7 @@ struct hamx_context {
     hamx_top2* d_p2p_local; size_t p2p_local_bytes;
     // tensor-core path: the train set expanded to +-1 bytes in the MMA operand image (hamming_tc.cuh)
     uint8_t* d_texp; size_t texp_bytes;
-    bool tc_ready;
+    bool tc_ready, loop_tc_ready;
     int kernel_mode;                   // HAMX_KERNEL_*
 };
 
@@ -1175,9 +1175,38 @@ extern "C" int hamx_loop_score_dev(hamx_handle h, const uint8_t* d_q, int nq, co
     if (nframes && nq) {
         ORBX_REQUIRE(d_q && d_frames && d_counts, "hamx_loop_score_dev: NULL pointer");
         if ((((uintptr_t)d_q) | ((uintptr_t)d_frames)) & 15) { set_error("hamx_loop_score_dev: descriptor pointers must be 16-byte aligned"); return ORBX_E_ALIGN; }
-        const dim3 grid((unsigned)((nq + HT_QB - 1) / HT_QB), (unsigned)nframes);
-        k_loop_score<<<grid, HT_THREADS, 0, h->stream>>>(d_q, nq, d_frames, d_counts, cap, n, (uint32_t)thr, d_scores);
-        ORBX_CUDA(cudaGetLastError());
+        const bool tc = h->kernel_mode == HAMX_KERNEL_TENSOR ||
+                        (h->kernel_mode == HAMX_KERNEL_AUTO && (int64_t)nq * cap * nframes >= (1ll << 24) && thr <= 256);
+        if (tc) {
+            // tensor-core formulation (hamming_tc.cuh): the stored frames are expanded into operand images, at most ~256 MB at a time
+            if (!h->loop_tc_ready) {
+                ORBX_CUDA(cudaFuncSetAttribute(k_loop_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+                h->loop_tc_ready = true;
+            }
+            const int tpf = (cap + TC_TN - 1) / TC_TN;
+            const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nframes, ((size_t)256 << 20) / ((size_t)tpf * TC_TILE_BYTES)));
+            int rc = grow(&h->d_texp, &h->texp_bytes, (size_t)chunk * tpf * TC_TILE_BYTES);
+            if (rc) return rc;
+            const unsigned int nqb = (unsigned int)((nq + TC_QB - 1) / TC_QB);
+            for (int c0 = 0; c0 < nframes; c0 += chunk) {
+                const int nf = std::min(chunk, nframes - c0);
+                const long long per_frame = (long long)tpf * (TC_TILE_BYTES / 16);
+                k_expand_frames<<<dim3((unsigned int)((per_frame + 255) / 256), (unsigned int)nf), 256, 0, h->stream>>>(
+                    d_frames + (size_t)c0 * cap * 32, d_counts + c0, cap, tpf, reinterpret_cast<uint4*>(h->d_texp));
+                ORBX_CUDA(cudaGetLastError());
+                // two CTAs' worth of work per SM, each walking a run of frames with its queries resident
+                int fpc = (int)std::max<int64_t>(1, ((int64_t)nf * nqb + 2 * h->sm_count - 1) / (2 * h->sm_count));
+                if (fpc > nf) fpc = nf;
+                const dim3 grid(nqb, (unsigned int)((nf + fpc - 1) / fpc));
+                k_loop_score_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(d_q, nq, h->d_texp, d_counts + c0, cap, nf, tpf, fpc, n, thr,
+                                                                                d_scores + c0);
+                ORBX_CUDA(cudaGetLastError());
+            }
+        } else {
+            const dim3 grid((unsigned)((nq + HT_QB - 1) / HT_QB), (unsigned)nframes);
+            k_loop_score<<<grid, HT_THREADS, 0, h->stream>>>(d_q, nq, d_frames, d_counts, cap, n, (uint32_t)thr, d_scores);
+            ORBX_CUDA(cudaGetLastError());
+        }
     }
     if (d_best) return hamx_loop_best_dev(h, d_scores, nframes, d_best);
     return ORBX_OK;

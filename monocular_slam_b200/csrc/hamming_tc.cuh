@@ -332,5 +332,158 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
     if (P2P) p2p_publish(pv, gridDim.x);      // one merging CTA per query block
 }
 
+// ---- loop-closure candidate scoring on the same machinery (k_loop_score's contract, hamming.cu) ---------------------------------
+// grid = (query blocks of 256, frame chunks).  A CTA keeps its 256 expanded queries in shared memory and walks the stored frames
+// [f0, f0 + frames_per_cta) of its chunk as ONE flat stream of train tiles (every frame occupies tiles_per_frame tiles of the
+// expanded image, so the producer and the MMA issuer do not see frame borders).  The folding warps count, per query, the keys
+// below the threshold (key < 128 thr - 16384  <=>  distance < thr, because the index part is < 128); at the last tile of a
+// frame the two warps that share a query add their counts in shared memory, the 16 warps meet at a named barrier, and the
+// count is clipped at n, reduced and added to the frame's score.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_loop_score_tc(const uint8_t* __restrict__ q_, int nq, const uint8_t* __restrict__ texp, const int32_t* __restrict__ counts, int cap, int nframes,
+                int tiles_per_frame, int frames_per_cta, int nbest, int thr, int32_t* __restrict__ scores)
+{
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_cnt[2][TC_QB];
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 2 * TC_TILE_BYTES;
+    const int f0 = blockIdx.y * frames_per_cta;
+    const int nf = max(min(f0 + frames_per_cta, nframes) - f0, 0);
+    const int ntiles = nf * tiles_per_frame;
+    const int qbase = blockIdx.x * TC_QB;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == TC_EPI_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int u = tid; u < 2 * TC_QB; u += TC_THREADS) (&s_cnt[0][0])[u] = 0;
+    for (int u = tid; u < TC_QB * TC_KC; u += TC_THREADS) {
+        const int row = u / TC_KC, kc = u - row * TC_KC;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (qbase + row < nq) {
+            if (kc < 16) v = expand_bits16<false>(*reinterpret_cast<const uint16_t*>(q_ + (size_t)(qbase + row) * 32 + 2 * kc));
+            else if (kc == 16) v.x = 1u;
+        }
+        const int blk = row >> 7, r = row & 127;
+        *reinterpret_cast<uint4*>(sA + blk * TC_TILE_BYTES + (r >> 3) * TC_SBO + kc * TC_LBO + (r & 7) * 16) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (wid == TC_EPI_WARPS) {
+        if (lane == 0) {
+            const uint8_t* src = texp + (size_t)f0 * tiles_per_frame * TC_TILE_BYTES;
+            for (int i = 0; i < ntiles; i++) {
+                const int s = i % TC_STAGES;
+                mbar_wait(&s_empty[s], ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
+                mbar_expect_tx(&s_full[s], (uint32_t)TC_TILE_BYTES);
+                tma_bulk_g2s(sB + s * TC_TILE_BYTES, src + (size_t)i * TC_TILE_BYTES, (uint32_t)TC_TILE_BYTES, &s_full[s]);
+            }
+        }
+    } else if (wid == TC_EPI_WARPS + 1) {
+        if (lane == 0) {
+            const uint64_t adesc0 = tc_smem_desc(smem_u32(sA)), adesc1 = tc_smem_desc(smem_u32(sA + TC_TILE_BYTES));
+            for (int i = 0; i < ntiles; i++) {
+                const int s = i % TC_STAGES, a = i & 1;
+                mbar_wait(&s_full[s], (uint32_t)(i / TC_STAGES) & 1u);
+                mbar_wait(&s_tempty[a], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint64_t bdesc = tc_smem_desc(smem_u32(sB + s * TC_TILE_BYTES));
+                const uint32_t d0 = tmem_base + (uint32_t)(a * 256), d1 = d0 + 128u;
+#pragma unroll
+                for (int k = 0; k < TC_KSTEPS; k++) {
+                    tc_mma_i8(d0, adesc0 + (uint64_t)(16 * k), bdesc + (uint64_t)(16 * k), TC_IDESC, k > 0);
+                    tc_mma_i8(d1, adesc1 + (uint64_t)(16 * k), bdesc + (uint64_t)(16 * k), TC_IDESC, k > 0);
+                }
+                tc_commit(&s_empty[s]);
+                tc_commit(&s_tfull[a]);
+            }
+        }
+    } else {
+        const int blk = (wid >> 2) & 1, half = wid >> 3;
+        const int row = (wid & 7) * 32 + lane;                 // this thread's query inside the CTA's 256
+        const uint32_t lane_base = (uint32_t)(32 * (wid & 3)) << 16;
+        const int T = 128 * thr - 16384;
+        int cnt = 0, fl = 0, ti = 0;
+        int nt = nf > 0 ? min(counts[f0], cap) : 0;
+        for (int i = 0; i < ntiles; i++) {
+            const int a = i & 1;
+            mbar_wait(&s_tfull[a], (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const int valid = max(min(TC_TN, nt - ti * TC_TN), 0);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int col0 = half * 64 + c * 32;
+                int v[32];
+                tc_ld32(tmem_base + lane_base + (uint32_t)(a * 256 + blk * 128 + col0), v);
+                if (col0 + 32 <= valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) cnt += v[j] < T ? 1 : 0;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) cnt += (col0 + j < valid && v[j] < T) ? 1 : 0;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_tempty[a]);
+            if (++ti == tiles_per_frame) {
+                // frame f0 + fl is complete for this thread's columns
+                int* slot = &s_cnt[fl & 1][row];
+                if (cnt) atomicAdd(slot, cnt);
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+                if (half == 0) {
+                    int c = qbase + row < nq ? min(*slot, nbest) : 0;
+                    *slot = 0;                                  // this buffer is next used two frames on, past the next barrier
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+                    if (lane == 0 && c) atomicAdd(&scores[f0 + fl], c);
+                }
+                cnt = 0; ti = 0; fl++;
+                if (fl < nf) nt = min(counts[f0 + fl], cap);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == TC_EPI_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Stored frames [nframes][cap][32] -> [nframes][tiles_per_frame] operand images (rows beyond a frame's count: zeros)
+__global__ void __launch_bounds__(256) k_expand_frames(const uint8_t* __restrict__ frames, const int32_t* __restrict__ counts, int cap, int tiles_per_frame,
+                                                       uint4* __restrict__ out)
+{
+    const int f = blockIdx.y;
+    const int nt = min(counts[f], cap);
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_frame = (long long)tiles_per_frame * (TC_TILE_BYTES / 16);
+    if (u >= per_frame) return;
+    const int tile = (int)(u / (TC_TILE_BYTES / 16)), r = (int)(u % (TC_TILE_BYTES / 16));
+    const int n1 = r / (TC_KC * 8), kc = (r / 8) % TC_KC, n0 = r & 7;
+    const int nl = n1 * 8 + n0, row = tile * TC_TN + nl;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < nt) {
+        if (kc < 16) v = expand_bits16<true>(*reinterpret_cast<const uint16_t*>(frames + ((size_t)f * cap + row) * 32 + 2 * kc));
+        else if (kc == 16) v.x = (uint32_t)nl;
+    }
+    out[(size_t)f * per_frame + u] = v;
+}
+
 }  // namespace
 }  // namespace orbx

@@ -5,15 +5,18 @@ import numpy as np
 import pytest
 
 import oracle
-from monocular_slam_b200 import BFMatcher
+from monocular_slam_b200 import BFMatcher, _lib
 from monocular_slam_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def bf():
+@pytest.fixture(scope="module", params=["auto", "integer", "tensor"])
+def bf(request):
+    """The scoring runs on the integer pipes (XOR + POPC) or on the tensor cores (the matcher's int8 contraction with a
+    counting epilogue); every test must hold for both and for the size-based choice."""
     m = BFMatcher()
+    m.set_kernel({"auto": _lib.KERNEL_AUTO, "integer": _lib.KERNEL_INTEGER, "tensor": _lib.KERNEL_TENSOR}[request.param])
     yield m
     m.close()
 
@@ -46,7 +49,7 @@ def test_nbest_low_entropy_ties(bf):
 
 
 @pytest.mark.parametrize("nq,nf,cap,n,thr", [(200, 9, 300, 10, 60), (2000, 12, 2100, 10, 40), (1, 3, 10, 10, 256), (300, 4, 128, 3, 118),
-                                               (257, 5, 256, 16, 100)])
+                                               (257, 5, 256, 16, 100), (700, 333, 129, 10, 125), (513, 40, 1000, 2, 131)])
 def test_loop_score_matches_oracle(bf, nq, nf, cap, n, thr):
     r = np.random.default_rng(nq + nf)
     q = r.integers(0, 256, (nq, 32), dtype=np.uint8)

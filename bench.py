@@ -978,6 +978,47 @@ def run_ours(args, rank, world, local_rank):
         roofline.update({"loop_gcmp_s": loop["value"], "loop_ms_per_query_frame": loop_ms})
         del lframes
 
+    # ---- frame ingest: the reference decodes every frame on the host (imread, src/FrameLoader.cpp:62).  The
+    # same frames as PNG / JPEG files in memory -> decode workers -> pinned slots -> the pipelined extract + match path: frames/s
+    # one worker sustains, frames/s of the whole ring on this box's cores, and the cores a GPU-bound rate would need
+    ingest = None
+    if world == 1 and not args.no_ingest:
+        try:
+            import cv2
+            from monocular_slam_b200.ingest import IngestRing, imread_unchanged
+            try:
+                ncpu = len(os.sched_getaffinity(0))
+            except Exception:
+                ncpu = os.cpu_count() or 1
+            ingest = {"host_cores": ncpu, "frame": "%dx%d gray" % (W, H), "gpu_bound_fps": e2e_value}
+            for fmt, ext, params in (("png", ".png", [cv2.IMWRITE_PNG_COMPRESSION, 3]), ("jpeg", ".jpg", [cv2.IMWRITE_JPEG_QUALITY, 90])):
+                enc = [cv2.imencode(ext, seq[i], params)[1].tobytes() for i in range(B)]
+                t0 = time.perf_counter()
+                for e in enc[:8]:
+                    imread_unchanged(e)
+                per_core = 8 / (time.perf_counter() - t0)
+                ring = IngestRing(orb, matcher, W, H, batch=B, workers=ncpu, ratio=RATIO)
+                nb = 0
+                for res in ring.run(enc * 2):       # first pass: warm-up
+                    nb += 1
+                ring.stats.update({"frames": 0, "decode_seconds": 0.0, "wall_seconds": 0.0})
+                reps = max(2, int(1.5 * per_core * ncpu / B))
+                kp_total = 0
+                for first, n, kps_, desc_, counts_, good_, ngood_ in ring.run(enc * reps):
+                    kp_total += int(counts_[:n].sum())
+                st = dict(ring.stats)
+                ring.close()
+                ingest[fmt] = {"bytes_per_frame": int(np.mean([len(e) for e in enc])), "decode_fps_per_core": per_core,
+                               "ring_fps": st["frames"] / st["wall_seconds"], "ring_workers": ncpu, "frames": st["frames"],
+                               "decode_fps_per_worker_in_ring": st["frames"] / max(st["decode_seconds"], 1e-9),
+                               "keypoints_per_frame": kp_total / max(st["frames"], 1),
+                               "cores_for_gpu_bound_rate": e2e_value / per_core}
+            e2e_extra = {"ingest_png_fps": ingest["png"]["ring_fps"], "ingest_jpeg_fps": ingest["jpeg"]["ring_fps"],
+                         "ingest_png_decode_fps_per_core": ingest["png"]["decode_fps_per_core"],
+                         "ingest_jpeg_decode_fps_per_core": ingest["jpeg"]["decode_fps_per_core"]}
+        except Exception as e:
+            ingest = {"failed": repr(e)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores -- the same B frames the GPU step
     # processes, dealt to one single-threaded cv2 process per core; plus the two thread settings BASELINE.md asks for
     cpu = None
@@ -1021,6 +1062,8 @@ def run_ours(args, rank, world, local_rank):
                "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None)}
         if single:
             e2e["single_frame_ms"] = single["ms_per_frame"]
+        if ingest and "png" in ingest:
+            e2e.update(e2e_extra)
         if cfg3:
             e2e["cfg3_e2e_fps"] = cfg3["e2e"]["value"]
             roofline["cfg3_fps"] = cfg3["value"]
@@ -1055,7 +1098,8 @@ def run_ours(args, rank, world, local_rank):
                 "single_frame": single,
                 "hamming": hamming,
                 "fundamental": fundamental,
-                "loop_closure": loop}
+                "loop_closure": loop,
+                "ingest": ingest}
         emit(line)
     matcher.close()
     orb.close()
@@ -1100,6 +1144,7 @@ def main():
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-triangulation", action="store_true")
     ap.add_argument("--no-loop", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true")
     ap.add_argument("--frame", default="1920x1080", help="frame size WxH (default: BASELINE.json configs[1]; 3840x2160 with --nfeatures 8000 is configs[2])")
     ap.add_argument("--nfeatures", type=int, default=2000)
     args = ap.parse_args()

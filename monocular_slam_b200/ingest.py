@@ -1,0 +1,118 @@
+"""Frame ingest in front of the extractor: encoded images -> host decode workers -> pinned slots -> orbx_submit_batch.
+
+The reference reads every frame with ``imread(path, CV_LOAD_IMAGE_UNCHANGED)`` on the host before anything else happens
+(src/FrameLoader.cpp:36-67, the call at :62).  PNG / JPEG entropy decoding is a serial bit stream per image and stays on the
+host here too (OpenCV's decoder, the one the reference calls); what this module adds is the plumbing that keeps the GPU fed:
+``workers`` threads decode straight into page-locked slots (cv2 releases the GIL while decoding), a full slot goes to the
+pipelined ``ORB.submit_batch`` (upload, extraction and matching overlap the decoding of the next slot), and gray conversion
+of colour frames happens on the device (orbx_set_input_channels), as cv::ORB does it on the CPU.  ``IngestRing.stats`` says
+how many frames per second one decode worker sustains, which is the number that tells how many host cores a given GPU rate
+needs (bench.py ``ingest``).
+"""
+import ctypes as C
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import _lib
+from ._lib import DMATCH_DTYPE, KEYPOINT_DTYPE, check
+
+
+def _pinned(shape, dtype):
+    """A numpy array over page-locked memory from orbx_host_alloc (freed by IngestRing.close)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    check(_lib.lib().orbx_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape), p
+
+
+def imread_unchanged(source):
+    """The reference's loader call: a path (imread) or encoded bytes (imdecode), flag IMREAD_UNCHANGED."""
+    import cv2
+    if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
+        img = cv2.imdecode(np.frombuffer(source, np.uint8) if not isinstance(source, np.ndarray) else source, cv2.IMREAD_UNCHANGED)
+    else:
+        img = cv2.imread(str(source), cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise ValueError("cannot decode %r" % (source if not isinstance(source, (bytes, bytearray, memoryview, np.ndarray)) else "<bytes>"))
+    return img
+
+
+class IngestRing:
+    """Decode -> pinned slot -> ``orb.submit_batch``.  ``channels`` = 1 (gray files) or 3 (BGR files, converted on the device).
+
+    ``run(sources)`` yields, per batch and in order, ``(first_index, n, kps, desc, counts, good, ngood)`` -- the arrays are
+    the ring's own pinned buffers and are overwritten ``pipeline_depth`` batches later, so consume or copy them."""
+
+    def __init__(self, orb, matcher, width, height, batch=None, workers=4, ratio=0.8, channels=1, decode=imread_unchanged):
+        self.orb, self.matcher, self.ratio = orb, matcher, float(ratio)
+        self.w, self.h, self.ch = int(width), int(height), int(channels)
+        self.batch = int(batch or orb.max_batch)
+        self.workers = int(workers)
+        self.decode = decode
+        self.depth = orb.pipeline_depth()
+        cap = self.cap = orb.default_cap
+        self._ptrs = []
+        shape = (self.batch, self.h, self.w) if self.ch == 1 else (self.batch, self.h, self.w, self.ch)
+        self.slots, self.outs = [], []
+        for _ in range(self.depth + 1):        # one slot is being filled while `depth` batches are in flight
+            a, p = _pinned(shape, np.uint8)
+            self._ptrs.append(p)
+            self.slots.append(a)
+            o = []
+            for shp, dt in (((self.batch, cap), KEYPOINT_DTYPE), ((self.batch, cap, 32), np.uint8), ((self.batch, cap), DMATCH_DTYPE)):
+                a, p = _pinned(shp, dt)
+                self._ptrs.append(p)
+                o.append(a)
+            self.outs.append((o[0], o[1], np.zeros(self.batch, np.int32), o[2], np.zeros(self.batch, np.int64)))
+        self.pool = ThreadPoolExecutor(self.workers)
+        self.stats = {"frames": 0, "decode_seconds": 0.0, "wall_seconds": 0.0, "workers": self.workers}
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
+            self.pool = None
+        while self.orb.batches_in_flight():
+            self.orb.wait_batch()
+        for p in self._ptrs:
+            _lib.lib().orbx_host_free(p)
+        self._ptrs = []
+
+    def _decode_into(self, source, dst):
+        t0 = time.perf_counter()
+        img = self.decode(source)
+        if img.shape[:2] != (self.h, self.w) or (img.ndim == 3) != (self.ch == 3) or img.dtype != np.uint8:
+            raise ValueError("decoded frame is %s %s, the ring was built for %dx%d with %d channel(s)" % (img.dtype, img.shape, self.w, self.h, self.ch))
+        np.copyto(dst, img)
+        return time.perf_counter() - t0
+
+    def run(self, sources):
+        sources = list(sources)
+        orb = self.orb
+        orb.reset_sequence()
+        pending = []                                  # (first index, n, slot index) of the batches in flight
+        t_start = time.perf_counter()
+        nslots = len(self.slots)
+
+        def collect():
+            first, n, si = pending.pop(0)
+            kps, desc, counts, good, ngood = orb.wait_batch()
+            return first, n, kps, desc, counts, good, ngood
+
+        for b, first in enumerate(range(0, len(sources), self.batch)):
+            n = min(self.batch, len(sources) - first)
+            si = b % nslots
+            slot = self.slots[si]
+            futs = [self.pool.submit(self._decode_into, sources[first + i], slot[i]) for i in range(n)]
+            # the oldest batch is collected while the workers decode (its slot is the one that will be filled next)
+            if len(pending) == self.depth:
+                yield collect()
+            self.stats["decode_seconds"] += sum(f.result() for f in futs)
+            orb.submit_batch([slot[i] for i in range(n)], self.matcher, self.ratio, self.outs[si])
+            pending.append((first, n, si))
+            self.stats["frames"] += n
+        while pending:
+            yield collect()
+        self.stats["wall_seconds"] += time.perf_counter() - t_start

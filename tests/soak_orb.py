@@ -30,11 +30,16 @@ def main():
         st = int(r.integers(0, 2))
         thr = int(r.choice([5, 10, 20, 20, 40, 80]))
         seed = int(r.integers(1 << 30))
-        kind = int(r.integers(0, 3))
+        kind = int(r.integers(0, 5))
         if kind == 0:
             img = syn.frame(seed, w, h, nrect=max(5, w * h // 4000))
         elif kind == 1:
             img = syn.textured_frame(seed, w, h)
+        elif kind == 2:
+            img = syn.natural_frame(seed, w, h)          # camera-like: K2's compass pre-test and work lists do the scoring
+        elif kind == 3:                                  # half camera-like, half corner-dense: per-row decisions differ inside a tile
+            img = syn.natural_frame(seed, w, h)
+            img[:, w // 2:] = syn.frame(seed + 1, w, h, nrect=max(5, w * h // 4000))[:, w // 2:]
         else:
             img = np.random.default_rng(seed).integers(0, 256, (h, w), dtype=np.uint8)      # white noise: corners everywhere
         P = oracle.Params(nfeatures=nf, scale_factor=sf, nlevels=nl, score_type=st, fast_threshold=thr)
@@ -46,6 +51,8 @@ def main():
             continue
         ok, od = oracle.detect_and_compute(img, P)
         k, d = orb.detectAndCompute(img)
+        if r.random() < 0.5:             # again on the same handle: K3's density hint of the first call now steers K2
+            k, d = orb.detectAndCompute(img)
         orb.close()
         same = len(k) == len(ok) and all(np.array_equal(k[f], ok[f]) for f in ok.dtype.names) and np.array_equal(d, od)
         if not same:
@@ -53,6 +60,7 @@ def main():
             print("EXTRACT MISMATCH: %dx%d nf %d sf %.2f nl %d score %d thr %d seed %d kind %d: %d vs %d keypoints"
                   % (w, h, nf, sf, nl, st, thr, seed, kind, len(k), len(ok)))
     print("%d frames compared in %.0f s (%d configurations rejected for an empty pyramid level): %d mismatches" % (nframes - skipped, time.time() - t0, skipped, bad))
+    from monocular_slam_b200 import _lib
     m = BFMatcher()
     badm = 0
     t0 = time.time()
@@ -67,6 +75,7 @@ def main():
             flips = r.integers(0, 256, (nq // 2, 32), dtype=np.uint8) & r.integers(0, 256, (nq // 2, 32), dtype=np.uint8) & r.integers(0, 256, (nq // 2, 32), dtype=np.uint8)
             q[: nq // 2] ^= flips * (r.random((nq // 2, 1)) < 0.7).astype(np.uint8)
         ratio = float(r.choice([0.6, 0.75, 0.8, 0.85, 1.0]))
+        m.set_kernel(int(r.choice([_lib.KERNEL_AUTO, _lib.KERNEL_INTEGER, _lib.KERNEL_TENSOR])))    # XOR + POPC or tcgen05 contraction
         good = m.match_ratio(q, t, ratio)
         gq, gt, gd = oracle.match_features(q, t, ratio)
         if not (np.array_equal(good["query_idx"], gq) and np.array_equal(good["train_idx"], gt) and np.array_equal(good["distance"].astype(np.int32), gd)):

@@ -1040,13 +1040,13 @@ def run_ours(args, rank, world, local_rank):
 
     clocks = sampler.summary()
     # kernels of liborbx.so per timed step: ingest; per part of the batch (ORBX_SPLIT=n cuts batches in n parts on n
-    # streams; default 1): 7 pyramid levels, FAST, score cut, Harris selection, orient+describe; then pair table, kNN2,
-    # ratio test
+    # streams; default 1): 7 pyramid levels, FAST, score cut, Harris selection, orient+describe; then pair table, train-set
+    # expansion, tensor-core kNN2, ratio test (profiles/r2_launches.csv)
     try:
         halves = max(1, min(int(os.environ.get("ORBX_SPLIT", "1")), B // 8))
     except ValueError:
         halves = 1
-    launches_per_step = 1 + halves * ((len(ws) - 1) + 4) + 3
+    launches_per_step = 1 + halves * ((len(ws) - 1) + 4) + 4
     if rank == 0:
         assert level_px == level_pixels()
         cfg = workload_config(world, B)

@@ -190,29 +190,28 @@ __device__ __forceinline__ void p2p_wait_world(const P2PView& pv)
     __syncthreads();
 }
 
-// called by every CTA that wrote results, after its last p2p_store; `writers` = number of such CTAs in the grid.  The
-// last of them publishes this rank's epoch to the world.  With pv.merge_out set (small query sets) that same CTA -- by
-// then the only one of the kernel still running -- also waits for the world's flags and does the merge, so one kernel
-// launch per rank computes, exchanges and reduces.
+// called by every CTA that wrote results, after its last p2p_store; `writers` = number of such CTAs in the grid (one per
+// block of HT_QB queries).  The last of them publishes this rank's epoch to the world.  With pv.merge_out set (small query
+// sets) every writer then waits for the world's flags and merges ITS OWN block of queries, so one kernel launch per rank
+// computes, exchanges and reduces -- and the reduction is spread over the writers instead of queueing behind one CTA (a
+// single CTA merging 2000 queries x 8 ranks cost as much as the all-gather it replaces).  At most 64 writers spin (the host
+// fuses only up to 16 k queries), far fewer than SMs, so the CTAs of the grid that have not run yet always find one.
 __device__ __forceinline__ void p2p_publish(const P2PView& pv, unsigned int writers)
 {
-    __shared__ int s_final;
     __threadfence_system();     // this thread's peer stores are visible system-wide before the flag can be
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int prev = atomicAdd(pv.done, 1u);
-        s_final = prev == writers - 1;
-        if (s_final) {
+        if (prev == writers - 1) {
             *pv.done = 0;       // ready for the next launch (stream-ordered)
             __threadfence_system();
             for (int r = 0; r < pv.world; r++) st_release_sys(pv.flags[r] + (pv.epoch & 1u) * pv.world + pv.rank, pv.epoch);
         }
     }
     if (pv.merge_out == nullptr) return;
-    __syncthreads();
-    if (!s_final) return;
     p2p_wait_world(pv);
-    for (long long i = threadIdx.x; i < pv.merge_nq; i += blockDim.x) pv.merge_out[i] = p2p_merge_one(pv, i);
+    const long long q0 = (long long)blockIdx.x * HT_QB, q1 = q0 + HT_QB < pv.merge_nq ? q0 + HT_QB : pv.merge_nq;
+    for (long long i = q0 + threadIdx.x; i < q1; i += blockDim.x) pv.merge_out[i] = p2p_merge_one(pv, i);
 }
 
 // grid = (query blocks, train splits, pairs).  partial is [pair][nsplit][nq_stride] (only touched when nsplit > 1); the

@@ -29,6 +29,7 @@ namespace {
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_QB = 256;                 // queries per CTA (two MMA row blocks of 128)
+static_assert(TC_QB == HT_QB, "the peer-memory epilogue (p2p_publish) merges one block of HT_QB queries per writer");
 constexpr int TC_TN = 128;                 // train rows per tile (MMA N)
 constexpr int TC_KC = 18;                  // 16-byte K chunks per row: 16 of descriptor bits, 1 with the index byte, 1 of zeros
 constexpr int TC_KSTEPS = TC_KC / 2;       // MMA K steps (32 bytes each)

@@ -123,6 +123,28 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 64 consecutive columns of this thread's TMEM lane as 32 registers: .pack::16b puts the low halves of two adjacent 32-bit
+// columns into one register (column 2r in bits 0-15, column 2r+1 in bits 16-31).  The keys fit 16 signed bits
+// (-16384 .. 16511), so nothing is lost and the min/max below handle two columns per instruction.
+__device__ __forceinline__ void tc_ld64_pack16(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+#ifndef TC_PACK16
+#define TC_PACK16 1
+#endif
+
 // Same launch geometry and split / merge protocol as k_hamming_knn2 (grid = (query blocks of 256, train splits, pairs)); `texp`
 // is the expanded train set of k_expand_train.  With `pairs` the launch handles pair blockIdx.z of a device-resident table.
 template <bool P2P>
@@ -227,8 +249,39 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
             tc_fence_after();
             const int tile = tile_begin + i;
             const int valid = min(TC_TN, nt - tile * TC_TN);
+            int t0 = TC_NONE_KEY, t1 = TC_NONE_KEY;
+            if (TC_PACK16 && half * 64 + 64 <= valid) {
+                // the warp's 64 columns as 32 registers of two 16-bit keys: each half-word lane keeps its own top-2 (even / odd
+                // columns) in two independent chains -- 5 packed min/max per 8 keys
+                uint32_t p[32];
+                tc_ld64_pack16(tmem_base + lane_base + (uint32_t)(a * 256 + blk * 128 + half * 64), p);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_tempty[a]);      // the registers hold everything this warp needs from the stage
+                uint32_t a0 = 0x7FFF7FFFu, a1 = 0x7FFF7FFFu, b0 = 0x7FFF7FFFu, b1 = 0x7FFF7FFFu;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const uint32_t lo = __vmins2(p[j], p[j + 1]), hi = __vmaxs2(p[j], p[j + 1]);
+                    const uint32_t m = __vmaxs2(a0, lo);
+                    a0 = __vmins2(a0, lo);
+                    a1 = __vimin3_s16x2(a1, m, hi);
+                    const uint32_t lo2 = __vmins2(p[j + 2], p[j + 3]), hi2 = __vmaxs2(p[j + 2], p[j + 3]);
+                    const uint32_t m2 = __vmaxs2(b0, lo2);
+                    b0 = __vmins2(b0, lo2);
+                    b1 = __vimin3_s16x2(b1, m2, hi2);
+                }
+                const uint32_t m = __vmaxs2(a0, b0);
+                a0 = __vmins2(a0, b0);
+                a1 = __vimin3_s16x2(a1, b1, m);
+                // (a0 <= a1) per half-word lane -> the two smallest of the four
+                const int el = (int)(short)(a0 & 0xFFFFu), eh = (int)a0 >> 16, fl = (int)(short)(a1 & 0xFFFFu), fh = (int)a1 >> 16;
+                t0 = min(el, eh);
+                t1 = __vimin3_s32(fl, fh, max(el, eh));
+                if (t1 == 0x7FFF) t1 = TC_NONE_KEY;
+                if (t0 == 0x7FFF) t0 = TC_NONE_KEY;
+            } else {
             // two independent insertion chains (even / odd column pairs) keep the min/max pipe busy; merged per tile
-            int t0 = TC_NONE_KEY, t1 = TC_NONE_KEY, u0 = TC_NONE_KEY, u1 = TC_NONE_KEY;
+            int u0 = TC_NONE_KEY, u1 = TC_NONE_KEY;
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 const int col0 = half * 64 + c * 32;
@@ -263,6 +316,7 @@ k_hamming_tc(const uint8_t* __restrict__ q_, int64_t nq, const uint8_t* __restri
                 const int lo = min(t0, u0), m = max(t0, u0);
                 t1 = __vimin3_s32(t1, u1, m);
                 t0 = lo;
+            }
             }
             // tile-local keys 128 ham - 16384 + n  ->  ham << 23 | (tile * 128 + n), folded into the running top-2
 #pragma unroll

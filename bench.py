@@ -698,11 +698,7 @@ def run_ours(args, rank, world, local_rank):
         ham_clk = (ham_sampler.summary().get("sm_mhz") or 1965.0) * 1e6
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         tmem_peak = world * sms * 64 * ham_clk / 4 / 1e9        # accumulators per second readable from tensor memory (64 B / clk / SM)
-        int8_peak = None
-        try:
-            int8_peak = 2 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) * world
-        except Exception:
-            pass
+        int8_peak = 4500.0 * world      # nominal dense int8 / fp8 TOP/s of a B200 (B200_PROFILING.md); no measured int8 peak exists
         hamming = {"value": gcmp, "unit": "Gcmp/s", "nq": nq, "nt_per_gpu": nt_shard, "ms_per_step": ham_ms, "clocks": ham_sampler.summary(),
                    "kernel": "tensor cores: +-1 int8 contraction (tcgen05.mma kind::i8, accumulators in tensor memory), integer pipes fold the top-2",
                    "workload": "%d queries x %d train rows per GPU (train-sharded; %s)" % (
@@ -714,11 +710,15 @@ def run_ours(args, rank, world, local_rank):
                                 "note": "ALGORITHMIC work of 8 POPC per 256-bit comparison (SURVEY.md 8d) against the register-only POPC "
                                         "microbenchmark (hamx_popc_peak) per GPU x n_gpus.  The product kernel issues no POPC at all (the distances "
                                         "come out of the tensor cores), hence frac >> 1; what bounds it is the tensor-memory read path: see roofline_tmem"},
-                   "roofline_tmem": {"bound": "tensor memory read (64 B / clk / SM: 16 int32 accumulators)", "achieved": gcmp, "peak": tmem_peak,
-                                     "unit": "G accumulators/s", "frac": gcmp / tmem_peak},
+                   "roofline_tmem": {"bound": "tensor memory read", "achieved": gcmp, "peak": tmem_peak, "unit": "G accumulators/s", "frac": gcmp / tmem_peak,
+                                     "bytes_per_clk_per_sm": gcmp * 1e9 * 4 / (world * sms * ham_clk),
+                                     "note": "every comparison is one 32-bit accumulator that has to leave tensor memory; peak = the 64 B/clk/SM measured "
+                                             "for plain tcgen05.ld in B300_MICROARCH.md.  The kernel reads with .pack::16b (two 16-bit keys per register) "
+                                             "and exceeds that figure, so it is a reference line, not a ceiling; the accumulator stage of a tile takes "
+                                             "longer to read than to compute, which is what keeps the tensor pipe at ~68 % (profiles/r2_hamming_tc.txt)"},
                    "roofline_tensor": {"bound": "tensor", "achieved": gcmp * 2 * 288 / 1e3, "peak": int8_peak, "unit": "TOP/s (int8, 288-byte K incl. the index step)",
                                        "frac": (gcmp * 2 * 288 / 1e3 / int8_peak) if int8_peak else None,
-                                       "peak_source": "2 x the measured bf16 GEMM burst of MEASURED_PEAKS.json (no int8 measurement exists; nominal ratio)"}}
+                                       "peak_source": "nominal 4.5 POP/s dense int8 per B200 (B200_PROFILING.md table); ncu's tensor-pipe-active of the same kernel agrees"}}
         # BASELINE.json configs[3]: map-vs-frame tracking match, 200k map descriptors x 2000 queries, train set sharded over the ranks
         mq = q[:2000].contiguous()
         m_nt = 200000 // world

@@ -35,7 +35,10 @@ constexpr int TC_KC = 18;                  // 16-byte K chunks per row: 16 of de
 constexpr int TC_KSTEPS = TC_KC / 2;       // MMA K steps (32 bytes each)
 constexpr uint32_t TC_LBO = 128, TC_SBO = TC_KC * 128;
 constexpr int TC_TILE_BYTES = 16 * (int)TC_SBO;   // 36 KB
-constexpr int TC_STAGES = 3;
+#ifndef TC_STAGES_N
+#define TC_STAGES_N 3
+#endif
+constexpr int TC_STAGES = TC_STAGES_N;
 constexpr int TC_NONE_KEY = 0x7FFFFFFF;
 // kind::i8 instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8-bit (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
 // N >> 3 at bit 17, M >> 4 at bit 24

@@ -30,6 +30,12 @@ def test_library_builds_and_exports_header():
     assert names == set(declared), "exported symbols differ from the header: %s" % (names ^ set(declared))
 
 
+def test_header_is_plain_c_and_matches_integration_md(tmp_path):
+    """include/orbx.h compiled as C99 (the boundary is a C ABI), together with the call sequences INTEGRATION.md documents."""
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
+                           os.path.join(ROOT, "tests", "cpp", "abi_c_check.c"), "-o", str(tmp_path / "abi_c_check.o")])
+
+
 def test_pod_layouts():
     assert _lib.KEYPOINT_DTYPE.itemsize == 28 and _lib.DMATCH_DTYPE.itemsize == 16 and _lib.TOP2_DTYPE.itemsize == 16
     assert C.sizeof(_lib.Params) == 36

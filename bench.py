@@ -369,7 +369,17 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     # every rank owns its own block of the sequence (frame sharding): B consecutive frames, seeded by rank
     seq = syn.sequence(B, W, H, seed=100 + rank)
-    h_frames = torch.from_numpy(seq).pin_memory()
+    if args.wc_frames:
+        # write-combined page-locked frames (orbx_host_alloc_wc): the host only writes them
+        import ctypes as _C
+        from monocular_slam_b200 import _lib as _LL
+        _p = _C.c_void_p()
+        _LL.check(_LL.lib().orbx_host_alloc_wc(seq.nbytes, _C.byref(_p)))
+        _wc = np.frombuffer((_C.c_uint8 * seq.nbytes).from_address(_p.value), np.uint8).reshape(seq.shape)
+        np.copyto(_wc, seq)
+        h_frames = torch.from_numpy(_wc)
+    else:
+        h_frames = torch.from_numpy(seq).pin_memory()
     d_frames = h_frames.to(dev, non_blocking=True)
     orb = ORB(nfeatures=NFEAT, max_size=(W, H), max_batch=B, device=local_rank)
     matcher = BFMatcher(device=local_rank)
@@ -1145,6 +1155,7 @@ def main():
     ap.add_argument("--no-triangulation", action="store_true")
     ap.add_argument("--no-loop", action="store_true")
     ap.add_argument("--no-ingest", action="store_true")
+    ap.add_argument("--wc-frames", action="store_true", help="keep the host frames in write-combined page-locked memory")
     ap.add_argument("--frame", default="1920x1080", help="frame size WxH (default: BASELINE.json configs[1]; 3840x2160 with --nfeatures 8000 is configs[2])")
     ap.add_argument("--nfeatures", type=int, default=2000)
     args = ap.parse_args()

@@ -85,6 +85,9 @@ ORBX_API int orbx_device_count(void);
 /* Page-locked host memory for frames and result buffers (callers that do not link the CUDA runtime themselves): copies
  * from / to such memory are asynchronous, which is what lets orbx_submit_batch overlap them with the kernels. */
 ORBX_API int orbx_host_alloc(size_t bytes, void** out);
+/* The same, write-combined: for buffers the host only WRITES (frames on their way to the device); reading them back on the
+ * host is very slow.  Freed with orbx_host_free. */
+ORBX_API int orbx_host_alloc_wc(size_t bytes, void** out);
 ORBX_API int orbx_host_free(void* p);
 ORBX_API void orbx_default_params(orbx_params* p);
 

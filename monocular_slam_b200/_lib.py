@@ -30,7 +30,7 @@ SYMBOLS = [
     "hamx_popc_peak", "hamx_match_pairs_dev", "hamx_match_consecutive_dev", "orbx_match_consecutive", "orbx_reset_sequence",
     "orbx_set_profiling", "orbx_read_profile", "orbx_submit_batch", "orbx_wait_batch", "orbx_batches_in_flight",
     "hamx_p2p_export", "hamx_p2p_import", "hamx_p2p_import_ptrs", "hamx_p2p_close", "hamx_knn2_p2p_dev",
-    "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev", "orbx_set_input_channels", "orbx_pipeline_depth", "hamx_match_back_dev", "hamx_update_history_dev", "orbx_match_back", "orbx_host_alloc", "orbx_host_free",
+    "hamx_knn2_p2p_scatter_dev", "hamx_p2p_merge_dev", "orbx_set_input_channels", "orbx_pipeline_depth", "hamx_match_back_dev", "hamx_update_history_dev", "orbx_match_back", "orbx_host_alloc", "orbx_host_alloc_wc", "orbx_host_free",
     "fmx_create", "fmx_destroy", "fmx_set_stream", "fmx_synchronize", "fmx_compute_fundamental", "fmx_fundamental_batch",
     "fmx_last_info", "fmx_fundamental_batch_dev", "fmx_filter_consecutive_dev", "orbx_filter_consecutive", "orbx_submit_batch_filtered", "fmx_filter_back_dev", "orbx_filter_back", "orbx_submit_batch_back",
     "hamx_get_stream", "fmx_get_stream", "hamx_reserve", "hamx_set_kernel", "hamx_nbest", "hamx_nbest_dev", "hamx_loop_score", "hamx_loop_score_dev", "hamx_loop_best_dev",
@@ -144,6 +144,7 @@ def lib():
     L.orbx_set_input_channels.argtypes = [vp, C.c_int]
     L.orbx_pipeline_depth.argtypes = [vp]
     L.orbx_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.orbx_host_alloc_wc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.orbx_host_free.argtypes = [vp]
     L.hamx_match_back_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_float, vp, vp]
     L.hamx_update_history_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]

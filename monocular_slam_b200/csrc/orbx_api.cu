@@ -303,6 +303,15 @@ extern "C" int orbx_host_alloc(size_t bytes, void** out)
     return ORBX_OK;
 }
 
+extern "C" int orbx_host_alloc_wc(size_t bytes, void** out)
+{
+    ORBX_REQUIRE(out != nullptr && bytes > 0, "orbx_host_alloc_wc: bad arguments");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocWriteCombined);
+    if (e != cudaSuccess) { set_error("orbx_host_alloc_wc: cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); *out = nullptr; return ORBX_E_ALLOC; }
+    return ORBX_OK;
+}
+
 extern "C" int orbx_host_free(void* p)
 {
     if (p) ORBX_CUDA(cudaFreeHost(p));

@@ -57,6 +57,13 @@ constexpr int ORBX_MAX_BACK = 8;
 constexpr int ORBX_SPLIT_MIN = 8;
 constexpr int ORBX_MAX_SPLIT = 8;       // a batch is split in two when each half has at least this many frames
 
+// The host reads the per-level counts, the total and the overflow flags of each frame; the score histograms behind them
+// (8 KB per frame, K3's scratch) stay on the device: a strided copy of the leading bytes of every FrameCounters.
+static cudaError_t copy_counters_d2h(FrameCounters* dst, const FrameCounters* src, int nframes, cudaStream_t s) {
+    return cudaMemcpy2DAsync(dst, sizeof(FrameCounters), src, sizeof(FrameCounters), offsetof(FrameCounters, hist), (size_t)nframes,
+                             cudaMemcpyDeviceToHost, s);
+}
+
 struct orbx_context {
     int device;
     orbx_params p;
@@ -791,7 +798,7 @@ static int extract_host(orbx_handle h, const uint8_t* const* frames, int nframes
     h->filter_nframes = 0;
     h->back_n = 0;
     h->last_cap = dcap;
-    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(copy_counters_d2h(h->h_ctr, h->d_ctr, nframes, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     for (int f = 0; f < nframes; f++) counts[f] = h->h_ctr[f].total;
     rc = check_counters(h, nframes, dcap);
@@ -873,7 +880,7 @@ extern "C" int orbx_check_dev(orbx_handle h)
     if (!h->dev_pending) { ORBX_CUDA(cudaStreamSynchronize(h->stream)); return ORBX_OK; }
     // only the slots the unchecked submissions used: a flag left in a higher slot by an earlier, larger batch is stale
     const int n = h->dev_pending;
-    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr, h->d_ctr, (size_t)n * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(copy_counters_d2h(h->h_ctr, h->d_ctr, n, h->stream));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     h->dev_pending = 0;
     h->dev_unordered = false;
@@ -1266,7 +1273,7 @@ static int submit_impl(orbx_handle h, hamx_handle m, fmx_handle fm, int back, co
     }
     ORBX_CUDA(cudaEventRecord(L.computed, h->stream));
     ORBX_CUDA(cudaStreamWaitEvent(h->d2h_stream, L.computed, 0));
-    ORBX_CUDA(cudaMemcpyAsync(h->h_ctr + s0, h->d_ctr + s0, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, h->d2h_stream));
+    ORBX_CUDA(copy_counters_d2h(h->h_ctr + s0, h->d_ctr + s0, nframes, h->d2h_stream));
     ORBX_CUDA(cudaMemcpyAsync(out, d_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->d2h_stream));
     ORBX_CUDA(cudaMemcpyAsync(desc, d_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, h->d2h_stream));
     if (m && back >= 1) {

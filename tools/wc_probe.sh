@@ -6,6 +6,6 @@ for F in "" "--wc-frames"; do
 import json
 d=json.loads(open('gpurun_out/wc.json').read())
 e=d['e2e']
-print("N=$N '$F': e2e %.0f fps (%.3f ms) blocking %.0f floor h2d %.3f ms (%.1f GB/s/GPU) d2h %.3f over %.3f" % (e['value'], e['ms_per_step'], e['blocking_value'], e['h2d_floor_ms'], e['h2d_floor_gbs_per_gpu'], e['d2h_floor_ms'], e['over_h2d_floor']))
+print("N=$N '$F': e2e %.0f fps (%.3f ms) blocking %.0f floor h2d %.3f ms (%.1f GB/s/GPU) d2h %.3f duplex %.3f over h2d %.3f over duplex %.3f" % (e['value'], e['ms_per_step'], e['blocking_value'], e['h2d_floor_ms'], e['h2d_floor_gbs_per_gpu'], e['d2h_floor_ms'], e['duplex_floor_ms'], e['over_h2d_floor'], e['over_duplex_floor']))
 PY
 done

@@ -52,6 +52,14 @@ constexpr int FM_SMEM_POINTS = 9000;  // pairs with at most this many correspond
 #ifdef FM_PROFILE
 __device__ unsigned long long g_fm_prof[8];     // cycles of thread 0 per phase, summed over CTAs (debug builds only)
 #define FM_TICK(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_fm_prof[k], (unsigned long long)(now_ - tick_)); tick_ = now_; } } while (0)
+constexpr int FM_PROF_PAIRS = 4096;
+__device__ unsigned long long g_fm_pair_ns[FM_PROF_PAIRS][2];    // %globaltimer when a pair's CTA starts and when it ends (every exit)
+__device__ __forceinline__ unsigned long long fm_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+struct FmPairTimer {
+    int pair;
+    __device__ explicit FmPairTimer(int p) : pair(p) { if (threadIdx.x == 0 && pair < FM_PROF_PAIRS) g_fm_pair_ns[pair][0] = fm_globaltimer(); }
+    __device__ ~FmPairTimer() { if (threadIdx.x == 0 && pair < FM_PROF_PAIRS) g_fm_pair_ns[pair][1] = fm_globaltimer(); }
+};
 #else
 #define FM_TICK(k) do { } while (0)
 #endif
@@ -548,6 +556,9 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     extern __shared__ __align__(16) unsigned char fm_smem[];
     FmShared& sh = *reinterpret_cast<FmShared*>(fm_smem);
     const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef FM_PROFILE
+    FmPairTimer pair_timer_(pair);
+#endif
     const int n = min(counts[pair], cap);
     const float2* P1 = pts1 + (size_t)pair * cap;
     const float2* P2 = pts2 + (size_t)pair * cap;
@@ -1045,7 +1056,6 @@ extern "C" int fmx_create(fmx_handle* out, int device)
     int optin = 0;
     ORBX_CUDA_OR(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), fmx_destroy(h));
     h->smem_optin = (size_t)optin;
-    ORBX_CUDA_OR(cudaFuncSetAttribute(k_fm_ransac<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin), fmx_destroy(h));
     ORBX_CUDA_OR(cudaFuncSetAttribute(k_fm_ransac<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin), fmx_destroy(h));
     ORBX_CUDA_OR(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), fmx_destroy(h));
     *out = h;
@@ -1096,16 +1106,12 @@ static int fm_launch(fmx_handle h, const float* d_pts1, const float* d_pts2, con
     const size_t smem = sizeof(FmShared) + (in_smem ? (size_t)max_count * 16 : 0);
     const float2* p1 = (const float2*)d_pts1;
     const float2* p2 = (const float2*)d_pts2;
-    // 256-thread CTAs (8 warps score one pair's candidates) measured faster than 128 at every batch size tried (64..640 pairs):
-    // the batch ends with its slowest pairs, and those finish sooner with more warps each.  ORBX_FM_THREADS=128 selects the
-    // small CTA for experiments.
-    bool wide = true;
-    if (const char* e = getenv("ORBX_FM_THREADS")) wide = atoi(e) >= 256;
-#define FM_LAUNCH(SM, T) k_fm_ransac<SM, T><<<npairs, T, smem, h->stream>>>(p1, p2, d_counts, cap, max_distance, confidence, 1000, d_status, d_F, d_info)
-    if (in_smem && wide) FM_LAUNCH(true, 256);
-    else if (in_smem) FM_LAUNCH(true, 128);
-    else if (wide) FM_LAUNCH(false, 256);
-    else FM_LAUNCH(false, 128);
+    // 256-thread CTAs (8 warps score one pair's candidates), two per SM.  Measured against 128 x 4, 192 x 3 and 256 x 3 (80
+    // registers) at 64 / 296 / 320 / 640 pairs: the batch ends with its slowest pairs, and those finish sooner with more warps
+    // and all 128 registers each (profiles/README.md).
+#define FM_LAUNCH(SM) k_fm_ransac<SM, 256><<<npairs, 256, smem, h->stream>>>(p1, p2, d_counts, cap, max_distance, confidence, 1000, d_status, d_F, d_info)
+    if (in_smem) FM_LAUNCH(true);
+    else FM_LAUNCH(false);
 #undef FM_LAUNCH
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
@@ -1239,6 +1245,14 @@ extern "C" __attribute__((visibility("default"))) int fmx_debug_profile(unsigned
     ORBX_CUDA(cudaDeviceSynchronize());
     ORBX_CUDA(cudaMemcpyFromSymbol(out8, g_fm_prof, sizeof(g_fm_prof)));
     if (reset) { unsigned long long z[8] = {0}; ORBX_CUDA(cudaMemcpyToSymbol(g_fm_prof, z, sizeof(z))); }
+    return ORBX_OK;
+}
+// start / end %globaltimer (ns) of the first npairs CTAs of the last launch
+extern "C" __attribute__((visibility("default"))) int fmx_debug_pair_times(unsigned long long* out, int npairs)
+{
+    ORBX_REQUIRE(npairs >= 0 && npairs <= FM_PROF_PAIRS, "fmx_debug_pair_times: %d pairs outside [0, %d]", npairs, FM_PROF_PAIRS);
+    ORBX_CUDA(cudaDeviceSynchronize());
+    ORBX_CUDA(cudaMemcpyFromSymbol(out, g_fm_pair_ns, (size_t)npairs * 2 * sizeof(unsigned long long)));
     return ORBX_OK;
 }
 #endif

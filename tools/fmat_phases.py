@@ -21,3 +21,14 @@ tot = v.sum()
 info = fm.last_info(npairs)
 print("pairs %d n %d inl %.2f: iterations mean %.1f; per-pair kcycles (thread 0) total %.1f" % (npairs, n, inl, info[:,1].mean(), tot / npairs / 1e3))
 for k in range(7): print("  %-18s %8.1f kcycles/pair  %5.1f %%" % (names[k], v[k] / npairs / 1e3, 100 * v[k] / tot))
+# per-pair latency: %globaltimer at the start and at the end of every pair's CTA in the last launch
+t = np.zeros((npairs, 2), np.uint64)
+L.fmx_debug_pair_times(t.ctypes.data_as(C.POINTER(C.c_ulonglong)), npairs)
+lat = (t[:, 1] - t[:, 0]).astype(np.float64) / 1e3
+start = (t[:, 0] - t[:, 0].min()).astype(np.float64) / 1e3
+end = (t[:, 1] - t[:, 0].min()).astype(np.float64) / 1e3
+it = info[:, 1]
+print("pair latency us: p50 %.0f  p90 %.0f  p99 %.0f  max %.0f   (iterations of the slowest pair: %d; correlation with iterations %.2f)"
+      % (np.percentile(lat, 50), np.percentile(lat, 90), np.percentile(lat, 99), lat.max(), it[lat.argmax()], np.corrcoef(lat, it)[0, 1]))
+print("pair start us:   p50 %.0f  p99 %.0f  max %.0f   (pairs that started after the first one ended: %d)" % (np.percentile(start, 50), np.percentile(start, 99), start.max(), int((start > end.min()).sum())))
+print("pair end us:     p50 %.0f  p99 %.0f  max %.0f = the launch" % (np.percentile(end, 50), np.percentile(end, 99), end.max()))

@@ -184,3 +184,99 @@ def layered_pair(seed, w, h, nlayers=4, motion=(2, 5)):
         y0, y1 = int(edges[layer]), int(edges[layer + 1])
         b[y0:y1] = big[y0 + sy:y1 + sy, sx:sx + w]
     return a, b
+
+
+# ---- bag-of-words vocabulary (DBoW2, ThirdParty/DBoW2/DBoW2/TemplatedVocabulary.h): there is no network to fetch a trained
+# ORB vocabulary from, so the tests and the bench use a synthetic tree of the same shape
+
+def vocabulary(seed, k=10, L=3, ragged=False, stop_frac=0.03):
+    """A k-ary vocabulary tree of depth L as the arrays the text format holds, in the order HKmeansStep creates nodes (the k
+    children of a node get consecutive ids, then each child is expanded): ``parent`` [N] int32 (node 0 is the root),
+    ``leaf`` [N] uint8 (the file's isLeaf column: flagged nodes get word ids in node order), ``desc`` [N][32] uint8,
+    ``weight`` [N] float64.  A child is its parent with fewer and fewer bits flipped per level, so descents are decided by a
+    few bits and ties between children are common.  ``ragged``: some nodes have fewer than k children, some branches end
+    early, and one childless node is not flagged as a word (the reference then ends the descent there with word id 0)."""
+    rng = np.random.default_rng(seed)
+    parent, leaf, desc, weight = [0], [0], [np.zeros(32, np.uint8)], [0.0]
+    unflagged_done = not ragged
+
+    def flips(d, nbits):
+        bits = np.unpackbits(d)
+        idx = rng.choice(256, size=nbits, replace=False)
+        bits[idx] ^= 1
+        return np.packbits(bits)
+
+    def expand(node, level):
+        nonlocal unflagged_done
+        nchild = k if not ragged else int(rng.integers(max(1, k - 3), k + 1))
+        first = len(parent)
+        for _ in range(nchild):
+            base = desc[node] if level > 1 else rng.integers(0, 256, 32, dtype=np.uint8)
+            parent.append(node)
+            leaf.append(0)
+            desc.append(flips(base, max(2, 96 >> (level - 1))) if level > 1 else base)
+            weight.append(0.0)
+        for c in range(first, first + nchild):
+            ends_early = ragged and level >= 2 and rng.random() < 0.15
+            if level == L or ends_early:
+                if ragged and not unflagged_done and level == L:
+                    unflagged_done = True                 # childless, not a word: weight from the file, word id 0
+                    weight[c] = float(rng.uniform(0.5, 9.0))
+                    continue
+                leaf[c] = 1
+                weight[c] = 0.0 if rng.random() < stop_frac else float(rng.uniform(0.5, 9.0))
+            else:
+                expand(c, level + 1)
+
+    expand(0, 1)
+    return {"k": int(k), "L": int(L), "parent": np.asarray(parent, np.int32), "leaf": np.asarray(leaf, np.uint8),
+            "desc": np.stack(desc).astype(np.uint8), "weight": np.asarray(weight, np.float64)}
+
+
+def vocabulary_features(seed, voc, n, pool=None, max_flips=6):
+    """n descriptors near the vocabulary's words: each is a word's descriptor (drawn from a pool of ``pool`` words, so words
+    repeat within a frame) with up to ``max_flips`` bits flipped."""
+    rng = np.random.default_rng(seed)
+    words = np.flatnonzero(voc["leaf"])
+    if pool is not None and pool < len(words):
+        words = rng.choice(words, size=pool, replace=False)
+    out = np.empty((n, 32), np.uint8)
+    for i in range(n):
+        bits = np.unpackbits(voc["desc"][rng.choice(words)])
+        nf = int(rng.integers(0, max_flips + 1))
+        if nf:
+            bits[rng.choice(256, size=nf, replace=False)] ^= 1
+        out[i] = np.packbits(bits)
+    return out
+
+
+def write_vocabulary_text(path, voc, scoring=0, weighting=0, trailing_newline=False):
+    """saveToTextFile's format (TemplatedVocabulary.h:1426-1448): "k L  scoring weighting", then one line per node after the
+    root: parent, isLeaf, the 32 descriptor bytes, the weight.  The reference writes a newline after the last node, and its
+    loader (:1329-1416, `while(!f.eof())`) then reads one more, empty, line as an extra child of the root whose descriptor
+    is never initialised; ``trailing_newline=False`` leaves that newline out so the file loads as what it says."""
+    lines = ["%d %d  %d %d" % (voc["k"], voc["L"], scoring, weighting)]
+    for i in range(1, len(voc["parent"])):
+        lines.append("%d %d %s %s" % (voc["parent"][i], 1 if voc["leaf"][i] else 0, " ".join(str(int(b)) for b in voc["desc"][i]) + " ",
+                                      repr(float(voc["weight"][i]))))
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + ("\n" if trailing_newline else ""))
+
+
+def read_vocabulary_text(path):
+    """The arrays of `vocabulary` plus ``scoring`` / ``weighting`` from a file in loadFromTextFile's format (empty lines are
+    skipped: the phantom node of a trailing newline is not reproduced, see write_vocabulary_text)."""
+    with open(path) as f:
+        head = f.readline().split()
+        k, L, scoring, weighting = (int(x) for x in head[:4])
+        parent, leaf, desc, weight = [0], [0], [np.zeros(32, np.uint8)], [0.0]
+        for line in f:
+            t = line.split()
+            if not t:
+                continue
+            parent.append(int(t[0]))
+            leaf.append(1 if int(t[1]) > 0 else 0)
+            desc.append(np.asarray([int(x) for x in t[2:34]], np.uint8))
+            weight.append(float(t[34]))
+    return {"k": k, "L": L, "scoring": scoring, "weighting": weighting, "parent": np.asarray(parent, np.int32),
+            "leaf": np.asarray(leaf, np.uint8), "desc": np.stack(desc), "weight": np.asarray(weight, np.float64)}

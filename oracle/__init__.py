@@ -45,7 +45,7 @@ class Params(C.Structure):
 
 def build(force=False):
     """Compile liborb_oracle.so with the committed Makefile (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "fmat_oracle.c", "tri_oracle.c", "loop_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "fmat_oracle.c", "tri_oracle.c", "loop_oracle.c", "bow_oracle.c")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -102,6 +102,23 @@ def lib():
         L.orc_nbest.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, i32p, i32p]
         L.orc_nbest.restype = None
         L.orc_loop_score.argtypes = [u8p, C.c_int, u8p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+        u32p = C.POINTER(C.c_uint32)
+        L.bow_voc_create.restype = C.c_void_p
+        L.bow_voc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, u8p, u8p, f64p]
+        L.bow_voc_free.argtypes = [C.c_void_p]
+        L.bow_voc_free.restype = None
+        L.bow_voc_words.argtypes = [C.c_void_p]
+        L.bow_transform_feature.argtypes = [C.c_void_p, u8p, C.c_int, u32p, f64p, u32p]
+        L.bow_transform_feature.restype = None
+        L.bow_transform.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, u32p, f64p, C.POINTER(C.c_int), u32p, i32p, u32p, C.POINTER(C.c_int)]
+        L.bow_transform.restype = None
+        L.bow_score.restype = C.c_double
+        L.bow_score.argtypes = [C.c_int, u32p, f64p, C.c_int, u32p, f64p, C.c_int]
+        L.bow_stop_words.argtypes = [C.c_void_p, C.c_double]
+        L.bow_parent_node.restype = C.c_uint32
+        L.bow_parent_node.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+        L.bow_word_weight.restype = C.c_double
+        L.bow_word_weight.argtypes = [C.c_void_p, C.c_uint32]
         _lib = L
     return _lib
 
@@ -442,3 +459,79 @@ def loop_score(d1, frames_desc, frame_counts, n=10, thr=40):
     counts = np.zeros(max(nf, 1), np.int32)
     best = lib().orc_loop_score(_u8(q), len(q), _u8(fd), _i32(fc), nf, cap, n, thr, _i32(counts))
     return counts[:nf], int(best)
+
+
+# ---- bag of words (bow_oracle.c; ThirdParty/DBoW2)
+TF_IDF, TF, IDF, BINARY = 0, 1, 2, 3
+L1_NORM, L2_NORM, CHI_SQUARE, KL, BHATTACHARYYA, DOT_PRODUCT = 0, 1, 2, 3, 4, 5
+
+
+def _u32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+class BowVocabulary:
+    """TemplatedVocabulary<FORB::TDescriptor, FORB> over the arrays of a text vocabulary (synthetic.vocabulary /
+    read_vocabulary_text): transform, score, stopWords, getParentNode, getWordWeight as bow_oracle.c restates them."""
+
+    def __init__(self, voc, scoring=L1_NORM, weighting=TF_IDF):
+        self.scoring, self.weighting = int(voc.get("scoring", scoring)), int(voc.get("weighting", weighting))
+        parent = np.ascontiguousarray(voc["parent"], np.int32)
+        leaf = np.ascontiguousarray(voc["leaf"], np.uint8)
+        desc = np.ascontiguousarray(voc["desc"], np.uint8)
+        weight = np.ascontiguousarray(voc["weight"], np.float64)
+        self._h = lib().bow_voc_create(int(voc["k"]), int(voc["L"]), self.scoring, self.weighting, len(parent), _i32(parent), _u8(leaf),
+                                       _u8(desc), _f64(weight))
+        if not self._h:
+            raise ValueError("bow_voc_create: parent[i] must be in [0, i)")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().bow_voc_free(self._h)
+            self._h = None
+
+    def size(self):
+        return lib().bow_voc_words(self._h)
+
+    def transform_features(self, desc, levelsup=0):
+        """Per feature: (word id, word weight, node id `levelsup` levels above the words)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word, weight, nid = np.zeros(n, np.uint32), np.zeros(n, np.float64), np.zeros(n, np.uint32)
+        for i in range(n):
+            lib().bow_transform_feature(self._h, _u8(desc[i]), levelsup, _u32(word[i:]), _f64(weight[i:]), _u32(nid[i:]))
+        return word, weight, nid
+
+    def transform(self, desc, levelsup=None):
+        """(words, values) of the BowVector; with ``levelsup`` also (nodes, offsets, features) of the FeatureVector."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        m = max(n, 1)
+        words, vals, nb = np.zeros(m, np.uint32), np.zeros(m, np.float64), C.c_int(0)
+        if levelsup is None:
+            lib().bow_transform(self._h, _u8(desc), n, 0, _u32(words), _f64(vals), C.byref(nb), None, None, None, None)
+            return words[:nb.value].copy(), vals[:nb.value].copy()
+        nodes, offs, feats, nf = np.zeros(m, np.uint32), np.zeros(m + 1, np.int32), np.zeros(m, np.uint32), C.c_int(0)
+        lib().bow_transform(self._h, _u8(desc), n, int(levelsup), _u32(words), _f64(vals), C.byref(nb), _u32(nodes), _i32(offs), _u32(feats),
+                            C.byref(nf))
+        k = nf.value
+        return words[:nb.value].copy(), vals[:nb.value].copy(), nodes[:k].copy(), offs[:k + 1].copy(), feats[:offs[k]].copy()
+
+    def score(self, a, b):
+        return bow_score(self.scoring, a, b)
+
+    def stop_words(self, min_weight):
+        return lib().bow_stop_words(self._h, float(min_weight))
+
+    def parent_node(self, wid, levelsup):
+        return int(lib().bow_parent_node(self._h, int(wid), int(levelsup)))
+
+    def word_weight(self, wid):
+        return float(lib().bow_word_weight(self._h, int(wid)))
+
+
+def bow_score(scoring, a, b):
+    """score(v1, v2) of the scoring object `scoring`; a, b = (words ascending, values)."""
+    w1, v1 = np.ascontiguousarray(a[0], np.uint32), np.ascontiguousarray(a[1], np.float64)
+    w2, v2 = np.ascontiguousarray(b[0], np.uint32), np.ascontiguousarray(b[1], np.float64)
+    return float(lib().bow_score(int(scoring), _u32(w1), _f64(v1), len(w1), _u32(w2), _f64(v2), len(w2)))

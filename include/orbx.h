@@ -407,6 +407,72 @@ ORBX_API int trx_select_new_dev(trx_handle h, const orbx_dmatch* d_good, const i
                        int32_t* d_cur_map, const int32_t* d_ncur, const int32_t* d_next_id, int nprob, int back, int cap,
                        uint8_t* d_accept, int32_t* d_nnew);
 
+/* ------------------------------------------------------------------ bag of words (vendored DBoW2: loop closing)
+ * The reference vendors DBoW2 with the ORB descriptor class (ThirdParty/DBoW2/DBoW2: TemplatedVocabulary.h, FORB.cpp,
+ * BowVector.cpp, FeatureVector.cpp, ScoringObject.cpp) for the loop closer its authors sketched (src/LoopCloser.cpp).  This
+ * family replaces TemplatedVocabulary<FORB::TDescriptor, FORB>: transform() of whole batches of frames straight from the
+ * extractor's device-resident descriptors, and score() of one bag-of-words vector against a database of them.
+ * Results are the reference's doubles bit for bit (sums run in std::map order); only KL scores, which go through log(),
+ * may differ in the last place.  One defined deviation: when a descent ends at a childless node above level L - levelsup
+ * the reference leaves the feature-vector node id unwritten (an uninitialised local); here it is the node the descent
+ * ended at. */
+typedef struct bowx_context* bowx_handle;
+enum { BOWX_TF_IDF = 0, BOWX_TF = 1, BOWX_IDF = 2, BOWX_BINARY = 3 };                    /* WeightingType, BowVector.h:36-42 */
+enum { BOWX_L1_NORM = 0, BOWX_L2_NORM = 1, BOWX_CHI_SQUARE = 2, BOWX_KL = 3, BOWX_BHATTACHARYYA = 4, BOWX_DOT_PRODUCT = 5 };  /* ScoringType, :45-53 */
+
+ORBX_API int bowx_create(bowx_handle* out, int device);
+ORBX_API int bowx_destroy(bowx_handle h);
+ORBX_API int bowx_set_stream(bowx_handle h, void* cuda_stream);    /* same rules as hamx_set_stream */
+ORBX_API int bowx_get_stream(bowx_handle h, void** cuda_stream);
+ORBX_API int bowx_synchronize(bowx_handle h);
+/* The vocabulary as loadFromTextFile reads it (TemplatedVocabulary.h:1333-1416): node 0 is the root, node i >= 1 is line i
+ * of the file with parent[i] < i, leaf[i] its isLeaf column (flagged nodes get word ids in node order), desc[i] its 32
+ * descriptor bytes, weight[i] its weight; k, L, scoring, weighting the header line.  Children keep node order; a descent
+ * ends at the first node without children, as isLeaf() does.  (A file written by saveToTextFile ends with a newline, which
+ * the reference's loader turns into one more child of the root with an uninitialised descriptor; pass the nodes the file
+ * lists.)  Blocking; replaces any previous vocabulary. */
+ORBX_API int bowx_set_vocabulary(bowx_handle h, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent,
+                                 const uint8_t* leaf, const uint8_t* desc, const double* weight);
+/* info[6] = {k, L, scoring, weighting, nodes, words}: getBranchingFactor, getDepthLevels, getScoringType, getWeightingType, size */
+ORBX_API int bowx_vocabulary_info(bowx_handle h, int32_t* info);
+/* stopWords(minWeight) (:1316-1329): words lighter than min_weight get weight 0 and are ignored from then on; *count of them */
+ORBX_API int bowx_stop_words(bowx_handle h, double min_weight, int32_t* count);
+/* getParentNode(wid, levelsup) (:1264-1275) and getWordWeight(wid) (:1042-1045) */
+ORBX_API int bowx_parent_node(bowx_handle h, uint32_t word, int levelsup, uint32_t* node);
+ORBX_API int bowx_word_weight(bowx_handle h, uint32_t word, double* weight);
+/* transform(feature, word, weight, nid, levelsup) (:1218-1260) for n descriptors [n][32]: the word each one falls into, the
+ * weight of the node its descent ended at, and the node `levelsup` levels above the words.  Blocking, host buffers. */
+ORBX_API int bowx_transform_features(bowx_handle h, const uint8_t* desc, int n, int levelsup, uint32_t* word, double* weight, uint32_t* node);
+/* the same for the first d_counts[f] descriptors of every frame f of a device-resident [nframes][cap][32] array (the layout of
+ * orbx_extract_batch_dev); outputs [nframes][cap]; asynchronous on the handle's stream */
+ORBX_API int bowx_transform_features_dev(bowx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int levelsup,
+                                         uint32_t* d_word, double* d_weight, uint32_t* d_node);
+/* transform(features, BowVector&, FeatureVector&, levelsup) (:1128-1199) for nframes frames: desc [nframes][cap][32] with
+ * counts[f] descriptors each (cap <= 16384).  Frame f's bag-of-words vector is bow_words / bow_vals [f*cap .. f*cap + nbow[f])
+ * in ascending word order (the iteration order of the std::map); its feature vector has nfv[f] nodes fv_nodes[f*cap + g] in
+ * ascending order, node g owning the feature indices fv_feats[f*cap + fv_offsets[f*(cap+1) + g] .. f*cap + fv_offsets[f*(cap+1) + g+1])
+ * in the order they were added.  The four fv_* pointers may all be NULL (the overload without a feature vector, :1064-1122).
+ * Blocking, host buffers. */
+ORBX_API int bowx_transform_batch(bowx_handle h, const uint8_t* desc, const int32_t* counts, int nframes, int cap, int levelsup,
+                                  uint32_t* bow_words, double* bow_vals, int32_t* nbow, uint32_t* fv_nodes, int32_t* fv_offsets,
+                                  uint32_t* fv_feats, int32_t* nfv);
+/* device-resident form, asynchronous on the handle's stream */
+ORBX_API int bowx_transform_batch_dev(bowx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int levelsup,
+                                      uint32_t* d_bow_words, double* d_bow_vals, int32_t* d_nbow, uint32_t* d_fv_nodes,
+                                      int32_t* d_fv_offsets, uint32_t* d_fv_feats, int32_t* d_nfv);
+/* score(v1, v2) of the vocabulary's scoring object (ScoringObject.cpp) for two vectors in ascending word order */
+ORBX_API int bowx_score(bowx_handle h, const uint32_t* words1, const double* vals1, int n1, const uint32_t* words2, const double* vals2,
+                        int n2, double* score);
+/* One query vector (as v1) against nentries stored vectors (each as v2): entry e is db_words / db_vals
+ * [db_start[e] .. db_start[e] + db_count[e]) of arrays db_len long -- a packed database or the padded output of
+ * bowx_transform_batch alike.  scores [nentries].  nq <= 12288. */
+ORBX_API int bowx_score_batch(bowx_handle h, const uint32_t* qwords, const double* qvals, int nq, const int64_t* db_start,
+                              const int32_t* db_count, const uint32_t* db_words, const double* db_vals, int64_t db_len, int nentries,
+                              double* scores);
+ORBX_API int bowx_score_batch_dev(bowx_handle h, const uint32_t* d_qwords, const double* d_qvals, int nq, const int64_t* d_db_start,
+                                  const int32_t* d_db_count, const uint32_t* d_db_words, const double* d_db_vals, int nentries,
+                                  double* d_scores);
+
 #ifdef __cplusplus
 }
 #endif

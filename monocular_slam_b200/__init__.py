@@ -8,3 +8,4 @@ algorithm on the CPU.
 from ._lib import (CAMERAS_DTYPE, DMATCH_DTYPE, FAST_SCORE, HARRIS_SCORE, KEYPOINT_DTYPE, LIB_PATH, TOP2_DTYPE, OrbxError, Params, build)  # noqa: F401
 from .orb import (NORM_HAMMING, ORB, BFMatcher, DataManager, FeatureExtractor, Features, Frame, FundamentalFilter,  # noqa: F401
                   ORB_create, OrbDescriptorExtractor, OrbFeatureDetector, Triangulator, match_features, popc_peak)
+from .bow import Vocabulary  # noqa: F401

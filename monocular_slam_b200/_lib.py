@@ -36,6 +36,9 @@ SYMBOLS = [
     "hamx_get_stream", "fmx_get_stream", "hamx_reserve", "hamx_set_kernel", "hamx_nbest", "hamx_nbest_dev", "hamx_loop_score", "hamx_loop_score_dev", "hamx_loop_best_dev",
     "trx_create", "trx_destroy", "trx_set_stream", "trx_get_stream", "trx_synchronize", "trx_triangulate", "trx_triangulate_hypotheses",
     "trx_triangulate_batch", "trx_triangulate_batch_dev", "trx_triangulate_back_dev", "trx_associate_dev", "trx_select_new_dev",
+    "bowx_create", "bowx_destroy", "bowx_set_stream", "bowx_get_stream", "bowx_synchronize", "bowx_set_vocabulary", "bowx_vocabulary_info",
+    "bowx_stop_words", "bowx_parent_node", "bowx_word_weight", "bowx_transform_features", "bowx_transform_features_dev",
+    "bowx_transform_batch", "bowx_transform_batch_dev", "bowx_score", "bowx_score_batch", "bowx_score_batch_dev",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -118,6 +121,23 @@ def lib():
     L.trx_triangulate_back_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.trx_associate_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.trx_select_new_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.bowx_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.bowx_destroy.argtypes = [vp]
+    L.bowx_set_stream.argtypes = [vp, vp]
+    L.bowx_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.bowx_synchronize.argtypes = [vp]
+    L.bowx_set_vocabulary.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.bowx_vocabulary_info.argtypes = [vp, i32p]
+    L.bowx_stop_words.argtypes = [vp, C.c_double, i32p]
+    L.bowx_parent_node.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
+    L.bowx_word_weight.argtypes = [vp, C.c_uint32, dp]
+    L.bowx_transform_features.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    L.bowx_transform_features_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.bowx_transform_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.bowx_transform_batch_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.bowx_score.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, dp]
+    L.bowx_score_batch.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int64, C.c_int, vp]
+    L.bowx_score_batch_dev.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp]
     L.hamx_nbest.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
     L.hamx_nbest_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
     L.hamx_loop_score.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, i32p]

@@ -1,0 +1,728 @@
+// bow.cu -- the bag-of-words side of loop closing (the reference vendors DBoW2 for it: ThirdParty/DBoW2), batched on the
+// device (sm_100a):
+//
+//   K14 k_bow_descend   TemplatedVocabulary::transform(feature, word, weight, nid, levelsup) (TemplatedVocabulary.h:1218-1260)
+//                       for every descriptor of every frame: at each level the child with the smallest FORB::distance
+//                       (FORB.cpp:81-101), the first one on ties.  A group of 16 (or 32) lanes owns a descriptor; each lane
+//                       holds one child: the vocabulary is stored so that the children of a node are consecutive 48-byte
+//                       records {descriptor, first child, child count, node id, word id}, one dependent load per level.
+//   K15 k_bow_build     transform(features, BowVector&, FeatureVector&, levelsup) (:1128-1199): one CTA per frame sorts
+//                       (word, feature) and (node, feature) keys in shared memory (std::map order), adds the word weights
+//                       as BowVector::addWeight / addIfNotExist do (BowVector.cpp:33-58), normalises as
+//                       BowVector::normalize does (:62-87) -- the sum runs in map order on one thread, so the doubles
+//                       are the reference's -- and writes the feature vector grouped by node (FeatureVector.cpp:28-43).
+//   K16 k_bow_score     GeneralScoring::score of one vector against many (ScoringObject.cpp:24-300): one warp per stored
+//                       vector, binary search of its words in the query, terms added in ascending word order.
+//
+// Doubles are IEEE (-fmad=false, correctly rounded division and sqrt), so every output except the KL score (log()) is
+// bit-identical to the reference's.
+#include <float.h>
+#include <math.h>
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace orbx {
+namespace {
+
+struct __align__(16) BowNode {      // 48 bytes; the children of a node are consecutive records
+    uint32_t desc[8];
+    int32_t child_base;             // record index of the first child
+    int32_t nchild;
+    uint32_t node_id;               // the vocabulary's own node id
+    uint32_t word_id;               // word id if the node is a word, else 0 (Node() default in the reference)
+};
+static_assert(sizeof(BowNode) == 48, "three 16-byte loads per record");
+
+constexpr int BOW_THREADS = 256;
+
+// ---- K14: tree descent.  LPF lanes per feature (16 when no node has more than 16 children).
+template <int LPF>
+__global__ void __launch_bounds__(BOW_THREADS)
+k_bow_descend(const BowNode* __restrict__ nodes, const double* __restrict__ weights, const uint8_t* __restrict__ desc,
+              const int32_t* __restrict__ counts, int nframes, int cap, int nid_level,
+              uint32_t* __restrict__ word, double* __restrict__ weight, uint32_t* __restrict__ nid)
+{
+    const int lane = threadIdx.x & 31, sub = lane & (LPF - 1);
+    const unsigned gmask = LPF == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+    const long long group = ((long long)blockIdx.x * BOW_THREADS + threadIdx.x) / LPF;
+    const long long total = (long long)nframes * cap;
+    if (group >= total) return;
+    const int frame = (int)(group / cap), f = (int)(group - (long long)frame * cap);
+    if (f >= counts[frame]) return;
+    const uint4* dp = reinterpret_cast<const uint4*>(desc + (size_t)group * 32);
+    const uint4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
+    int base = nodes[0].child_base, nch = nodes[0].nchild;
+    uint32_t out_nid = 0;
+    bool have_nid = nid_level <= 0;
+    int level = 0, final_rec = 0;
+    uint32_t out_word = 0;
+    while (nch > 0) {
+        unsigned best = 0xffffffffu;
+        uint4 info = make_uint4(0, 0, 0, 0);
+        for (int c = sub; c < nch; c += LPF) {
+            const uint4* rp = reinterpret_cast<const uint4*>(nodes + base + c);
+            const uint4 a = __ldg(rp), b = __ldg(rp + 1), i4 = __ldg(rp + 2);
+            const unsigned d = __popc(a.x ^ q0.x) + __popc(a.y ^ q0.y) + __popc(a.z ^ q0.z) + __popc(a.w ^ q0.w) +
+                               __popc(b.x ^ q1.x) + __popc(b.y ^ q1.y) + __popc(b.z ^ q1.z) + __popc(b.w ^ q1.w);
+            const unsigned key = (d << 20) | (unsigned)c;        // strict `<` in the reference: the first child wins a tie
+            if (key < best) { best = key; info = i4; }
+        }
+        unsigned m = best;
+#pragma unroll
+        for (int o = LPF / 2; o; o >>= 1) m = min(m, __shfl_xor_sync(gmask, m, o));
+        const unsigned owner = __ffs(__ballot_sync(gmask, best == m) & gmask) - 1;     // keys are distinct: exactly one lane
+        info.x = __shfl_sync(gmask, info.x, owner);
+        info.y = __shfl_sync(gmask, info.y, owner);
+        info.z = __shfl_sync(gmask, info.z, owner);
+        info.w = __shfl_sync(gmask, info.w, owner);
+        final_rec = base + (int)(m & 0xfffffu);
+        ++level;
+        if (level == nid_level) { out_nid = info.z; have_nid = true; }
+        base = (int)info.x; nch = (int)info.y;
+        if (nch == 0) { out_word = info.w; if (!have_nid) out_nid = info.z; }
+    }
+    if (sub == 0) {
+        word[group] = out_word;
+        weight[group] = level ? weights[final_rec] : 0.0;
+        nid[group] = out_nid;
+    }
+}
+
+// ---- K15: one frame's BowVector and FeatureVector
+__device__ __forceinline__ void bitonic_sort(unsigned long long* keys, int P)
+{
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// exclusive prefix sum of one flag per element over P elements (P a multiple of blockDim.x is not required); returns the total
+__device__ int block_compact_offsets(const unsigned long long* keys, int n, int shift, int* pos, int* s_warp)
+{
+    // pos[i] = number of heads before i, where i is a head when its key's upper bits differ from its predecessor's
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool head = i < n && (i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift));
+        const unsigned bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_carry;
+        for (int w = 0; w < warp; w++) before += s_warp[w];
+        if (i < n) pos[i] = before + __popc(bal & ((1u << lane) - 1));
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < nwarps; w++) t += s_warp[w]; s_carry += t; }
+        __syncthreads();
+    }
+    const int total = s_carry;
+    __syncthreads();            // the next call resets s_carry
+    return total;
+}
+
+__global__ void __launch_bounds__(BOW_THREADS)
+k_bow_build(const uint32_t* __restrict__ word, const double* __restrict__ weight, const uint32_t* __restrict__ nid,
+            const int32_t* __restrict__ counts, int cap, int P, int accumulate, int must, int l2,
+            uint32_t* __restrict__ bow_words, double* __restrict__ bow_vals, int32_t* __restrict__ nbow,
+            uint32_t* __restrict__ fv_nodes, int32_t* __restrict__ fv_offsets, uint32_t* __restrict__ fv_feats, int32_t* __restrict__ nfv)
+{
+    extern __shared__ __align__(16) unsigned char bow_smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(bow_smem);     // [P]
+    int* pos = reinterpret_cast<int*>(keys + P);                                    // [P]
+    __shared__ int s_warp[BOW_THREADS / 32];
+    __shared__ int s_nvalid;
+    __shared__ double s_norm;
+    const int frame = blockIdx.x, n = min(counts[frame], cap);
+    const size_t f0 = (size_t)frame * cap;
+    word += f0; weight += f0; nid += f0;
+    bow_words += f0; bow_vals += f0;
+
+    // (word, feature) keys of the features whose word is not stopped (w > 0), the others sort to the end
+    if (threadIdx.x == 0) s_nvalid = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const bool ok = i < n && weight[i] > 0;
+        keys[i] = ok ? ((unsigned long long)word[i] << 32) | (unsigned)i : ~0ULL;
+        mine += ok;
+    }
+    atomicAdd(&s_nvalid, mine);
+    __syncthreads();
+    const int nvalid = s_nvalid;
+    bitonic_sort(keys, P);
+    const int nb = block_compact_offsets(keys, nvalid, 32, pos, s_warp);
+    for (int i = threadIdx.x; i < nvalid; i += blockDim.x) {
+        const unsigned w = (unsigned)(keys[i] >> 32);
+        if (i == 0 || (unsigned)(keys[i - 1] >> 32) != w) {
+            const double wt = weight[(unsigned)keys[i]];
+            double v = wt;
+            if (accumulate)                                   // addWeight: v += w once per further occurrence, in order
+                for (int j = i + 1; j < nvalid && (unsigned)(keys[j] >> 32) == w; j++) v += wt;
+            bow_words[pos[i]] = w;
+            bow_vals[pos[i]] = v;
+        }
+    }
+    __syncthreads();
+    if (accumulate && nb > 0 && !must) {
+        const double nd = (double)nb;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) bow_vals[i] /= nd;
+    }
+    if (must) {
+        if (threadIdx.x == 0) {                                // BowVector::normalize sums in map order
+            double norm = 0.0;
+            if (!l2) for (int i = 0; i < nb; i++) norm += fabs(bow_vals[i]);
+            else { for (int i = 0; i < nb; i++) norm += bow_vals[i] * bow_vals[i]; norm = sqrt(norm); }
+            s_norm = norm;
+        }
+        __syncthreads();
+        const double norm = s_norm;
+        if (norm > 0.0)
+            for (int i = threadIdx.x; i < nb; i += blockDim.x) bow_vals[i] /= norm;
+    }
+    if (threadIdx.x == 0) nbow[frame] = nb;
+    if (!fv_nodes) return;
+
+    // (node, feature) keys: the feature vector, nodes ascending, each node's features in the order they were added
+    fv_nodes += f0; fv_feats += f0; fv_offsets += (size_t)frame * (cap + 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const bool ok = i < n && weight[i] > 0;
+        keys[i] = ok ? ((unsigned long long)nid[i] << 32) | (unsigned)i : ~0ULL;
+    }
+    __syncthreads();
+    bitonic_sort(keys, P);
+    const int ng = block_compact_offsets(keys, nvalid, 32, pos, s_warp);
+    for (int i = threadIdx.x; i < nvalid; i += blockDim.x) {
+        fv_feats[i] = (unsigned)keys[i];
+        if (i == 0 || (keys[i - 1] >> 32) != (keys[i] >> 32)) { fv_nodes[pos[i]] = (unsigned)(keys[i] >> 32); fv_offsets[pos[i]] = i; }
+    }
+    if (threadIdx.x == 0) { fv_offsets[ng] = nvalid; nfv[frame] = ng; }
+}
+
+// ---- K16: one query vector against M stored vectors
+enum { S_L1 = 0, S_L2 = 1, S_CHI = 2, S_KL = 3, S_BHAT = 4, S_DOT = 5 };
+
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_t key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int SCORING>
+__global__ void __launch_bounds__(BOW_THREADS)
+k_bow_score(const uint32_t* __restrict__ qwords, const double* __restrict__ qvals, int nq, const int64_t* __restrict__ db_start,
+            const int32_t* __restrict__ db_count, const uint32_t* __restrict__ db_words, const double* __restrict__ db_vals, int M,
+            double* __restrict__ scores)
+{
+    extern __shared__ __align__(16) unsigned char bow_smem[];
+    uint32_t* s_q = reinterpret_cast<uint32_t*>(bow_smem);       // the query's words
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[i] = qwords[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (BOW_THREADS / 32) + (threadIdx.x >> 5);
+    if (e >= M) return;
+    const uint32_t* w2 = db_words + db_start[e];
+    const double* v2 = db_vals + db_start[e];
+    const int n2 = db_count[e];
+    double score = 0;
+    if (SCORING == S_KL) {
+        // every word of the query contributes, in ascending order: with its partner in the stored vector, or alone
+        const double log_eps = log(DBL_EPSILON);
+        const uint32_t last2 = n2 > 0 ? w2[n2 - 1] : 0;
+        for (int i0 = 0; i0 < nq; i0 += 32) {
+            const int i = i0 + lane;
+            double term = 0;
+            bool add = false;
+            if (i < nq) {
+                const uint32_t w = s_q[i];
+                const double vi = qvals[i];
+                const int j = lower_bound_u32(w2, n2, w);
+                if (j < n2 && w2[j] == w) { const double wi = v2[j]; if (vi != 0 && wi != 0) { term = vi * log(vi / wi); add = true; } }
+                else if (n2 > 0 && w < last2) { term = vi * (log(vi) - log_eps); add = true; }       // inside the merge loop: unconditional
+                else if (vi != 0) { term = vi * (log(vi) - log_eps); add = true; }                   // after it: zero values skipped
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, add);
+            while (bal) {
+                const int b = __ffs(bal) - 1;
+                bal &= bal - 1;
+                score += __shfl_sync(0xffffffffu, term, b);
+            }
+        }
+    } else {
+        for (int j0 = 0; j0 < n2; j0 += 32) {
+            const int j = j0 + lane;
+            double term = 0;
+            bool add = false;
+            if (j < n2) {
+                const uint32_t w = w2[j];
+                const int i = lower_bound_u32(s_q, nq, w);
+                if (i < nq && s_q[i] == w) {
+                    const double vi = qvals[i], wi = v2[j];
+                    add = true;
+                    if (SCORING == S_L1) term = fabs(vi - wi) - fabs(vi) - fabs(wi);
+                    else if (SCORING == S_L2 || SCORING == S_DOT) term = vi * wi;
+                    else if (SCORING == S_CHI) { add = vi + wi != 0.0; if (add) term = vi * wi / (vi + wi); }
+                    else term = sqrt(vi * wi);
+                }
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, add);
+            while (bal) {
+                const int b = __ffs(bal) - 1;
+                bal &= bal - 1;
+                score += __shfl_sync(0xffffffffu, term, b);
+            }
+        }
+    }
+    if (SCORING == S_L1) score = -score / 2.0;
+    else if (SCORING == S_L2) score = score >= 1 ? 1.0 : 1.0 - sqrt(1.0 - score);
+    else if (SCORING == S_CHI) score = 2. * score;
+    if (lane == 0) scores[e] = score;
+}
+
+template <typename T>
+int bow_grow(T** p, size_t* have, size_t want)
+{
+    if (*p && *have >= want) return ORBX_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *have = 0; }
+    const size_t bytes = align_up(want + want / 4, 256);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e != cudaSuccess) { *p = nullptr; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ORBX_E_ALLOC; }
+    *have = bytes;
+    return ORBX_OK;
+}
+
+}  // namespace
+}  // namespace orbx
+
+using namespace orbx;
+
+struct bowx_context {
+    int device;
+    cudaStream_t own_stream, stream;
+    size_t smem_optin;
+    // vocabulary: host copy in the reference's numbering, device copy in child-contiguous record order
+    int k, L, scoring, weighting, nnodes, nwords, max_children;
+    std::vector<int32_t> parent, word_node, rec_of_node;
+    std::vector<double> weight;          // by node id
+    BowNode* d_nodes; size_t nodes_bytes;
+    double* d_weights; size_t weights_bytes;     // by record
+    // per-feature results of the descent (the staging of the host forms follows in d_buf)
+    uint32_t* d_word; size_t word_bytes;
+    double* d_weight; size_t weight_bytes;
+    uint32_t* d_nid; size_t nid_bytes;
+    uint8_t* d_buf; size_t buf_bytes;
+};
+
+extern "C" int bowx_destroy(bowx_handle h)
+{
+    if (!h) return ORBX_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_nodes); cudaFree(h->d_weights); cudaFree(h->d_word); cudaFree(h->d_weight); cudaFree(h->d_nid); cudaFree(h->d_buf);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return ORBX_OK;
+}
+
+extern "C" int bowx_create(bowx_handle* out, int device)
+{
+    ORBX_REQUIRE(out != nullptr, "bowx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { set_error("bowx_create: no CUDA device (%s); liborbx has no CPU fallback", cudaGetErrorString(e)); return ORBX_E_CUDA; }
+    ORBX_REQUIRE(device >= 0 && device < ndev, "bowx_create: device %d out of range [0,%d)", device, ndev);
+    ORBX_CUDA(cudaSetDevice(device));
+    bowx_context* h = new bowx_context();
+    h->device = device;
+    h->own_stream = h->stream = nullptr;
+    h->k = h->L = h->scoring = h->weighting = h->nnodes = h->nwords = h->max_children = 0;
+    h->d_nodes = nullptr; h->d_weights = nullptr; h->d_word = nullptr; h->d_weight = nullptr; h->d_nid = nullptr; h->d_buf = nullptr;
+    h->nodes_bytes = h->weights_bytes = h->word_bytes = h->weight_bytes = h->nid_bytes = h->buf_bytes = 0;
+    ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), bowx_destroy(h));
+    h->stream = h->own_stream;
+    int optin = 0;
+    ORBX_CUDA_OR(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), bowx_destroy(h));
+    h->smem_optin = (size_t)optin - 1024;       // dynamic part: k_bow_build also has a few static words
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024), bowx_destroy(h));
+    *out = h;
+    return ORBX_OK;
+}
+
+extern "C" int bowx_set_stream(bowx_handle h, void* cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr, "bowx_set_stream: NULL handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ORBX_OK;
+}
+
+extern "C" int bowx_get_stream(bowx_handle h, void** cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr && cuda_stream != nullptr, "bowx_get_stream: NULL argument");
+    *cuda_stream = h->stream == h->own_stream ? nullptr : (void*)h->stream;
+    return ORBX_OK;
+}
+
+extern "C" int bowx_synchronize(bowx_handle h)
+{
+    ORBX_REQUIRE(h != nullptr, "bowx_synchronize: NULL handle");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+static int upload_weights(bowx_handle h)
+{
+    std::vector<double> by_rec((size_t)h->nnodes);
+    for (int i = 0; i < h->nnodes; i++) by_rec[(size_t)h->rec_of_node[i]] = h->weight[(size_t)i];
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(cudaMemcpy(h->d_weights, by_rec.data(), sizeof(double) * (size_t)h->nnodes, cudaMemcpyHostToDevice));
+    return ORBX_OK;
+}
+
+extern "C" int bowx_set_vocabulary(bowx_handle h, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent,
+                                   const uint8_t* leaf, const uint8_t* desc, const double* weight)
+{
+    ORBX_REQUIRE(h != nullptr, "bowx_set_vocabulary: NULL handle");
+    ORBX_REQUIRE(parent && leaf && desc && weight, "bowx_set_vocabulary: NULL pointer");
+    ORBX_REQUIRE(nnodes >= 1 && nnodes < (1 << 20) * 16, "bowx_set_vocabulary: %d nodes out of range", nnodes);
+    ORBX_REQUIRE(scoring >= BOWX_L1_NORM && scoring <= BOWX_DOT_PRODUCT, "bowx_set_vocabulary: scoring type %d", scoring);
+    ORBX_REQUIRE(weighting >= BOWX_TF_IDF && weighting <= BOWX_BINARY, "bowx_set_vocabulary: weighting type %d", weighting);
+    for (int i = 1; i < nnodes; i++)
+        ORBX_REQUIRE(parent[i] >= 0 && parent[i] < i, "bowx_set_vocabulary: parent[%d] = %d is not an earlier node", i, parent[i]);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    // children of every node in node order (loadFromTextFile appends them as it reads)
+    std::vector<int32_t> off((size_t)nnodes + 1, 0), child((size_t)nnodes);
+    for (int i = 1; i < nnodes; i++) off[(size_t)parent[i] + 1]++;
+    int max_children = 0;
+    for (int i = 0; i < nnodes; i++) { max_children = std::max(max_children, off[(size_t)i + 1]); off[(size_t)i + 1] += off[(size_t)i]; }
+    ORBX_REQUIRE(max_children < (1 << 20), "bowx_set_vocabulary: a node with %d children", max_children);
+    {
+        std::vector<int32_t> fill(off.begin(), off.end() - 1);
+        for (int i = 1; i < nnodes; i++) child[(size_t)fill[(size_t)parent[i]]++] = i;
+    }
+    // records: breadth first, every node's children consecutive
+    std::vector<BowNode> rec((size_t)nnodes);
+    std::vector<int32_t> rec_of_node((size_t)nnodes, -1), order;
+    order.reserve((size_t)nnodes);
+    order.push_back(0);
+    rec_of_node[0] = 0;
+    int next = 1;
+    for (size_t q = 0; q < order.size(); q++) {
+        const int node = order[q];
+        for (int c = off[(size_t)node]; c < off[(size_t)node + 1]; c++) { rec_of_node[(size_t)child[(size_t)c]] = next++; order.push_back(child[(size_t)c]); }
+    }
+    h->word_node.clear();
+    std::vector<uint32_t> word_id((size_t)nnodes, 0);
+    for (int i = 1; i < nnodes; i++)
+        if (leaf[i]) { word_id[(size_t)i] = (uint32_t)h->word_node.size(); h->word_node.push_back(i); }
+    for (int i = 0; i < nnodes; i++) {
+        BowNode& r = rec[(size_t)rec_of_node[(size_t)i]];
+        memcpy(r.desc, desc + (size_t)i * 32, 32);
+        const int nch = off[(size_t)i + 1] - off[(size_t)i];
+        r.nchild = nch;
+        r.child_base = nch ? rec_of_node[(size_t)child[(size_t)off[(size_t)i]]] : 0;
+        r.node_id = (uint32_t)i;
+        r.word_id = word_id[(size_t)i];
+    }
+    int rc = bow_grow(&h->d_nodes, &h->nodes_bytes, sizeof(BowNode) * (size_t)nnodes);
+    if (!rc) rc = bow_grow(&h->d_weights, &h->weights_bytes, sizeof(double) * (size_t)nnodes);
+    if (rc) return rc;
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(cudaMemcpy(h->d_nodes, rec.data(), sizeof(BowNode) * (size_t)nnodes, cudaMemcpyHostToDevice));
+    h->k = k; h->L = L; h->scoring = scoring; h->weighting = weighting; h->nnodes = nnodes; h->nwords = (int)h->word_node.size();
+    h->max_children = max_children;
+    h->parent.assign(parent, parent + nnodes);
+    h->parent[0] = 0;
+    h->weight.assign(weight, weight + nnodes);
+    h->rec_of_node.swap(rec_of_node);
+    return upload_weights(h);
+}
+
+extern "C" int bowx_vocabulary_info(bowx_handle h, int32_t* info)
+{
+    ORBX_REQUIRE(h != nullptr && info != nullptr, "bowx_vocabulary_info: NULL argument");
+    info[0] = h->k; info[1] = h->L; info[2] = h->scoring; info[3] = h->weighting; info[4] = h->nnodes; info[5] = h->nwords;
+    return ORBX_OK;
+}
+
+extern "C" int bowx_stop_words(bowx_handle h, double min_weight, int32_t* count)
+{
+    ORBX_REQUIRE(h != nullptr && count != nullptr, "bowx_stop_words: NULL argument");
+    ORBX_REQUIRE(h->nnodes > 0, "bowx_stop_words: no vocabulary");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    int c = 0;
+    for (size_t w = 0; w < h->word_node.size(); w++) {
+        double& wt = h->weight[(size_t)h->word_node[w]];
+        if (wt < min_weight) { c++; wt = 0; }
+    }
+    *count = c;
+    return upload_weights(h);
+}
+
+extern "C" int bowx_parent_node(bowx_handle h, uint32_t word, int levelsup, uint32_t* node)
+{
+    ORBX_REQUIRE(h != nullptr && node != nullptr, "bowx_parent_node: NULL argument");
+    ORBX_REQUIRE(word < (uint32_t)h->nwords, "bowx_parent_node: word %u of %d", word, h->nwords);
+    int ret = h->word_node[word];
+    while (levelsup > 0 && ret != 0) { --levelsup; ret = h->parent[(size_t)ret]; }
+    *node = (uint32_t)ret;
+    return ORBX_OK;
+}
+
+extern "C" int bowx_word_weight(bowx_handle h, uint32_t word, double* weight)
+{
+    ORBX_REQUIRE(h != nullptr && weight != nullptr, "bowx_word_weight: NULL argument");
+    ORBX_REQUIRE(word < (uint32_t)h->nwords, "bowx_word_weight: word %u of %d", word, h->nwords);
+    *weight = h->weight[(size_t)h->word_node[word]];
+    return ORBX_OK;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static int descend(bowx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int levelsup,
+                   uint32_t* d_word, double* d_weight, uint32_t* d_nid)
+{
+    const long long total = (long long)nframes * cap;
+    if (total == 0) return ORBX_OK;
+    const int nid_level = h->L - levelsup;
+    if (h->max_children <= 16) {
+        const long long blocks = (total * 16 + BOW_THREADS - 1) / BOW_THREADS;
+        k_bow_descend<16><<<(unsigned)blocks, BOW_THREADS, 0, h->stream>>>(h->d_nodes, h->d_weights, d_desc, d_counts, nframes, cap, nid_level,
+                                                                         d_word, d_weight, d_nid);
+    } else {
+        const long long blocks = (total * 32 + BOW_THREADS - 1) / BOW_THREADS;
+        k_bow_descend<32><<<(unsigned)blocks, BOW_THREADS, 0, h->stream>>>(h->d_nodes, h->d_weights, d_desc, d_counts, nframes, cap, nid_level,
+                                                                         d_word, d_weight, d_nid);
+    }
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+static int check_transform_args(bowx_handle h, const char* fn, int nframes, int cap)
+{
+    ORBX_REQUIRE(h != nullptr, "%s: NULL handle", fn);
+    ORBX_REQUIRE(h->nnodes > 0, "%s: no vocabulary (bowx_set_vocabulary)", fn);
+    ORBX_REQUIRE(nframes >= 0 && cap >= 1, "%s: nframes %d / cap %d out of range", fn, nframes, cap);
+    ORBX_REQUIRE((long long)nframes * cap * 32 < (1LL << 40), "%s: %d frames x %d features is too large", fn, nframes, cap);
+    return ORBX_OK;
+}
+
+extern "C" int bowx_transform_features_dev(bowx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int levelsup,
+                                           uint32_t* d_word, double* d_weight, uint32_t* d_nid)
+{
+    int rc = check_transform_args(h, "bowx_transform_features_dev", nframes, cap);
+    if (rc) return rc;
+    ORBX_REQUIRE(d_desc && d_counts && d_word && d_weight && d_nid, "bowx_transform_features_dev: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    return descend(h, d_desc, d_counts, nframes, cap, levelsup, d_word, d_weight, d_nid);
+}
+
+extern "C" int bowx_transform_batch_dev(bowx_handle h, const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, int levelsup,
+                                        uint32_t* d_bow_words, double* d_bow_vals, int32_t* d_nbow, uint32_t* d_fv_nodes,
+                                        int32_t* d_fv_offsets, uint32_t* d_fv_feats, int32_t* d_nfv)
+{
+    int rc = check_transform_args(h, "bowx_transform_batch_dev", nframes, cap);
+    if (rc) return rc;
+    ORBX_REQUIRE(d_desc && d_counts && d_bow_words && d_bow_vals && d_nbow, "bowx_transform_batch_dev: NULL pointer");
+    const bool fv = d_fv_nodes || d_fv_offsets || d_fv_feats || d_nfv;
+    ORBX_REQUIRE(!fv || (d_fv_nodes && d_fv_offsets && d_fv_feats && d_nfv), "bowx_transform_batch_dev: the feature vector needs all four of its arrays");
+    const int P = next_pow2(std::max(cap, 32));
+    const size_t smem = (size_t)P * (sizeof(unsigned long long) + sizeof(int));
+    ORBX_REQUIRE(smem <= h->smem_optin, "bowx_transform_batch_dev: cap %d needs %zu bytes of shared memory (limit %zu): at most 16384 features per frame", cap, smem, h->smem_optin);
+    if (nframes == 0) return ORBX_OK;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t total = (size_t)nframes * cap;
+    rc = bow_grow(&h->d_word, &h->word_bytes, total * sizeof(uint32_t));
+    if (!rc) rc = bow_grow(&h->d_weight, &h->weight_bytes, total * sizeof(double));
+    if (!rc) rc = bow_grow(&h->d_nid, &h->nid_bytes, total * sizeof(uint32_t));
+    if (rc) return rc;
+    if (h->nwords == 0) {          // empty(): transform() returns empty vectors
+        ORBX_CUDA(cudaMemsetAsync(d_nbow, 0, sizeof(int32_t) * (size_t)nframes, h->stream));
+        if (fv) {
+            ORBX_CUDA(cudaMemsetAsync(d_nfv, 0, sizeof(int32_t) * (size_t)nframes, h->stream));
+            ORBX_CUDA(cudaMemsetAsync(d_fv_offsets, 0, sizeof(int32_t) * (size_t)nframes * ((size_t)cap + 1), h->stream));
+        }
+        return ORBX_OK;
+    }
+    rc = descend(h, d_desc, d_counts, nframes, cap, levelsup, h->d_word, h->d_weight, h->d_nid);
+    if (rc) return rc;
+    const int accumulate = h->weighting == BOWX_TF || h->weighting == BOWX_TF_IDF;
+    const int must = h->scoring != BOWX_DOT_PRODUCT, l2 = h->scoring == BOWX_L2_NORM;
+    k_bow_build<<<nframes, BOW_THREADS, smem, h->stream>>>(h->d_word, h->d_weight, h->d_nid, d_counts, cap, P, accumulate, must, l2, d_bow_words,
+                                                          d_bow_vals, d_nbow, fv ? d_fv_nodes : nullptr, d_fv_offsets, d_fv_feats, d_nfv);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+// carve `bytes` (rounded to 256) out of the staging buffer
+static uint8_t* carve(uint8_t*& p, size_t bytes) { uint8_t* r = p; p += align_up(bytes, 256); return r; }
+
+extern "C" int bowx_transform_features(bowx_handle h, const uint8_t* desc, int n, int levelsup, uint32_t* word, double* weight, uint32_t* node)
+{
+    int rc = check_transform_args(h, "bowx_transform_features", 1, std::max(n, 1));
+    if (rc) return rc;
+    ORBX_REQUIRE(n >= 0, "bowx_transform_features: n %d", n);
+    if (n == 0) return ORBX_OK;
+    ORBX_REQUIRE(desc && word && weight && node, "bowx_transform_features: NULL pointer");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t need = align_up((size_t)n * 32, 256) + 256 + align_up((size_t)n * 4, 256) * 2 + align_up((size_t)n * 8, 256);
+    rc = bow_grow(&h->d_buf, &h->buf_bytes, need);
+    if (rc) return rc;
+    uint8_t* p = h->d_buf;
+    uint8_t* d_desc = carve(p, (size_t)n * 32);
+    int32_t* d_count = (int32_t*)carve(p, 4);
+    uint32_t* d_word = (uint32_t*)carve(p, (size_t)n * 4);
+    uint32_t* d_nid = (uint32_t*)carve(p, (size_t)n * 4);
+    double* d_weight = (double*)carve(p, (size_t)n * 8);
+    ORBX_CUDA(cudaMemcpyAsync(d_desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(d_count, &n, 4, cudaMemcpyHostToDevice, h->stream));
+    rc = descend(h, d_desc, d_count, 1, n, levelsup, d_word, d_weight, d_nid);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(word, d_word, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(weight, d_weight, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(node, d_nid, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int bowx_transform_batch(bowx_handle h, const uint8_t* desc, const int32_t* counts, int nframes, int cap, int levelsup,
+                                    uint32_t* bow_words, double* bow_vals, int32_t* nbow, uint32_t* fv_nodes, int32_t* fv_offsets,
+                                    uint32_t* fv_feats, int32_t* nfv)
+{
+    int rc = check_transform_args(h, "bowx_transform_batch", nframes, cap);
+    if (rc) return rc;
+    if (nframes == 0) return ORBX_OK;
+    ORBX_REQUIRE(desc && counts && bow_words && bow_vals && nbow, "bowx_transform_batch: NULL pointer");
+    const bool fv = fv_nodes || fv_offsets || fv_feats || nfv;
+    ORBX_REQUIRE(!fv || (fv_nodes && fv_offsets && fv_feats && nfv), "bowx_transform_batch: the feature vector needs all four of its arrays");
+    for (int i = 0; i < nframes; i++)
+        ORBX_REQUIRE(counts[i] >= 0 && counts[i] <= cap, "bowx_transform_batch: counts[%d] = %d outside [0, cap = %d]", i, counts[i], cap);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t total = (size_t)nframes * cap, nf = (size_t)nframes;
+    const size_t need = align_up(total * 32, 256) + align_up(nf * 4, 256) * 3 + align_up(total * 4, 256) * 3 + align_up(total * 8, 256) +
+                        align_up(nf * ((size_t)cap + 1) * 4, 256);
+    rc = bow_grow(&h->d_buf, &h->buf_bytes, need);
+    if (rc) return rc;
+    uint8_t* p = h->d_buf;
+    uint8_t* d_desc = carve(p, total * 32);
+    int32_t* d_counts = (int32_t*)carve(p, nf * 4);
+    int32_t* d_nbow = (int32_t*)carve(p, nf * 4);
+    int32_t* d_nfv = (int32_t*)carve(p, nf * 4);
+    uint32_t* d_words = (uint32_t*)carve(p, total * 4);
+    uint32_t* d_nodes = (uint32_t*)carve(p, total * 4);
+    uint32_t* d_feats = (uint32_t*)carve(p, total * 4);
+    double* d_vals = (double*)carve(p, total * 8);
+    int32_t* d_offs = (int32_t*)carve(p, nf * ((size_t)cap + 1) * 4);
+    ORBX_CUDA(cudaMemcpyAsync(d_desc, desc, total * 32, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(d_counts, counts, nf * 4, cudaMemcpyHostToDevice, h->stream));
+    rc = bowx_transform_batch_dev(h, d_desc, d_counts, nframes, cap, levelsup, d_words, d_vals, d_nbow, fv ? d_nodes : nullptr,
+                                  fv ? d_offs : nullptr, fv ? d_feats : nullptr, fv ? d_nfv : nullptr);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(bow_words, d_words, total * 4, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(bow_vals, d_vals, total * 8, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(nbow, d_nbow, nf * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (fv) {
+        ORBX_CUDA(cudaMemcpyAsync(fv_nodes, d_nodes, total * 4, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(fv_offsets, d_offs, nf * ((size_t)cap + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(fv_feats, d_feats, total * 4, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(nfv, d_nfv, nf * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int bowx_score_batch_dev(bowx_handle h, const uint32_t* d_qwords, const double* d_qvals, int nq, const int64_t* d_db_start,
+                                    const int32_t* d_db_count, const uint32_t* d_db_words, const double* d_db_vals, int nentries,
+                                    double* d_scores)
+{
+    ORBX_REQUIRE(h != nullptr, "bowx_score_batch_dev: NULL handle");
+    ORBX_REQUIRE(h->nnodes > 0, "bowx_score_batch_dev: no vocabulary (its scoring type selects the score)");
+    ORBX_REQUIRE(nq >= 0 && nentries >= 0, "bowx_score_batch_dev: nq %d / nentries %d", nq, nentries);
+    if (nentries == 0) return ORBX_OK;
+    ORBX_REQUIRE((nq == 0 || (d_qwords && d_qvals)) && d_db_start && d_db_count && d_db_words && d_db_vals && d_scores, "bowx_score_batch_dev: NULL pointer");
+    const size_t smem = (size_t)std::max(nq, 1) * sizeof(uint32_t);
+    ORBX_REQUIRE(smem <= 48 * 1024, "bowx_score_batch_dev: a query of %d words (at most 12288)", nq);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const unsigned blocks = (unsigned)((nentries + BOW_THREADS / 32 - 1) / (BOW_THREADS / 32));
+#define BOW_SCORE(S) k_bow_score<S><<<blocks, BOW_THREADS, smem, h->stream>>>(d_qwords, d_qvals, nq, d_db_start, d_db_count, d_db_words, d_db_vals, nentries, d_scores)
+    switch (h->scoring) {
+    case BOWX_L1_NORM: BOW_SCORE(S_L1); break;
+    case BOWX_L2_NORM: BOW_SCORE(S_L2); break;
+    case BOWX_CHI_SQUARE: BOW_SCORE(S_CHI); break;
+    case BOWX_KL: BOW_SCORE(S_KL); break;
+    case BOWX_BHATTACHARYYA: BOW_SCORE(S_BHAT); break;
+    default: BOW_SCORE(S_DOT); break;
+    }
+#undef BOW_SCORE
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int bowx_score_batch(bowx_handle h, const uint32_t* qwords, const double* qvals, int nq, const int64_t* db_start,
+                                const int32_t* db_count, const uint32_t* db_words, const double* db_vals, int64_t db_len, int nentries,
+                                double* scores)
+{
+    ORBX_REQUIRE(h != nullptr, "bowx_score_batch: NULL handle");
+    ORBX_REQUIRE(nq >= 0 && nentries >= 0 && db_len >= 0, "bowx_score_batch: nq %d / nentries %d / db_len %lld", nq, nentries, (long long)db_len);
+    if (nentries == 0) return ORBX_OK;
+    ORBX_REQUIRE((nq == 0 || (qwords && qvals)) && db_start && db_count && (db_len == 0 || (db_words && db_vals)) && scores, "bowx_score_batch: NULL pointer");
+    for (int e = 0; e < nentries; e++)
+        ORBX_REQUIRE(db_count[e] >= 0 && db_start[e] >= 0 && db_start[e] + db_count[e] <= db_len,
+                     "bowx_score_batch: entry %d [%lld, +%d) outside the %lld stored words", e, (long long)db_start[e], db_count[e], (long long)db_len);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t ne = (size_t)nentries, q = (size_t)std::max(nq, 1), dl = (size_t)std::max<int64_t>(db_len, 1);
+    const size_t need = align_up(q * 4, 256) + align_up(q * 8, 256) + align_up(ne * 8, 256) * 2 + align_up(ne * 4, 256) + align_up(dl * 4, 256) +
+                        align_up(dl * 8, 256);
+    int rc = bow_grow(&h->d_buf, &h->buf_bytes, need);
+    if (rc) return rc;
+    uint8_t* p = h->d_buf;
+    uint32_t* d_qw = (uint32_t*)carve(p, q * 4);
+    double* d_qv = (double*)carve(p, q * 8);
+    int64_t* d_start = (int64_t*)carve(p, ne * 8);
+    double* d_scores = (double*)carve(p, ne * 8);
+    int32_t* d_cnt = (int32_t*)carve(p, ne * 4);
+    uint32_t* d_w = (uint32_t*)carve(p, dl * 4);
+    double* d_v = (double*)carve(p, dl * 8);
+    if (nq) {
+        ORBX_CUDA(cudaMemcpyAsync(d_qw, qwords, (size_t)nq * 4, cudaMemcpyHostToDevice, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(d_qv, qvals, (size_t)nq * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    ORBX_CUDA(cudaMemcpyAsync(d_start, db_start, ne * 8, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(d_cnt, db_count, ne * 4, cudaMemcpyHostToDevice, h->stream));
+    if (db_len) {
+        ORBX_CUDA(cudaMemcpyAsync(d_w, db_words, (size_t)db_len * 4, cudaMemcpyHostToDevice, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(d_v, db_vals, (size_t)db_len * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = bowx_score_batch_dev(h, d_qw, d_qv, nq, d_start, d_cnt, d_w, d_v, nentries, d_scores);
+    if (rc) return rc;
+    ORBX_CUDA(cudaMemcpyAsync(scores, d_scores, ne * 8, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int bowx_score(bowx_handle h, const uint32_t* words1, const double* vals1, int n1, const uint32_t* words2, const double* vals2,
+                          int n2, double* score)
+{
+    ORBX_REQUIRE(score != nullptr && n2 >= 0, "bowx_score: bad argument");
+    const int64_t start = 0;
+    const int32_t count = n2;
+    return bowx_score_batch(h, words1, vals1, n1, &start, &count, words2, vals2, n2, 1, score);
+}

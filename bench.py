@@ -998,6 +998,76 @@ def run_ours(args, rank, world, local_rank):
         roofline.update({"loop_gcmp_s": loop["value"], "loop_ms_per_query_frame": loop_ms})
         del lframes
 
+    # ---- bag of words (the DBoW2 half: ThirdParty/DBoW2): the batch's descriptors, still on the device,
+    # through a k = 10, L = 6 vocabulary (the ORB-SLAM shape, 1.1 M nodes, synthetic) into one BowVector + FeatureVector per
+    # frame, then one frame's vector scored against a database of stored vectors.  Frames are independent: sharded like the
+    # extraction, no collective.
+    bow = None
+    if not args.no_bow:
+        from monocular_slam_b200 import Vocabulary
+        vk, vL, levelsup, ndb = 10, 6, 4, 10000
+        va = syn.vocabulary_large(77, vk, vL)
+        voc = Vocabulary(va, device=local_rank)
+        voc.set_stream(stream.cuda_stream)
+        orb.extract_batch_dev(d_frames.data_ptr(), W * H, B, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
+        bw = torch.zeros((B, cap), dtype=torch.int32, device=dev); bv = torch.zeros((B, cap), dtype=torch.float64, device=dev)
+        bn = torch.zeros(B, dtype=torch.int32, device=dev); fn_ = torch.zeros(B, dtype=torch.int32, device=dev)
+        fnod = torch.zeros((B, cap), dtype=torch.int32, device=dev); foff = torch.zeros((B, cap + 1), dtype=torch.int32, device=dev)
+        ffe = torch.zeros((B, cap), dtype=torch.int32, device=dev)
+
+        def step_bow():
+            voc.transform_batch_dev(d_desc.data_ptr(), d_cnt.data_ptr(), B, cap, levelsup, bw.data_ptr(), bv.data_ptr(), bn.data_ptr(),
+                                    fnod.data_ptr(), foff.data_ptr(), ffe.data_ptr(), fn_.data_ptr())
+        reps = 10
+        bow_ms = max_over_ranks(timed(step_bow, reps, 3)[0]) / reps
+        nfeat = int(d_cnt.sum().item())
+        nbw = bn.cpu().numpy()
+        # the database: the batch's own vectors repeated up to ndb entries (entry e = frame e % B), padded layout
+        dstart = (torch.arange(ndb, dtype=torch.int64, device=dev) % B) * cap
+        dcount = bn[(torch.arange(ndb, device=dev) % B)].contiguous()
+        dscore = torch.zeros(ndb, dtype=torch.float64, device=dev)
+        # ... and a packed copy as large as ndb distinct vectors would be, so that the reads come from HBM, not from L2
+        per = int(nbw.max())
+        pw = bw[:, :per].repeat((ndb + B - 1) // B, 1)[:ndb].contiguous(); pv = bv[:, :per].repeat((ndb + B - 1) // B, 1)[:ndb].contiguous()
+        pstart = torch.arange(ndb, dtype=torch.int64, device=dev) * per
+
+        def step_score():
+            voc.score_batch_dev(bw[0].data_ptr(), bv[0].data_ptr(), int(nbw[0]), pstart.data_ptr(), dcount.data_ptr(), pw.data_ptr(), pv.data_ptr(), ndb,
+                                dscore.data_ptr())
+        score_ms = max_over_ranks(timed(step_score, reps, 3)[0]) / reps
+        sc = dscore.cpu().numpy()
+        assert abs(sc[0] - 1.0) < 1e-9 and sc.argmax() % B == 0, "a frame's best match in the database must be itself"
+        db_bytes = int(dcount.sum().item()) * 12
+        bow = {"value": world * nfeat / (bow_ms * 1e-3) / 1e6, "unit": "Mfeatures/s", "transform_ms_per_step": bow_ms,
+               "workload": "%d frames x %d descriptors through a k=%d L=%d vocabulary (%d nodes, %.0f MB of node records), levelsup %d: "
+                           "BowVector + FeatureVector per frame" % (B, cap, vk, vL, len(va["parent"]), len(va["parent"]) * 48 / 1e6, levelsup),
+               "words_per_frame": float(nbw.mean()),
+               "record_bytes_per_step": nfeat * vL * vk * 48, "record_gbs": nfeat * vL * vk * 48 / (bow_ms * 1e-3) / 1e9,
+               "score_ms": score_ms, "score_entries": ndb, "score_mentries_s": world * ndb / (score_ms * 1e-3) / 1e6,
+               "score_db_bytes": db_bytes, "score_gbs": db_bytes / (score_ms * 1e-3) / 1e9, "score_frac_hbm": db_bytes / (score_ms * 1e-3) / 1e9 / peak}
+        if world == 1 and not args.no_cpu:
+            try:
+                import oracle
+                ov = oracle.BowVocabulary(va)
+                hd, hc = d_desc[:4].cpu().numpy(), d_cnt[:4].cpu().numpy()
+                t0 = time.perf_counter()
+                obows = [ov.transform(hd[f, :hc[f]], levelsup) for f in range(4)]
+                o_s = time.perf_counter() - t0
+                for f in range(4):     # the oracle is the checker here too
+                    assert np.array_equal(obows[f][0], bw[f, :nbw[f]].cpu().numpy().view(np.uint32)) and np.array_equal(obows[f][1], bv[f, :nbw[f]].cpu().numpy())
+                t0 = time.perf_counter()
+                os_ = [ov.score(obows[0][:2], obows[e % 4][:2]) for e in range(400)]
+                s_s = time.perf_counter() - t0
+                assert os_[0] == sc[0] and os_[1] == sc[1]
+                bow["cpu_baseline"] = {"value": int(hc.sum()) / o_s / 1e6, "unit": "Mfeatures/s", "cores": 1, "kind": "port",
+                                       "sample": "oracle/bow_oracle.c transform() of the first 4 frames, one thread",
+                                       "score_mentries_s": 400 / s_s / 1e6}
+            except Exception as e:
+                bow["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
+        roofline.update({"bow_mfeatures_s": bow["value"], "bow_transform_ms": bow_ms, "bow_score_ms": score_ms, "bow_score_frac_hbm": bow["score_frac_hbm"]})
+        voc.close()
+        del pw, pv
+
     # ---- frame ingest: the reference decodes every frame on the host (imread, src/FrameLoader.cpp:62).  The
     # same frames as PNG / JPEG files in memory -> decode workers -> pinned slots -> the pipelined extract + match path: frames/s
     # one worker sustains, frames/s of the whole ring on this box's cores, and the cores a GPU-bound rate would need
@@ -1121,6 +1191,7 @@ def run_ours(args, rank, world, local_rank):
                 "hamming": hamming,
                 "fundamental": fundamental,
                 "loop_closure": loop,
+                "bag_of_words": bow,
                 "ingest": ingest}
         emit(line)
     matcher.close()
@@ -1166,6 +1237,7 @@ def main():
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-triangulation", action="store_true")
     ap.add_argument("--no-loop", action="store_true")
+    ap.add_argument("--no-bow", action="store_true")
     ap.add_argument("--no-ingest", action="store_true")
     ap.add_argument("--wc-frames", action="store_true", help="keep the host frames in write-combined page-locked memory")
     ap.add_argument("--frame", default="1920x1080", help="frame size WxH (default: BASELINE.json configs[1]; 3840x2160 with --nfeatures 8000 is configs[2])")

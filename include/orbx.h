@@ -465,7 +465,7 @@ ORBX_API int bowx_score(bowx_handle h, const uint32_t* words1, const double* val
                         int n2, double* score);
 /* One query vector (as v1) against nentries stored vectors (each as v2): entry e is db_words / db_vals
  * [db_start[e] .. db_start[e] + db_count[e]) of arrays db_len long -- a packed database or the padded output of
- * bowx_transform_batch alike.  scores [nentries].  nq <= 12288. */
+ * bowx_transform_batch alike.  scores [nentries].  nq <= 8192. */
 ORBX_API int bowx_score_batch(bowx_handle h, const uint32_t* qwords, const double* qvals, int nq, const int64_t* db_start,
                               const int32_t* db_count, const uint32_t* db_words, const double* db_vals, int64_t db_len, int nentries,
                               double* scores);

@@ -12,7 +12,8 @@
 //                       BowVector::normalize does (:62-87) -- the sum runs in map order on one thread, so the doubles
 //                       are the reference's -- and writes the feature vector grouped by node (FeatureVector.cpp:28-43).
 //   K16 k_bow_score     GeneralScoring::score of one vector against many (ScoringObject.cpp:24-300): one warp per stored
-//                       vector, binary search of its words in the query, terms added in ascending word order.
+//                       vector streams its words through a bit table of the query's words, looks the survivors up in the
+//                       query, and adds the terms of the common words in ascending word order.
 //
 // Doubles are IEEE (-fmad=false, correctly rounded division and sqrt), so every output except the KL score (log()) is
 // bit-identical to the reference's.
@@ -37,179 +38,191 @@ static_assert(sizeof(BowNode) == 48, "three 16-byte loads per record");
 
 constexpr int BOW_THREADS = 256;
 
-// ---- K14: tree descent.  LPF lanes per feature (16 when no node has more than 16 children).
+// ---- K14: tree descent.  LPF lanes per feature (16 when no node has more than 16 children).  All 32 lanes of a warp stay in
+// the level loop until both of its descriptors have reached a childless node, so every shuffle runs under the full mask
+// (xor offsets below LPF stay inside a group).
 template <int LPF>
 __global__ void __launch_bounds__(BOW_THREADS)
 k_bow_descend(const BowNode* __restrict__ nodes, const double* __restrict__ weights, const uint8_t* __restrict__ desc,
               const int32_t* __restrict__ counts, int nframes, int cap, int nid_level,
               uint32_t* __restrict__ word, double* __restrict__ weight, uint32_t* __restrict__ nid)
 {
-    const int lane = threadIdx.x & 31, sub = lane & (LPF - 1);
-    const unsigned gmask = LPF == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+    const int sub = threadIdx.x & (LPF - 1);
     const long long group = ((long long)blockIdx.x * BOW_THREADS + threadIdx.x) / LPF;
-    const long long total = (long long)nframes * cap;
-    if (group >= total) return;
-    const int frame = (int)(group / cap), f = (int)(group - (long long)frame * cap);
-    if (f >= counts[frame]) return;
-    const uint4* dp = reinterpret_cast<const uint4*>(desc + (size_t)group * 32);
-    const uint4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
-    int base = nodes[0].child_base, nch = nodes[0].nchild;
-    uint32_t out_nid = 0;
+    bool active = group < (long long)nframes * cap;
+    if (active) {
+        const int frame = (int)(group / cap);
+        active = (int)(group - (long long)frame * cap) < counts[frame];
+    }
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    int base = 0, nch = 0;
+    if (active) {
+        const uint4* dp = reinterpret_cast<const uint4*>(desc + (size_t)group * 32);
+        q0 = __ldg(dp); q1 = __ldg(dp + 1);
+        const uint4 root = __ldg(reinterpret_cast<const uint4*>(nodes) + 2);
+        base = (int)root.x; nch = (int)root.y;
+    }
+    uint32_t out_nid = 0, out_word = 0;
     bool have_nid = nid_level <= 0;
     int level = 0, final_rec = 0;
-    uint32_t out_word = 0;
-    while (nch > 0) {
+    while (__any_sync(0xffffffffu, nch > 0)) {
         unsigned best = 0xffffffffu;
-        uint4 info = make_uint4(0, 0, 0, 0);
         for (int c = sub; c < nch; c += LPF) {
             const uint4* rp = reinterpret_cast<const uint4*>(nodes + base + c);
-            const uint4 a = __ldg(rp), b = __ldg(rp + 1), i4 = __ldg(rp + 2);
+            const uint4 a = __ldg(rp), b = __ldg(rp + 1);
             const unsigned d = __popc(a.x ^ q0.x) + __popc(a.y ^ q0.y) + __popc(a.z ^ q0.z) + __popc(a.w ^ q0.w) +
                                __popc(b.x ^ q1.x) + __popc(b.y ^ q1.y) + __popc(b.z ^ q1.z) + __popc(b.w ^ q1.w);
-            const unsigned key = (d << 20) | (unsigned)c;        // strict `<` in the reference: the first child wins a tie
-            if (key < best) { best = key; info = i4; }
+            best = min(best, (d << 20) | (unsigned)c);           // strict `<` in the reference: the first child wins a tie
         }
-        unsigned m = best;
 #pragma unroll
-        for (int o = LPF / 2; o; o >>= 1) m = min(m, __shfl_xor_sync(gmask, m, o));
-        const unsigned owner = __ffs(__ballot_sync(gmask, best == m) & gmask) - 1;     // keys are distinct: exactly one lane
-        info.x = __shfl_sync(gmask, info.x, owner);
-        info.y = __shfl_sync(gmask, info.y, owner);
-        info.z = __shfl_sync(gmask, info.z, owner);
-        info.w = __shfl_sync(gmask, info.w, owner);
-        final_rec = base + (int)(m & 0xfffffu);
-        ++level;
-        if (level == nid_level) { out_nid = info.z; have_nid = true; }
-        base = (int)info.x; nch = (int)info.y;
-        if (nch == 0) { out_word = info.w; if (!have_nid) out_nid = info.z; }
+        for (int o = LPF / 2; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (nch > 0) {
+            final_rec = base + (int)(best & 0xfffffu);
+            const uint4 info = __ldg(reinterpret_cast<const uint4*>(nodes + final_rec) + 2);    // one address per group; the line is in L1
+            ++level;
+            if (level == nid_level) { out_nid = info.z; have_nid = true; }
+            base = (int)info.x; nch = (int)info.y;
+            if (nch == 0) { out_word = info.w; if (!have_nid) out_nid = info.z; }
+        }
     }
-    if (sub == 0) {
+    if (active && sub == 0) {
         word[group] = out_word;
         weight[group] = level ? weights[final_rec] : 0.0;
         nid[group] = out_nid;
     }
 }
 
-// ---- K15: one frame's BowVector and FeatureVector
-__device__ __forceinline__ void bitonic_sort(unsigned long long* keys, int P)
+// ---- K15: one frame's BowVector (blockIdx.y == 0) or FeatureVector (blockIdx.y == 1)
+constexpr int BOW_BUILD_THREADS = 1024;
+
+template <typename KeyT>
+__device__ __forceinline__ void bitonic_sort(KeyT* keys, int P)
 {
     for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
-                }
+            for (int t = threadIdx.x; t < P / 2; t += BOW_BUILD_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;      // the t-th pair of this stage
+                const KeyT a = keys[i], b = keys[ixj];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
             }
             __syncthreads();
         }
 }
 
-// exclusive prefix sum of one flag per element over P elements (P a multiple of blockDim.x is not required); returns the total
-__device__ int block_compact_offsets(const unsigned long long* keys, int n, int shift, int* pos, int* s_warp)
+// pos[i] = number of run heads before i (i is a head when its key's id differs from its predecessor's); returns the number of runs
+template <typename KeyT>
+__device__ int run_offsets(const KeyT* keys, int n, int shift, int* pos, int* s_warp, int* s_carry)
 {
-    // pos[i] = number of heads before i, where i is a head when its key's upper bits differ from its predecessor's
-    __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) *s_carry = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < n; i0 += BOW_BUILD_THREADS) {
         const int i = i0 + threadIdx.x;
         const bool head = i < n && (i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift));
         const unsigned bal = __ballot_sync(0xffffffffu, head);
         if (lane == 0) s_warp[warp] = __popc(bal);
         __syncthreads();
-        int before = s_carry;
-        for (int w = 0; w < warp; w++) before += s_warp[w];
-        if (i < n) pos[i] = before + __popc(bal & ((1u << lane) - 1));
+        if (warp == 0) {                       // exclusive scan of the 32 warp totals
+            const int v = s_warp[lane];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            s_warp[lane] = incl - v + *s_carry;
+            __syncwarp();
+            if (lane == 31) *s_carry += incl;
+        }
         __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < nwarps; w++) t += s_warp[w]; s_carry += t; }
+        if (i < n) pos[i] = s_warp[warp] + __popc(bal & ((1u << lane) - 1));
         __syncthreads();
     }
-    const int total = s_carry;
-    __syncthreads();            // the next call resets s_carry
-    return total;
+    return *s_carry;
 }
 
-__global__ void __launch_bounds__(BOW_THREADS)
+template <typename KeyT>
+__global__ void __launch_bounds__(BOW_BUILD_THREADS)
 k_bow_build(const uint32_t* __restrict__ word, const double* __restrict__ weight, const uint32_t* __restrict__ nid,
-            const int32_t* __restrict__ counts, int cap, int P, int accumulate, int must, int l2,
-            uint32_t* __restrict__ bow_words, double* __restrict__ bow_vals, int32_t* __restrict__ nbow,
-            uint32_t* __restrict__ fv_nodes, int32_t* __restrict__ fv_offsets, uint32_t* __restrict__ fv_feats, int32_t* __restrict__ nfv)
+            const int32_t* __restrict__ counts, int cap, int P, int shift, int accumulate, int must, int l2,
+            uint32_t* __restrict__ bow_words, double* bow_vals, int32_t* __restrict__ nbow,
+            uint32_t* __restrict__ fv_nodes, int32_t* __restrict__ fv_offsets, uint32_t* __restrict__ fv_feats, int32_t* __restrict__ nfv,
+            int first_part)
 {
     extern __shared__ __align__(16) unsigned char bow_smem[];
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(bow_smem);     // [P]
-    int* pos = reinterpret_cast<int*>(keys + P);                                    // [P]
-    __shared__ int s_warp[BOW_THREADS / 32];
-    __shared__ int s_nvalid;
+    KeyT* keys = reinterpret_cast<KeyT*>(bow_smem);                                 // [P]
+    int* pos = reinterpret_cast<int*>(bow_smem + (size_t)P * sizeof(KeyT));         // [P]
+    __shared__ int s_warp[32];
+    __shared__ int s_carry, s_nvalid;
     __shared__ double s_norm;
     const int frame = blockIdx.x, n = min(counts[frame], cap);
+    const bool feature_vector = first_part + (int)blockIdx.y == 1;
     const size_t f0 = (size_t)frame * cap;
-    word += f0; weight += f0; nid += f0;
-    bow_words += f0; bow_vals += f0;
+    const uint32_t* id = (feature_vector ? nid : word) + f0;
+    weight += f0;
+    const KeyT idx_mask = (KeyT)(((KeyT)1 << shift) - 1);
 
-    // (word, feature) keys of the features whose word is not stopped (w > 0), the others sort to the end
+    // (id, feature) keys of the features whose word is not stopped (w > 0); the others sort to the end
     if (threadIdx.x == 0) s_nvalid = 0;
     __syncthreads();
     int mine = 0;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    for (int i = threadIdx.x; i < P; i += BOW_BUILD_THREADS) {
         const bool ok = i < n && weight[i] > 0;
-        keys[i] = ok ? ((unsigned long long)word[i] << 32) | (unsigned)i : ~0ULL;
+        keys[i] = ok ? (KeyT)(((KeyT)id[i] << shift) | (KeyT)i) : (KeyT)~(KeyT)0;
         mine += ok;
     }
-    atomicAdd(&s_nvalid, mine);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_nvalid, mine);
     __syncthreads();
     const int nvalid = s_nvalid;
     bitonic_sort(keys, P);
-    const int nb = block_compact_offsets(keys, nvalid, 32, pos, s_warp);
-    for (int i = threadIdx.x; i < nvalid; i += blockDim.x) {
-        const unsigned w = (unsigned)(keys[i] >> 32);
-        if (i == 0 || (unsigned)(keys[i - 1] >> 32) != w) {
-            const double wt = weight[(unsigned)keys[i]];
+    const int nruns = run_offsets(keys, nvalid, shift, pos, s_warp, &s_carry);
+
+    if (feature_vector) {
+        // nodes ascending, each node's features in the order they were added (FeatureVector::addFeature)
+        fv_nodes += f0; fv_feats += f0; fv_offsets += (size_t)frame * (cap + 1);
+        for (int i = threadIdx.x; i < nvalid; i += BOW_BUILD_THREADS) {
+            fv_feats[i] = (uint32_t)(keys[i] & idx_mask);
+            if (i == 0 || (keys[i - 1] >> shift) != (keys[i] >> shift)) { fv_nodes[pos[i]] = (uint32_t)(keys[i] >> shift); fv_offsets[pos[i]] = i; }
+        }
+        if (threadIdx.x == 0) { fv_offsets[nruns] = nvalid; nfv[frame] = nruns; }
+        return;
+    }
+
+    bow_words += f0; bow_vals += f0;
+    const int nb = nruns;
+    for (int i = threadIdx.x; i < nvalid; i += BOW_BUILD_THREADS) {
+        const uint32_t w = (uint32_t)(keys[i] >> shift);
+        if (i == 0 || (uint32_t)(keys[i - 1] >> shift) != w) {
+            const double wt = weight[(uint32_t)(keys[i] & idx_mask)];
             double v = wt;
             if (accumulate)                                   // addWeight: v += w once per further occurrence, in order
-                for (int j = i + 1; j < nvalid && (unsigned)(keys[j] >> 32) == w; j++) v += wt;
+                for (int j = i + 1; j < nvalid && (uint32_t)(keys[j] >> shift) == w; j++) v += wt;
             bow_words[pos[i]] = w;
             bow_vals[pos[i]] = v;
         }
     }
-    __syncthreads();
-    if (accumulate && nb > 0 && !must) {
-        const double nd = (double)nb;
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) bow_vals[i] /= nd;
-    }
-    if (must) {
-        if (threadIdx.x == 0) {                                // BowVector::normalize sums in map order
-            double norm = 0.0;
-            if (!l2) for (int i = 0; i < nb; i++) norm += fabs(bow_vals[i]);
-            else { for (int i = 0; i < nb; i++) norm += bow_vals[i] * bow_vals[i]; norm = sqrt(norm); }
-            s_norm = norm;
-        }
-        __syncthreads();
-        const double norm = s_norm;
-        if (norm > 0.0)
-            for (int i = threadIdx.x; i < nb; i += blockDim.x) bow_vals[i] /= norm;
-    }
     if (threadIdx.x == 0) nbow[frame] = nb;
-    if (!fv_nodes) return;
-
-    // (node, feature) keys: the feature vector, nodes ascending, each node's features in the order they were added
-    fv_nodes += f0; fv_feats += f0; fv_offsets += (size_t)frame * (cap + 1);
+    if (!(accumulate && nb > 0 && !must) && !must) return;
     __syncthreads();
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        const bool ok = i < n && weight[i] > 0;
-        keys[i] = ok ? ((unsigned long long)nid[i] << 32) | (unsigned)i : ~0ULL;
+    if (!must) {                                              // TF / TF_IDF without normalisation: v /= v.size()
+        const double nd = (double)nb;
+        for (int i = threadIdx.x; i < nb; i += BOW_BUILD_THREADS) bow_vals[i] /= nd;
+        return;
+    }
+    // BowVector::normalize sums in map order: the values go to shared memory (the keys are dead), one thread adds them up
+    double* sv = reinterpret_cast<double*>(bow_smem);
+    for (int i = threadIdx.x; i < nb; i += BOW_BUILD_THREADS) sv[i] = bow_vals[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double norm = 0.0;
+        if (!l2) for (int i = 0; i < nb; i++) norm += fabs(sv[i]);
+        else { for (int i = 0; i < nb; i++) norm += sv[i] * sv[i]; norm = sqrt(norm); }
+        s_norm = norm;
     }
     __syncthreads();
-    bitonic_sort(keys, P);
-    const int ng = block_compact_offsets(keys, nvalid, 32, pos, s_warp);
-    for (int i = threadIdx.x; i < nvalid; i += blockDim.x) {
-        fv_feats[i] = (unsigned)keys[i];
-        if (i == 0 || (keys[i - 1] >> 32) != (keys[i] >> 32)) { fv_nodes[pos[i]] = (unsigned)(keys[i] >> 32); fv_offsets[pos[i]] = i; }
-    }
-    if (threadIdx.x == 0) { fv_offsets[ng] = nvalid; nfv[frame] = ng; }
+    const double norm = s_norm;
+    if (norm > 0.0)
+        for (int i = threadIdx.x; i < nb; i += BOW_BUILD_THREADS) bow_vals[i] = sv[i] / norm;
 }
 
 // ---- K16: one query vector against M stored vectors
@@ -225,75 +238,135 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_
     return lo;
 }
 
+// The query's words sit in shared memory twice: sorted (for the position of a common word) and as a 2^17-bit table indexed by
+// the low bits of the word id, which answers "not in the query" for ~98 % of a stored vector's words with one load.  A warp
+// walks its stored vectors 128 words at a time (four coalesced loads in flight) and adds the terms of the common words in
+// ascending word order, as the reference's merge does.
+constexpr int BOW_FILTER_BITS = 17;
+constexpr int BOW_FILTER_WORDS = 1 << (BOW_FILTER_BITS - 5);
+constexpr int BOW_BUCKETS = 1024;
+constexpr int BOW_QUEUE = 160;           // a queue is drained at 32 entries; 128 words can arrive before the next check
+
 template <int SCORING>
 __global__ void __launch_bounds__(BOW_THREADS)
 k_bow_score(const uint32_t* __restrict__ qwords, const double* __restrict__ qvals, int nq, const int64_t* __restrict__ db_start,
             const int32_t* __restrict__ db_count, const uint32_t* __restrict__ db_words, const double* __restrict__ db_vals, int M,
-            double* __restrict__ scores)
+            int word_shift, double* __restrict__ scores)
 {
     extern __shared__ __align__(16) unsigned char bow_smem[];
-    uint32_t* s_q = reinterpret_cast<uint32_t*>(bow_smem);       // the query's words
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[i] = qwords[i];
+    uint32_t* s_filter = reinterpret_cast<uint32_t*>(bow_smem);  // [BOW_FILTER_WORDS]
+    uint32_t* s_q = s_filter + BOW_FILTER_WORDS;                 // the query's words, ascending
+    __shared__ uint2 s_queue[BOW_THREADS / 32][BOW_QUEUE];       // per warp: (position in the stored vector, word)
+    __shared__ uint16_t s_bucket[BOW_BUCKETS + 1];               // first query word of every range of 2^word_shift word ids
+    for (int i = threadIdx.x; i < BOW_FILTER_WORDS; i += blockDim.x) s_filter[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nq; i += blockDim.x) {
+        const int prev = i ? min((int)(qwords[i - 1] >> word_shift), BOW_BUCKETS - 1) : -1;
+        int cur = BOW_BUCKETS;
+        if (i < nq) {
+            const uint32_t w = qwords[i];
+            s_q[i] = w;
+            atomicOr(&s_filter[(w >> 5) & (BOW_FILTER_WORDS - 1)], 1u << (w & 31));
+            cur = min((int)(w >> word_shift), BOW_BUCKETS - 1);
+        }
+        for (int bk = prev + 1; bk <= cur; bk++) s_bucket[bk] = (uint16_t)i;       // ascending words: every bucket is written once
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (BOW_THREADS / 32) + (threadIdx.x >> 5);
-    if (e >= M) return;
-    const uint32_t* w2 = db_words + db_start[e];
-    const double* v2 = db_vals + db_start[e];
-    const int n2 = db_count[e];
-    double score = 0;
-    if (SCORING == S_KL) {
-        // every word of the query contributes, in ascending order: with its partner in the stored vector, or alone
-        const double log_eps = log(DBL_EPSILON);
-        const uint32_t last2 = n2 > 0 ? w2[n2 - 1] : 0;
-        for (int i0 = 0; i0 < nq; i0 += 32) {
-            const int i = i0 + lane;
-            double term = 0;
-            bool add = false;
-            if (i < nq) {
-                const uint32_t w = s_q[i];
-                const double vi = qvals[i];
-                const int j = lower_bound_u32(w2, n2, w);
-                if (j < n2 && w2[j] == w) { const double wi = v2[j]; if (vi != 0 && wi != 0) { term = vi * log(vi / wi); add = true; } }
-                else if (n2 > 0 && w < last2) { term = vi * (log(vi) - log_eps); add = true; }       // inside the merge loop: unconditional
-                else if (vi != 0) { term = vi * (log(vi) - log_eps); add = true; }                   // after it: zero values skipped
-            }
-            unsigned bal = __ballot_sync(0xffffffffu, add);
-            while (bal) {
-                const int b = __ffs(bal) - 1;
-                bal &= bal - 1;
-                score += __shfl_sync(0xffffffffu, term, b);
-            }
-        }
-    } else {
-        for (int j0 = 0; j0 < n2; j0 += 32) {
-            const int j = j0 + lane;
-            double term = 0;
-            bool add = false;
-            if (j < n2) {
-                const uint32_t w = w2[j];
-                const int i = lower_bound_u32(s_q, nq, w);
-                if (i < nq && s_q[i] == w) {
-                    const double vi = qvals[i], wi = v2[j];
-                    add = true;
-                    if (SCORING == S_L1) term = fabs(vi - wi) - fabs(vi) - fabs(wi);
-                    else if (SCORING == S_L2 || SCORING == S_DOT) term = vi * wi;
-                    else if (SCORING == S_CHI) { add = vi + wi != 0.0; if (add) term = vi * wi / (vi + wi); }
-                    else term = sqrt(vi * wi);
+    const int warps = gridDim.x * (BOW_THREADS / 32);
+    for (int e = blockIdx.x * (BOW_THREADS / 32) + (threadIdx.x >> 5); e < M; e += warps) {
+        const uint32_t* w2 = db_words + db_start[e];
+        const double* v2 = db_vals + db_start[e];
+        const int n2 = db_count[e];
+        double score = 0;
+        if (SCORING == S_KL) {
+            // every word of the query contributes, in ascending order: with its partner in the stored vector, or alone
+            const double log_eps = log(DBL_EPSILON);
+            const uint32_t last2 = n2 > 0 ? w2[n2 - 1] : 0;
+            for (int i0 = 0; i0 < nq; i0 += 32) {
+                const int i = i0 + lane;
+                double term = 0;
+                bool add = false;
+                if (i < nq) {
+                    const uint32_t w = s_q[i];
+                    const double vi = qvals[i];
+                    const int j = lower_bound_u32(w2, n2, w);
+                    if (j < n2 && w2[j] == w) { const double wi = v2[j]; if (vi != 0 && wi != 0) { term = vi * log(vi / wi); add = true; } }
+                    else if (n2 > 0 && w < last2) { term = vi * (log(vi) - log_eps); add = true; }       // inside the merge loop: unconditional
+                    else if (vi != 0) { term = vi * (log(vi) - log_eps); add = true; }                   // after it: zero values skipped
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, add);
+                while (bal) {
+                    const int b = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    score += __shfl_sync(0xffffffffu, term, b);
                 }
             }
-            unsigned bal = __ballot_sync(0xffffffffu, add);
-            while (bal) {
-                const int b = __ffs(bal) - 1;
-                bal &= bal - 1;
-                score += __shfl_sync(0xffffffffu, term, b);
+        } else {
+            // words that pass the table wait, in order, in a per-warp queue; a full queue is resolved 32 at a time: exact
+            // position in the query, the term, and the terms of the common words added in lane (= word) order
+            uint2* queue = s_queue[threadIdx.x >> 5];
+            auto drain = [&](int count) {
+                for (int g = 0; g < count; g += 32) {
+                    const int t = g + lane;
+                    bool hit = t < count;
+                    double term = 0;
+                    if (hit) {
+                        const uint2 c = queue[t];
+                        const int bk = min((int)(c.y >> word_shift), BOW_BUCKETS - 1);
+                        const int lo = s_bucket[bk];
+                        const int i = lo + lower_bound_u32(s_q + lo, s_bucket[bk + 1] - lo, c.y);
+                        hit = i < nq && s_q[i] == c.y;
+                        if (hit) {
+                            const double vi = qvals[i], wi = v2[c.x];
+                            if (SCORING == S_L1) term = fabs(vi - wi) - fabs(vi) - fabs(wi);
+                            else if (SCORING == S_L2 || SCORING == S_DOT) term = vi * wi;
+                            else if (SCORING == S_CHI) { hit = vi + wi != 0.0; if (hit) term = vi * wi / (vi + wi); }
+                            else term = sqrt(vi * wi);
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                    if (bal) {
+#pragma unroll
+                        for (int b = 0; b < 32; b++) {
+                            const double tb = __shfl_sync(0xffffffffu, term, b);
+                            if ((bal >> b) & 1) score += tb;
+                        }
+                    }
+                }
+            };
+            int qn = 0;
+            uint32_t w[4], wn[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int j = u * 32 + lane; wn[u] = j < n2 ? __ldg(w2 + j) : 0xffffffffu; }
+            for (int j0 = 0; j0 < n2; j0 += 128) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {           // the next 128 words are on their way while these are looked at
+                    w[u] = wn[u];
+                    const int j = j0 + 128 + u * 32 + lane;
+                    wn[u] = j < n2 ? __ldg(w2 + j) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = j0 + u * 32 + lane;
+                    const bool maybe = j < n2 && ((s_filter[(w[u] >> 5) & (BOW_FILTER_WORDS - 1)] >> (w[u] & 31)) & 1);
+                    const unsigned bal = __ballot_sync(0xffffffffu, maybe);
+                    if (maybe) {
+                        queue[qn + __popc(bal & ((1u << lane) - 1))] = make_uint2((unsigned)j, w[u]);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(v2 + j));      // its value is wanted when the queue is drained
+                    }
+                    qn += __popc(bal);
+                }
+                if (qn >= 32) { __syncwarp(); drain(qn); qn = 0; __syncwarp(); }
             }
+            if (qn) { __syncwarp(); drain(qn); }
+            __syncwarp();
         }
+        if (SCORING == S_L1) score = -score / 2.0;
+        else if (SCORING == S_L2) score = score >= 1 ? 1.0 : 1.0 - sqrt(1.0 - score);
+        else if (SCORING == S_CHI) score = 2. * score;
+        if (lane == 0) scores[e] = score;
     }
-    if (SCORING == S_L1) score = -score / 2.0;
-    else if (SCORING == S_L2) score = score >= 1 ? 1.0 : 1.0 - sqrt(1.0 - score);
-    else if (SCORING == S_CHI) score = 2. * score;
-    if (lane == 0) scores[e] = score;
 }
 
 template <typename T>
@@ -317,6 +390,7 @@ struct bowx_context {
     int device;
     cudaStream_t own_stream, stream;
     size_t smem_optin;
+    int sm_count;
     // vocabulary: host copy in the reference's numbering, device copy in child-contiguous record order
     int k, L, scoring, weighting, nnodes, nwords, max_children;
     std::vector<int32_t> parent, word_node, rec_of_node;
@@ -360,8 +434,16 @@ extern "C" int bowx_create(bowx_handle* out, int device)
     h->stream = h->own_stream;
     int optin = 0;
     ORBX_CUDA_OR(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), bowx_destroy(h));
     h->smem_optin = (size_t)optin - 1024;       // dynamic part: k_bow_build also has a few static words
-    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_score<S_L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_score<S_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_score<S_CHI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_score<S_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_score<S_BHAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_score<S_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_build<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_build<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024), bowx_destroy(h));
     *out = h;
     return ORBX_OK;
 }
@@ -544,9 +626,14 @@ extern "C" int bowx_transform_batch_dev(bowx_handle h, const uint8_t* d_desc, co
     ORBX_REQUIRE(d_desc && d_counts && d_bow_words && d_bow_vals && d_nbow, "bowx_transform_batch_dev: NULL pointer");
     const bool fv = d_fv_nodes || d_fv_offsets || d_fv_feats || d_nfv;
     ORBX_REQUIRE(!fv || (d_fv_nodes && d_fv_offsets && d_fv_feats && d_nfv), "bowx_transform_batch_dev: the feature vector needs all four of its arrays");
-    const int P = next_pow2(std::max(cap, 32));
-    const size_t smem = (size_t)P * (sizeof(unsigned long long) + sizeof(int));
-    ORBX_REQUIRE(smem <= h->smem_optin, "bowx_transform_batch_dev: cap %d needs %zu bytes of shared memory (limit %zu): at most 16384 features per frame", cap, smem, h->smem_optin);
+    // keys are (id << idx_bits) | feature index: 32 bits when the ids leave room for the index, else 64
+    const int P = next_pow2(std::max(cap, 64));
+    int idx_bits = 0;
+    while ((1 << idx_bits) < cap) idx_bits++;
+    const bool bow32 = idx_bits < 32 && (unsigned long long)std::max(h->nwords, 1) < (1ull << (32 - idx_bits)) - 1;
+    const bool fv32 = idx_bits < 32 && (unsigned long long)h->nnodes < (1ull << (32 - idx_bits)) - 1;
+    const size_t smem64 = (size_t)P * (sizeof(unsigned long long) + sizeof(int));
+    ORBX_REQUIRE(smem64 <= h->smem_optin, "bowx_transform_batch_dev: cap %d needs %zu bytes of shared memory (limit %zu): at most 16384 features per frame", cap, smem64, h->smem_optin);
     if (nframes == 0) return ORBX_OK;
     ORBX_CUDA(cudaSetDevice(h->device));
     const size_t total = (size_t)nframes * cap;
@@ -566,8 +653,22 @@ extern "C" int bowx_transform_batch_dev(bowx_handle h, const uint8_t* d_desc, co
     if (rc) return rc;
     const int accumulate = h->weighting == BOWX_TF || h->weighting == BOWX_TF_IDF;
     const int must = h->scoring != BOWX_DOT_PRODUCT, l2 = h->scoring == BOWX_L2_NORM;
-    k_bow_build<<<nframes, BOW_THREADS, smem, h->stream>>>(h->d_word, h->d_weight, h->d_nid, d_counts, cap, P, accumulate, must, l2, d_bow_words,
-                                                          d_bow_vals, d_nbow, fv ? d_fv_nodes : nullptr, d_fv_offsets, d_fv_feats, d_nfv);
+    // one CTA per frame and vector; both vectors in one launch when their keys have the same width
+    const size_t smem32 = (size_t)P * 8;        // 4-byte keys + offsets; also holds the P doubles of the normalisation
+#define BOW_BUILD(KEY, SMEM, SHIFT, PARTS, FIRST)                                                                                   \
+    k_bow_build<KEY><<<dim3((unsigned)nframes, PARTS), BOW_BUILD_THREADS, SMEM, h->stream>>>(                                      \
+        h->d_word, h->d_weight, h->d_nid, d_counts, cap, P, SHIFT, accumulate, must, l2, d_bow_words, d_bow_vals, d_nbow, d_fv_nodes, \
+        d_fv_offsets, d_fv_feats, d_nfv, FIRST)
+    if (!fv) {
+        if (bow32) BOW_BUILD(uint32_t, smem32, idx_bits, 1, 0); else BOW_BUILD(unsigned long long, smem64, 32, 1, 0);
+    } else if (bow32 == fv32) {
+        if (bow32) BOW_BUILD(uint32_t, smem32, idx_bits, 2, 0); else BOW_BUILD(unsigned long long, smem64, 32, 2, 0);
+    } else {
+        if (bow32) BOW_BUILD(uint32_t, smem32, idx_bits, 1, 0); else BOW_BUILD(unsigned long long, smem64, 32, 1, 0);
+        ORBX_CUDA(cudaGetLastError());
+        if (fv32) BOW_BUILD(uint32_t, smem32, idx_bits, 1, 1); else BOW_BUILD(unsigned long long, smem64, 32, 1, 1);
+    }
+#undef BOW_BUILD
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
 }
@@ -658,11 +759,15 @@ extern "C" int bowx_score_batch_dev(bowx_handle h, const uint32_t* d_qwords, con
     ORBX_REQUIRE(nq >= 0 && nentries >= 0, "bowx_score_batch_dev: nq %d / nentries %d", nq, nentries);
     if (nentries == 0) return ORBX_OK;
     ORBX_REQUIRE((nq == 0 || (d_qwords && d_qvals)) && d_db_start && d_db_count && d_db_words && d_db_vals && d_scores, "bowx_score_batch_dev: NULL pointer");
-    const size_t smem = (size_t)std::max(nq, 1) * sizeof(uint32_t);
-    ORBX_REQUIRE(smem <= 48 * 1024, "bowx_score_batch_dev: a query of %d words (at most 12288)", nq);
+    ORBX_REQUIRE(nq <= 8192, "bowx_score_batch_dev: a query of %d words (at most 8192)", nq);
+    const size_t smem = ((size_t)BOW_FILTER_WORDS + (size_t)std::max(nq, 1)) * sizeof(uint32_t);       // <= 48 KB
     ORBX_CUDA(cudaSetDevice(h->device));
-    const unsigned blocks = (unsigned)((nentries + BOW_THREADS / 32 - 1) / (BOW_THREADS / 32));
-#define BOW_SCORE(S) k_bow_score<S><<<blocks, BOW_THREADS, smem, h->stream>>>(d_qwords, d_qvals, nq, d_db_start, d_db_count, d_db_words, d_db_vals, nentries, d_scores)
+    // a CTA builds the query's tables once and its 8 warps walk stored vectors e, e + warps, ...: at most 8 CTAs per SM
+    const unsigned blocks = (unsigned)std::min((nentries + BOW_THREADS / 32 - 1) / (BOW_THREADS / 32), h->sm_count * 8);
+    int word_bits = 1;
+    while (word_bits < 31 && (1u << word_bits) < (unsigned)std::max(h->nwords, 2)) word_bits++;
+    const int word_shift = std::max(0, word_bits - 10);          // BOW_BUCKETS ranges cover the word ids
+#define BOW_SCORE(S) k_bow_score<S><<<blocks, BOW_THREADS, smem, h->stream>>>(d_qwords, d_qvals, nq, d_db_start, d_db_count, d_db_words, d_db_vals, nentries, word_shift, d_scores)
     switch (h->scoring) {
     case BOWX_L1_NORM: BOW_SCORE(S_L1); break;
     case BOWX_L2_NORM: BOW_SCORE(S_L2); break;

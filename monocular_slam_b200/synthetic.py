@@ -280,3 +280,34 @@ def read_vocabulary_text(path):
             weight.append(float(t[34]))
     return {"k": k, "L": L, "scoring": scoring, "weighting": weighting, "parent": np.asarray(parent, np.int32),
             "leaf": np.asarray(leaf, np.uint8), "desc": np.stack(desc), "weight": np.asarray(weight, np.float64)}
+
+
+def vocabulary_large(seed, k=10, L=6, stop_frac=0.01):
+    """A complete k-ary tree of depth L in breadth-first node order, generated level by level with array operations (the
+    ORB-SLAM vocabulary shape k = 10, L = 6 has 1.1 M nodes): level-1 descriptors are random, a child differs from its parent
+    in a random subset of bits that halves with every level (the AND of `level` random byte arrays: 64, 32, 16 ... bits on
+    average).  Same dictionary as `vocabulary`."""
+    rng = np.random.default_rng(seed)
+    counts = [k ** lvl for lvl in range(L + 1)]
+    n = sum(counts)
+    parent = np.zeros(n, np.int32)
+    desc = np.zeros((n, 32), np.uint8)
+    first = np.cumsum([0] + counts)           # first node id of every level
+    for lvl in range(1, L + 1):
+        lo, hi = first[lvl], first[lvl + 1]
+        par = first[lvl - 1] + np.arange(counts[lvl], dtype=np.int64) // k
+        parent[lo:hi] = par
+        if lvl == 1:
+            desc[lo:hi] = rng.integers(0, 256, (counts[lvl], 32), dtype=np.uint8)
+        else:
+            mask = rng.integers(0, 256, (counts[lvl], 32), dtype=np.uint8)
+            for _ in range(lvl - 1):
+                mask &= rng.integers(0, 256, (counts[lvl], 32), dtype=np.uint8)
+            desc[lo:hi] = desc[par] ^ mask
+    leaf = np.zeros(n, np.uint8)
+    leaf[first[L]:] = 1
+    weight = np.zeros(n, np.float64)
+    w = rng.uniform(0.5, 9.0, counts[L])
+    w[rng.random(counts[L]) < stop_frac] = 0.0
+    weight[first[L]:] = w
+    return {"k": int(k), "L": int(L), "parent": parent, "leaf": leaf, "desc": desc, "weight": weight}

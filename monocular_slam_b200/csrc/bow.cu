@@ -245,36 +245,61 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_
 constexpr int BOW_FILTER_BITS = 17;
 constexpr int BOW_FILTER_WORDS = 1 << (BOW_FILTER_BITS - 5);
 constexpr int BOW_BUCKETS = 1024;
-constexpr int BOW_QUEUE = 160;           // a queue is drained at 32 entries; 128 words can arrive before the next check
+constexpr int BOW_UNROLL = 4;            // 32-word loads a warp keeps in flight
+constexpr int BOW_QUEUE = 32 + 32 * BOW_UNROLL;      // a queue is drained at 32 entries; 32 * BOW_UNROLL words can arrive before the next check
 
-template <int SCORING>
-__global__ void __launch_bounds__(BOW_THREADS)
-k_bow_score(const uint32_t* __restrict__ qwords, const double* __restrict__ qvals, int nq, const int64_t* __restrict__ db_start,
-            const int32_t* __restrict__ db_count, const uint32_t* __restrict__ db_words, const double* __restrict__ db_vals, int M,
-            int word_shift, double* __restrict__ scores)
+// the query's bit table and bucket starts, built once per call in global memory (every CTA of k_bow_score copies them)
+__global__ void __launch_bounds__(1024)
+k_bow_query_tables(const uint32_t* __restrict__ qwords, int nq, int word_shift, uint32_t* __restrict__ tables, int* __restrict__ next_entry)
 {
-    extern __shared__ __align__(16) unsigned char bow_smem[];
-    uint32_t* s_filter = reinterpret_cast<uint32_t*>(bow_smem);  // [BOW_FILTER_WORDS]
-    uint32_t* s_q = s_filter + BOW_FILTER_WORDS;                 // the query's words, ascending
-    __shared__ uint2 s_queue[BOW_THREADS / 32][BOW_QUEUE];       // per warp: (position in the stored vector, word)
-    __shared__ uint16_t s_bucket[BOW_BUCKETS + 1];               // first query word of every range of 2^word_shift word ids
-    for (int i = threadIdx.x; i < BOW_FILTER_WORDS; i += blockDim.x) s_filter[i] = 0;
+    if (threadIdx.x == 0) *next_entry = 0;        // k_bow_score's work counter
+    uint32_t* filter = tables;                                                   // [BOW_FILTER_WORDS]
+    uint16_t* bucket = reinterpret_cast<uint16_t*>(tables + BOW_FILTER_WORDS);   // [BOW_BUCKETS + 1] (+ padding)
+    for (int i = threadIdx.x; i < BOW_FILTER_WORDS; i += blockDim.x) filter[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i <= nq; i += blockDim.x) {
         const int prev = i ? min((int)(qwords[i - 1] >> word_shift), BOW_BUCKETS - 1) : -1;
         int cur = BOW_BUCKETS;
         if (i < nq) {
             const uint32_t w = qwords[i];
-            s_q[i] = w;
-            atomicOr(&s_filter[(w >> 5) & (BOW_FILTER_WORDS - 1)], 1u << (w & 31));
+            atomicOr(&filter[(w >> 5) & (BOW_FILTER_WORDS - 1)], 1u << (w & 31));
             cur = min((int)(w >> word_shift), BOW_BUCKETS - 1);
         }
-        for (int bk = prev + 1; bk <= cur; bk++) s_bucket[bk] = (uint16_t)i;       // ascending words: every bucket is written once
+        for (int bk = prev + 1; bk <= cur; bk++) bucket[bk] = (uint16_t)i;       // ascending words: every bucket is written once
+    }
+}
+constexpr int BOW_TABLE_WORDS = BOW_FILTER_WORDS + (BOW_BUCKETS + 8) / 2;       // uint32 words of the two tables, a multiple of 4
+
+template <int SCORING>
+__global__ void __launch_bounds__(BOW_THREADS)
+k_bow_score(const uint32_t* __restrict__ qwords, const double* __restrict__ qvals, int nq, const uint32_t* __restrict__ tables,
+            const int64_t* __restrict__ db_start, const int32_t* __restrict__ db_count, const uint32_t* __restrict__ db_words,
+            const double* __restrict__ db_vals, int M, int word_shift, int vals_in_smem, int* __restrict__ next_entry,
+            double* __restrict__ scores)
+{
+    extern __shared__ __align__(16) unsigned char bow_smem[];
+    uint32_t* s_filter = reinterpret_cast<uint32_t*>(bow_smem);                     // [BOW_FILTER_WORDS]
+    const uint16_t* s_bucket = reinterpret_cast<const uint16_t*>(s_filter + BOW_FILTER_WORDS);   // first query word of every range of 2^word_shift ids
+    double* s_qv = vals_in_smem ? reinterpret_cast<double*>(s_filter + BOW_TABLE_WORDS) : nullptr;       // the query's values, if they fit
+    uint32_t* s_q = s_filter + BOW_TABLE_WORDS + (vals_in_smem ? 2 * nq : 0);                            // the query's words, ascending
+    __shared__ uint32_t s_queue[BOW_THREADS / 32][BOW_QUEUE];    // per warp: positions in the stored vector of the words that passed the table
+    __shared__ double s_terms[BOW_THREADS / 32][32];             // per warp: the terms of 32 queue entries
+    static_assert(BOW_TABLE_WORDS % 4 == 0 && BOW_FILTER_WORDS % 4 == 0, "the tables are copied as 16-byte words");
+    for (int i = threadIdx.x; i < BOW_TABLE_WORDS / 4; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_filter)[i] = __ldg(reinterpret_cast<const uint4*>(tables) + i);
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+        s_q[i] = qwords[i];
+        if (s_qv) s_qv[i] = qvals[i];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int warps = gridDim.x * (BOW_THREADS / 32);
-    for (int e = blockIdx.x * (BOW_THREADS / 32) + (threadIdx.x >> 5); e < M; e += warps) {
+    // stored vectors are handed out one at a time: a vector that shares many words with the query takes much longer than one
+    // that shares few, and a fixed assignment would let two of those land on one warp
+    for (;;) {
+        int e = 0;
+        if (lane == 0) e = atomicAdd(next_entry, 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= M) break;
         const uint32_t* w2 = db_words + db_start[e];
         const double* v2 = db_vals + db_start[e];
         const int n2 = db_count[e];
@@ -305,54 +330,65 @@ k_bow_score(const uint32_t* __restrict__ qwords, const double* __restrict__ qval
         } else {
             // words that pass the table wait, in order, in a per-warp queue; a full queue is resolved 32 at a time: exact
             // position in the query, the term, and the terms of the common words added in lane (= word) order
-            uint2* queue = s_queue[threadIdx.x >> 5];
+            uint32_t* queue = s_queue[threadIdx.x >> 5];
+            double* terms = s_terms[threadIdx.x >> 5];
+            // look(t): is queue entry t a word of the query, and if so the two values (loads issued, not yet used)
+            auto look = [&](int t, int count, double& vi, double& wi) -> bool {
+                if (t >= count) return false;
+                const uint32_t j = queue[t], w = __ldg(w2 + j);       // the word again: it is in L1 / L2
+                const int bk = min((int)(w >> word_shift), BOW_BUCKETS - 1);
+                const int lo = s_bucket[bk];
+                const int i = lo + lower_bound_u32(s_q + lo, s_bucket[bk + 1] - lo, w);
+                if (i >= nq || s_q[i] != w) return false;
+                vi = s_qv ? s_qv[i] : qvals[i];
+                wi = v2[j];
+                return true;
+            };
             auto drain = [&](int count) {
+                double vi = 0, wi = 0;
+                bool hit = look(lane, count, vi, wi);
                 for (int g = 0; g < count; g += 32) {
-                    const int t = g + lane;
-                    bool hit = t < count;
+                    double vn = 0, wn_ = 0;
+                    const bool hit_next = look(g + 32 + lane, count, vn, wn_);      // the next 32 are fetched while these are added
                     double term = 0;
                     if (hit) {
-                        const uint2 c = queue[t];
-                        const int bk = min((int)(c.y >> word_shift), BOW_BUCKETS - 1);
-                        const int lo = s_bucket[bk];
-                        const int i = lo + lower_bound_u32(s_q + lo, s_bucket[bk + 1] - lo, c.y);
-                        hit = i < nq && s_q[i] == c.y;
-                        if (hit) {
-                            const double vi = qvals[i], wi = v2[c.x];
-                            if (SCORING == S_L1) term = fabs(vi - wi) - fabs(vi) - fabs(wi);
-                            else if (SCORING == S_L2 || SCORING == S_DOT) term = vi * wi;
-                            else if (SCORING == S_CHI) { hit = vi + wi != 0.0; if (hit) term = vi * wi / (vi + wi); }
-                            else term = sqrt(vi * wi);
-                        }
+                        if (SCORING == S_L1) term = fabs(vi - wi) - fabs(vi) - fabs(wi);
+                        else if (SCORING == S_L2 || SCORING == S_DOT) term = vi * wi;
+                        else if (SCORING == S_CHI) { hit = vi + wi != 0.0; if (hit) term = vi * wi / (vi + wi); }
+                        else term = sqrt(vi * wi);
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, hit);
                     if (bal) {
+                        // through shared memory, not shuffles: the 32 loads are independent of the sum, so the chain of
+                        // additions runs at the latency of an addition
+                        terms[lane] = term;
+                        __syncwarp();
 #pragma unroll
-                        for (int b = 0; b < 32; b++) {
-                            const double tb = __shfl_sync(0xffffffffu, term, b);
-                            if ((bal >> b) & 1) score += tb;
-                        }
+                        for (int b = 0; b < 32; b++)
+                            if ((bal >> b) & 1) score += terms[b];
+                        __syncwarp();
                     }
+                    hit = hit_next; vi = vn; wi = wn_;
                 }
             };
             int qn = 0;
-            uint32_t w[4], wn[4];
+            uint32_t w[BOW_UNROLL], wn[BOW_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const int j = u * 32 + lane; wn[u] = j < n2 ? __ldg(w2 + j) : 0xffffffffu; }
-            for (int j0 = 0; j0 < n2; j0 += 128) {
+            for (int u = 0; u < BOW_UNROLL; u++) { const int j = u * 32 + lane; wn[u] = j < n2 ? __ldg(w2 + j) : 0xffffffffu; }
+            for (int j0 = 0; j0 < n2; j0 += 32 * BOW_UNROLL) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) {           // the next 128 words are on their way while these are looked at
+                for (int u = 0; u < BOW_UNROLL; u++) {   // the next 32 * BOW_UNROLL words are on their way while these are looked at
                     w[u] = wn[u];
-                    const int j = j0 + 128 + u * 32 + lane;
+                    const int j = j0 + 32 * BOW_UNROLL + u * 32 + lane;
                     wn[u] = j < n2 ? __ldg(w2 + j) : 0xffffffffu;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < BOW_UNROLL; u++) {
                     const int j = j0 + u * 32 + lane;
                     const bool maybe = j < n2 && ((s_filter[(w[u] >> 5) & (BOW_FILTER_WORDS - 1)] >> (w[u] & 31)) & 1);
                     const unsigned bal = __ballot_sync(0xffffffffu, maybe);
                     if (maybe) {
-                        queue[qn + __popc(bal & ((1u << lane) - 1))] = make_uint2((unsigned)j, w[u]);
+                        queue[qn + __popc(bal & ((1u << lane) - 1))] = (uint32_t)j;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(v2 + j));      // its value is wanted when the queue is drained
                     }
                     qn += __popc(bal);
@@ -402,6 +438,8 @@ struct bowx_context {
     double* d_weight; size_t weight_bytes;
     uint32_t* d_nid; size_t nid_bytes;
     uint8_t* d_buf; size_t buf_bytes;
+    int* d_next;                         // k_bow_score's work counter
+    uint32_t* d_tables;                  // the query's bit table and bucket starts (k_bow_query_tables)
 };
 
 extern "C" int bowx_destroy(bowx_handle h)
@@ -409,7 +447,7 @@ extern "C" int bowx_destroy(bowx_handle h)
     if (!h) return ORBX_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_nodes); cudaFree(h->d_weights); cudaFree(h->d_word); cudaFree(h->d_weight); cudaFree(h->d_nid); cudaFree(h->d_buf);
+    cudaFree(h->d_nodes); cudaFree(h->d_weights); cudaFree(h->d_word); cudaFree(h->d_weight); cudaFree(h->d_nid); cudaFree(h->d_buf); cudaFree(h->d_next); cudaFree(h->d_tables);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ORBX_OK;
@@ -428,6 +466,7 @@ extern "C" int bowx_create(bowx_handle* out, int device)
     h->device = device;
     h->own_stream = h->stream = nullptr;
     h->k = h->L = h->scoring = h->weighting = h->nnodes = h->nwords = h->max_children = 0;
+    h->d_next = nullptr; h->d_tables = nullptr;
     h->d_nodes = nullptr; h->d_weights = nullptr; h->d_word = nullptr; h->d_weight = nullptr; h->d_nid = nullptr; h->d_buf = nullptr;
     h->nodes_bytes = h->weights_bytes = h->word_bytes = h->weight_bytes = h->nid_bytes = h->buf_bytes = 0;
     ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), bowx_destroy(h));
@@ -435,6 +474,8 @@ extern "C" int bowx_create(bowx_handle* out, int device)
     int optin = 0;
     ORBX_CUDA_OR(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), bowx_destroy(h));
     ORBX_CUDA_OR(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaMalloc((void**)&h->d_next, sizeof(int)), bowx_destroy(h));
+    ORBX_CUDA_OR(cudaMalloc((void**)&h->d_tables, sizeof(uint32_t) * BOW_TABLE_WORDS), bowx_destroy(h));
     h->smem_optin = (size_t)optin - 1024;       // dynamic part: k_bow_build also has a few static words
     ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_score<S_L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), bowx_destroy(h));
     ORBX_CUDA_OR(cudaFuncSetAttribute(k_bow_score<S_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), bowx_destroy(h));
@@ -760,14 +801,17 @@ extern "C" int bowx_score_batch_dev(bowx_handle h, const uint32_t* d_qwords, con
     if (nentries == 0) return ORBX_OK;
     ORBX_REQUIRE((nq == 0 || (d_qwords && d_qvals)) && d_db_start && d_db_count && d_db_words && d_db_vals && d_scores, "bowx_score_batch_dev: NULL pointer");
     ORBX_REQUIRE(nq <= 8192, "bowx_score_batch_dev: a query of %d words (at most 8192)", nq);
-    const size_t smem = ((size_t)BOW_FILTER_WORDS + (size_t)std::max(nq, 1)) * sizeof(uint32_t);       // <= 48 KB
+    const int vals_in_smem = nq <= 3584;         // tables 18 KB + words + values within the 64 KB the kernels opt in to
+    const size_t smem = ((size_t)BOW_TABLE_WORDS + (size_t)std::max(nq, 1) * (vals_in_smem ? 3 : 1)) * sizeof(uint32_t);
     ORBX_CUDA(cudaSetDevice(h->device));
-    // a CTA builds the query's tables once and its 8 warps walk stored vectors e, e + warps, ...: at most 8 CTAs per SM
-    const unsigned blocks = (unsigned)std::min((nentries + BOW_THREADS / 32 - 1) / (BOW_THREADS / 32), h->sm_count * 8);
+    // a CTA copies the query's tables once and its 8 warps take stored vectors from a counter until none is left
+    const unsigned blocks = (unsigned)std::min((nentries + BOW_THREADS / 32 - 1) / (BOW_THREADS / 32), h->sm_count * 4);
     int word_bits = 1;
     while (word_bits < 31 && (1u << word_bits) < (unsigned)std::max(h->nwords, 2)) word_bits++;
     const int word_shift = std::max(0, word_bits - 10);          // BOW_BUCKETS ranges cover the word ids
-#define BOW_SCORE(S) k_bow_score<S><<<blocks, BOW_THREADS, smem, h->stream>>>(d_qwords, d_qvals, nq, d_db_start, d_db_count, d_db_words, d_db_vals, nentries, word_shift, d_scores)
+    k_bow_query_tables<<<1, 1024, 0, h->stream>>>(d_qwords, nq, word_shift, h->d_tables, h->d_next);
+    ORBX_CUDA(cudaGetLastError());
+#define BOW_SCORE(S) k_bow_score<S><<<blocks, BOW_THREADS, smem, h->stream>>>(d_qwords, d_qvals, nq, h->d_tables, d_db_start, d_db_count, d_db_words, d_db_vals, nentries, word_shift, vals_in_smem, h->d_next, d_scores)
     switch (h->scoring) {
     case BOWX_L1_NORM: BOW_SCORE(S_L1); break;
     case BOWX_L2_NORM: BOW_SCORE(S_L2); break;

@@ -60,8 +60,19 @@ def main():
     sc = torch.zeros(ndb, dtype=torch.float64, device=dev)
     t_sc = timed(lambda: voc.score_batch_dev(bw[0].data_ptr(), bv[0].data_ptr(), int(nb[0]), pstart.data_ptr(), dcount.data_ptr(), pw.data_ptr(),
                                              pv.data_ptr(), ndb, sc.data_ptr()))
-    bytes_ = int(dcount.sum().item()) * 12
-    print("score: 1 x %d stored vectors of %.0f words: %.3f ms = %.0f GB/s of stored words" % (ndb, nb.mean(), t_sc, bytes_ / t_sc / 1e6))
+    bytes_ = int(dcount.sum().item()) * 4
+    print("score: 1 x %d stored vectors of %.0f words, every %dth one the query itself: %.3f ms = %.0f GB/s of stored word ids" % (ndb, nb.mean(), B, t_sc, bytes_ / t_sc / 1e6))
+    # the same database without the copies of the query: entries that held frame 0 now hold frame 1
+    pw2, pv2, dc2 = pw.clone(), pv.clone(), dcount.clone()
+    pw2[0::B] = pw[1::B][:len(pw2[0::B])]; pv2[0::B] = pv[1::B][:len(pv2[0::B])]; dc2[0::B] = dcount[1::B][:len(dc2[0::B])]
+    t_sc2 = timed(lambda: voc.score_batch_dev(bw[0].data_ptr(), bv[0].data_ptr(), int(nb[0]), pstart.data_ptr(), dc2.data_ptr(), pw2.data_ptr(),
+                                              pv2.data_ptr(), ndb, sc.data_ptr()))
+    print("score: the same without the copies of the query: %.3f ms = %.0f GB/s of stored word ids" % (t_sc2, int(dc2.sum().item()) * 4 / t_sc2 / 1e6))
+    t_one = timed(lambda: voc.score_batch_dev(bw[0].data_ptr(), bv[0].data_ptr(), int(nb[0]), pstart.data_ptr(), dcount.data_ptr(), pw.data_ptr(),
+                                              pv.data_ptr(), 1, sc.data_ptr()))
+    t_none = timed(lambda: voc.score_batch_dev(bw[0].data_ptr(), bv[0].data_ptr(), int(nb[0]), pstart[1:].data_ptr(), dcount[1:].data_ptr(), pw.data_ptr(),
+                                               pv.data_ptr(), 1, sc.data_ptr()))
+    print("score: the query against itself alone (%d common words, added in order): %.3f ms; against one other vector: %.3f ms" % (nb[0], t_one, t_none))
 
 
 if __name__ == "__main__":

@@ -18,6 +18,9 @@
 #include <cstdint>
 #include <algorithm>
 #include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -372,6 +375,147 @@ static inline int TriangulateMultiplePointsFromTwoView(const std::vector<Point2d
                                                 mat_f64(K2, 3, 3, "K2"), result, countFront);
 }
 #endif
+
+// ---- the vendored DBoW2 (ThirdParty/DBoW2/DBoW2), the part a loop closer calls: BowVector / FeatureVector keep the
+// reference's types (std::map), OrbVocabulary stands where TemplatedVocabulary<FORB::TDescriptor, FORB> stood; transform()
+// and score() run on the GPU (bowx_*).
+namespace DBoW2 {
+typedef unsigned int WordId;
+typedef double WordValue;
+typedef unsigned int NodeId;
+enum WeightingType { TF_IDF, TF, IDF, BINARY };                                               // BowVector.h:36-42
+enum ScoringType { L1_NORM, L2_NORM, CHI_SQUARE, KL, BHATTACHARYYA, DOT_PRODUCT };            // BowVector.h:45-53
+typedef std::map<WordId, WordValue> BowVector;                                                // BowVector.h:56-57
+typedef std::map<NodeId, std::vector<unsigned int> > FeatureVector;                           // FeatureVector.h:21-22
+
+class OrbVocabulary {
+public:
+    explicit OrbVocabulary(int device = 0) : h_(nullptr) { check(bowx_create(&h_, device), "OrbVocabulary"); }
+    ~OrbVocabulary() { if (h_) bowx_destroy(h_); }
+    OrbVocabulary(const OrbVocabulary&) = delete;
+    OrbVocabulary& operator=(const OrbVocabulary&) = delete;
+
+    // TemplatedVocabulary.h:1333-1416.  Empty lines are skipped: the reference's own loader turns the newline that ends a
+    // file written by saveToTextFile into one more child of the root with an uninitialised descriptor.
+    bool loadFromTextFile(const std::string& filename)
+    {
+        std::ifstream f(filename.c_str());
+        if (!f) return false;
+        std::string line;
+        if (!std::getline(f, line)) return false;
+        int k = 0, L = 0, n1 = 0, n2 = 0;
+        { std::stringstream ss(line); ss >> k >> L >> n1 >> n2; }
+        if (k < 0 || k > 20 || L < 1 || L > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) return false;
+        std::vector<int32_t> parent(1, 0);
+        std::vector<uint8_t> leaf(1, 0), desc(32, 0);
+        std::vector<double> weight(1, 0.);
+        while (std::getline(f, line)) {
+            std::stringstream ss(line);
+            int pid, is_leaf;
+            if (!(ss >> pid >> is_leaf)) continue;
+            parent.push_back(pid);
+            leaf.push_back(is_leaf > 0);
+            for (int i = 0; i < 32; i++) { int b = 0; ss >> b; desc.push_back((uint8_t)b); }
+            double w = 0;
+            ss >> w;
+            weight.push_back(w);
+        }
+        check(bowx_set_vocabulary(h_, k, L, n1, n2, (int)parent.size(), parent.data(), leaf.data(), desc.data(), weight.data()), "loadFromTextFile");
+        return true;
+    }
+    unsigned int size() const { return (unsigned)info(5); }
+    bool empty() const { return size() == 0; }
+    int getBranchingFactor() const { return info(0); }
+    int getDepthLevels() const { return info(1); }
+    ScoringType getScoringType() const { return (ScoringType)info(2); }
+    WeightingType getWeightingType() const { return (WeightingType)info(3); }
+
+    // transform(features, v, fv, levelsup) with the features as the rows of one n x 32 descriptor matrix (what
+    // OrbDescriptorExtractor::compute returns) ...
+    void transform(const Mat& descriptors, BowVector& v, FeatureVector& fv, int levelsup) const { run(descriptors, v, &fv, levelsup); }
+    void transform(const Mat& descriptors, BowVector& v) const { run(descriptors, v, nullptr, 0); }
+    // ... or, as in the reference, as a vector of 1 x 32 rows
+    void transform(const std::vector<Mat>& features, BowVector& v, FeatureVector& fv, int levelsup) const { run(gather(features), v, &fv, levelsup); }
+    void transform(const std::vector<Mat>& features, BowVector& v) const { run(gather(features), v, nullptr, 0); }
+    WordId transform(const Mat& feature) const
+    {
+        if (empty()) return 0;
+        uint32_t word = 0, node = 0;
+        double weight = 0;
+        check(bowx_transform_features(h_, mat_ptr(feature), 1, 0, &word, &weight, &node), "transform");
+        return word;
+    }
+    double score(const BowVector& a, const BowVector& b) const
+    {
+        std::vector<uint32_t> w1, w2;
+        std::vector<double> v1, v2;
+        flatten(a, w1, v1); flatten(b, w2, v2);
+        double s = 0;
+        check(bowx_score(h_, w1.data(), v1.data(), (int)w1.size(), w2.data(), v2.data(), (int)w2.size(), &s), "score");
+        return s;
+    }
+    // score(query, entry) for every entry of a database of vectors, one launch
+    std::vector<double> score(const BowVector& query, const std::vector<BowVector>& database) const
+    {
+        std::vector<uint32_t> qw, words;
+        std::vector<double> qv, vals;
+        flatten(query, qw, qv);
+        std::vector<int64_t> start(database.size());
+        std::vector<int32_t> count(database.size());
+        for (size_t e = 0; e < database.size(); e++) {
+            start[e] = (int64_t)words.size();
+            count[e] = (int32_t)database[e].size();
+            for (BowVector::const_iterator it = database[e].begin(); it != database[e].end(); ++it) { words.push_back(it->first); vals.push_back(it->second); }
+        }
+        std::vector<double> scores(database.size());
+        check(bowx_score_batch(h_, qw.data(), qv.data(), (int)qw.size(), start.data(), count.data(), words.data(), vals.data(), (int64_t)words.size(),
+                               (int)database.size(), scores.data()), "score");
+        return scores;
+    }
+    NodeId getParentNode(WordId wid, int levelsup) const { uint32_t n = 0; check(bowx_parent_node(h_, wid, levelsup, &n), "getParentNode"); return n; }
+    WordValue getWordWeight(WordId wid) const { double w = 0; check(bowx_word_weight(h_, wid, &w), "getWordWeight"); return w; }
+    int stopWords(double minWeight) { int32_t c = 0; check(bowx_stop_words(h_, minWeight, &c), "stopWords"); return c; }
+    bowx_handle handle() { return h_; }
+
+private:
+    int info(int i) const { int32_t v[6]; check(bowx_vocabulary_info(h_, v), "OrbVocabulary"); return v[i]; }
+    static void flatten(const BowVector& m, std::vector<uint32_t>& w, std::vector<double>& v)
+    {
+        w.reserve(m.size()); v.reserve(m.size());
+        for (BowVector::const_iterator it = m.begin(); it != m.end(); ++it) { w.push_back(it->first); v.push_back(it->second); }
+    }
+    static Mat gather(const std::vector<Mat>& features)
+    {
+        Mat all;
+        mat_create_u8(all, (int)features.size(), 32);
+        for (size_t i = 0; i < features.size(); i++) {
+            if (features[i].rows != 1 || features[i].cols != 32) throw Error(ORBX_E_INVALID, "transform: a feature is not a 1 x 32 row");
+            std::memcpy(all.ptr((int)i), mat_ptr(features[i]), 32);
+        }
+        return all;
+    }
+    void run(const Mat& d, BowVector& v, FeatureVector* fv, int levelsup) const
+    {
+        v.clear();
+        if (fv) fv->clear();
+        const int n = d.rows;
+        if (n == 0 || empty()) return;
+        if (d.cols != 32 || mat_channels(d) != 1 || mat_step(d) != 32) throw Error(ORBX_E_INVALID, "transform: descriptors must be a continuous n x 32 8-bit matrix");
+        const int32_t count = n;
+        std::vector<uint32_t> words((size_t)n), nodes, feats;
+        std::vector<double> vals((size_t)n);
+        std::vector<int32_t> offs;
+        int32_t nbow = 0, nfv = 0;
+        if (fv) { nodes.resize((size_t)n); feats.resize((size_t)n); offs.resize((size_t)n + 1); }
+        check(bowx_transform_batch(h_, mat_ptr(d), &count, 1, n, levelsup, words.data(), vals.data(), &nbow, fv ? nodes.data() : nullptr,
+                                   fv ? offs.data() : nullptr, fv ? feats.data() : nullptr, fv ? &nfv : nullptr), "transform");
+        for (int i = 0; i < nbow; i++) v.insert(v.end(), BowVector::value_type(words[(size_t)i], vals[(size_t)i]));
+        for (int g = 0; g < nfv; g++)
+            fv->insert(fv->end(), FeatureVector::value_type(nodes[(size_t)g], std::vector<unsigned int>(feats.begin() + offs[(size_t)g], feats.begin() + offs[(size_t)g + 1])));
+    }
+    bowx_handle h_;
+};
+}  // namespace DBoW2
 
 #ifndef ORBX_SHIM_USE_OPENCV
 // ---- the slice of the reference's data model and node API that the front-end touches

@@ -159,3 +159,43 @@ def test_sequence_front_end_with_filter(tmp_path):
         prev = kps
     assert off == len(buf)
     fm.close()
+
+
+def test_bow_demo_compiles(tmp_path):
+    _build_demo(tmp_path, "bow_demo")
+
+
+@pytest.mark.gpu
+def test_shim_vocabulary_matches_oracle(tmp_path):
+    """DBoW2::OrbVocabulary of the C++ shim: a text vocabulary loaded from disk, BowVector / FeatureVector per frame and scores
+    as the oracle computes them, bit for bit."""
+    import oracle
+    from monocular_slam_b200 import synthetic as syn
+    exe = _build_demo(tmp_path, "bow_demo")
+    va = syn.vocabulary(61, k=9, L=3)
+    vpath = tmp_path / "voc.txt"
+    syn.write_vocabulary_text(str(vpath), va, trailing_newline=True)       # as saveToTextFile ends its files
+    nframes, n, lu = 3, 400, 2
+    desc = np.stack([syn.vocabulary_features(70 + f, va, n, pool=150) for f in range(nframes)])
+    dpath = tmp_path / "desc.bin"
+    dpath.write_bytes(desc.tobytes())
+    out = tmp_path / "out.bin"
+    subprocess.check_call([exe, str(vpath), str(dpath), str(nframes), str(n), str(lu), str(out)])
+    buf = out.read_bytes()
+    ov = oracle.BowVocabulary(va)
+    pos, bows = 0, []
+    for f in range(nframes):
+        w, v, nodes, offs, feats = ov.transform(desc[f], lu)
+        (nb,) = struct.unpack_from("<i", buf, pos); pos += 4
+        rec = np.frombuffer(buf, np.dtype([("w", "<u4"), ("v", "<f8")]), nb, pos); pos += nb * 12
+        assert np.array_equal(rec["w"], w) and np.array_equal(rec["v"], v)
+        (nf,) = struct.unpack_from("<i", buf, pos); pos += 4
+        assert nf == len(nodes)
+        for g in range(nf):
+            node, c = struct.unpack_from("<Ii", buf, pos); pos += 8
+            fe = np.frombuffer(buf, "<u4", c, pos); pos += 4 * c
+            assert node == nodes[g] and np.array_equal(fe, feats[offs[g]:offs[g + 1]])
+        bows.append((w, v))
+    s = np.frombuffer(buf, "<f8", 2 * nframes, pos)
+    expect = np.array([ov.score(bows[0], b) for b in bows])
+    assert np.array_equal(s[:nframes], expect) and np.array_equal(s[nframes:], expect)

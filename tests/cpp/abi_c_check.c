@@ -54,3 +54,26 @@ int consumers(trx_handle tx, hamx_handle bf, const orbx_dmatch* d_good, const in
     rc |= hamx_loop_score(bf, cur_desc, ncur, stored, counts, nframes, cap, 10, 40, scores, &best_frame);
     return rc + best_frame;
 }
+
+/* INTEGRATION.md "The vendored DBoW2": the vocabulary's text-file columns in, whole batches transformed and scored on the device */
+int bag_of_words(int k, int L, int nnodes, const int32_t* parent, const uint8_t* leaf, const uint8_t* desc, const double* weight,
+                 const uint8_t* d_desc, const int32_t* d_counts, int nframes, int cap, uint32_t* d_words, double* d_vals, int32_t* d_nbow,
+                 uint32_t* d_fv_nodes, int32_t* d_fv_offsets, uint32_t* d_fv_feats, int32_t* d_nfv, const int64_t* d_start, double* d_scores,
+                 int q, int nbow_q)
+{
+    bowx_handle bw;
+    int32_t info[6], stopped;
+    uint32_t node;
+    double w;
+    int rc = bowx_create(&bw, 0);
+    rc |= bowx_set_vocabulary(bw, k, L, BOWX_L1_NORM, BOWX_TF_IDF, nnodes, parent, leaf, desc, weight);
+    rc |= bowx_vocabulary_info(bw, info);
+    rc |= bowx_transform_batch_dev(bw, d_desc, d_counts, nframes, cap, 4, d_words, d_vals, d_nbow, d_fv_nodes, d_fv_offsets, d_fv_feats, d_nfv);
+    rc |= bowx_score_batch_dev(bw, d_words + (size_t)q * cap, d_vals + (size_t)q * cap, nbow_q, d_start, d_nbow, d_words, d_vals, nframes, d_scores);
+    rc |= bowx_stop_words(bw, 0.5, &stopped);
+    rc |= bowx_parent_node(bw, 0, 2, &node);
+    rc |= bowx_word_weight(bw, 0, &w);
+    rc |= bowx_synchronize(bw);
+    rc |= bowx_destroy(bw);
+    return rc + info[5] + stopped + (int)node + (w > 0);
+}

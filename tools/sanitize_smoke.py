@@ -73,6 +73,18 @@ tri.select_new_dev(d_g.data_ptr(), d_ng.data_ptr(), 0, d_pm.data_ptr(), d_cur.da
 tri.synchronize()
 tri.close(); fm.close(); orb.close()
 m.set_kernel(_lib.KERNEL_AUTO)
+# bag of words: 16- and 32-lane descents, both key widths of the sort, every scoring type
+from monocular_slam_b200 import Vocabulary
+for shape in (dict(k=10, L=3), dict(k=19, L=2, ragged=True), dict(k=40, L=2)):
+    va = syn.vocabulary(3, **shape)
+    for scoring in range(6):
+        voc = Vocabulary(va, scoring, scoring % 4)
+        d = np.stack([syn.vocabulary_features(4, va, 300, pool=60), syn.descriptors(6, 300)])
+        bows = voc.transform_batch(d, [300, 77], 1)
+        voc.transform_batch(d, [0, 300])
+        voc.score_batch(bows[0][0], [b[0] for b in bows] * 5)
+        voc.transform_features(d[0], 2)
+        voc.close()
 s = torch.cuda.Stream()
 with torch.cuda.stream(s):
     ms = [BFMatcher() for _ in range(3)]

@@ -282,3 +282,62 @@ class ShardedLoopScorer:
             self.dist.all_gather_into_tensor(flat, padded, group=self.group)
         scores = torch.cat([flat[r * width:r * width + int(b[r + 1] - b[r])] for r in range(self.world)])
         return scores, self._best(scores)
+
+
+class ShardedBowDatabase:
+    """score(query, entry) of the vendored DBoW2's scoring objects (ThirdParty/DBoW2/DBoW2/ScoringObject.cpp) against a
+    database of bag-of-words vectors sharded BY ENTRY over the ranks: every rank scores its own contiguous block
+    ``shard_bounds(nentries_total, world)`` in one launch (bowx_score_batch_dev), the 8-byte scores are exchanged with one
+    all-gather, and every rank takes the same best entry (largest score, the first one on ties).  Entries are independent, so
+    the scores equal a single-device pass.
+
+    ``local_scores(qwords, qvals, start, count, words, vals) -> float64 tensor [nlocal]`` defaults to the CUDA kernel of a
+    ``Vocabulary``; a stand-in can be injected to exercise the exchange on CPU (gloo)."""
+
+    def __init__(self, vocabulary=None, group=None, local_scores=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.voc = vocabulary
+        self._local = local_scores or self._local_cuda
+        if vocabulary is None and local_scores is None:
+            raise ValueError("ShardedBowDatabase needs a Vocabulary (CUDA); there is no CPU implementation in this package")
+
+    def _local_cuda(self, qwords, qvals, start, count, words, vals):
+        import torch
+        s = torch.cuda.current_stream().cuda_stream
+        if s == 0:
+            raise RuntimeError("run ShardedBowDatabase under a non-default torch stream")
+        self.voc.set_stream(s)
+        n = count.shape[0]
+        scores = torch.empty(max(n, 1), dtype=torch.float64, device=qwords.device)
+        self.voc.score_batch_dev(qwords.data_ptr(), qvals.data_ptr(), qwords.shape[0], start.data_ptr(), count.data_ptr(), words.data_ptr(),
+                                 vals.data_ptr(), n, scores.data_ptr())
+        return scores[:n]
+
+    def score(self, qwords, qvals, start_shard, count_shard, words, vals, nentries_total):
+        """The query (replicated) against this rank's block of entries: entry e of the block is words / vals
+        [start_shard[e], start_shard[e] + count_shard[e]).  Returns (scores[nentries_total] float64 tensor, best entry or -1)."""
+        import torch
+        b = shard_bounds(nentries_total, self.world)
+        lo, hi = int(b[self.rank]), int(b[self.rank + 1])
+        if count_shard.shape[0] != hi - lo:
+            raise ValueError("rank %d owns entries [%d, %d) but was given %d" % (self.rank, lo, hi, count_shard.shape[0]))
+        local = self._local(qwords, qvals, start_shard, count_shard, words, vals)
+        if self.world == 1:
+            scores = local
+        else:
+            width = int((b[1:] - b[:-1]).max())
+            padded = torch.zeros(width, dtype=torch.float64, device=local.device)
+            padded[:hi - lo] = local
+            if self.dist.get_backend(self.group) == "gloo" and padded.is_cuda:
+                parts = [torch.empty(width, dtype=torch.float64) for _ in range(self.world)]     # plumbing fallback, as ShardedLoopScorer
+                self.dist.all_gather(parts, padded.cpu(), group=self.group)
+                flat = torch.cat(parts).to(local.device)
+            else:
+                flat = torch.empty(self.world * width, dtype=torch.float64, device=local.device)
+                self.dist.all_gather_into_tensor(flat, padded, group=self.group)
+            scores = torch.cat([flat[r * width:r * width + int(b[r + 1] - b[r])] for r in range(self.world)])
+        best = int(torch.argmax(scores)) if nentries_total else -1
+        return scores, best

@@ -93,6 +93,32 @@ def main():
     scores, best = sl.score(q, frames[lo:hi].contiguous(), counts[lo:hi].contiguous(), nf)
     stream.synchronize()
     assert torch.equal(scores, want) and torch.equal(best, wbest) and int(best[0]) == 9, "rank %d: frame-sharded loop scores differ" % rank
+    # entry-sharded bag-of-words scoring: 41 stored vectors (uneven blocks) built on this device from seeded descriptors
+    from monocular_slam_b200 import Vocabulary
+    from monocular_slam_b200 import synthetic as syn
+    from monocular_slam_b200.sharded import ShardedBowDatabase
+    va = syn.vocabulary(13, k=9, L=3)
+    voc = Vocabulary(va, device=dev.index)
+    voc.set_stream(stream.cuda_stream)
+    nent, bcap = 41, 500
+    bdesc = np.stack([syn.vocabulary_features(200 + e, va, bcap, pool=120) for e in range(nent)])
+    bcnt = torch.from_numpy(np.array([bcap if e % 5 else 37 * (e % 3) for e in range(nent)], np.int32)).to(dev)
+    d_bdesc = torch.from_numpy(bdesc).to(dev)
+    bw = torch.zeros((nent, bcap), dtype=torch.int32, device=dev); bv = torch.zeros((nent, bcap), dtype=torch.float64, device=dev)
+    bn = torch.zeros(nent, dtype=torch.int32, device=dev)
+    voc.transform_batch_dev(d_bdesc.data_ptr(), bcnt.data_ptr(), nent, bcap, 0, bw.data_ptr(), bv.data_ptr(), bn.data_ptr())
+    bstart = torch.arange(nent, dtype=torch.int64, device=dev) * bcap
+    bwant = torch.empty(nent, dtype=torch.float64, device=dev)
+    qe = 23
+    nq_ = int(bn[qe])
+    voc.score_batch_dev(bw[qe].data_ptr(), bv[qe].data_ptr(), nq_, bstart.data_ptr(), bn.data_ptr(), bw.data_ptr(), bv.data_ptr(), nent, bwant.data_ptr())
+    b = shard_bounds(nent, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    sdb = ShardedBowDatabase(voc)
+    bscores, bbest = sdb.score(bw[qe, :nq_].contiguous(), bv[qe, :nq_].contiguous(), bstart[lo:hi].contiguous(), bn[lo:hi].contiguous(), bw, bv, nent)
+    stream.synchronize()
+    assert torch.equal(bscores, bwant) and bbest == qe and abs(float(bwant[qe]) - 1.0) < 1e-12, "rank %d: entry-sharded bag-of-words scores differ" % rank
+    voc.close()
     p2p.close()
     m.close()
     dist.barrier()

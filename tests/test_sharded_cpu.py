@@ -142,3 +142,45 @@ def test_frame_sharded_loop_scoring_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_loop_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def _bow_worker(rank, world, port, ret):
+    """Entry-sharded bag-of-words scoring over gloo with the oracle standing in for the scoring kernel."""
+    from monocular_slam_b200.sharded import ShardedBowDatabase
+    from monocular_slam_b200 import synthetic as syn
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    va = syn.vocabulary(3, k=6, L=3)
+    ov = oracle.BowVocabulary(va)
+    bows = [ov.transform(syn.vocabulary_features(20 + e, va, n, pool=60)) for e, n in enumerate([200, 0, 150, 1, 90, 200, 33])]   # 7 entries: 4 + 3
+    query = ov.transform(syn.vocabulary_features(24, va, 90, pool=60))          # entry 4's descriptors: score 1
+    nent = len(bows)
+    b = shard_bounds(nent, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    count = np.array([len(bw[0]) for bw in bows[lo:hi]], np.int32)
+    start = np.concatenate([[0], np.cumsum(count[:-1])]).astype(np.int64)
+    words = np.concatenate([bw[0] for bw in bows[lo:hi]]).astype(np.int64)
+    vals = np.concatenate([bw[1] for bw in bows[lo:hi]])
+
+    def local(qw, qv, st, ct, w, v):
+        out = [ov.score((qw.numpy().astype(np.uint32), qv.numpy()), (w.numpy()[s:s + c].astype(np.uint32), v.numpy()[s:s + c])) for s, c in zip(st.tolist(), ct.tolist())]
+        return torch.tensor(out, dtype=torch.float64)
+    db = ShardedBowDatabase(None, local_scores=local)
+    scores, best = db.score(torch.from_numpy(query[0].astype(np.int64)), torch.from_numpy(query[1]), torch.from_numpy(start), torch.from_numpy(count),
+                            torch.from_numpy(words), torch.from_numpy(vals), nent)
+    want = np.array([ov.score(query, bw) for bw in bows])
+    ret[rank] = bool(np.array_equal(scores.numpy(), want) and best == 4 and abs(want[4] - 1.0) < 1e-12)
+    dist.destroy_process_group()
+
+
+def test_entry_sharded_bow_scoring_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    oracle.build()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bow_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -45,7 +45,7 @@ class Params(C.Structure):
 
 def build(force=False):
     """Compile liborb_oracle.so with the committed Makefile (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "fmat_oracle.c", "tri_oracle.c", "loop_oracle.c", "bow_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "fmat_oracle.c", "tri_oracle.c", "loop_oracle.c", "bow_oracle.c", "jpeg_oracle.c")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -119,6 +119,8 @@ def lib():
         L.bow_parent_node.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
         L.bow_word_weight.restype = C.c_double
         L.bow_word_weight.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_jpeg_probe.argtypes = [u8p, C.c_size_t, i32p]
+        L.orc_jpeg_decode_gray.argtypes = [u8p, C.c_size_t, u8p, C.c_int]
         _lib = L
     return _lib
 
@@ -535,3 +537,27 @@ def bow_score(scoring, a, b):
     w1, v1 = np.ascontiguousarray(a[0], np.uint32), np.ascontiguousarray(a[1], np.float64)
     w2, v2 = np.ascontiguousarray(b[0], np.uint32), np.ascontiguousarray(b[1], np.float64)
     return float(lib().bow_score(int(scoring), _u32(w1), _f64(v1), len(w1), _u32(w2), _f64(v2), len(w2)))
+
+
+# ---- grey-scale baseline JPEG (jpeg_oracle.c; the decoder behind imread in src/FrameLoader.cpp:62)
+JPEG_UNSUPPORTED, JPEG_CORRUPT = -1, -2
+
+
+def jpeg_probe(data):
+    """(width, height, restart interval, blocks) of a file the decoder handles; raises ValueError with the status otherwise."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    info = np.zeros(4, np.int32)
+    rc = lib().orc_jpeg_probe(_u8(buf), len(buf), _i32(info))
+    if rc:
+        raise ValueError(rc)
+    return tuple(int(x) for x in info)
+
+
+def jpeg_decode_gray(data):
+    w, h, _, _ = jpeg_probe(data)
+    buf = np.frombuffer(bytes(data), np.uint8)
+    out = np.zeros((h, w), np.uint8)
+    rc = lib().orc_jpeg_decode_gray(_u8(buf), len(buf), _u8(out), w)
+    if rc:
+        raise ValueError(rc)
+    return out

@@ -47,7 +47,8 @@ typedef enum {
     ORBX_E_CUDA = -2,      /* CUDA runtime error, or no usable device */
     ORBX_E_CAPACITY = -3,  /* more keypoints than the caller's buffer (or the handle's internal lists) can hold */
     ORBX_E_ALLOC = -4,     /* out of host or device memory */
-    ORBX_E_ALIGN = -5      /* a device pointer is not 16-byte aligned */
+    ORBX_E_ALIGN = -5,     /* a device pointer is not 16-byte aligned */
+    ORBX_E_UNSUPPORTED = -6 /* a valid input of a kind this library does not handle (jpgx_*: a JPEG that is not one-component baseline) */
 } orbx_status;
 
 /* == cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle (degrees), response, octave, class_id (-1) */
@@ -472,6 +473,30 @@ ORBX_API int bowx_score_batch(bowx_handle h, const uint32_t* qwords, const doubl
 ORBX_API int bowx_score_batch_dev(bowx_handle h, const uint32_t* d_qwords, const double* d_qvals, int nq, const int64_t* d_db_start,
                                   const int32_t* d_db_count, const uint32_t* d_db_words, const double* d_db_vals, int nentries,
                                   double* d_scores);
+
+/* ------------------------------------------------------------------ frame ingest: grey-scale baseline JPEG files
+ * The reference reads every frame with cv::imread(path, CV_LOAD_IMAGE_UNCHANGED) (src/FrameLoader.cpp:62); for a .jpg that is
+ * libjpeg behind OpenCV (default DCT method JDCT_ISLOW).  This family decodes a whole batch of such files on the GPU, straight
+ * into the device-resident frames orbx_extract_batch_dev reads, bit for bit what cv2.imdecode returns (tests/golden/
+ * jpeg_cases.npz): only the compressed bytes cross PCIe.  Handled: one component, 8 bits, Huffman, baseline or extended
+ * sequential (SOF0 / SOF1), any quantisation / Huffman tables, with or without restart markers (the restart interval is the
+ * unit of parallelism: files without markers decode one warp per file).  Everything else -- colour, progressive, arithmetic,
+ * 12-bit -- returns ORBX_E_UNSUPPORTED and the caller keeps its CPU decoder for that file; damaged headers ORBX_E_INVALID. */
+typedef struct jpgx_context* jpgx_handle;
+ORBX_API int jpgx_create(jpgx_handle* out, int device);
+ORBX_API int jpgx_destroy(jpgx_handle h);
+ORBX_API int jpgx_set_stream(jpgx_handle h, void* cuda_stream);    /* same rules as hamx_set_stream */
+ORBX_API int jpgx_get_stream(jpgx_handle h, void** cuda_stream);
+ORBX_API int jpgx_synchronize(jpgx_handle h);
+/* Headers only (no GPU work): info[4] = {width, height, restart interval in 8x8 blocks (0: none), 8x8 blocks}. */
+ORBX_API int jpgx_probe(const uint8_t* file, size_t size, int32_t* info);
+/* nfiles encoded files in host memory, all w x h, into device frames: frame i at d_frames + i*frame_pitch, rows `stride` bytes
+ * apart.  The files are copied before the call returns; the decode is asynchronous on the handle's stream. */
+ORBX_API int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int h_,
+                                        uint8_t* d_frames, size_t frame_pitch, size_t stride);
+/* the same into host memory (blocking) */
+ORBX_API int jpgx_decode_gray_batch(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int h_, uint8_t* frames,
+                                    size_t frame_pitch, size_t stride);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ assert KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DT
 
 HARRIS_SCORE, FAST_SCORE = 0, 1
 KERNEL_AUTO, KERNEL_INTEGER, KERNEL_TENSOR = 0, 1, 2     # hamx_set_kernel
-OK, E_INVALID, E_CUDA, E_CAPACITY, E_ALLOC, E_ALIGN = 0, -1, -2, -3, -4, -5
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_ALLOC, E_ALIGN, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 
 # every symbol include/orbx.h declares (tests/test_abi.py checks the header against this list and the built library)
 SYMBOLS = [
@@ -39,6 +39,8 @@ SYMBOLS = [
     "bowx_create", "bowx_destroy", "bowx_set_stream", "bowx_get_stream", "bowx_synchronize", "bowx_set_vocabulary", "bowx_vocabulary_info",
     "bowx_stop_words", "bowx_parent_node", "bowx_word_weight", "bowx_transform_features", "bowx_transform_features_dev",
     "bowx_transform_batch", "bowx_transform_batch_dev", "bowx_score", "bowx_score_batch", "bowx_score_batch_dev",
+    "jpgx_create", "jpgx_destroy", "jpgx_set_stream", "jpgx_get_stream", "jpgx_synchronize", "jpgx_probe", "jpgx_decode_gray_batch_dev",
+    "jpgx_decode_gray_batch",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -121,6 +123,14 @@ def lib():
     L.trx_triangulate_back_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.trx_associate_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.trx_select_new_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.jpgx_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.jpgx_destroy.argtypes = [vp]
+    L.jpgx_set_stream.argtypes = [vp, vp]
+    L.jpgx_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.jpgx_synchronize.argtypes = [vp]
+    L.jpgx_probe.argtypes = [vp, C.c_size_t, i32p]
+    L.jpgx_decode_gray_batch_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t]
+    L.jpgx_decode_gray_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t]
     L.bowx_create.argtypes = [C.POINTER(vp), C.c_int]
     L.bowx_destroy.argtypes = [vp]
     L.bowx_set_stream.argtypes = [vp, vp]

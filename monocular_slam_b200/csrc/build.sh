@@ -6,7 +6,7 @@ NVCC=${NVCC:-nvcc}
 OUT=../liborbx.so
 FLAGS="$ORBX_EXTRA_FLAGS -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-Wall,-Wextra,-fvisibility=hidden -Xptxas -v"
 OBJS=""
-for f in hamming fmat triangulate bow orb_pyramid orb_fast orb_select orb_describe orbx_api; do
+for f in hamming fmat triangulate bow jpeg orb_pyramid orb_fast orb_select orb_describe orbx_api; do
     $NVCC $FLAGS -c $f.cu -o $f.o
     OBJS="$OBJS $f.o"
 done

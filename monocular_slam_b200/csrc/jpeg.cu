@@ -1,0 +1,610 @@
+// jpeg.cu -- frame ingest for grey-scale baseline JPEG files (sm_100a): what cv::imread does for the reference's frame loader
+// (src/FrameLoader.cpp:62, imread(path, CV_LOAD_IMAGE_UNCHANGED); for .jpg that is libjpeg behind OpenCV, JDCT_ISLOW), for a
+// whole batch of files at once and straight into the device-resident frames the extractor reads.  Only the compressed bytes
+// cross PCIe (a fifth of the raw frames at quality 90).
+//
+//   host      marker parsing (ITU-T T.81 Annex B): DQT, SOF0/1, DHT, DRI, SOS of a one-component 8-bit Huffman file; the
+//             entropy-coded segment is cut at its restart markers into intervals (T.81 E.2.4) -- the unit of parallelism
+//   K17 k_jpeg_huff   one warp per restart interval: all lanes strip the stuffed zero bytes (FF 00 -> FF) into a scratch
+//             copy, then lane 0 runs the sequential Huffman decoder of T.81 F.2.2 over it (10-bit lookahead tables, the DC
+//             predictor restarting with the interval) and scatters the non-zero coefficients of each 8x8 block
+//   K18 k_jpeg_idct   one thread per block: dequantisation and libjpeg's jpeg_idct_islow (jidctint.c: 13-bit constants, two
+//             passes, DESCALE) in registers, the range-limit table of jdmaster.c as arithmetic, 8-byte row stores that
+//             coalesce across the blocks of a block row
+//
+// Bit-exact with cv2.imdecode (libjpeg-turbo 3.1.2) on every file of tests/golden/jpeg_cases.npz.  Files without restart
+// markers decode too -- one warp per file, so only a batch of them is fast.  Anything but one-component baseline / extended
+// sequential Huffman (progressive, colour, 12-bit, arithmetic) is refused with ORBX_E_UNSUPPORTED: the caller keeps its CPU
+// decoder for those.
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace orbx {
+namespace {
+
+constexpr int JP_LOOK = 10;                       // lookahead bits of the Huffman tables
+constexpr int JP_HUFF_THREADS = 128;              // 4 intervals per CTA
+constexpr int JP_IDCT_THREADS = 128;
+
+struct JpHuff {                                   // one Huffman table on the device
+    uint16_t look[1 << JP_LOOK];                  // (length << 8) | symbol for codes of at most JP_LOOK bits, 0: longer
+    int32_t maxcode[18];                          // T.81 F.2.2.3, per code length; [17] = sentinel
+    int32_t valoff[17];                           // valptr[l] - mincode[l]
+    uint8_t vals[256];
+};
+struct JpTables {                                 // what one file's scan needs
+    JpHuff dc, ac;
+    uint16_t quant[64];                           // natural order
+};
+struct JpInterval {
+    uint32_t src, src_len;                        // bytes of the interval in the uploaded stream
+    uint32_t scratch;                             // byte offset of its stripped copy (multiple of 4)
+    uint32_t first_block, nblocks;                // blocks of its file, raster order
+    uint32_t file;
+};
+
+__constant__ uint8_t c_natural_order[64] = {
+    0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// bit reader over the stripped bytes of an interval (a whole number of 32-bit words; zero bits past the end, as libjpeg pads)
+struct JpBits {
+    const uint32_t* words; uint32_t nwords, wi;
+    unsigned long long buf; int nbits;            // `nbits` valid bits at the top of buf
+    __device__ __forceinline__ void fill()
+    {
+        if (nbits <= 32) {
+            const uint32_t w = wi < nwords ? words[wi] : 0u;          // written by this warp a moment ago: a plain load
+            wi++;
+            buf |= (unsigned long long)__byte_perm(w, 0, 0x0123) << (32 - nbits);
+            nbits += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek16() const { return (uint32_t)(buf >> 48); }
+    __device__ __forceinline__ void skip(int n) { buf <<= n; nbits -= n; }
+    __device__ __forceinline__ int get(int n) { const int v = (int)(buf >> (64 - n)); skip(n); return v; }     // 1 <= n <= 16
+};
+
+__device__ __forceinline__ int jp_decode(JpBits& b, const JpHuff* __restrict__ t)
+{
+    b.fill();
+    const uint32_t p = b.peek16();
+    const uint32_t e = __ldg(&t->look[p >> (16 - JP_LOOK)]);
+    if (e) { b.skip((int)(e >> 8)); return (int)(e & 255); }
+    for (int l = JP_LOOK + 1; l <= 16; l++) {
+        const int code = (int)(p >> (16 - l));
+        if (code <= __ldg(&t->maxcode[l])) { b.skip(l); return __ldg(&t->vals[(code + __ldg(&t->valoff[l])) & 255]); }
+    }
+    b.skip(16);
+    return 0;                                     // no such code: corrupt data; libjpeg substitutes a zero, too
+}
+__device__ __forceinline__ int jp_extend(int x, int s) { return x < (1 << (s - 1)) ? x - (1 << s) + 1 : x; }
+
+// ---- K17
+__global__ void __launch_bounds__(JP_HUFF_THREADS)
+k_jpeg_huff(const uint8_t* __restrict__ stream, const JpInterval* __restrict__ intervals, int nintervals, const JpTables* __restrict__ tables,
+            const int32_t* __restrict__ file_tables, uint8_t* __restrict__ scratch, int16_t* __restrict__ coefs, uint32_t blocks_per_file)
+{
+    const int lane = threadIdx.x & 31;
+    const int it = blockIdx.x * (JP_HUFF_THREADS / 32) + (threadIdx.x >> 5);
+    if (it >= nintervals) return;
+    const JpInterval iv = intervals[it];
+    // phase 1, all lanes: copy the interval without the zero byte that follows every FF
+    uint8_t* dst = scratch + iv.scratch;
+    uint32_t out = 0;
+    uint32_t prev_ff = 0;                         // was the last byte of the previous round FF?
+    for (uint32_t i0 = 0; i0 < iv.src_len; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool in = i < iv.src_len;
+        const uint32_t byte = in ? stream[iv.src + i] : 0u;
+        uint32_t before = __shfl_up_sync(0xffffffffu, byte, 1);
+        if (lane == 0) before = prev_ff ? 0xFFu : 0u;
+        const bool keep = in && !(byte == 0 && before == 0xFF);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) dst[out + __popc(bal & ((1u << lane) - 1))] = (uint8_t)byte;
+        out += __popc(bal);
+        // (FF 00 FF 00: the second FF is data, its predecessor 00 was dropped -- `before` looks at the raw stream, which is right:
+        // a stuffed 00 is never itself followed by a meaningful 00)
+        prev_ff = __shfl_sync(0xffffffffu, byte, 31) == 0xFF && (i0 + 31 < iv.src_len);
+    }
+    const uint32_t nwords = (out + 3) / 4;
+    if (lane < 4 && out + lane < nwords * 4) dst[out + lane] = 0;      // pad the last word
+    __syncwarp();
+    if (lane != 0) return;
+    // phase 2, lane 0: T.81 F.2.2 over the stripped bytes
+    const JpTables* tb = tables + file_tables[iv.file];
+    JpBits b = {reinterpret_cast<const uint32_t*>(dst), nwords, 0, 0ull, 0};
+    int16_t* co = coefs + ((size_t)iv.file * blocks_per_file + iv.first_block) * 64;
+    int dc = 0;
+    for (uint32_t blk = 0; blk < iv.nblocks; blk++, co += 64) {
+        int s = jp_decode(b, &tb->dc) & 15;
+        if (s) { b.fill(); s = jp_extend(b.get(s), s); }
+        dc += s;
+        if (dc) co[0] = (int16_t)dc;
+        for (int k = 1; k < 64; k++) {
+            const int rs = jp_decode(b, &tb->ac);
+            const int r = rs >> 4, sz = rs & 15;
+            if (sz) {
+                k += r;
+                b.fill();
+                const int v = b.get(sz);
+                if (k > 63) break;                // corrupt data
+                co[c_natural_order[k]] = (int16_t)jp_extend(v, sz);
+            } else {
+                if (r != 15) break;               // end of block
+                k += 15;
+            }
+        }
+    }
+}
+
+// ---- K18: jidctint.c jpeg_idct_islow
+#define JP_FIX_0_298631336 2446
+#define JP_FIX_0_390180644 3196
+#define JP_FIX_0_541196100 4433
+#define JP_FIX_0_765366865 6270
+#define JP_FIX_0_899976223 7373
+#define JP_FIX_1_175875602 9633
+#define JP_FIX_1_501321110 12299
+#define JP_FIX_1_847759065 15137
+#define JP_FIX_1_961570560 16069
+#define JP_FIX_2_053119869 16819
+#define JP_FIX_2_562915447 20995
+#define JP_FIX_3_072711026 25172
+
+// one 8-point pass: in[0..7] -> out[0..7] before the final shift
+__device__ __forceinline__ void jp_idct8(const int* in, int* o)
+{
+    int z2 = in[2], z3 = in[6];
+    int z1 = (z2 + z3) * JP_FIX_0_541196100;
+    int tmp2 = z1 + z3 * (-JP_FIX_1_847759065);
+    int tmp3 = z1 + z2 * JP_FIX_0_765366865;
+    int tmp0 = (int)((unsigned)(in[0] + in[4]) << 13);
+    int tmp1 = (int)((unsigned)(in[0] - in[4]) << 13);
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * JP_FIX_1_175875602;
+    tmp0 *= JP_FIX_0_298631336; tmp1 *= JP_FIX_2_053119869; tmp2 *= JP_FIX_3_072711026; tmp3 *= JP_FIX_1_501321110;
+    z1 *= -JP_FIX_0_899976223; z2 *= -JP_FIX_2_562915447; z3 *= -JP_FIX_1_961570560; z4 *= -JP_FIX_0_390180644;
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    o[0] = tmp10 + tmp3; o[7] = tmp10 - tmp3;
+    o[1] = tmp11 + tmp2; o[6] = tmp11 - tmp2;
+    o[2] = tmp12 + tmp1; o[5] = tmp12 - tmp1;
+    o[3] = tmp13 + tmp0; o[4] = tmp13 - tmp0;
+}
+// sample_range_limit + CENTERJSAMPLE indexed with & RANGE_MASK (jdmaster.c prepare_range_limit_table)
+__device__ __forceinline__ uint32_t jp_range_limit(int x)
+{
+    x &= 1023;
+    return x < 128 ? x + 128 : (x < 512 ? 255 : (x < 896 ? 0 : x - 896));
+}
+
+__global__ void __launch_bounds__(JP_IDCT_THREADS)
+k_jpeg_idct(const int16_t* __restrict__ coefs, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables, int nfiles, int w, int h,
+            int bw, uint32_t blocks_per_file, uint8_t* __restrict__ frames, size_t frame_pitch, size_t stride)
+{
+    const uint32_t blk = blockIdx.x * JP_IDCT_THREADS + threadIdx.x;
+    const int file = blockIdx.y;
+    if (blk >= blocks_per_file || file >= nfiles) return;
+    const uint16_t* q = tables[file_tables[file]].quant;
+    const uint4* cp = reinterpret_cast<const uint4*>(coefs + ((size_t)file * blocks_per_file + blk) * 64);
+    int ws[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {                 // dequantise (row r of the block)
+        const uint4 v = __ldg(cp + r);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int coef = (int)(short)((c & 1) ? (u[c >> 1] >> 16) : (u[c >> 1] & 0xffff));
+            ws[r * 8 + c] = coef * (int)__ldg(q + r * 8 + c);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {                 // pass 1: columns
+        int in[8], o[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) in[r] = ws[r * 8 + c];
+        jp_idct8(in, o);
+#pragma unroll
+        for (int r = 0; r < 8; r++) ws[r * 8 + c] = (o[r] + (1 << 10)) >> 11;
+    }
+    const int bx = (int)(blk % (uint32_t)bw), by = (int)(blk / (uint32_t)bw);
+    uint8_t* out = frames + (size_t)file * frame_pitch + (size_t)by * 8 * stride + (size_t)bx * 8;
+    const int cols = min(8, w - bx * 8), rows = min(8, h - by * 8);
+    const bool aligned = cols == 8 && ((reinterpret_cast<uintptr_t>(out) | stride) & 7) == 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {                 // pass 2: rows
+        int o[8];
+        jp_idct8(ws + r * 8, o);
+        uint32_t px[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) px[c] = jp_range_limit((o[c] + (1 << 17)) >> 18);
+        if (r < rows) {
+            uint8_t* row = out + (size_t)r * stride;
+            if (aligned) {
+                *reinterpret_cast<uint2*>(row) = make_uint2(px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24), px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    if (c < cols) row[c] = (uint8_t)px[c];
+            }
+        }
+    }
+}
+
+// ---- host: marker parsing
+struct HostHuff { bool present; uint8_t bits[17]; uint8_t vals[256]; };
+struct HostFile {
+    int width, height, restart;
+    uint16_t quant[64];
+    HostHuff dc, ac;
+    size_t scan, scan_len;                        // entropy-coded segment
+};
+
+static bool build_table(const HostHuff& h, JpHuff& t)
+{
+    memset(&t, 0, sizeof(t));
+    memcpy(t.vals, h.vals, 256);
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; l++) {
+        t.valoff[l] = k - code;
+        for (int i = 0; i < h.bits[l]; i++, code++, k++) {
+            if (code >= (1 << l) || k >= 256) return false;        // over-subscribed table
+            if (l <= JP_LOOK)
+                for (int fill = 0; fill < (1 << (JP_LOOK - l)); fill++) t.look[(code << (JP_LOOK - l)) | fill] = (uint16_t)((l << 8) | h.vals[k]);
+        }
+        t.maxcode[l] = h.bits[l] ? code - 1 : -1;
+        code <<= 1;
+    }
+    t.maxcode[17] = 0x7fffffff;
+    return true;
+}
+
+// returns ORBX_OK, ORBX_E_UNSUPPORTED (a valid JPEG of another kind) or ORBX_E_INVALID (not a JPEG / damaged headers)
+static int parse_jpeg(const uint8_t* f, size_t n, HostFile& out, const char** why)
+{
+    static const uint8_t natural[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                        35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+#define JP_FAIL(code, msg) do { *why = msg; return code; } while (0)
+    if (n < 4 || f[0] != 0xFF || f[1] != 0xD8) JP_FAIL(ORBX_E_INVALID, "not a JPEG file (no SOI)");
+    uint16_t quant[4][64];
+    bool have_quant[4] = {false, false, false, false}, have_sof = false;
+    HostHuff dc[4], ac[4];
+    for (int i = 0; i < 4; i++) dc[i].present = ac[i].present = false;
+    int tq = 0;
+    out.restart = 0;
+    size_t p = 2;
+    for (;;) {
+        if (p + 4 > n || f[p] != 0xFF) JP_FAIL(ORBX_E_INVALID, "damaged marker structure");
+        while (p < n && f[p] == 0xFF) p++;
+        if (p >= n) JP_FAIL(ORBX_E_INVALID, "damaged marker structure");
+        const int m = f[p++];
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+        if (m == 0xD9) JP_FAIL(ORBX_E_INVALID, "end of image before the scan");
+        if (p + 2 > n) JP_FAIL(ORBX_E_INVALID, "truncated header");
+        const size_t len = ((size_t)f[p] << 8) | f[p + 1];
+        if (len < 2 || p + len > n) JP_FAIL(ORBX_E_INVALID, "truncated header");
+        const uint8_t* s = f + p + 2;
+        const size_t sl = len - 2;
+        if (m == 0xC0 || m == 0xC1) {
+            if (sl < 6) JP_FAIL(ORBX_E_INVALID, "short SOF");
+            if (s[0] != 8) JP_FAIL(ORBX_E_UNSUPPORTED, "sample precision is not 8 bits");
+            out.height = (s[1] << 8) | s[2];
+            out.width = (s[3] << 8) | s[4];
+            if (s[5] != 1) JP_FAIL(ORBX_E_UNSUPPORTED, "not a one-component (grey-scale) file");
+            if (sl < 9 || out.width == 0 || out.height == 0) JP_FAIL(ORBX_E_INVALID, "bad SOF");
+            tq = s[8] & 3;
+            have_sof = true;
+        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            JP_FAIL(ORBX_E_UNSUPPORTED, "progressive, lossless, hierarchical or arithmetic-coded file");
+        } else if (m == 0xC4) {
+            size_t q = 0;
+            while (q < sl) {
+                if (q + 17 > sl) JP_FAIL(ORBX_E_INVALID, "short DHT");
+                const int tc = s[q] >> 4, th = s[q] & 15;
+                if (tc > 1 || th > 3) JP_FAIL(ORBX_E_INVALID, "bad DHT selector");
+                HostHuff& t = tc ? ac[th] : dc[th];
+                int count = 0;
+                t.bits[0] = 0;
+                for (int l = 1; l <= 16; l++) { t.bits[l] = s[q + l]; count += t.bits[l]; }
+                q += 17;
+                if (count > 256 || q + (size_t)count > sl) JP_FAIL(ORBX_E_INVALID, "bad DHT counts");
+                memset(t.vals, 0, sizeof(t.vals));
+                memcpy(t.vals, s + q, (size_t)count);
+                q += (size_t)count;
+                t.present = true;
+            }
+        } else if (m == 0xDB) {
+            size_t q = 0;
+            while (q < sl) {
+                const int pq = s[q] >> 4, t = s[q] & 15;
+                if (t > 3 || pq > 1) JP_FAIL(ORBX_E_INVALID, "bad DQT selector");
+                q++;
+                if (q + (size_t)(pq ? 128 : 64) > sl) JP_FAIL(ORBX_E_INVALID, "short DQT");
+                for (int i = 0; i < 64; i++) {
+                    quant[t][natural[i]] = (uint16_t)(pq ? ((s[q] << 8) | s[q + 1]) : s[q]);
+                    q += pq ? 2 : 1;
+                }
+                have_quant[t] = true;
+            }
+        } else if (m == 0xDD) {
+            if (sl < 2) JP_FAIL(ORBX_E_INVALID, "short DRI");
+            out.restart = (s[0] << 8) | s[1];
+        } else if (m == 0xDA) {
+            if (!have_sof) JP_FAIL(ORBX_E_INVALID, "scan before the frame header");
+            if (sl < 6 || s[0] != 1) JP_FAIL(ORBX_E_UNSUPPORTED, "scan of several components");
+            const int td = s[2] >> 4, ta = s[2] & 15;
+            if (s[3] != 0 || s[4] != 63 || s[5] != 0) JP_FAIL(ORBX_E_UNSUPPORTED, "not a sequential scan");
+            if (td > 3 || ta > 3 || !dc[td].present || !ac[ta].present || !have_quant[tq]) JP_FAIL(ORBX_E_INVALID, "scan refers to a missing table");
+            out.dc = dc[td]; out.ac = ac[ta];
+            memcpy(out.quant, quant[tq], sizeof(out.quant));
+            out.scan = p + len;
+            out.scan_len = n - out.scan;
+            return ORBX_OK;
+        }
+        p += len;
+    }
+#undef JP_FAIL
+}
+
+}  // namespace
+}  // namespace orbx
+
+using namespace orbx;
+
+struct jpgx_context {
+    int device;
+    cudaStream_t own_stream, stream;
+    cudaEvent_t staged;                           // the last call's uploads have left the pinned staging buffers
+    bool staged_pending;
+    uint8_t* h_stream; size_t h_stream_bytes;     // pinned: the entropy-coded segments of a batch, one after the other
+    uint8_t* d_stream; size_t d_stream_bytes;
+    uint8_t* d_scratch; size_t d_scratch_bytes;   // the same without stuffed bytes
+    JpInterval* h_intervals; size_t h_intervals_n;
+    JpInterval* d_intervals; size_t d_intervals_bytes;
+    JpTables* h_tables; JpTables* d_tables; int tables_cap;
+    int32_t* h_file_tables; size_t h_file_tables_n;
+    int32_t* d_file_tables; size_t d_file_tables_bytes;
+    int16_t* d_coefs; size_t d_coefs_bytes;
+    uint8_t* d_frames; size_t d_frames_bytes;     // staging of the host-output form
+};
+
+template <typename T>
+static int jp_grow(T** p, size_t* have, size_t want)
+{
+    if (*p && *have >= want) return ORBX_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *have = 0; }
+    const size_t bytes = align_up(want + want / 4, 256);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e != cudaSuccess) { *p = nullptr; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ORBX_E_ALLOC; }
+    *have = bytes;
+    return ORBX_OK;
+}
+template <typename T>
+static int jp_grow_host(T** p, size_t* have_n, size_t want_n)
+{
+    if (*p && *have_n >= want_n) return ORBX_OK;
+    if (*p) { cudaFreeHost(*p); *p = nullptr; *have_n = 0; }
+    const size_t n = want_n + want_n / 4 + 64;
+    cudaError_t e = cudaMallocHost((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) { *p = nullptr; set_error("cudaMallocHost(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return ORBX_E_ALLOC; }
+    *have_n = n;
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_destroy(jpgx_handle h)
+{
+    if (!h) return ORBX_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_stream); cudaFree(h->d_scratch); cudaFree(h->d_intervals); cudaFree(h->d_tables); cudaFree(h->d_file_tables);
+    cudaFree(h->d_coefs); cudaFree(h->d_frames);
+    if (h->h_stream) cudaFreeHost(h->h_stream);
+    if (h->h_intervals) cudaFreeHost(h->h_intervals);
+    if (h->h_tables) cudaFreeHost(h->h_tables);
+    if (h->h_file_tables) cudaFreeHost(h->h_file_tables);
+    if (h->staged) cudaEventDestroy(h->staged);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_create(jpgx_handle* out, int device)
+{
+    ORBX_REQUIRE(out != nullptr, "jpgx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { set_error("jpgx_create: no CUDA device (%s); liborbx has no CPU fallback", cudaGetErrorString(e)); return ORBX_E_CUDA; }
+    ORBX_REQUIRE(device >= 0 && device < ndev, "jpgx_create: device %d out of range [0,%d)", device, ndev);
+    ORBX_CUDA(cudaSetDevice(device));
+    jpgx_context* h = new jpgx_context();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->tables_cap = 16;
+    ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), jpgx_destroy(h));
+    h->stream = h->own_stream;
+    ORBX_CUDA_OR(cudaEventCreateWithFlags(&h->staged, cudaEventDisableTiming), jpgx_destroy(h));
+    ORBX_CUDA_OR(cudaMallocHost((void**)&h->h_tables, sizeof(JpTables) * (size_t)h->tables_cap), jpgx_destroy(h));
+    ORBX_CUDA_OR(cudaMalloc((void**)&h->d_tables, sizeof(JpTables) * (size_t)h->tables_cap), jpgx_destroy(h));
+    *out = h;
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_set_stream(jpgx_handle h, void* cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr, "jpgx_set_stream: NULL handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_get_stream(jpgx_handle h, void** cuda_stream)
+{
+    ORBX_REQUIRE(h != nullptr && cuda_stream != nullptr, "jpgx_get_stream: NULL argument");
+    *cuda_stream = h->stream == h->own_stream ? nullptr : (void*)h->stream;
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_synchronize(jpgx_handle h)
+{
+    ORBX_REQUIRE(h != nullptr, "jpgx_synchronize: NULL handle");
+    ORBX_CUDA(cudaSetDevice(h->device));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_probe(const uint8_t* file, size_t size, int32_t* info)
+{
+    ORBX_REQUIRE(file != nullptr && info != nullptr, "jpgx_probe: NULL argument");
+    HostFile hf;
+    const char* why = "";
+    const int rc = parse_jpeg(file, size, hf, &why);
+    if (rc) { set_error("jpgx_probe: %s", why); return rc; }
+    info[0] = hf.width; info[1] = hf.height; info[2] = hf.restart;
+    info[3] = ((hf.width + 7) / 8) * ((hf.height + 7) / 8);
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh,
+                                          uint8_t* d_frames, size_t frame_pitch, size_t stride)
+{
+    ORBX_REQUIRE(h != nullptr, "jpgx_decode_gray_batch_dev: NULL handle");
+    ORBX_REQUIRE(nfiles >= 0 && w >= 1 && hh >= 1 && w <= 65535 && hh <= 65535, "jpgx_decode_gray_batch_dev: nfiles %d / size %dx%d out of range", nfiles, w, hh);
+    if (nfiles == 0) return ORBX_OK;
+    ORBX_REQUIRE(files && sizes && d_frames, "jpgx_decode_gray_batch_dev: NULL pointer");
+    ORBX_REQUIRE(stride >= (size_t)w && frame_pitch >= stride * (size_t)(hh - 1) + (size_t)w, "jpgx_decode_gray_batch_dev: stride %zu / frame pitch %zu too small for %dx%d", stride, frame_pitch, w, hh);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const int bw = (w + 7) / 8, bh = (hh + 7) / 8;
+    const uint32_t blocks = (uint32_t)bw * (uint32_t)bh;
+    // the previous call's uploads must have left the pinned buffers before they are overwritten
+    if (h->staged_pending) { ORBX_CUDA(cudaEventSynchronize(h->staged)); h->staged_pending = false; }
+
+    // 1. headers
+    std::vector<HostFile> hf((size_t)nfiles);
+    size_t total = 0, nint = 0;
+    for (int i = 0; i < nfiles; i++) {
+        ORBX_REQUIRE(files[i] != nullptr, "jpgx_decode_gray_batch_dev: file %d is NULL", i);
+        const char* why = "";
+        const int rc = parse_jpeg(files[i], sizes[i], hf[(size_t)i], &why);
+        if (rc) { set_error("jpgx_decode_gray_batch_dev: file %d: %s", i, why); return rc; }
+        ORBX_REQUIRE(hf[(size_t)i].width == w && hf[(size_t)i].height == hh, "jpgx_decode_gray_batch_dev: file %d is %dx%d, the batch is %dx%d", i,
+                     hf[(size_t)i].width, hf[(size_t)i].height, w, hh);
+        total += align_up(hf[(size_t)i].scan_len, 4);
+        const uint32_t ri = hf[(size_t)i].restart ? (uint32_t)hf[(size_t)i].restart : blocks;
+        nint += (blocks + ri - 1) / ri;
+    }
+    ORBX_REQUIRE(total < (1ull << 32) - (nint + 1) * 8, "jpgx_decode_gray_batch_dev: %zu bytes of compressed data in one batch", total);
+    int rc = jp_grow_host(&h->h_stream, &h->h_stream_bytes, total + 64);
+    if (!rc) rc = jp_grow_host(&h->h_intervals, &h->h_intervals_n, nint);
+    if (!rc) rc = jp_grow_host(&h->h_file_tables, &h->h_file_tables_n, (size_t)nfiles);
+    if (!rc) rc = jp_grow(&h->d_stream, &h->d_stream_bytes, total + 64);
+    if (!rc) rc = jp_grow(&h->d_scratch, &h->d_scratch_bytes, total + nint * 8 + 64);
+    if (!rc) rc = jp_grow(&h->d_intervals, &h->d_intervals_bytes, nint * sizeof(JpInterval));
+    if (!rc) rc = jp_grow(&h->d_file_tables, &h->d_file_tables_bytes, (size_t)nfiles * sizeof(int32_t));
+    if (!rc) rc = jp_grow(&h->d_coefs, &h->d_coefs_bytes, (size_t)nfiles * blocks * 64 * sizeof(int16_t));
+    if (rc) return rc;
+
+    // 2. the scans, cut at their restart markers; table sets shared by the files that carry the same ones
+    std::vector<JpTables> sets;
+    std::vector<const HostFile*> set_owner;
+    size_t off = 0, ni = 0, scratch = 0;
+    for (int i = 0; i < nfiles; i++) {
+        const HostFile& f = hf[(size_t)i];
+        int set = -1;
+        for (size_t s = 0; s < set_owner.size(); s++) {
+            const HostFile& o = *set_owner[s];
+            if (!memcmp(o.quant, f.quant, sizeof(f.quant)) && !memcmp(o.dc.bits, f.dc.bits, 17) && !memcmp(o.dc.vals, f.dc.vals, 256) &&
+                !memcmp(o.ac.bits, f.ac.bits, 17) && !memcmp(o.ac.vals, f.ac.vals, 256)) { set = (int)s; break; }
+        }
+        if (set < 0) {
+            JpTables t;
+            if (!build_table(f.dc, t.dc) || !build_table(f.ac, t.ac)) { set_error("jpgx_decode_gray_batch_dev: file %d: over-subscribed Huffman table", i); return ORBX_E_INVALID; }
+            memcpy(t.quant, f.quant, sizeof(t.quant));
+            set = (int)sets.size();
+            sets.push_back(t);
+            set_owner.push_back(&f);
+        }
+        h->h_file_tables[i] = set;
+        const uint8_t* scan = files[i] + f.scan;
+        memcpy(h->h_stream + off, scan, f.scan_len);
+        const uint32_t ri = f.restart ? (uint32_t)f.restart : blocks;
+        size_t p = 0;
+        for (uint32_t b0 = 0; b0 < blocks; b0 += ri) {
+            // the interval ends at the next marker: FF followed by anything but 00 (RSTn between intervals, EOI after the last)
+            size_t q = p;
+            for (;;) {
+                const uint8_t* hit = q < f.scan_len ? (const uint8_t*)memchr(scan + q, 0xFF, f.scan_len - q) : nullptr;
+                if (!hit) { q = f.scan_len; break; }
+                q = (size_t)(hit - scan);
+                if (q + 1 >= f.scan_len) { q = f.scan_len; break; }
+                if (scan[q + 1] != 0x00) break;
+                q += 2;
+            }
+            JpInterval& iv = h->h_intervals[ni++];
+            iv.src = (uint32_t)(off + p);
+            iv.src_len = (uint32_t)(q - p);
+            iv.scratch = (uint32_t)scratch;
+            iv.first_block = b0;
+            iv.nblocks = std::min(ri, blocks - b0);
+            iv.file = (uint32_t)i;
+            scratch += align_up((size_t)iv.src_len, 4) + 4;
+            p = q;
+            if (p + 1 < f.scan_len) {              // skip the marker
+                while (p < f.scan_len && scan[p] == 0xFF) p++;
+                if (p < f.scan_len) p++;
+            }
+        }
+        off += align_up(f.scan_len, 4);
+    }
+    if ((int)sets.size() > h->tables_cap) {
+        cudaFreeHost(h->h_tables); h->h_tables = nullptr;
+        cudaFree(h->d_tables); h->d_tables = nullptr;
+        h->tables_cap = (int)sets.size() * 2;
+        ORBX_CUDA(cudaMallocHost((void**)&h->h_tables, sizeof(JpTables) * (size_t)h->tables_cap));
+        ORBX_CUDA(cudaMalloc((void**)&h->d_tables, sizeof(JpTables) * (size_t)h->tables_cap));
+    }
+    memcpy(h->h_tables, sets.data(), sizeof(JpTables) * sets.size());
+
+    // 3. upload, decode
+    ORBX_CUDA(cudaMemcpyAsync(h->d_stream, h->h_stream, off, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_intervals, h->h_intervals, ni * sizeof(JpInterval), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_file_tables, h->h_file_tables, (size_t)nfiles * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_tables, h->h_tables, sizeof(JpTables) * sets.size(), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(cudaEventRecord(h->staged, h->stream));
+    h->staged_pending = true;
+    ORBX_CUDA(cudaMemsetAsync(h->d_coefs, 0, (size_t)nfiles * blocks * 64 * sizeof(int16_t), h->stream));
+    const unsigned hb = (unsigned)((ni + JP_HUFF_THREADS / 32 - 1) / (JP_HUFF_THREADS / 32));
+    k_jpeg_huff<<<hb, JP_HUFF_THREADS, 0, h->stream>>>(h->d_stream, h->d_intervals, (int)ni, h->d_tables, h->d_file_tables, h->d_scratch, h->d_coefs, blocks);
+    ORBX_CUDA(cudaGetLastError());
+    k_jpeg_idct<<<dim3((blocks + JP_IDCT_THREADS - 1) / JP_IDCT_THREADS, (unsigned)nfiles), JP_IDCT_THREADS, 0, h->stream>>>(
+        h->d_coefs, h->d_tables, h->d_file_tables, nfiles, w, hh, bw, blocks, d_frames, frame_pitch, stride);
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_decode_gray_batch(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh, uint8_t* frames,
+                                      size_t frame_pitch, size_t stride)
+{
+    ORBX_REQUIRE(h != nullptr, "jpgx_decode_gray_batch: NULL handle");
+    ORBX_REQUIRE(nfiles >= 0 && w >= 1 && hh >= 1, "jpgx_decode_gray_batch: nfiles %d / size %dx%d out of range", nfiles, w, hh);
+    if (nfiles == 0) return ORBX_OK;
+    ORBX_REQUIRE(frames != nullptr, "jpgx_decode_gray_batch: NULL pointer");
+    ORBX_REQUIRE(stride >= (size_t)w && frame_pitch >= stride * (size_t)(hh - 1) + (size_t)w, "jpgx_decode_gray_batch: stride %zu / frame pitch %zu too small for %dx%d", stride, frame_pitch, w, hh);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t dpitch = align_up((size_t)w, 16), dframe = dpitch * (size_t)hh;
+    int rc = jp_grow(&h->d_frames, &h->d_frames_bytes, dframe * (size_t)nfiles);
+    if (rc) return rc;
+    rc = jpgx_decode_gray_batch_dev(h, files, sizes, nfiles, w, hh, h->d_frames, dframe, dpitch);
+    if (rc) return rc;
+    for (int i = 0; i < nfiles; i++)
+        ORBX_CUDA(cudaMemcpy2DAsync(frames + (size_t)i * frame_pitch, stride, h->d_frames + (size_t)i * dframe, dpitch, (size_t)w, (size_t)hh,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}

@@ -40,6 +40,65 @@ def imread_unchanged(source):
     return img
 
 
+class JpegDecoder:
+    """Grey-scale baseline JPEG files decoded on the GPU (include/orbx.h "jpgx_*"): the pixels cv2.imdecode / the reference's
+    imread would return, for a whole batch at once.  ``decode(files)`` returns host frames; ``decode_dev(files, w, h, d_frames,
+    frame_pitch, stride)`` writes device frames (asynchronous on the handle's stream) for ORB.extract_batch_dev.  A file of
+    another kind raises OrbxError with status E_UNSUPPORTED -- decode that one with ``imread_unchanged``."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self.device = device
+        check(_lib.lib().jpgx_create(C.byref(self._h), device))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().jpgx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(_lib.lib().jpgx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(_lib.lib().jpgx_synchronize(self._h))
+
+    @staticmethod
+    def probe(data):
+        """(width, height, restart interval in blocks, blocks) from the headers; raises OrbxError for files this decoder refuses."""
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(bytes(data))
+        info = (C.c_int32 * 4)()
+        check(_lib.lib().jpgx_probe(buf, len(data), info))
+        return tuple(info)
+
+    @staticmethod
+    def _args(files):
+        keep = [np.frombuffer(bytes(f), np.uint8) if not isinstance(f, np.ndarray) else np.ascontiguousarray(f, np.uint8).reshape(-1) for f in files]
+        ptrs = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+        sizes = (C.c_size_t * len(keep))(*[k.size for k in keep])
+        return keep, ptrs, sizes
+
+    def decode_dev(self, files, w, h, d_frames_ptr, frame_pitch, stride):
+        keep, ptrs, sizes = self._args(files)
+        check(_lib.lib().jpgx_decode_gray_batch_dev(self._h, ptrs, sizes, len(keep), int(w), int(h), d_frames_ptr, int(frame_pitch), int(stride)))
+
+    def decode(self, files, out=None):
+        files = list(files)
+        if not files:
+            return np.zeros((0, 0, 0), np.uint8)
+        w, h, _, _ = self.probe(files[0])
+        if out is None:
+            out = np.zeros((len(files), h, w), np.uint8)
+        keep, ptrs, sizes = self._args(files)
+        check(_lib.lib().jpgx_decode_gray_batch(self._h, ptrs, sizes, len(keep), w, h, out.ctypes.data_as(C.c_void_p), h * w, w))
+        return out
+
+
 class IngestRing:
     """Decode -> pinned slot -> ``orb.submit_batch``.  ``channels`` = 1 (gray files) or 3 (BGR files, converted on the device).
 

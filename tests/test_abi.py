@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _header_symbols():
     src = open(os.path.join(ROOT, "include", "orbx.h")).read()
-    return re.findall(r"ORBX_API\s+[\w\s\*]+?\b((?:orbx|hamx|fmx|trx|bowx)_\w+)\s*\(", src)
+    return re.findall(r"ORBX_API\s+[\w\s\*]+?\b((?:orbx|hamx|fmx|trx|bowx|jpgx)_\w+)\s*\(", src)
 
 
 def test_library_builds_and_exports_header():

@@ -1,0 +1,98 @@
+"""GPU parity of the grey-scale JPEG decoder (csrc/jpeg.cu through the C ABI, `jpgx_*`): every committed file of
+tests/golden/jpeg_cases.npz must decode to the pixels cv2.imdecode returned for it (tests/golden/make_golden_jpeg.py), larger
+seeded frames to the oracle's pixels, and files of another kind must be refused."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from monocular_slam_b200 import ORB, JpegDecoder, OrbxError, _lib
+from monocular_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg_cases.npz"))
+
+
+def test_golden_files_decode_to_cv2s_pixels():
+    dec = JpegDecoder()
+    by_shape = {}
+    for k in G["names"]:
+        by_shape.setdefault(G[k + "_pixels"].shape, []).append(k)
+    assert len(by_shape) == 6
+    for shape, keys in by_shape.items():
+        files = [G[k + "_file"].tobytes() for k in keys]
+        got = dec.decode(files)                        # one batch per image size: 5 files with different tables / restart intervals
+        for i, k in enumerate(keys):
+            assert np.array_equal(got[i], G[k + "_pixels"]), k
+        for f, k in zip(files, keys):                  # and one at a time
+            assert np.array_equal(dec.decode([f])[0], G[k + "_pixels"]), k
+    dec.close()
+
+
+def test_unsupported_and_damaged_files_are_refused():
+    dec = JpegDecoder()
+    for k in ("refuse_progressive_file", "refuse_colour_file"):
+        with pytest.raises(OrbxError) as e:
+            dec.decode([G[k].tobytes()])
+        assert e.value.status == _lib.E_UNSUPPORTED
+    with pytest.raises(OrbxError) as e:
+        dec.probe(b"\\x89PNG\\r\\n\\x1a\\n" + bytes(64))
+    assert e.value.status == _lib.E_INVALID
+    good = G["tex333_q90_file"].tobytes()
+    with pytest.raises(OrbxError):
+        dec.decode([good, G["noise64_q90_file"].tobytes()])       # two sizes in one batch
+    # a file cut in the middle of its scan: zero bits past the end, as libjpeg pads -- the rows before the cut are intact
+    ref = G["tex333_q90_pixels"]
+    cut = dec.decode([good[:len(good) // 2]])[0]
+    assert np.array_equal(cut[:64], ref[:64]) and np.array_equal(cut, oracle.jpeg_decode_gray(good[:len(good) // 2]))
+    dec.close()
+
+
+@pytest.mark.parametrize("w,h,rst,quality", [(640, 480, 80, 90), (1920, 1080, 240, 90), (1920, 1080, 0, 75), (1001, 701, 7, 97)])
+def test_larger_frames_match_the_oracle_and_feed_the_extractor(w, h, rst, quality):
+    cv2 = pytest.importorskip("cv2")
+    frames = [syn.frame(40 + i, w, h) if i % 2 else syn.natural_frame(40 + i, w, h) for i in range(3)]
+    params = [cv2.IMWRITE_JPEG_QUALITY, quality] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else [])
+    files = [cv2.imencode(".jpg", f, params)[1].tobytes() for f in frames]
+    dec = JpegDecoder()
+    assert dec.probe(files[0])[:3] == (w, h, rst)
+    got = dec.decode(files)
+    for i, f in enumerate(files):
+        assert np.array_equal(got[i], oracle.jpeg_decode_gray(f)), i
+        assert np.array_equal(got[i], cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED)), i
+    dec.close()
+
+
+def test_device_frames_go_straight_into_extraction():
+    """jpgx_decode_gray_batch_dev -> orbx_extract_batch_dev on one stream: the keypoints of the decoded frames."""
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    B, W, H = 3, 640, 480
+    seq = syn.sequence(B, W, H, seed=6)
+    files = [cv2.imencode(".jpg", seq[i], [cv2.IMWRITE_JPEG_QUALITY, 92, cv2.IMWRITE_JPEG_RST_INTERVAL, 80])[1].tobytes() for i in range(B)]
+    decoded = np.stack([cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED) for f in files])
+    orb = ORB(nfeatures=500, max_size=(W, H), max_batch=B)
+    dec = JpegDecoder()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        orb.set_stream(stream.cuda_stream)
+        dec.set_stream(stream.cuda_stream)
+        cap = orb.default_cap
+        d_frames = torch.zeros((B, H, W), dtype=torch.uint8, device="cuda")
+        d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device="cuda")
+        d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+        for _ in range(2):
+            dec.decode_dev(files, W, H, d_frames.data_ptr(), W * H, W)
+            orb.extract_batch_dev(d_frames.data_ptr(), W * H, B, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
+        orb.check_dev()
+        stream.synchronize()
+    assert np.array_equal(d_frames.cpu().numpy(), decoded)
+    kps, desc, counts = orb.extract_batch(list(decoded))
+    cnt = d_cnt.cpu().numpy()
+    assert np.array_equal(cnt, counts)
+    for f in range(B):
+        assert np.array_equal(d_desc[f, :cnt[f]].cpu().numpy(), desc[f, :cnt[f]])
+    dec.close(); orb.close()

@@ -1104,9 +1104,50 @@ def run_ours(args, rank, world, local_rank):
                                "decode_fps_per_worker_in_ring": st["frames"] / max(st["decode_seconds"], 1e-9),
                                "keypoints_per_frame": kp_total / max(st["frames"], 1),
                                "cores_for_gpu_bound_rate": e2e_value / per_core}
+            # the same JPEG frames with the entropy decoder on the GPU (jpgx_*): files in host memory -> compressed bytes over PCIe
+            # -> restart-interval parallel Huffman + IDCT -> the extractor's device frames -> extraction + matching -> results in
+            # pinned host memory.  `rows`: one restart marker per block row (what a recorder under our control writes);
+            # `none`: no restart markers (one warp per file: only large batches pay)
+            from monocular_slam_b200 import JpegDecoder
+            jdec = JpegDecoder(device=local_rank)
+            jstream = torch.cuda.Stream(device=dev)       # the decoder's own stream: batch k+1 is decoded while batch k is extracted
+            jdec.set_stream(jstream.cuda_stream)
+            jbuf = [torch.zeros((B, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
+            ev_dec = [torch.cuda.Event() for _ in range(2)]
+            ev_ext = [torch.cuda.Event() for _ in range(2)]
+            h_kps = torch.empty((B, cap, 7), dtype=torch.float32).pin_memory(); h_desc = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
+            h_good = torch.empty((B, cap, 4), dtype=torch.int32).pin_memory(); h_cnt = torch.empty(B, dtype=torch.int32).pin_memory()
+            ingest["jpeg_gpu"] = {}
+            jstate = {"k": 0}
+            for label, rst in (("rows", (W + 7) // 8), ("none", 0)):
+                enc = [cv2.imencode(".jpg", seq[i], [cv2.IMWRITE_JPEG_QUALITY, 90] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else []))[1].tobytes()
+                       for i in range(B)]
+
+                def step_jpeg():
+                    b = jstate["k"] & 1
+                    jstate["k"] += 1
+                    jstream.wait_event(ev_ext[b])                       # the extraction that read this buffer two steps ago
+                    jdec.decode_dev(enc, W, H, jbuf[b].data_ptr(), W * H, W)
+                    ev_dec[b].record(jstream)
+                    stream.wait_event(ev_dec[b])
+                    orb.extract_batch_dev(jbuf[b].data_ptr(), W * H, B, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
+                    ev_ext[b].record(stream)
+                    matcher.match_consecutive_dev(d_desc.data_ptr(), d_cnt.data_ptr(), B, cap, 0, 0, RATIO, d_good.data_ptr(), d_ngood.data_ptr())
+                    h_kps.copy_(d_kps, non_blocking=True); h_desc.copy_(d_desc, non_blocking=True)
+                    h_good.copy_(d_good, non_blocking=True); h_cnt.copy_(d_cnt, non_blocking=True)
+                jreps = 8 if rst else 2
+                _, jwall = timed(step_jpeg, jreps, 2)
+                orb.check_dev()
+                ref0 = cv2.imdecode(np.frombuffer(enc[0], np.uint8), cv2.IMREAD_UNCHANGED)
+                assert np.array_equal(jbuf[(jstate["k"] - 1) & 1][0].cpu().numpy(), ref0), "GPU-decoded frame differs from cv2.imdecode"
+                ingest["jpeg_gpu"][label] = {"fps": B * jreps / (jwall * 1e-3), "bytes_per_frame": int(np.mean([len(e) for e in enc])),
+                                             "restart_interval_blocks": rst, "keypoints_per_frame": float(h_cnt.numpy().mean())}
+            jdec.close()
             e2e_extra = {"ingest_png_fps": ingest["png"]["ring_fps"], "ingest_jpeg_fps": ingest["jpeg"]["ring_fps"],
                          "ingest_png_decode_fps_per_core": ingest["png"]["decode_fps_per_core"],
-                         "ingest_jpeg_decode_fps_per_core": ingest["jpeg"]["decode_fps_per_core"]}
+                         "ingest_jpeg_decode_fps_per_core": ingest["jpeg"]["decode_fps_per_core"],
+                         "ingest_jpeg_gpu_decode_fps": ingest["jpeg_gpu"]["rows"]["fps"],
+                         "ingest_jpeg_gpu_decode_no_restart_fps": ingest["jpeg_gpu"]["none"]["fps"]}
         except Exception as e:
             ingest = {"failed": repr(e)}
 

@@ -10,5 +10,5 @@ for f in hamming fmat triangulate bow jpeg orb_pyramid orb_fast orb_select orb_d
     $NVCC $FLAGS -c $f.cu -o $f.o
     OBJS="$OBJS $f.o"
 done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $OBJS -cudart static
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $OBJS -cudart static -lpthread
 echo "built $OUT"

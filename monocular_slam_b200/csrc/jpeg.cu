@@ -5,9 +5,10 @@
 //
 //   host      marker parsing (ITU-T T.81 Annex B): DQT, SOF0/1, DHT, DRI, SOS of a one-component 8-bit Huffman file; the
 //             entropy-coded segment is cut at its restart markers into intervals (T.81 E.2.4) -- the unit of parallelism
-//   K17 k_jpeg_huff   one warp per restart interval: all lanes strip the stuffed zero bytes (FF 00 -> FF) into a scratch
-//             copy, then lane 0 runs the sequential Huffman decoder of T.81 F.2.2 over it (10-bit lookahead tables, the DC
-//             predictor restarting with the interval) and scatters the non-zero coefficients of each 8x8 block
+//   K17 k_jpeg_unstuff, k_jpeg_huff   a warp per restart interval strips the stuffed zero bytes (FF 00 -> FF) into a scratch
+//             copy; then one LANE per interval runs the sequential Huffman decoder of T.81 F.2.2 over it (10-bit lookahead
+//             tables, the DC predictor restarting with the interval), one symbol per loop iteration so that the 32 intervals
+//             of a warp stay in step, and scatters the non-zero coefficients of each 8x8 block
 //   K18 k_jpeg_idct   one thread per block: dequantisation and libjpeg's jpeg_idct_islow (jidctint.c: 13-bit constants, two
 //             passes, DESCALE) in registers, the range-limit table of jdmaster.c as arithmetic, 8-byte row stores that
 //             coalesce across the blocks of a block row
@@ -18,6 +19,10 @@
 // decoder for those.
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -26,7 +31,7 @@ namespace orbx {
 namespace {
 
 constexpr int JP_LOOK = 10;                       // lookahead bits of the Huffman tables
-constexpr int JP_HUFF_THREADS = 128;              // 4 intervals per CTA
+constexpr int JP_HUFF_THREADS = 128;
 constexpr int JP_IDCT_THREADS = 128;
 
 struct JpHuff {                                   // one Huffman table on the device
@@ -57,7 +62,7 @@ struct JpBits {
     __device__ __forceinline__ void fill()
     {
         if (nbits <= 32) {
-            const uint32_t w = wi < nwords ? words[wi] : 0u;          // written by this warp a moment ago: a plain load
+            const uint32_t w = wi < nwords ? words[wi] : 0u;
             wi++;
             buf |= (unsigned long long)__byte_perm(w, 0, 0x0123) << (32 - nbits);
             nbits += 32;
@@ -83,16 +88,15 @@ __device__ __forceinline__ int jp_decode(JpBits& b, const JpHuff* __restrict__ t
 }
 __device__ __forceinline__ int jp_extend(int x, int s) { return x < (1 << (s - 1)) ? x - (1 << s) + 1 : x; }
 
-// ---- K17
+// ---- K17a: one warp per interval copies it without the zero byte that follows every FF (T.81 B.1.1.5), pads the last word
 __global__ void __launch_bounds__(JP_HUFF_THREADS)
-k_jpeg_huff(const uint8_t* __restrict__ stream, const JpInterval* __restrict__ intervals, int nintervals, const JpTables* __restrict__ tables,
-            const int32_t* __restrict__ file_tables, uint8_t* __restrict__ scratch, int16_t* __restrict__ coefs, uint32_t blocks_per_file)
+k_jpeg_unstuff(const uint8_t* __restrict__ stream, const JpInterval* __restrict__ intervals, int nintervals, uint8_t* __restrict__ scratch,
+               uint32_t* __restrict__ nwords_out)
 {
     const int lane = threadIdx.x & 31;
     const int it = blockIdx.x * (JP_HUFF_THREADS / 32) + (threadIdx.x >> 5);
     if (it >= nintervals) return;
     const JpInterval iv = intervals[it];
-    // phase 1, all lanes: copy the interval without the zero byte that follows every FF
     uint8_t* dst = scratch + iv.scratch;
     uint32_t out = 0;
     uint32_t prev_ff = 0;                         // was the last byte of the previous round FF?
@@ -106,38 +110,51 @@ k_jpeg_huff(const uint8_t* __restrict__ stream, const JpInterval* __restrict__ i
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) dst[out + __popc(bal & ((1u << lane) - 1))] = (uint8_t)byte;
         out += __popc(bal);
-        // (FF 00 FF 00: the second FF is data, its predecessor 00 was dropped -- `before` looks at the raw stream, which is right:
-        // a stuffed 00 is never itself followed by a meaningful 00)
         prev_ff = __shfl_sync(0xffffffffu, byte, 31) == 0xFF && (i0 + 31 < iv.src_len);
     }
     const uint32_t nwords = (out + 3) / 4;
-    if (lane < 4 && out + lane < nwords * 4) dst[out + lane] = 0;      // pad the last word
-    __syncwarp();
-    if (lane != 0) return;
-    // phase 2, lane 0: T.81 F.2.2 over the stripped bytes
+    if (lane < 4 && out + lane < nwords * 4) dst[out + lane] = 0;
+    if (lane == 0) nwords_out[it] = nwords;
+}
+
+// ---- K17b: one lane per interval runs the sequential decoder of T.81 F.2.2 over its stripped bytes.  The loop body decodes
+// one symbol -- a DC difference when the lane is at the start of a block, else an AC run/size -- so the 32 intervals of a
+// warp execute the same instructions whatever their data; only the rare codes longer than JP_LOOK bits diverge.
+__global__ void __launch_bounds__(JP_HUFF_THREADS)
+k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables,
+            const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, int16_t* __restrict__ coefs, uint32_t blocks_per_file,
+            int lane_step)
+{
+    // every lane_step-th lane of a warp owns an interval: with few intervals (a row of blocks each, or whole files) spreading them
+    // over more warps costs issue slots but shortens every warp's memory gathers; with many, all 32 lanes work
+    const long long t = (long long)blockIdx.x * JP_HUFF_THREADS + threadIdx.x;
+    if (t % lane_step) return;
+    const long long it = t / lane_step;
+    if (it >= nintervals) return;
+    const JpInterval iv = intervals[it];
     const JpTables* tb = tables + file_tables[iv.file];
-    JpBits b = {reinterpret_cast<const uint32_t*>(dst), nwords, 0, 0ull, 0};
+    JpBits b = {reinterpret_cast<const uint32_t*>(scratch + iv.scratch), nwords_in[it], 0, 0ull, 0};
     int16_t* co = coefs + ((size_t)iv.file * blocks_per_file + iv.first_block) * 64;
-    int dc = 0;
-    for (uint32_t blk = 0; blk < iv.nblocks; blk++, co += 64) {
-        int s = jp_decode(b, &tb->dc) & 15;
-        if (s) { b.fill(); s = jp_extend(b.get(s), s); }
-        dc += s;
-        if (dc) co[0] = (int16_t)dc;
-        for (int k = 1; k < 64; k++) {
-            const int rs = jp_decode(b, &tb->ac);
-            const int r = rs >> 4, sz = rs & 15;
-            if (sz) {
-                k += r;
-                b.fill();
-                const int v = b.get(sz);
-                if (k > 63) break;                // corrupt data
-                co[c_natural_order[k]] = (int16_t)jp_extend(v, sz);
-            } else {
-                if (r != 15) break;               // end of block
-                k += 15;
-            }
+    int dc = 0, k = 0;
+    uint32_t blk = 0;
+    while (blk < iv.nblocks) {
+        const bool is_dc = k == 0;
+        const int sym = jp_decode(b, is_dc ? &tb->dc : &tb->ac);
+        const int r = is_dc ? 0 : sym >> 4, sz = sym & 15;
+        int val = 0;
+        if (sz) { b.fill(); val = jp_extend(b.get(sz), sz); }
+        if (is_dc) {
+            dc += val;
+            if (dc) co[0] = (int16_t)dc;
+            k = 1;
+        } else if (sz) {
+            k += r;
+            if (k <= 63) co[c_natural_order[k]] = (int16_t)val;
+            k = k > 63 ? 64 : k + 1;              // (k > 63: corrupt data ends the block, as the reference's loop does)
+        } else {
+            k = r == 15 ? k + 16 : 64;            // ZRL, or end of block
         }
+        if (k >= 64) { k = 0; blk++; co += 64; }
     }
 }
 
@@ -358,19 +375,27 @@ static int parse_jpeg(const uint8_t* f, size_t n, HostFile& out, const char** wh
 
 using namespace orbx;
 
-struct jpgx_context {
-    int device;
-    cudaStream_t own_stream, stream;
-    cudaEvent_t staged;                           // the last call's uploads have left the pinned staging buffers
-    bool staged_pending;
-    uint8_t* h_stream; size_t h_stream_bytes;     // pinned: the entropy-coded segments of a batch, one after the other
+struct JpSet {                                    // what one call uploads: pinned staging + its device copy
+    uint8_t* h_stream; size_t h_stream_bytes;     // the entropy-coded segments of a batch, one after the other
     uint8_t* d_stream; size_t d_stream_bytes;
-    uint8_t* d_scratch; size_t d_scratch_bytes;   // the same without stuffed bytes
     JpInterval* h_intervals; size_t h_intervals_n;
     JpInterval* d_intervals; size_t d_intervals_bytes;
     JpTables* h_tables; JpTables* d_tables; int tables_cap;
     int32_t* h_file_tables; size_t h_file_tables_n;
     int32_t* d_file_tables; size_t d_file_tables_bytes;
+    cudaEvent_t uploaded;                         // on the copy stream: the uploads have left the pinned buffers
+    cudaEvent_t decoded;                          // on the caller's stream: the kernels that read the device copy are done
+    bool uploaded_pending, decoded_pending;
+};
+
+struct jpgx_context {
+    int device;
+    cudaStream_t own_stream, stream;
+    cudaStream_t copy_stream;                     // uploads of call k+1 run beside the kernels of call k
+    JpSet set[2];                                 // the buffers of two calls in flight, used in turn
+    int next_set;
+    uint8_t* d_scratch; size_t d_scratch_bytes;   // the same without stuffed bytes
+    uint32_t* d_nwords; size_t d_nwords_bytes;    // 32-bit words of every interval's stripped copy
     int16_t* d_coefs; size_t d_coefs_bytes;
     uint8_t* d_frames; size_t d_frames_bytes;     // staging of the host-output form
 };
@@ -386,13 +411,15 @@ static int jp_grow(T** p, size_t* have, size_t want)
     *have = bytes;
     return ORBX_OK;
 }
+// write_combined: for buffers the CPU only ever writes front to back (the DMA engine then reads memory that is not sitting
+// dirty in a cache: measured 19 MB in 0.35 ms instead of 1.1 ms)
 template <typename T>
-static int jp_grow_host(T** p, size_t* have_n, size_t want_n)
+static int jp_grow_host(T** p, size_t* have_n, size_t want_n, bool write_combined = false)
 {
     if (*p && *have_n >= want_n) return ORBX_OK;
     if (*p) { cudaFreeHost(*p); *p = nullptr; *have_n = 0; }
     const size_t n = want_n + want_n / 4 + 64;
-    cudaError_t e = cudaMallocHost((void**)p, n * sizeof(T));
+    cudaError_t e = cudaHostAlloc((void**)p, n * sizeof(T), write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
     if (e != cudaSuccess) { *p = nullptr; set_error("cudaMallocHost(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return ORBX_E_ALLOC; }
     *have_n = n;
     return ORBX_OK;
@@ -403,13 +430,19 @@ extern "C" int jpgx_destroy(jpgx_handle h)
     if (!h) return ORBX_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_stream); cudaFree(h->d_scratch); cudaFree(h->d_intervals); cudaFree(h->d_tables); cudaFree(h->d_file_tables);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    for (JpSet& S : h->set) {
+        cudaFree(S.d_stream); cudaFree(S.d_intervals); cudaFree(S.d_tables); cudaFree(S.d_file_tables);
+        if (S.h_stream) cudaFreeHost(S.h_stream);
+        if (S.h_intervals) cudaFreeHost(S.h_intervals);
+        if (S.h_tables) cudaFreeHost(S.h_tables);
+        if (S.h_file_tables) cudaFreeHost(S.h_file_tables);
+        if (S.uploaded) cudaEventDestroy(S.uploaded);
+        if (S.decoded) cudaEventDestroy(S.decoded);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    cudaFree(h->d_scratch); cudaFree(h->d_nwords);
     cudaFree(h->d_coefs); cudaFree(h->d_frames);
-    if (h->h_stream) cudaFreeHost(h->h_stream);
-    if (h->h_intervals) cudaFreeHost(h->h_intervals);
-    if (h->h_tables) cudaFreeHost(h->h_tables);
-    if (h->h_file_tables) cudaFreeHost(h->h_file_tables);
-    if (h->staged) cudaEventDestroy(h->staged);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ORBX_OK;
@@ -427,12 +460,16 @@ extern "C" int jpgx_create(jpgx_handle* out, int device)
     jpgx_context* h = new jpgx_context();
     memset(h, 0, sizeof(*h));
     h->device = device;
-    h->tables_cap = 16;
     ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), jpgx_destroy(h));
     h->stream = h->own_stream;
-    ORBX_CUDA_OR(cudaEventCreateWithFlags(&h->staged, cudaEventDisableTiming), jpgx_destroy(h));
-    ORBX_CUDA_OR(cudaMallocHost((void**)&h->h_tables, sizeof(JpTables) * (size_t)h->tables_cap), jpgx_destroy(h));
-    ORBX_CUDA_OR(cudaMalloc((void**)&h->d_tables, sizeof(JpTables) * (size_t)h->tables_cap), jpgx_destroy(h));
+    ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), jpgx_destroy(h));
+    for (JpSet& S : h->set) {
+        S.tables_cap = 16;
+        ORBX_CUDA_OR(cudaEventCreateWithFlags(&S.uploaded, cudaEventDisableTiming), jpgx_destroy(h));
+        ORBX_CUDA_OR(cudaEventCreateWithFlags(&S.decoded, cudaEventDisableTiming), jpgx_destroy(h));
+        ORBX_CUDA_OR(cudaMallocHost((void**)&S.h_tables, sizeof(JpTables) * (size_t)S.tables_cap), jpgx_destroy(h));
+        ORBX_CUDA_OR(cudaMalloc((void**)&S.d_tables, sizeof(JpTables) * (size_t)S.tables_cap), jpgx_destroy(h));
+    }
     *out = h;
     return ORBX_OK;
 }
@@ -482,12 +519,35 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
     ORBX_CUDA(cudaSetDevice(h->device));
     const int bw = (w + 7) / 8, bh = (hh + 7) / 8;
     const uint32_t blocks = (uint32_t)bw * (uint32_t)bh;
-    // the previous call's uploads must have left the pinned buffers before they are overwritten
-    if (h->staged_pending) { ORBX_CUDA(cudaEventSynchronize(h->staged)); h->staged_pending = false; }
+#ifdef JP_TRACE
+    auto t_0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { auto n = std::chrono::steady_clock::now(); fprintf(stderr, "  jpgx %-10s %.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t_0).count()); t_0 = n; };
+#else
+    auto lap = [](const char*) {};
+#endif
+    // this call's buffer set was last used two calls ago: its uploads must have left the pinned buffers before they are
+    // overwritten (the device copy is protected in stream order, below)
+    JpSet& S = h->set[h->next_set];
+    h->next_set ^= 1;
+    if (S.uploaded_pending) { ORBX_CUDA(cudaEventSynchronize(S.uploaded)); S.uploaded_pending = false; }
 
-    // 1. headers
+    lap("wait");
+#ifdef JP_TRACE
+    static cudaEvent_t ev[6];
+    static bool ev_init = false, ev_have = false;
+    if (!ev_init) { for (int i = 0; i < 6; i++) cudaEventCreate(&ev[i]); ev_init = true; }
+    if (ev_have) {
+        cudaEventSynchronize(ev[5]);
+        const char* names[5] = {"h2d", "memset", "unstuff", "huff", "idct"};
+        for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, "  jpgx dev %-8s %.3f ms\n", names[i], ms); }
+    }
+#define JP_EV(i) cudaEventRecord(ev[i], h->stream)
+#else
+#define JP_EV(i) do { } while (0)
+#endif
+    // 1. headers: where every file's bytes, intervals and stripped copy go follows from them alone
     std::vector<HostFile> hf((size_t)nfiles);
-    size_t total = 0, nint = 0;
+    std::vector<size_t> off((size_t)nfiles + 1, 0), first_iv((size_t)nfiles + 1, 0), scr((size_t)nfiles + 1, 0);
     for (int i = 0; i < nfiles; i++) {
         ORBX_REQUIRE(files[i] != nullptr, "jpgx_decode_gray_batch_dev: file %d is NULL", i);
         const char* why = "";
@@ -495,25 +555,29 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         if (rc) { set_error("jpgx_decode_gray_batch_dev: file %d: %s", i, why); return rc; }
         ORBX_REQUIRE(hf[(size_t)i].width == w && hf[(size_t)i].height == hh, "jpgx_decode_gray_batch_dev: file %d is %dx%d, the batch is %dx%d", i,
                      hf[(size_t)i].width, hf[(size_t)i].height, w, hh);
-        total += align_up(hf[(size_t)i].scan_len, 4);
         const uint32_t ri = hf[(size_t)i].restart ? (uint32_t)hf[(size_t)i].restart : blocks;
-        nint += (blocks + ri - 1) / ri;
+        const size_t niv = (blocks + ri - 1) / ri;
+        off[(size_t)i + 1] = off[(size_t)i] + align_up(hf[(size_t)i].scan_len, 4);
+        first_iv[(size_t)i + 1] = first_iv[(size_t)i] + niv;
+        scr[(size_t)i + 1] = scr[(size_t)i] + align_up(hf[(size_t)i].scan_len, 4) + 12 * niv + 16;      // interval j at align4(its start) + 12 j
     }
-    ORBX_REQUIRE(total < (1ull << 32) - (nint + 1) * 8, "jpgx_decode_gray_batch_dev: %zu bytes of compressed data in one batch", total);
-    int rc = jp_grow_host(&h->h_stream, &h->h_stream_bytes, total + 64);
-    if (!rc) rc = jp_grow_host(&h->h_intervals, &h->h_intervals_n, nint);
-    if (!rc) rc = jp_grow_host(&h->h_file_tables, &h->h_file_tables_n, (size_t)nfiles);
-    if (!rc) rc = jp_grow(&h->d_stream, &h->d_stream_bytes, total + 64);
-    if (!rc) rc = jp_grow(&h->d_scratch, &h->d_scratch_bytes, total + nint * 8 + 64);
-    if (!rc) rc = jp_grow(&h->d_intervals, &h->d_intervals_bytes, nint * sizeof(JpInterval));
-    if (!rc) rc = jp_grow(&h->d_file_tables, &h->d_file_tables_bytes, (size_t)nfiles * sizeof(int32_t));
+    const size_t total = off[(size_t)nfiles], nint = first_iv[(size_t)nfiles];
+    ORBX_REQUIRE(scr[(size_t)nfiles] < (1ull << 32), "jpgx_decode_gray_batch_dev: %zu bytes of compressed data in one batch", total);
+    int rc = jp_grow_host(&S.h_stream, &S.h_stream_bytes, total + 64, true);
+    if (!rc) rc = jp_grow_host(&S.h_intervals, &S.h_intervals_n, nint);
+    if (!rc) rc = jp_grow_host(&S.h_file_tables, &S.h_file_tables_n, (size_t)nfiles);
+    if (!rc) rc = jp_grow(&S.d_stream, &S.d_stream_bytes, total + 64);
+    if (!rc) rc = jp_grow(&h->d_scratch, &h->d_scratch_bytes, scr[(size_t)nfiles] + 64);
+    if (!rc) rc = jp_grow(&S.d_intervals, &S.d_intervals_bytes, nint * sizeof(JpInterval));
+    if (!rc) rc = jp_grow(&h->d_nwords, &h->d_nwords_bytes, nint * sizeof(uint32_t));
+    if (!rc) rc = jp_grow(&S.d_file_tables, &S.d_file_tables_bytes, (size_t)nfiles * sizeof(int32_t));
     if (!rc) rc = jp_grow(&h->d_coefs, &h->d_coefs_bytes, (size_t)nfiles * blocks * 64 * sizeof(int16_t));
     if (rc) return rc;
 
-    // 2. the scans, cut at their restart markers; table sets shared by the files that carry the same ones
+    lap("headers");
+    // 2a. table sets, shared by the files that carry the same ones
     std::vector<JpTables> sets;
     std::vector<const HostFile*> set_owner;
-    size_t off = 0, ni = 0, scratch = 0;
     for (int i = 0; i < nfiles; i++) {
         const HostFile& f = hf[(size_t)i];
         int set = -1;
@@ -530,12 +594,18 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
             sets.push_back(t);
             set_owner.push_back(&f);
         }
-        h->h_file_tables[i] = set;
+        S.h_file_tables[i] = set;
+    }
+    lap("tables");
+    // 2b. per file, independent of the others (host threads when there is enough to copy): its scan into the pinned stream,
+    // cut at its restart markers
+    auto stage_file = [&](int i) {
+        const HostFile& f = hf[(size_t)i];
         const uint8_t* scan = files[i] + f.scan;
-        memcpy(h->h_stream + off, scan, f.scan_len);
+        memcpy(S.h_stream + off[(size_t)i], scan, f.scan_len);
         const uint32_t ri = f.restart ? (uint32_t)f.restart : blocks;
-        size_t p = 0;
-        for (uint32_t b0 = 0; b0 < blocks; b0 += ri) {
+        size_t p = 0, j = 0;
+        for (uint32_t b0 = 0; b0 < blocks; b0 += ri, j++) {
             // the interval ends at the next marker: FF followed by anything but 00 (RSTn between intervals, EOI after the last)
             size_t q = p;
             for (;;) {
@@ -546,45 +616,77 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
                 if (scan[q + 1] != 0x00) break;
                 q += 2;
             }
-            JpInterval& iv = h->h_intervals[ni++];
-            iv.src = (uint32_t)(off + p);
+            JpInterval& iv = S.h_intervals[first_iv[(size_t)i] + j];
+            iv.src = (uint32_t)(off[(size_t)i] + p);
             iv.src_len = (uint32_t)(q - p);
-            iv.scratch = (uint32_t)scratch;
+            iv.scratch = (uint32_t)(scr[(size_t)i] + align_up(p, 4) + 12 * j);
             iv.first_block = b0;
             iv.nblocks = std::min(ri, blocks - b0);
             iv.file = (uint32_t)i;
-            scratch += align_up((size_t)iv.src_len, 4) + 4;
             p = q;
             if (p + 1 < f.scan_len) {              // skip the marker
                 while (p < f.scan_len && scan[p] == 0xFF) p++;
                 if (p < f.scan_len) p++;
             }
         }
-        off += align_up(f.scan_len, 4);
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int nthreads = total < (2u << 20) ? 1 : (int)std::min<unsigned>(std::min<unsigned>(hw, 8u), (unsigned)nfiles);
+    if (nthreads <= 1) {
+        for (int i = 0; i < nfiles; i++) stage_file(i);
+    } else {
+        std::atomic<int> next(0);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++)
+            pool.emplace_back([&] { for (int i = next.fetch_add(1); i < nfiles; i = next.fetch_add(1)) stage_file(i); });
+        for (std::thread& t : pool) t.join();
     }
-    if ((int)sets.size() > h->tables_cap) {
-        cudaFreeHost(h->h_tables); h->h_tables = nullptr;
-        cudaFree(h->d_tables); h->d_tables = nullptr;
-        h->tables_cap = (int)sets.size() * 2;
-        ORBX_CUDA(cudaMallocHost((void**)&h->h_tables, sizeof(JpTables) * (size_t)h->tables_cap));
-        ORBX_CUDA(cudaMalloc((void**)&h->d_tables, sizeof(JpTables) * (size_t)h->tables_cap));
+    const size_t ni = nint;
+    lap("stage");
+    if ((int)sets.size() > S.tables_cap) {
+        cudaFreeHost(S.h_tables); S.h_tables = nullptr;
+        cudaFree(S.d_tables); S.d_tables = nullptr;
+        S.tables_cap = (int)sets.size() * 2;
+        ORBX_CUDA(cudaMallocHost((void**)&S.h_tables, sizeof(JpTables) * (size_t)S.tables_cap));
+        ORBX_CUDA(cudaMalloc((void**)&S.d_tables, sizeof(JpTables) * (size_t)S.tables_cap));
     }
-    memcpy(h->h_tables, sets.data(), sizeof(JpTables) * sets.size());
+    memcpy(S.h_tables, sets.data(), sizeof(JpTables) * sets.size());
 
     // 3. upload, decode
-    ORBX_CUDA(cudaMemcpyAsync(h->d_stream, h->h_stream, off, cudaMemcpyHostToDevice, h->stream));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_intervals, h->h_intervals, ni * sizeof(JpInterval), cudaMemcpyHostToDevice, h->stream));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_file_tables, h->h_file_tables, (size_t)nfiles * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_tables, h->h_tables, sizeof(JpTables) * sets.size(), cudaMemcpyHostToDevice, h->stream));
-    ORBX_CUDA(cudaEventRecord(h->staged, h->stream));
-    h->staged_pending = true;
+    JP_EV(0);
+    // uploads on the copy stream, behind the kernels that last read this set's device copy; the caller's stream waits for them
+    if (S.decoded_pending) ORBX_CUDA(cudaStreamWaitEvent(h->copy_stream, S.decoded, 0));
+    ORBX_CUDA(cudaMemcpyAsync(S.d_stream, S.h_stream, total, cudaMemcpyHostToDevice, h->copy_stream));
+    ORBX_CUDA(cudaMemcpyAsync(S.d_intervals, S.h_intervals, ni * sizeof(JpInterval), cudaMemcpyHostToDevice, h->copy_stream));
+    ORBX_CUDA(cudaMemcpyAsync(S.d_file_tables, S.h_file_tables, (size_t)nfiles * sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
+    ORBX_CUDA(cudaMemcpyAsync(S.d_tables, S.h_tables, sizeof(JpTables) * sets.size(), cudaMemcpyHostToDevice, h->copy_stream));
+    ORBX_CUDA(cudaEventRecord(S.uploaded, h->copy_stream));
+    S.uploaded_pending = true;
+    ORBX_CUDA(cudaStreamWaitEvent(h->stream, S.uploaded, 0));
+    JP_EV(1);
     ORBX_CUDA(cudaMemsetAsync(h->d_coefs, 0, (size_t)nfiles * blocks * 64 * sizeof(int16_t), h->stream));
-    const unsigned hb = (unsigned)((ni + JP_HUFF_THREADS / 32 - 1) / (JP_HUFF_THREADS / 32));
-    k_jpeg_huff<<<hb, JP_HUFF_THREADS, 0, h->stream>>>(h->d_stream, h->d_intervals, (int)ni, h->d_tables, h->d_file_tables, h->d_scratch, h->d_coefs, blocks);
+    JP_EV(2);
+    const unsigned ub = (unsigned)((ni + JP_HUFF_THREADS / 32 - 1) / (JP_HUFF_THREADS / 32));
+    k_jpeg_unstuff<<<ub, JP_HUFF_THREADS, 0, h->stream>>>(S.d_stream, S.d_intervals, (int)ni, h->d_scratch, h->d_nwords);
     ORBX_CUDA(cudaGetLastError());
+    JP_EV(3);
+    int lanes = 1;                                  // active lanes per warp: enough warps to keep every scheduler busy first
+    while (lanes < 32 && ni / (size_t)(lanes * 2) >= 1200) lanes *= 2;
+    const int lane_step = 32 / lanes;
+    k_jpeg_huff<<<(unsigned)((ni * (size_t)lane_step + JP_HUFF_THREADS - 1) / JP_HUFF_THREADS), JP_HUFF_THREADS, 0, h->stream>>>(
+        S.d_intervals, (int)ni, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, h->d_coefs, blocks, lane_step);
+    ORBX_CUDA(cudaGetLastError());
+    JP_EV(4);
     k_jpeg_idct<<<dim3((blocks + JP_IDCT_THREADS - 1) / JP_IDCT_THREADS, (unsigned)nfiles), JP_IDCT_THREADS, 0, h->stream>>>(
-        h->d_coefs, h->d_tables, h->d_file_tables, nfiles, w, hh, bw, blocks, d_frames, frame_pitch, stride);
+        h->d_coefs, S.d_tables, S.d_file_tables, nfiles, w, hh, bw, blocks, d_frames, frame_pitch, stride);
     ORBX_CUDA(cudaGetLastError());
+    ORBX_CUDA(cudaEventRecord(S.decoded, h->stream));
+    S.decoded_pending = true;
+    JP_EV(5);
+#ifdef JP_TRACE
+    ev_have = true;
+#endif
+    lap("enqueue");
     return ORBX_OK;
 }
 

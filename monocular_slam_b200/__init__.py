@@ -9,4 +9,4 @@ from ._lib import (CAMERAS_DTYPE, DMATCH_DTYPE, FAST_SCORE, HARRIS_SCORE, KEYPOI
 from .orb import (NORM_HAMMING, ORB, BFMatcher, DataManager, FeatureExtractor, Features, Frame, FundamentalFilter,  # noqa: F401
                   ORB_create, OrbDescriptorExtractor, OrbFeatureDetector, Triangulator, match_features, popc_peak)
 from .bow import Vocabulary  # noqa: F401
-from .ingest import JpegDecoder  # noqa: F401
+from .ingest import JpegDecoder, JpegIngest  # noqa: F401

@@ -175,3 +175,90 @@ class IngestRing:
         while pending:
             yield collect()
         self.stats["wall_seconds"] += time.perf_counter() - t_start
+
+
+class JpegIngest:
+    """Grey-scale JPEG files -> features, with the entropy decoder on the GPU: compressed bytes over PCIe -> ``JpegDecoder`` on its
+    own stream -> ``ORB.extract_batch_dev`` + consecutive-frame matching on the extractor's stream -> results in pinned host
+    memory.  Two frame buffers: batch k+1 is decoded while batch k is extracted.  torch supplies the device buffers, streams and
+    events (plumbing only).  A batch holding a file the decoder refuses (colour, progressive ...) raises OrbxError with status
+    E_UNSUPPORTED: feed such files to ``IngestRing`` instead.
+
+    ``run(files)`` yields, per batch and in order, ``(first_index, n, kps, desc, counts, good, ngood)`` -- pinned buffers that are
+    overwritten two batches later.  While it runs the extractor and the matcher work on this object's stream; afterwards they are
+    back on their own."""
+
+    def __init__(self, orb, matcher, width, height, batch=None, ratio=0.8):
+        import torch
+        self.torch = torch
+        self.orb, self.matcher, self.ratio = orb, matcher, float(ratio)
+        self.w, self.h = int(width), int(height)
+        self.batch = int(batch or orb.max_batch)
+        dev = torch.device("cuda", orb.device)
+        self.dev = dev
+        self.dec = JpegDecoder(device=orb.device)
+        self.s_dec, self.s_orb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.dec.set_stream(self.s_dec.cuda_stream)
+        cap = self.cap = orb.default_cap
+        B = self.batch
+        self.frames = [torch.zeros((B, self.h, self.w), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.d = [{"kps": torch.empty((B, cap, 7), dtype=torch.float32, device=dev), "desc": torch.empty((B, cap, 32), dtype=torch.uint8, device=dev),
+                   "cnt": torch.zeros(B, dtype=torch.int32, device=dev), "good": torch.empty((B, cap, 4), dtype=torch.int32, device=dev),
+                   "ngood": torch.zeros(B, dtype=torch.int64, device=dev)} for _ in range(2)]
+        self.hst = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in d.items()} for d in self.d]
+        self.prev_desc = torch.zeros((cap, 32), dtype=torch.uint8, device=dev)
+        self.prev_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ev_dec = [torch.cuda.Event() for _ in range(2)]
+        self.ev_ext = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def close(self):
+        self.torch.cuda.synchronize(self.dev)
+        self.dec.close()
+
+    def run(self, files):
+        torch = self.torch
+        files = list(files)
+        orb, m, B, cap = self.orb, self.matcher, self.batch, self.cap
+        orb.set_stream(self.s_orb.cuda_stream)
+        m.set_stream(self.s_orb.cuda_stream)
+        have_prev = False
+        pending = []
+
+        def collect():
+            first, n, b = pending.pop(0)
+            self.ev_done[b].synchronize()
+            h = self.hst[b]
+            return (first, n, h["kps"].numpy().view(KEYPOINT_DTYPE).reshape(B, cap), h["desc"].numpy(), h["cnt"].numpy(),
+                    h["good"].numpy().view(DMATCH_DTYPE).reshape(B, cap), h["ngood"].numpy())
+        try:
+            for k, first in enumerate(range(0, len(files), B)):
+                n = min(B, len(files) - first)
+                b = k & 1
+                if len(pending) == 2:
+                    yield collect()                          # frees buffer set b
+                self.s_dec.wait_event(self.ev_ext[b])
+                self.dec.decode_dev(files[first:first + n], self.w, self.h, self.frames[b].data_ptr(), self.w * self.h, self.w)
+                self.ev_dec[b].record(self.s_dec)
+                d, h = self.d[b], self.hst[b]
+                with torch.cuda.stream(self.s_orb):
+                    self.s_orb.wait_event(self.ev_dec[b])
+                    orb.extract_batch_dev(self.frames[b].data_ptr(), self.w * self.h, n, self.w, self.h, self.w, d["kps"].data_ptr(), d["desc"].data_ptr(),
+                                          cap, d["cnt"].data_ptr())
+                    self.ev_ext[b].record(self.s_orb)
+                    m.match_consecutive_dev(d["desc"].data_ptr(), d["cnt"].data_ptr(), n, cap, self.prev_desc.data_ptr() if have_prev else 0,
+                                            self.prev_cnt.data_ptr() if have_prev else 0, self.ratio, d["good"].data_ptr(), d["ngood"].data_ptr())
+                    self.prev_desc.copy_(d["desc"][n - 1], non_blocking=True)
+                    self.prev_cnt.copy_(d["cnt"][n - 1:n], non_blocking=True)
+                    have_prev = True
+                    for key in d:
+                        h[key].copy_(d[key], non_blocking=True)
+                    self.ev_done[b].record(self.s_orb)
+                pending.append((first, n, b))
+            while pending:
+                yield collect()
+            orb.check_dev()
+        finally:
+            torch.cuda.synchronize(self.dev)
+            orb.set_stream(0)                                # both handles are left on their own streams
+            m.set_stream(0)

@@ -77,3 +77,18 @@ int bag_of_words(int k, int L, int nnodes, const int32_t* parent, const uint8_t*
     rc |= bowx_destroy(bw);
     return rc + info[5] + stopped + (int)node + (w > 0);
 }
+
+/* INTEGRATION.md "Frame ingest from JPEG files" */
+int jpeg_ingest(orbx_handle orb, const uint8_t* const* files, const size_t* sizes, int n, int w, int h, uint8_t* d_frames, orbx_keypoint* d_kps,
+                uint8_t* d_desc, int cap, int32_t* d_counts)
+{
+    jpgx_handle jp;
+    int32_t info[4];
+    int rc = jpgx_create(&jp, 0);
+    if (jpgx_probe(files[0], sizes[0], info) == ORBX_E_UNSUPPORTED) return 1;      /* keep imread for this file */
+    rc |= jpgx_decode_gray_batch_dev(jp, files, sizes, n, w, h, d_frames, (size_t)w * h, (size_t)w);
+    rc |= orbx_extract_batch_dev(orb, d_frames, (size_t)w * h, n, w, h, (size_t)w, d_kps, d_desc, cap, d_counts);
+    rc |= jpgx_synchronize(jp);
+    rc |= jpgx_destroy(jp);
+    return rc + info[0];
+}

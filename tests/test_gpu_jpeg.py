@@ -96,3 +96,36 @@ def test_device_frames_go_straight_into_extraction():
     for f in range(B):
         assert np.array_equal(d_desc[f, :cnt[f]].cpu().numpy(), desc[f, :cnt[f]])
     dec.close(); orb.close()
+
+
+def test_jpeg_ingest_equals_the_blocking_path_on_decoded_frames():
+    """JpegIngest (decoder and extractor on two streams, two buffer sets): keypoints, descriptors and consecutive-frame matches of
+    10 files in batches of 4 equal those of the blocking calls on the frames cv2 decodes."""
+    cv2 = pytest.importorskip("cv2")
+    from monocular_slam_b200 import BFMatcher, JpegIngest
+    n, W, H = 10, 640, 480
+    seq = syn.sequence(n, W, H, seed=11)
+    files = [cv2.imencode(".jpg", seq[i], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 80])[1].tobytes() for i in range(n)]
+    decoded = [cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED) for f in files]
+    orb = ORB(nfeatures=400, max_size=(W, H), max_batch=4)
+    m = BFMatcher()
+    ing = JpegIngest(orb, m, W, H, batch=4, ratio=0.8)
+    got = {}
+    for first, nb, kps, desc, counts, good, ngood in ing.run(files):
+        for i in range(nb):
+            c = int(counts[i])
+            got[first + i] = (kps[i, :c].copy(), desc[i, :c].copy(), good[i, :int(ngood[i])].copy())
+    ing.close()
+    assert sorted(got) == list(range(n))
+    prev = None
+    for f in range(n):
+        k, d = orb.detectAndCompute(decoded[f])
+        gk, gd, gg = got[f]
+        assert np.array_equal(gk, k) and np.array_equal(gd, d), f
+        if prev is not None:
+            want = m.match_ratio(d, prev, 0.8)
+            assert np.array_equal(gg["query_idx"], want["query_idx"]) and np.array_equal(gg["train_idx"], want["train_idx"]), f
+        else:
+            assert len(gg) == 0
+        prev = d
+    m.close(); orb.close()

@@ -73,6 +73,16 @@ tri.select_new_dev(d_g.data_ptr(), d_ng.data_ptr(), 0, d_pm.data_ptr(), d_cur.da
 tri.synchronize()
 tri.close(); fm.close(); orb.close()
 m.set_kernel(_lib.KERNEL_AUTO)
+# JPEG ingest: every committed file (restart intervals 0 / 1 / 8 / 42, two table kinds), batched per image size
+from monocular_slam_b200 import JpegDecoder
+G = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "jpeg_cases.npz"))
+jd = JpegDecoder()
+by_shape = {}
+for k_ in G["names"]:
+    by_shape.setdefault(G[k_ + "_pixels"].shape, []).append(G[k_ + "_file"].tobytes())
+for fl in by_shape.values():
+    jd.decode(fl)
+jd.close()
 # bag of words: 16- and 32-lane descents, both key widths of the sort, every scoring type
 from monocular_slam_b200 import Vocabulary
 for shape in (dict(k=10, L=3), dict(k=19, L=2, ragged=True), dict(k=40, L=2)):

@@ -33,6 +33,8 @@ namespace {
 constexpr int JP_LOOK = 10;                       // lookahead bits of the Huffman tables
 constexpr int JP_HUFF_THREADS = 128;
 constexpr int JP_IDCT_THREADS = 128;
+constexpr uint32_t JP_SUB_BITS = 1024;            // bits of an interval one lane decodes in the self-synchronising path
+constexpr uint32_t JP_MAX_INTERVAL_BITS = 1u << 26;    // exit states pack the bit position into 26 bits
 
 struct JpHuff {                                   // one Huffman table on the device
     uint16_t look[1 << JP_LOOK];                  // (length << 8) | symbol for codes of at most JP_LOOK bits, 0: longer
@@ -49,6 +51,7 @@ struct JpInterval {
     uint32_t scratch;                             // byte offset of its stripped copy (multiple of 4)
     uint32_t first_block, nblocks;                // blocks of its file, raster order
     uint32_t file;
+    uint32_t first_sub, nsub;                     // its subsequences of JP_SUB_BITS bits (the self-synchronising path)
 };
 
 __constant__ uint8_t c_natural_order[64] = {
@@ -68,14 +71,15 @@ struct JpBits {
             nbits += 32;
         }
     }
+    __device__ __forceinline__ void seek(uint32_t bit) { wi = bit >> 5; buf = 0; nbits = 0; fill(); skip((int)(bit & 31)); }
+    __device__ __forceinline__ uint32_t pos() const { return wi * 32u - (uint32_t)nbits; }      // bits consumed so far
     __device__ __forceinline__ uint32_t peek16() const { return (uint32_t)(buf >> 48); }
     __device__ __forceinline__ void skip(int n) { buf <<= n; nbits -= n; }
     __device__ __forceinline__ int get(int n) { const int v = (int)(buf >> (64 - n)); skip(n); return v; }     // 1 <= n <= 16
 };
 
-__device__ __forceinline__ int jp_decode(JpBits& b, const JpHuff* __restrict__ t)
+__device__ __forceinline__ int jp_decode(JpBits& b, const JpHuff* __restrict__ t)     // at least 16 bits buffered
 {
-    b.fill();
     const uint32_t p = b.peek16();
     const uint32_t e = __ldg(&t->look[p >> (16 - JP_LOOK)]);
     if (e) { b.skip((int)(e >> 8)); return (int)(e & 255); }
@@ -127,6 +131,9 @@ k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTa
 {
     // every lane_step-th lane of a warp owns an interval: with few intervals (a row of blocks each, or whole files) spreading them
     // over more warps costs issue slots but shortens every warp's memory gathers; with many, all 32 lanes work
+    __shared__ uint8_t s_natural[64];             // the lanes index it with different k: shared memory, not the constant cache
+    if (threadIdx.x < 64) s_natural[threadIdx.x] = c_natural_order[threadIdx.x];
+    __syncthreads();
     const long long t = (long long)blockIdx.x * JP_HUFF_THREADS + threadIdx.x;
     if (t % lane_step) return;
     const long long it = t / lane_step;
@@ -138,23 +145,133 @@ k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTa
     int dc = 0, k = 0;
     uint32_t blk = 0;
     while (blk < iv.nblocks) {
+        // one refill per symbol: at least 33 bits are buffered, a code takes at most 16 and its value bits at most 16
+        b.fill();
         const bool is_dc = k == 0;
         const int sym = jp_decode(b, is_dc ? &tb->dc : &tb->ac);
         const int r = is_dc ? 0 : sym >> 4, sz = sym & 15;
         int val = 0;
-        if (sz) { b.fill(); val = jp_extend(b.get(sz), sz); }
+        if (sz) val = jp_extend(b.get(sz), sz);
         if (is_dc) {
             dc += val;
             if (dc) co[0] = (int16_t)dc;
             k = 1;
         } else if (sz) {
             k += r;
-            if (k <= 63) co[c_natural_order[k]] = (int16_t)val;
+            if (k <= 63) co[s_natural[k]] = (int16_t)val;
             k = k > 63 ? 64 : k + 1;              // (k > 63: corrupt data ends the block, as the reference's loop does)
         } else {
             k = r == 15 ? k + 16 : 64;            // ZRL, or end of block
         }
         if (k >= 64) { k = 0; blk++; co += 64; }
+    }
+}
+
+// ---- K17c: the self-synchronising path for intervals longer than JP_SUB_BITS (whole files without restart markers, block rows):
+// an interval is cut into subsequences of JP_SUB_BITS bits and every lane decodes ONE of them.  A lane does not know where the
+// first code of its subsequence starts nor which coefficient of a block it belongs to, so it starts on a guess (its first bit, a
+// DC code) -- Huffman streams re-synchronise quickly, so its exit state (bit position and coefficient index where the next
+// subsequence begins) is usually right even then.  Every following round re-decodes a subsequence from its predecessor's exit
+// state if that has changed; subsequence 0 starts from the truth, so the fixed point IS the sequential decode, and a round in
+// which nothing changes proves it has been reached.  The per-subsequence block counts and DC sums then tell every lane which
+// block and which DC value it starts with, and a last decode writes the coefficients.  (The idea of self-synchronising
+// subsequences is from A. Weissenberger and B. Schmidt, "Massively parallel Huffman decoding on GPUs", 2018.)
+__device__ __forceinline__ uint32_t jp_state(uint32_t pos, int k) { return (pos << 6) | (uint32_t)k; }
+
+// decodes from `state` up to bit `end`; WRITE: stores coefficients, starting at block `blk` with DC predictor `dc`
+template <bool WRITE>
+__device__ __forceinline__ uint32_t jp_run(JpBits& b, const JpTables* __restrict__ tb, const uint8_t* s_natural, uint32_t state, uint32_t end,
+                                           int& nblk, int& dcsum, int16_t* co, uint32_t blocks_left)
+{
+    int k = (int)(state & 63);
+    b.seek(state >> 6);
+    while (b.pos() < end && (!WRITE || blocks_left)) {
+        b.fill();
+        const bool is_dc = k == 0;
+        const int sym = jp_decode(b, is_dc ? &tb->dc : &tb->ac);
+        const int r = is_dc ? 0 : sym >> 4, sz = sym & 15;
+        int val = 0;
+        if (sz) val = jp_extend(b.get(sz), sz);
+        if (is_dc) {
+            dcsum += val;
+            if (WRITE && dcsum) co[0] = (int16_t)dcsum;
+            k = 1;
+        } else if (sz) {
+            k += r;
+            if (WRITE && k <= 63) co[s_natural[k]] = (int16_t)val;
+            k = k > 63 ? 64 : k + 1;
+        } else {
+            k = r == 15 ? k + 16 : 64;
+        }
+        if (k >= 64) { k = 0; nblk++; if (WRITE) { co += 64; blocks_left--; } }
+    }
+    return jp_state(b.pos(), k);
+}
+
+// One CTA per interval, its lanes striding over the interval's subsequences.  Round 0: every subsequence from its own first bit.
+// Rounds 1..: a subsequence whose predecessor's exit state is not the state it was last decoded from is decoded again.  A round
+// without a changed exit state ends the loop (at the latest after as many rounds as there are subsequences: a perfectly periodic
+// stream -- a blank image -- never re-synchronises by itself and is walked front to back).  Then thread 0 adds up the block counts
+// and DC sums, and every lane decodes its subsequences once more, writing coefficients.
+__global__ void __launch_bounds__(1024)
+k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables,
+            const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, uint32_t* exit_state, uint32_t* used_state,
+            int32_t* sub_blocks, int32_t* sub_dcsum, int16_t* __restrict__ coefs, uint32_t blocks_per_file)
+{
+    __shared__ uint8_t s_natural[64];
+    __shared__ int s_changed;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_natural[i] = c_natural_order[i];      // (a CTA can be a single warp)
+    const JpInterval iv = intervals[blockIdx.x];
+    const JpTables* tb = tables + file_tables[iv.file];
+    const uint32_t nwords = nwords_in[blockIdx.x], total = nwords * 32u;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(scratch + iv.scratch);
+    volatile uint32_t* ex = exit_state + iv.first_sub;
+    uint32_t* used = used_state + iv.first_sub;
+    int32_t* nb = sub_blocks + iv.first_sub;
+    int32_t* ds = sub_dcsum + iv.first_sub;
+    for (int round = 0;; round++) {
+        if (threadIdx.x == 0) s_changed = 0;
+        __syncthreads();
+        bool mine = false;
+        for (uint32_t j = threadIdx.x; j < iv.nsub; j += blockDim.x) {
+            uint32_t start;
+            if (round == 0) start = jp_state(j * JP_SUB_BITS, 0);
+            else {
+                if (j == 0) continue;              // started from the truth in round 0
+                start = ex[j - 1];
+                if (start == used[j]) continue;
+            }
+            JpBits b = {words, nwords, 0, 0ull, 0};
+            int nblk = 0, dcsum = 0;
+            const uint32_t e = jp_run<false>(b, tb, nullptr, start, min((j + 1) * JP_SUB_BITS, total), nblk, dcsum, nullptr, 0);
+            used[j] = start; nb[j] = nblk; ds[j] = dcsum;
+            if (round == 0 || e != ex[j]) { ex[j] = e; mine = true; }
+        }
+        if (mine && round) s_changed = 1;
+        __syncthreads();
+        if (round && !s_changed) break;
+        __syncthreads();
+    }
+    // first block and DC predictor of every subsequence: an exclusive prefix sum, in place
+    if (threadIdx.x == 0) {
+        int blk = 0, dc = 0;
+        for (uint32_t j = 0; j < iv.nsub; j++) {
+            const int n = nb[j], d = ds[j];
+            nb[j] = blk; ds[j] = dc;
+            blk += n; dc += d;
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < iv.nsub; j += blockDim.x) {
+        const uint32_t first = (uint32_t)nb[j];
+        if (first >= iv.nblocks) continue;
+        JpBits b = {words, nwords, 0, 0ull, 0};
+        int nblk = 0, dc = ds[j];
+        // the lane that reaches the end of the data goes on over zero bits until the interval's blocks are complete, as libjpeg
+        // (and the sequential kernel) do with a truncated file
+        const uint32_t end = (j + 1) * JP_SUB_BITS >= total ? 0xffffffffu : (j + 1) * JP_SUB_BITS;
+        jp_run<true>(b, tb, s_natural, j ? ex[j - 1] : jp_state(0, 0), end, nblk, dc,
+                     coefs + ((size_t)iv.file * blocks_per_file + iv.first_block + first) * 64, iv.nblocks - first);
     }
 }
 
@@ -396,6 +513,7 @@ struct jpgx_context {
     int next_set;
     uint8_t* d_scratch; size_t d_scratch_bytes;   // the same without stuffed bytes
     uint32_t* d_nwords; size_t d_nwords_bytes;    // 32-bit words of every interval's stripped copy
+    uint32_t* d_subw; size_t d_subw_bytes;        // per subsequence: exit state, state it was last decoded from, blocks, DC sum
     int16_t* d_coefs; size_t d_coefs_bytes;
     uint8_t* d_frames; size_t d_frames_bytes;     // staging of the host-output form
 };
@@ -441,7 +559,7 @@ extern "C" int jpgx_destroy(jpgx_handle h)
         if (S.decoded) cudaEventDestroy(S.decoded);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    cudaFree(h->d_scratch); cudaFree(h->d_nwords);
+    cudaFree(h->d_scratch); cudaFree(h->d_nwords); cudaFree(h->d_subw);
     cudaFree(h->d_coefs); cudaFree(h->d_frames);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -642,6 +760,24 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         for (std::thread& t : pool) t.join();
     }
     const size_t ni = nint;
+    // subsequences of the self-synchronising path: ceil(bits / JP_SUB_BITS) per interval (from the stuffed length: a few may be empty)
+    size_t nsubs = 0;
+    uint32_t max_nsub = 1;
+    bool packable = true;
+    for (size_t i = 0; i < ni; i++) {
+        JpInterval& iv = S.h_intervals[i];
+        iv.nsub = std::max<uint32_t>(1u, (uint32_t)(((size_t)iv.src_len * 8 + JP_SUB_BITS - 1) / JP_SUB_BITS));
+        iv.first_sub = (uint32_t)nsubs;
+        nsubs += iv.nsub;
+        max_nsub = std::max(max_nsub, iv.nsub);
+        packable = packable && (size_t)iv.src_len * 8 + 64 < JP_MAX_INTERVAL_BITS;
+    }
+    // short intervals (a restart marker every few blocks) are decoded one lane each, sequentially: nothing to synchronise
+    const bool sync_path = max_nsub > 4 && packable;
+    if (sync_path) {
+        rc = jp_grow(&h->d_subw, &h->d_subw_bytes, nsubs * 4 * sizeof(uint32_t));
+        if (rc) return rc;
+    }
     lap("stage");
     if ((int)sets.size() > S.tables_cap) {
         cudaFreeHost(S.h_tables); S.h_tables = nullptr;
@@ -670,11 +806,19 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
     k_jpeg_unstuff<<<ub, JP_HUFF_THREADS, 0, h->stream>>>(S.d_stream, S.d_intervals, (int)ni, h->d_scratch, h->d_nwords);
     ORBX_CUDA(cudaGetLastError());
     JP_EV(3);
-    int lanes = 1;                                  // active lanes per warp: enough warps to keep every scheduler busy first
+    int lanes = 1;                                  // active lanes per warp of the sequential kernel: enough warps to keep every scheduler busy first
     while (lanes < 32 && ni / (size_t)(lanes * 2) >= 1200) lanes *= 2;
     const int lane_step = 32 / lanes;
-    k_jpeg_huff<<<(unsigned)((ni * (size_t)lane_step + JP_HUFF_THREADS - 1) / JP_HUFF_THREADS), JP_HUFF_THREADS, 0, h->stream>>>(
-        S.d_intervals, (int)ni, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, h->d_coefs, blocks, lane_step);
+    const unsigned seq_blocks = (unsigned)((ni * (size_t)lane_step + JP_HUFF_THREADS - 1) / JP_HUFF_THREADS);
+    if (!sync_path) {
+        k_jpeg_huff<<<seq_blocks, JP_HUFF_THREADS, 0, h->stream>>>(S.d_intervals, (int)ni, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords,
+                                                                  h->d_coefs, blocks, lane_step);
+    } else {
+        const unsigned threads = std::min(1024u, (max_nsub + 31u) / 32u * 32u);
+        k_jpeg_sync<<<(unsigned)ni, threads, 0, h->stream>>>(S.d_intervals, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, h->d_subw,
+                                                            h->d_subw + nsubs, (int32_t*)(h->d_subw + 2 * nsubs), (int32_t*)(h->d_subw + 3 * nsubs),
+                                                            h->d_coefs, blocks);
+    }
     ORBX_CUDA(cudaGetLastError());
     JP_EV(4);
     k_jpeg_idct<<<dim3((blocks + JP_IDCT_THREADS - 1) / JP_IDCT_THREADS, (unsigned)nfiles), JP_IDCT_THREADS, 0, h->stream>>>(

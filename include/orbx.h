@@ -479,8 +479,8 @@ ORBX_API int bowx_score_batch_dev(bowx_handle h, const uint32_t* d_qwords, const
  * libjpeg behind OpenCV (default DCT method JDCT_ISLOW).  This family decodes a whole batch of such files on the GPU, straight
  * into the device-resident frames orbx_extract_batch_dev reads, bit for bit what cv2.imdecode returns (tests/golden/
  * jpeg_cases.npz): only the compressed bytes cross PCIe.  Handled: one component, 8 bits, Huffman, baseline or extended
- * sequential (SOF0 / SOF1), any quantisation / Huffman tables, with or without restart markers (the restart interval is the
- * unit of parallelism: files without markers decode one warp per file).  Everything else -- colour, progressive, arithmetic,
+ * sequential (SOF0 / SOF1), any quantisation / Huffman tables, with or without restart markers (both decode in parallel:
+ * self-synchronising subsequences inside every restart interval).  Everything else -- colour, progressive, arithmetic,
  * 12-bit -- returns ORBX_E_UNSUPPORTED and the caller keeps its CPU decoder for that file; damaged headers ORBX_E_INVALID. */
 typedef struct jpgx_context* jpgx_handle;
 ORBX_API int jpgx_create(jpgx_handle* out, int device);

@@ -5,16 +5,18 @@
 //
 //   host      marker parsing (ITU-T T.81 Annex B): DQT, SOF0/1, DHT, DRI, SOS of a one-component 8-bit Huffman file; the
 //             entropy-coded segment is cut at its restart markers into intervals (T.81 E.2.4) -- the unit of parallelism
-//   K17 k_jpeg_unstuff, k_jpeg_huff   a warp per restart interval strips the stuffed zero bytes (FF 00 -> FF) into a scratch
-//             copy; then one LANE per interval runs the sequential Huffman decoder of T.81 F.2.2 over it (10-bit lookahead
-//             tables, the DC predictor restarting with the interval), one symbol per loop iteration so that the 32 intervals
-//             of a warp stay in step, and scatters the non-zero coefficients of each 8x8 block
+//   K17 k_jpeg_unstuff, k_jpeg_sync / k_jpeg_huff   a warp per restart interval strips the stuffed zero bytes (FF 00 -> FF) into
+//             a scratch copy; the Huffman decoder of T.81 F.2.2 (10-bit lookahead tables, the DC predictor restarting with the
+//             interval, one symbol per loop iteration so that lanes on different data stay in step) then runs either one lane
+//             per interval (short intervals) or, for block rows and whole files, one lane per subsequence of <= 1024 bits,
+//             iterated until every subsequence was decoded from its predecessor's true exit state; the non-zero coefficients
+//             of each 8x8 block are scattered into a zeroed array
 //   K18 k_jpeg_idct   one thread per block: dequantisation and libjpeg's jpeg_idct_islow (jidctint.c: 13-bit constants, two
 //             passes, DESCALE) in registers, the range-limit table of jdmaster.c as arithmetic, 8-byte row stores that
 //             coalesce across the blocks of a block row
 //
-// Bit-exact with cv2.imdecode (libjpeg-turbo 3.1.2) on every file of tests/golden/jpeg_cases.npz.  Files without restart
-// markers decode too -- one warp per file, so only a batch of them is fast.  Anything but one-component baseline / extended
+// Bit-exact with cv2.imdecode (libjpeg-turbo 3.1.2) on every file of tests/golden/jpeg_cases.npz, with and without restart
+// markers.  Anything but one-component baseline / extended
 // sequential Huffman (progressive, colour, 12-bit, arithmetic) is refused with ORBX_E_UNSUPPORTED: the caller keeps its CPU
 // decoder for those.
 #include <string.h>
@@ -216,7 +218,7 @@ __device__ __forceinline__ uint32_t jp_run(JpBits& b, const JpTables* __restrict
 __global__ void __launch_bounds__(1024)
 k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables,
             const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, uint32_t* exit_state, uint32_t* used_state,
-            int32_t* sub_blocks, int32_t* sub_dcsum, int16_t* __restrict__ coefs, uint32_t blocks_per_file)
+            int32_t* sub_blocks, int32_t* sub_dcsum, int16_t* __restrict__ coefs, uint32_t blocks_per_file, uint32_t sub_bits)
 {
     __shared__ uint8_t s_natural[64];
     __shared__ int s_changed;
@@ -235,7 +237,7 @@ k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict
         bool mine = false;
         for (uint32_t j = threadIdx.x; j < iv.nsub; j += blockDim.x) {
             uint32_t start;
-            if (round == 0) start = jp_state(j * JP_SUB_BITS, 0);
+            if (round == 0) start = jp_state(j * sub_bits, 0);
             else {
                 if (j == 0) continue;              // started from the truth in round 0
                 start = ex[j - 1];
@@ -243,7 +245,7 @@ k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict
             }
             JpBits b = {words, nwords, 0, 0ull, 0};
             int nblk = 0, dcsum = 0;
-            const uint32_t e = jp_run<false>(b, tb, nullptr, start, min((j + 1) * JP_SUB_BITS, total), nblk, dcsum, nullptr, 0);
+            const uint32_t e = jp_run<false>(b, tb, nullptr, start, min((j + 1) * sub_bits, total), nblk, dcsum, nullptr, 0);
             used[j] = start; nb[j] = nblk; ds[j] = dcsum;
             if (round == 0 || e != ex[j]) { ex[j] = e; mine = true; }
         }
@@ -269,7 +271,7 @@ k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict
         int nblk = 0, dc = ds[j];
         // the lane that reaches the end of the data goes on over zero bits until the interval's blocks are complete, as libjpeg
         // (and the sequential kernel) do with a truncated file
-        const uint32_t end = (j + 1) * JP_SUB_BITS >= total ? 0xffffffffu : (j + 1) * JP_SUB_BITS;
+        const uint32_t end = (j + 1) * sub_bits >= total ? 0xffffffffu : (j + 1) * sub_bits;
         jp_run<true>(b, tb, s_natural, j ? ex[j - 1] : jp_state(0, 0), end, nblk, dc,
                      coefs + ((size_t)iv.file * blocks_per_file + iv.first_block + first) * 64, iv.nblocks - first);
     }
@@ -760,20 +762,25 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         for (std::thread& t : pool) t.join();
     }
     const size_t ni = nint;
-    // subsequences of the self-synchronising path: ceil(bits / JP_SUB_BITS) per interval (from the stuffed length: a few may be empty)
+    // subsequences of the self-synchronising path: ceil(bits / sub_bits) per interval (from the stuffed length: a few may be
+    // empty).  JP_SUB_BITS bits each, fewer when the longest interval would then not fill a warp (block rows: ~18 x 1024 bits)
+    uint32_t longest = 0;
+    for (size_t i = 0; i < ni; i++) longest = std::max(longest, S.h_intervals[i].src_len);
+    uint32_t sub_bits = JP_SUB_BITS;
+    if ((size_t)longest * 8 < 32u * JP_SUB_BITS) sub_bits = std::max(256u, (uint32_t)(((size_t)longest * 8 + 31) / 32 + 31) / 32 * 32);
     size_t nsubs = 0;
     uint32_t max_nsub = 1;
     bool packable = true;
     for (size_t i = 0; i < ni; i++) {
         JpInterval& iv = S.h_intervals[i];
-        iv.nsub = std::max<uint32_t>(1u, (uint32_t)(((size_t)iv.src_len * 8 + JP_SUB_BITS - 1) / JP_SUB_BITS));
+        iv.nsub = std::max<uint32_t>(1u, (uint32_t)(((size_t)iv.src_len * 8 + sub_bits - 1) / sub_bits));
         iv.first_sub = (uint32_t)nsubs;
         nsubs += iv.nsub;
         max_nsub = std::max(max_nsub, iv.nsub);
         packable = packable && (size_t)iv.src_len * 8 + 64 < JP_MAX_INTERVAL_BITS;
     }
     // short intervals (a restart marker every few blocks) are decoded one lane each, sequentially: nothing to synchronise
-    const bool sync_path = max_nsub > 4 && packable;
+    const bool sync_path = (size_t)longest * 8 > 4 * JP_SUB_BITS && packable;
     if (sync_path) {
         rc = jp_grow(&h->d_subw, &h->d_subw_bytes, nsubs * 4 * sizeof(uint32_t));
         if (rc) return rc;
@@ -817,7 +824,7 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         const unsigned threads = std::min(1024u, (max_nsub + 31u) / 32u * 32u);
         k_jpeg_sync<<<(unsigned)ni, threads, 0, h->stream>>>(S.d_intervals, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, h->d_subw,
                                                             h->d_subw + nsubs, (int32_t*)(h->d_subw + 2 * nsubs), (int32_t*)(h->d_subw + 3 * nsubs),
-                                                            h->d_coefs, blocks);
+                                                            h->d_coefs, blocks, sub_bits);
     }
     ORBX_CUDA(cudaGetLastError());
     JP_EV(4);

@@ -22,8 +22,6 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
-#include <chrono>
-#include <cstdio>
 #include <thread>
 #include <vector>
 
@@ -639,32 +637,11 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
     ORBX_CUDA(cudaSetDevice(h->device));
     const int bw = (w + 7) / 8, bh = (hh + 7) / 8;
     const uint32_t blocks = (uint32_t)bw * (uint32_t)bh;
-#ifdef JP_TRACE
-    auto t_0 = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) { auto n = std::chrono::steady_clock::now(); fprintf(stderr, "  jpgx %-10s %.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t_0).count()); t_0 = n; };
-#else
-    auto lap = [](const char*) {};
-#endif
     // this call's buffer set was last used two calls ago: its uploads must have left the pinned buffers before they are
     // overwritten (the device copy is protected in stream order, below)
     JpSet& S = h->set[h->next_set];
     h->next_set ^= 1;
     if (S.uploaded_pending) { ORBX_CUDA(cudaEventSynchronize(S.uploaded)); S.uploaded_pending = false; }
-
-    lap("wait");
-#ifdef JP_TRACE
-    static cudaEvent_t ev[6];
-    static bool ev_init = false, ev_have = false;
-    if (!ev_init) { for (int i = 0; i < 6; i++) cudaEventCreate(&ev[i]); ev_init = true; }
-    if (ev_have) {
-        cudaEventSynchronize(ev[5]);
-        const char* names[5] = {"h2d", "memset", "unstuff", "huff", "idct"};
-        for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, "  jpgx dev %-8s %.3f ms\n", names[i], ms); }
-    }
-#define JP_EV(i) cudaEventRecord(ev[i], h->stream)
-#else
-#define JP_EV(i) do { } while (0)
-#endif
     // 1. headers: where every file's bytes, intervals and stripped copy go follows from them alone
     std::vector<HostFile> hf((size_t)nfiles);
     std::vector<size_t> off((size_t)nfiles + 1, 0), first_iv((size_t)nfiles + 1, 0), scr((size_t)nfiles + 1, 0);
@@ -693,8 +670,6 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
     if (!rc) rc = jp_grow(&S.d_file_tables, &S.d_file_tables_bytes, (size_t)nfiles * sizeof(int32_t));
     if (!rc) rc = jp_grow(&h->d_coefs, &h->d_coefs_bytes, (size_t)nfiles * blocks * 64 * sizeof(int16_t));
     if (rc) return rc;
-
-    lap("headers");
     // 2a. table sets, shared by the files that carry the same ones
     std::vector<JpTables> sets;
     std::vector<const HostFile*> set_owner;
@@ -716,7 +691,6 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         }
         S.h_file_tables[i] = set;
     }
-    lap("tables");
     // 2b. per file, independent of the others (host threads when there is enough to copy): its scan into the pinned stream,
     // cut at its restart markers
     auto stage_file = [&](int i) {
@@ -785,7 +759,6 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         rc = jp_grow(&h->d_subw, &h->d_subw_bytes, nsubs * 4 * sizeof(uint32_t));
         if (rc) return rc;
     }
-    lap("stage");
     if ((int)sets.size() > S.tables_cap) {
         cudaFreeHost(S.h_tables); S.h_tables = nullptr;
         cudaFree(S.d_tables); S.d_tables = nullptr;
@@ -796,7 +769,6 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
     memcpy(S.h_tables, sets.data(), sizeof(JpTables) * sets.size());
 
     // 3. upload, decode
-    JP_EV(0);
     // uploads on the copy stream, behind the kernels that last read this set's device copy; the caller's stream waits for them
     if (S.decoded_pending) ORBX_CUDA(cudaStreamWaitEvent(h->copy_stream, S.decoded, 0));
     ORBX_CUDA(cudaMemcpyAsync(S.d_stream, S.h_stream, total, cudaMemcpyHostToDevice, h->copy_stream));
@@ -806,13 +778,10 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
     ORBX_CUDA(cudaEventRecord(S.uploaded, h->copy_stream));
     S.uploaded_pending = true;
     ORBX_CUDA(cudaStreamWaitEvent(h->stream, S.uploaded, 0));
-    JP_EV(1);
     ORBX_CUDA(cudaMemsetAsync(h->d_coefs, 0, (size_t)nfiles * blocks * 64 * sizeof(int16_t), h->stream));
-    JP_EV(2);
     const unsigned ub = (unsigned)((ni + JP_HUFF_THREADS / 32 - 1) / (JP_HUFF_THREADS / 32));
     k_jpeg_unstuff<<<ub, JP_HUFF_THREADS, 0, h->stream>>>(S.d_stream, S.d_intervals, (int)ni, h->d_scratch, h->d_nwords);
     ORBX_CUDA(cudaGetLastError());
-    JP_EV(3);
     int lanes = 1;                                  // active lanes per warp of the sequential kernel: enough warps to keep every scheduler busy first
     while (lanes < 32 && ni / (size_t)(lanes * 2) >= 1200) lanes *= 2;
     const int lane_step = 32 / lanes;
@@ -827,17 +796,11 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
                                                             h->d_coefs, blocks, sub_bits);
     }
     ORBX_CUDA(cudaGetLastError());
-    JP_EV(4);
     k_jpeg_idct<<<dim3((blocks + JP_IDCT_THREADS - 1) / JP_IDCT_THREADS, (unsigned)nfiles), JP_IDCT_THREADS, 0, h->stream>>>(
         h->d_coefs, S.d_tables, S.d_file_tables, nfiles, w, hh, bw, blocks, d_frames, frame_pitch, stride);
     ORBX_CUDA(cudaGetLastError());
     ORBX_CUDA(cudaEventRecord(S.decoded, h->stream));
     S.decoded_pending = true;
-    JP_EV(5);
-#ifdef JP_TRACE
-    ev_have = true;
-#endif
-    lap("enqueue");
     return ORBX_OK;
 }
 

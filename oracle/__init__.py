@@ -121,6 +121,8 @@ def lib():
         L.bow_word_weight.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_jpeg_probe.argtypes = [u8p, C.c_size_t, i32p]
         L.orc_jpeg_decode_gray.argtypes = [u8p, C.c_size_t, u8p, C.c_int]
+        L.orc_jpeg_probe_colour.argtypes = [u8p, C.c_size_t, i32p]
+        L.orc_jpeg_decode_bgr.argtypes = [u8p, C.c_size_t, u8p, C.c_int]
         _lib = L
     return _lib
 
@@ -558,6 +560,21 @@ def jpeg_decode_gray(data):
     buf = np.frombuffer(bytes(data), np.uint8)
     out = np.zeros((h, w), np.uint8)
     rc = lib().orc_jpeg_decode_gray(_u8(buf), len(buf), _u8(out), w)
+    if rc:
+        raise ValueError(rc)
+    return out
+
+
+def jpeg_decode_bgr(data):
+    """A three-component (YCbCr 4:2:0 / 4:2:2 / 4:4:4) baseline file as imread returns it: [h][w][3] BGR."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    info = np.zeros(12, np.int32)
+    rc = lib().orc_jpeg_probe_colour(_u8(buf), len(buf), _i32(info))
+    if rc:
+        raise ValueError(rc)
+    w, h = int(info[0]), int(info[1])
+    out = np.zeros((h, w, 3), np.uint8)
+    rc = lib().orc_jpeg_decode_bgr(_u8(buf), len(buf), _u8(out), 3 * w)
     if rc:
         raise ValueError(rc)
     return out

@@ -319,3 +319,237 @@ int orc_jpeg_decode_gray(const uint8_t* file, size_t size, uint8_t* out, int str
     }
     return ORC_JPEG_OK;
 }
+
+
+/* ---- colour: three-component YCbCr files (JFIF), interleaved scan, luma sampling 2x2 (4:2:0), 2x1 (4:2:2) or 1x1 (4:4:4) with
+ * 1x1 chroma.  What OpenCV returns for them (imread IMREAD_UNCHANGED: BGR) is libjpeg's default output path:
+ *   interleaved MCU decoding              T.81 A.2.3; jdhuff.c decode_mcu (one DC predictor per component), jdcoefct.c
+ *   chroma upsampling                     jdsample.c h2v2_fancy_upsample / h2v1_fancy_upsample (do_fancy_upsampling, the default);
+ *                                         context rows at the top and bottom replicate the first / last real row (jdmainct.c)
+ *   colour conversion                     jdcolor.c ycc_rgb_convert (16-bit fixed point tables, SCALEBITS 16), range-limited
+ * pinned against cv2.imdecode on the colour files of tests/golden/jpeg_cases.npz.
+ * orc_jpeg_decode_planes: the component planes after the inverse DCT, each padded to whole MCUs; planes[c] must hold the
+ * pw[c] * ph[c] bytes orc_jpeg_probe_colour reports. */
+typedef struct { int h, v, tq, td, ta; } jcomp;
+typedef struct {
+    int width, height, restart_interval, ncomp, hmax, vmax;
+    jcomp comp[3];
+    uint16_t quant[4][64];
+    huff_table dc[4], ac[4];
+    const uint8_t* scan; size_t scan_len;
+} jpeg_cinfo;
+
+static int jpeg_parse_colour(const uint8_t* f, size_t n, jpeg_cinfo* ji)
+{
+    memset(ji, 0, sizeof(*ji));
+    if (n < 4 || f[0] != 0xFF || f[1] != 0xD8) return ORC_JPEG_CORRUPT;
+    size_t p = 2;
+    int have_sof = 0, qp[4] = {0, 0, 0, 0}, cid[3] = {0, 0, 0};
+    for (;;) {
+        if (p + 4 > n || f[p] != 0xFF) return ORC_JPEG_CORRUPT;
+        while (p < n && f[p] == 0xFF) p++;
+        if (p >= n) return ORC_JPEG_CORRUPT;
+        const int m = f[p++];
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+        if (m == 0xD9) return ORC_JPEG_CORRUPT;
+        if (p + 2 > n) return ORC_JPEG_CORRUPT;
+        const size_t len = ((size_t)f[p] << 8) | f[p + 1];
+        if (len < 2 || p + len > n) return ORC_JPEG_CORRUPT;
+        const uint8_t* s = f + p + 2;
+        const size_t sl = len - 2;
+        if (m == 0xC0 || m == 0xC1) {
+            if (sl < 6 || s[0] != 8) return ORC_JPEG_UNSUPPORTED;
+            ji->height = (s[1] << 8) | s[2];
+            ji->width = (s[3] << 8) | s[4];
+            ji->ncomp = s[5];
+            if (ji->ncomp != 3 || sl < 6 + 9 || ji->width == 0 || ji->height == 0) return ORC_JPEG_UNSUPPORTED;
+            for (int c = 0; c < 3; c++) {
+                cid[c] = s[6 + 3 * c];
+                ji->comp[c].h = s[7 + 3 * c] >> 4; ji->comp[c].v = s[7 + 3 * c] & 15; ji->comp[c].tq = s[8 + 3 * c] & 3;
+                if (ji->comp[c].h > ji->hmax) ji->hmax = ji->comp[c].h;
+                if (ji->comp[c].v > ji->vmax) ji->vmax = ji->comp[c].v;
+            }
+            have_sof = 1;
+        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return ORC_JPEG_UNSUPPORTED;
+        } else if (m == 0xC4) {
+            size_t q = 0;
+            while (q < sl) {
+                if (q + 17 > sl) return ORC_JPEG_CORRUPT;
+                const int tc = s[q] >> 4, th = s[q] & 15;
+                if (tc > 1 || th > 3) return ORC_JPEG_CORRUPT;
+                huff_table* t = tc ? &ji->ac[th] : &ji->dc[th];
+                int count = 0;
+                t->bits[0] = 0;
+                for (int l = 1; l <= 16; l++) { t->bits[l] = s[q + l]; count += t->bits[l]; }
+                q += 17;
+                if (count > 256 || q + (size_t)count > sl) return ORC_JPEG_CORRUPT;
+                memset(t->vals, 0, sizeof(t->vals));
+                memcpy(t->vals, s + q, (size_t)count);
+                q += (size_t)count;
+                t->present = 1;
+                huff_build(t);
+            }
+        } else if (m == 0xDB) {
+            size_t q = 0;
+            while (q < sl) {
+                const int pq = s[q] >> 4, tq = s[q] & 15;
+                if (tq > 3 || pq > 1) return ORC_JPEG_CORRUPT;
+                q++;
+                if (q + (size_t)(pq ? 128 : 64) > sl) return ORC_JPEG_CORRUPT;
+                for (int i = 0; i < 64; i++) {
+                    const int v = pq ? ((s[q] << 8) | s[q + 1]) : s[q];
+                    q += pq ? 2 : 1;
+                    ji->quant[tq][jpeg_natural_order[i]] = (uint16_t)v;
+                }
+                qp[tq] = 1;
+            }
+        } else if (m == 0xDD) {
+            if (sl < 2) return ORC_JPEG_CORRUPT;
+            ji->restart_interval = (s[0] << 8) | s[1];
+        } else if (m == 0xDA) {
+            if (!have_sof) return ORC_JPEG_CORRUPT;
+            if (sl < 4 + 6 || s[0] != 3) return ORC_JPEG_UNSUPPORTED;
+            for (int c = 0; c < 3; c++) {
+                if (s[1 + 2 * c] != cid[c]) return ORC_JPEG_UNSUPPORTED;
+                ji->comp[c].td = s[2 + 2 * c] >> 4; ji->comp[c].ta = s[2 + 2 * c] & 15;
+                if (ji->comp[c].td > 3 || ji->comp[c].ta > 3 || !ji->dc[ji->comp[c].td].present || !ji->ac[ji->comp[c].ta].present || !qp[ji->comp[c].tq]) return ORC_JPEG_CORRUPT;
+            }
+            if (s[7] != 0 || s[8] != 63 || s[9] != 0) return ORC_JPEG_UNSUPPORTED;
+            if (ji->comp[1].h != 1 || ji->comp[1].v != 1 || ji->comp[2].h != 1 || ji->comp[2].v != 1) return ORC_JPEG_UNSUPPORTED;
+            if (!((ji->comp[0].h == 2 && ji->comp[0].v == 2) || (ji->comp[0].h == 2 && ji->comp[0].v == 1) || (ji->comp[0].h == 1 && ji->comp[0].v == 1)))
+                return ORC_JPEG_UNSUPPORTED;
+            ji->scan = f + p + len;
+            ji->scan_len = n - (p + len);
+            return ORC_JPEG_OK;
+        }
+        p += len;
+    }
+}
+
+/* info[12] = {width, height, restart interval, hmax, vmax, then per component: plane width, plane height} (+ h0 v0 of luma at [11]?) */
+int orc_jpeg_probe_colour(const uint8_t* file, size_t size, int32_t* info)
+{
+    jpeg_cinfo ji;
+    const int rc = jpeg_parse_colour(file, size, &ji);
+    if (rc) return rc;
+    const int mx = (ji.width + 8 * ji.hmax - 1) / (8 * ji.hmax), my = (ji.height + 8 * ji.vmax - 1) / (8 * ji.vmax);
+    info[0] = ji.width; info[1] = ji.height; info[2] = ji.restart_interval; info[3] = ji.hmax; info[4] = ji.vmax;
+    for (int c = 0; c < 3; c++) { info[5 + 2 * c] = mx * ji.comp[c].h * 8; info[6 + 2 * c] = my * ji.comp[c].v * 8; }
+    info[11] = ji.comp[0].h * 16 + ji.comp[0].v;
+    return ORC_JPEG_OK;
+}
+
+int orc_jpeg_decode_planes(const uint8_t* file, size_t size, uint8_t* p0, uint8_t* p1, uint8_t* p2)
+{
+    jpeg_cinfo ji;
+    const int rc = jpeg_parse_colour(file, size, &ji);
+    if (rc) return rc;
+    uint8_t* planes[3] = {p0, p1, p2};
+    const int mx = (ji.width + 8 * ji.hmax - 1) / (8 * ji.hmax), my = (ji.height + 8 * ji.vmax - 1) / (8 * ji.vmax);
+    const int nmcu = mx * my, ri = ji.restart_interval ? ji.restart_interval : nmcu;
+    const uint8_t* p = ji.scan;
+    const uint8_t* end = ji.scan + ji.scan_len;
+    for (int m0 = 0; m0 < nmcu; m0 += ri) {
+        const uint8_t* q = p;
+        while (q + 1 < end && !(q[0] == 0xFF && q[1] != 0x00)) q++;
+        if (q + 1 >= end) q = end;
+        bitreader br = {p, q, 0, 0};
+        int dc[3] = {0, 0, 0};
+        const int m1 = m0 + ri < nmcu ? m0 + ri : nmcu;
+        for (int m = m0; m < m1; m++) {
+            const int mcx = m % mx, mcy = m / mx;
+            for (int c = 0; c < 3; c++) {
+                const int stride = mx * ji.comp[c].h * 8;
+                for (int by = 0; by < ji.comp[c].v; by++)
+                    for (int bx = 0; bx < ji.comp[c].h; bx++) {
+                        int16_t coef[64];
+                        memset(coef, 0, sizeof(coef));
+                        int s = huff_decode(&br, &ji.dc[ji.comp[c].td]);
+                        if (s) { const int r = br_get(&br, s & 15); s = HUFF_EXTEND(r, s & 15); }
+                        dc[c] += s;
+                        coef[0] = (int16_t)dc[c];
+                        for (int k = 1; k < 64; k++) {
+                            const int rs = huff_decode(&br, &ji.ac[ji.comp[c].ta]);
+                            const int r = rs >> 4, sz = rs & 15;
+                            if (sz) {
+                                k += r;
+                                const int v = br_get(&br, sz);
+                                if (k > 63) break;
+                                coef[jpeg_natural_order[k]] = (int16_t)HUFF_EXTEND(v, sz);
+                            } else {
+                                if (r != 15) break;
+                                k += 15;
+                            }
+                        }
+                        const int X = (mcx * ji.comp[c].h + bx) * 8, Y = (mcy * ji.comp[c].v + by) * 8;
+                        idct_islow(coef, ji.quant[ji.comp[c].tq], planes[c] + (size_t)Y * stride + X, stride, 8, 8);
+                    }
+            }
+        }
+        p = q;
+        if (p + 1 < end && p[0] == 0xFF) {
+            while (p < end && *p == 0xFF) p++;
+            if (p < end) p++;
+        }
+    }
+    return ORC_JPEG_OK;
+}
+
+static uint8_t clamp255(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+
+/* one upsampled chroma sample at output position (x, y); cw x ch = the component's real (downsampled) size */
+static int chroma_at(const uint8_t* pl, int stride, int cw, int ch, int x, int y, int hs, int vs)
+{
+    if (hs == 1 && vs == 1) return pl[(size_t)y * stride + x];
+    const int cx = x >> 1;
+    if (vs == 1) {                                  /* h2v1_fancy_upsample */
+        const uint8_t* r = pl + (size_t)y * stride;
+        if (x & 1) return cx == cw - 1 ? r[cx] : (3 * r[cx] + r[cx + 1] + 2) >> 2;
+        return cx == 0 ? r[0] : (3 * r[cx] + r[cx - 1] + 1) >> 2;
+    }
+    /* h2v2_fancy_upsample: the nearer row weighs 3, the row above (even output rows) or below (odd) 1; then the same across */
+    const int cy = y >> 1;
+    int oy = (y & 1) ? cy + 1 : cy - 1;
+    if (oy < 0) oy = 0;
+    if (oy > ch - 1) oy = ch - 1;
+    const uint8_t* r0 = pl + (size_t)cy * stride;
+    const uint8_t* r1 = pl + (size_t)oy * stride;
+    const int cur = 3 * r0[cx] + r1[cx];
+    if (x & 1) {
+        if (cx == cw - 1) return (cur * 4 + 7) >> 4;
+        return (3 * cur + 3 * r0[cx + 1] + r1[cx + 1] + 7) >> 4;
+    }
+    if (cx == 0) return (cur * 4 + 8) >> 4;
+    return (3 * cur + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
+}
+
+/* out: height rows of `stride` bytes, 3 bytes (B, G, R) per pixel */
+int orc_jpeg_decode_bgr(const uint8_t* file, size_t size, uint8_t* out, int stride)
+{
+    jpeg_cinfo ji;
+    int rc = jpeg_parse_colour(file, size, &ji);
+    if (rc) return rc;
+    int32_t info[12];
+    orc_jpeg_probe_colour(file, size, info);
+    uint8_t* pl[3];
+    for (int c = 0; c < 3; c++) pl[c] = (uint8_t*)malloc((size_t)info[5 + 2 * c] * info[6 + 2 * c]);
+    rc = orc_jpeg_decode_planes(file, size, pl[0], pl[1], pl[2]);
+    if (!rc) {
+        const int hs = ji.comp[0].h, vs = ji.comp[0].v;
+        const int cw = (ji.width + hs - 1) / hs, ch = (ji.height + vs - 1) / vs;
+        for (int y = 0; y < ji.height; y++)
+            for (int x = 0; x < ji.width; x++) {
+                const int Y = pl[0][(size_t)y * info[5] + x];
+                const int cb = chroma_at(pl[1], info[7], cw, ch, x, y, hs, vs) - 128, cr = chroma_at(pl[2], info[9], cw, ch, x, y, hs, vs) - 128;
+                /* jdcolor.c build_ycc_rgb_table: FIX(x) = x * 65536 + 0.5 */
+                const int r = Y + ((91881 * cr + 32768) >> 16);
+                const int b = Y + ((116130 * cb + 32768) >> 16);
+                const int g = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+                uint8_t* o = out + (size_t)y * stride + 3 * x;
+                o[0] = clamp255(b); o[1] = clamp255(g); o[2] = clamp255(r);
+            }
+    }
+    for (int c = 0; c < 3; c++) free(pl[c]);
+    return rc;
+}

@@ -33,7 +33,7 @@ def test_golden_files_decode_to_cv2s_pixels():
 
 def test_unsupported_and_damaged_files_are_refused():
     dec = JpegDecoder()
-    for k in ("refuse_progressive_file", "refuse_colour_file"):
+    for k in ("refuse_progressive_file", "refuse_411_file"):
         with pytest.raises(OrbxError) as e:
             dec.decode([G[k].tobytes()])
         assert e.value.status == _lib.E_UNSUPPORTED

@@ -22,11 +22,21 @@ def test_every_golden_file_decodes_to_cv2s_pixels():
     assert seen_rst == 18          # three of the five settings carry restart markers
 
 
+def test_colour_files_decode_to_cv2s_pixels():
+    assert len(G["colour_names"]) == 16
+    for k in G["colour_names"]:
+        assert np.array_equal(oracle.jpeg_decode_bgr(G[k + "_file"].tobytes()), G[k + "_pixels"]), k
+
+
 def test_unsupported_files_are_refused_not_guessed():
-    for k in ("refuse_progressive_file", "refuse_colour_file"):
-        with pytest.raises(ValueError) as e:
-            oracle.jpeg_probe(G[k].tobytes())
-        assert e.value.args[0] == oracle.JPEG_UNSUPPORTED
+    for k in ("refuse_progressive_file", "refuse_411_file"):
+        for fn in (oracle.jpeg_probe, oracle.jpeg_decode_bgr):
+            with pytest.raises(ValueError) as e:
+                fn(G[k].tobytes())
+            assert e.value.args[0] == oracle.JPEG_UNSUPPORTED
+    with pytest.raises(ValueError) as e:
+        oracle.jpeg_probe(G["bgr71_420q90_file"].tobytes())          # the grey-scale entry point refuses a colour file
+    assert e.value.args[0] == oracle.JPEG_UNSUPPORTED
     with pytest.raises(ValueError) as e:
         oracle.jpeg_probe(b"\x89PNG\r\n\x1a\n" + bytes(64))
     assert e.value.args[0] == oracle.JPEG_CORRUPT

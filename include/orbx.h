@@ -474,21 +474,24 @@ ORBX_API int bowx_score_batch_dev(bowx_handle h, const uint32_t* d_qwords, const
                                   const int32_t* d_db_count, const uint32_t* d_db_words, const double* d_db_vals, int nentries,
                                   double* d_scores);
 
-/* ------------------------------------------------------------------ frame ingest: grey-scale baseline JPEG files
+/* ------------------------------------------------------------------ frame ingest: baseline JPEG files
  * The reference reads every frame with cv::imread(path, CV_LOAD_IMAGE_UNCHANGED) (src/FrameLoader.cpp:62); for a .jpg that is
  * libjpeg behind OpenCV (default DCT method JDCT_ISLOW).  This family decodes a whole batch of such files on the GPU, straight
  * into the device-resident frames orbx_extract_batch_dev reads, bit for bit what cv2.imdecode returns (tests/golden/
- * jpeg_cases.npz): only the compressed bytes cross PCIe.  Handled: one component, 8 bits, Huffman, baseline or extended
- * sequential (SOF0 / SOF1), any quantisation / Huffman tables, with or without restart markers (both decode in parallel:
- * self-synchronising subsequences inside every restart interval).  Everything else -- colour, progressive, arithmetic,
- * 12-bit -- returns ORBX_E_UNSUPPORTED and the caller keeps its CPU decoder for that file; damaged headers ORBX_E_INVALID. */
+ * jpeg_cases.npz): only the compressed bytes cross PCIe.  Handled: 8 bits, Huffman, baseline or extended sequential (SOF0 /
+ * SOF1), one component (grey: one byte per pixel) or three (YCbCr with 4:2:0, 4:2:2 or 4:4:4 sampling, one interleaved scan:
+ * B, G, R bytes per pixel as imread returns them -- libjpeg's fancy chroma upsampling and fixed-point colour conversion), any
+ * quantisation / Huffman tables, with or without restart markers (both decode in parallel: self-synchronising subsequences
+ * inside every restart interval).  Everything else -- progressive, arithmetic, 12-bit, other samplings, CMYK -- returns
+ * ORBX_E_UNSUPPORTED and the caller keeps its CPU decoder for that file; damaged headers ORBX_E_INVALID. */
 typedef struct jpgx_context* jpgx_handle;
 ORBX_API int jpgx_create(jpgx_handle* out, int device);
 ORBX_API int jpgx_destroy(jpgx_handle h);
 ORBX_API int jpgx_set_stream(jpgx_handle h, void* cuda_stream);    /* same rules as hamx_set_stream */
 ORBX_API int jpgx_get_stream(jpgx_handle h, void** cuda_stream);
 ORBX_API int jpgx_synchronize(jpgx_handle h);
-/* Headers only (no GPU work): info[4] = {width, height, restart interval in 8x8 blocks (0: none), 8x8 blocks}. */
+/* Headers only (no GPU work): info[6] = {width, height, restart interval in MCUs (0: none), 8x8 blocks, components (1 or 3),
+ * luma sampling h*16 + v (0x11 for grey)}. */
 ORBX_API int jpgx_probe(const uint8_t* file, size_t size, int32_t* info);
 /* nfiles encoded files in host memory, all w x h, into device frames: frame i at d_frames + i*frame_pitch, rows `stride` bytes
  * apart.  The files are copied before the call returns; the decode is asynchronous on the handle's stream. */
@@ -497,6 +500,13 @@ ORBX_API int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* fil
 /* the same into host memory (blocking) */
 ORBX_API int jpgx_decode_gray_batch(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int h_, uint8_t* frames,
                                     size_t frame_pitch, size_t stride);
+/* three-component files into BGR frames (3 bytes per pixel, rows `stride` >= 3 w bytes apart): what orbx_set_input_channels(h, 3)
+ * makes the extractor read.  All files of a batch share the chroma sampling.  A grey file here, or a colour file in the calls
+ * above, returns ORBX_E_UNSUPPORTED. */
+ORBX_API int jpgx_decode_bgr_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int h_,
+                                       uint8_t* d_frames, size_t frame_pitch, size_t stride);
+ORBX_API int jpgx_decode_bgr_batch(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int h_, uint8_t* frames,
+                                   size_t frame_pitch, size_t stride);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,7 @@ SYMBOLS = [
     "bowx_stop_words", "bowx_parent_node", "bowx_word_weight", "bowx_transform_features", "bowx_transform_features_dev",
     "bowx_transform_batch", "bowx_transform_batch_dev", "bowx_score", "bowx_score_batch", "bowx_score_batch_dev",
     "jpgx_create", "jpgx_destroy", "jpgx_set_stream", "jpgx_get_stream", "jpgx_synchronize", "jpgx_probe", "jpgx_decode_gray_batch_dev",
-    "jpgx_decode_gray_batch",
+    "jpgx_decode_gray_batch", "jpgx_decode_bgr_batch_dev", "jpgx_decode_bgr_batch",
 ]
 NSTAGES = 5
 STAGE_NAMES = ("pyramid", "fast", "select", "harris_select", "orient_describe")
@@ -131,6 +131,8 @@ def lib():
     L.jpgx_probe.argtypes = [vp, C.c_size_t, i32p]
     L.jpgx_decode_gray_batch_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t]
     L.jpgx_decode_gray_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t]
+    L.jpgx_decode_bgr_batch_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t]
+    L.jpgx_decode_bgr_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t]
     L.bowx_create.argtypes = [C.POINTER(vp), C.c_int]
     L.bowx_destroy.argtypes = [vp]
     L.bowx_set_stream.argtypes = [vp, vp]

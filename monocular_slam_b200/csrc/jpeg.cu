@@ -34,7 +34,7 @@ constexpr int JP_LOOK = 10;                       // lookahead bits of the Huffm
 constexpr int JP_HUFF_THREADS = 128;
 constexpr int JP_IDCT_THREADS = 128;
 constexpr uint32_t JP_SUB_BITS = 1024;            // bits of an interval one lane decodes in the self-synchronising path
-constexpr uint32_t JP_MAX_INTERVAL_BITS = 1u << 26;    // exit states pack the bit position into 26 bits
+constexpr uint32_t JP_MAX_INTERVAL_BITS = 0xfffff000u;  // bit positions are 32-bit
 
 struct JpHuff {                                   // one Huffman table on the device
     uint16_t look[1 << JP_LOOK];                  // (length << 8) | symbol for codes of at most JP_LOOK bits, 0: longer
@@ -42,14 +42,33 @@ struct JpHuff {                                   // one Huffman table on the de
     int32_t valoff[17];                           // valptr[l] - mincode[l]
     uint8_t vals[256];
 };
-struct JpTables {                                 // what one file's scan needs
-    JpHuff dc, ac;
-    uint16_t quant[64];                           // natural order
+struct JpTables {                                 // what one file's scan needs, per component (a grey file uses entry 0)
+    JpHuff dc[3], ac[3];
+    uint16_t quant[3][64];                        // natural order
 };
+constexpr int JP_MAX_SLOTS = 6;                   // blocks of an MCU: 1 (grey), 3 (4:4:4), 4 (4:2:2), 6 (4:2:0)
+struct JpGeom {                                   // the same for every file of a batch
+    int ncomp, bpm;                               // components; blocks per MCU
+    int mcus_x;                                   // MCUs per row
+    int slot_comp[JP_MAX_SLOTS], slot_bx[JP_MAX_SLOTS], slot_by[JP_MAX_SLOTS];   // block s of an MCU: its component and place in it
+    int comp_h[3], comp_v[3];                     // sampling factors (blocks of the component per MCU, across and down)
+    int comp_bw[3];                               // blocks per row of the component's plane
+    uint32_t comp_off[3];                         // first block of the plane in a file's coefficient array
+    uint32_t blocks_per_file;                     // all planes
+};
+// where block number s of the scan (MCU by MCU, the blocks of an MCU in T.81 A.2.3 order) lives in the file's coefficient array
+__device__ __forceinline__ uint32_t jp_dest(const JpGeom& g, uint32_t s)
+{
+    if (g.bpm == 1) return s;
+    const uint32_t mcu = s / (uint32_t)g.bpm, slot = s - mcu * (uint32_t)g.bpm;
+    const uint32_t my = mcu / (uint32_t)g.mcus_x, mx = mcu - my * (uint32_t)g.mcus_x;
+    const int c = g.slot_comp[slot];
+    return g.comp_off[c] + (my * g.comp_v[c] + g.slot_by[slot]) * g.comp_bw[c] + mx * g.comp_h[c] + g.slot_bx[slot];
+}
 struct JpInterval {
     uint32_t src, src_len;                        // bytes of the interval in the uploaded stream
     uint32_t scratch;                             // byte offset of its stripped copy (multiple of 4)
-    uint32_t first_block, nblocks;                // blocks of its file, raster order
+    uint32_t first_block, nblocks;                // blocks of its file, in scan order (whole MCUs)
     uint32_t file;
     uint32_t first_sub, nsub;                     // its subsequences of JP_SUB_BITS bits (the self-synchronising path)
 };
@@ -121,16 +140,59 @@ k_jpeg_unstuff(const uint8_t* __restrict__ stream, const JpInterval* __restrict_
     if (lane == 0) nwords_out[it] = nwords;
 }
 
+// ---- the decoder proper.  State = (bit position, block of the MCU, coefficient index); decodes from `state` up to bit `end`.
+// WRITE: stores coefficients, `blk` being the scan-order number of the block the state is in and dc0..2 the DC predictors.
+__device__ __forceinline__ unsigned long long jp_state(uint32_t pos, int slot, int k) { return ((unsigned long long)pos << 16) | ((unsigned)slot << 8) | (unsigned)k; }
+
+template <bool WRITE>
+__device__ __forceinline__ unsigned long long jp_run(JpBits& b, const JpTables* __restrict__ tb, const JpGeom& g, const uint8_t* s_natural,
+                                                     unsigned long long state, uint32_t end, int& nblk, int& dc0, int& dc1, int& dc2,
+                                                     int16_t* coefs_file, uint32_t blk, uint32_t blocks_left)
+{
+    int k = (int)(state & 255), slot = (int)((state >> 8) & 255);
+    b.seek((uint32_t)(state >> 16));
+    int c = g.slot_comp[slot];
+    int16_t* co = WRITE ? coefs_file + (size_t)jp_dest(g, blk) * 64 : nullptr;
+    while (b.pos() < end && (!WRITE || blocks_left)) {
+        // one refill per symbol: at least 33 bits are buffered, a code takes at most 16 and its value bits at most 16
+        b.fill();
+        const bool is_dc = k == 0;
+        const int sym = jp_decode(b, is_dc ? &tb->dc[c] : &tb->ac[c]);
+        const int r = is_dc ? 0 : sym >> 4, sz = sym & 15;
+        int val = 0;
+        if (sz) val = jp_extend(b.get(sz), sz);
+        if (is_dc) {
+            int d = c == 0 ? dc0 : (c == 1 ? dc1 : dc2);
+            d += val;
+            if (c == 0) dc0 = d; else if (c == 1) dc1 = d; else dc2 = d;
+            if (WRITE && d) co[0] = (int16_t)d;
+            k = 1;
+        } else if (sz) {
+            k += r;
+            if (WRITE && k <= 63) co[s_natural[k]] = (int16_t)val;
+            k = k > 63 ? 64 : k + 1;              // (k > 63: corrupt data ends the block, as the reference's loop does)
+        } else {
+            k = r == 15 ? k + 16 : 64;            // ZRL, or end of block
+        }
+        if (k >= 64) {
+            k = 0; nblk++;
+            slot = slot + 1 == g.bpm ? 0 : slot + 1;
+            c = g.slot_comp[slot];
+            if (WRITE) { blk++; blocks_left--; co = coefs_file + (size_t)jp_dest(g, blk) * 64; }
+        }
+    }
+    return jp_state(b.pos(), slot, k);
+}
+
 // ---- K17b: one lane per interval runs the sequential decoder of T.81 F.2.2 over its stripped bytes.  The loop body decodes
 // one symbol -- a DC difference when the lane is at the start of a block, else an AC run/size -- so the 32 intervals of a
 // warp execute the same instructions whatever their data; only the rare codes longer than JP_LOOK bits diverge.
 __global__ void __launch_bounds__(JP_HUFF_THREADS)
 k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables,
-            const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, int16_t* __restrict__ coefs, uint32_t blocks_per_file,
-            int lane_step)
+            const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, int16_t* __restrict__ coefs, const JpGeom g, int lane_step)
 {
-    // every lane_step-th lane of a warp owns an interval: with few intervals (a row of blocks each, or whole files) spreading them
-    // over more warps costs issue slots but shortens every warp's memory gathers; with many, all 32 lanes work
+    // every lane_step-th lane of a warp owns an interval: with few intervals spreading them over more warps costs issue slots but
+    // shortens every warp's memory gathers; with many, all 32 lanes work
     __shared__ uint8_t s_natural[64];             // the lanes index it with different k: shared memory, not the constant cache
     if (threadIdx.x < 64) s_natural[threadIdx.x] = c_natural_order[threadIdx.x];
     __syncthreads();
@@ -139,32 +201,10 @@ k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTa
     const long long it = t / lane_step;
     if (it >= nintervals) return;
     const JpInterval iv = intervals[it];
-    const JpTables* tb = tables + file_tables[iv.file];
     JpBits b = {reinterpret_cast<const uint32_t*>(scratch + iv.scratch), nwords_in[it], 0, 0ull, 0};
-    int16_t* co = coefs + ((size_t)iv.file * blocks_per_file + iv.first_block) * 64;
-    int dc = 0, k = 0;
-    uint32_t blk = 0;
-    while (blk < iv.nblocks) {
-        // one refill per symbol: at least 33 bits are buffered, a code takes at most 16 and its value bits at most 16
-        b.fill();
-        const bool is_dc = k == 0;
-        const int sym = jp_decode(b, is_dc ? &tb->dc : &tb->ac);
-        const int r = is_dc ? 0 : sym >> 4, sz = sym & 15;
-        int val = 0;
-        if (sz) val = jp_extend(b.get(sz), sz);
-        if (is_dc) {
-            dc += val;
-            if (dc) co[0] = (int16_t)dc;
-            k = 1;
-        } else if (sz) {
-            k += r;
-            if (k <= 63) co[s_natural[k]] = (int16_t)val;
-            k = k > 63 ? 64 : k + 1;              // (k > 63: corrupt data ends the block, as the reference's loop does)
-        } else {
-            k = r == 15 ? k + 16 : 64;            // ZRL, or end of block
-        }
-        if (k >= 64) { k = 0; blk++; co += 64; }
-    }
+    int nblk = 0, dc0 = 0, dc1 = 0, dc2 = 0;
+    jp_run<true>(b, tables + file_tables[iv.file], g, s_natural, jp_state(0, 0, 0), 0xffffffffu, nblk, dc0, dc1, dc2,
+                 coefs + (size_t)iv.file * g.blocks_per_file * 64, iv.first_block, iv.nblocks);
 }
 
 // ---- K17c: the self-synchronising path for intervals longer than JP_SUB_BITS (whole files without restart markers, block rows):
@@ -176,38 +216,6 @@ k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTa
 // which nothing changes proves it has been reached.  The per-subsequence block counts and DC sums then tell every lane which
 // block and which DC value it starts with, and a last decode writes the coefficients.  (The idea of self-synchronising
 // subsequences is from A. Weissenberger and B. Schmidt, "Massively parallel Huffman decoding on GPUs", 2018.)
-__device__ __forceinline__ uint32_t jp_state(uint32_t pos, int k) { return (pos << 6) | (uint32_t)k; }
-
-// decodes from `state` up to bit `end`; WRITE: stores coefficients, starting at block `blk` with DC predictor `dc`
-template <bool WRITE>
-__device__ __forceinline__ uint32_t jp_run(JpBits& b, const JpTables* __restrict__ tb, const uint8_t* s_natural, uint32_t state, uint32_t end,
-                                           int& nblk, int& dcsum, int16_t* co, uint32_t blocks_left)
-{
-    int k = (int)(state & 63);
-    b.seek(state >> 6);
-    while (b.pos() < end && (!WRITE || blocks_left)) {
-        b.fill();
-        const bool is_dc = k == 0;
-        const int sym = jp_decode(b, is_dc ? &tb->dc : &tb->ac);
-        const int r = is_dc ? 0 : sym >> 4, sz = sym & 15;
-        int val = 0;
-        if (sz) val = jp_extend(b.get(sz), sz);
-        if (is_dc) {
-            dcsum += val;
-            if (WRITE && dcsum) co[0] = (int16_t)dcsum;
-            k = 1;
-        } else if (sz) {
-            k += r;
-            if (WRITE && k <= 63) co[s_natural[k]] = (int16_t)val;
-            k = k > 63 ? 64 : k + 1;
-        } else {
-            k = r == 15 ? k + 16 : 64;
-        }
-        if (k >= 64) { k = 0; nblk++; if (WRITE) { co += 64; blocks_left--; } }
-    }
-    return jp_state(b.pos(), k);
-}
-
 // One CTA per interval, its lanes striding over the interval's subsequences.  Round 0: every subsequence from its own first bit.
 // Rounds 1..: a subsequence whose predecessor's exit state is not the state it was last decoded from is decoded again.  A round
 // without a changed exit state ends the loop (at the latest after as many rounds as there are subsequences: a perfectly periodic
@@ -215,8 +223,9 @@ __device__ __forceinline__ uint32_t jp_run(JpBits& b, const JpTables* __restrict
 // and DC sums, and every lane decodes its subsequences once more, writing coefficients.
 __global__ void __launch_bounds__(1024)
 k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables,
-            const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, uint32_t* exit_state, uint32_t* used_state,
-            int32_t* sub_blocks, int32_t* sub_dcsum, int16_t* __restrict__ coefs, uint32_t blocks_per_file, uint32_t sub_bits)
+            const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, unsigned long long* exit_state,
+            unsigned long long* used_state, int32_t* sub_counts /* [nsubs][4]: blocks, DC sums of the components */, int16_t* __restrict__ coefs,
+            const JpGeom g, uint32_t sub_bits)
 {
     __shared__ uint8_t s_natural[64];
     __shared__ int s_changed;
@@ -225,26 +234,26 @@ k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict
     const JpTables* tb = tables + file_tables[iv.file];
     const uint32_t nwords = nwords_in[blockIdx.x], total = nwords * 32u;
     const uint32_t* words = reinterpret_cast<const uint32_t*>(scratch + iv.scratch);
-    volatile uint32_t* ex = exit_state + iv.first_sub;
-    uint32_t* used = used_state + iv.first_sub;
-    int32_t* nb = sub_blocks + iv.first_sub;
-    int32_t* ds = sub_dcsum + iv.first_sub;
+    volatile unsigned long long* ex = exit_state + iv.first_sub;
+    unsigned long long* used = used_state + iv.first_sub;
+    int4* cnt = reinterpret_cast<int4*>(sub_counts) + iv.first_sub;
     for (int round = 0;; round++) {
         if (threadIdx.x == 0) s_changed = 0;
         __syncthreads();
         bool mine = false;
         for (uint32_t j = threadIdx.x; j < iv.nsub; j += blockDim.x) {
-            uint32_t start;
-            if (round == 0) start = jp_state(j * sub_bits, 0);
+            unsigned long long start;
+            if (round == 0) start = jp_state(j * sub_bits, 0, 0);
             else {
                 if (j == 0) continue;              // started from the truth in round 0
                 start = ex[j - 1];
                 if (start == used[j]) continue;
             }
             JpBits b = {words, nwords, 0, 0ull, 0};
-            int nblk = 0, dcsum = 0;
-            const uint32_t e = jp_run<false>(b, tb, nullptr, start, min((j + 1) * sub_bits, total), nblk, dcsum, nullptr, 0);
-            used[j] = start; nb[j] = nblk; ds[j] = dcsum;
+            int nblk = 0, d0 = 0, d1 = 0, d2 = 0;
+            const unsigned long long e = jp_run<false>(b, tb, g, nullptr, start, min((j + 1) * sub_bits, total), nblk, d0, d1, d2, nullptr, 0, 0);
+            used[j] = start;
+            cnt[j] = make_int4(nblk, d0, d1, d2);
             if (round == 0 || e != ex[j]) { ex[j] = e; mine = true; }
         }
         if (mine && round) s_changed = 1;
@@ -252,26 +261,27 @@ k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict
         if (round && !s_changed) break;
         __syncthreads();
     }
-    // first block and DC predictor of every subsequence: an exclusive prefix sum, in place
+    // first block and DC predictors of every subsequence: an exclusive prefix sum, in place
     if (threadIdx.x == 0) {
-        int blk = 0, dc = 0;
+        int4 run = make_int4(0, 0, 0, 0);
         for (uint32_t j = 0; j < iv.nsub; j++) {
-            const int n = nb[j], d = ds[j];
-            nb[j] = blk; ds[j] = dc;
-            blk += n; dc += d;
+            const int4 v = cnt[j];
+            cnt[j] = run;
+            run.x += v.x; run.y += v.y; run.z += v.z; run.w += v.w;
         }
     }
     __syncthreads();
     for (uint32_t j = threadIdx.x; j < iv.nsub; j += blockDim.x) {
-        const uint32_t first = (uint32_t)nb[j];
+        const int4 at = cnt[j];
+        const uint32_t first = (uint32_t)at.x;
         if (first >= iv.nblocks) continue;
         JpBits b = {words, nwords, 0, 0ull, 0};
-        int nblk = 0, dc = ds[j];
+        int nblk = 0, d0 = at.y, d1 = at.z, d2 = at.w;
         // the lane that reaches the end of the data goes on over zero bits until the interval's blocks are complete, as libjpeg
         // (and the sequential kernel) do with a truncated file
         const uint32_t end = (j + 1) * sub_bits >= total ? 0xffffffffu : (j + 1) * sub_bits;
-        jp_run<true>(b, tb, s_natural, j ? ex[j - 1] : jp_state(0, 0), end, nblk, dc,
-                     coefs + ((size_t)iv.file * blocks_per_file + iv.first_block + first) * 64, iv.nblocks - first);
+        jp_run<true>(b, tb, g, s_natural, j ? ex[j - 1] : jp_state(0, 0, 0), end, nblk, d0, d1, d2, coefs + (size_t)iv.file * g.blocks_per_file * 64,
+                     iv.first_block + first, iv.nblocks - first);
     }
 }
 
@@ -319,65 +329,127 @@ __device__ __forceinline__ uint32_t jp_range_limit(int x)
     return x < 128 ? x + 128 : (x < 512 ? 255 : (x < 896 ? 0 : x - 896));
 }
 
+struct JpOut {                                    // where the planes go: the caller's frames (grey) or the internal planes (colour)
+    uint8_t* base[3]; size_t pitch[3], stride[3];
+    int cw[3], ch[3];                             // samples to write (the image size for grey frames, whole blocks for internal planes)
+};
+
 __global__ void __launch_bounds__(JP_IDCT_THREADS)
-k_jpeg_idct(const int16_t* __restrict__ coefs, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables, int nfiles, int w, int h,
-            int bw, uint32_t blocks_per_file, uint8_t* __restrict__ frames, size_t frame_pitch, size_t stride)
+k_jpeg_idct(const int16_t* __restrict__ coefs, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables, int nfiles, const JpGeom g,
+            const JpOut o)
 {
     const uint32_t blk = blockIdx.x * JP_IDCT_THREADS + threadIdx.x;
     const int file = blockIdx.y;
-    if (blk >= blocks_per_file || file >= nfiles) return;
-    const uint16_t* q = tables[file_tables[file]].quant;
-    const uint4* cp = reinterpret_cast<const uint4*>(coefs + ((size_t)file * blocks_per_file + blk) * 64);
+    if (blk >= g.blocks_per_file || file >= nfiles) return;
+    const int c = g.ncomp == 1 || blk < g.comp_off[1] ? 0 : (blk < g.comp_off[2] ? 1 : 2);
+    const uint16_t* q = tables[file_tables[file]].quant[c];
+    const uint4* cp = reinterpret_cast<const uint4*>(coefs + ((size_t)file * g.blocks_per_file + blk) * 64);
     int ws[64];
 #pragma unroll
     for (int r = 0; r < 8; r++) {                 // dequantise (row r of the block)
         const uint4 v = __ldg(cp + r);
         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const int coef = (int)(short)((c & 1) ? (u[c >> 1] >> 16) : (u[c >> 1] & 0xffff));
-            ws[r * 8 + c] = coef * (int)__ldg(q + r * 8 + c);
+        for (int cc = 0; cc < 8; cc++) {
+            const int coef = (int)(short)((cc & 1) ? (u[cc >> 1] >> 16) : (u[cc >> 1] & 0xffff));
+            ws[r * 8 + cc] = coef * (int)__ldg(q + r * 8 + cc);
         }
     }
 #pragma unroll
-    for (int c = 0; c < 8; c++) {                 // pass 1: columns
-        int in[8], o[8];
+    for (int cc = 0; cc < 8; cc++) {              // pass 1: columns
+        int in[8], ov[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) in[r] = ws[r * 8 + c];
-        jp_idct8(in, o);
+        for (int r = 0; r < 8; r++) in[r] = ws[r * 8 + cc];
+        jp_idct8(in, ov);
 #pragma unroll
-        for (int r = 0; r < 8; r++) ws[r * 8 + c] = (o[r] + (1 << 10)) >> 11;
+        for (int r = 0; r < 8; r++) ws[r * 8 + cc] = (ov[r] + (1 << 10)) >> 11;
     }
-    const int bx = (int)(blk % (uint32_t)bw), by = (int)(blk / (uint32_t)bw);
-    uint8_t* out = frames + (size_t)file * frame_pitch + (size_t)by * 8 * stride + (size_t)bx * 8;
-    const int cols = min(8, w - bx * 8), rows = min(8, h - by * 8);
-    const bool aligned = cols == 8 && ((reinterpret_cast<uintptr_t>(out) | stride) & 7) == 0;
+    const uint32_t i = blk - g.comp_off[c];
+    const int bx = (int)(i % (uint32_t)g.comp_bw[c]), by = (int)(i / (uint32_t)g.comp_bw[c]);
+    uint8_t* out = o.base[c] + (size_t)file * o.pitch[c] + (size_t)by * 8 * o.stride[c] + (size_t)bx * 8;
+    const int cols = min(8, o.cw[c] - bx * 8), rows = min(8, o.ch[c] - by * 8);
+    const bool aligned = cols == 8 && ((reinterpret_cast<uintptr_t>(out) | o.stride[c]) & 7) == 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) {                 // pass 2: rows
-        int o[8];
-        jp_idct8(ws + r * 8, o);
+        int ov[8];
+        jp_idct8(ws + r * 8, ov);
         uint32_t px[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) px[c] = jp_range_limit((o[c] + (1 << 17)) >> 18);
+        for (int cc = 0; cc < 8; cc++) px[cc] = jp_range_limit((ov[cc] + (1 << 17)) >> 18);
         if (r < rows) {
-            uint8_t* row = out + (size_t)r * stride;
+            uint8_t* row = out + (size_t)r * o.stride[c];
             if (aligned) {
                 *reinterpret_cast<uint2*>(row) = make_uint2(px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24), px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24));
             } else {
 #pragma unroll
-                for (int c = 0; c < 8; c++)
-                    if (c < cols) row[c] = (uint8_t)px[c];
+                for (int cc = 0; cc < 8; cc++)
+                    if (cc < cols) row[cc] = (uint8_t)px[cc];
             }
         }
+    }
+}
+
+// ---- K19: chroma upsampling (jdsample.c h2v2_fancy_upsample / h2v1_fancy_upsample) and YCbCr -> BGR (jdcolor.c
+// ycc_rgb_convert, 16-bit fixed point) for four pixels of a row per thread
+__device__ __forceinline__ int jp_chroma(const uint8_t* __restrict__ pl, int stride, int cw, int ch, int x, int y, int hs, int vs)
+{
+    if (hs == 1) return pl[(size_t)y * stride + x];
+    const int cx = x >> 1;
+    if (vs == 1) {
+        const uint8_t* r = pl + (size_t)y * stride;
+        if (x & 1) return cx == cw - 1 ? r[cx] : (3 * r[cx] + r[cx + 1] + 2) >> 2;
+        return cx == 0 ? r[0] : (3 * r[cx] + r[cx - 1] + 1) >> 2;
+    }
+    // the nearer row weighs 3, the row above (even output rows) or below (odd) 1 -- the first / last real row at the edges --
+    // then the same across
+    const int cy = y >> 1;
+    const int oy = min(max((y & 1) ? cy + 1 : cy - 1, 0), ch - 1);
+    const uint8_t* r0 = pl + (size_t)cy * stride;
+    const uint8_t* r1 = pl + (size_t)oy * stride;
+    const int cur = 3 * r0[cx] + r1[cx];
+    if (x & 1) return cx == cw - 1 ? (cur * 4 + 7) >> 4 : (3 * cur + 3 * r0[cx + 1] + r1[cx + 1] + 7) >> 4;
+    return cx == 0 ? (cur * 4 + 8) >> 4 : (3 * cur + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
+}
+
+__global__ void __launch_bounds__(256)
+k_jpeg_ycc(const uint8_t* __restrict__ planes, size_t planes_pitch, size_t off1, size_t off2, int stride0, int stride1, int w, int h, int hs, int vs,
+           uint8_t* __restrict__ frames, size_t frame_pitch, size_t stride)
+{
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4, y = blockIdx.y, file = blockIdx.z;
+    if (x0 >= w) return;
+    const uint8_t* p0 = planes + (size_t)file * planes_pitch;
+    const uint8_t* p1 = p0 + off1;
+    const uint8_t* p2 = p0 + off2;
+    const int cw = (w + hs - 1) / hs, ch = (h + vs - 1) / vs;
+    uint8_t bgr[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = min(x0 + i, w - 1);
+        const int Y = p0[(size_t)y * stride0 + x];
+        const int cb = jp_chroma(p1, stride1, cw, ch, x, y, hs, vs) - 128, cr = jp_chroma(p2, stride1, cw, ch, x, y, hs, vs) - 128;
+        const int r = Y + ((91881 * cr + 32768) >> 16);           // FIX(1.40200), ONE_HALF
+        const int b = Y + ((116130 * cb + 32768) >> 16);          // FIX(1.77200)
+        const int gg = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);   // FIX(0.34414), FIX(0.71414)
+        bgr[3 * i] = (uint8_t)min(max(b, 0), 255); bgr[3 * i + 1] = (uint8_t)min(max(gg, 0), 255); bgr[3 * i + 2] = (uint8_t)min(max(r, 0), 255);
+    }
+    uint8_t* out = frames + (size_t)file * frame_pitch + (size_t)y * stride + (size_t)x0 * 3;
+    if (x0 + 4 <= w && ((reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+        o32[0] = bgr[0] | (bgr[1] << 8) | (bgr[2] << 16) | ((uint32_t)bgr[3] << 24);
+        o32[1] = bgr[4] | (bgr[5] << 8) | (bgr[6] << 16) | ((uint32_t)bgr[7] << 24);
+        o32[2] = bgr[8] | (bgr[9] << 8) | (bgr[10] << 16) | ((uint32_t)bgr[11] << 24);
+    } else {
+        for (int i = 0; i < 12 && x0 + i / 3 < w; i++) out[i] = bgr[i];
     }
 }
 
 // ---- host: marker parsing
 struct HostHuff { bool present; uint8_t bits[17]; uint8_t vals[256]; };
 struct HostFile {
-    int width, height, restart;
-    uint16_t quant[64];
-    HostHuff dc, ac;
+    int width, height, restart;                   // restart interval in MCUs
+    int ncomp, hs, vs;                            // components; luma sampling factors (chroma is 1x1)
+    uint16_t quant[3][64];                        // per component
+    HostHuff dc[3], ac[3];
     size_t scan, scan_len;                        // entropy-coded segment
 };
 
@@ -411,7 +483,7 @@ static int parse_jpeg(const uint8_t* f, size_t n, HostFile& out, const char** wh
     bool have_quant[4] = {false, false, false, false}, have_sof = false;
     HostHuff dc[4], ac[4];
     for (int i = 0; i < 4; i++) dc[i].present = ac[i].present = false;
-    int tq = 0;
+    int tq[3] = {0, 0, 0}, cid[3] = {0, 0, 0};
     out.restart = 0;
     size_t p = 2;
     for (;;) {
@@ -431,9 +503,19 @@ static int parse_jpeg(const uint8_t* f, size_t n, HostFile& out, const char** wh
             if (s[0] != 8) JP_FAIL(ORBX_E_UNSUPPORTED, "sample precision is not 8 bits");
             out.height = (s[1] << 8) | s[2];
             out.width = (s[3] << 8) | s[4];
-            if (s[5] != 1) JP_FAIL(ORBX_E_UNSUPPORTED, "not a one-component (grey-scale) file");
-            if (sl < 9 || out.width == 0 || out.height == 0) JP_FAIL(ORBX_E_INVALID, "bad SOF");
-            tq = s[8] & 3;
+            out.ncomp = s[5];
+            if (out.ncomp != 1 && out.ncomp != 3) JP_FAIL(ORBX_E_UNSUPPORTED, "neither a grey-scale nor a three-component file");
+            if (sl < (size_t)(6 + 3 * out.ncomp) || out.width == 0 || out.height == 0) JP_FAIL(ORBX_E_INVALID, "bad SOF");
+            for (int c = 0; c < out.ncomp; c++) {
+                cid[c] = s[6 + 3 * c];
+                tq[c] = s[8 + 3 * c] & 3;
+                const int hh_ = s[7 + 3 * c] >> 4, vv_ = s[7 + 3 * c] & 15;
+                if (c == 0) { out.hs = hh_; out.vs = vv_; }
+                else if (hh_ != 1 || vv_ != 1) JP_FAIL(ORBX_E_UNSUPPORTED, "chroma sampling other than 1x1");
+            }
+            if (out.ncomp == 1) out.hs = out.vs = 1;       // a single-component scan is not interleaved: one block per MCU
+            else if (!((out.hs == 2 && out.vs == 2) || (out.hs == 2 && out.vs == 1) || (out.hs == 1 && out.vs == 1)))
+                JP_FAIL(ORBX_E_UNSUPPORTED, "luma sampling other than 2x2, 2x1 or 1x1");
             have_sof = true;
         } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
             JP_FAIL(ORBX_E_UNSUPPORTED, "progressive, lossless, hierarchical or arithmetic-coded file");
@@ -472,12 +554,17 @@ static int parse_jpeg(const uint8_t* f, size_t n, HostFile& out, const char** wh
             out.restart = (s[0] << 8) | s[1];
         } else if (m == 0xDA) {
             if (!have_sof) JP_FAIL(ORBX_E_INVALID, "scan before the frame header");
-            if (sl < 6 || s[0] != 1) JP_FAIL(ORBX_E_UNSUPPORTED, "scan of several components");
-            const int td = s[2] >> 4, ta = s[2] & 15;
-            if (s[3] != 0 || s[4] != 63 || s[5] != 0) JP_FAIL(ORBX_E_UNSUPPORTED, "not a sequential scan");
-            if (td > 3 || ta > 3 || !dc[td].present || !ac[ta].present || !have_quant[tq]) JP_FAIL(ORBX_E_INVALID, "scan refers to a missing table");
-            out.dc = dc[td]; out.ac = ac[ta];
-            memcpy(out.quant, quant[tq], sizeof(out.quant));
+            if (sl < (size_t)(4 + 2 * out.ncomp) || s[0] != out.ncomp) JP_FAIL(ORBX_E_UNSUPPORTED, "a scan that does not hold every component");
+            const uint8_t* e = s + 1 + 2 * out.ncomp;
+            if (e[0] != 0 || e[1] != 63 || e[2] != 0) JP_FAIL(ORBX_E_UNSUPPORTED, "not a sequential scan");
+            for (int c = 0; c < out.ncomp; c++) {
+                if (s[1 + 2 * c] != cid[c]) JP_FAIL(ORBX_E_UNSUPPORTED, "scan components out of frame order");
+                const int td = s[2 + 2 * c] >> 4, ta = s[2 + 2 * c] & 15;
+                if (td > 3 || ta > 3 || !dc[td].present || !ac[ta].present || !have_quant[tq[c]]) JP_FAIL(ORBX_E_INVALID, "scan refers to a missing table");
+                out.dc[c] = dc[td]; out.ac[c] = ac[ta];
+                memcpy(out.quant[c], quant[tq[c]], sizeof(out.quant[c]));
+            }
+            for (int c = out.ncomp; c < 3; c++) { out.dc[c] = out.dc[0]; out.ac[c] = out.ac[0]; memcpy(out.quant[c], out.quant[0], sizeof(out.quant[c])); }
             out.scan = p + len;
             out.scan_len = n - out.scan;
             return ORBX_OK;
@@ -513,7 +600,8 @@ struct jpgx_context {
     int next_set;
     uint8_t* d_scratch; size_t d_scratch_bytes;   // the same without stuffed bytes
     uint32_t* d_nwords; size_t d_nwords_bytes;    // 32-bit words of every interval's stripped copy
-    uint32_t* d_subw; size_t d_subw_bytes;        // per subsequence: exit state, state it was last decoded from, blocks, DC sum
+    unsigned long long* d_subw; size_t d_subw_bytes;   // per subsequence: exit state, state it was last decoded from, block count and DC sums
+    uint8_t* d_planes; size_t d_planes_bytes;     // colour files: the component planes before upsampling
     int16_t* d_coefs; size_t d_coefs_bytes;
     uint8_t* d_frames; size_t d_frames_bytes;     // staging of the host-output form
 };
@@ -559,7 +647,7 @@ extern "C" int jpgx_destroy(jpgx_handle h)
         if (S.decoded) cudaEventDestroy(S.decoded);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    cudaFree(h->d_scratch); cudaFree(h->d_nwords); cudaFree(h->d_subw);
+    cudaFree(h->d_scratch); cudaFree(h->d_nwords); cudaFree(h->d_subw); cudaFree(h->d_planes);
     cudaFree(h->d_coefs); cudaFree(h->d_frames);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -621,45 +709,80 @@ extern "C" int jpgx_probe(const uint8_t* file, size_t size, int32_t* info)
     const char* why = "";
     const int rc = parse_jpeg(file, size, hf, &why);
     if (rc) { set_error("jpgx_probe: %s", why); return rc; }
+    const int mx = (hf.width + 8 * hf.hs - 1) / (8 * hf.hs), my = (hf.height + 8 * hf.vs - 1) / (8 * hf.vs);
     info[0] = hf.width; info[1] = hf.height; info[2] = hf.restart;
-    info[3] = ((hf.width + 7) / 8) * ((hf.height + 7) / 8);
+    info[3] = mx * my * (hf.ncomp == 1 ? 1 : hf.hs * hf.vs + 2);
+    info[4] = hf.ncomp; info[5] = hf.hs * 16 + hf.vs;
     return ORBX_OK;
 }
 
-extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh,
-                                          uint8_t* d_frames, size_t frame_pitch, size_t stride)
+// ncomp: 1 = grey files into one-byte pixels, 3 = YCbCr files into BGR pixels
+static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh, uint8_t* d_frames,
+                            size_t frame_pitch, size_t stride, int ncomp)
 {
-    ORBX_REQUIRE(h != nullptr, "jpgx_decode_gray_batch_dev: NULL handle");
-    ORBX_REQUIRE(nfiles >= 0 && w >= 1 && hh >= 1 && w <= 65535 && hh <= 65535, "jpgx_decode_gray_batch_dev: nfiles %d / size %dx%d out of range", nfiles, w, hh);
+    ORBX_REQUIRE(h != nullptr, "jpgx_decode_batch: NULL handle");
+    ORBX_REQUIRE(nfiles >= 0 && w >= 1 && hh >= 1 && w <= 65535 && hh <= 65535, "jpgx_decode_batch: nfiles %d / size %dx%d out of range", nfiles, w, hh);
     if (nfiles == 0) return ORBX_OK;
-    ORBX_REQUIRE(files && sizes && d_frames, "jpgx_decode_gray_batch_dev: NULL pointer");
-    ORBX_REQUIRE(stride >= (size_t)w && frame_pitch >= stride * (size_t)(hh - 1) + (size_t)w, "jpgx_decode_gray_batch_dev: stride %zu / frame pitch %zu too small for %dx%d", stride, frame_pitch, w, hh);
+    ORBX_REQUIRE(files && sizes && d_frames, "jpgx_decode_batch: NULL pointer");
+    ORBX_REQUIRE(stride >= (size_t)w * ncomp && frame_pitch >= stride * (size_t)(hh - 1) + (size_t)w * ncomp, "jpgx_decode_batch: stride %zu / frame pitch %zu too small for %dx%d x %d", stride, frame_pitch, w, hh, ncomp);
     ORBX_CUDA(cudaSetDevice(h->device));
-    const int bw = (w + 7) / 8, bh = (hh + 7) / 8;
-    const uint32_t blocks = (uint32_t)bw * (uint32_t)bh;
     // this call's buffer set was last used two calls ago: its uploads must have left the pinned buffers before they are
     // overwritten (the device copy is protected in stream order, below)
     JpSet& S = h->set[h->next_set];
     h->next_set ^= 1;
     if (S.uploaded_pending) { ORBX_CUDA(cudaEventSynchronize(S.uploaded)); S.uploaded_pending = false; }
     // 1. headers: where every file's bytes, intervals and stripped copy go follows from them alone
+    JpGeom g;
+    memset(&g, 0, sizeof(g));
+    int mcus_y = 0;
+    uint32_t blocks = 0;
     std::vector<HostFile> hf((size_t)nfiles);
     std::vector<size_t> off((size_t)nfiles + 1, 0), first_iv((size_t)nfiles + 1, 0), scr((size_t)nfiles + 1, 0);
     for (int i = 0; i < nfiles; i++) {
-        ORBX_REQUIRE(files[i] != nullptr, "jpgx_decode_gray_batch_dev: file %d is NULL", i);
+        ORBX_REQUIRE(files[i] != nullptr, "jpgx_decode_batch: file %d is NULL", i);
         const char* why = "";
         const int rc = parse_jpeg(files[i], sizes[i], hf[(size_t)i], &why);
-        if (rc) { set_error("jpgx_decode_gray_batch_dev: file %d: %s", i, why); return rc; }
-        ORBX_REQUIRE(hf[(size_t)i].width == w && hf[(size_t)i].height == hh, "jpgx_decode_gray_batch_dev: file %d is %dx%d, the batch is %dx%d", i,
+        if (rc) { set_error("jpgx_decode_batch: file %d: %s", i, why); return rc; }
+        ORBX_REQUIRE(hf[(size_t)i].width == w && hf[(size_t)i].height == hh, "jpgx_decode_batch: file %d is %dx%d, the batch is %dx%d", i,
                      hf[(size_t)i].width, hf[(size_t)i].height, w, hh);
-        const uint32_t ri = hf[(size_t)i].restart ? (uint32_t)hf[(size_t)i].restart : blocks;
-        const size_t niv = (blocks + ri - 1) / ri;
+        if (hf[(size_t)i].ncomp != ncomp) {
+            set_error("jpgx_decode_batch: file %d has %d component(s); %s", i, hf[(size_t)i].ncomp,
+                      ncomp == 1 ? "colour files go through jpgx_decode_bgr_batch" : "grey-scale files go through jpgx_decode_gray_batch");
+            return ORBX_E_UNSUPPORTED;
+        }
+        ORBX_REQUIRE(hf[(size_t)i].hs == hf[0].hs && hf[(size_t)i].vs == hf[0].vs, "jpgx_decode_batch: file %d has another chroma sampling than file 0", i);
+        if (i == 0) {
+            // the geometry every file of the batch shares
+            const HostFile& f0 = hf[0];
+            g.ncomp = ncomp;
+            g.bpm = ncomp == 1 ? 1 : f0.hs * f0.vs + 2;
+            g.mcus_x = (w + 8 * f0.hs - 1) / (8 * f0.hs);
+            mcus_y = (hh + 8 * f0.vs - 1) / (8 * f0.vs);
+            int slot = 0;
+            uint32_t offb = 0;
+            for (int c = 0; c < 3; c++) {
+                g.comp_h[c] = c == 0 ? f0.hs : 1; g.comp_v[c] = c == 0 ? f0.vs : 1;
+                g.comp_bw[c] = g.mcus_x * g.comp_h[c];
+                g.comp_off[c] = offb;
+                if (c < ncomp) {
+                    offb += (uint32_t)g.comp_bw[c] * (uint32_t)(mcus_y * g.comp_v[c]);
+                    for (int by = 0; by < g.comp_v[c]; by++)
+                        for (int bx = 0; bx < g.comp_h[c]; bx++, slot++) { g.slot_comp[slot] = c; g.slot_bx[slot] = bx; g.slot_by[slot] = by; }
+                }
+            }
+            for (; slot < JP_MAX_SLOTS; slot++) { g.slot_comp[slot] = 0; g.slot_bx[slot] = g.slot_by[slot] = 0; }
+            g.blocks_per_file = offb;
+            blocks = (uint32_t)g.mcus_x * (uint32_t)mcus_y * (uint32_t)g.bpm;         // == offb
+        }
+        const uint32_t nmcus = blocks / (uint32_t)g.bpm;
+        const uint32_t ri = hf[(size_t)i].restart ? (uint32_t)hf[(size_t)i].restart : nmcus;
+        const size_t niv = (nmcus + ri - 1) / ri;
         off[(size_t)i + 1] = off[(size_t)i] + align_up(hf[(size_t)i].scan_len, 4);
         first_iv[(size_t)i + 1] = first_iv[(size_t)i] + niv;
         scr[(size_t)i + 1] = scr[(size_t)i] + align_up(hf[(size_t)i].scan_len, 4) + 12 * niv + 16;      // interval j at align4(its start) + 12 j
     }
     const size_t total = off[(size_t)nfiles], nint = first_iv[(size_t)nfiles];
-    ORBX_REQUIRE(scr[(size_t)nfiles] < (1ull << 32), "jpgx_decode_gray_batch_dev: %zu bytes of compressed data in one batch", total);
+    ORBX_REQUIRE(scr[(size_t)nfiles] < (1ull << 32), "jpgx_decode_batch: %zu bytes of compressed data in one batch", total);
     int rc = jp_grow_host(&S.h_stream, &S.h_stream_bytes, total + 64, true);
     if (!rc) rc = jp_grow_host(&S.h_intervals, &S.h_intervals_n, nint);
     if (!rc) rc = jp_grow_host(&S.h_file_tables, &S.h_file_tables_n, (size_t)nfiles);
@@ -678,15 +801,19 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         int set = -1;
         for (size_t s = 0; s < set_owner.size(); s++) {
             const HostFile& o = *set_owner[s];
-            if (!memcmp(o.quant, f.quant, sizeof(f.quant)) && !memcmp(o.dc.bits, f.dc.bits, 17) && !memcmp(o.dc.vals, f.dc.vals, 256) &&
-                !memcmp(o.ac.bits, f.ac.bits, 17) && !memcmp(o.ac.vals, f.ac.vals, 256)) { set = (int)s; break; }
+            bool same = !memcmp(o.quant, f.quant, sizeof(f.quant));
+            for (int c = 0; c < 3 && same; c++)
+                same = !memcmp(o.dc[c].bits, f.dc[c].bits, 17) && !memcmp(o.dc[c].vals, f.dc[c].vals, 256) && !memcmp(o.ac[c].bits, f.ac[c].bits, 17) &&
+                       !memcmp(o.ac[c].vals, f.ac[c].vals, 256);
+            if (same) { set = (int)s; break; }
         }
         if (set < 0) {
-            JpTables t;
-            if (!build_table(f.dc, t.dc) || !build_table(f.ac, t.ac)) { set_error("jpgx_decode_gray_batch_dev: file %d: over-subscribed Huffman table", i); return ORBX_E_INVALID; }
+            sets.emplace_back();
+            JpTables& t = sets.back();
+            for (int c = 0; c < 3; c++)
+                if (!build_table(f.dc[c], t.dc[c]) || !build_table(f.ac[c], t.ac[c])) { set_error("jpgx_decode_batch: file %d: over-subscribed Huffman table", i); return ORBX_E_INVALID; }
             memcpy(t.quant, f.quant, sizeof(t.quant));
-            set = (int)sets.size();
-            sets.push_back(t);
+            set = (int)sets.size() - 1;
             set_owner.push_back(&f);
         }
         S.h_file_tables[i] = set;
@@ -697,9 +824,10 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         const HostFile& f = hf[(size_t)i];
         const uint8_t* scan = files[i] + f.scan;
         memcpy(S.h_stream + off[(size_t)i], scan, f.scan_len);
-        const uint32_t ri = f.restart ? (uint32_t)f.restart : blocks;
+        const uint32_t nmcus = blocks / (uint32_t)g.bpm;
+        const uint32_t ri = f.restart ? (uint32_t)f.restart : nmcus;
         size_t p = 0, j = 0;
-        for (uint32_t b0 = 0; b0 < blocks; b0 += ri, j++) {
+        for (uint32_t m0 = 0; m0 < nmcus; m0 += ri, j++) {
             // the interval ends at the next marker: FF followed by anything but 00 (RSTn between intervals, EOI after the last)
             size_t q = p;
             for (;;) {
@@ -714,8 +842,8 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
             iv.src = (uint32_t)(off[(size_t)i] + p);
             iv.src_len = (uint32_t)(q - p);
             iv.scratch = (uint32_t)(scr[(size_t)i] + align_up(p, 4) + 12 * j);
-            iv.first_block = b0;
-            iv.nblocks = std::min(ri, blocks - b0);
+            iv.first_block = m0 * (uint32_t)g.bpm;
+            iv.nblocks = std::min(ri, nmcus - m0) * (uint32_t)g.bpm;
             iv.file = (uint32_t)i;
             p = q;
             if (p + 1 < f.scan_len) {              // skip the marker
@@ -751,12 +879,12 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
         iv.first_sub = (uint32_t)nsubs;
         nsubs += iv.nsub;
         max_nsub = std::max(max_nsub, iv.nsub);
-        packable = packable && (size_t)iv.src_len * 8 + 64 < JP_MAX_INTERVAL_BITS;
+        packable = packable && (size_t)iv.src_len * 8 + 64 < JP_MAX_INTERVAL_BITS;      // (bit positions are 32-bit)
     }
     // short intervals (a restart marker every few blocks) are decoded one lane each, sequentially: nothing to synchronise
     const bool sync_path = (size_t)longest * 8 > 4 * JP_SUB_BITS && packable;
     if (sync_path) {
-        rc = jp_grow(&h->d_subw, &h->d_subw_bytes, nsubs * 4 * sizeof(uint32_t));
+        rc = jp_grow(&h->d_subw, &h->d_subw_bytes, nsubs * 4 * sizeof(unsigned long long));
         if (rc) return rc;
     }
     if ((int)sets.size() > S.tables_cap) {
@@ -788,39 +916,85 @@ extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* f
     const unsigned seq_blocks = (unsigned)((ni * (size_t)lane_step + JP_HUFF_THREADS - 1) / JP_HUFF_THREADS);
     if (!sync_path) {
         k_jpeg_huff<<<seq_blocks, JP_HUFF_THREADS, 0, h->stream>>>(S.d_intervals, (int)ni, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords,
-                                                                  h->d_coefs, blocks, lane_step);
+                                                                  h->d_coefs, g, lane_step);
     } else {
         const unsigned threads = std::min(1024u, (max_nsub + 31u) / 32u * 32u);
-        k_jpeg_sync<<<(unsigned)ni, threads, 0, h->stream>>>(S.d_intervals, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, h->d_subw,
-                                                            h->d_subw + nsubs, (int32_t*)(h->d_subw + 2 * nsubs), (int32_t*)(h->d_subw + 3 * nsubs),
-                                                            h->d_coefs, blocks, sub_bits);
+        unsigned long long* st = h->d_subw;       // [nsubs] exit states, [nsubs] states decoded from, [nsubs][4] counts
+        k_jpeg_sync<<<(unsigned)ni, threads, 0, h->stream>>>(S.d_intervals, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, st, st + nsubs,
+                                                            (int32_t*)(st + 2 * nsubs), h->d_coefs, g, sub_bits);
     }
     ORBX_CUDA(cudaGetLastError());
+    JpOut o;
+    memset(&o, 0, sizeof(o));
+    size_t plane_off[3] = {0, 0, 0}, planes_pitch = 0;
+    if (ncomp == 1) {
+        o.base[0] = d_frames; o.pitch[0] = frame_pitch; o.stride[0] = stride; o.cw[0] = w; o.ch[0] = hh;
+    } else {
+        // the component planes, whole blocks each, one set per file
+        for (int c = 0; c < 3; c++) {
+            plane_off[c] = planes_pitch;
+            o.stride[c] = (size_t)g.comp_bw[c] * 8;
+            o.cw[c] = g.comp_bw[c] * 8; o.ch[c] = mcus_y * g.comp_v[c] * 8;
+            planes_pitch += o.stride[c] * (size_t)o.ch[c];
+        }
+        rc = jp_grow(&h->d_planes, &h->d_planes_bytes, planes_pitch * (size_t)nfiles);
+        if (rc) return rc;
+        for (int c = 0; c < 3; c++) { o.base[c] = h->d_planes + plane_off[c]; o.pitch[c] = planes_pitch; }
+    }
     k_jpeg_idct<<<dim3((blocks + JP_IDCT_THREADS - 1) / JP_IDCT_THREADS, (unsigned)nfiles), JP_IDCT_THREADS, 0, h->stream>>>(
-        h->d_coefs, S.d_tables, S.d_file_tables, nfiles, w, hh, bw, blocks, d_frames, frame_pitch, stride);
+        h->d_coefs, S.d_tables, S.d_file_tables, nfiles, g, o);
     ORBX_CUDA(cudaGetLastError());
+    if (ncomp == 3) {
+        k_jpeg_ycc<<<dim3((unsigned)((w + 1023) / 1024), (unsigned)hh, (unsigned)nfiles), 256, 0, h->stream>>>(
+            h->d_planes, planes_pitch, plane_off[1], plane_off[2], (int)o.stride[0], (int)o.stride[1], w, hh, hf[0].hs, hf[0].vs, d_frames, frame_pitch, stride);
+        ORBX_CUDA(cudaGetLastError());
+    }
     ORBX_CUDA(cudaEventRecord(S.decoded, h->stream));
     S.decoded_pending = true;
+    return ORBX_OK;
+}
+
+extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh,
+                                          uint8_t* d_frames, size_t frame_pitch, size_t stride)
+{
+    return decode_batch_dev(h, files, sizes, nfiles, w, hh, d_frames, frame_pitch, stride, 1);
+}
+
+extern "C" int jpgx_decode_bgr_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh,
+                                         uint8_t* d_frames, size_t frame_pitch, size_t stride)
+{
+    return decode_batch_dev(h, files, sizes, nfiles, w, hh, d_frames, frame_pitch, stride, 3);
+}
+
+static int decode_batch_host(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh, uint8_t* frames,
+                             size_t frame_pitch, size_t stride, int ncomp)
+{
+    ORBX_REQUIRE(h != nullptr, "jpgx_decode_batch: NULL handle");
+    ORBX_REQUIRE(nfiles >= 0 && w >= 1 && hh >= 1, "jpgx_decode_batch: nfiles %d / size %dx%d out of range", nfiles, w, hh);
+    if (nfiles == 0) return ORBX_OK;
+    ORBX_REQUIRE(frames != nullptr, "jpgx_decode_batch: NULL pointer");
+    ORBX_REQUIRE(stride >= (size_t)w * ncomp && frame_pitch >= stride * (size_t)(hh - 1) + (size_t)w * ncomp, "jpgx_decode_batch: stride %zu / frame pitch %zu too small for %dx%d x %d", stride, frame_pitch, w, hh, ncomp);
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const size_t dpitch = align_up((size_t)w * ncomp, 16), dframe = dpitch * (size_t)hh;
+    int rc = jp_grow(&h->d_frames, &h->d_frames_bytes, dframe * (size_t)nfiles);
+    if (rc) return rc;
+    rc = decode_batch_dev(h, files, sizes, nfiles, w, hh, h->d_frames, dframe, dpitch, ncomp);
+    if (rc) return rc;
+    for (int i = 0; i < nfiles; i++)
+        ORBX_CUDA(cudaMemcpy2DAsync(frames + (size_t)i * frame_pitch, stride, h->d_frames + (size_t)i * dframe, dpitch, (size_t)w * ncomp, (size_t)hh,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
     return ORBX_OK;
 }
 
 extern "C" int jpgx_decode_gray_batch(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh, uint8_t* frames,
                                       size_t frame_pitch, size_t stride)
 {
-    ORBX_REQUIRE(h != nullptr, "jpgx_decode_gray_batch: NULL handle");
-    ORBX_REQUIRE(nfiles >= 0 && w >= 1 && hh >= 1, "jpgx_decode_gray_batch: nfiles %d / size %dx%d out of range", nfiles, w, hh);
-    if (nfiles == 0) return ORBX_OK;
-    ORBX_REQUIRE(frames != nullptr, "jpgx_decode_gray_batch: NULL pointer");
-    ORBX_REQUIRE(stride >= (size_t)w && frame_pitch >= stride * (size_t)(hh - 1) + (size_t)w, "jpgx_decode_gray_batch: stride %zu / frame pitch %zu too small for %dx%d", stride, frame_pitch, w, hh);
-    ORBX_CUDA(cudaSetDevice(h->device));
-    const size_t dpitch = align_up((size_t)w, 16), dframe = dpitch * (size_t)hh;
-    int rc = jp_grow(&h->d_frames, &h->d_frames_bytes, dframe * (size_t)nfiles);
-    if (rc) return rc;
-    rc = jpgx_decode_gray_batch_dev(h, files, sizes, nfiles, w, hh, h->d_frames, dframe, dpitch);
-    if (rc) return rc;
-    for (int i = 0; i < nfiles; i++)
-        ORBX_CUDA(cudaMemcpy2DAsync(frames + (size_t)i * frame_pitch, stride, h->d_frames + (size_t)i * dframe, dpitch, (size_t)w, (size_t)hh,
-                                    cudaMemcpyDeviceToHost, h->stream));
-    ORBX_CUDA(cudaStreamSynchronize(h->stream));
-    return ORBX_OK;
+    return decode_batch_host(h, files, sizes, nfiles, w, hh, frames, frame_pitch, stride, 1);
+}
+
+extern "C" int jpgx_decode_bgr_batch(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh, uint8_t* frames,
+                                     size_t frame_pitch, size_t stride)
+{
+    return decode_batch_host(h, files, sizes, nfiles, w, hh, frames, frame_pitch, stride, 3);
 }

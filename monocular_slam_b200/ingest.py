@@ -41,10 +41,11 @@ def imread_unchanged(source):
 
 
 class JpegDecoder:
-    """Grey-scale baseline JPEG files decoded on the GPU (include/orbx.h "jpgx_*"): the pixels cv2.imdecode / the reference's
-    imread would return, for a whole batch at once.  ``decode(files)`` returns host frames; ``decode_dev(files, w, h, d_frames,
-    frame_pitch, stride)`` writes device frames (asynchronous on the handle's stream) for ORB.extract_batch_dev.  A file of
-    another kind raises OrbxError with status E_UNSUPPORTED -- decode that one with ``imread_unchanged``."""
+    """Baseline JPEG files decoded on the GPU (include/orbx.h "jpgx_*"): the pixels cv2.imdecode / the reference's imread would
+    return, for a whole batch at once -- grey files as [h][w], YCbCr files (4:2:0, 4:2:2, 4:4:4) as [h][w][3] BGR.
+    ``decode(files)`` returns host frames; ``decode_dev(files, w, h, d_frames, frame_pitch, stride, channels)`` writes device
+    frames (asynchronous on the handle's stream) for ORB.extract_batch_dev.  A file of another kind raises OrbxError with status
+    E_UNSUPPORTED -- decode that one with ``imread_unchanged``."""
 
     def __init__(self, device=0):
         self._h = C.c_void_p()
@@ -70,9 +71,10 @@ class JpegDecoder:
 
     @staticmethod
     def probe(data):
-        """(width, height, restart interval in blocks, blocks) from the headers; raises OrbxError for files this decoder refuses."""
+        """(width, height, restart interval in MCUs, blocks, components, luma sampling h*16+v) from the headers; raises OrbxError
+        for files this decoder refuses."""
         buf = (C.c_uint8 * len(data)).from_buffer_copy(bytes(data))
-        info = (C.c_int32 * 4)()
+        info = (C.c_int32 * 6)()
         check(_lib.lib().jpgx_probe(buf, len(data), info))
         return tuple(info)
 
@@ -83,19 +85,21 @@ class JpegDecoder:
         sizes = (C.c_size_t * len(keep))(*[k.size for k in keep])
         return keep, ptrs, sizes
 
-    def decode_dev(self, files, w, h, d_frames_ptr, frame_pitch, stride):
+    def decode_dev(self, files, w, h, d_frames_ptr, frame_pitch, stride, channels=1):
         keep, ptrs, sizes = self._args(files)
-        check(_lib.lib().jpgx_decode_gray_batch_dev(self._h, ptrs, sizes, len(keep), int(w), int(h), d_frames_ptr, int(frame_pitch), int(stride)))
+        fn = _lib.lib().jpgx_decode_gray_batch_dev if channels == 1 else _lib.lib().jpgx_decode_bgr_batch_dev
+        check(fn(self._h, ptrs, sizes, len(keep), int(w), int(h), d_frames_ptr, int(frame_pitch), int(stride)))
 
     def decode(self, files, out=None):
         files = list(files)
         if not files:
             return np.zeros((0, 0, 0), np.uint8)
-        w, h, _, _ = self.probe(files[0])
+        w, h, _, _, ncomp, _ = self.probe(files[0])
         if out is None:
-            out = np.zeros((len(files), h, w), np.uint8)
+            out = np.zeros((len(files), h, w) if ncomp == 1 else (len(files), h, w, 3), np.uint8)
         keep, ptrs, sizes = self._args(files)
-        check(_lib.lib().jpgx_decode_gray_batch(self._h, ptrs, sizes, len(keep), w, h, out.ctypes.data_as(C.c_void_p), h * w, w))
+        fn = _lib.lib().jpgx_decode_gray_batch if ncomp == 1 else _lib.lib().jpgx_decode_bgr_batch
+        check(fn(self._h, ptrs, sizes, len(keep), w, h, out.ctypes.data_as(C.c_void_p), h * w * ncomp, w * ncomp))
         return out
 
 

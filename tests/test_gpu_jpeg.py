@@ -31,6 +31,61 @@ def test_golden_files_decode_to_cv2s_pixels():
     dec.close()
 
 
+def test_golden_colour_files_decode_to_cv2s_pixels():
+    dec = JpegDecoder()
+    for k in G["colour_names"]:
+        f, ref = G[k + "_file"].tobytes(), G[k + "_pixels"]
+        assert dec.probe(f)[4] == 3
+        got = dec.decode([f, f])                           # a batch of two
+        assert got.shape == (2,) + ref.shape
+        assert np.array_equal(got[0], ref) and np.array_equal(got[1], ref), k
+        assert np.array_equal(got[0], oracle.jpeg_decode_bgr(f))
+    # grey and colour files do not mix in a call
+    with pytest.raises(OrbxError) as e:
+        dec.decode([G["bgr71_420q90_file"].tobytes(), G["tex333_q90_file"].tobytes()])
+    assert e.value.status in (_lib.E_UNSUPPORTED, _lib.E_INVALID)
+    dec.close()
+
+
+@pytest.mark.parametrize("sampling", ["420", "422", "444"])
+def test_colour_frames_feed_the_extractor_as_bgr(sampling):
+    """1080p-class colour files with and without restart markers: BGR frames identical to cv2's, and ORB on them (three input
+    channels, gray conversion on the device) identical to ORB on cv2's frames."""
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    W, H, B = 1001, 701, 2
+    frames = [syn.bgr_frame(30 + i, W, H) for i in range(B)]
+    sf = {"420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444}[sampling]
+    dec = JpegDecoder()
+    for rst in (0, 9):
+        params = [cv2.IMWRITE_JPEG_QUALITY, 88, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else [])
+        files = [cv2.imencode(".jpg", f, params)[1].tobytes() for f in frames]
+        ref = np.stack([cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED) for f in files])
+        got = dec.decode(files)
+        assert np.array_equal(got, ref), (sampling, rst)
+    orb = ORB(nfeatures=400, max_size=(W, H), max_batch=B)
+    orb.set_input_channels(3)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        orb.set_stream(stream.cuda_stream); dec.set_stream(stream.cuda_stream)
+        cap = orb.default_cap
+        d_frames = torch.zeros((B, H, W, 3), dtype=torch.uint8, device="cuda")
+        d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device="cuda"); d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+        dec.decode_dev(files, W, H, d_frames.data_ptr(), W * H * 3, W * 3, channels=3)
+        orb.extract_batch_dev(d_frames.data_ptr(), W * H * 3, B, W, H, W * 3, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
+        orb.check_dev()
+        stream.synchronize()
+    assert np.array_equal(d_frames.cpu().numpy(), ref)
+    orb.set_stream(0)
+    kps, desc, counts = orb.extract_batch(list(ref))
+    cnt = d_cnt.cpu().numpy()
+    assert np.array_equal(cnt, counts) and cnt.min() > 100
+    for f in range(B):
+        assert np.array_equal(d_desc[f, :cnt[f]].cpu().numpy(), desc[f, :cnt[f]])
+    dec.close(); orb.close()
+
+
 def test_unsupported_and_damaged_files_are_refused():
     dec = JpegDecoder()
     for k in ("refuse_progressive_file", "refuse_411_file"):
@@ -57,7 +112,7 @@ def test_larger_frames_match_the_oracle_and_feed_the_extractor(w, h, rst, qualit
     params = [cv2.IMWRITE_JPEG_QUALITY, quality] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else [])
     files = [cv2.imencode(".jpg", f, params)[1].tobytes() for f in frames]
     dec = JpegDecoder()
-    assert dec.probe(files[0])[:3] == (w, h, rst)
+    assert dec.probe(files[0])[:3] == (w, h, rst) and dec.probe(files[0])[4:] == (1, 0x11)
     got = dec.decode(files)
     for i, f in enumerate(files):
         assert np.array_equal(got[i], oracle.jpeg_decode_gray(f)), i

@@ -1,9 +1,10 @@
-// jpeg.cu -- frame ingest for grey-scale baseline JPEG files (sm_100a): what cv::imread does for the reference's frame loader
+// jpeg.cu -- frame ingest for baseline JPEG files, grey-scale and YCbCr colour (sm_100a): what cv::imread does for the reference's frame loader
 // (src/FrameLoader.cpp:62, imread(path, CV_LOAD_IMAGE_UNCHANGED); for .jpg that is libjpeg behind OpenCV, JDCT_ISLOW), for a
 // whole batch of files at once and straight into the device-resident frames the extractor reads.  Only the compressed bytes
 // cross PCIe (a fifth of the raw frames at quality 90).
 //
-//   host      marker parsing (ITU-T T.81 Annex B): DQT, SOF0/1, DHT, DRI, SOS of a one-component 8-bit Huffman file; the
+//   host      marker parsing (ITU-T T.81 Annex B): DQT, SOF0/1, DHT, DRI, SOS of an 8-bit Huffman file with one component or
+//             three (YCbCr 4:2:0 / 4:2:2 / 4:4:4, one interleaved scan); the
 //             entropy-coded segment is cut at its restart markers into intervals (T.81 E.2.4) -- the unit of parallelism
 //   K17 k_jpeg_unstuff, k_jpeg_sync / k_jpeg_huff   a warp per restart interval strips the stuffed zero bytes (FF 00 -> FF) into
 //             a scratch copy; the Huffman decoder of T.81 F.2.2 (10-bit lookahead tables, the DC predictor restarting with the
@@ -13,12 +14,12 @@
 //             of each 8x8 block are scattered into a zeroed array
 //   K18 k_jpeg_idct   one thread per block: dequantisation and libjpeg's jpeg_idct_islow (jidctint.c: 13-bit constants, two
 //             passes, DESCALE) in registers, the range-limit table of jdmaster.c as arithmetic, 8-byte row stores that
-//             coalesce across the blocks of a block row
+//             coalesce across the blocks of a block row; for colour files into whole-block Y / Cb / Cr planes
+//   K19 k_jpeg_ycc    colour files: libjpeg's fancy chroma upsampling (jdsample.c) and fixed-point YCbCr -> RGB (jdcolor.c), BGR out
 //
 // Bit-exact with cv2.imdecode (libjpeg-turbo 3.1.2) on every file of tests/golden/jpeg_cases.npz, with and without restart
-// markers.  Anything but one-component baseline / extended
-// sequential Huffman (progressive, colour, 12-bit, arithmetic) is refused with ORBX_E_UNSUPPORTED: the caller keeps its CPU
-// decoder for those.
+// markers, grey and colour.  Anything else (progressive, 12-bit, arithmetic, other samplings) is refused with
+// ORBX_E_UNSUPPORTED: the caller keeps its CPU decoder for those.
 #include <string.h>
 #include <algorithm>
 #include <atomic>
@@ -395,6 +396,8 @@ __device__ __forceinline__ int jp_chroma(const uint8_t* __restrict__ pl, int str
 {
     if (hs == 1) return pl[(size_t)y * stride + x];
     const int cx = x >> 1;
+    // jdsample.c jinit_upsampler: the fancy filters only for components more than two samples wide, replication below that
+    if (cw <= 2) return pl[(size_t)(vs == 2 ? y >> 1 : y) * stride + cx];
     if (vs == 1) {
         const uint8_t* r = pl + (size_t)y * stride;
         if (x & 1) return cx == cw - 1 ? r[cx] : (3 * r[cx] + r[cx + 1] + 2) >> 2;

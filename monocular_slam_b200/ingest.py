@@ -182,7 +182,7 @@ class IngestRing:
 
 
 class JpegIngest:
-    """Grey-scale JPEG files -> features, with the entropy decoder on the GPU: compressed bytes over PCIe -> ``JpegDecoder`` on its
+    """JPEG files (grey, or colour with ``channels=3``) -> features, with the entropy decoder on the GPU: compressed bytes over PCIe -> ``JpegDecoder`` on its
     own stream -> ``ORB.extract_batch_dev`` + consecutive-frame matching on the extractor's stream -> results in pinned host
     memory.  Two frame buffers: batch k+1 is decoded while batch k is extracted.  torch supplies the device buffers, streams and
     events (plumbing only).  A batch holding a file the decoder refuses (colour, progressive ...) raises OrbxError with status
@@ -192,11 +192,12 @@ class JpegIngest:
     overwritten two batches later.  While it runs the extractor and the matcher work on this object's stream; afterwards they are
     back on their own."""
 
-    def __init__(self, orb, matcher, width, height, batch=None, ratio=0.8):
+    def __init__(self, orb, matcher, width, height, batch=None, ratio=0.8, channels=1):
         import torch
         self.torch = torch
         self.orb, self.matcher, self.ratio = orb, matcher, float(ratio)
-        self.w, self.h = int(width), int(height)
+        self.w, self.h, self.ch = int(width), int(height), int(channels)
+        orb.set_input_channels(self.ch)
         self.batch = int(batch or orb.max_batch)
         dev = torch.device("cuda", orb.device)
         self.dev = dev
@@ -205,7 +206,7 @@ class JpegIngest:
         self.dec.set_stream(self.s_dec.cuda_stream)
         cap = self.cap = orb.default_cap
         B = self.batch
-        self.frames = [torch.zeros((B, self.h, self.w), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.frames = [torch.zeros((B, self.h, self.w * self.ch), dtype=torch.uint8, device=dev) for _ in range(2)]
         self.d = [{"kps": torch.empty((B, cap, 7), dtype=torch.float32, device=dev), "desc": torch.empty((B, cap, 32), dtype=torch.uint8, device=dev),
                    "cnt": torch.zeros(B, dtype=torch.int32, device=dev), "good": torch.empty((B, cap, 4), dtype=torch.int32, device=dev),
                    "ngood": torch.zeros(B, dtype=torch.int64, device=dev)} for _ in range(2)]
@@ -242,12 +243,12 @@ class JpegIngest:
                 if len(pending) == 2:
                     yield collect()                          # frees buffer set b
                 self.s_dec.wait_event(self.ev_ext[b])
-                self.dec.decode_dev(files[first:first + n], self.w, self.h, self.frames[b].data_ptr(), self.w * self.h, self.w)
+                self.dec.decode_dev(files[first:first + n], self.w, self.h, self.frames[b].data_ptr(), self.w * self.h * self.ch, self.w * self.ch, self.ch)
                 self.ev_dec[b].record(self.s_dec)
                 d, h = self.d[b], self.hst[b]
                 with torch.cuda.stream(self.s_orb):
                     self.s_orb.wait_event(self.ev_dec[b])
-                    orb.extract_batch_dev(self.frames[b].data_ptr(), self.w * self.h, n, self.w, self.h, self.w, d["kps"].data_ptr(), d["desc"].data_ptr(),
+                    orb.extract_batch_dev(self.frames[b].data_ptr(), self.w * self.h * self.ch, n, self.w, self.h, self.w * self.ch, d["kps"].data_ptr(), d["desc"].data_ptr(),
                                           cap, d["cnt"].data_ptr())
                     self.ev_ext[b].record(self.s_orb)
                     m.match_consecutive_dev(d["desc"].data_ptr(), d["cnt"].data_ptr(), n, cap, self.prev_desc.data_ptr() if have_prev else 0,

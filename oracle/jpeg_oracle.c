@@ -503,6 +503,9 @@ static int chroma_at(const uint8_t* pl, int stride, int cw, int ch, int x, int y
 {
     if (hs == 1 && vs == 1) return pl[(size_t)y * stride + x];
     const int cx = x >> 1;
+    /* jdsample.c jinit_upsampler: the fancy filters are chosen only for components more than two samples wide; narrower
+     * ones are replicated (h2v1_upsample / h2v2_upsample) */
+    if (cw <= 2) return pl[(size_t)(vs == 2 ? y >> 1 : y) * stride + cx];
     if (vs == 1) {                                  /* h2v1_fancy_upsample */
         const uint8_t* r = pl + (size_t)y * stride;
         if (x & 1) return cx == cw - 1 ? r[cx] : (3 * r[cx] + r[cx + 1] + 2) >> 2;

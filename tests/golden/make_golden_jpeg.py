@@ -55,7 +55,8 @@ def main():
     # restart intervals counted in MCUs
     cnames = []
     colour = {"bgr71": syn.bgr_frame(5, 71, 53), "bgr16": syn.bgr_frame(6, 16, 16), "bgr1": syn.bgr_frame(7, 16, 16)[:1, :1].copy(),
-              "noise33": rng.integers(0, 256, (33, 47, 3), dtype=np.uint8)}
+              "noise33": rng.integers(0, 256, (33, 47, 3), dtype=np.uint8),
+              "narrow3": rng.integers(0, 256, (21, 3, 3), dtype=np.uint8)}     # chroma two samples wide: libjpeg replicates instead of filtering
     csettings = {"420q90": [cv2.IMWRITE_JPEG_QUALITY, 90], "420q30rst3": [cv2.IMWRITE_JPEG_QUALITY, 30, cv2.IMWRITE_JPEG_RST_INTERVAL, 3],
                  "422q85rst1": [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_RST_INTERVAL, 1],
                  "444q100opt": [cv2.IMWRITE_JPEG_QUALITY, 100, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_OPTIMIZE, 1]}

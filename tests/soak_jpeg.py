@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Random soak of the GPU JPEG decoder against cv2.imdecode (run by hand on a GPU box that has cv2; not collected by pytest):
-random sizes, qualities 1-100, restart intervals, optimised tables, image kinds; single files and batches.
+random sizes, qualities 1-100, restart intervals, optimised tables, image kinds, grey and colour (4:2:0 / 4:2:2 / 4:4:4); single
+files and batches.
 Usage: python tests/soak_jpeg.py [cases] [seed]"""
 import os
 import sys
@@ -41,17 +42,23 @@ def main():
         w, h = (int(rng.integers(300, 2000)), int(rng.integers(300, 1200))) if big else (int(rng.integers(1, 300)), int(rng.integers(1, 300)))
         n = int(rng.integers(1, 5))
         files, refs = [], []
+        colour = rng.random() < 0.4
+        samp = int(rng.choice([cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]))
         for _ in range(n):
             q = int(rng.integers(1, 101))
             rst = int(rng.choice([0, 0, 1, 2, 5, max(1, (w + 7) // 8), 100, 1000]))
             params = [cv2.IMWRITE_JPEG_QUALITY, q] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else []) + \
                      ([cv2.IMWRITE_JPEG_OPTIMIZE, 1] if rng.random() < 0.3 else [])
-            f = cv2.imencode(".jpg", image(rng, w, h), params)[1].tobytes()
+            img = image(rng, w, h)
+            if colour:                                   # three different planes; one sampling per batch
+                img = np.stack([img, image(rng, w, h), np.roll(img, 3, axis=1)], -1)
+                params = params + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, samp]
+            f = cv2.imencode(".jpg", img, params)[1].tobytes()
             files.append(f)
             refs.append(cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED))
         got = dec.decode(files)
         for i in range(n):
-            if not np.array_equal(got[i], refs[i]) or (c % 10 == 0 and not np.array_equal(oracle.jpeg_decode_gray(files[i]), refs[i])):
+            if not np.array_equal(got[i], refs[i]) or (c % 10 == 0 and not np.array_equal((oracle.jpeg_decode_bgr if colour else oracle.jpeg_decode_gray)(files[i]), refs[i])):
                 bad += 1
                 print("case %d file %d (%dx%d): MISMATCH (%d pixels)" % (c, i, w, h, int((got[i] != refs[i]).sum())))
     dec.close()

@@ -23,7 +23,7 @@ def test_every_golden_file_decodes_to_cv2s_pixels():
 
 
 def test_colour_files_decode_to_cv2s_pixels():
-    assert len(G["colour_names"]) == 16
+    assert len(G["colour_names"]) == 20
     for k in G["colour_names"]:
         assert np.array_equal(oracle.jpeg_decode_bgr(G[k + "_file"].tobytes()), G[k + "_pixels"]), k
 

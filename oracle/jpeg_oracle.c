@@ -1,4 +1,5 @@
-/* CPU restatement of the decoder behind the reference's frame loader for grey-scale baseline JPEG files.
+/* CPU restatement of the decoder behind the reference's frame loader for baseline JPEG files (grey-scale first; YCbCr colour in
+ * the second half of this file).
  *
  * TEST INFRASTRUCTURE ONLY (see orb_oracle.c).  The reference reads every frame with cv::imread (src/FrameLoader.cpp:62); for
  * .jpg files that is OpenCV's JPEG decoder, i.e. libjpeg -- a dependency that is neither in /root/reference nor vendored
@@ -13,8 +14,8 @@
  * and is pinned against cv2.imdecode(..., IMREAD_UNCHANGED) on the committed files of tests/golden/jpeg_cases.npz
  * (tests/golden/make_golden_jpeg.py; tests/test_oracle_jpeg.py: every pixel equal).
  *
- * Anything else (progressive, arithmetic coding, 12-bit, several components) returns ORC_JPEG_UNSUPPORTED: the caller keeps
- * using its CPU decoder for those files. */
+ * Anything else (progressive, arithmetic coding, 12-bit, samplings other than 4:2:0 / 4:2:2 / 4:4:4) returns
+ * ORC_JPEG_UNSUPPORTED: the caller keeps using its CPU decoder for those files. */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>

@@ -95,7 +95,6 @@ struct JpBits {
     __device__ __forceinline__ uint32_t pos() const { return wi * 32u - (uint32_t)nbits; }      // bits consumed so far
     __device__ __forceinline__ uint32_t peek16() const { return (uint32_t)(buf >> 48); }
     __device__ __forceinline__ void skip(int n) { buf <<= n; nbits -= n; }
-    __device__ __forceinline__ int get(int n) { const int v = (int)(buf >> (64 - n)); skip(n); return v; }     // 1 <= n <= 16
 };
 
 __device__ __forceinline__ int jp_decode(JpBits& b, const JpHuff* __restrict__ t)     // at least 16 bits buffered
@@ -110,7 +109,6 @@ __device__ __forceinline__ int jp_decode(JpBits& b, const JpHuff* __restrict__ t
     b.skip(16);
     return 0;                                     // no such code: corrupt data; libjpeg substitutes a zero, too
 }
-__device__ __forceinline__ int jp_extend(int x, int s) { return x < (1 << (s - 1)) ? x - (1 << s) + 1 : x; }
 
 // ---- K17a: one warp per interval copies it without the zero byte that follows every FF (T.81 B.1.1.5), pads the last word
 __global__ void __launch_bounds__(JP_HUFF_THREADS)
@@ -155,26 +153,28 @@ __device__ __forceinline__ unsigned long long jp_run(JpBits& b, const JpTables* 
     int c = g.slot_comp[slot];
     int16_t* co = WRITE ? coefs_file + (size_t)jp_dest(g, blk) * 64 : nullptr;
     while (b.pos() < end && (!WRITE || blocks_left)) {
-        // one refill per symbol: at least 33 bits are buffered, a code takes at most 16 and its value bits at most 16
+        // one refill per symbol: at least 33 bits are buffered, a code takes at most 16 and its value bits at most 15.  The body
+        // is written with selects, not branches: the lanes of a warp are at different places of different blocks
         b.fill();
         const bool is_dc = k == 0;
         const int sym = jp_decode(b, is_dc ? &tb->dc[c] : &tb->ac[c]);
         const int r = is_dc ? 0 : sym >> 4, sz = sym & 15;
-        int val = 0;
-        if (sz) val = jp_extend(b.get(sz), sz);
-        if (is_dc) {
-            int d = c == 0 ? dc0 : (c == 1 ? dc1 : dc2);
-            d += val;
-            if (c == 0) dc0 = d; else if (c == 1) dc1 = d; else dc2 = d;
-            if (WRITE && d) co[0] = (int16_t)d;
-            k = 1;
-        } else if (sz) {
-            k += r;
-            if (WRITE && k <= 63) co[s_natural[k]] = (int16_t)val;
-            k = k > 63 ? 64 : k + 1;              // (k > 63: corrupt data ends the block, as the reference's loop does)
-        } else {
-            k = r == 15 ? k + 16 : 64;            // ZRL, or end of block
+        const int raw = (int)(b.peek16() >> (16 - sz));                   // the sz bits after the code (0 for sz = 0)
+        b.skip(sz);
+        const int half = (1 << sz) >> 1;
+        const int val = raw < half ? raw - (1 << sz) + 1 : raw;         // HUFF_EXTEND; 0 for sz = 0
+        int d = c == 0 ? dc0 : (c == 1 ? dc1 : dc2);
+        d += is_dc ? val : 0;
+        dc0 = c == 0 ? d : dc0; dc1 = c == 1 ? d : dc1; dc2 = c == 2 ? d : dc2;
+        const int kk = k + r;                                             // the coefficient this symbol sets (AC with sz != 0)
+        if (WRITE) {
+            const int store = is_dc ? d : val;
+            const bool doit = is_dc ? d != 0 : (sz != 0 && kk <= 63);
+            if (doit) co[is_dc ? 0 : s_natural[kk & 63]] = (int16_t)store;
         }
+        // next coefficient index: after a DC 1; after a value kk + 1 (a run past 63 is corrupt data and ends the block, as the
+        // reference's loop does); ZRL skips 16; end of block
+        k = is_dc ? 1 : (sz ? (kk > 63 ? 64 : kk + 1) : (r == 15 ? k + 16 : 64));
         if (k >= 64) {
             k = 0; nblk++;
             slot = slot + 1 == g.bpm ? 0 : slot + 1;

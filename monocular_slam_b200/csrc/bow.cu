@@ -520,8 +520,17 @@ static int upload_weights(bowx_handle h)
     return ORBX_OK;
 }
 
+static int set_vocabulary(bowx_handle h, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* leaf,
+                          const uint8_t* desc, const double* weight);
+
 extern "C" int bowx_set_vocabulary(bowx_handle h, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent,
                                    const uint8_t* leaf, const uint8_t* desc, const double* weight)
+{
+    ORBX_NOTHROW(set_vocabulary(h, k, L, scoring, weighting, nnodes, parent, leaf, desc, weight))
+}
+
+static int set_vocabulary(bowx_handle h, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* leaf,
+                          const uint8_t* desc, const double* weight)
 {
     ORBX_REQUIRE(h != nullptr, "bowx_set_vocabulary: NULL handle");
     ORBX_REQUIRE(parent && leaf && desc && weight, "bowx_set_vocabulary: NULL pointer");

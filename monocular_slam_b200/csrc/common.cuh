@@ -1,6 +1,8 @@
 // common.cuh -- shared declarations of liborbx.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <exception>
+#include <new>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -33,6 +35,12 @@ void set_error(const char* fmt, ...);
             return ORBX_E_CUDA;                                                                  \
         }                                                                                        \
     } while (0)
+
+// Entry points whose host side allocates (std::vector, std::thread): no C++ exception may cross the C ABI.
+#define ORBX_NOTHROW(expr)                                                                                   \
+    try { return (expr); }                                                                                   \
+    catch (const std::bad_alloc&) { orbx::set_error("%s: out of host memory", __func__); return ORBX_E_ALLOC; } \
+    catch (const std::exception& e_) { orbx::set_error("%s: %s", __func__, e_.what()); return ORBX_E_INVALID; }
 
 #define ORBX_REQUIRE(cond, ...)            \
     do {                                   \

@@ -960,13 +960,13 @@ static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const si
 extern "C" int jpgx_decode_gray_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh,
                                           uint8_t* d_frames, size_t frame_pitch, size_t stride)
 {
-    return decode_batch_dev(h, files, sizes, nfiles, w, hh, d_frames, frame_pitch, stride, 1);
+    ORBX_NOTHROW(decode_batch_dev(h, files, sizes, nfiles, w, hh, d_frames, frame_pitch, stride, 1))
 }
 
 extern "C" int jpgx_decode_bgr_batch_dev(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh,
                                          uint8_t* d_frames, size_t frame_pitch, size_t stride)
 {
-    return decode_batch_dev(h, files, sizes, nfiles, w, hh, d_frames, frame_pitch, stride, 3);
+    ORBX_NOTHROW(decode_batch_dev(h, files, sizes, nfiles, w, hh, d_frames, frame_pitch, stride, 3))
 }
 
 static int decode_batch_host(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh, uint8_t* frames,
@@ -993,11 +993,11 @@ static int decode_batch_host(jpgx_handle h, const uint8_t* const* files, const s
 extern "C" int jpgx_decode_gray_batch(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh, uint8_t* frames,
                                       size_t frame_pitch, size_t stride)
 {
-    return decode_batch_host(h, files, sizes, nfiles, w, hh, frames, frame_pitch, stride, 1);
+    ORBX_NOTHROW(decode_batch_host(h, files, sizes, nfiles, w, hh, frames, frame_pitch, stride, 1))
 }
 
 extern "C" int jpgx_decode_bgr_batch(jpgx_handle h, const uint8_t* const* files, const size_t* sizes, int nfiles, int w, int hh, uint8_t* frames,
                                      size_t frame_pitch, size_t stride)
 {
-    return decode_batch_host(h, files, sizes, nfiles, w, hh, frames, frame_pitch, stride, 3);
+    ORBX_NOTHROW(decode_batch_host(h, files, sizes, nfiles, w, hh, frames, frame_pitch, stride, 3))
 }

@@ -376,6 +376,57 @@ static inline int TriangulateMultiplePointsFromTwoView(const std::vector<Point2d
 }
 #endif
 
+// ---- frame ingest: what FrameLoader's imread(path, CV_LOAD_IMAGE_UNCHANGED) (src/FrameLoader.cpp:62) returns for baseline JPEG
+// files, decoded on the GPU a batch at a time (jpgx_*): grey files as 1-channel matrices, YCbCr files as 3-channel BGR.
+class JpegDecoder {
+public:
+    explicit JpegDecoder(int device = 0) : h_(nullptr) { check(jpgx_create(&h_, device), "JpegDecoder"); }
+    ~JpegDecoder() { if (h_) jpgx_destroy(h_); }
+    JpegDecoder(const JpegDecoder&) = delete;
+    JpegDecoder& operator=(const JpegDecoder&) = delete;
+
+    // false for files the GPU path does not take (progressive, 12-bit, CMYK ...): keep imread for those
+    static bool supported(const std::vector<uint8_t>& file, int* width = nullptr, int* height = nullptr, int* channels = nullptr)
+    {
+        int32_t info[6];
+        if (jpgx_probe(file.data(), file.size(), info) != ORBX_OK) return false;
+        if (width) *width = info[0];
+        if (height) *height = info[1];
+        if (channels) *channels = info[4];
+        return true;
+    }
+    // all files of one size and kind; frames[i] is rows x cols x channels, 8 bits, as imread would have returned it
+    void decode(const std::vector<std::vector<uint8_t> >& files, std::vector<Mat>& frames)
+    {
+        frames.clear();
+        if (files.empty()) return;
+        int32_t info[6];
+        check(jpgx_probe(files[0].data(), files[0].size(), info), "JpegDecoder::decode");
+        const int w = info[0], h = info[1], ch = info[4];
+        std::vector<const uint8_t*> ptrs(files.size());
+        std::vector<size_t> sizes(files.size());
+        for (size_t i = 0; i < files.size(); i++) { ptrs[i] = files[i].data(); sizes[i] = files[i].size(); }
+        std::vector<uint8_t> raw(files.size() * (size_t)w * h * ch);
+        check((ch == 1 ? jpgx_decode_gray_batch : jpgx_decode_bgr_batch)(h_, ptrs.data(), sizes.data(), (int)files.size(), w, h, raw.data(),
+                                                                          (size_t)w * h * ch, (size_t)w * ch), "JpegDecoder::decode");
+        frames.resize(files.size());
+        for (size_t i = 0; i < files.size(); i++) {
+#ifdef ORBX_SHIM_USE_OPENCV
+            frames[i].create(h, w, ch == 1 ? CV_8UC1 : CV_8UC3);
+            for (int y = 0; y < h; y++) std::memcpy(frames[i].ptr(y), raw.data() + (i * h + y) * (size_t)w * ch, (size_t)w * ch);
+#else
+            frames[i].create(h, w * ch);
+            frames[i].cols = w; frames[i].nchannels = ch; frames[i].step = (size_t)w * ch;
+            std::memcpy(frames[i].data, raw.data() + i * (size_t)w * h * ch, (size_t)w * h * ch);
+#endif
+        }
+    }
+    jpgx_handle handle() { return h_; }
+
+private:
+    jpgx_handle h_;
+};
+
 // ---- the vendored DBoW2 (ThirdParty/DBoW2/DBoW2), the part a loop closer calls: BowVector / FeatureVector keep the
 // reference's types (std::map), OrbVocabulary stands where TemplatedVocabulary<FORB::TDescriptor, FORB> stood; transform()
 // and score() run on the GPU (bowx_*).

@@ -199,3 +199,30 @@ def test_shim_vocabulary_matches_oracle(tmp_path):
     s = np.frombuffer(buf, "<f8", 2 * nframes, pos)
     expect = np.array([ov.score(bows[0], b) for b in bows])
     assert np.array_equal(s[:nframes], expect) and np.array_equal(s[nframes:], expect)
+
+
+def test_jpeg_demo_compiles(tmp_path):
+    _build_demo(tmp_path, "jpeg_demo")
+
+
+@pytest.mark.gpu
+def test_shim_jpeg_decoder_matches_golden(tmp_path):
+    """orbx_shim::JpegDecoder on committed files read from disk: the pixels cv2.imdecode returned (grey and colour)."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "jpeg_cases.npz"))
+    exe = _build_demo(tmp_path, "jpeg_demo")
+    for keys in (["tex333_q90", "tex333_q50rst8", "tex333_q75opt"], ["bgr71_420q90", "bgr71_420q30rst3"], ["bgr71_444q100opt"]):
+        paths = []
+        for k in keys:
+            p = tmp_path / (k + ".jpg")
+            p.write_bytes(G[k + "_file"].tobytes())
+            paths.append(str(p))
+        out = tmp_path / "frames.bin"
+        subprocess.check_call([exe, str(out)] + paths)
+        buf = out.read_bytes()
+        rows, cols, ch = struct.unpack_from("<iii", buf, 0)
+        frames = np.frombuffer(buf, np.uint8, len(keys) * rows * cols * ch, 12).reshape((len(keys), rows, cols) + ((ch,) if ch > 1 else ()))
+        for i, k in enumerate(keys):
+            assert np.array_equal(frames[i], G[k + "_pixels"]), k
+    prog = tmp_path / "prog.jpg"
+    prog.write_bytes(G["refuse_progressive_file"].tobytes())
+    assert subprocess.call([exe, str(tmp_path / "x.bin"), str(prog)], stderr=subprocess.DEVNULL) == 4

@@ -83,7 +83,7 @@ int jpeg_ingest(orbx_handle orb, const uint8_t* const* files, const size_t* size
                 uint8_t* d_desc, int cap, int32_t* d_counts)
 {
     jpgx_handle jp;
-    int32_t info[4];
+    int32_t info[6];
     int rc = jpgx_create(&jp, 0);
     if (jpgx_probe(files[0], sizes[0], info) == ORBX_E_UNSUPPORTED) return 1;      /* keep imread for this file */
     rc |= jpgx_decode_gray_batch_dev(jp, files, sizes, n, w, h, d_frames, (size_t)w * h, (size_t)w);

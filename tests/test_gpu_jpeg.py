@@ -184,3 +184,26 @@ def test_jpeg_ingest_equals_the_blocking_path_on_decoded_frames():
             assert len(gg) == 0
         prev = d
     m.close(); orb.close()
+
+
+def test_jpeg_ingest_colour_files():
+    """JpegIngest with channels=3: colour files -> BGR frames on the device -> gray conversion + ORB; equals the blocking path on
+    cv2's BGR frames."""
+    cv2 = pytest.importorskip("cv2")
+    from monocular_slam_b200 import BFMatcher, JpegIngest
+    n, W, H = 5, 640, 480
+    frames = [syn.bgr_frame(50 + i, W, H) for i in range(n)]
+    files = [cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for f in frames]          # 4:2:0, no restart markers
+    decoded = [cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED) for f in files]
+    orb = ORB(nfeatures=300, max_size=(W, H), max_batch=2)
+    m = BFMatcher()
+    ing = JpegIngest(orb, m, W, H, batch=2, ratio=0.8, channels=3)
+    got = {}
+    for first, nb, kps, desc, counts, good, ngood in ing.run(files):
+        for i in range(nb):
+            got[first + i] = (kps[i, :int(counts[i])].copy(), desc[i, :int(counts[i])].copy())
+    ing.close()
+    for f in range(n):
+        k, d = orb.detectAndCompute(decoded[f])
+        assert len(k) > 50 and np.array_equal(got[f][0], k) and np.array_equal(got[f][1], d), f
+    m.close(); orb.close()

@@ -139,6 +139,49 @@ k_jpeg_unstuff(const uint8_t* __restrict__ stream, const JpInterval* __restrict_
     if (lane == 0) nwords_out[it] = nwords;
 }
 
+// the same for long intervals (a whole file without restart markers): one CTA per interval, 1024 bytes per round
+__global__ void __launch_bounds__(1024)
+k_jpeg_unstuff_block(const uint8_t* __restrict__ stream, const JpInterval* __restrict__ intervals, uint8_t* __restrict__ scratch,
+                     uint32_t* __restrict__ nwords_out)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_last;                   // the last byte of the previous round
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const JpInterval iv = intervals[blockIdx.x];
+    uint8_t* dst = scratch + iv.scratch;
+    uint32_t out = 0;
+    if (threadIdx.x == 0) s_last = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < iv.src_len; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        const bool in = i < iv.src_len;
+        const uint32_t byte = in ? stream[iv.src + i] : 0u;
+        const uint32_t before = threadIdx.x ? (in ? stream[iv.src + i - 1] : 0u) : s_last;
+        const bool keep = in && !(byte == 0 && before == 0xFF);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {                          // exclusive scan of the 32 warp totals; lane 31 ends up with the round's total
+            const uint32_t v = s_warp[lane];
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            s_warp[lane] = incl - v;
+            if (lane == 31) s_last = incl | 0x80000000u;          // (stashed here for a moment: the total)
+        }
+        __syncthreads();
+        const uint32_t total = s_last & 0x7fffffffu;
+        if (keep) dst[out + s_warp[warp] + __popc(bal & ((1u << lane) - 1))] = (uint8_t)byte;
+        out += total;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_last = byte;                  // thread 1023 holds the round's last byte (0 past the end: harmless)
+        __syncthreads();
+    }
+    const uint32_t nwords = (out + 3) / 4;
+    if (threadIdx.x < 4 && out + threadIdx.x < nwords * 4) dst[out + threadIdx.x] = 0;
+    if (threadIdx.x == 0) nwords_out[blockIdx.x] = nwords;
+}
+
 // ---- the decoder proper.  State = (bit position, block of the MCU, coefficient index); decodes from `state` up to bit `end`.
 // WRITE: stores coefficients, `blk` being the scan-order number of the block the state is in and dc0..2 the DC predictors.
 __device__ __forceinline__ unsigned long long jp_state(uint32_t pos, int slot, int k) { return ((unsigned long long)pos << 16) | ((unsigned)slot << 8) | (unsigned)k; }
@@ -222,6 +265,9 @@ k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTa
 // without a changed exit state ends the loop (at the latest after as many rounds as there are subsequences: a perfectly periodic
 // stream -- a blank image -- never re-synchronises by itself and is walked front to back).  Then thread 0 adds up the block counts
 // and DC sums, and every lane decodes its subsequences once more, writing coefficients.
+#ifdef JP_PROFILE
+__device__ unsigned int g_jp_rounds[3];           // debug builds: intervals, sum and maximum of the rounds they took
+#endif
 __global__ void __launch_bounds__(1024)
 k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables,
             const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, unsigned long long* exit_state,
@@ -259,7 +305,12 @@ k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict
         }
         if (mine && round) s_changed = 1;
         __syncthreads();
-        if (round && !s_changed) break;
+        if (round && !s_changed) {
+#ifdef JP_PROFILE
+            if (threadIdx.x == 0) { atomicAdd(&g_jp_rounds[0], 1u); atomicAdd(&g_jp_rounds[1], (unsigned)round); atomicMax(&g_jp_rounds[2], (unsigned)round); }
+#endif
+            break;
+        }
         __syncthreads();
     }
     // first block and DC predictors of every subsequence: an exclusive prefix sum, in place
@@ -910,8 +961,12 @@ static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const si
     S.uploaded_pending = true;
     ORBX_CUDA(cudaStreamWaitEvent(h->stream, S.uploaded, 0));
     ORBX_CUDA(cudaMemsetAsync(h->d_coefs, 0, (size_t)nfiles * blocks * 64 * sizeof(int16_t), h->stream));
-    const unsigned ub = (unsigned)((ni + JP_HUFF_THREADS / 32 - 1) / (JP_HUFF_THREADS / 32));
-    k_jpeg_unstuff<<<ub, JP_HUFF_THREADS, 0, h->stream>>>(S.d_stream, S.d_intervals, (int)ni, h->d_scratch, h->d_nwords);
+    if (longest > 16384) {                          // long intervals: a CTA each
+        k_jpeg_unstuff_block<<<(unsigned)ni, 1024, 0, h->stream>>>(S.d_stream, S.d_intervals, h->d_scratch, h->d_nwords);
+    } else {
+        const unsigned ub = (unsigned)((ni + JP_HUFF_THREADS / 32 - 1) / (JP_HUFF_THREADS / 32));
+        k_jpeg_unstuff<<<ub, JP_HUFF_THREADS, 0, h->stream>>>(S.d_stream, S.d_intervals, (int)ni, h->d_scratch, h->d_nwords);
+    }
     ORBX_CUDA(cudaGetLastError());
     int lanes = 1;                                  // active lanes per warp of the sequential kernel: enough warps to keep every scheduler busy first
     while (lanes < 32 && ni / (size_t)(lanes * 2) >= 1200) lanes *= 2;
@@ -1001,3 +1056,15 @@ extern "C" int jpgx_decode_bgr_batch(jpgx_handle h, const uint8_t* const* files,
 {
     ORBX_NOTHROW(decode_batch_host(h, files, sizes, nfiles, w, hh, frames, frame_pitch, stride, 3))
 }
+
+#ifdef JP_PROFILE
+// {intervals, sum of rounds, maximum} of k_jpeg_sync since the last call (debug builds only: tools/jpeg_probe.py prints it)
+extern "C" __attribute__((visibility("default"))) int jpgx_debug_rounds(unsigned int* out3)
+{
+    ORBX_CUDA(cudaDeviceSynchronize());
+    ORBX_CUDA(cudaMemcpyFromSymbol(out3, g_jp_rounds, sizeof(g_jp_rounds)));
+    unsigned int z[3] = {0, 0, 0};
+    ORBX_CUDA(cudaMemcpyToSymbol(g_jp_rounds, z, sizeof(z)));
+    return ORBX_OK;
+}
+#endif

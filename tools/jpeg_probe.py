@@ -11,8 +11,19 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from monocular_slam_b200 import JpegDecoder  # noqa: E402
+from monocular_slam_b200 import JpegDecoder, _lib  # noqa: E402
 from monocular_slam_b200 import synthetic as syn  # noqa: E402
+
+
+def rounds():
+    """Rounds of k_jpeg_sync since the last call, if the library was built with -DJP_PROFILE (ORBX_EXTRA_FLAGS)."""
+    import ctypes as C
+    L = _lib.lib()
+    if not hasattr(L, "jpgx_debug_rounds"):
+        return ""
+    out = (C.c_uint * 3)()
+    L.jpgx_debug_rounds(out)
+    return "; sync rounds per interval: mean %.1f, max %d" % (out[1] / max(out[0], 1), out[2]) if out[0] else ""
 
 
 def main():
@@ -48,6 +59,7 @@ def main():
         e1.record(stream)
         stream.synchronize()
         wall = time.perf_counter() - t0
+        print(rounds()[2:])
         print("%-32s %5.0f KB per file: call returns after %.2f ms (host parse + staging), batch done after %.2f ms wall = %.0f frames/s "
               "(device span %.2f ms); cv2.imdecode on one core: %.0f frames/s" % (name, nbytes / B / 1e3, host / reps * 1e3, wall / reps * 1e3, B * reps / wall,
                                                                                   e0.elapsed_time(e1) / reps, cpu))
@@ -70,6 +82,7 @@ def main():
             dec.decode_dev(files, W, H, d_bgr.data_ptr(), W * H * 3, W * 3, channels=3)
         stream.synchronize()
         wall = time.perf_counter() - t0
+        print(rounds()[2:])
         print("%-36s %5.0f KB per file: %.2f ms per batch = %.0f frames/s; cv2.imdecode on one core: %.0f frames/s"
               % (name, sum(len(f) for f in files) / B / 1e3, wall / reps * 1e3, B * reps / wall, cpu))
     dec.close()

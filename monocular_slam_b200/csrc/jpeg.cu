@@ -26,6 +26,8 @@
 #include <thread>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace orbx {
@@ -139,42 +141,50 @@ k_jpeg_unstuff(const uint8_t* __restrict__ stream, const JpInterval* __restrict_
     if (lane == 0) nwords_out[it] = nwords;
 }
 
-// the same for long intervals (a whole file without restart markers): one CTA per interval, 1024 bytes per round
+// the same for long intervals (a whole file without restart markers): one CTA per interval, 4096 bytes per round, four
+// consecutive bytes per thread
 __global__ void __launch_bounds__(1024)
 k_jpeg_unstuff_block(const uint8_t* __restrict__ stream, const JpInterval* __restrict__ intervals, uint8_t* __restrict__ scratch,
                      uint32_t* __restrict__ nwords_out)
 {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_last;                   // the last byte of the previous round
+    __shared__ uint32_t s_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const JpInterval iv = intervals[blockIdx.x];
+    const uint8_t* src = stream + iv.src;
     uint8_t* dst = scratch + iv.scratch;
     uint32_t out = 0;
-    if (threadIdx.x == 0) s_last = 0;
-    __syncthreads();
-    for (uint32_t i0 = 0; i0 < iv.src_len; i0 += 1024) {
-        const uint32_t i = i0 + threadIdx.x;
-        const bool in = i < iv.src_len;
-        const uint32_t byte = in ? stream[iv.src + i] : 0u;
-        const uint32_t before = threadIdx.x ? (in ? stream[iv.src + i - 1] : 0u) : s_last;
-        const bool keep = in && !(byte == 0 && before == 0xFF);
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) s_warp[warp] = __popc(bal);
-        __syncthreads();
-        if (warp == 0) {                          // exclusive scan of the 32 warp totals; lane 31 ends up with the round's total
-            const uint32_t v = s_warp[lane];
-            uint32_t incl = v;
+    for (uint32_t i0 = 0; i0 < iv.src_len; i0 += 4096) {
+        const uint32_t i = i0 + threadIdx.x * 4;
+        uint32_t byte[4], keep = 0, n = 0;
+        uint32_t before = i && i <= iv.src_len ? src[i - 1] : 0u;       // the byte in front of this thread's four
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-            s_warp[lane] = incl - v;
-            if (lane == 31) s_last = incl | 0x80000000u;          // (stashed here for a moment: the total)
+        for (int k = 0; k < 4; k++) {
+            const bool in = i + k < iv.src_len;
+            byte[k] = in ? src[i + k] : 0u;
+            if (in && !(byte[k] == 0 && before == 0xFF)) { keep |= 1u << k; n++; }
+            before = byte[k];
+        }
+        // exclusive scan of the per-thread counts over the CTA
+        uint32_t incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = s_warp[lane];
+            uint32_t wi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
+            s_warp[lane] = wi - v;
+            if (lane == 31) s_total = wi;
         }
         __syncthreads();
-        const uint32_t total = s_last & 0x7fffffffu;
-        if (keep) dst[out + s_warp[warp] + __popc(bal & ((1u << lane) - 1))] = (uint8_t)byte;
-        out += total;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_last = byte;                  // thread 1023 holds the round's last byte (0 past the end: harmless)
+        uint32_t at = out + s_warp[warp] + incl - n;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (keep & (1u << k)) dst[at++] = (uint8_t)byte[k];
+        out += s_total;
         __syncthreads();
     }
     const uint32_t nwords = (out + 3) / 4;
@@ -268,27 +278,35 @@ k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTa
 #ifdef JP_PROFILE
 __device__ unsigned int g_jp_rounds[3];           // debug builds: intervals, sum and maximum of the rounds they took
 #endif
+// CL > 1: a thread-block cluster of CL CTAs shares one interval (whole files without restart markers in a small batch would
+// otherwise occupy one SM each); the rounds are separated by cluster barriers and the "anything changed" flags are read through
+// distributed shared memory.
+template <int CL>
 __global__ void __launch_bounds__(1024)
 k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables,
             const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, unsigned long long* exit_state,
             unsigned long long* used_state, int32_t* sub_counts /* [nsubs][4]: blocks, DC sums of the components */, int16_t* __restrict__ coefs,
             const JpGeom g, uint32_t sub_bits)
 {
+    namespace cg = cooperative_groups;
     __shared__ uint8_t s_natural[64];
     __shared__ int s_changed;
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_natural[i] = c_natural_order[i];      // (a CTA can be a single warp)
-    const JpInterval iv = intervals[blockIdx.x];
+    const unsigned ivx = blockIdx.x / CL, rank = CL > 1 ? cg::this_cluster().block_rank() : 0u;
+    auto barrier = [&]() { if (CL > 1) cg::this_cluster().sync(); else __syncthreads(); };
+    const JpInterval iv = intervals[ivx];
     const JpTables* tb = tables + file_tables[iv.file];
-    const uint32_t nwords = nwords_in[blockIdx.x], total = nwords * 32u;
+    const uint32_t nwords = nwords_in[ivx], total = nwords * 32u;
     const uint32_t* words = reinterpret_cast<const uint32_t*>(scratch + iv.scratch);
     volatile unsigned long long* ex = exit_state + iv.first_sub;
     unsigned long long* used = used_state + iv.first_sub;
     int4* cnt = reinterpret_cast<int4*>(sub_counts) + iv.first_sub;
+    const uint32_t lane0 = rank * blockDim.x + threadIdx.x, stride = CL * blockDim.x;
     for (int round = 0;; round++) {
         if (threadIdx.x == 0) s_changed = 0;
-        __syncthreads();
+        barrier();
         bool mine = false;
-        for (uint32_t j = threadIdx.x; j < iv.nsub; j += blockDim.x) {
+        for (uint32_t j = lane0; j < iv.nsub; j += stride) {
             unsigned long long start;
             if (round == 0) start = jp_state(j * sub_bits, 0, 0);
             else {
@@ -304,27 +322,31 @@ k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict
             if (round == 0 || e != ex[j]) { ex[j] = e; mine = true; }
         }
         if (mine && round) s_changed = 1;
-        __syncthreads();
-        if (round && !s_changed) {
+        barrier();
+        int any = s_changed;
+        if (CL > 1)
+            for (unsigned r = 0; r < (unsigned)CL; r++) any |= *cg::this_cluster().map_shared_rank(&s_changed, r);
+        if (round && !any) {
 #ifdef JP_PROFILE
-            if (threadIdx.x == 0) { atomicAdd(&g_jp_rounds[0], 1u); atomicAdd(&g_jp_rounds[1], (unsigned)round); atomicMax(&g_jp_rounds[2], (unsigned)round); }
+            if (threadIdx.x == 0 && rank == 0) { atomicAdd(&g_jp_rounds[0], 1u); atomicAdd(&g_jp_rounds[1], (unsigned)round); atomicMax(&g_jp_rounds[2], (unsigned)round); }
 #endif
             break;
         }
-        __syncthreads();
+        barrier();
     }
-    // first block and DC predictors of every subsequence: an exclusive prefix sum, in place
-    if (threadIdx.x == 0) {
+    // first block and DC predictors of every subsequence: an exclusive prefix sum, in place (L2 loads: other CTAs of the cluster
+    // wrote some of the counts, and will read the sums)
+    if (threadIdx.x == 0 && rank == 0) {
         int4 run = make_int4(0, 0, 0, 0);
         for (uint32_t j = 0; j < iv.nsub; j++) {
-            const int4 v = cnt[j];
+            const int4 v = __ldcg(cnt + j);
             cnt[j] = run;
             run.x += v.x; run.y += v.y; run.z += v.z; run.w += v.w;
         }
     }
-    __syncthreads();
-    for (uint32_t j = threadIdx.x; j < iv.nsub; j += blockDim.x) {
-        const int4 at = cnt[j];
+    barrier();
+    for (uint32_t j = lane0; j < iv.nsub; j += stride) {
+        const int4 at = __ldcg(cnt + j);
         const uint32_t first = (uint32_t)at.x;
         if (first >= iv.nblocks) continue;
         JpBits b = {words, nwords, 0, 0ull, 0};
@@ -649,6 +671,7 @@ struct JpSet {                                    // what one call uploads: pinn
 struct jpgx_context {
     int device;
     cudaStream_t own_stream, stream;
+    int sm_count;
     cudaStream_t copy_stream;                     // uploads of call k+1 run beside the kernels of call k
     JpSet set[2];                                 // the buffers of two calls in flight, used in turn
     int next_set;
@@ -723,6 +746,7 @@ extern "C" int jpgx_create(jpgx_handle* out, int device)
     ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), jpgx_destroy(h));
     h->stream = h->own_stream;
     ORBX_CUDA_OR(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), jpgx_destroy(h));
+    ORBX_CUDA_OR(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), jpgx_destroy(h));
     for (JpSet& S : h->set) {
         S.tables_cap = 16;
         ORBX_CUDA_OR(cudaEventCreateWithFlags(&S.uploaded, cudaEventDisableTiming), jpgx_destroy(h));
@@ -976,10 +1000,30 @@ static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const si
         k_jpeg_huff<<<seq_blocks, JP_HUFF_THREADS, 0, h->stream>>>(S.d_intervals, (int)ni, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords,
                                                                   h->d_coefs, g, lane_step);
     } else {
-        const unsigned threads = std::min(1024u, (max_nsub + 31u) / 32u * 32u);
         unsigned long long* st = h->d_subw;       // [nsubs] exit states, [nsubs] states decoded from, [nsubs][4] counts
-        k_jpeg_sync<<<(unsigned)ni, threads, 0, h->stream>>>(S.d_intervals, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, st, st + nsubs,
-                                                            (int32_t*)(st + 2 * nsubs), h->d_coefs, g, sub_bits);
+        // a few very long intervals (a small batch of files without restart markers): a cluster of CTAs per interval, so that the
+        // batch covers the SMs
+        int cl = 1;
+        while (cl < 8 && ni * (size_t)(cl * 2) <= 2 * (size_t)h->sm_count && max_nsub >= 1024u * (unsigned)(cl * 2)) cl *= 2;
+        const unsigned threads = std::min(1024u, ((max_nsub + (unsigned)cl - 1) / (unsigned)cl + 31u) / 32u * 32u);
+        if (cl == 1) {
+            k_jpeg_sync<1><<<(unsigned)ni, threads, 0, h->stream>>>(S.d_intervals, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, st, st + nsubs,
+                                                                   (int32_t*)(st + 2 * nsubs), h->d_coefs, g, sub_bits);
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)ni * (unsigned)cl); cfg.blockDim = dim3(threads); cfg.stream = h->stream;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = (unsigned)cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            const JpInterval* a0 = S.d_intervals; const JpTables* a1 = S.d_tables; const int32_t* a2 = S.d_file_tables;
+            const uint8_t* a3 = h->d_scratch; const uint32_t* a4 = h->d_nwords;
+            unsigned long long* a5 = st; unsigned long long* a6 = st + nsubs; int32_t* a7 = (int32_t*)(st + 2 * nsubs);
+            int16_t* a8 = h->d_coefs;
+            if (cl == 2) ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<2>, a0, a1, a2, a3, a4, a5, a6, a7, a8, g, sub_bits));
+            else if (cl == 4) ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<4>, a0, a1, a2, a3, a4, a5, a6, a7, a8, g, sub_bits));
+            else ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<8>, a0, a1, a2, a3, a4, a5, a6, a7, a8, g, sub_bits));
+        }
     }
     ORBX_CUDA(cudaGetLastError());
     JpOut o;

@@ -548,8 +548,11 @@ __device__ void smallest_eigvec3(double* G, double* vs)
 // One CTA per pair.  pts1/pts2: npairs x cap correspondences (float x, y); counts[pair] of them valid.
 // status: npairs x cap bytes (0/1); F: npairs x 9 doubles (zeros: no result); info: npairs x 4 ints
 // {inliers, iterations run, candidates scored, 0}.
+#ifndef FM_CTAS_PER_SM
+#define FM_CTAS_PER_SM (512 / FM_THREADS)   // 128 registers per thread; 3 CTAs of 256 threads (80 registers) were measured: see profiles/README.md
+#endif
 template <bool SMEM_POINTS, int FM_THREADS>
-__global__ void __launch_bounds__(FM_THREADS, 512 / FM_THREADS)
+__global__ void __launch_bounds__(FM_THREADS, FM_CTAS_PER_SM)
 k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ counts, int cap,
             double thr, double conf, int max_iters, uint8_t* __restrict__ status, double* __restrict__ Fout, int32_t* __restrict__ info)
 {

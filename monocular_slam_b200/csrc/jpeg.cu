@@ -192,6 +192,109 @@ k_jpeg_unstuff_block(const uint8_t* __restrict__ stream, const JpInterval* __res
     if (threadIdx.x == 0) nwords_out[blockIdx.x] = nwords;
 }
 
+// the same with several CTAs per interval, when few long intervals (a batch of files without restart markers) would leave most SMs
+// idle: whether a byte stays depends on its predecessor alone, so every JP_CHUNK source bytes are handled by a CTA of their own --
+// a first kernel counts the bytes each chunk keeps, the second adds up the counts in front of its chunk and compacts it there.
+constexpr uint32_t JP_CHUNK = 8192;
+constexpr int JP_CHUNK_THREADS = 256;
+
+// thread's four source bytes at offset i of the interval -> keep mask (bit k: byte k stays); `aligned`: 32-bit loads are possible
+// (the uploaded stream is padded, so a word that starts inside the interval can be read whole)
+__device__ __forceinline__ uint32_t jp_keep4(const uint8_t* __restrict__ src, uint32_t src_len, uint32_t i, bool aligned, uint32_t* byte)
+{
+    if (i >= src_len) { byte[0] = byte[1] = byte[2] = byte[3] = 0; return 0u; }
+    if (aligned) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(src + i);
+        byte[0] = w & 255u; byte[1] = (w >> 8) & 255u; byte[2] = (w >> 16) & 255u; byte[3] = w >> 24;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) byte[k] = i + k < src_len ? src[i + k] : 0u;
+    }
+    uint32_t before = i ? src[i - 1] : 0u, keep = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (i + k < src_len && !(byte[k] == 0 && before == 0xFF)) keep |= 1u << k;
+        before = byte[k];
+    }
+    return keep;
+}
+
+__global__ void __launch_bounds__(JP_CHUNK_THREADS)
+k_jpeg_unstuff_count(const uint8_t* __restrict__ stream, const JpInterval* __restrict__ intervals, uint32_t max_chunks, uint32_t* __restrict__ chunk_kept)
+{
+    __shared__ uint32_t s_warp[JP_CHUNK_THREADS / 32];
+    const JpInterval iv = intervals[blockIdx.y];
+    const uint32_t c0 = blockIdx.x * JP_CHUNK;
+    if (c0 >= iv.src_len) return;                 // (the chunks an interval does not have are never read)
+    const uint8_t* src = stream + iv.src;
+    const bool aligned = (iv.src & 3u) == 0;
+    uint32_t n = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < JP_CHUNK / (JP_CHUNK_THREADS * 4); r++) {
+        uint32_t byte[4];
+        n += __popc(jp_keep4(src, iv.src_len, c0 + r * (JP_CHUNK_THREADS * 4) + threadIdx.x * 4, aligned, byte));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < JP_CHUNK_THREADS / 32; i++) t += s_warp[i];
+        chunk_kept[(size_t)blockIdx.y * max_chunks + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(JP_CHUNK_THREADS)
+k_jpeg_unstuff_chunk(const uint8_t* __restrict__ stream, const JpInterval* __restrict__ intervals, uint32_t max_chunks, const uint32_t* __restrict__ chunk_kept,
+                     uint8_t* __restrict__ scratch, uint32_t* __restrict__ nwords_out)
+{
+    constexpr int NW = JP_CHUNK_THREADS / 32;
+    __shared__ uint32_t s_warp[2][NW];
+    __shared__ uint32_t s_base[NW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const JpInterval iv = intervals[blockIdx.y];
+    const uint32_t c0 = blockIdx.x * JP_CHUNK;
+    if (c0 >= iv.src_len && blockIdx.x) return;   // an empty interval still gets its word count (0) from chunk 0
+    const uint8_t* src = stream + iv.src;
+    uint8_t* dst = scratch + iv.scratch;
+    const bool aligned = (iv.src & 3u) == 0;
+    // bytes kept in front of this chunk
+    uint32_t b = 0;
+    for (uint32_t c = threadIdx.x; c < blockIdx.x; c += JP_CHUNK_THREADS) b += chunk_kept[(size_t)blockIdx.y * max_chunks + c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (lane == 0) s_base[warp] = b;
+    __syncthreads();
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) out += s_base[i];
+    for (uint32_t r = 0; r < JP_CHUNK / (JP_CHUNK_THREADS * 4); r++) {
+        const uint32_t i = c0 + r * (JP_CHUNK_THREADS * 4) + threadIdx.x * 4;
+        if (c0 + r * (JP_CHUNK_THREADS * 4) >= iv.src_len) break;      // (uniform over the CTA)
+        uint32_t byte[4];
+        const uint32_t keep = jp_keep4(src, iv.src_len, i, aligned, byte);
+        const uint32_t n = __popc(keep);
+        uint32_t incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) s_warp[r & 1][warp] = incl;
+        __syncthreads();                          // (the buffers alternate: one barrier per round)
+        uint32_t at = out + incl - n, total = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) { const uint32_t v = s_warp[r & 1][k]; total += v; at += k < warp ? v : 0u; }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (keep & (1u << k)) dst[at++] = (uint8_t)byte[k];
+        out += total;
+    }
+    if (c0 + JP_CHUNK >= iv.src_len) {            // the interval's last chunk: pad the last word, publish the word count
+        const uint32_t nwords = (out + 3) / 4;
+        if (threadIdx.x < 4 && out + threadIdx.x < nwords * 4) dst[out + threadIdx.x] = 0;
+        if (threadIdx.x == 0) nwords_out[blockIdx.y] = nwords;
+    }
+}
+
 // ---- the decoder proper.  State = (bit position, block of the MCU, coefficient index); decodes from `state` up to bit `end`.
 // WRITE: stores coefficients, `blk` being the scan-order number of the block the state is in and dc0..2 the DC predictors.
 __device__ __forceinline__ unsigned long long jp_state(uint32_t pos, int slot, int k) { return ((unsigned long long)pos << 16) | ((unsigned)slot << 8) | (unsigned)k; }
@@ -464,7 +567,7 @@ k_jpeg_idct(const int16_t* __restrict__ coefs, const JpTables* __restrict__ tabl
 }
 
 // ---- K19: chroma upsampling (jdsample.c h2v2_fancy_upsample / h2v1_fancy_upsample) and YCbCr -> BGR (jdcolor.c
-// ycc_rgb_convert, 16-bit fixed point) for four pixels of a row per thread
+// ycc_rgb_convert, 16-bit fixed point); jp_chroma: one sample, the general form
 __device__ __forceinline__ int jp_chroma(const uint8_t* __restrict__ pl, int stride, int cw, int ch, int x, int y, int hs, int vs)
 {
     if (hs == 1) return pl[(size_t)y * stride + x];
@@ -487,36 +590,105 @@ __device__ __forceinline__ int jp_chroma(const uint8_t* __restrict__ pl, int str
     return cx == 0 ? (cur * 4 + 8) >> 4 : (3 * cur + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
 }
 
-__global__ void __launch_bounds__(256)
-k_jpeg_ycc(const uint8_t* __restrict__ planes, size_t planes_pitch, size_t off1, size_t off2, int stride0, int stride1, int w, int h, int hs, int vs,
+// one pixel of the colour conversion: jdcolor.c ycc_rgb_convert
+__device__ __forceinline__ void jp_ycc_px(int Y, int cb, int cr, uint8_t* bgr)
+{
+    cb -= 128; cr -= 128;
+    const int r = Y + ((91881 * cr + 32768) >> 16);           // FIX(1.40200), ONE_HALF
+    const int b = Y + ((116130 * cb + 32768) >> 16);          // FIX(1.77200)
+    const int gg = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);   // FIX(0.34414), FIX(0.71414)
+    bgr[0] = (uint8_t)min(max(b, 0), 255); bgr[1] = (uint8_t)min(max(gg, 0), 255); bgr[2] = (uint8_t)min(max(r, 0), 255);
+}
+
+// sixteen upsampled chroma samples of row y from column x0 (a multiple of 16, x0 + 16 <= w) of a plane subsampled 2:1 across
+// (HS == 2; down as well when vs == 2): the eight plane samples under them as one 8-byte load per row, their two neighbours as
+// byte loads.  At the image's left and right edge jdsample.c's special cases equal the general formula with the missing
+// neighbour replaced by the sample itself.
+__device__ __forceinline__ void jp_chroma16(const uint8_t* __restrict__ pl, int stride, int cw, int ch, int x0, int y, int vs, int* out)
+{
+    const int cx0 = x0 >> 1;
+    const int cy = vs == 2 ? y >> 1 : y;
+    const uint8_t* r0 = pl + (size_t)cy * stride + cx0;
+    int cur[10];                                  // columns cx0 - 1 .. cx0 + 8
+    {
+        const uint2 v = *reinterpret_cast<const uint2*>(r0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) cur[1 + i] = (int)(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 255u);
+        cur[0] = cx0 > 0 ? (int)r0[-1] : cur[1];
+        cur[9] = cx0 + 8 <= cw - 1 ? (int)r0[8] : cur[8];
+    }
+    if (vs == 2) {                                // the nearer row weighs 3, the other one 1
+        const int oy = min(max((y & 1) ? cy + 1 : cy - 1, 0), ch - 1);
+        const uint8_t* r1 = pl + (size_t)oy * stride + cx0;
+        const uint2 v = *reinterpret_cast<const uint2*>(r1);
+        int far_[10];
+#pragma unroll
+        for (int i = 0; i < 8; i++) far_[1 + i] = (int)(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 255u);
+        far_[0] = cx0 > 0 ? (int)r1[-1] : far_[1];
+        far_[9] = cx0 + 8 <= cw - 1 ? (int)r1[8] : far_[8];
+#pragma unroll
+        for (int i = 0; i < 10; i++) cur[i] = 3 * cur[i] + far_[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            out[2 * i] = (3 * cur[1 + i] + cur[i] + 8) >> 4;
+            out[2 * i + 1] = (3 * cur[1 + i] + cur[2 + i] + 7) >> 4;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            out[2 * i] = (3 * cur[1 + i] + cur[i] + 1) >> 2;
+            out[2 * i + 1] = (3 * cur[1 + i] + cur[2 + i] + 2) >> 2;
+        }
+    }
+}
+
+// sixteen pixels of a row per thread: the luma and chroma samples arrive as 8-byte loads, the 48 bytes of B, G, R leave as three
+// 16-byte stores; the threads at the right edge of the image (and every thread of a frame whose rows are not 16-byte aligned) take
+// the samples one by one
+template <int HS>
+__global__ void __launch_bounds__(128)
+k_jpeg_ycc(const uint8_t* __restrict__ planes, size_t planes_pitch, size_t off1, size_t off2, int stride0, int stride1, int w, int h, int vs,
            uint8_t* __restrict__ frames, size_t frame_pitch, size_t stride)
 {
-    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4, y = blockIdx.y, file = blockIdx.z;
+    const int x0 = (blockIdx.x * 128 + threadIdx.x) * 16, y = blockIdx.y, file = blockIdx.z;
     if (x0 >= w) return;
     const uint8_t* p0 = planes + (size_t)file * planes_pitch;
     const uint8_t* p1 = p0 + off1;
     const uint8_t* p2 = p0 + off2;
-    const int cw = (w + hs - 1) / hs, ch = (h + vs - 1) / vs;
-    uint8_t bgr[12];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int x = min(x0 + i, w - 1);
-        const int Y = p0[(size_t)y * stride0 + x];
-        const int cb = jp_chroma(p1, stride1, cw, ch, x, y, hs, vs) - 128, cr = jp_chroma(p2, stride1, cw, ch, x, y, hs, vs) - 128;
-        const int r = Y + ((91881 * cr + 32768) >> 16);           // FIX(1.40200), ONE_HALF
-        const int b = Y + ((116130 * cb + 32768) >> 16);          // FIX(1.77200)
-        const int gg = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);   // FIX(0.34414), FIX(0.71414)
-        bgr[3 * i] = (uint8_t)min(max(b, 0), 255); bgr[3 * i + 1] = (uint8_t)min(max(gg, 0), 255); bgr[3 * i + 2] = (uint8_t)min(max(r, 0), 255);
-    }
+    const int cw = (w + HS - 1) / HS, ch = (h + vs - 1) / vs;
     uint8_t* out = frames + (size_t)file * frame_pitch + (size_t)y * stride + (size_t)x0 * 3;
-    if (x0 + 4 <= w && ((reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
-        o32[0] = bgr[0] | (bgr[1] << 8) | (bgr[2] << 16) | ((uint32_t)bgr[3] << 24);
-        o32[1] = bgr[4] | (bgr[5] << 8) | (bgr[6] << 16) | ((uint32_t)bgr[7] << 24);
-        o32[2] = bgr[8] | (bgr[9] << 8) | (bgr[10] << 16) | ((uint32_t)bgr[11] << 24);
-    } else {
-        for (int i = 0; i < 12 && x0 + i / 3 < w; i++) out[i] = bgr[i];
+    if (x0 + 16 > w || (reinterpret_cast<uintptr_t>(out) & 15) != 0 || (HS == 2 && cw <= 2)) {
+        for (int i = 0; i < 16 && x0 + i < w; i++) {
+            const int x = x0 + i;
+            jp_ycc_px(p0[(size_t)y * stride0 + x], jp_chroma(p1, stride1, cw, ch, x, y, HS, vs), jp_chroma(p2, stride1, cw, ch, x, y, HS, vs), out + 3 * i);
+        }
+        return;
     }
+    int cb[16], cr[16];
+    if (HS == 2) {
+        jp_chroma16(p1, stride1, cw, ch, x0, y, vs, cb);
+        jp_chroma16(p2, stride1, cw, ch, x0, y, vs, cr);
+    } else {
+        const uint2* q1 = reinterpret_cast<const uint2*>(p1 + (size_t)y * stride1 + x0);
+        const uint2* q2 = reinterpret_cast<const uint2*>(p2 + (size_t)y * stride1 + x0);
+        const uint2 a0 = q1[0], a1 = q1[1], b0 = q2[0], b1 = q2[1];
+        const uint32_t aw[4] = {a0.x, a0.y, a1.x, a1.y}, bw[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+        for (int i = 0; i < 16; i++) { cb[i] = (int)((aw[i >> 2] >> (8 * (i & 3))) & 255u); cr[i] = (int)((bw[i >> 2] >> (8 * (i & 3))) & 255u); }
+    }
+    const uint2* qy = reinterpret_cast<const uint2*>(p0 + (size_t)y * stride0 + x0);
+    const uint2 y0 = qy[0], y1 = qy[1];
+    const uint32_t yw[4] = {y0.x, y0.y, y1.x, y1.y};
+    uint8_t bgr[48];
+#pragma unroll
+    for (int i = 0; i < 16; i++) jp_ycc_px((int)((yw[i >> 2] >> (8 * (i & 3))) & 255u), cb[i], cr[i], bgr + 3 * i);
+    uint32_t ow[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) ow[i] = bgr[4 * i] | (bgr[4 * i + 1] << 8) | (bgr[4 * i + 2] << 16) | ((uint32_t)bgr[4 * i + 3] << 24);
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    o4[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    o4[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    o4[2] = make_uint4(ow[8], ow[9], ow[10], ow[11]);
 }
 
 // ---- host: marker parsing
@@ -677,6 +849,7 @@ struct jpgx_context {
     int next_set;
     uint8_t* d_scratch; size_t d_scratch_bytes;   // the same without stuffed bytes
     uint32_t* d_nwords; size_t d_nwords_bytes;    // 32-bit words of every interval's stripped copy
+    uint32_t* d_chunk_kept; size_t d_chunk_kept_bytes;   // chunked unstuffing: bytes every chunk keeps, [interval][chunk]
     unsigned long long* d_subw; size_t d_subw_bytes;   // per subsequence: exit state, state it was last decoded from, block count and DC sums
     uint8_t* d_planes; size_t d_planes_bytes;     // colour files: the component planes before upsampling
     int16_t* d_coefs; size_t d_coefs_bytes;
@@ -724,7 +897,7 @@ extern "C" int jpgx_destroy(jpgx_handle h)
         if (S.decoded) cudaEventDestroy(S.decoded);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    cudaFree(h->d_scratch); cudaFree(h->d_nwords); cudaFree(h->d_subw); cudaFree(h->d_planes);
+    cudaFree(h->d_scratch); cudaFree(h->d_nwords); cudaFree(h->d_chunk_kept); cudaFree(h->d_subw); cudaFree(h->d_planes);
     cudaFree(h->d_coefs); cudaFree(h->d_frames);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -985,7 +1158,15 @@ static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const si
     S.uploaded_pending = true;
     ORBX_CUDA(cudaStreamWaitEvent(h->stream, S.uploaded, 0));
     ORBX_CUDA(cudaMemsetAsync(h->d_coefs, 0, (size_t)nfiles * blocks * 64 * sizeof(int16_t), h->stream));
-    if (longest > 16384) {                          // long intervals: a CTA each
+    const size_t max_chunks = ((size_t)longest + JP_CHUNK - 1) / JP_CHUNK;
+    if (longest > 16384 && ni <= 65535 && ni < 4 * (size_t)h->sm_count && ni * max_chunks <= (1u << 18)) {
+        // few long intervals (files without restart markers): several CTAs per interval
+        rc = jp_grow(&h->d_chunk_kept, &h->d_chunk_kept_bytes, ni * max_chunks * sizeof(uint32_t));
+        if (rc) return rc;
+        const dim3 cg((unsigned)max_chunks, (unsigned)ni);
+        k_jpeg_unstuff_count<<<cg, JP_CHUNK_THREADS, 0, h->stream>>>(S.d_stream, S.d_intervals, (uint32_t)max_chunks, h->d_chunk_kept);
+        k_jpeg_unstuff_chunk<<<cg, JP_CHUNK_THREADS, 0, h->stream>>>(S.d_stream, S.d_intervals, (uint32_t)max_chunks, h->d_chunk_kept, h->d_scratch, h->d_nwords);
+    } else if (longest > 16384) {                   // long intervals: a CTA each
         k_jpeg_unstuff_block<<<(unsigned)ni, 1024, 0, h->stream>>>(S.d_stream, S.d_intervals, h->d_scratch, h->d_nwords);
     } else {
         const unsigned ub = (unsigned)((ni + JP_HUFF_THREADS / 32 - 1) / (JP_HUFF_THREADS / 32));
@@ -1047,8 +1228,13 @@ static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const si
         h->d_coefs, S.d_tables, S.d_file_tables, nfiles, g, o);
     ORBX_CUDA(cudaGetLastError());
     if (ncomp == 3) {
-        k_jpeg_ycc<<<dim3((unsigned)((w + 1023) / 1024), (unsigned)hh, (unsigned)nfiles), 256, 0, h->stream>>>(
-            h->d_planes, planes_pitch, plane_off[1], plane_off[2], (int)o.stride[0], (int)o.stride[1], w, hh, hf[0].hs, hf[0].vs, d_frames, frame_pitch, stride);
+        const dim3 yg((unsigned)((w + 2047) / 2048), (unsigned)hh, (unsigned)nfiles);
+        if (hf[0].hs == 2)
+            k_jpeg_ycc<2><<<yg, 128, 0, h->stream>>>(h->d_planes, planes_pitch, plane_off[1], plane_off[2], (int)o.stride[0], (int)o.stride[1], w, hh, hf[0].vs,
+                                                    d_frames, frame_pitch, stride);
+        else
+            k_jpeg_ycc<1><<<yg, 128, 0, h->stream>>>(h->d_planes, planes_pitch, plane_off[1], plane_off[2], (int)o.stride[0], (int)o.stride[1], w, hh, hf[0].vs,
+                                                    d_frames, frame_pitch, stride);
         ORBX_CUDA(cudaGetLastError());
     }
     ORBX_CUDA(cudaEventRecord(S.decoded, h->stream));

@@ -120,6 +120,47 @@ def test_larger_frames_match_the_oracle_and_feed_the_extractor(w, h, rst, qualit
     dec.close()
 
 
+@pytest.mark.parametrize("sampling", ["420", "422", "444"])
+@pytest.mark.parametrize("w,h", [(16, 16), (32, 8), (48, 33), (640, 480), (1008, 350), (2064, 40)])
+def test_colour_frames_with_16_byte_aligned_rows(sampling, w, h):
+    """Widths that are multiples of 16: every row of the tight BGR output is 16-byte aligned, so the colour conversion takes its
+    sixteen-pixels-per-thread form (edge columns included: the first and the last thread of a row); the larger sizes, without restart
+    markers, are unstuffed by several CTAs per file.  Pixels identical to cv2.imdecode and to the oracle."""
+    cv2 = pytest.importorskip("cv2")
+    sf = {"420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444}[sampling]
+    rng = np.random.default_rng(w * 131 + h)
+    frames = [syn.bgr_frame(70 + i, w, h) if min(w, h) >= 64 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for i in range(3)]
+    frames[2] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)          # noise: many FF bytes in the entropy-coded segment
+    dec = JpegDecoder()
+    for rst in (0, 1000):
+        params = [cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else [])
+        files = [cv2.imencode(".jpg", f, params)[1].tobytes() for f in frames]
+        got = dec.decode(files)
+        for i, f in enumerate(files):
+            assert np.array_equal(got[i], cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED)), (rst, i)
+        assert np.array_equal(got[2], oracle.jpeg_decode_bgr(files[2]))
+    dec.close()
+
+
+@pytest.mark.parametrize("n,w,h,rst", [(1, 1920, 1080, 0), (5, 800, 600, 0), (3, 1600, 900, 5000), (2, 3840, 2160, 0)])
+def test_long_intervals_are_unstuffed_by_several_ctas(n, w, h, rst):
+    """Grey files whose restart intervals are far longer than 16 KB (none, or a marker every few thousand blocks -- intervals that
+    start at any byte offset): the chunked unstuffing.  Noise frames: an FF byte every ~200 bytes of the scan."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(n * 7 + w)
+    frames = [rng.integers(0, 256, (h, w), dtype=np.uint8) if i % 2 == 0 else syn.frame(80 + i, w, h) for i in range(n)]
+    params = [cv2.IMWRITE_JPEG_QUALITY, 92] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, rst] if rst else [])
+    files = [cv2.imencode(".jpg", f, params)[1].tobytes() for f in frames]
+    dec = JpegDecoder()
+    got = dec.decode(files)
+    for i, f in enumerate(files):
+        assert np.array_equal(got[i], cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED)), i
+    # a file cut in the middle of its scan (zero bits past the end, as libjpeg pads) and one cut on a chunk boundary of the scan
+    for cut in (len(files[0]) // 2, len(files[0]) - (len(files[0]) % 8192)):
+        assert np.array_equal(dec.decode([files[0][:cut]])[0], oracle.jpeg_decode_gray(files[0][:cut])), cut
+    dec.close()
+
+
 def test_device_frames_go_straight_into_extraction():
     """jpgx_decode_gray_batch_dev -> orbx_extract_batch_dev on one stream: the keypoints of the decoded frames."""
     import torch

@@ -375,7 +375,7 @@ k_jpeg_huff(const JpInterval* __restrict__ intervals, int nintervals, const JpTa
 // subsequences is from A. Weissenberger and B. Schmidt, "Massively parallel Huffman decoding on GPUs", 2018.)
 // One CTA per interval, its lanes striding over the interval's subsequences.  Round 0: every subsequence from its own first bit.
 // Rounds 1..: a subsequence whose predecessor's exit state is not the state it was last decoded from is decoded again.  A round
-// without a changed exit state ends the loop (at the latest after as many rounds as there are subsequences: a perfectly periodic
+// with no such subsequence ends the loop (at the latest after as many rounds as there are subsequences: a perfectly periodic
 // stream -- a blank image -- never re-synchronises by itself and is walked front to back).  Then thread 0 adds up the block counts
 // and DC sums, and every lane decodes its subsequences once more, writing coefficients.
 #ifdef JP_PROFILE
@@ -385,15 +385,15 @@ __device__ unsigned int g_jp_rounds[3];           // debug builds: intervals, su
 // otherwise occupy one SM each); the rounds are separated by cluster barriers and the "anything changed" flags are read through
 // distributed shared memory.
 template <int CL>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 2)
 k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict__ tables, const int32_t* __restrict__ file_tables,
             const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ nwords_in, unsigned long long* exit_state,
-            unsigned long long* used_state, int32_t* sub_counts /* [nsubs][4]: blocks, DC sums of the components */, int16_t* __restrict__ coefs,
-            const JpGeom g, uint32_t sub_bits)
+            unsigned long long* used_state, int32_t* sub_counts /* [nsubs][4]: blocks, DC sums of the components */, uint32_t* work_list,
+            int16_t* __restrict__ coefs, const JpGeom g, uint32_t sub_bits)
 {
     namespace cg = cooperative_groups;
     __shared__ uint8_t s_natural[64];
-    __shared__ int s_changed;
+    __shared__ int s_count;                       // subsequences this CTA decodes again in the current round
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_natural[i] = c_natural_order[i];      // (a CTA can be a single warp)
     const unsigned ivx = blockIdx.x / CL, rank = CL > 1 ? cg::this_cluster().block_rank() : 0u;
     auto barrier = [&]() { if (CL > 1) cg::this_cluster().sync(); else __syncthreads(); };
@@ -405,37 +405,54 @@ k_jpeg_sync(const JpInterval* __restrict__ intervals, const JpTables* __restrict
     unsigned long long* used = used_state + iv.first_sub;
     int4* cnt = reinterpret_cast<int4*>(sub_counts) + iv.first_sub;
     const uint32_t lane0 = rank * blockDim.x + threadIdx.x, stride = CL * blockDim.x;
-    for (int round = 0;; round++) {
-        if (threadIdx.x == 0) s_changed = 0;
-        barrier();
-        bool mine = false;
-        for (uint32_t j = lane0; j < iv.nsub; j += stride) {
-            unsigned long long start;
-            if (round == 0) start = jp_state(j * sub_bits, 0, 0);
-            else {
-                if (j == 0) continue;              // started from the truth in round 0
-                start = ex[j - 1];
-                if (start == used[j]) continue;
-            }
-            JpBits b = {words, nwords, 0, 0ull, 0};
-            int nblk = 0, d0 = 0, d1 = 0, d2 = 0;
-            const unsigned long long e = jp_run<false>(b, tb, g, nullptr, start, min((j + 1) * sub_bits, total), nblk, d0, d1, d2, nullptr, 0, 0);
-            used[j] = start;
-            cnt[j] = make_int4(nblk, d0, d1, d2);
-            if (round == 0 || e != ex[j]) { ex[j] = e; mine = true; }
+    // this CTA's list of subsequences to decode again: it owns at most ceil(nsub / stride) * blockDim of them (the lists of an
+    // interval take nsub + stride entries in all)
+    uint32_t* list = work_list + iv.first_sub + (size_t)ivx * stride + (size_t)rank * ((iv.nsub + stride - 1) / stride) * blockDim.x;
+    // round 0: every subsequence from its own first bit (subsequence 0: from the truth)
+    for (uint32_t j = lane0; j < iv.nsub; j += stride) {
+        const unsigned long long start = jp_state(j * sub_bits, 0, 0);
+        JpBits b = {words, nwords, 0, 0ull, 0};
+        int nblk = 0, d0 = 0, d1 = 0, d2 = 0;
+        const unsigned long long e = jp_run<false>(b, tb, g, nullptr, start, min((j + 1) * sub_bits, total), nblk, d0, d1, d2, nullptr, 0, 0);
+        used[j] = start;
+        cnt[j] = make_int4(nblk, d0, d1, d2);
+        ex[j] = e;
+    }
+    barrier();
+    // rounds 1..: the subsequences whose predecessor's exit state is not the state they were last decoded from are collected into a
+    // dense list first, so that a round costs what it has to decode, not a pass of every warp over mostly settled subsequences
+    for (int round = 1;; round++) {
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        if (round > 1) {                          // (round 1 decodes nearly every subsequence again: no list)
+            for (uint32_t j = lane0; j < iv.nsub; j += stride)
+                if (j && ex[j - 1] != used[j]) list[atomicAdd(&s_count, 1)] = j;
         }
-        if (mine && round) s_changed = 1;
         barrier();
-        int any = s_changed;
-        if (CL > 1)
-            for (unsigned r = 0; r < (unsigned)CL; r++) any |= *cg::this_cluster().map_shared_rank(&s_changed, r);
-        if (round && !any) {
+        const int n = round > 1 ? s_count : (int)((iv.nsub - min(iv.nsub, lane0 - threadIdx.x) + stride - 1) / stride) * (int)blockDim.x;
+        int any = round > 1 ? n : 1;
+        if (CL > 1 && round > 1)
+            for (unsigned r = 0; r < (unsigned)CL; r++) any |= *cg::this_cluster().map_shared_rank(&s_count, r);
+        if (!any) {                               // nothing left to decode again anywhere: the fixed point
 #ifdef JP_PROFILE
             if (threadIdx.x == 0 && rank == 0) { atomicAdd(&g_jp_rounds[0], 1u); atomicAdd(&g_jp_rounds[1], (unsigned)round); atomicMax(&g_jp_rounds[2], (unsigned)round); }
 #endif
             break;
         }
-        barrier();
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            // round 1: the CTA's own subsequences in order, t-th of them = rank * blockDim + t + (t / blockDim) * (stride - blockDim)
+            const uint32_t j = round > 1 ? list[t] : lane0 + (uint32_t)(t / (int)blockDim.x) * stride;
+            if (j == 0 || j >= iv.nsub) continue;
+            const unsigned long long start = ex[j - 1];
+            if (start == used[j]) continue;
+            JpBits b = {words, nwords, 0, 0ull, 0};
+            int nblk = 0, d0 = 0, d1 = 0, d2 = 0;
+            const unsigned long long e = jp_run<false>(b, tb, g, nullptr, start, min((j + 1) * sub_bits, total), nblk, d0, d1, d2, nullptr, 0, 0);
+            used[j] = start;
+            cnt[j] = make_int4(nblk, d0, d1, d2);
+            if (e != ex[j]) ex[j] = e;
+        }
+        barrier();                                // (also: every CTA of the cluster has read the counts before they are reset)
     }
     // first block and DC predictors of every subsequence: an exclusive prefix sum, in place (L2 loads: other CTAs of the cluster
     // wrote some of the counts, and will read the sums)
@@ -1134,8 +1151,14 @@ static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const si
     }
     // short intervals (a restart marker every few blocks) are decoded one lane each, sequentially: nothing to synchronise
     const bool sync_path = (size_t)longest * 8 > 4 * JP_SUB_BITS && packable;
+    // a few very long intervals (a small batch of files without restart markers): a cluster of CTAs per interval, so that the
+    // batch covers the SMs
+    int cl = 1;
+    while (cl < 8 && ni * (size_t)(cl * 2) <= 2 * (size_t)h->sm_count && max_nsub >= 1024u * (unsigned)(cl * 2)) cl *= 2;
+    const unsigned sync_threads = std::min(1024u, ((max_nsub + (unsigned)cl - 1) / (unsigned)cl + 31u) / 32u * 32u);
+    const size_t list_entries = nsubs + ni * (size_t)cl * sync_threads;      // the CTAs' work lists (k_jpeg_sync)
     if (sync_path) {
-        rc = jp_grow(&h->d_subw, &h->d_subw_bytes, nsubs * 4 * sizeof(unsigned long long));
+        rc = jp_grow(&h->d_subw, &h->d_subw_bytes, nsubs * 4 * sizeof(unsigned long long) + list_entries * sizeof(uint32_t));
         if (rc) return rc;
     }
     if ((int)sets.size() > S.tables_cap) {
@@ -1181,15 +1204,12 @@ static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const si
         k_jpeg_huff<<<seq_blocks, JP_HUFF_THREADS, 0, h->stream>>>(S.d_intervals, (int)ni, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords,
                                                                   h->d_coefs, g, lane_step);
     } else {
-        unsigned long long* st = h->d_subw;       // [nsubs] exit states, [nsubs] states decoded from, [nsubs][4] counts
-        // a few very long intervals (a small batch of files without restart markers): a cluster of CTAs per interval, so that the
-        // batch covers the SMs
-        int cl = 1;
-        while (cl < 8 && ni * (size_t)(cl * 2) <= 2 * (size_t)h->sm_count && max_nsub >= 1024u * (unsigned)(cl * 2)) cl *= 2;
-        const unsigned threads = std::min(1024u, ((max_nsub + (unsigned)cl - 1) / (unsigned)cl + 31u) / 32u * 32u);
+        unsigned long long* st = h->d_subw;       // [nsubs] exit states, [nsubs] states decoded from, [nsubs][4] counts, the work lists
+        uint32_t* wl = reinterpret_cast<uint32_t*>(st + 4 * nsubs);
+        const unsigned threads = sync_threads;
         if (cl == 1) {
             k_jpeg_sync<1><<<(unsigned)ni, threads, 0, h->stream>>>(S.d_intervals, S.d_tables, S.d_file_tables, h->d_scratch, h->d_nwords, st, st + nsubs,
-                                                                   (int32_t*)(st + 2 * nsubs), h->d_coefs, g, sub_bits);
+                                                                   (int32_t*)(st + 2 * nsubs), wl, h->d_coefs, g, sub_bits);
         } else {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)ni * (unsigned)cl); cfg.blockDim = dim3(threads); cfg.stream = h->stream;
@@ -1201,9 +1221,9 @@ static int decode_batch_dev(jpgx_handle h, const uint8_t* const* files, const si
             const uint8_t* a3 = h->d_scratch; const uint32_t* a4 = h->d_nwords;
             unsigned long long* a5 = st; unsigned long long* a6 = st + nsubs; int32_t* a7 = (int32_t*)(st + 2 * nsubs);
             int16_t* a8 = h->d_coefs;
-            if (cl == 2) ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<2>, a0, a1, a2, a3, a4, a5, a6, a7, a8, g, sub_bits));
-            else if (cl == 4) ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<4>, a0, a1, a2, a3, a4, a5, a6, a7, a8, g, sub_bits));
-            else ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<8>, a0, a1, a2, a3, a4, a5, a6, a7, a8, g, sub_bits));
+            if (cl == 2) ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<2>, a0, a1, a2, a3, a4, a5, a6, a7, wl, a8, g, sub_bits));
+            else if (cl == 4) ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<4>, a0, a1, a2, a3, a4, a5, a6, a7, wl, a8, g, sub_bits));
+            else ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_jpeg_sync<8>, a0, a1, a2, a3, a4, a5, a6, a7, wl, a8, g, sub_bits));
         }
     }
     ORBX_CUDA(cudaGetLastError());

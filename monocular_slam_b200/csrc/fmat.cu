@@ -64,6 +64,8 @@ struct FmPairTimer {
 #define FM_TICK(k) do { } while (0)
 #endif
 
+constexpr int FM_EIGHT_WS = 88;          // doubles per pair between k_fm_ransac and k_fm_eight_point: A[81], c1x c1y s1 c2x c2y s2, valid
+
 struct FmShared {
     double models[FM_MAXCHUNK][27];
     double best[9];
@@ -456,7 +458,8 @@ __device__ void block_sum(FmShared& sh, const double* v)
 // Jacobi on the symmetric 9x9 sh.A by warp 0; eigenvectors = rows of sh.V.  Round-robin ordering: each of the 9 rounds of a
 // sweep applies 4 rotations on disjoint index pairs at once -- lanes 0..3 compute the angles, then 36 lanes update the
 // 4 x 9 column pairs, then the row pairs (and V).
-__device__ void jacobi9_warp(FmShared& sh, int lane)
+template <class Shared>
+__device__ void jacobi9_warp(Shared& sh, int lane)
 {
     for (int i = lane; i < 81; i += 32) sh.V[i] = (i / 9 == i % 9) ? 1. : 0.;
     __syncwarp();
@@ -545,6 +548,36 @@ __device__ void smallest_eigvec3(double* G, double* vs)
     for (int k = 0; k < 3; k++) vs[k] = V[m * 3 + k];
 }
 
+// after jacobi9_warp: the eigenvector of the smallest eigenvalue as F, rank 2 enforced, normalisation undone (lane 0)
+template <class Shared>
+__device__ void eight_point_finish(Shared& sh, double c1x, double c1y, double s1, double c2x, double c2y, double s2, double* Fo, int32_t* inf)
+{
+    int small = 0, m = 0;
+    for (int i = 0; i < 9; i++) {
+        if (fabs(sh.A[i * 10]) < DBL_EPSILON) small++;
+        if (sh.A[i * 10] < sh.A[m * 10]) m = i;
+    }
+    if (small < 2) {                                   // run8Point: the 8 largest eigenvalues must be non-zero
+        double F0[9], G[9], vs[3];
+        for (int i = 0; i < 9; i++) F0[i] = sh.V[m * 9 + i];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) {
+                double s = 0;
+                for (int c = 0; c < 3; c++) s += F0[c * 3 + a] * F0[c * 3 + b];
+                G[a * 3 + b] = s;
+            }
+        smallest_eigvec3(G, vs);
+        // rank 2: F0 - (F0 v) v' == U diag(w0, w1, 0) V'
+        for (int a = 0; a < 3; a++) {
+            const double fv = F0[a * 3] * vs[0] + F0[a * 3 + 1] * vs[1] + F0[a * 3 + 2] * vs[2];
+            for (int b = 0; b < 3; b++) F0[a * 3 + b] -= fv * vs[b];
+        }
+        denormalise(F0, c1x, c1y, s1, c2x, c2y, s2);
+        for (int i = 0; i < 9; i++) Fo[i] = F0[i];
+        inf[3] = 1;
+    }
+}
+
 // One CTA per pair.  pts1/pts2: npairs x cap correspondences (float x, y); counts[pair] of them valid.
 // status: npairs x cap bytes (0/1); F: npairs x 9 doubles (zeros: no result); info: npairs x 4 ints
 // {inliers, iterations run, candidates scored, 0}.
@@ -554,7 +587,8 @@ __device__ void smallest_eigvec3(double* G, double* vs)
 template <bool SMEM_POINTS, int FM_THREADS>
 __global__ void __launch_bounds__(FM_THREADS, FM_CTAS_PER_SM)
 k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, const int32_t* __restrict__ counts, int cap,
-            double thr, double conf, int max_iters, uint8_t* __restrict__ status, double* __restrict__ Fout, int32_t* __restrict__ info)
+            double thr, double conf, int max_iters, uint8_t* __restrict__ status, double* __restrict__ Fout, int32_t* __restrict__ info,
+            double* __restrict__ eight_ws /* null: the 8-point step ends here; else [npairs][FM_EIGHT_WS] for k_fm_eight_point */)
 {
     extern __shared__ __align__(16) unsigned char fm_smem[];
     FmShared& sh = *reinterpret_cast<FmShared*>(fm_smem);
@@ -572,6 +606,7 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     for (int i = tid; i < cap; i += FM_THREADS) st[i] = 0;
     if (tid < 9) Fo[tid] = 0.;
     if (tid < 4) inf[tid] = 0;
+    if (eight_ws && tid == 0) eight_ws[(size_t)pair * FM_EIGHT_WS + 87] = 0.;        // no system for the second kernel (yet)
     // OpenCV: fewer than 7 points -> empty result; exactly 7 -> the bare 7-point solver (up to three stacked matrices the
     // reference cannot use): both report "no model" here.  8..14 points -> least median of squares instead of RANSAC
     // (findFundamentalMat: `npoints >= 15` selects RANSAC): same sampler, a fixed iteration count, the candidate with the
@@ -957,36 +992,42 @@ k_fm_ransac(const float2* __restrict__ pts1, const float2* __restrict__ pts2, co
     }
     __syncthreads();
     FM_TICK(5);
+    if (eight_ws) {
+        // large batches: the eigen-decomposition is one warp's work; left to k_fm_eight_point (a warp per pair, every pair of the
+        // batch at once) it does not hold this CTA's slot while other pairs wait for one
+        double* ws = eight_ws + (size_t)pair * FM_EIGHT_WS;
+        if (tid < 81) ws[tid] = sh.A[tid];
+        if (tid == 0) { ws[81] = c1x; ws[82] = c1y; ws[83] = s1; ws[84] = c2x; ws[85] = c2y; ws[86] = s2; ws[87] = 1.; }
+        return;
+    }
     if (warp == 0) {
         jacobi9_warp(sh, lane);
         FM_TICK(6);
-        if (lane == 0) {
-            int small = 0, m = 0;
-            for (int i = 0; i < 9; i++) {
-                if (fabs(sh.A[i * 10]) < DBL_EPSILON) small++;
-                if (sh.A[i * 10] < sh.A[m * 10]) m = i;
-            }
-            if (small < 2) {                                   // run8Point: the 8 largest eigenvalues must be non-zero
-                double F0[9], G[9], vs[3];
-                for (int i = 0; i < 9; i++) F0[i] = sh.V[m * 9 + i];
-                for (int a = 0; a < 3; a++)
-                    for (int b = 0; b < 3; b++) {
-                        double s = 0;
-                        for (int c = 0; c < 3; c++) s += F0[c * 3 + a] * F0[c * 3 + b];
-                        G[a * 3 + b] = s;
-                    }
-                smallest_eigvec3(G, vs);
-                // rank 2: F0 - (F0 v) v' == U diag(w0, w1, 0) V'
-                for (int a = 0; a < 3; a++) {
-                    const double fv = F0[a * 3] * vs[0] + F0[a * 3 + 1] * vs[1] + F0[a * 3 + 2] * vs[2];
-                    for (int b = 0; b < 3; b++) F0[a * 3 + b] -= fv * vs[b];
-                }
-                denormalise(F0, c1x, c1y, s1, c2x, c2y, s2);
-                for (int i = 0; i < 9; i++) Fo[i] = F0[i];
-                inf[3] = 1;
-            }
-        }
+        if (lane == 0) eight_point_finish(sh, c1x, c1y, s1, c2x, c2y, s2, Fo, inf);
     }
+}
+
+// The end of the 8-point step for the pairs whose normal equations k_fm_ransac left in the workspace: one warp per pair.
+struct FmEightShared {
+    double A[81], V[81];
+    double rot_cs[4], rot_sn[4];
+    int rot_p[4], rot_q[4];
+};
+constexpr int FM_EIGHT_WARPS = 2;
+__global__ void __launch_bounds__(FM_EIGHT_WARPS * 32)
+k_fm_eight_point(const double* __restrict__ eight_ws, int npairs, double* __restrict__ Fout, int32_t* __restrict__ info)
+{
+    __shared__ FmEightShared s_sh[FM_EIGHT_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = blockIdx.x * FM_EIGHT_WARPS + warp;
+    if (pair >= npairs) return;
+    const double* ws = eight_ws + (size_t)pair * FM_EIGHT_WS;
+    if (ws[87] == 0.) return;
+    FmEightShared& sh = s_sh[warp];
+    for (int i = lane; i < 81; i += 32) sh.A[i] = ws[i];
+    __syncwarp();
+    jacobi9_warp(sh, lane);
+    if (lane == 0) eight_point_finish(sh, ws[81], ws[82], ws[83], ws[84], ws[85], ws[86], Fout + (size_t)pair * 9, info + (size_t)pair * 4);
 }
 
 // Correspondences from the device-resident keypoints and match lists of the sequence mode.  Pair p = f*back + (j-1) is
@@ -1025,6 +1066,7 @@ struct fmx_context {
     uint8_t* d_status; size_t status_bytes;
     double* d_F; size_t F_bytes;
     int32_t* d_info; size_t info_bytes;
+    double* d_eight; size_t eight_bytes;     // normal equations of the pairs of a large batch (k_fm_eight_point)
     int32_t* h_info; size_t h_info_n;
     float* h_pts; size_t h_pts_n;            // pinned staging of fmx_compute_fundamental (grow-only)
     size_t smem_optin;
@@ -1070,7 +1112,7 @@ extern "C" int fmx_destroy(fmx_handle h)
     if (!h) return ORBX_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_counts); cudaFree(h->d_status); cudaFree(h->d_F); cudaFree(h->d_info);
+    cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_counts); cudaFree(h->d_status); cudaFree(h->d_F); cudaFree(h->d_info); cudaFree(h->d_eight);
     if (h->h_info) cudaFreeHost(h->h_info);
     if (h->h_pts) cudaFreeHost(h->h_pts);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1112,11 +1154,23 @@ static int fm_launch(fmx_handle h, const float* d_pts1, const float* d_pts2, con
     // 256-thread CTAs (8 warps score one pair's candidates), two per SM.  Measured against 128 x 4, 192 x 3 and 256 x 3 (80
     // registers) at 64 / 296 / 320 / 640 pairs: the batch ends with its slowest pairs, and those finish sooner with more warps
     // and all 128 registers each (profiles/README.md).
-#define FM_LAUNCH(SM) k_fm_ransac<SM, 256><<<npairs, 256, smem, h->stream>>>(p1, p2, d_counts, cap, max_distance, confidence, 1000, d_status, d_F, d_info)
+    // batches of more pairs than CTA slots (2 per SM): the last step of every pair, one warp's eigen-decomposition, runs in a
+    // second kernel for all pairs at once instead of holding a slot
+    double* ws = nullptr;
+    if (npairs > 2 * h->sm_count) {
+        const int rc = fm_grow(&h->d_eight, &h->eight_bytes, (size_t)npairs * FM_EIGHT_WS * sizeof(double));
+        if (rc) return rc;
+        ws = h->d_eight;
+    }
+#define FM_LAUNCH(SM) k_fm_ransac<SM, 256><<<npairs, 256, smem, h->stream>>>(p1, p2, d_counts, cap, max_distance, confidence, 1000, d_status, d_F, d_info, ws)
     if (in_smem) FM_LAUNCH(true);
     else FM_LAUNCH(false);
 #undef FM_LAUNCH
     ORBX_CUDA(cudaGetLastError());
+    if (ws) {
+        k_fm_eight_point<<<(npairs + FM_EIGHT_WARPS - 1) / FM_EIGHT_WARPS, FM_EIGHT_WARPS * 32, 0, h->stream>>>(ws, npairs, d_F, d_info);
+        ORBX_CUDA(cudaGetLastError());
+    }
     return ORBX_OK;
 }
 

@@ -136,9 +136,16 @@ def test_full_size_batch_properties(fm):
     s3, F3, n3 = fm.find_batch(p1[perm], p2[perm], counts[perm])
     assert np.array_equal(s3, s1[perm]) and np.array_equal(F3, F1[perm]) and np.array_equal(n3, n1[perm])
     assert np.array_equal(s1.sum(1), n1) and (n1 >= 0.5 * 0.55 * counts).all()
+    # a batch of more pairs than CTA slots leaves the eigen-decomposition of the 8-point step to a second kernel (k_fm_eight_point);
+    # in two halves the same pairs run through the single kernel: bit-identical matrices, masks and counts
+    half = npairs // 2
+    for lo, hi in ((0, half), (half, npairs)):
+        s4, F4, n4 = fm.find_batch(p1[lo:hi], p2[lo:hi], counts[lo:hi])
+        assert np.array_equal(s4, s1[lo:hi]) and np.array_equal(F4, F1[lo:hi]) and np.array_equal(n4, n1[lo:hi])
+    assert (np.abs(F1.reshape(npairs, -1)).sum(1) > 0).all()
     for i in range(0, npairs, 23):
         n = int(counts[i])
-        _, mo, _ = oracle.fm_ransac(p1[i, :n], p2[i, :n], 3.0, 0.85)
+        Fo, mo, _ = oracle.fm_ransac(p1[i, :n], p2[i, :n], 3.0, 0.85)
         assert np.array_equal(s1[i, :n], mo)
 
 

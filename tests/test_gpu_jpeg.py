@@ -142,10 +142,11 @@ def test_colour_frames_with_16_byte_aligned_rows(sampling, w, h):
     dec.close()
 
 
-@pytest.mark.parametrize("n,w,h,rst", [(1, 1920, 1080, 0), (5, 800, 600, 0), (3, 1600, 900, 5000), (2, 3840, 2160, 0)])
+@pytest.mark.parametrize("n,w,h,rst", [(1, 1920, 1080, 0), (5, 800, 600, 0), (3, 1600, 900, 5000), (2, 3840, 2160, 0), (3, 3840, 2160, 480)])
 def test_long_intervals_are_unstuffed_by_several_ctas(n, w, h, rst):
     """Grey files whose restart intervals are far longer than 16 KB (none, or a marker every few thousand blocks -- intervals that
-    start at any byte offset): the chunked unstuffing.  Noise frames: an FF byte every ~200 bytes of the scan."""
+    start at any byte offset): the chunked unstuffing.  Noise frames: an FF byte every ~200 bytes of the scan.  The last case -- 4K
+    frames with a marker per block row, 810 intervals of up to ~27 KB -- has too many intervals for it and takes the CTA-per-interval form."""
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(n * 7 + w)
     frames = [rng.integers(0, 256, (h, w), dtype=np.uint8) if i % 2 == 0 else syn.frame(80 + i, w, h) for i in range(n)]

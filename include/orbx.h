@@ -306,7 +306,9 @@ ORBX_API int fmx_fundamental_batch(fmx_handle h, const float* pts1, const float*
                           double max_distance, double confidence, uint8_t* status, double* F, int32_t* ninliers);
 /* Per pair {inliers, RANSAC iterations run, candidate matrices scored, 1 if F was produced} of the last fmx_fundamental_batch. */
 ORBX_API int fmx_last_info(fmx_handle h, int npairs, int32_t* info /* npairs * 4 */);
-/* Device-resident form (asynchronous on the handle's stream); d_info is [npairs][4] as fmx_last_info returns it. */
+/* Device-resident form (asynchronous on the handle's stream); d_info is [npairs][4] as fmx_last_info returns it.  Batches of more
+ * pairs than the device has CTA slots for (2 per SM) keep 704 bytes per pair in a grow-only workspace of the handle: the first such
+ * call, and any later one with more pairs, allocates (a device-wide synchronisation), the others do not. */
 ORBX_API int fmx_fundamental_batch_dev(fmx_handle h, const float* d_pts1, const float* d_pts2, const int32_t* d_counts, int npairs, int cap,
                               double max_distance, double confidence, uint8_t* d_status, double* d_F, int32_t* d_info);
 /* Sequence mode on the device: pair f = (frame f, frame f-1) of a batch whose keypoints [nframes][cap] and consecutive-frame

@@ -7,7 +7,7 @@
 //             three (YCbCr 4:2:0 / 4:2:2 / 4:4:4, one interleaved scan); the
 //             entropy-coded segment is cut at its restart markers into intervals (T.81 E.2.4) -- the unit of parallelism
 //   K17 k_jpeg_unstuff, k_jpeg_sync / k_jpeg_huff   a warp per restart interval strips the stuffed zero bytes (FF 00 -> FF) into
-//             a scratch copy; the Huffman decoder of T.81 F.2.2 (10-bit lookahead tables, the DC predictor restarting with the
+//             a scratch copy (whole files without restart markers: a CTA per 8 KB chunk); the Huffman decoder of T.81 F.2.2 (10-bit lookahead tables, the DC predictor restarting with the
 //             interval, one symbol per loop iteration so that lanes on different data stay in step) then runs either one lane
 //             per interval (short intervals) or, for block rows and whole files, one lane per subsequence of <= 1024 bits,
 //             iterated until every subsequence was decoded from its predecessor's true exit state; the non-zero coefficients
